@@ -1,0 +1,674 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Never linked into the product;
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load it.
+//
+// CPU restatement of the reference's *CPU* branch of RHSoperator::Mult
+// (src/rhs_operator.cpp:343-464) for 3-D hexahedral DG meshes, using the same DENSE
+// per-element operators the reference builds (Me_inv, Ke, the (F,grad w) element blocks of
+// Aflux) and the same per-face / per-quadrature-point loops -- deliberately NOT
+// sum-factorised, so it is independent of the CUDA kernels it checks.
+//
+// MFEM (third party, >=4.4, absent from /root/reference) supplies the mesh/FE conventions
+// the reference relies on; they are restated here from MFEM's documented behaviour
+//  and are "parity unpinned" until an MFEM build exists:
+//   hex vertex / face-vertex / quad-orientation tables, FaceElementTransformations Loc1/Loc2,
+//   CalcOrtho, IntegrationRules, L2 tensor basis ordering, RK4Solver tableau.
+// Per-point physics goes through orc::Physics (port or the reference's own object code).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "orc_basis.hpp"
+#include "orc_physics.hpp"
+
+namespace orc {
+
+// ---- MFEM geometry constants [MFEM fem/geom.cpp: Geometry::Constants<CUBE/SQUARE>] ----
+static const double HEX_VERT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
+                                      {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+static const int HEX_FACE_VERT[6][4] = {{3, 2, 1, 0}, {0, 1, 5, 4}, {1, 2, 6, 5},
+                                        {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+static const int QUAD_ORIENT[8][4] = {{0, 1, 2, 3}, {0, 3, 2, 1}, {1, 2, 3, 0}, {1, 0, 3, 2},
+                                      {2, 3, 0, 1}, {2, 1, 0, 3}, {3, 0, 1, 2}, {3, 2, 1, 0}};
+
+static inline void cross3(const double *a, const double *b, double *c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Dense in-place inverse, Gauss-Jordan with partial pivoting (stands in for
+// DenseMatrix::Invert, src/rhs_operator.cpp:187). Row-major n x n.
+static void invert_dense(std::vector<double> &a, int n) {
+  std::vector<double> inv(static_cast<size_t>(n) * n, 0.0);
+  for (int i = 0; i < n; i++) inv[i * n + i] = 1.0;
+  for (int c = 0; c < n; c++) {
+    int piv = c;
+    double best = fabs(a[c * n + c]);
+    for (int r = c + 1; r < n; r++)
+      if (fabs(a[r * n + c]) > best) {
+        best = fabs(a[r * n + c]);
+        piv = r;
+      }
+    if (piv != c) {
+      for (int k = 0; k < n; k++) {
+        std::swap(a[c * n + k], a[piv * n + k]);
+        std::swap(inv[c * n + k], inv[piv * n + k]);
+      }
+    }
+    double d = 1.0 / a[c * n + c];
+    for (int k = 0; k < n; k++) {
+      a[c * n + k] *= d;
+      inv[c * n + k] *= d;
+    }
+    for (int r = 0; r < n; r++) {
+      if (r == c) continue;
+      double f = a[r * n + c];
+      if (f == 0.0) continue;
+      for (int k = 0; k < n; k++) {
+        a[r * n + k] -= f * a[c * n + k];
+        inv[r * n + k] -= f * inv[c * n + k];
+      }
+    }
+  }
+  a.swap(inv);
+}
+
+// smallest singular value of a 3x3 matrix (Mesh::GetElementSize(e, 1) -> J.CalcSingularvalue(dim-1))
+static double min_singular_3x3(const double *J) {
+  double A[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += J[k + 3 * i] * J[k + 3 * j];
+      A[i][j] = s;
+    }
+  // cyclic Jacobi on symmetric A
+  for (int sweep = 0; sweep < 50; sweep++) {
+    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; k++) {
+          double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {
+          double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+      }
+  }
+  double m = std::min(A[0][0], std::min(A[1][1], A[2][2]));
+  return sqrt(std::max(m, 0.0));
+}
+
+struct Oracle {
+  int dim = 3, p = 0, np = 0, dof = 0, NE = 0, NF = 0, neq = 5, nvel = 3, nthreads = 1;
+  long N = 0;  // vfes->GetNDofs()
+  OrcPhysParams phys;
+  Physics *ph = nullptr;
+  std::vector<double> vx;  // [NE][8][3]
+  std::vector<int> f_el1, f_el2, f_inf1, f_inf2;
+  std::vector<std::vector<int>> el_faces;  // interior faces per element, ascending (element_to_faces)
+  std::vector<double> nodes1d;
+  int nqv1 = 0, nqf1 = 0, nqv = 0, nqf = 0;
+  std::vector<double> qxv, qwv, qxf, qwf;
+  std::vector<double> Me_inv, Ke, Kfl;  // per element dense
+  std::vector<double> elSize;           // per element delta = h_min / order
+  std::vector<double> nodeXYZ;          // [NE][dof][3]
+  std::map<int, std::vector<double>> shapeTab;  // inf code -> [nqf][dof]
+  // work
+  std::vector<double> Up, gradUp;
+  double max_char_speed = 0;
+
+  // ---- element geometry: trilinear map from the 8 vertices (mesh nodes of order 1) ----
+  void elem_map(int e, const double *xi, double *x, double *J) const {
+    const double *v = &vx[static_cast<size_t>(e) * 24];
+    double N[8], dN[8][3];
+    for (int a = 0; a < 8; a++) {
+      double fx = HEX_VERT[a][0] ? xi[0] : 1 - xi[0], gx = HEX_VERT[a][0] ? 1 : -1;
+      double fy = HEX_VERT[a][1] ? xi[1] : 1 - xi[1], gy = HEX_VERT[a][1] ? 1 : -1;
+      double fz = HEX_VERT[a][2] ? xi[2] : 1 - xi[2], gz = HEX_VERT[a][2] ? 1 : -1;
+      N[a] = fx * fy * fz;
+      dN[a][0] = gx * fy * fz;
+      dN[a][1] = fx * gy * fz;
+      dN[a][2] = fx * fy * gz;
+    }
+    if (x)
+      for (int i = 0; i < 3; i++) {
+        double s = 0;
+        for (int a = 0; a < 8; a++) s += N[a] * v[a * 3 + i];
+        x[i] = s;
+      }
+    if (J)  // column-major J(i,j) = dx_i/dxi_j at J[i + 3*j]
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+          double s = 0;
+          for (int a = 0; a < 8; a++) s += dN[a][j] * v[a * 3 + i];
+          J[i + 3 * j] = s;
+        }
+  }
+  static double det3(const double *J) {
+    return J[0] * (J[4] * J[8] - J[5] * J[7]) - J[3] * (J[1] * J[8] - J[2] * J[7]) + J[6] * (J[1] * J[5] - J[2] * J[4]);
+  }
+  // adjugate, column-major: adj(J) = det(J) * inv(J)
+  static void adj3(const double *J, double *A) {
+    A[0 + 3 * 0] = J[4] * J[8] - J[7] * J[5];
+    A[0 + 3 * 1] = J[6] * J[5] - J[3] * J[8];
+    A[0 + 3 * 2] = J[3] * J[7] - J[6] * J[4];
+    A[1 + 3 * 0] = J[7] * J[2] - J[1] * J[8];
+    A[1 + 3 * 1] = J[0] * J[8] - J[6] * J[2];
+    A[1 + 3 * 2] = J[6] * J[1] - J[0] * J[7];
+    A[2 + 3 * 0] = J[1] * J[5] - J[4] * J[2];
+    A[2 + 3 * 1] = J[3] * J[2] - J[0] * J[5];
+    A[2 + 3 * 2] = J[0] * J[4] - J[3] * J[1];
+  }
+  // L2 tensor basis, lexicographic x fastest
+  void calc_shape(const double *xi, double *shape, double *dshape /*[dof][3] row-major or NULL*/) const {
+    double vx_[16], vy_[16], vz_[16], dx_[16], dy_[16], dz_[16];
+    lagrange(nodes1d, xi[0], vx_, dx_);
+    lagrange(nodes1d, xi[1], vy_, dy_);
+    lagrange(nodes1d, xi[2], vz_, dz_);
+    for (int k = 0; k < np; k++)
+      for (int j = 0; j < np; j++)
+        for (int i = 0; i < np; i++) {
+          int n = i + np * (j + np * k);
+          shape[n] = vx_[i] * vy_[j] * vz_[k];
+          if (dshape) {
+            dshape[n * 3 + 0] = dx_[i] * vy_[j] * vz_[k];
+            dshape[n * 3 + 1] = vx_[i] * dy_[j] * vz_[k];
+            dshape[n * 3 + 2] = vx_[i] * vy_[j] * dz_[k];
+          }
+        }
+  }
+  // [MFEM Mesh::GetLocalQuadToHexTransformation]: face reference (s,t) -> element reference
+  // point for info code inf = 64*local_face + orientation; dloc = d(xi)/d(s,t) (3x2, col-major).
+  static void loc_map(int inf, double s, double t, double *xi, double *dloc) {
+    const int *hv = HEX_FACE_VERT[inf / 64];
+    const int *qo = QUAD_ORIENT[inf % 64];
+    const double Nq[4] = {(1 - s) * (1 - t), s * (1 - t), s * t, (1 - s) * t};
+    const double dNs[4] = {-(1 - t), (1 - t), t, -t};
+    const double dNt[4] = {-(1 - s), -s, s, (1 - s)};
+    for (int i = 0; i < 3; i++) {
+      double a = 0, b = 0, c = 0;
+      for (int j = 0; j < 4; j++) {
+        const double vj = HEX_VERT[hv[qo[j]]][i];
+        a += Nq[j] * vj;
+        b += dNs[j] * vj;
+        c += dNt[j] * vj;
+      }
+      xi[i] = a;
+      if (dloc) {
+        dloc[i + 3 * 0] = b;
+        dloc[i + 3 * 1] = c;
+      }
+    }
+  }
+  const std::vector<double> &shape_table(int inf) {
+    auto it = shapeTab.find(inf);
+    if (it != shapeTab.end()) return it->second;
+    std::vector<double> tab(static_cast<size_t>(nqf) * dof);
+    for (int q = 0; q < nqf; q++) {
+      double s = qxf[q % nqf1], t = qxf[q / nqf1], xi[3];
+      loc_map(inf, s, t, xi, nullptr);
+      calc_shape(xi, &tab[static_cast<size_t>(q) * dof], nullptr);
+    }
+    return shapeTab.emplace(inf, std::move(tab)).first->second;
+  }
+  // face geometry at quadrature point q of face f: CalcOrtho(Tr.Jacobian()) and Tr.Transform
+  void face_geom(int f, int q, double *nor, double *xyz) const {
+    double s = qxf[q % nqf1], t = qxf[q / nqf1], xi[3], dloc[6], J[9], Jf[6];
+    loc_map(f_inf1[f], s, t, xi, dloc);
+    elem_map(f_el1[f], xi, xyz, J);
+    for (int i = 0; i < 3; i++)
+      for (int c = 0; c < 2; c++) {
+        double a = 0;
+        for (int k = 0; k < 3; k++) a += J[i + 3 * k] * dloc[k + 3 * c];
+        Jf[i + 3 * c] = a;
+      }
+    cross3(&Jf[0], &Jf[3], nor);
+  }
+
+  void setup() {
+    np = p + 1;
+    dof = np * np * np;
+    N = static_cast<long>(NE) * dof;
+    std::vector<double> wtmp;
+    gauss_legendre01(np, nodes1d, wtmp);  // BasisType::GaussLegendre nodes
+    // volume rule: order 2p (src/rhs_operator.cpp:181, src/gradients.cpp:97, src/domain_integrator.cpp:69)
+    nqv1 = gl_npts_for_order(2 * p);
+    gauss_legendre01(nqv1, qxv, qwv);
+    nqv = nqv1 * nqv1 * nqv1;
+    // face rule: min(OrderW1,OrderW2) + 2p, OrderW(trilinear hex) = 1*3-1 = 2 (src/face_integrator.cpp:233-243)
+    nqf1 = gl_npts_for_order(2 + 2 * p);
+    gauss_legendre01(nqf1, qxf, qwf);
+    nqf = nqf1 * nqf1;
+
+    el_faces.assign(NE, {});
+    for (int f = 0; f < NF; f++) {
+      if (f_el2[f] < 0) continue;  // boundary faces are not in element_to_faces (src/M2ulPhyS.cpp:937-958)
+      el_faces[f_el1[f]].push_back(f);
+      if (f_el2[f] < NE) el_faces[f_el2[f]].push_back(f);
+      shape_table(f_inf1[f]);
+      shape_table(f_inf2[f]);
+    }
+
+    const size_t d2 = static_cast<size_t>(dof) * dof;
+    Me_inv.assign(NE * d2, 0.0);
+    Ke.assign(NE * d2 * 3, 0.0);
+    Kfl.assign(NE * d2 * 3, 0.0);
+    elSize.assign(NE, 0.0);
+    nodeXYZ.assign(static_cast<size_t>(N) * 3, 0.0);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int e = 0; e < NE; e++) {
+      std::vector<double> shape(dof), dshape(dof * 3), Me(d2, 0.0), phys(dof * 3), dsdx(dof * 3);
+      double *ke = &Ke[e * d2 * 3], *kf = &Kfl[e * d2 * 3];
+      for (int q = 0; q < nqv; q++) {
+        const int qi = q % nqv1, qj = (q / nqv1) % nqv1, qk = q / (nqv1 * nqv1);
+        const double xi[3] = {qxv[qi], qxv[qj], qxv[qk]};
+        const double w = qwv[qi] * qwv[qj] * qwv[qk];
+        double J[9], A[9];
+        elem_map(e, xi, nullptr, J);
+        const double det = det3(J);
+        adj3(J, A);
+        calc_shape(xi, shape.data(), dshape.data());
+        // MassIntegrator (src/rhs_operator.cpp:179-185)
+        for (int i = 0; i < dof; i++)
+          for (int j = 0; j < dof; j++) Me[i * dof + j] += w * det * shape[i] * shape[j];
+        // CalcPhysDShape = dshape * inv(J); dshapedx = dshape * adj(J)
+        for (int k = 0; k < dof; k++)
+          for (int d = 0; d < 3; d++) {
+            double a = 0;
+            for (int r = 0; r < 3; r++) a += dshape[k * 3 + r] * A[r + 3 * d];
+            dsdx[k * 3 + d] = a;
+            phys[k * 3 + d] = a / det;
+          }
+        // Ke(j, k + d*dof) += shape(j) * dshape(k,d) * detJac  (src/gradients.cpp:112-120)
+        const double detJac = det * w;
+        for (int d = 0; d < 3; d++)
+          for (int k = 0; k < dof; k++)
+            for (int j = 0; j < dof; j++) ke[j * (3 * dof) + k + d * dof] += shape[j] * phys[k * 3 + d] * detJac;
+        // elmat(j, k + d*dof) += (shape(k)*w) * dshapedx(j,d)  (src/domain_integrator.cpp:71-97)
+        for (int d = 0; d < 3; d++)
+          for (int j = 0; j < dof; j++)
+            for (int k = 0; k < dof; k++) kf[j * (3 * dof) + k + d * dof] += shape[k] * w * dsdx[j * 3 + d];
+      }
+      invert_dense(Me, dof);
+      std::copy(Me.begin(), Me.end(), &Me_inv[e * d2]);
+      // elSize: GetElementSize(e,1)/order (src/rhs_operator.cpp:149-156)
+      {
+        const double c[3] = {0.5, 0.5, 0.5};
+        double J[9];
+        elem_map(e, c, nullptr, J);
+        elSize[e] = min_singular_3x3(J) / p;
+      }
+      // node coordinates (mesh->GetNodes into a byNODES L2 space, src/rhs_operator.cpp:139-142)
+      for (int n = 0; n < dof; n++) {
+        const double xi[3] = {nodes1d[n % np], nodes1d[(n / np) % np], nodes1d[n / (np * np)]};
+        elem_map(e, xi, &nodeXYZ[(static_cast<size_t>(e) * dof + n) * 3], nullptr);
+      }
+    }
+    Up.assign(static_cast<size_t>(N) * neq, 0.0);
+    gradUp.assign(static_cast<size_t>(N) * neq * 3, 0.0);
+  }
+
+  // src/rhs_operator.cpp:641-649
+  void update_primitives(const double *x) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (long i = 0; i < N; i++) {
+      double s[16], pr[16];
+      for (int eq = 0; eq < neq; eq++) s[eq] = x[i + eq * N];
+      ph->prim(s, pr);
+      for (int eq = 0; eq < neq; eq++) Up[i + eq * N] = pr[eq];
+    }
+  }
+
+  // src/gradients.cpp:144-232 with GradFaceIntegrator (src/faceGradientIntegration.cpp:40-140)
+  void compute_gradients() {
+    const int nd = neq * 3;
+    // face contributions, one private buffer per face side, gathered in face order below
+    std::vector<double> fc(static_cast<size_t>(NF) * 2 * dof * nd, 0.0);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 16)
+    for (int f = 0; f < NF; f++) {
+      if (f_el2[f] < 0) continue;
+      const int e1 = f_el1[f], e2 = f_el2[f];
+      const std::vector<double> &sh1 = shapeTab.at(f_inf1[f]), &sh2 = shapeTab.at(f_inf2[f]);
+      double *v1 = &fc[(static_cast<size_t>(f) * 2 + 0) * dof * nd];
+      double *v2 = &fc[(static_cast<size_t>(f) * 2 + 1) * dof * nd];
+      double iUp1[16], iUp2[16], mean[16], du1n[48], du2n[48], nor[3], xyz[3];
+      for (int q = 0; q < nqf; q++) {
+        const double *s1 = &sh1[static_cast<size_t>(q) * dof], *s2 = &sh2[static_cast<size_t>(q) * dof];
+        for (int eq = 0; eq < neq; eq++) {
+          double a = 0, b = 0;
+          for (int k = 0; k < dof; k++) a += Up[static_cast<size_t>(e1) * dof + k + eq * N] * s1[k];
+          for (int k = 0; k < dof; k++) b += Up[static_cast<size_t>(e2) * dof + k + eq * N] * s2[k];
+          iUp1[eq] = a;
+          iUp2[eq] = b;
+          mean[eq] = 0.5 * a;
+          mean[eq] += 0.5 * b;
+        }
+        face_geom(f, q, nor, xyz);
+        const double w = qwf[q % nqf1] * qwf[q / nqf1];
+        for (int d = 0; d < 3; d++) nor[d] *= w;
+        for (int d = 0; d < 3; d++)
+          for (int eq = 0; eq < neq; eq++) {
+            du1n[eq + d * neq] = (mean[eq] - iUp1[eq]) * nor[d];
+            du2n[eq + d * neq] = (iUp2[eq] - mean[eq]) * nor[d];
+          }
+        for (int k = 0; k < dof; k++)
+          for (int c = 0; c < nd; c++) {
+            v1[k * nd + c] += s1[k] * du1n[c];
+            v2[k * nd + c] += s2[k] * du2n[c];
+          }
+      }
+    }
+    const size_t d2 = static_cast<size_t>(dof) * dof;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int e = 0; e < NE; e++) {
+      std::vector<double> rhs(static_cast<size_t>(dof) * nd, 0.0), fsum(static_cast<size_t>(dof) * nd, 0.0);
+      const double *ke = &Ke[e * d2 * 3];
+      // volume: elGradUp(j, eq + d*neq) = sum_k Ke(j, k + d*dof) * elUp(k, eq)  (src/gradients.cpp:174-182)
+      for (int eq = 0; eq < neq; eq++)
+        for (int d = 0; d < 3; d++)
+          for (int j = 0; j < dof; j++) {
+            double a = 0;
+            for (int k = 0; k < dof; k++) a += ke[j * (3 * dof) + k + d * dof] * Up[static_cast<size_t>(e) * dof + k + eq * N];
+            rhs[j * nd + eq + d * neq] = a;
+          }
+      for (int f : el_faces[e]) {
+        const int side = (f_el1[f] == e) ? 0 : 1;
+        const double *v = &fc[(static_cast<size_t>(f) * 2 + side) * dof * nd];
+        for (size_t i = 0; i < fsum.size(); i++) fsum[i] += v[i];
+      }
+      for (size_t i = 0; i < rhs.size(); i++) rhs[i] += fsum[i];
+      // Me_inv (src/gradients.cpp:209-227)
+      const double *mi = &Me_inv[e * d2];
+      for (int d = 0; d < 3; d++)
+        for (int eq = 0; eq < neq; eq++)
+          for (int j = 0; j < dof; j++) {
+            double a = 0;
+            for (int k = 0; k < dof; k++) a += mi[j * dof + k] * rhs[k * nd + eq + d * neq];
+            gradUp[static_cast<size_t>(e) * dof + j + eq * N + static_cast<size_t>(d) * neq * N] = a;
+          }
+    }
+  }
+
+  // RHSoperator::Mult, CPU branch (src/rhs_operator.cpp:343-464)
+  void mult(const double *x, double *y) {
+    max_char_speed = 0.;
+    update_primitives(x);
+    compute_gradients();
+    const int nact = ph->num_active_species();
+    // ---- A->Mult: FaceIntegrator::NonLinearFaceIntegration (src/face_integrator.cpp:194-352)
+    std::vector<double> fz(static_cast<size_t>(NF) * 2 * dof * neq, 0.0);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 16)
+    for (int f = 0; f < NF; f++) {
+      if (f_el2[f] < 0) continue;
+      const int e1 = f_el1[f], e2 = f_el2[f];
+      const std::vector<double> &sh1 = shapeTab.at(f_inf1[f]), &sh2 = shapeTab.at(f_inf2[f]);
+      double *v1 = &fz[(static_cast<size_t>(f) * 2 + 0) * dof * neq];
+      double *v2 = &fz[(static_cast<size_t>(f) * 2 + 1) * dof * neq];
+      const double delta1 = elSize[e1], delta2 = elSize[e2];
+      double u1[16], u2[16], g1[48], g2[48], nor[3], xyz[3], fluxN[16], vF1[48], vF2[48];
+      for (int q = 0; q < nqf; q++) {
+        const double *s1 = &sh1[static_cast<size_t>(q) * dof], *s2 = &sh2[static_cast<size_t>(q) * dof];
+        for (int eq = 0; eq < neq; eq++) {
+          double a = 0, b = 0;
+          for (int k = 0; k < dof; k++) a += x[static_cast<size_t>(e1) * dof + k + eq * N] * s1[k];
+          for (int k = 0; k < dof; k++) b += x[static_cast<size_t>(e2) * dof + k + eq * N] * s2[k];
+          u1[eq] = a;
+          u2[eq] = b;
+        }
+        for (int sp = 0; sp < nact; sp++) {
+          const int eq = nvel + 2 + sp;
+          u1[eq] = std::max(u1[eq], 0.0);
+          u2[eq] = std::max(u2[eq], 0.0);
+        }
+        for (int eq = 0; eq < neq; eq++)
+          for (int d = 0; d < 3; d++) {
+            double a = 0, b = 0;
+            const double *ga = &gradUp[static_cast<size_t>(e1) * dof + eq * N + static_cast<size_t>(d) * neq * N];
+            const double *gb = &gradUp[static_cast<size_t>(e2) * dof + eq * N + static_cast<size_t>(d) * neq * N];
+            for (int k = 0; k < dof; k++) a += ga[k] * s1[k];
+            for (int k = 0; k < dof; k++) b += gb[k] * s2[k];
+            g1[eq + d * neq] = a;
+            g2[eq + d * neq] = b;
+          }
+        face_geom(f, q, nor, xyz);
+        ph->riemann(u1, u2, nor, fluxN);
+        ph->visc_flux(u1, g1, xyz, delta1, 0.0, vF1);
+        ph->visc_flux(u2, g2, xyz, delta2, 0.0, vF2);
+        // viscF1 += viscF2; viscF1 *= -0.5; viscF1.AddMult(nor, fluxN); fluxN *= ip.weight
+        for (int i = 0; i < neq * 3; i++) {
+          vF1[i] += vF2[i];
+          vF1[i] *= -0.5;
+        }
+        for (int eq = 0; eq < neq; eq++) {
+          double a = 0;
+          for (int d = 0; d < 3; d++) a += vF1[eq + d * neq] * nor[d];
+          fluxN[eq] += a;
+        }
+        const double w = qwf[q % nqf1] * qwf[q / nqf1];
+        for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
+        for (int k = 0; k < dof; k++)
+          for (int eq = 0; eq < neq; eq++) {
+            v2[k * neq + eq] += s2[k] * fluxN[eq];
+            v1[k * neq + eq] += -1.0 * s1[k] * fluxN[eq];
+          }
+      }
+    }
+    // ---- GetFlux (src/rhs_operator.cpp:493-559), Aflux->AddMult (:379-391), Me_inv (:432-448)
+    const size_t d2 = static_cast<size_t>(dof) * dof;
+    std::vector<double> mcs_t(nthreads, 0.0);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int e = 0; e < NE; e++) {
+      int tid = 0;
+#ifdef _OPENMP
+      tid = omp_get_thread_num();
+#endif
+      std::vector<double> z(static_cast<size_t>(dof) * neq, 0.0), fl(static_cast<size_t>(dof) * 3 * neq);
+      for (int f : el_faces[e]) {
+        const int side = (f_el1[f] == e) ? 0 : 1;
+        const double *v = &fz[(static_cast<size_t>(f) * 2 + side) * dof * neq];
+        for (size_t i = 0; i < z.size(); i++) z[i] += v[i];
+      }
+      for (int n = 0; n < dof; n++) {
+        const size_t i = static_cast<size_t>(e) * dof + n;
+        double st[16], g[48], fc[48], fv[48], xyz[3];
+        for (int k = 0; k < neq; k++) st[k] = x[i + k * N];
+        for (int sp = 0; sp < nact; sp++) st[nvel + 2 + sp] = std::max(st[nvel + 2 + sp], 0.0);
+        for (int eq = 0; eq < neq; eq++)
+          for (int d = 0; d < 3; d++) g[eq + d * neq] = gradUp[i + eq * N + static_cast<size_t>(d) * neq * N];
+        for (int d = 0; d < 3; d++) xyz[d] = nodeXYZ[i * 3 + d];
+        ph->conv_flux(st, fc);
+        if (phys.eq_system != 0) {
+          ph->visc_flux(st, g, xyz, elSize[e], 0.0, fv);
+          for (int c = 0; c < neq * 3; c++) fc[c] -= fv[c];
+        }
+        for (int d = 0; d < 3; d++)
+          for (int k = 0; k < neq; k++) fl[(n * 3 + d) * neq + k] = fc[k + d * neq];
+        const double mcs = ph->max_char_speed(st);
+        if (mcs > mcs_t[tid]) mcs_t[tid] = mcs;
+      }
+      const double *kf = &Kfl[e * d2 * 3];
+      for (int eq = 0; eq < neq; eq++)
+        for (int j = 0; j < dof; j++) {
+          double a = 0;
+          for (int d = 0; d < 3; d++)
+            for (int k = 0; k < dof; k++) a += kf[j * (3 * dof) + k + d * dof] * fl[(k * 3 + d) * neq + eq];
+          z[j * neq + eq] += a;
+        }
+      const double *mi = &Me_inv[e * d2];
+      for (int eq = 0; eq < neq; eq++)
+        for (int j = 0; j < dof; j++) {
+          double a = 0;
+          for (int k = 0; k < dof; k++) a += mi[j * dof + k] * z[k * neq + eq];
+          y[static_cast<size_t>(e) * dof + j + eq * N] = a;
+        }
+    }
+    for (double m : mcs_t) max_char_speed = std::max(max_char_speed, m);
+  }
+};
+
+}  // namespace orc
+
+using orc::Oracle;
+
+extern "C" {
+
+const char *orc_physics_kind() {
+  OrcPhysParams p;
+  memset(&p, 0, sizeof(p));
+  p.gamma = 1.4;
+  p.R = 287.058;
+  p.Pr = 0.71;
+  p.S0 = 110.4;
+  p.C1 = 1.458e-6;
+  p.visc_mult = 1;
+  orc::Physics *ph = orc::make_physics(p, 3, 3, 5);
+  static char buf[32];
+  snprintf(buf, sizeof(buf), "%s", ph ? ph->kind() : "none");
+  delete ph;
+  return buf;
+}
+
+// vx: [NE][8][3] element vertex coordinates (MFEM hex vertex order); faces in MFEM convention:
+// el1/el2 = Elem1No/Elem2No (-1 boundary), inf = 64*local_face + orientation.
+void *orc_create(int order, int NE, const double *vx, int NF, const int *el1, const int *el2, const int *inf1,
+                 const int *inf2, const OrcPhysParams *phys, int nthreads) {
+  Oracle *o = new Oracle;
+  o->p = order;
+  o->NE = NE;
+  o->NF = NF;
+  o->vx.assign(vx, vx + static_cast<size_t>(NE) * 24);
+  o->f_el1.assign(el1, el1 + NF);
+  o->f_el2.assign(el2, el2 + NF);
+  o->f_inf1.assign(inf1, inf1 + NF);
+  o->f_inf2.assign(inf2, inf2 + NF);
+  o->phys = *phys;
+  o->nthreads = nthreads > 0 ? nthreads : 1;
+  o->ph = orc::make_physics(*phys, 3, 3, 5);
+  if (!o->ph) {
+    delete o;
+    return nullptr;
+  }
+  o->setup();
+  return o;
+}
+void orc_destroy(void *h) {
+  Oracle *o = static_cast<Oracle *>(h);
+  if (!o) return;
+  delete o->ph;
+  delete o;
+}
+long orc_ndofs(void *h) { return static_cast<Oracle *>(h)->N; }
+int orc_num_equation(void *h) { return static_cast<Oracle *>(h)->neq; }
+void orc_update_primitives(void *h, const double *x, double *Up_out) {
+  Oracle *o = static_cast<Oracle *>(h);
+  o->update_primitives(x);
+  if (Up_out) std::copy(o->Up.begin(), o->Up.end(), Up_out);
+}
+void orc_compute_gradients(void *h, const double *x, double *gradUp_out) {
+  Oracle *o = static_cast<Oracle *>(h);
+  o->update_primitives(x);
+  o->compute_gradients();
+  if (gradUp_out) std::copy(o->gradUp.begin(), o->gradUp.end(), gradUp_out);
+}
+void orc_rhs_mult(void *h, const double *x, double *y, double *gradUp_out, double *max_char_speed) {
+  Oracle *o = static_cast<Oracle *>(h);
+  o->mult(x, y);
+  if (gradUp_out) std::copy(o->gradUp.begin(), o->gradUp.end(), gradUp_out);
+  if (max_char_speed) *max_char_speed = o->max_char_speed;
+}
+// [MFEM RK4Solver::Step]: classic RK4, stages at t, t+dt/2, t+dt/2, t+dt (src/M2ulPhyS.cpp:721-739, :2005)
+void orc_rk4_steps(void *h, double *U, double dt, int nsteps) {
+  Oracle *o = static_cast<Oracle *>(h);
+  const size_t n = static_cast<size_t>(o->N) * o->neq;
+  std::vector<double> k(n), yv(n), z(n);
+  for (int s = 0; s < nsteps; s++) {
+    o->mult(U, k.data());
+    for (size_t i = 0; i < n; i++) {
+      yv[i] = U[i] + (dt / 2) * k[i];
+      z[i] = U[i] + (dt / 6) * k[i];
+    }
+    o->mult(yv.data(), k.data());
+    for (size_t i = 0; i < n; i++) {
+      yv[i] = U[i] + (dt / 2) * k[i];
+      z[i] += (dt / 3) * k[i];
+    }
+    o->mult(yv.data(), k.data());
+    for (size_t i = 0; i < n; i++) {
+      yv[i] = U[i] + dt * k[i];
+      z[i] += (dt / 3) * k[i];
+    }
+    o->mult(yv.data(), k.data());
+    for (size_t i = 0; i < n; i++) U[i] = z[i] + (dt / 6) * k[i];
+  }
+}
+// geometry / table probes for the unit tests
+void orc_node_coords(void *h, double *xyz /*[N][3]*/) {
+  Oracle *o = static_cast<Oracle *>(h);
+  std::copy(o->nodeXYZ.begin(), o->nodeXYZ.end(), xyz);
+}
+int orc_face_nq(void *h) { return static_cast<Oracle *>(h)->nqf; }
+void orc_face_geometry(void *h, int f, double *nor /*[nqf][3]*/, double *xyz /*[nqf][3]*/, double *w /*[nqf]*/) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (int q = 0; q < o->nqf; q++) {
+    o->face_geom(f, q, &nor[q * 3], &xyz[q * 3]);
+    w[q] = o->qwf[q % o->nqf1] * o->qwf[q / o->nqf1];
+  }
+}
+void orc_elem_size(void *h, double *delta /*[NE]*/) {
+  Oracle *o = static_cast<Oracle *>(h);
+  std::copy(o->elSize.begin(), o->elSize.end(), delta);
+}
+void orc_dense_ops(void *h, int e, double *Me_inv, double *Ke, double *Kfl) {
+  Oracle *o = static_cast<Oracle *>(h);
+  const size_t d2 = static_cast<size_t>(o->dof) * o->dof;
+  if (Me_inv) std::copy(&o->Me_inv[e * d2], &o->Me_inv[(e + 1) * d2], Me_inv);
+  if (Ke) std::copy(&o->Ke[e * d2 * 3], &o->Ke[(e + 1) * d2 * 3], Ke);
+  if (Kfl) std::copy(&o->Kfl[e * d2 * 3], &o->Kfl[(e + 1) * d2 * 3], Kfl);
+}
+void orc_gl_rule(int n, double *x, double *w) {
+  std::vector<double> xv, wv;
+  orc::gauss_legendre01(n, xv, wv);
+  std::copy(xv.begin(), xv.end(), x);
+  std::copy(wv.begin(), wv.end(), w);
+}
+
+// ---- point-wise physics probes (tests compare product device physics and port vs reference) ----
+static orc::Physics *g_pp = nullptr;
+void orc_phys_init(const OrcPhysParams *p) {
+  delete g_pp;
+  g_pp = orc::make_physics(*p, 3, 3, 5);
+}
+void orc_phys_prim(int n, const double *U, double *Up) {
+  for (int i = 0; i < n; i++) g_pp->prim(U + 5 * i, Up + 5 * i);
+}
+void orc_phys_max_char_speed(int n, const double *U, double *out) {
+  for (int i = 0; i < n; i++) out[i] = g_pp->max_char_speed(U + 5 * i);
+}
+void orc_phys_conv_flux(int n, const double *U, double *F) {
+  for (int i = 0; i < n; i++) g_pp->conv_flux(U + 5 * i, F + 15 * i);
+}
+void orc_phys_visc_flux(int n, const double *U, const double *gradUp, double *F) {
+  double xyz[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++) g_pp->visc_flux(U + 5 * i, gradUp + 15 * i, xyz, 0.0, 0.0, F + 15 * i);
+}
+void orc_phys_riemann(int n, const double *U1, const double *U2, const double *nor, double *F) {
+  for (int i = 0; i < n; i++) g_pp->riemann(U1 + 5 * i, U2 + 5 * i, nor + 3 * i, F + 5 * i);
+}
+}

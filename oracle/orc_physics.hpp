@@ -1,0 +1,53 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Never linked into the product.
+//
+// Per-point physics interface used by the DG oracle (oracle/dg_oracle.cpp).  Two
+// interchangeable back ends implement it:
+//   * orc_physics_port.cpp : a plain restatement of the reference formulas
+//                            (cpu_baseline.kind == "port");
+//   * orc_physics_ref.cpp  : thin calls into the reference's OWN, unmodified object code
+//                            (DryAir, DryAirTransport, Fluxes, RiemannSolverTPS) compiled from
+//                            /root/reference/src against oracle/refstub/ -- built only into
+//                            oracle/_ref/ (cpu_baseline.kind == "reference").
+// Array conventions are the reference's: states are [rho, rho u(nvel), rho E, ...],
+// per-point matrices are column-major f[eq + d*neq] (src/fluxes.cpp:141-145).
+#pragma once
+
+extern "C" {
+// Mirrors the scalar inputs of DryAirInput (src/dataStructures.hpp:609-622) and the
+// DryAirTransport constructor (src/transport_properties.cpp:208-221).
+struct OrcPhysParams {
+  int eq_system;  // Equations enum of the reference: 0 EULER, 1 NS (src/dataStructures.hpp:65-69)
+  int fluid;      // WorkingFluid: 0 DRY_AIR
+  double gamma;   // specific_heat_ratio
+  double R;       // gas_constant
+  double visc_mult;
+  double bulk_visc_mult;
+  double C1, S0, Pr;  // Sutherland data (src/dataStructures.hpp:205-209)
+};
+}
+
+namespace orc {
+
+struct Physics {
+  virtual ~Physics() {}
+  virtual const char *kind() const = 0;
+  // GasMixture::GetPrimitivesFromConservatives
+  virtual void prim(const double *U, double *Up) = 0;
+  // GasMixture::GetConservativesFromPrimitives
+  virtual void cons(const double *Up, double *U) = 0;
+  // GasMixture::ComputeMaxCharSpeed
+  virtual double max_char_speed(const double *U) = 0;
+  // Fluxes::ComputeConvectiveFluxes
+  virtual void conv_flux(const double *U, double *F) = 0;
+  // Fluxes::ComputeViscousFluxes
+  virtual void visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist,
+                         double *F) = 0;
+  // RiemannSolverTPS::Eval (useRoe = false -> Eval_LF)
+  virtual void riemann(const double *U1, const double *U2, const double *nor, double *flux) = 0;
+  virtual int num_active_species() const = 0;
+};
+
+// Implemented by exactly one of orc_physics_port.cpp / orc_physics_ref.cpp per library.
+Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq);
+
+}  // namespace orc

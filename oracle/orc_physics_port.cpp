@@ -1,0 +1,147 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Never linked into the product.
+//
+// "port" physics back end: a line-by-line CPU restatement of the reference's dry-air
+// closure.  Each function cites the reference lines it follows.  It is validated against
+// the reference's own object code (orc_physics_ref.cpp) by tests/test_oracle_physics.py.
+#include <cmath>
+#include <cstring>
+
+#include "orc_physics.hpp"
+
+namespace orc {
+
+class DryAirPort : public Physics {
+  OrcPhysParams p_;
+  int dim_, nvel_, neq_;
+  double cp_div_pr_;
+
+ public:
+  DryAirPort(const OrcPhysParams &p, int dim, int nvel, int neq) : p_(p), dim_(dim), nvel_(nvel), neq_(neq) {
+    // src/transport_properties.cpp:220
+    cp_div_pr_ = p.gamma * p.R / (p.Pr * (p.gamma - 1.));
+  }
+  const char *kind() const override { return "port"; }
+  int num_active_species() const override { return 0; }
+
+  // src/equation_of_state.hpp:610-617 (DryAir::ComputePressure)
+  double pressure(const double *s) const {
+    double den_vel2 = 0;
+    for (int d = 0; d < nvel_; d++) den_vel2 += s[d + 1] * s[d + 1];
+    den_vel2 /= s[0];
+    return (p_.gamma - 1.0) * (s[1 + nvel_] - 0.5 * den_vel2);
+  }
+  // src/equation_of_state.hpp:621-627 (DryAir::ComputeTemperature)
+  double temperature(const double *s) const {
+    double den_vel2 = 0;
+    for (int d = 0; d < nvel_; d++) den_vel2 += s[d + 1] * s[d + 1];
+    den_vel2 /= s[0];
+    return (p_.gamma - 1.0) / p_.R * (s[1 + nvel_] - 0.5 * den_vel2) / s[0];
+  }
+  // src/equation_of_state.cpp:321-335
+  void prim(const double *U, double *Up) override {
+    double T = temperature(U);
+    for (int eq = 0; eq < neq_; eq++) Up[eq] = U[eq];
+    for (int d = 0; d < nvel_; d++) Up[1 + d] /= U[0];
+    Up[1 + nvel_] = T;
+  }
+  // src/equation_of_state.cpp:298-315
+  void cons(const double *Up, double *U) override {
+    for (int eq = 0; eq < neq_; eq++) U[eq] = Up[eq];
+    double v2 = 0.;
+    for (int d = 0; d < nvel_; d++) {
+      v2 += Up[1 + d] * Up[1 + d];
+      U[1 + d] *= Up[0];
+    }
+    U[1 + nvel_] = p_.R * Up[0] * Up[1 + nvel_] / (p_.gamma - 1.) + 0.5 * Up[0] * v2;
+  }
+  // src/equation_of_state.cpp:279-294
+  double max_char_speed(const double *s) override {
+    const double den = s[0];
+    double den_vel2 = 0;
+    for (int d = 0; d < nvel_; d++) den_vel2 += s[d + 1] * s[d + 1];
+    den_vel2 /= den;
+    const double pres = pressure(s);
+    const double sound = sqrt(p_.gamma * pres / den);
+    const double vel = sqrt(den_vel2 / den);
+    return vel + sound;
+  }
+  // src/fluxes.cpp:135-170 (no species, single temperature)
+  void conv_flux(const double *s, double *flux) override {
+    const double pres = pressure(s);
+    for (int d = 0; d < dim_; d++) {
+      flux[0 + d * neq_] = s[d + 1];
+      for (int i = 0; i < nvel_; i++) flux[1 + i + d * neq_] = s[i + 1] * s[d + 1] / s[0];
+      flux[1 + d + d * neq_] += pres;
+    }
+    const double H = (s[1 + nvel_] + pres) / s[0];
+    for (int d = 0; d < dim_; d++) flux[1 + nvel_ + d * neq_] = s[d + 1] * H;
+  }
+  // src/fluxes.cpp:178-335 with DryAirTransport::ComputeFluxMolecularTransport
+  // (src/transport_properties.cpp:223-234); non-axisymmetric, no SGS, no sponge.
+  void visc_flux(const double *s, const double *gradUp, double * /*xyz*/, double /*delta*/, double /*dist*/,
+                 double *flux) override {
+    for (int d = 0; d < dim_; d++)
+      for (int eq = 0; eq < neq_; eq++) flux[eq + d * neq_] = 0.;
+    if (p_.eq_system == 0) return;  // EULER, src/fluxes.cpp:185-187
+
+    double pr = pressure(s);
+    double temp = pr / p_.R / s[0];
+    double visc = (p_.C1 * p_.visc_mult * pow(temp, 1.5) / (temp + p_.S0));
+    double bulkViscosity = p_.bulk_visc_mult * visc;
+    double k = cp_div_pr_ * visc;
+    bulkViscosity -= 2. / 3. * visc;
+    double ke = 0.0;
+    k += ke;  // single temperature, src/fluxes.cpp:257
+
+    double stress[9], vel[3], vtmp[3];
+    double divV = 0.;
+    for (int i = 0; i < dim_; i++) {
+      for (int j = 0; j < dim_; j++)
+        stress[i + j * dim_] = gradUp[(1 + j) + i * neq_] + gradUp[(1 + i) + j * neq_];
+      divV += gradUp[(1 + i) + i * neq_];
+    }
+    for (int i = 0; i < dim_; i++)
+      for (int j = 0; j < dim_; j++) stress[i + j * dim_] *= visc;
+    for (int i = 0; i < dim_; i++) stress[i + i * dim_] += bulkViscosity * divV;
+    for (int i = 0; i < dim_; i++)
+      for (int j = 0; j < dim_; j++) flux[(1 + i) + j * neq_] = stress[i + j * dim_];
+
+    for (int d = 0; d < dim_; d++) vel[d] = s[1 + d] / s[0];
+    for (int i = 0; i < dim_; i++) {
+      vtmp[i] = 0.0;
+      for (int j = 0; j < dim_; j++) vtmp[i] += stress[i + j * dim_] * vel[j];
+    }
+    for (int d = 0; d < dim_; d++) {
+      flux[(1 + nvel_) + d * neq_] += vtmp[d];
+      flux[(1 + nvel_) + d * neq_] += k * gradUp[(1 + nvel_) + d * neq_];
+    }
+  }
+  // src/riemann_solver.cpp:89-114 (Eval_LF) with ComputeFluxDotN :53-64
+  void riemann(const double *s1, const double *s2, const double *nor, double *flux) override {
+    const double maxE1 = max_char_speed(s1);
+    const double maxE2 = max_char_speed(s2);
+    const double maxE = fmax(maxE1, maxE2);
+    double f1[16 * 3], f2[16 * 3], flux1[16], flux2[16];
+    conv_flux(s1, f1);
+    conv_flux(s2, f2);
+    for (int eq = 0; eq < neq_; eq++) {
+      flux1[eq] = 0;
+      flux2[eq] = 0;
+      for (int d = 0; d < dim_; d++) {
+        flux1[eq] += f1[eq + d * neq_] * nor[d];
+        flux2[eq] += f2[eq + d * neq_] * nor[d];
+      }
+    }
+    double normag = 0;
+    for (int i = 0; i < dim_; i++) normag += nor[i] * nor[i];
+    normag = sqrt(normag);
+    for (int i = 0; i < neq_; i++) flux[i] = 0.5 * (flux1[i] + flux2[i]) - 0.5 * maxE * (s2[i] - s1[i]) * normag;
+  }
+};
+
+Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq) {
+  if (p.fluid != 0) return nullptr;
+  return new DryAirPort(p, dim, nvel, neq);
+}
+
+}  // namespace orc

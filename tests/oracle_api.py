@@ -1,0 +1,122 @@
+"""ctypes access to the CPU oracle (oracle/liboracle.so, oracle/_ref/liboracle_ref.so).
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+class OrcPhysParams(C.Structure):
+    _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("gamma", C.c_double), ("R", C.c_double),
+                ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double), ("C1", C.c_double),
+                ("S0", C.c_double), ("Pr", C.c_double)]
+
+
+def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0):
+    """Defaults of the reference: gamma/R src/equation_of_state.cpp:175-179; Sutherland SURVEY.md 8(d)."""
+    return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71)
+
+
+def build(ref=False):
+    """Compile the oracle (and, when /root/reference is present, the reference-physics flavour)."""
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "all"])
+    if ref and os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def load(kind="port"):
+    path = os.path.join(ORACLE_DIR, "liboracle.so" if kind == "port" else "_ref/liboracle_ref.so")
+    if not os.path.exists(path):
+        if kind == "port":
+            build()
+        else:
+            raise FileNotFoundError(path)
+    lib = C.CDLL(path)
+    lib.orc_physics_kind.restype = C.c_char_p
+    lib.orc_create.restype = C.c_void_p
+    lib.orc_create.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip, _ip, C.POINTER(OrcPhysParams), C.c_int]
+    lib.orc_destroy.argtypes = [C.c_void_p]
+    lib.orc_ndofs.restype = C.c_long
+    lib.orc_ndofs.argtypes = [C.c_void_p]
+    lib.orc_update_primitives.argtypes = [C.c_void_p, _dp, _dp]
+    lib.orc_compute_gradients.argtypes = [C.c_void_p, _dp, _dp]
+    lib.orc_rhs_mult.argtypes = [C.c_void_p, _dp, _dp, C.c_void_p, C.POINTER(C.c_double)]
+    lib.orc_rk4_steps.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int]
+    lib.orc_node_coords.argtypes = [C.c_void_p, _dp]
+    lib.orc_face_nq.argtypes = [C.c_void_p]
+    lib.orc_face_geometry.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+    lib.orc_elem_size.argtypes = [C.c_void_p, _dp]
+    lib.orc_dense_ops.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.orc_gl_rule.argtypes = [C.c_int, _dp, _dp]
+    lib.orc_phys_init.argtypes = [C.POINTER(OrcPhysParams)]
+    lib.orc_phys_prim.argtypes = [C.c_int, _dp, _dp]
+    lib.orc_phys_max_char_speed.argtypes = [C.c_int, _dp, _dp]
+    lib.orc_phys_conv_flux.argtypes = [C.c_int, _dp, _dp]
+    lib.orc_phys_visc_flux.argtypes = [C.c_int, _dp, _dp, _dp]
+    lib.orc_phys_riemann.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+    return lib
+
+
+class Oracle:
+    """Thin object over orc_*: one DG operator on one mesh."""
+
+    def __init__(self, order, elem_xyz, el1, el2, inf1, inf2, phys=None, nthreads=None, kind="port"):
+        self.lib = load(kind)
+        self.phys = phys or dry_air_params()
+        self.NE = elem_xyz.shape[0]
+        self.order = order
+        self.neq = 5
+        nthreads = nthreads or os.cpu_count()
+        self.h = self.lib.orc_create(order, self.NE, np.ascontiguousarray(elem_xyz, dtype=np.float64), len(el1),
+                                     np.ascontiguousarray(el1, np.int32), np.ascontiguousarray(el2, np.int32),
+                                     np.ascontiguousarray(inf1, np.int32), np.ascontiguousarray(inf2, np.int32),
+                                     C.byref(self.phys), nthreads)
+        assert self.h, "orc_create failed"
+        self.N = self.lib.orc_ndofs(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def node_coords(self):
+        xyz = np.zeros((self.N, 3))
+        self.lib.orc_node_coords(self.h, xyz)
+        return xyz
+
+    def primitives(self, x):
+        up = np.zeros_like(x)
+        self.lib.orc_update_primitives(self.h, x, up)
+        return up
+
+    def gradients(self, x):
+        g = np.zeros(self.N * self.neq * 3)
+        self.lib.orc_compute_gradients(self.h, x, g)
+        return g
+
+    def mult(self, x, want_grad=False):
+        y = np.zeros_like(x)
+        g = np.zeros(self.N * self.neq * 3) if want_grad else None
+        mcs = C.c_double(0.0)
+        self.lib.orc_rhs_mult(self.h, x, y, g.ctypes.data if want_grad else None, C.byref(mcs))
+        self.max_char_speed = mcs.value
+        return (y, g) if want_grad else y
+
+    def rk4(self, U, dt, nsteps):
+        U = np.ascontiguousarray(U.copy())
+        self.lib.orc_rk4_steps(self.h, U, dt, nsteps)
+        return U
+
+    def face_geometry(self, f):
+        nq = self.lib.orc_face_nq(self.h)
+        nor, xyz, w = np.zeros((nq, 3)), np.zeros((nq, 3)), np.zeros(nq)
+        self.lib.orc_face_geometry(self.h, f, nor, xyz, w)
+        return nor, xyz, w
