@@ -1,0 +1,168 @@
+/* tpsb200.h -- C ABI of libtpsb200.so: the B200-native (sm_100a, FP64) replacement for the
+ * explicit DG right-hand-side path of pecos/tps (RHSoperator::Mult and everything it calls).
+ *
+ * The reference has no C ABI: its "plugin API" is a set of C++ classes wired with raw pointers in
+ * M2ulPhyS::initVariables (src/M2ulPhyS.cpp:599-621,692-753).  Each entry point below names the
+ * reference interface it replaces; INTEGRATION.md shows the C++ shim a TPS maintainer adds so that
+ * M2ulPhyS, MFEM's ODESolver and utils/compute_rhs.cpp keep calling the same class methods.
+ *
+ * Conventions (all from the reference):
+ *   - nodal vectors are Ordering::byNODES: U[n + eq*N], gradUp[n + eq*N + d*neq*N], N = vfes->GetNDofs()
+ *     = num_elems * dof, node n = e*dof + local node (lexicographic, x fastest)   (src/rhs_operator.cpp:589-591)
+ *   - conserved state [rho, rho u (nvel), rho E, ...], primitives [rho, u (nvel), T, ...]
+ *     (src/equation_of_state.cpp:321-335)
+ *   - faces follow MFEM's Mesh::GetFaceElements / GetFaceInfos numbering:
+ *     ElemXInf = 64*local_face + orientation                                     (src/M2ulPhyS.cpp:937-958)
+ * Plain pointers and sizes only; no C++/torch types.  Every function returns 0 on success or a
+ * TPSB_E* code (message via tpsb_last_error); nothing here calls exit()/abort().
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with TPSB_ECUDA.
+ */
+#ifndef TPSB200_H_
+#define TPSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPSB_OK 0
+#define TPSB_EINVAL 1    /* bad argument / unsupported configuration */
+#define TPSB_ECUDA 2     /* CUDA runtime error (or no device)          */
+#define TPSB_ENCCL 3     /* NCCL error                                  */
+#define TPSB_ENOTIMPL 4  /* valid in the reference, not built yet       */
+
+/* ---- enums: numeric values equal the reference's (src/dataStructures.hpp:65-72) ---- */
+enum { TPSB_EULER = 0, TPSB_NS = 1, TPSB_NS_PASSIVE = 2 }; /* Equations     */
+enum { TPSB_DRY_AIR = 0, TPSB_USER_DEFINED = 1, TPSB_LTE_FLUID = 2 }; /* WorkingFluid */
+
+/* Mesh/connectivity tables the MFEM host code hands over (what initIndirectionArrays reads from
+ * ParMesh, src/M2ulPhyS.cpp:816-1075).  All arrays are HOST memory, copied at create.          */
+typedef struct {
+  int dim;                      /* 3 (hexahedra); 2-D quads: TPSB_ENOTIMPL for now                          */
+  int num_elems;                /* vfes->GetNE(), local elements                                           */
+  int num_nbr_elems;            /* face-neighbour (halo) elements, pmesh->GetNFaceNeighborElements(); 0 serial */
+  const double *elem_vertices;  /* [(num_elems+num_nbr_elems)][2^dim][dim] vertex coordinates, MFEM vertex
+                                   order, taken per element from the mesh nodes (so periodic meshes are
+                                   un-wrapped exactly as MFEM's L2 nodal GridFunction is)                  */
+  int num_faces;                /* mesh->GetNumFaces()                                                     */
+  const int *face_el1;          /* [num_faces] Elem1No                                                     */
+  const int *face_el2;          /* [num_faces] Elem2No: -1 boundary; >= num_elems: num_elems + nbr index   */
+  const int *face_inf1;         /* [num_faces] Elem1Inf = 64*local_face (+0)                               */
+  const int *face_inf2;         /* [num_faces] Elem2Inf = 64*local_face + orientation (-1 on boundary)     */
+  const int *face_attr;         /* [num_faces] boundary attribute of boundary faces (else 0); may be NULL  */
+} tpsb_mesh_maps;
+
+/* FE space description (src/M2ulPhyS.cpp:558-579). */
+typedef struct {
+  int order;          /* flow/order                                                   */
+  int basis_type;     /* flow/basisType: 0 Gauss-Legendre nodes, 1 Gauss-Lobatto      */
+  int int_rule_type;  /* flow/integrationRule: 0 Gauss-Legendre, 1 Gauss-Lobatto      */
+  int num_equation;   /* vfes vdim                                                    */
+  int nvel;           /* dim, or 3 when axisymmetric                                  */
+} tpsb_space_desc;
+
+/* Physics parameter block: the POD input structs of the reference flattened
+ * (DryAirInput src/dataStructures.hpp:609-622; DryAirTransport ctor src/transport_properties.cpp:208;
+ *  SutherlandData :205-209).                                                                     */
+typedef struct {
+  int eq_system;          /* TPSB_EULER / TPSB_NS                              */
+  int fluid;              /* TPSB_DRY_AIR                                      */
+  double specific_heat_ratio;
+  double gas_constant;
+  double visc_mult;       /* flow/viscosityMultiplier                          */
+  double bulk_visc_mult;  /* flow/bulkViscosityMultiplier                      */
+  double sutherland_C1, sutherland_S0, sutherland_Pr;
+} tpsb_physics;
+
+/* Partition neighbours for the face-neighbour exchange that replaces RHSoperator::initNBlockDataTransfer /
+ * waitAllDataTransfer (src/rhs_operator.cpp:716-831).  NULL / num_nbr_ranks == 0 for a serial run.  */
+typedef struct {
+  int num_nbr_ranks;
+  const int *nbr_rank;          /* [num_nbr_ranks] peer rank                                             */
+  const int *send_offset;       /* [num_nbr_ranks+1] into send_elems (== send_face_nbr_elements of MFEM) */
+  const int *send_elems;        /* local element ids whose dofs are sent, grouped by peer                */
+  const int *recv_offset;       /* [num_nbr_ranks+1] halo-element ranges (face_nbr_elements_offset)      */
+  void *nccl_comm;              /* ncclComm_t created by the host (or by tpsb_comm_init_rank)            */
+} tpsb_halo_desc;
+
+typedef struct tpsb_ctx tpsb_ctx; /* opaque, one per rank / GPU */
+
+/* Library / build information. */
+const char *tpsb_version(void);
+const char *tpsb_last_error(const tpsb_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+
+/* RHSoperator::RHSoperator + Gradients::Gradients + M2ulPhyS::initIndirectionArrays
+ * (src/rhs_operator.cpp:38-322, src/gradients.cpp:36-138, src/M2ulPhyS.cpp:816-1532):
+ * builds every device-side table.  cuda_stream: the caller's cudaStream_t (0 = default stream);
+ * all work of this context is enqueued on / ordered against it.                                   */
+int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys,
+                const tpsb_halo_desc *halo, int device, void *cuda_stream, tpsb_ctx **out);
+void tpsb_destroy(tpsb_ctx *ctx);
+
+/* vfes->GetNDofs(), num_equation */
+int64_t tpsb_num_dofs(const tpsb_ctx *ctx);
+int tpsb_num_equation(const tpsb_ctx *ctx);
+
+/* RHSoperator::Mult(const Vector &x, Vector &y) const   (src/rhs_operator.cpp:343-464)
+ * d_x, d_y: DEVICE pointers, neq*N doubles each, byNODES.  Asynchronous on the context stream.    */
+int tpsb_rhs_mult(tpsb_ctx *ctx, const double *d_x, double *d_y);
+
+/* Same call on HOST buffers (pinned or pageable): copies x in, runs Mult, copies y out, synchronises.
+ * This is what a host-resident MFEM Vector costs and what bench.py reports as "e2e".               */
+int tpsb_rhs_mult_host(tpsb_ctx *ctx, const double *h_x, double *h_y);
+
+/* RHSoperator::updatePrimitives (src/rhs_operator.cpp:623-651) */
+int tpsb_update_primitives(tpsb_ctx *ctx, const double *d_x);
+/* RHSoperator::updateGradients (src/rhs_operator.cpp:653-680) */
+int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updated);
+/* Views of the context-owned fields: M2ulPhyS::getPrimitiveGF / getGradientGF (src/M2ulPhyS.hpp:368-470).
+ * Up: neq*N, gradUp: dim*neq*N doubles, device memory, valid until destroy.                       */
+int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp);
+/* max_char_speed of the last Mult (src/rhs_operator.cpp:549-558), reduced over this rank's nodes
+ * (and over ranks when a communicator is attached); synchronises the stream.                      */
+int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out);
+
+/* MFEM ODESolver::Step for the solvers M2ulPhyS selects (src/M2ulPhyS.cpp:721-739, :2005):
+ * scheme 1 ForwardEuler, 2 RK2(1.0), 3 RK3SSP, 4 RK4.  d_U is advanced in place nsteps times with a
+ * constant dt, stage vectors stay on the device.                                                   */
+int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps);
+
+/* Index maps derived at create, in the layout of the reference's precomputedIntegrationData
+ * (src/dataStructures.hpp:297-517) -- exported so they can be compared bit-for-bit.
+ * element_to_faces: 7*num_elems ints (count + up to 6 interior face ids, src/M2ulPhyS.cpp:878-958). */
+int tpsb_get_element_to_faces(const tpsb_ctx *ctx, int *out);
+
+/* Test hook: the reference-element tables the kernels use (1-D nodes/weights, differentiation and
+ * interpolation matrices, face-node maps, orientation permutations) for a given order, flattened as
+ * doubles in the order documented in tps_b200/csrc/tables.hpp (struct RefTables).  Returns the number
+ * of doubles written (<= cap) or a negative error.                                                */
+int tpsb_get_ref_tables(int order, double *out, int cap);
+
+/* Kernel launches issued by this context since create (for bench.py's gpu_launches). */
+int64_t tpsb_launch_count(const tpsb_ctx *ctx);
+
+/* ---- meshkit: host-side stand-in for the few MFEM mesh services the path needs when MFEM is absent ----
+ * Cartesian hexahedral box, elements and vertices x-fastest, hex vertex order of
+ * test/meshes/periodic-cube.mesh; periodic directions identify vertices (Mesh::MakePeriodic).
+ * order_mode 0: lexicographic element order; 1: blocked (8^3 tiles) locality-preserving order.
+ * elem_verts: [NE][8] ints; elem_xyz: [NE][8][3] doubles (un-wrapped).                              */
+int tpsb_mk_cartesian_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], const int periodic[3],
+                          int order_mode, int *elem_verts, double *elem_xyz);
+/* MFEM face generation (GetElementToFaceTable + GenerateFaces): returns the number of faces;
+ * arrays sized 6*num_elems are always sufficient.  Pass NULL outputs to only count.                */
+int tpsb_mk_build_faces(int num_elems, const int *elem_verts, int *face_el1, int *face_el2, int *face_inf1,
+                        int *face_inf2);
+
+/* ---- communicator bootstrap for the NCCL face-neighbour exchange ----
+ * unique_id: 128-byte ncclUniqueId produced on rank 0 by tpsb_comm_get_unique_id and broadcast by
+ * the host (MPI_Bcast in TPS, torch.distributed in bench.py).                                      */
+int tpsb_comm_get_unique_id(unsigned char unique_id[128]);
+int tpsb_comm_init_rank(const unsigned char unique_id[128], int nranks, int rank, int device, void **nccl_comm);
+int tpsb_comm_destroy(void *nccl_comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPSB200_H_ */

@@ -1,0 +1,42 @@
+"""Shared inputs for the parity tests: the Taylor-Green state of SURVEY.md section 8(d) plus the seeded
++-1 % perturbation that breaks every symmetry (so index-map bugs cannot hide)."""
+import numpy as np
+
+SEED = 20261018
+
+
+def tgv_state(xyz, perturb=0.01, seed=SEED, gamma=1.4):
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    rho0, p0, M0 = 1.2, 101300.0, 0.1
+    c0 = np.sqrt(gamma * p0 / rho0)
+    V0 = M0 * c0
+    rho = np.full_like(x, rho0)
+    u = V0 * np.sin(x) * np.cos(y) * np.cos(z)
+    v = -V0 * np.cos(x) * np.sin(y) * np.cos(z)
+    w = np.zeros_like(x)
+    p = p0 + rho0 * V0 * V0 / 16.0 * (np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2.0)
+    U = np.concatenate([rho, rho * u, rho * v, rho * w, p / (gamma - 1.0) + 0.5 * rho * (u * u + v * v + w * w)])
+    if perturb:
+        rng = np.random.default_rng(seed)
+        U = U * (1.0 + perturb * rng.uniform(-1.0, 1.0, size=U.shape))
+    return np.ascontiguousarray(U)
+
+
+def node_coords_from_mesh(elem_xyz, order):
+    """Physical coordinates of the GL nodes (lexicographic, x fastest) of every trilinear hex."""
+    from numpy.polynomial.legendre import leggauss
+    g, _ = leggauss(order + 1)
+    xn = 0.5 * (g + 1.0)
+    npn = order + 1
+    k, j, i = np.meshgrid(np.arange(npn), np.arange(npn), np.arange(npn), indexing="ij")
+    xi = np.stack([xn[i.ravel()], xn[j.ravel()], xn[k.ravel()]], axis=1)  # [dof,3]
+    hv = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=float)
+    shp = np.ones((xi.shape[0], 8))
+    for a in range(8):
+        for d in range(3):
+            shp[:, a] *= np.where(hv[a, d] > 0, xi[:, d], 1.0 - xi[:, d])
+    return np.einsum("na,ead->end", shp, elem_xyz).reshape(-1, 3)
+
+
+def rel_l2(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))

@@ -1,0 +1,156 @@
+// meshkit -- host-side stand-in for the handful of MFEM mesh services the RHS path consumes
+// when MFEM itself is not linked (MFEM still does this job in a TPS build).
+// It produces tables in MFEM's conventions so that an MFEM-built table and a meshkit-built table
+// of the same mesh can be compared bit-for-bit:
+//   * hex vertex order and Cartesian numbering of test/meshes/periodic-cube.mesh,
+//   * face numbering by first appearance over (element, local face)   [MFEM GetElementToFaceTable],
+//   * Elem1 = first element seen, Elem2Inf = 64*lf + quad orientation [MFEM GenerateFaces],
+// which is what M2ulPhyS::initIndirectionArrays walks (src/M2ulPhyS.cpp:937-958).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tpsb200.h"
+#include "tables.hpp"
+
+namespace {
+
+struct Key {
+  int a, b, c;  // three smallest vertex ids of the quad
+  bool operator==(const Key &o) const { return a == o.a && b == o.b && c == o.c; }
+};
+struct KeyHash {
+  size_t operator()(const Key &k) const {
+    uint64_t h = static_cast<uint64_t>(k.a) * 0x9E3779B97F4A7C15ull;
+    h ^= (static_cast<uint64_t>(k.b) + 0x7F4A7C159E3779B9ull + (h << 6) + (h >> 2));
+    h ^= (static_cast<uint64_t>(k.c) + 0x94D049BB133111EBull + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
+
+// [MFEM Mesh::GetQuadOrientation]
+int quad_orientation(const int *base, const int *test) {
+  int i;
+  for (i = 0; i < 4; i++)
+    if (test[i] == base[0]) break;
+  if (i == 4) return -1;
+  if (test[(i + 1) % 4] == base[1]) return 2 * i;
+  return 2 * i + 1;
+}
+
+}  // namespace
+
+extern "C" int tpsb_mk_cartesian_hex(int nx, int ny, int nz, const double lo[3], const double hi[3],
+                                     const int periodic[3], int order_mode, int *elem_verts, double *elem_xyz) {
+  if (nx < 1 || ny < 1 || nz < 1 || !elem_verts || !elem_xyz) return TPSB_EINVAL;
+  const int n[3] = {nx, ny, nz};
+  int nv[3];
+  for (int d = 0; d < 3; d++) {
+    if (periodic[d] && n[d] < 3) return TPSB_EINVAL;  // two elements would share two faces
+    nv[d] = periodic[d] ? n[d] : n[d] + 1;
+  }
+  const double h[3] = {(hi[0] - lo[0]) / nx, (hi[1] - lo[1]) / ny, (hi[2] - lo[2]) / nz};
+  // element visiting order
+  std::vector<int64_t> order;
+  order.reserve(static_cast<size_t>(nx) * ny * nz);
+  if (order_mode == 0) {
+    for (int64_t e = 0; e < static_cast<int64_t>(nx) * ny * nz; e++) order.push_back(e);
+  } else {
+    const int B = 8;  // blocked order: 8^3 tiles, lexicographic inside and across tiles
+    for (int bz = 0; bz < nz; bz += B)
+      for (int by = 0; by < ny; by += B)
+        for (int bx = 0; bx < nx; bx += B)
+          for (int k = bz; k < std::min(bz + B, nz); k++)
+            for (int j = by; j < std::min(by + B, ny); j++)
+              for (int i = bx; i < std::min(bx + B, nx); i++)
+                order.push_back(i + static_cast<int64_t>(nx) * (j + static_cast<int64_t>(ny) * k));
+  }
+  for (size_t e = 0; e < order.size(); e++) {
+    const int64_t c = order[e];
+    const int ei[3] = {static_cast<int>(c % nx), static_cast<int>((c / nx) % ny),
+                       static_cast<int>(c / (static_cast<int64_t>(nx) * ny))};
+    for (int a = 0; a < 8; a++) {
+      int iv[3];
+      for (int d = 0; d < 3; d++) {
+        iv[d] = ei[d] + tpsb::HEX_VERT[a][d];
+        elem_xyz[(e * 8 + a) * 3 + d] = lo[d] + iv[d] * h[d];
+      }
+      elem_verts[e * 8 + a] = (iv[0] % nv[0]) + nv[0] * ((iv[1] % nv[1]) + nv[1] * (iv[2] % nv[2]));
+    }
+  }
+  return TPSB_OK;
+}
+
+extern "C" int tpsb_mk_build_faces(int num_elems, const int *elem_verts, int *face_el1, int *face_el2,
+                                   int *face_inf1, int *face_inf2) {
+  if (num_elems < 0 || !elem_verts) return -1;
+  std::unordered_map<Key, int, KeyHash> table;
+  table.reserve(static_cast<size_t>(num_elems) * 4);
+  std::vector<int> base;  // first-seen vertex order of every face
+  base.reserve(static_cast<size_t>(num_elems) * 12);
+  int nfaces = 0;
+  const bool fill = face_el1 && face_el2 && face_inf1 && face_inf2;
+  for (int e = 0; e < num_elems; e++) {
+    const int *v = &elem_verts[static_cast<size_t>(e) * 8];
+    for (int lf = 0; lf < 6; lf++) {
+      int fv[4], s[4];
+      for (int k = 0; k < 4; k++) s[k] = fv[k] = v[tpsb::HEX_FACE_VERT[lf][k]];
+      std::sort(s, s + 4);
+      const Key key{s[0], s[1], s[2]};
+      auto it = table.find(key);
+      if (it == table.end()) {
+        table.emplace(key, nfaces);
+        base.insert(base.end(), fv, fv + 4);
+        if (fill) {
+          face_el1[nfaces] = e;
+          face_el2[nfaces] = -1;
+          face_inf1[nfaces] = 64 * lf;
+          face_inf2[nfaces] = -1;
+        }
+        nfaces++;
+      } else if (fill) {
+        const int f = it->second;
+        if (face_el2[f] != -1) return -2;  // non-manifold
+        const int ori = quad_orientation(&base[static_cast<size_t>(f) * 4], fv);
+        if (ori < 0) return -3;
+        face_el2[f] = e;
+        face_inf2[f] = 64 * lf + ori;
+      }
+    }
+  }
+  return nfaces;
+}
+
+// Flattened RefTables for the tests: [np, nq, xn(np), wn(np), D(np*np), lb(2*np), xq(nq), wq(nq), P(nq*np),
+// face_base(6*np^2), face_cstride(6), face_side(6), perm(8*np^2), iperm(8*np^2)]
+extern "C" int tpsb_get_ref_tables(int order, double *out, int cap) {
+  tpsb::RefTables T;
+  if (!tpsb::build_ref_tables(order, T)) return -1;
+  std::vector<double> v;
+  const int np = T.np, nq = T.nq;
+  v.push_back(np);
+  v.push_back(nq);
+  for (int i = 0; i < np; i++) v.push_back(T.xn[i]);
+  for (int i = 0; i < np; i++) v.push_back(T.wn[i]);
+  for (int i = 0; i < np; i++)
+    for (int m = 0; m < np; m++) v.push_back(T.D[i][m]);
+  for (int s = 0; s < 2; s++)
+    for (int c = 0; c < np; c++) v.push_back(T.lb[s][c]);
+  for (int i = 0; i < nq; i++) v.push_back(T.xq[i]);
+  for (int i = 0; i < nq; i++) v.push_back(T.wq[i]);
+  for (int a = 0; a < nq; a++)
+    for (int m = 0; m < np; m++) v.push_back(T.P[a][m]);
+  for (int lf = 0; lf < 6; lf++)
+    for (int ab = 0; ab < np * np; ab++) v.push_back(T.face_base[lf][ab]);
+  for (int lf = 0; lf < 6; lf++) v.push_back(T.face_cstride[lf]);
+  for (int lf = 0; lf < 6; lf++) v.push_back(T.face_side[lf]);
+  for (int o = 0; o < 8; o++)
+    for (int ab = 0; ab < np * np; ab++) v.push_back(T.perm[o][ab]);
+  for (int o = 0; o < 8; o++)
+    for (int ab = 0; ab < np * np; ab++) v.push_back(T.iperm[o][ab]);
+  if (!out || cap < static_cast<int>(v.size())) return -2;
+  std::copy(v.begin(), v.end(), out);
+  return static_cast<int>(v.size());
+}

@@ -1,0 +1,605 @@
+// libtpsb200: context management, launch orchestration and the C ABI declared in include/tpsb200.h.
+// Single CUDA translation unit (kernels are included below); host mesh tables live in meshkit.cpp.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tpsb200.h"
+#include "rhs_kernels_impl.cuh"
+
+using namespace tpsb;
+
+static thread_local std::string g_create_error;
+static int g_uploaded_order = -1;  // order whose RefTables currently sit in __constant__ memory
+
+struct tpsb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // caller's stream: all compute is enqueued here
+  cudaStream_t comm_stream = nullptr;  // NCCL face-neighbour exchange
+  cudaEvent_t ev_pack = nullptr, ev_recvU = nullptr, ev_recvG = nullptr;
+  int order = 0, np = 0, nd = 0;
+  int NE = 0, NEH = 0, NF = 0, NFint = 0, NFlocal = 0;  // NFlocal: two-sided faces with both elements local
+  long long N = 0, NH = 0;
+  RefTables T;
+  PhysParams phys;
+  std::vector<int> element_to_faces;  // reference layout, stride 7
+  // device tables
+  double *d_vx = nullptr;
+  int *d_nbr_elem = nullptr, *d_nbr_code = nullptr, *d_face_el1 = nullptr, *d_face_el2 = nullptr,
+      *d_face_inf1 = nullptr, *d_face_inf2 = nullptr, *d_el_face = nullptr, *d_el_face_code = nullptr;
+  int *d_elem_list = nullptr;  // interior elements first, then elements touching a shared face
+  int n_int_elems = 0, n_pb_elems = 0;
+  // device fields owned by the context
+  double *d_Up = nullptr, *d_gradUp = nullptr, *d_faceRes = nullptr;
+  double *d_Uhalo = nullptr, *d_UpHalo = nullptr, *d_gradUpHalo = nullptr, *d_sendU = nullptr, *d_sendG = nullptr;
+  unsigned long long *d_maxBits = nullptr;
+  double *d_mcs = nullptr;
+  // halo description
+  ncclComm_t comm = nullptr;
+  std::vector<int> nbr_rank, send_offset, recv_offset;
+  int *d_send_elems = nullptr;
+  int n_send = 0;
+  // ODE / host-staging work vectors (lazy)
+  double *d_k = nullptr, *d_yv = nullptr, *d_z = nullptr, *d_hx = nullptr, *d_hy = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+static int fail(tpsb_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(ctx, TPSB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define NC(call)                                                                                     \
+  do {                                                                                               \
+    ncclResult_t r_ = (call);                                                                        \
+    if (r_ != ncclSuccess) return fail(ctx, TPSB_ENCCL, "%s failed: %s", #call, ncclGetErrorString(r_)); \
+  } while (0)
+
+template <class T>
+static cudaError_t upload(T **dst, const std::vector<T> &src) {
+  *dst = nullptr;
+  if (src.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), src.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static bool element_is_affine(const double *v) {
+  double scale = 0;
+  for (int i = 0; i < 3; i++) scale = std::max(scale, std::fabs(v[6 * 3 + i] - v[i]));
+  const double tol = 1e-12 * std::max(scale, 1e-300);
+  for (int i = 0; i < 3; i++) {
+    const double X0 = v[i], e1 = v[3 + i] - X0, e2 = v[9 + i] - X0, e3 = v[12 + i] - X0;
+    if (std::fabs(v[2 * 3 + i] - (X0 + e1 + e2)) > tol) return false;
+    if (std::fabs(v[5 * 3 + i] - (X0 + e1 + e3)) > tol) return false;
+    if (std::fabs(v[7 * 3 + i] - (X0 + e2 + e3)) > tol) return false;
+    if (std::fabs(v[6 * 3 + i] - (X0 + e1 + e2 + e3)) > tol) return false;
+  }
+  return true;
+}
+
+extern "C" {
+
+const char *tpsb_version(void) { return "tpsb200 0.1 (sm_100a, fp64)"; }
+
+const char *tpsb_last_error(const tpsb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys,
+                const tpsb_halo_desc *halo, int device, void *cuda_stream, tpsb_ctx **out) {
+  tpsb_ctx *ctx = nullptr;  // errors before allocation go to the thread-local create error
+  if (!maps || !space || !phys || !out) return fail(ctx, TPSB_EINVAL, "null argument");
+  *out = nullptr;
+  if (maps->dim != 3) return fail(ctx, TPSB_ENOTIMPL, "only dim = 3 (hexahedra) is built; got dim = %d", maps->dim);
+  if (space->basis_type != 0 || space->int_rule_type != 0)
+    return fail(ctx, TPSB_ENOTIMPL, "only basisType = 0 / integrationRule = 0 (Gauss-Legendre) is built");
+  if (space->order < 1 || space->order > 3) return fail(ctx, TPSB_ENOTIMPL, "order must be 1..3");
+  if (phys->fluid != TPSB_DRY_AIR || space->num_equation != NEQ || space->nvel != DIM)
+    return fail(ctx, TPSB_ENOTIMPL, "only dry air with 5 equations is built");
+  if (phys->eq_system != TPSB_EULER && phys->eq_system != TPSB_NS)
+    return fail(ctx, TPSB_ENOTIMPL, "equation system %d not built", phys->eq_system);
+  if (maps->num_elems <= 0 || maps->num_faces <= 0 || !maps->elem_vertices || !maps->face_el1 || !maps->face_el2 ||
+      !maps->face_inf1 || !maps->face_inf2)
+    return fail(ctx, TPSB_EINVAL, "incomplete mesh maps");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(ctx, TPSB_ECUDA, "no CUDA device: libtpsb200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(ctx, TPSB_EINVAL, "device %d out of range", device);
+
+  tpsb_ctx *c = new tpsb_ctx;
+  ctx = c;
+  c->device = device;
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  c->order = space->order;
+  c->np = space->order + 1;
+  c->nd = c->np * c->np * c->np;
+  c->NE = maps->num_elems;
+  c->NEH = maps->num_nbr_elems;
+  c->NF = maps->num_faces;
+  c->N = static_cast<long long>(c->NE) * c->nd;
+  c->NH = static_cast<long long>(c->NEH) * c->nd;
+  if (!build_ref_tables(c->order, c->T)) {
+    delete c;
+    return fail(nullptr, TPSB_EINVAL, "reference tables");
+  }
+  c->phys.eq_system = phys->eq_system;
+  c->phys.gamma = phys->specific_heat_ratio;
+  c->phys.R = phys->gas_constant;
+  c->phys.gm1 = phys->specific_heat_ratio - 1.0;
+  c->phys.visc_mult = phys->visc_mult;
+  c->phys.bulk_visc_mult = phys->bulk_visc_mult;
+  c->phys.C1 = phys->sutherland_C1;
+  c->phys.S0 = phys->sutherland_S0;
+  c->phys.Pr = phys->sutherland_Pr;
+  c->phys.cp_div_pr = phys->specific_heat_ratio * phys->gas_constant /
+                      (phys->sutherland_Pr * (phys->specific_heat_ratio - 1.));
+
+  const int NE = c->NE, NEH = c->NEH;
+  for (int e = 0; e < NE; e++)
+    if (!element_is_affine(&maps->elem_vertices[static_cast<size_t>(e) * 24])) {
+      delete c;
+      return fail(nullptr, TPSB_ENOTIMPL, "element %d is not a parallelepiped: curved/trilinear metric path not built yet", e);
+    }
+
+  // ---- derive the index maps (M2ulPhyS::initIndirectionArrays, src/M2ulPhyS.cpp:816-1075) ----
+  std::vector<int> e2f(static_cast<size_t>(7) * NE, 0);
+  std::vector<int> fl_el1, fl_el2, fl_inf1, fl_inf2, sh_el1, sh_el2, sh_inf1, sh_inf2;
+  for (int f = 0; f < c->NF; f++) {
+    const int e1 = maps->face_el1[f], e2 = maps->face_el2[f];
+    if (e1 < 0 || e1 >= NE || e2 >= NE + NEH) {
+      delete c;
+      return fail(nullptr, TPSB_EINVAL, "face %d has invalid elements (%d,%d)", f, e1, e2);
+    }
+    if (e2 < 0) continue;  // boundary face: handled by the BC integrators
+    // element_to_faces: interior (incl. shared) faces in ascending face order
+    int nf = e2f[7 * e1];
+    if (nf >= 6) {
+      delete c;
+      return fail(nullptr, TPSB_EINVAL, "element %d has more than 6 faces", e1);
+    }
+    e2f[7 * e1 + nf + 1] = f;
+    e2f[7 * e1] = nf + 1;
+    if (e2 < NE) {
+      nf = e2f[7 * e2];
+      if (nf >= 6) {
+        delete c;
+        return fail(nullptr, TPSB_EINVAL, "element %d has more than 6 faces", e2);
+      }
+      e2f[7 * e2 + nf + 1] = f;
+      e2f[7 * e2] = nf + 1;
+      fl_el1.push_back(e1), fl_el2.push_back(e2), fl_inf1.push_back(maps->face_inf1[f]), fl_inf2.push_back(maps->face_inf2[f]);
+    } else {
+      sh_el1.push_back(e1), sh_el2.push_back(e2), sh_inf1.push_back(maps->face_inf1[f]), sh_inf2.push_back(maps->face_inf2[f]);
+    }
+  }
+  c->element_to_faces = e2f;
+  c->NFlocal = static_cast<int>(fl_el1.size());
+  fl_el1.insert(fl_el1.end(), sh_el1.begin(), sh_el1.end());
+  fl_el2.insert(fl_el2.end(), sh_el2.begin(), sh_el2.end());
+  fl_inf1.insert(fl_inf1.end(), sh_inf1.begin(), sh_inf1.end());
+  fl_inf2.insert(fl_inf2.end(), sh_inf2.begin(), sh_inf2.end());
+  c->NFint = static_cast<int>(fl_el1.size());
+
+  std::vector<int> nbr_elem(static_cast<size_t>(6) * NE, -1), nbr_code(static_cast<size_t>(6) * NE, 0);
+  std::vector<int> el_face(static_cast<size_t>(6) * NE, -1), el_face_code(static_cast<size_t>(6) * NE, 0);
+  std::vector<char> touches_shared(NE, 0);
+  for (int fc = 0; fc < c->NFint; fc++) {
+    const int e1 = fl_el1[fc], e2 = fl_el2[fc];
+    const int lf1 = fl_inf1[fc] / 64, lf2 = fl_inf2[fc] / 64, ori = fl_inf2[fc] % 64;
+    if (lf1 < 0 || lf1 > 5 || lf2 < 0 || lf2 > 5 || ori < 0 || ori > 7 || fl_inf1[fc] % 64 != 0) {
+      delete c;
+      return fail(nullptr, TPSB_EINVAL, "face info codes out of range on two-sided face %d", fc);
+    }
+    nbr_elem[e1 * 6 + lf1] = e2;
+    nbr_code[e1 * 6 + lf1] = lf2 | (ori << 3);  // face coords == own coords: perm[ori]
+    el_face[e1 * 6 + lf1] = fc;
+    el_face_code[e1 * 6 + lf1] = 0 | (ori << 1);
+    if (e2 < NE) {
+      nbr_elem[e2 * 6 + lf2] = e1;
+      nbr_code[e2 * 6 + lf2] = lf1 | ((8 + ori) << 3);  // own coords -> face coords: iperm[ori]
+      el_face[e2 * 6 + lf2] = fc;
+      el_face_code[e2 * 6 + lf2] = 1 | (ori << 1);
+    } else {
+      touches_shared[e1] = 1;
+    }
+  }
+  std::vector<int> elem_list;
+  elem_list.reserve(NE);
+  for (int e = 0; e < NE; e++)
+    if (!touches_shared[e]) elem_list.push_back(e);
+  c->n_int_elems = static_cast<int>(elem_list.size());
+  for (int e = 0; e < NE; e++)
+    if (touches_shared[e]) elem_list.push_back(e);
+  c->n_pb_elems = NE - c->n_int_elems;
+
+  // ---- device allocations ----
+  cudaError_t ce = cudaSetDevice(device);
+  std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE + NEH) * 24);
+  if (ce == cudaSuccess) ce = upload(&c->d_vx, vx);
+  if (ce == cudaSuccess) ce = upload(&c->d_nbr_elem, nbr_elem);
+  if (ce == cudaSuccess) ce = upload(&c->d_nbr_code, nbr_code);
+  if (ce == cudaSuccess) ce = upload(&c->d_face_el1, fl_el1);
+  if (ce == cudaSuccess) ce = upload(&c->d_face_el2, fl_el2);
+  if (ce == cudaSuccess) ce = upload(&c->d_face_inf1, fl_inf1);
+  if (ce == cudaSuccess) ce = upload(&c->d_face_inf2, fl_inf2);
+  if (ce == cudaSuccess) ce = upload(&c->d_el_face, el_face);
+  if (ce == cudaSuccess) ce = upload(&c->d_el_face_code, el_face_code);
+  if (ce == cudaSuccess) ce = upload(&c->d_elem_list, elem_list);
+  const size_t nb = static_cast<size_t>(c->N) * sizeof(double);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * NEQ);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUp, nb * NEQ * DIM);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_faceRes, static_cast<size_t>(c->NFint) * NEQ * c->np * c->np * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_maxBits, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_mcs, sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMemset(c->d_maxBits, 0, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(c_T, &c->T, sizeof(RefTables));
+  if (ce == cudaSuccess) g_uploaded_order = c->order;
+
+  // ---- halo ----
+  if (ce == cudaSuccess && NEH > 0) {
+    if (!halo || halo->num_nbr_ranks <= 0 || !halo->nccl_comm || !halo->nbr_rank || !halo->send_offset ||
+        !halo->send_elems || !halo->recv_offset) {
+      tpsb_destroy(c);
+      return fail(nullptr, TPSB_EINVAL, "mesh has %d face-neighbour elements but no halo description", NEH);
+    }
+    const int np = halo->num_nbr_ranks;
+    c->comm = static_cast<ncclComm_t>(halo->nccl_comm);
+    c->nbr_rank.assign(halo->nbr_rank, halo->nbr_rank + np);
+    c->send_offset.assign(halo->send_offset, halo->send_offset + np + 1);
+    c->recv_offset.assign(halo->recv_offset, halo->recv_offset + np + 1);
+    c->n_send = c->send_offset[np];
+    if (c->recv_offset[np] != NEH) {
+      tpsb_destroy(c);
+      return fail(nullptr, TPSB_EINVAL, "recv_offset does not cover the %d face-neighbour elements", NEH);
+    }
+    std::vector<int> se(halo->send_elems, halo->send_elems + c->n_send);
+    ce = upload(&c->d_send_elems, se);
+    const size_t hb = static_cast<size_t>(c->NH) * sizeof(double), sb = static_cast<size_t>(c->n_send) * c->nd * sizeof(double);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Uhalo, hb * NEQ);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_UpHalo, hb * NEQ);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUpHalo, hb * NEQ * DIM);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendU, sb * NEQ);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendG, sb * NEQ * DIM);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvU, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvG, cudaEventDisableTiming);
+  }
+  if (ce != cudaSuccess) {
+    const std::string msg = cudaGetErrorString(ce);
+    tpsb_destroy(c);
+    return fail(nullptr, TPSB_ECUDA, "device setup failed: %s", msg.c_str());
+  }
+  *out = c;
+  return TPSB_OK;
+}
+
+void tpsb_destroy(tpsb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  void *ptrs[] = {c->d_vx,       c->d_nbr_elem,  c->d_nbr_code,     c->d_face_el1, c->d_face_el2, c->d_face_inf1,
+                  c->d_face_inf2, c->d_el_face,  c->d_el_face_code, c->d_elem_list, c->d_Up,       c->d_gradUp,
+                  c->d_faceRes,  c->d_Uhalo,     c->d_UpHalo,       c->d_gradUpHalo, c->d_sendU,   c->d_sendG,
+                  c->d_maxBits,  c->d_mcs,       c->d_send_elems,   c->d_k,        c->d_yv,       c->d_z,
+                  c->d_hx,       c->d_hy};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_pack) cudaEventDestroy(c->ev_pack);
+  if (c->ev_recvU) cudaEventDestroy(c->ev_recvU);
+  if (c->ev_recvG) cudaEventDestroy(c->ev_recvG);
+  delete c;
+}
+
+int64_t tpsb_num_dofs(const tpsb_ctx *c) { return c ? c->N : 0; }
+int tpsb_num_equation(const tpsb_ctx *c) { return c ? NEQ : 0; }
+int64_t tpsb_launch_count(const tpsb_ctx *c) { return c ? c->launches : 0; }
+
+int tpsb_get_element_to_faces(const tpsb_ctx *c, int *out) {
+  if (!c || !out) return TPSB_EINVAL;
+  std::copy(c->element_to_faces.begin(), c->element_to_faces.end(), out);
+  return TPSB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
+  KernelArgs a;
+  a.NE = c->NE;
+  a.NEH = c->NEH;
+  a.N = c->N;
+  a.NH = c->NH;
+  a.NFint = c->NFint;
+  a.ND = c->nd;
+  a.phys = c->phys;
+  a.vx = c->d_vx;
+  a.nbr_elem = c->d_nbr_elem;
+  a.nbr_code = c->d_nbr_code;
+  a.face_el1 = c->d_face_el1;
+  a.face_el2 = c->d_face_el2;
+  a.face_inf1 = c->d_face_inf1;
+  a.face_inf2 = c->d_face_inf2;
+  a.el_face = c->d_el_face;
+  a.el_face_code = c->d_el_face_code;
+  a.U = d_x;
+  a.Uhalo = c->d_Uhalo;
+  a.Up = c->d_Up;
+  a.UpHalo = c->d_UpHalo;
+  a.gradUp = c->d_gradUp;
+  a.gradUpHalo = c->d_gradUpHalo;
+  a.faceRes = c->d_faceRes;
+  a.y = d_y;
+  a.maxCharBits = c->d_maxBits;
+  return a;
+}
+
+template <int NP, int EPB, int FPB>
+struct Launch {
+  static void grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
+    if (count <= 0) return;
+    grad_kernel<NP, EPB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
+    c->launches++;
+  }
+  static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+    if (count <= 0) return;
+    face_flux_kernel<NP, FPB><<<(count + FPB - 1) / FPB, NP * NP * NP * FPB, 0, c->stream>>>(a, begin, count, nullptr);
+    c->launches++;
+  }
+  static void resid(tpsb_ctx *c, const KernelArgs &a) {
+    elem_resid_kernel<NP, EPB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+    c->launches++;
+  }
+};
+
+#define DISPATCH(c, CALL)                      \
+  do {                                         \
+    switch ((c)->np) {                         \
+      case 4: Launch<4, 4, 1>::CALL; break;    \
+      case 3: Launch<3, 8, 2>::CALL; break;    \
+      default: Launch<2, 16, 4>::CALL; break;  \
+    }                                          \
+  } while (0)
+
+static void launch_prim(tpsb_ctx *c, const KernelArgs &a, int halo) {
+  const long long cnt = halo ? c->NH : c->N;
+  if (cnt <= 0) return;
+  prim_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, c->stream>>>(a, halo);
+  c->launches++;
+}
+
+// One grouped ncclSend/ncclRecv round on the communication stream: replaces
+// RHSoperator::initNBlockDataTransfer (MPI_Isend/Irecv per neighbour, src/rhs_operator.cpp:775-822).
+static int exchange(tpsb_ctx *ctx, const double *src, int nfld, double *sendbuf, double *recvbuf, cudaEvent_t done) {
+  tpsb_ctx *c = ctx;
+  const long long total = static_cast<long long>(c->n_send) * nfld * c->nd;
+  pack_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(c->n_send, c->nd, nfld, c->N,
+                                                                                c->d_send_elems, src, sendbuf);
+  c->launches++;
+  CU(cudaEventRecord(c->ev_pack, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+  const size_t per = static_cast<size_t>(nfld) * c->nd;
+  NC(ncclGroupStart());
+  for (size_t p = 0; p < c->nbr_rank.size(); p++) {
+    NC(ncclSend(sendbuf + c->send_offset[p] * per, (c->send_offset[p + 1] - c->send_offset[p]) * per, ncclDouble,
+                c->nbr_rank[p], c->comm, c->comm_stream));
+    NC(ncclRecv(recvbuf + c->recv_offset[p] * per, (c->recv_offset[p + 1] - c->recv_offset[p]) * per, ncclDouble,
+                c->nbr_rank[p], c->comm, c->comm_stream));
+  }
+  NC(ncclGroupEnd());
+  CU(cudaEventRecord(done, c->comm_stream));
+  return TPSB_OK;
+}
+
+// gradient pass = updatePrimitives + Gradients::computeGradients, with the exchange overlapped as in
+// the reference's GPU branch (src/rhs_operator.cpp:349-361)
+static int run_gradients(tpsb_ctx *ctx, const KernelArgs &a, bool prims_done) {
+  tpsb_ctx *c = ctx;
+  if (g_uploaded_order != c->order) {  // __constant__ tables are per process: re-upload on an order switch
+    CU(cudaMemcpyToSymbolAsync(c_T, &c->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, c->stream));
+    g_uploaded_order = c->order;
+  }
+  if (!prims_done) launch_prim(c, a, 0);
+  if (c->NEH > 0) {
+    int rc = exchange(c, a.U, NEQ, c->d_sendU, c->d_Uhalo, c->ev_recvU);
+    if (rc) return rc;
+    DISPATCH(c, grad(c, a, 0, c->n_int_elems, c->d_elem_list));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvU, 0));
+    launch_prim(c, a, 1);
+    DISPATCH(c, grad(c, a, c->n_int_elems, c->n_pb_elems, c->d_elem_list));
+  } else {
+    DISPATCH(c, grad(c, a, 0, c->NE, nullptr));
+  }
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+static int run_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  tpsb_ctx *c = ctx;
+  CU(cudaSetDevice(c->device));
+  KernelArgs a = make_args(c, d_x, d_y);
+  CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
+  int rc = run_gradients(c, a, false);
+  if (rc) return rc;
+  if (c->NEH > 0) {
+    rc = exchange(c, c->d_gradUp, NEQ * DIM, c->d_sendG, c->d_gradUpHalo, c->ev_recvG);
+    if (rc) return rc;
+    DISPATCH(c, face(c, a, 0, c->NFlocal));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvG, 0));
+    DISPATCH(c, face(c, a, c->NFlocal, c->NFint - c->NFlocal));
+  } else {
+    DISPATCH(c, face(c, a, 0, c->NFint));
+  }
+  DISPATCH(c, resid(c, a));
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+static __global__ void bits_to_double_kernel(const unsigned long long *bits, double *out) {
+  *out = __longlong_as_double(static_cast<long long>(*bits));
+}
+
+static int ensure_work(tpsb_ctx *ctx, double **p) {
+  if (*p) return TPSB_OK;
+  CU(cudaMalloc(p, static_cast<size_t>(ctx->N) * NEQ * sizeof(double)));
+  return TPSB_OK;
+}
+
+extern "C" {
+
+int tpsb_rhs_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  if (!ctx || !d_x || !d_y) return TPSB_EINVAL;
+  return run_mult(ctx, d_x, d_y);
+}
+
+int tpsb_rhs_mult_host(tpsb_ctx *ctx, const double *h_x, double *h_y) {
+  if (!ctx || !h_x || !h_y) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_work(ctx, &ctx->d_hx);
+  if (!rc) rc = ensure_work(ctx, &ctx->d_hy);
+  if (rc) return rc;
+  const size_t nb = static_cast<size_t>(ctx->N) * NEQ * sizeof(double);
+  CU(cudaMemcpyAsync(ctx->d_hx, h_x, nb, cudaMemcpyHostToDevice, ctx->stream));
+  rc = run_mult(ctx, ctx->d_hx, ctx->d_hy);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_y, ctx->d_hy, nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPSB_OK;
+}
+
+int tpsb_update_primitives(tpsb_ctx *ctx, const double *d_x) {
+  if (!ctx || !d_x) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  KernelArgs a = make_args(ctx, d_x, nullptr);
+  launch_prim(ctx, a, 0);
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updated) {
+  if (!ctx || !d_x) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  KernelArgs a = make_args(ctx, d_x, nullptr);
+  return run_gradients(ctx, a, primitives_updated != 0);
+}
+
+int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp) {
+  if (!ctx) return TPSB_EINVAL;
+  if (d_Up) *d_Up = ctx->d_Up;
+  if (d_gradUp) *d_gradUp = ctx->d_gradUp;
+  return TPSB_OK;
+}
+
+int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out) {
+  if (!ctx || !out) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  bits_to_double_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_maxBits, ctx->d_mcs);
+  ctx->launches++;
+  if (ctx->comm)  // MPI_Allreduce(MAX) of src/rhs_operator.cpp:557-558
+    NC(ncclAllReduce(ctx->d_mcs, ctx->d_mcs, 1, ncclDouble, ncclMax, ctx->comm, ctx->stream));
+  CU(cudaMemcpyAsync(out, ctx->d_mcs, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPSB_OK;
+}
+
+// MFEM ODESolver::Step restated (third party): ForwardEuler, RK2(a=1) (Heun),
+// RK3SSP, RK4 -- the solvers M2ulPhyS::initVariables can select (src/M2ulPhyS.cpp:721-739).
+int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps) {
+  if (!ctx || !d_U || nsteps < 0) return TPSB_EINVAL;
+  if (scheme < 1 || scheme > 4) return fail(ctx, TPSB_ENOTIMPL, "ODE scheme %d not built", scheme);
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_work(ctx, &ctx->d_k);
+  if (!rc) rc = ensure_work(ctx, &ctx->d_yv);
+  if (!rc) rc = ensure_work(ctx, &ctx->d_z);
+  if (rc) return rc;
+  const long long n = ctx->N * NEQ;
+  const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+  double *k = ctx->d_k, *y = ctx->d_yv, *z = ctx->d_z, *x = d_U;
+  cudaStream_t st = ctx->stream;
+#define AXPY(X, K, A, Y, B, Z, ACC)                                    do {                                                                   axpy2_kernel<<<nb, 256, 0, st>>>(n, X, K, A, Y, B, Z, ACC);          ctx->launches++;                                                   } while (0)
+  for (int s = 0; s < nsteps; s++) {
+    if (scheme == 1) {  // x += dt f(x)
+      if ((rc = run_mult(ctx, x, k))) return rc;
+      AXPY(x, k, dt, x, 0.0, nullptr, 0);
+    } else if (scheme == 2) {  // RK2Solver(a = 1): y = x + dt k1; x += dt/2 (k1 + k2)
+      if ((rc = run_mult(ctx, x, k))) return rc;
+      AXPY(x, k, dt, y, 0.5 * dt, z, 0);
+      if ((rc = run_mult(ctx, y, k))) return rc;
+      AXPY(z, k, 0.5 * dt, x, 0.0, nullptr, 0);
+    } else if (scheme == 3) {  // RK3SSPSolver
+      if ((rc = run_mult(ctx, x, k))) return rc;
+      AXPY(x, k, dt, y, 0.0, nullptr, 0);  // y = x + dt k
+      if ((rc = run_mult(ctx, y, k))) return rc;
+      // y = 3/4 x + 1/4 (y + dt k)
+      axpy2_kernel<<<nb, 256, 0, st>>>(n, y, k, dt, y, 0.0, nullptr, 0);
+      ctx->launches++;
+      rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 0.75, 0.25, y);
+      ctx->launches++;
+      if ((rc = run_mult(ctx, y, k))) return rc;
+      // x = 1/3 x + 2/3 (y + dt k)
+      axpy2_kernel<<<nb, 256, 0, st>>>(n, y, k, dt, y, 0.0, nullptr, 0);
+      ctx->launches++;
+      rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 1.0 / 3.0, 2.0 / 3.0, x);
+      ctx->launches++;
+    } else {  // RK4Solver
+      if ((rc = run_mult(ctx, x, k))) return rc;
+      AXPY(x, k, dt / 2, y, dt / 6, z, 0);
+      if ((rc = run_mult(ctx, y, k))) return rc;
+      AXPY(x, k, dt / 2, y, dt / 3, z, 1);
+      if ((rc = run_mult(ctx, y, k))) return rc;
+      AXPY(x, k, dt, y, dt / 3, z, 1);
+      if ((rc = run_mult(ctx, y, k))) return rc;
+      AXPY(z, k, dt / 6, x, 0.0, nullptr, 0);
+    }
+  }
+#undef AXPY
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+int tpsb_comm_get_unique_id(unsigned char unique_id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return TPSB_ENCCL;
+  memcpy(unique_id, &id, sizeof(id));
+  return TPSB_OK;
+}
+
+int tpsb_comm_init_rank(const unsigned char unique_id[128], int nranks, int rank, int device, void **nccl_comm) {
+  if (!unique_id || !nccl_comm) return TPSB_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return TPSB_ECUDA;
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  ncclComm_t comm;
+  if (ncclCommInitRank(&comm, nranks, id, rank) != ncclSuccess) return TPSB_ENCCL;
+  *nccl_comm = comm;
+  return TPSB_OK;
+}
+
+int tpsb_comm_destroy(void *nccl_comm) {
+  if (!nccl_comm) return TPSB_OK;
+  return ncclCommDestroy(static_cast<ncclComm_t>(nccl_comm)) == ncclSuccess ? TPSB_OK : TPSB_ENCCL;
+}
+
+}  // extern "C"
