@@ -140,6 +140,14 @@ int tpsb_get_element_to_faces(const tpsb_ctx *ctx, int *out);
  * of doubles written (<= cap) or a negative error.                                                */
 int tpsb_get_ref_tables(int order, double *out, int cap);
 
+/* Per-kernel device timers (the role GRVY timers play in the reference, src/M2ulPhyS.cpp:2146-2155):
+ * with profiling on, every launch is bracketed by CUDA events on the context stream; the accumulated
+ * milliseconds and launch counts per kernel class are returned in the order
+ * {prim, grad, face_flux, elem_resid, pack, axpy}.  Profiling serialises nothing but adds events.  */
+#define TPSB_NUM_KERNEL_CLASSES 6
+int tpsb_set_profiling(tpsb_ctx *ctx, int on);
+int tpsb_get_kernel_times(tpsb_ctx *ctx, double ms[TPSB_NUM_KERNEL_CLASSES], int64_t count[TPSB_NUM_KERNEL_CLASSES]);
+
 /* Kernel launches issued by this context since create (for bench.py's gpu_launches). */
 int64_t tpsb_launch_count(const tpsb_ctx *ctx);
 

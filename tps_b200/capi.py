@@ -56,7 +56,7 @@ class HaloDesc(C.Structure):
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -97,6 +97,8 @@ def lib():
     L.tpsb_get_element_to_faces.argtypes = [vp, ip]
     L.tpsb_launch_count.restype = C.c_int64
     L.tpsb_launch_count.argtypes = [vp]
+    L.tpsb_set_profiling.argtypes = [vp, C.c_int]
+    L.tpsb_get_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     L.tpsb_get_ref_tables.argtypes = [C.c_int, dp, C.c_int]
     L.tpsb_mk_cartesian_hex.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, ip, C.c_int, ip, dp]
     L.tpsb_mk_build_faces.argtypes = [C.c_int, ip, ip, ip, ip, ip]
@@ -243,6 +245,18 @@ class RhsOperator:
         out = np.zeros(7 * self.NE, dtype=np.int32)
         self._chk(self.L.tpsb_get_element_to_faces(self.ctx, _ip(out)), "tpsb_get_element_to_faces")
         return out
+
+    KERNEL_CLASSES = ("prim", "grad", "face_flux", "elem_resid", "pack", "axpy")
+
+    def set_profiling(self, on):
+        self._chk(self.L.tpsb_set_profiling(self.ctx, int(on)), "tpsb_set_profiling")
+
+    def kernel_times(self):
+        """{class: (total ms, launches)} accumulated since the last call (device timers)."""
+        ms = (C.c_double * 6)()
+        cnt = (C.c_int64 * 6)()
+        self._chk(self.L.tpsb_get_kernel_times(self.ctx, ms, cnt), "tpsb_get_kernel_times")
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def launch_count(self):
         return self.L.tpsb_launch_count(self.ctx)

@@ -49,6 +49,11 @@ struct tpsb_ctx {
   // ODE / host-staging work vectors (lazy)
   double *d_k = nullptr, *d_yv = nullptr, *d_z = nullptr, *d_hx = nullptr, *d_hy = nullptr;
   long long launches = 0;
+  // per-kernel device timers (tpsb_set_profiling)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[TPSB_NUM_KERNEL_CLASSES];
+  double prof_ms[TPSB_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0, 0};
+  long long prof_count[TPSB_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0, 0};
   std::string err;
 };
 
@@ -65,6 +70,15 @@ static int fail(tpsb_ctx *c, int code, const char *fmt, ...) {
   return code;
 }
 
+enum { K_PRIM = 0, K_GRAD, K_FACE, K_RESID, K_PACK, K_AXPY };
+struct ProfScope {  // brackets one launch with events when profiling is on
+  tpsb_ctx *c;
+  int k;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(tpsb_ctx *c_, int k_);
+  ~ProfScope();
+};
+
 #define CU(call)                                                                                     \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
@@ -75,6 +89,19 @@ static int fail(tpsb_ctx *c, int code, const char *fmt, ...) {
     ncclResult_t r_ = (call);                                                                        \
     if (r_ != ncclSuccess) return fail(ctx, TPSB_ENCCL, "%s failed: %s", #call, ncclGetErrorString(r_)); \
   } while (0)
+
+ProfScope::ProfScope(tpsb_ctx *c_, int k_) : c(c_), k(k_) {
+  c->launches++;
+  if (!c->profiling) return;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, c->stream);
+}
+ProfScope::~ProfScope() {
+  if (!c->profiling) return;
+  cudaEventRecord(e1, c->stream);
+  c->prof_events[k].emplace_back(e0, e1);
+}
 
 template <class T>
 static cudaError_t upload(T **dst, const std::vector<T> &src) {
@@ -359,17 +386,17 @@ template <int NP, int EPB, int FPB>
 struct Launch {
   static void grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
     if (count <= 0) return;
+    ProfScope ps(c, K_GRAD);
     grad_kernel<NP, EPB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
-    c->launches++;
   }
   static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
     if (count <= 0) return;
+    ProfScope ps(c, K_FACE);
     face_flux_kernel<NP, FPB><<<(count + FPB - 1) / FPB, NP * NP * NP * FPB, 0, c->stream>>>(a, begin, count, nullptr);
-    c->launches++;
   }
   static void resid(tpsb_ctx *c, const KernelArgs &a) {
+    ProfScope ps(c, K_RESID);
     elem_resid_kernel<NP, EPB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
-    c->launches++;
   }
 };
 
@@ -385,8 +412,8 @@ struct Launch {
 static void launch_prim(tpsb_ctx *c, const KernelArgs &a, int halo) {
   const long long cnt = halo ? c->NH : c->N;
   if (cnt <= 0) return;
+  ProfScope ps(c, K_PRIM);
   prim_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, c->stream>>>(a, halo);
-  c->launches++;
 }
 
 // One grouped ncclSend/ncclRecv round on the communication stream: replaces
@@ -394,9 +421,11 @@ static void launch_prim(tpsb_ctx *c, const KernelArgs &a, int halo) {
 static int exchange(tpsb_ctx *ctx, const double *src, int nfld, double *sendbuf, double *recvbuf, cudaEvent_t done) {
   tpsb_ctx *c = ctx;
   const long long total = static_cast<long long>(c->n_send) * nfld * c->nd;
-  pack_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(c->n_send, c->nd, nfld, c->N,
-                                                                                c->d_send_elems, src, sendbuf);
-  c->launches++;
+  {
+    ProfScope ps(c, K_PACK);
+    pack_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(c->n_send, c->nd, nfld, c->N,
+                                                                                  c->d_send_elems, src, sendbuf);
+  }
   CU(cudaEventRecord(c->ev_pack, c->stream));
   CU(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
   const size_t per = static_cast<size_t>(nfld) * c->nd;
@@ -552,16 +581,18 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
       AXPY(x, k, dt, y, 0.0, nullptr, 0);  // y = x + dt k
       if ((rc = run_mult(ctx, y, k))) return rc;
       // y = 3/4 x + 1/4 (y + dt k)
-      axpy2_kernel<<<nb, 256, 0, st>>>(n, y, k, dt, y, 0.0, nullptr, 0);
-      ctx->launches++;
-      rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 0.75, 0.25, y);
-      ctx->launches++;
+      AXPY(y, k, dt, y, 0.0, nullptr, 0);
+      {
+        ProfScope ps(ctx, K_AXPY);
+        rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 0.75, 0.25, y);
+      }
       if ((rc = run_mult(ctx, y, k))) return rc;
       // x = 1/3 x + 2/3 (y + dt k)
-      axpy2_kernel<<<nb, 256, 0, st>>>(n, y, k, dt, y, 0.0, nullptr, 0);
-      ctx->launches++;
-      rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 1.0 / 3.0, 2.0 / 3.0, x);
-      ctx->launches++;
+      AXPY(y, k, dt, y, 0.0, nullptr, 0);
+      {
+        ProfScope ps(ctx, K_AXPY);
+        rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 1.0 / 3.0, 2.0 / 3.0, x);
+      }
     } else {  // RK4Solver
       if ((rc = run_mult(ctx, x, k))) return rc;
       AXPY(x, k, dt / 2, y, dt / 6, z, 0);
@@ -575,6 +606,34 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
   }
 #undef AXPY
   CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+int tpsb_set_profiling(tpsb_ctx *ctx, int on) {
+  if (!ctx) return TPSB_EINVAL;
+  ctx->profiling = on != 0;
+  return TPSB_OK;
+}
+
+int tpsb_get_kernel_times(tpsb_ctx *ctx, double ms[TPSB_NUM_KERNEL_CLASSES], int64_t count[TPSB_NUM_KERNEL_CLASSES]) {
+  if (!ctx || !ms || !count) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < TPSB_NUM_KERNEL_CLASSES; k++) {
+    for (auto &ev : ctx->prof_events[k]) {
+      float t = 0;
+      CU(cudaEventElapsedTime(&t, ev.first, ev.second));
+      ctx->prof_ms[k] += t;
+      ctx->prof_count[k]++;
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
+    ctx->prof_events[k].clear();
+    ms[k] = ctx->prof_ms[k];
+    count[k] = ctx->prof_count[k];
+    ctx->prof_ms[k] = 0;
+    ctx->prof_count[k] = 0;
+  }
   return TPSB_OK;
 }
 
