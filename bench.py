@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the DG right-hand-side path (RHSoperator::Mult) on B200.
+
+Metric (BASELINE.json): RHS DOF-evals/s of the 3-D DG p=3 Navier-Stokes operator, DOF = one DG node.
+A "step" is one RHSoperator::Mult over the whole mesh.  Workload: the synthetic periodic Taylor-Green
+box of SURVEY.md section 8(d) (config C5): n^3 affine hexes per GPU (default n = 96 -> 56.6 M nodes,
+283 M unknowns per GPU), weak-scaled over a 2x1x1 / 2x2x1 / 2x2x2 rank grid with NCCL face-neighbour
+exchange.  Inputs (2.3 GB per field vector) are far larger than the 126 MB L2, so no L2 flush is needed
+between iterations.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...     # the reference's CPU algorithm (oracle) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "rhs_dof_evals_per_s"
+UNIT = "DOF-evals/s"
+B_PER_DOF = 360.0  # 8*neq*(3+2*dim): U + write gradUp + U + gradUp + write dU/dt
+# algorithmic bytes per DOF for each kernel class ("kernels and rooflines")
+KERNEL_BYTES = {"prim": 80.0, "grad": 160.0, "face_flux": 160.0, "elem_resid": 200.0}
+PROC_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+PI = float(np.pi)
+
+
+def tgv_visc_mult(Re=1600.0):
+    """viscosityMultiplier giving Re = rho0 V0 L / mu = 1600 with L = 1 (box 2 pi), Sutherland mu at T0."""
+    rho0, p0, gamma, R = 1.2, 101300.0, 1.4, 287.058
+    T0 = p0 / (rho0 * R)
+    V0 = 0.1 * np.sqrt(gamma * p0 / rho0)
+    mu_s = 1.458e-6 * T0 ** 1.5 / (T0 + 110.4)
+    return float(rho0 * V0 / Re / mu_s)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k] == "Active":
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(n, nthreads, evals=3, eq=1):
+    """The reference's CPU algorithm (dense per-element operators, per-quadrature-point physics calls)
+    timed on the host cores: oracle/_ref (reference object code for the physics) when present, else the
+    port.  Returns (DOF-evals/s, kind, ndofs)."""
+    import oracle_api
+    import tps_b200
+    from common import tgv_state
+    kind = "ref" if os.path.exists(os.path.join(oracle_api.ORACLE_DIR, "_ref", "liboracle_ref.so")) else "port"
+    if kind == "port" and not os.path.exists(os.path.join(oracle_api.ORACLE_DIR, "liboracle.so")):
+        oracle_api.build()
+    m = tps_b200.cartesian_hex_mesh(n, n, n, lo=(-PI,) * 3, hi=(PI,) * 3)
+    orc = oracle_api.Oracle(3, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(eq, tgv_visc_mult()), nthreads=nthreads, kind=kind)
+    U = tgv_state(orc.node_coords(), perturb=0.0)
+    orc.mult(U)
+    t0 = time.perf_counter()
+    for _ in range(evals):
+        orc.mult(U)
+    dt = (time.perf_counter() - t0) / evals
+    return orc.N / dt, ("reference" if kind == "ref" else "port"), orc.N, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
+    if rank != 0:
+        return
+    import oracle_api
+    import tps_b200
+    from common import tgv_state
+    nthreads = os.cpu_count()
+    n = args.cpu_n
+    kind = "ref" if os.path.exists(os.path.join(oracle_api.ORACLE_DIR, "_ref", "liboracle_ref.so")) else "port"
+    if kind == "port" and not os.path.exists(os.path.join(oracle_api.ORACLE_DIR, "liboracle.so")):
+        oracle_api.build()
+    m = tps_b200.cartesian_hex_mesh(n, n, n, lo=(-PI,) * 3, hi=(PI,) * 3)
+    orc = oracle_api.Oracle(3, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(1, tgv_visc_mult()), nthreads=nthreads, kind=kind)
+    U = tgv_state(orc.node_coords(), perturb=0.0)
+    for _ in range(args.warmup):
+        orc.mult(U)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.mult(U)
+    el = time.perf_counter() - t0
+    val = orc.N * args.steps / el
+    sample = f"TGV box {n}^3 hexes p=3 ({orc.N} DG nodes), {args.steps} RHS evaluations, {nthreads} OpenMP threads"
+    k = "reference" if kind == "ref" else "port"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, (1, 1, 1), sample_n=n),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": k, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, grid, sample_n=None):
+    n = args.n
+    cfg = {"workload": "C5 synthetic periodic 3-D hex box (compressible Taylor-Green), DG p=3 GL/GL, dry-air "
+                       "Navier-Stokes, Re=1600, M0=0.1",
+           "elements_per_gpu": f"{n}^3", "global_elements": f"{n * grid[0]}x{n * grid[1]}x{n * grid[2]}",
+           "order": 3, "num_equation": 5, "rank_grid": "x".join(map(str, grid)),
+           "l2_policy": "inputs (2.3 GB per state vector at 96^3) exceed the 126 MB L2; no flush needed"}
+    if sample_n is not None:
+        cfg["cpu_sample_elements"] = f"{sample_n}^3"
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=96, help="elements per direction per GPU")
+    ap.add_argument("--cpu-n", type=int, default=12, help="elements per direction of the CPU-baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import tps_b200
+    from tps_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the RHS path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world not in PROC_GRID:
+        raise SystemExit(f"unsupported world size {world}")
+    grid = PROC_GRID[world]
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf = capi.C.create_string_buffer(128)
+            assert tps_b200.lib().tpsb_comm_get_unique_id(buf) == 0
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        cptr = capi.C.c_void_p()
+        rc = tps_b200.lib().tpsb_comm_init_rank(bytes(uid.cpu().numpy().tobytes()), world, rank, local_rank,
+                                                capi.C.byref(cptr))
+        assert rc == 0, "tpsb_comm_init_rank failed"
+        comm = cptr
+
+    n = args.n
+    gn = (n * grid[0], n * grid[1], n * grid[2])
+    lo = tuple(-PI * g for g in grid)
+    hi = tuple(PI * g for g in grid)
+    phys = tps_b200.Physics.dry_air(1, tgv_visc_mult())
+    t_setup = time.perf_counter()
+    if world == 1:
+        mesh = tps_b200.cartesian_hex_mesh(n, n, n, lo=lo, hi=hi, order_mode=1)
+        op = tps_b200.RhsOperator(mesh, order=3, physics=phys, device=local_rank)
+        NE = n ** 3
+    else:
+        mesh = tps_b200.cartesian_hex_partition(gn, grid, rank, lo=lo, hi=hi, order_mode=1)
+        halo = tps_b200.make_halo_desc(mesh, comm)
+        op = tps_b200.RhsOperator(mesh, order=3, physics=phys, device=local_rank, halo=halo,
+                                  num_nbr_elems=mesh["num_nbr_elems"])
+        NE = mesh["num_elems"]
+    t_setup = time.perf_counter() - t_setup
+    N = op.N
+
+    # Taylor-Green initial state evaluated on the device from the element vertices
+    T = capi.ref_tables(3)
+    xn = torch.from_numpy(T["xn"]).to(dev)
+    ii = torch.arange(64, device=dev)
+    xi = torch.stack([xn[ii % 4], xn[(ii // 4) % 4], xn[ii // 16]], 1)
+    hv = torch.tensor([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]],
+                      dtype=torch.float64, device=dev)
+    shp = torch.ones(64, 8, dtype=torch.float64, device=dev)
+    for d in range(3):
+        shp = shp * torch.where(hv[None, :, d] > 0, xi[:, None, d], 1.0 - xi[:, None, d])
+    ev = torch.from_numpy(np.ascontiguousarray(mesh["elem_xyz"][:NE])).to(dev)
+    U = torch.empty(5 * N, dtype=torch.float64, device=dev)
+    rho0, p0, gamma = 1.2, 101300.0, 1.4
+    V0 = 0.1 * float(np.sqrt(gamma * p0 / rho0))
+    chunk = 1 << 17
+    for e0 in range(0, NE, chunk):
+        e1 = min(NE, e0 + chunk)
+        X = torch.einsum("na,ead->end", shp, ev[e0:e1]).reshape(-1, 3)
+        x, y, z = X[:, 0], X[:, 1], X[:, 2]
+        u = V0 * torch.sin(x) * torch.cos(y) * torch.cos(z)
+        v = -V0 * torch.cos(x) * torch.sin(y) * torch.cos(z)
+        p = p0 + rho0 * V0 * V0 / 16.0 * (torch.cos(2 * x) + torch.cos(2 * y)) * (torch.cos(2 * z) + 2.0)
+        sl = slice(e0 * 64, e1 * 64)
+        U[0 * N:1 * N][sl] = rho0
+        U[1 * N:2 * N][sl] = rho0 * u
+        U[2 * N:3 * N][sl] = rho0 * v
+        U[3 * N:4 * N][sl] = 0.0
+        U[4 * N:5 * N][sl] = p / (gamma - 1.0) + 0.5 * rho0 * (u * u + v * v)
+    del ev
+    Y = torch.empty_like(U)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        op.Mult(U, Y)
+    barrier()
+    l0 = op.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        op.Mult(U, Y)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = op.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    clocks = sampler.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(Y).all().item())
+    N_global = N * world
+    value = N_global * args.steps / (ms * 1e-3)
+
+    # per-kernel device timers (separate, untimed pass): the dominant kernel's own roofline
+    op.set_profiling(True)
+    op.kernel_times()
+    for _ in range(3):
+        op.Mult(U, Y)
+    kt = op.kernel_times()
+    op.set_profiling(False)
+    per_launch = {k: (v[0] / max(v[1], 1)) for k, v in kt.items() if v[1] > 0}
+    per_step = {k: v[0] / 3.0 for k, v in kt.items() if v[1] > 0}
+    dom = max((k for k in per_step if k in KERNEL_BYTES), key=lambda k: per_step[k])
+    peak, peak_src = peaks()
+    dom_launches_per_step = kt[dom][1] / 3.0
+    dom_bytes_per_launch = KERNEL_BYTES[dom] * N / dom_launches_per_step
+    achieved = dom_bytes_per_launch / (per_launch[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes_per_launch, "launch_ms": per_launch[dom],
+                "kernel_share_of_step": per_step[dom] / sum(per_step.values()),
+                "kernel_ms_per_step": per_step}
+    step_gbs = B_PER_DOF * (N * args.steps / (ms * 1e-3)) / 1e9  # per GPU
+    roofline_step = {"bound": "hbm", "bytes_per_dof_eval": B_PER_DOF, "achieved": step_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0}
+
+    # end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    try:
+        hx = torch.empty(5 * N, dtype=torch.float64, pin_memory=True)
+        hy = torch.empty(5 * N, dtype=torch.float64, pin_memory=True)
+        hx.copy_(U)
+        op.mult_host(hx, hy)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            op.mult_host(hx, hy)
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": N_global * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": int(5 * N * 8) * world,
+               "d2h_bytes_per_step": int(5 * N * 8) * world, "steps": args.e2e_steps,
+               "api": "tpsb_rhs_mult_host (pinned host x -> device, Mult, y -> pinned host)"}
+        del hx, hy
+    except Exception as ex:  # pinned allocation can fail on small hosts
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nthreads = os.cpu_count()
+        val, kind, nd, dt = cpu_baseline(args.cpu_n, nthreads)
+        cpu = {"value": val, "unit": UNIT, "cores": nthreads, "kind": kind,
+               "sample": f"TGV box {args.cpu_n}^3 hexes p=3 ({nd} DG nodes), 3 RHS evaluations of {dt:.2f} s, "
+                         f"{nthreads} OpenMP threads; dense per-element operators as in the reference CPU path"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, grid),
+            "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "finite": finite, "setup_s": t_setup, "dofs_per_gpu": N,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -163,6 +163,23 @@ int tpsb_mk_cartesian_hex(int nx, int ny, int nz, const double lo[3], const doub
 int tpsb_mk_build_faces(int num_elems, const int *elem_verts, int *face_el1, int *face_el2, int *face_inf1,
                         int *face_inf2);
 
+/* Structured block partition of the same box over a procs[0] x procs[1] x procs[2] rank grid (rank index
+ * x-fastest): the stand-in for Mesh::GeneratePartitioning + ParMesh's face-neighbour tables
+ * (src/M2ulPhyS.cpp:332,362,421; ExchangeFaceNbrData).  Local elements come first, then the
+ * face-neighbour (halo) elements grouped by owner rank and sorted by global element id -- the order in
+ * which the owner lists them in its send_elems, so one contiguous message per peer suffices.
+ * Call once with all array pointers NULL to obtain the sizes, then with arrays of at least:
+ *   elem_verts 8*(ne+nh) ints, elem_xyz 24*(ne+nh) doubles, elem_gid (ne+nh) int64 (global
+ *   lexicographic element id), face_* 6*(ne+nh) ints each, nbr_rank/num peers (<= 26),
+ *   send_offset/recv_offset peers+1, send_elems num_send.                                          */
+typedef struct {
+  int num_elems, num_nbr_elems, num_faces, num_nbr_ranks, num_send;
+} tpsb_mk_part_sizes;
+int tpsb_mk_partition(const int n[3], const double lo[3], const double hi[3], const int periodic[3],
+                      const int procs[3], int rank, int order_mode, tpsb_mk_part_sizes *sizes, int *elem_verts,
+                      double *elem_xyz, int64_t *elem_gid, int *face_el1, int *face_el2, int *face_inf1,
+                      int *face_inf2, int *nbr_rank, int *send_offset, int *send_elems, int *recv_offset);
+
 /* ---- communicator bootstrap for the NCCL face-neighbour exchange ----
  * unique_id: 128-byte ncclUniqueId produced on rank 0 by tpsb_comm_get_unique_id and broadcast by
  * the host (MPI_Bcast in TPS, torch.distributed in bench.py).                                      */

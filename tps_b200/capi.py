@@ -52,11 +52,16 @@ class HaloDesc(C.Structure):
                 ("send_elems", C.POINTER(C.c_int)), ("recv_offset", C.POINTER(C.c_int)), ("nccl_comm", C.c_void_p)]
 
 
+class PartSizes(C.Structure):
+    _fields_ = [("num_elems", C.c_int), ("num_nbr_elems", C.c_int), ("num_faces", C.c_int),
+                ("num_nbr_ranks", C.c_int), ("num_send", C.c_int)]
+
+
 # every symbol include/tpsb200.h declares (tests check the library exports all of them)
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -102,6 +107,8 @@ def lib():
     L.tpsb_get_ref_tables.argtypes = [C.c_int, dp, C.c_int]
     L.tpsb_mk_cartesian_hex.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, ip, C.c_int, ip, dp]
     L.tpsb_mk_build_faces.argtypes = [C.c_int, ip, ip, ip, ip, ip]
+    L.tpsb_mk_partition.argtypes = [ip, dp, dp, ip, ip, C.c_int, C.c_int, C.POINTER(PartSizes), ip, dp,
+                                    C.POINTER(C.c_int64), ip, ip, ip, ip, ip, ip, ip, ip]
     L.tpsb_comm_get_unique_id.argtypes = [C.c_char_p]
     L.tpsb_comm_init_rank.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.tpsb_comm_destroy.argtypes = [vp]
@@ -158,6 +165,45 @@ def ref_tables(order):
     T["face_cstride"], T["face_side"] = take(6).astype(int), take(6).astype(int)
     T["perm"], T["iperm"] = take(8, np_ * np_).astype(int), take(8, np_ * np_).astype(int)
     return T
+
+
+def cartesian_hex_partition(n, procs, rank, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), periodic=(1, 1, 1),
+                            order_mode=0):
+    """meshkit: this rank's block of the box + face-neighbour (halo) tables (host only)."""
+    L = lib()
+    n_a, p_a = np.asarray(n, dtype=np.int32), np.asarray(procs, dtype=np.int32)
+    lo_a, hi_a = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    per = np.asarray(periodic, dtype=np.int32)
+    sz = PartSizes()
+    args = (_ip(n_a), _dp(lo_a), _dp(hi_a), _ip(per), _ip(p_a), rank, order_mode, C.byref(sz))
+    rc = L.tpsb_mk_partition(*args, None, None, None, None, None, None, None, None, None, None, None)
+    if rc != 0:
+        raise TpsbError(f"tpsb_mk_partition failed ({rc})")
+    ne, nh = sz.num_elems, sz.num_nbr_elems
+    ev = np.zeros((ne + nh, 8), np.int32)
+    xyz = np.zeros((ne + nh, 8, 3))
+    gid = np.zeros(ne + nh, np.int64)
+    f = [np.zeros(6 * (ne + nh), np.int32) for _ in range(4)]
+    nbr = np.zeros(max(sz.num_nbr_ranks, 1), np.int32)
+    so, ro = np.zeros(sz.num_nbr_ranks + 1, np.int32), np.zeros(sz.num_nbr_ranks + 1, np.int32)
+    se = np.zeros(max(sz.num_send, 1), np.int32)
+    rc = L.tpsb_mk_partition(*args, _ip(ev), _dp(xyz), gid.ctypes.data_as(C.POINTER(C.c_int64)), _ip(f[0]), _ip(f[1]),
+                             _ip(f[2]), _ip(f[3]), _ip(nbr), _ip(so), _ip(se), _ip(ro))
+    if rc != 0:
+        raise TpsbError(f"tpsb_mk_partition failed ({rc})")
+    nf = sz.num_faces
+    return dict(num_elems=ne, num_nbr_elems=nh, elem_verts=ev, elem_xyz=xyz, elem_gid=gid,
+                face_el1=f[0][:nf].copy(), face_el2=f[1][:nf].copy(), face_inf1=f[2][:nf].copy(),
+                face_inf2=f[3][:nf].copy(), nbr_rank=nbr[:sz.num_nbr_ranks].copy(), send_offset=so, recv_offset=ro,
+                send_elems=se[:sz.num_send].copy())
+
+
+def make_halo_desc(part, nccl_comm):
+    """tpsb_halo_desc over the arrays of cartesian_hex_partition (keeps them alive on the struct)."""
+    h = HaloDesc(len(part["nbr_rank"]), _ip(part["nbr_rank"]), _ip(part["send_offset"]), _ip(part["send_elems"]),
+                 _ip(part["recv_offset"]), nccl_comm)
+    h._keep = part
+    return h
 
 
 class RhsOperator:

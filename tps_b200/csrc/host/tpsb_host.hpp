@@ -1,0 +1,136 @@
+// Host-side C++ mirror of the reference's operator interface for the RHS path, written above the C ABI
+// (include/tpsb200.h).  Class and method names, argument meaning and call order follow
+// src/rhs_operator.hpp:146-184 (RHSoperator), MFEM's ODESolver (Init/Step, as used at
+// src/M2ulPhyS.cpp:753,2005) and utils/compute_rhs.cpp:102, so TPS's M2ulPhyS can swap its RHSoperator for
+// this one without touching the Runge-Kutta loop.  In a TPS build `Vector` is
+// mfem::Vector with device memory (Read()/Write() return device pointers); here, without MFEM, a minimal
+// device-backed Vector with the same accessors stands in.
+//
+// Error behaviour: like the reference (mfem_error / exit(ERROR), src/rhs_operator.cpp) a failed call is
+// fatal for the solver -- it is reported through tpsb_last_error and raised as std::runtime_error.
+#pragma once
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/tpsb200.h"
+
+namespace tpsb_host {
+
+#ifndef TPSB_HAVE_MFEM
+// Device-backed vector with mfem::Vector's accessor names.
+class Vector {
+  double *d_ = nullptr;
+  int64_t n_ = 0;
+
+ public:
+  Vector() {}
+  explicit Vector(int64_t n) { SetSize(n); }
+  Vector(const Vector &) = delete;
+  Vector &operator=(const Vector &) = delete;
+  ~Vector() {
+    if (d_) cudaFree(d_);
+  }
+  void SetSize(int64_t n) {
+    if (d_) cudaFree(d_);
+    d_ = nullptr;
+    n_ = n;
+    if (n > 0 && cudaMalloc(reinterpret_cast<void **>(&d_), sizeof(double) * n) != cudaSuccess) throw std::runtime_error("Vector: cudaMalloc failed");
+  }
+  int64_t Size() const { return n_; }
+  void UseDevice(bool) {}
+  const double *Read() const { return d_; }
+  double *Write() { return d_; }
+  double *ReadWrite() { return d_; }
+  // host mirrors (explicit copies)
+  void SetFromHost(const std::vector<double> &h) {
+    if (static_cast<int64_t>(h.size()) != n_) SetSize(static_cast<int64_t>(h.size()));
+    cudaMemcpy(d_, h.data(), sizeof(double) * n_, cudaMemcpyHostToDevice);
+  }
+  std::vector<double> HostCopy() const {
+    std::vector<double> h(n_);
+    cudaMemcpy(h.data(), d_, sizeof(double) * n_, cudaMemcpyDeviceToHost);
+    return h;
+  }
+};
+#else
+using Vector = mfem::Vector;
+#endif
+
+// RHSoperator : public TimeDependentOperator   (src/rhs_operator.hpp:52-184)
+class RHSoperator {
+  tpsb_ctx *ctx_ = nullptr;
+  mutable double time_ = 0.0;
+
+  void check(int rc, const char *what) const {
+    if (rc != TPSB_OK) throw std::runtime_error(std::string(what) + ": " + tpsb_last_error(ctx_));
+  }
+
+ public:
+  // The reference constructor takes the FE spaces, integration rules, Fluxes, GasMixture, ... objects
+  // (src/rhs_operator.cpp:38-48); everything the device path needs from them is in these four POD blocks.
+  RHSoperator(const tpsb_mesh_maps &maps, const tpsb_space_desc &space, const tpsb_physics &phys,
+              const tpsb_halo_desc *halo = nullptr, int device = 0, void *cuda_stream = nullptr) {
+    const int rc = tpsb_create(&maps, &space, &phys, halo, device, cuda_stream, &ctx_);
+    if (rc != TPSB_OK) throw std::runtime_error(std::string("RHSoperator: ") + tpsb_last_error(nullptr));
+  }
+  RHSoperator(const RHSoperator &) = delete;
+  virtual ~RHSoperator() { tpsb_destroy(ctx_); }
+
+  int64_t Height() const { return tpsb_num_dofs(ctx_) * tpsb_num_equation(ctx_); }
+  void SetTime(double t) const { time_ = t; }
+  double GetTime() const { return time_; }
+
+  // src/rhs_operator.hpp:157
+  virtual void Mult(const Vector &x, Vector &y) const { check(tpsb_rhs_mult(ctx_, x.Read(), y.Write()), "RHSoperator::Mult"); }
+  // src/rhs_operator.hpp:158-159
+  void updatePrimitives(const Vector &x) const { check(tpsb_update_primitives(ctx_, x.Read()), "updatePrimitives"); }
+  void updateGradients(const Vector &x, const bool &primitiveUpdated) const {
+    check(tpsb_update_gradients(ctx_, x.Read(), primitiveUpdated ? 1 : 0), "updateGradients");
+  }
+  // device views of Up / gradUp (M2ulPhyS::getPrimitiveGF / getGradientGF)
+  const double *getPrimitives() const {
+    double *up = nullptr;
+    check(tpsb_get_fields(ctx_, &up, nullptr), "getPrimitives");
+    return up;
+  }
+  const double *getGradients() const {
+    double *g = nullptr;
+    check(tpsb_get_fields(ctx_, nullptr, &g), "getGradients");
+    return g;
+  }
+  // max_char_speed reference member (src/rhs_operator.hpp:73), reduced on the device
+  double getMaxCharSpeed() const {
+    double v = 0;
+    check(tpsb_get_max_char_speed(ctx_, &v), "getMaxCharSpeed");
+    return v;
+  }
+  tpsb_ctx *context() const { return ctx_; }
+};
+
+// mfem::ODESolver family selected at src/M2ulPhyS.cpp:721-739 (Init + Step as at :753 and :2005).
+class ODESolver {
+ protected:
+  RHSoperator *f_ = nullptr;
+  int scheme_;
+
+ public:
+  explicit ODESolver(int scheme) : scheme_(scheme) {}
+  virtual ~ODESolver() {}
+  virtual void Init(RHSoperator &f) { f_ = &f; }
+  virtual void Step(Vector &x, double &t, double &dt) {
+    const int rc = tpsb_ode_step(f_->context(), x.ReadWrite(), dt, scheme_, 1);
+    if (rc != TPSB_OK) throw std::runtime_error(std::string("ODESolver::Step: ") + tpsb_last_error(f_->context()));
+    t += dt;
+    f_->SetTime(t);
+  }
+};
+struct ForwardEulerSolver : ODESolver { ForwardEulerSolver() : ODESolver(1) {} };
+struct RK2Solver : ODESolver { explicit RK2Solver(double /*a = 1.0*/ = 1.0) : ODESolver(2) {} };
+struct RK3SSPSolver : ODESolver { RK3SSPSolver() : ODESolver(3) {} };
+struct RK4Solver : ODESolver { RK4Solver() : ODESolver(4) {} };
+
+}  // namespace tpsb_host

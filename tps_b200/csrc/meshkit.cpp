@@ -123,6 +123,144 @@ extern "C" int tpsb_mk_build_faces(int num_elems, const int *elem_verts, int *fa
   return nfaces;
 }
 
+extern "C" int tpsb_mk_partition(const int n[3], const double lo[3], const double hi[3], const int periodic[3],
+                                 const int procs[3], int rank, int order_mode, tpsb_mk_part_sizes *sizes,
+                                 int *elem_verts, double *elem_xyz, int64_t *elem_gid, int *face_el1, int *face_el2,
+                                 int *face_inf1, int *face_inf2, int *nbr_rank, int *send_offset, int *send_elems,
+                                 int *recv_offset) {
+  if (!n || !lo || !hi || !periodic || !procs || !sizes) return TPSB_EINVAL;
+  const int nranks = procs[0] * procs[1] * procs[2];
+  if (rank < 0 || rank >= nranks) return TPSB_EINVAL;
+  int nv[3];
+  for (int d = 0; d < 3; d++) {
+    if (procs[d] < 1 || n[d] < procs[d]) return TPSB_EINVAL;
+    if (periodic[d] && n[d] < 3) return TPSB_EINVAL;
+    nv[d] = periodic[d] ? n[d] : n[d] + 1;
+  }
+  const int rc[3] = {rank % procs[0], (rank / procs[0]) % procs[1], rank / (procs[0] * procs[1])};
+  int b0[3], b1[3];
+  for (int d = 0; d < 3; d++) {
+    b0[d] = static_cast<int>(static_cast<int64_t>(n[d]) * rc[d] / procs[d]);
+    b1[d] = static_cast<int>(static_cast<int64_t>(n[d]) * (rc[d] + 1) / procs[d]);
+  }
+  auto owner_of = [&](const int e[3]) {
+    int r[3];
+    for (int d = 0; d < 3; d++) {
+      // inverse of the even split above
+      int q = static_cast<int>((static_cast<int64_t>(e[d]) * procs[d] + procs[d] - 1) / n[d]);
+      while (q > 0 && static_cast<int64_t>(n[d]) * q / procs[d] > e[d]) q--;
+      while (q + 1 < procs[d] && static_cast<int64_t>(n[d]) * (q + 1) / procs[d] <= e[d]) q++;
+      r[d] = q;
+    }
+    return r[0] + procs[0] * (r[1] + procs[1] * r[2]);
+  };
+  auto gid_of = [&](const int e[3]) { return e[0] + static_cast<int64_t>(n[0]) * (e[1] + static_cast<int64_t>(n[1]) * e[2]); };
+  // local elements in visiting order
+  std::vector<int64_t> loc;
+  const int B = order_mode ? 8 : (1 << 30);
+  for (int bz = b0[2]; bz < b1[2]; bz += std::min(B, b1[2] - b0[2]))
+    for (int by = b0[1]; by < b1[1]; by += std::min(B, b1[1] - b0[1]))
+      for (int bx = b0[0]; bx < b1[0]; bx += std::min(B, b1[0] - b0[0]))
+        for (int k = bz; k < std::min<int64_t>(static_cast<int64_t>(bz) + B, b1[2]); k++)
+          for (int j = by; j < std::min<int64_t>(static_cast<int64_t>(by) + B, b1[1]); j++)
+            for (int i = bx; i < std::min<int64_t>(static_cast<int64_t>(bx) + B, b1[0]); i++) {
+              const int e[3] = {i, j, k};
+              loc.push_back(gid_of(e));
+            }
+  const int NE = static_cast<int>(loc.size());
+  std::unordered_map<int64_t, int> lid;
+  lid.reserve(loc.size() * 2);
+  for (int e = 0; e < NE; e++) lid[loc[e]] = e;
+  // halo elements (owner, gid) and send list (peer, local gid)
+  std::vector<std::pair<int, int64_t>> halo, send;
+  for (int e = 0; e < NE; e++) {
+    const int64_t g = loc[e];
+    const int c[3] = {static_cast<int>(g % n[0]), static_cast<int>((g / n[0]) % n[1]),
+                      static_cast<int>(g / (static_cast<int64_t>(n[0]) * n[1]))};
+    for (int d = 0; d < 3; d++)
+      for (int s = -1; s <= 1; s += 2) {
+        int q[3] = {c[0], c[1], c[2]};
+        q[d] += s;
+        if (q[d] < 0 || q[d] >= n[d]) {
+          if (!periodic[d]) continue;
+          q[d] = (q[d] + n[d]) % n[d];
+        }
+        const int ow = owner_of(q);
+        if (ow == rank) continue;
+        halo.emplace_back(ow, gid_of(q));
+        send.emplace_back(ow, g);
+      }
+  }
+  std::sort(halo.begin(), halo.end());
+  halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+  std::sort(send.begin(), send.end());
+  send.erase(std::unique(send.begin(), send.end()), send.end());
+  std::vector<int> peers;
+  for (auto &h : halo)
+    if (peers.empty() || peers.back() != h.first) peers.push_back(h.first);
+  const int NEH = static_cast<int>(halo.size());
+  sizes->num_elems = NE;
+  sizes->num_nbr_elems = NEH;
+  sizes->num_nbr_ranks = static_cast<int>(peers.size());
+  sizes->num_send = static_cast<int>(send.size());
+  // element tables
+  std::vector<int> ev(static_cast<size_t>(NE + NEH) * 8);
+  std::vector<double> xyz_tmp;
+  double *xyz = elem_xyz;
+  if (!xyz) {
+    xyz_tmp.resize(static_cast<size_t>(NE + NEH) * 24);
+    xyz = xyz_tmp.data();
+  }
+  const double h[3] = {(hi[0] - lo[0]) / n[0], (hi[1] - lo[1]) / n[1], (hi[2] - lo[2]) / n[2]};
+  for (int e = 0; e < NE + NEH; e++) {
+    const int64_t g = e < NE ? loc[e] : halo[e - NE].second;
+    if (elem_gid) elem_gid[e] = g;
+    const int c[3] = {static_cast<int>(g % n[0]), static_cast<int>((g / n[0]) % n[1]),
+                      static_cast<int>(g / (static_cast<int64_t>(n[0]) * n[1]))};
+    for (int a = 0; a < 8; a++) {
+      int iv[3];
+      for (int d = 0; d < 3; d++) {
+        iv[d] = c[d] + tpsb::HEX_VERT[a][d];
+        xyz[(static_cast<size_t>(e) * 8 + a) * 3 + d] = lo[d] + iv[d] * h[d];
+      }
+      ev[static_cast<size_t>(e) * 8 + a] = (iv[0] % nv[0]) + nv[0] * ((iv[1] % nv[1]) + nv[1] * (iv[2] % nv[2]));
+    }
+  }
+  // faces over local + halo elements; keep those whose first element is local
+  std::vector<int> f1(static_cast<size_t>(NE + NEH) * 6), f2(f1.size()), i1(f1.size()), i2(f1.size());
+  const int nf_all = tpsb_mk_build_faces(NE + NEH, ev.data(), f1.data(), f2.data(), i1.data(), i2.data());
+  if (nf_all < 0) return TPSB_EINVAL;
+  int nf = 0;
+  for (int f = 0; f < nf_all; f++) {
+    if (f1[f] >= NE) continue;  // halo-only face
+    if (face_el1) {
+      face_el1[nf] = f1[f];
+      face_el2[nf] = f2[f];
+      face_inf1[nf] = i1[f];
+      face_inf2[nf] = i2[f];
+    }
+    nf++;
+  }
+  sizes->num_faces = nf;
+  if (elem_verts) std::copy(ev.begin(), ev.end(), elem_verts);
+  if (nbr_rank && send_offset && send_elems && recv_offset) {
+    size_t hp = 0, sp = 0;
+    for (size_t p = 0; p < peers.size(); p++) {
+      nbr_rank[p] = peers[p];
+      recv_offset[p] = static_cast<int>(hp);
+      send_offset[p] = static_cast<int>(sp);
+      while (hp < halo.size() && halo[hp].first == peers[p]) hp++;
+      while (sp < send.size() && send[sp].first == peers[p]) {
+        send_elems[sp] = lid[send[sp].second];
+        sp++;
+      }
+    }
+    recv_offset[peers.size()] = static_cast<int>(hp);
+    send_offset[peers.size()] = static_cast<int>(sp);
+  }
+  return TPSB_OK;
+}
+
 // Flattened RefTables for the tests: [np, nq, xn(np), wn(np), D(np*np), lb(2*np), xq(nq), wq(nq), P(nq*np),
 // face_base(6*np^2), face_cstride(6), face_side(6), perm(8*np^2), iperm(8*np^2)]
 extern "C" int tpsb_get_ref_tables(int order, double *out, int cap) {
