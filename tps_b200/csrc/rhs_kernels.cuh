@@ -38,10 +38,10 @@ struct KernelArgs {
   // geometry / connectivity (device)
   const double *vx;        // [(NE+NEH)][8][3]
   const int *nbr_elem;     // [NE][6] neighbour element (>= NE: halo), -1 boundary
-  const int *nbr_code;     // [NE][6] (nbr local face) | (perm table index << 3), perm index 0-7 perm, 8-15 iperm
+  const int *nbr_code;     // [NE][6] (nbr local face) | (perm code << 3): own face coords -> neighbour face coords
   const int *face_el1, *face_el2, *face_inf1, *face_inf2;  // [NFint] compacted two-sided faces
   const int *el_face;      // [NE][6] compact face id or -1
-  const int *el_face_code; // [NE][6] side | (ori << 1)
+  const int *el_face_code; // [NE][6] side | (perm code own -> face coords << 1)
   // fields
   const double *U;         // [NEQ][N]
   const double *Uhalo;     // [NEH][NEQ][dof]  (element-major: one contiguous block per peer)
@@ -109,7 +109,7 @@ __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int 
 // grad_kernel / face_flux_kernel / elem_resid_kernel are templates on NP = p+1; see rhs_kernels.cu
 template <int NP, int EPB>
 __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list);
-template <int NP, int FPB>
+template <int NP, int FPB, int NT>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
 template <int NP, int EPB>
 __global__ void elem_resid_kernel(KernelArgs a);

@@ -44,111 +44,178 @@ __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Index helpers.  All per-face parameters come from c_T.face_par[] / perm codes staged in shared
+// memory: constant-bank reads with thread-dependent indices serialise on the ADU pipe (measured: 89 %
+// ADU utilisation in the first version of grad_kernel), so nothing below indexes c_T divergently.
+struct FacePar {
+  int as, at, an, ss, st, side;
+};
+__device__ __forceinline__ FacePar decode_face(int par) {
+  FacePar f;
+  f.as = par & 3;
+  f.at = (par >> 2) & 3;
+  f.an = (par >> 4) & 3;
+  f.ss = (par >> 6) & 1;
+  f.st = (par >> 7) & 1;
+  f.side = (par >> 8) & 1;
+  return f;
+}
+template <int NP>
+__device__ __forceinline__ int axis_stride(int axis) {
+  return axis == 0 ? 1 : (axis == 1 ? NP : NP * NP);
+}
+// element node index of face node (a,b) at normal index c = 0, and the stride along the normal
+template <int NP>
+__device__ __forceinline__ int face_node_base(const FacePar &f, int a, int b) {
+  const int ia = f.ss ? a : NP - 1 - a, ib = f.st ? b : NP - 1 - b;
+  return ia * axis_stride<NP>(f.as) + ib * axis_stride<NP>(f.at);
+}
+template <int NP>
+__device__ __forceinline__ void apply_perm(int code, int a, int b, int &a2, int &b2) {
+  const int x = (code & 1) ? b : a, y = (code & 1) ? a : b;
+  a2 = (code & 2) ? NP - 1 - x : x;
+  b2 = (code & 4) ? NP - 1 - y : y;
+}
+__device__ __forceinline__ int pick3(int axis, int i, int j, int k) { return axis == 0 ? i : (axis == 1 ? j : k); }
+
+// Affine (parallelepiped) element: constant Jacobian from three edge vectors.
+__device__ __forceinline__ void hex_jacobian_affine(const double *v, double *J) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    J[i + 0] = v[1 * 3 + i] - v[i];
+    J[i + 3] = v[3 * 3 + i] - v[i];
+    J[i + 6] = v[4 * 3 + i] - v[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // grad_kernel: EPB elements per CTA, one thread per node.
 //   volume : gradUp_j = sum_r inv(J)_rd * (D applied along r)             [= Me^-1 Ke Up, collocated]
 //   faces  : + l_c(face)/(w_c |J|) * 1/2 (Up_nbr - Up_own)(a,b) * n_d     [= Me^-1 of the face term of
 //            GradFaceIntegrator (src/faceGradientIntegration.cpp:119-137); on an affine element the
 //            (p+2)^2-point face rule integrates phi_i * jump exactly, so it collapses onto the
 //            (p+1)^2 face nodes]
-// Only parallelepiped elements take this path; create() rejects other meshes for now.
+// Neighbour traces are extrapolated straight from global memory (L2-resident neighbour data), own
+// traces from shared memory; all six faces are processed between two barriers.
 template <int NP, int EPB>
 __global__ void __launch_bounds__(NP *NP *NP *EPB)
     grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sUp[EPB][NEQ][ND];
-  __shared__ double sNb[EPB][NEQ][ND];
-  __shared__ double sJ[EPB][NEQ][NF2];
+  __shared__ double sJ[EPB][6][NEQ][NF2];
   __shared__ double sVx[EPB][24];
+  __shared__ double sNor[EPB][6][3];
+  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
+  __shared__ int sNbr[EPB][6], sCode[EPB][6], sFp[6];
   const int le = threadIdx.x / ND, n = threadIdx.x % ND;
   const int slot = blockIdx.x * EPB + le;
   const bool active = slot < elem_count;
   const int e = active ? (elem_list ? elem_list[elem_begin + slot] : elem_begin + slot) : 0;
   const long long N = a.N;
+  if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
   if (active) {
 #pragma unroll
     for (int f = 0; f < NEQ; f++) sUp[le][f][n] = a.Up[static_cast<long long>(e) * ND + n + f * N];
     for (int t = n; t < 24; t += ND) sVx[le][t] = a.vx[static_cast<long long>(e) * 24 + t];
+    for (int t = n; t < 6; t += ND) {
+      sNbr[le][t] = a.nbr_elem[e * 6 + t];
+      sCode[le][t] = a.nbr_code[e * 6 + t];
+    }
   }
   __syncthreads();
   const int i = n % NP, j = (n / NP) % NP, k = n / (NP * NP);
   double g[NEQ][DIM];
-  double J[9], A[9], det = 1.0;
+  double det = 1.0;
   if (active) {
-    hex_jacobian(sVx[le], c_T.xn[i], c_T.xn[j], c_T.xn[k], J);
-    det = det3(J);
-    adj3(J, A);
-    const double idet = 1.0 / det;
-#pragma unroll
-    for (int f = 0; f < NEQ; f++) {
-      double d0 = 0, d1 = 0, d2 = 0;
-#pragma unroll
-      for (int m = 0; m < NP; m++) {
-        d0 += c_T.D[i][m] * sUp[le][f][m + NP * j + NP * NP * k];
-        d1 += c_T.D[j][m] * sUp[le][f][i + NP * m + NP * NP * k];
-        d2 += c_T.D[k][m] * sUp[le][f][i + NP * j + NP * NP * m];
-      }
-      // inv(J)(r,d) = A[r + 3 d] / det
-#pragma unroll
-      for (int d = 0; d < DIM; d++) g[f][d] = (d0 * A[0 + 3 * d] + d1 * A[1 + 3 * d] + d2 * A[2 + 3 * d]) * idet;
-    }
-  }
-  for (int lf = 0; lf < 6; lf++) {
-    const int nbr = active ? a.nbr_elem[e * 6 + lf] : -1;
-    const int code = active ? a.nbr_code[e * 6 + lf] : 0;
-    __syncthreads();  // previous face done with sNb / sJ
-    if (nbr >= 0) {
-      if (nbr < a.NE) {
-#pragma unroll
-        for (int f = 0; f < NEQ; f++) sNb[le][f][n] = a.Up[static_cast<long long>(nbr) * ND + n + f * N];
-      } else {
-#pragma unroll
-        for (int f = 0; f < NEQ; f++)
-          sNb[le][f][n] = a.UpHalo[(static_cast<long long>(nbr - a.NE) * NEQ + f) * ND + n];
-      }
-    }
-    __syncthreads();
-    if (active) {
-      const int side = c_T.face_side[lf], cs = c_T.face_cstride[lf];
-      const int lf2 = code & 7, pidx = code >> 3;
-      const int side2 = c_T.face_side[lf2], cs2 = c_T.face_cstride[lf2];
-      for (int t = n; t < NEQ * NF2; t += ND) {
-        const int f = t / NF2, ab = t % NF2;
-        double own = 0;
-        const int b0 = c_T.face_base[lf][ab];
-#pragma unroll
-        for (int c = 0; c < NP; c++) own += c_T.lb[side][c] * sUp[le][f][b0 + c * cs];
-        double jump = 0.0;  // boundary faces: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
-        if (nbr >= 0) {
-          const int ab2 = (pidx < 8) ? c_T.perm[pidx][ab] : c_T.iperm[pidx - 8][ab];
-          const int b2 = c_T.face_base[lf2][ab2];
-          double oth = 0;
-#pragma unroll
-          for (int c = 0; c < NP; c++) oth += c_T.lb[side2][c] * sNb[le][f][b2 + c * cs2];
-          jump = 0.5 * (oth - own);
-        }
-        sJ[le][f][ab] = jump;
-      }
-    }
-    __syncthreads();
-    if (active) {
-      // outward area-weighted normal of own local face lf (affine: constant over the face)
+    // outward area-weighted normals of the six faces (affine: constant over the face)
+    for (int lf = n; lf < 6; lf += ND) {
       double Xf[12], nor[3];
 #pragma unroll
       for (int q = 0; q < 4; q++)
 #pragma unroll
         for (int d = 0; d < 3; d++) Xf[q * 3 + d] = sVx[le][c_T.face_vert[lf][q] * 3 + d];
       face_normal(Xf, 0.5, 0.5, nor);
-      const int ab = c_T.node_ab[lf][n], c = c_T.node_c[lf][n];
-      const double coef = c_T.lb[c_T.face_side[lf]][c] / (c_T.wn[c] * det);
+      sNor[le][lf][0] = nor[0];
+      sNor[le][lf][1] = nor[1];
+      sNor[le][lf][2] = nor[2];
+    }
+    double J[9], A[9];
+    hex_jacobian_affine(sVx[le], J);
+    det = det3(J);
+    adj3(J, A);
+    const double idet = 1.0 / det;
+    double dI[NP], dJ[NP], dK[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+      dI[m] = sD[i][m];
+      dJ[m] = sD[j][m];
+      dK[m] = sD[k][m];
+    }
+#pragma unroll
+    for (int f = 0; f < NEQ; f++) {
+      double d0 = 0, d1 = 0, d2 = 0;
+#pragma unroll
+      for (int m = 0; m < NP; m++) {
+        d0 += dI[m] * sUp[le][f][m + NP * j + NP * NP * k];
+        d1 += dJ[m] * sUp[le][f][i + NP * m + NP * NP * k];
+        d2 += dK[m] * sUp[le][f][i + NP * j + NP * NP * m];
+      }
+      // inv(J)(r,d) = A[r + 3 d] / det
+#pragma unroll
+      for (int d = 0; d < DIM; d++) g[f][d] = (d0 * A[0 + 3 * d] + d1 * A[1 + 3 * d] + d2 * A[2 + 3 * d]) * idet;
+    }
+    // face jumps 1/2 (Up_nbr - Up_own) at the face nodes of all six faces: task = (face, face node)
+    for (int t = n; t < 6 * NF2; t += ND) {
+      const int lf = t / NF2, ab = t % NF2, fa = ab % NP, fb = ab / NP;
+      const int nbr = sNbr[le][lf];
+      if (nbr < 0) {  // boundary face: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
+#pragma unroll
+        for (int f = 0; f < NEQ; f++) sJ[le][lf][f][ab] = 0.0;
+        continue;
+      }
+      const FacePar fp = decode_face(sFp[lf]);
+      const int code = sCode[le][lf];
+      const FacePar fq = decode_face(sFp[code & 7]);
+      int a2, b2;
+      apply_perm<NP>(code >> 3, fa, fb, a2, b2);
+      const int b0 = face_node_base<NP>(fp, fa, fb), cs = axis_stride<NP>(fp.an);
+      const int q0 = face_node_base<NP>(fq, a2, b2), qs = axis_stride<NP>(fq.an);
+      const bool local = nbr < a.NE;
+      const double *src = local ? a.Up + static_cast<long long>(nbr) * ND + q0
+                                : a.UpHalo + static_cast<long long>(nbr - a.NE) * NEQ * ND + q0;
+      const long long fstride = local ? N : ND;
 #pragma unroll
       for (int f = 0; f < NEQ; f++) {
-        const double v = coef * sJ[le][f][ab];
+        double own = 0, oth = 0;
 #pragma unroll
-        for (int d = 0; d < DIM; d++) g[f][d] += v * nor[d];
+        for (int c = 0; c < NP; c++) {
+          own += sLb[fp.side][c] * sUp[le][f][b0 + c * cs];
+          oth += sLb[fq.side][c] * __ldg(src + f * fstride + c * qs);
+        }
+        sJ[le][lf][f][ab] = 0.5 * (oth - own);
       }
     }
   }
+  __syncthreads();
   if (active) {
+#pragma unroll
+    for (int lf = 0; lf < 6; lf++) {
+      const FacePar fp = decode_face(sFp[lf]);
+      const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
+      const int ab = (fp.ss ? ia : NP - 1 - ia) + NP * (fp.st ? ib : NP - 1 - ib);
+      const double coef = sLb[fp.side][c] / (sWn[c] * det);
+      const double n0 = sNor[le][lf][0], n1 = sNor[le][lf][1], n2 = sNor[le][lf][2];
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) {
+        const double v = coef * sJ[le][lf][f][ab];
+        g[f][0] += v * n0;
+        g[f][1] += v * n1;
+        g[f][2] += v * n2;
+      }
+    }
 #pragma unroll
     for (int d = 0; d < DIM; d++)
 #pragma unroll
@@ -157,164 +224,207 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB)
 }
 
 // ------------------------------------------------------------------------------------------------
-// face_flux_kernel: FPB faces per CTA, NP^3 threads per face.
+// face_flux_kernel: FPB faces per CTA of NT threads; every phase is a flat task loop over the CTA so
+// that lanes stay packed (40->34 interpolation tasks and 25 flux tasks per face do not fill a warp).
 // Output faceRes[face][eq][a + NP*b] = sum_q w_q phi^face_ab(s_q) * Fhat_eq(s_q)   (face coordinates
 // of Elem1), Fhat = Rusanov(U1,U2,n) - 1/2 (Fv(U1,G1) + Fv(U2,G2)).n with n = CalcOrtho (Elem1 -> Elem2)
 // (src/face_integrator.cpp:282-351).  elem_resid_kernel lifts it into both elements.
-template <int NP, int FPB>
-__global__ void __launch_bounds__(NP *NP *NP *FPB)
-    face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list) {
-  constexpr int ND = NP * NP * NP, NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ;
-  // sN is reused for the quadrature-point values once the traces are extracted
-  constexpr int NS = ND > NQ2 ? ND : NQ2;
-  __shared__ double sN[FPB][2][NFLD][NS];
-  __shared__ double sT[FPB][2][NFLD][NF2];
-  __shared__ double sA[FPB][2][NFLD][NP * NQ];  // [b][alpha]
-  __shared__ double sF[FPB][NEQ][NQ2];
-  __shared__ double sB[FPB][NEQ][NP * NQ];  // [b][alpha]
+//   phase 1  traces of the carried fields of both sides, extrapolated straight from global memory
+//   phase 2  one task per (face, side, field): (p+1)^2 -> (p+2)^2 interpolation entirely in registers
+//   phase 3  one task per (face, quadrature point): numerical flux
+//   phase 4  projection back onto the (p+1)^2 face nodes
+// Carried fields (dry air): U (5), grad u (9), grad T (3); grad rho never enters the dry-air viscous flux.
+constexpr int NFC = NEQ + (NEQ - 1) * DIM;  // 17
+__device__ __forceinline__ int carried_grad_field(int u) {  // u in [NEQ, NFC) -> index into gradUp's NEQ*DIM fields
+  const int r = u - NEQ;
+  return (r / (NEQ - 1)) * NEQ + (r % (NEQ - 1)) + 1;
+}
+
+template <int NP, int FPB, int NT>
+__global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list) {
+  constexpr int NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ, ND = NP * NP * NP;
+  __shared__ double sT[FPB][2][NFC][NF2 + 1];  // +1: conflict-free per-(side,field) row reads
+  __shared__ double sQ[FPB][2][NFC][NQ2];
   __shared__ double sXf[FPB][12];
-  const int lfc = threadIdx.x / ND, n = threadIdx.x % ND;
-  const int slot = blockIdx.x * FPB + lfc;
-  const bool active = slot < face_count;
-  const int fc = active ? (face_list ? face_list[face_begin + slot] : face_begin + slot) : 0;
+  __shared__ double sLb[2][NP];
+  __shared__ const double *sBaseU[FPB][2], *sBaseG[FPB][2];
+  __shared__ long long sStrU[FPB][2], sStrG[FPB][2];
+  __shared__ int sOff[FPB][2][NF2], sCs[FPB][2], sSide[FPB][2], sFc[FPB];
+  static_assert(sizeof(double) * NEQ * (NQ2 + NP * NQ) <= sizeof(double) * 2 * NFC * (NF2 + 1), "sF/sB overlay");
+  const int tid = threadIdx.x;
   const long long N = a.N;
-  int e1 = 0, e2 = 0, lf1 = 0, lf2 = 0, ori = 0;
-  if (active) {
-    e1 = a.face_el1[fc];
-    e2 = a.face_el2[fc];
-    lf1 = a.face_inf1[fc] / 64;
-    lf2 = a.face_inf2[fc] / 64;
-    ori = a.face_inf2[fc] % 64;
-    const long long o1 = static_cast<long long>(e1) * ND + n;
-#pragma unroll
-    for (int f = 0; f < NEQ; f++) sN[lfc][0][f][n] = a.U[o1 + f * N];
-#pragma unroll
-    for (int f = 0; f < NEQ * DIM; f++) sN[lfc][0][NEQ + f][n] = a.gradUp[o1 + f * N];
-    if (e2 < a.NE) {
-      const long long o2 = static_cast<long long>(e2) * ND + n;
-#pragma unroll
-      for (int f = 0; f < NEQ; f++) sN[lfc][1][f][n] = a.U[o2 + f * N];
-#pragma unroll
-      for (int f = 0; f < NEQ * DIM; f++) sN[lfc][1][NEQ + f][n] = a.gradUp[o2 + f * N];
-    } else {
-      const long long k2 = e2 - a.NE;
-#pragma unroll
-      for (int f = 0; f < NEQ; f++) sN[lfc][1][f][n] = a.Uhalo[(k2 * NEQ + f) * ND + n];
-#pragma unroll
-      for (int f = 0; f < NEQ * DIM; f++) sN[lfc][1][NEQ + f][n] = a.gradUpHalo[(k2 * NEQ * DIM + f) * ND + n];
+  if (tid < 2 * NP) sLb[tid / NP][tid % NP] = c_T.lb[tid / NP][tid % NP];
+  // per-face setup: one thread per (face, side, face node)
+  for (int t = tid; t < FPB * 2 * NF2; t += NT) {
+    const int fl = t / (2 * NF2), s = (t / NF2) % 2, ab = t % NF2;
+    const int slot = blockIdx.x * FPB + fl;
+    if (slot >= face_count) {
+      if (s == 0 && ab == 0) sFc[fl] = -1;
+      continue;
     }
-    for (int t = n; t < 12; t += ND)
-      sXf[lfc][t] = a.vx[static_cast<long long>(e1) * 24 + c_T.face_vert[lf1][t / 3] * 3 + t % 3];
+    const int fc = face_list ? face_list[face_begin + slot] : face_begin + slot;
+    const int el = s ? a.face_el2[fc] : a.face_el1[fc];
+    const int inf = s ? a.face_inf2[fc] : a.face_inf1[fc];
+    const FacePar fp = decode_face(c_T.face_par[inf / 64]);
+    int fa = ab % NP, fb = ab / NP;
+    if (s) {
+      int a2, b2;
+      apply_perm<NP>(c_T.perm_code[inf % 64], fa, fb, a2, b2);
+      fa = a2;
+      fb = b2;
+    }
+    sOff[fl][s][ab] = face_node_base<NP>(fp, fa, fb);
+    if (ab == 0) {
+      sCs[fl][s] = axis_stride<NP>(fp.an);
+      sSide[fl][s] = fp.side;
+      if (el < a.NE) {
+        sBaseU[fl][s] = a.U + static_cast<long long>(el) * ND;
+        sBaseG[fl][s] = a.gradUp + static_cast<long long>(el) * ND;
+        sStrU[fl][s] = N;
+        sStrG[fl][s] = N;
+      } else {
+        const long long k2 = el - a.NE;
+        sBaseU[fl][s] = a.Uhalo + k2 * NEQ * ND;
+        sBaseG[fl][s] = a.gradUpHalo + k2 * NEQ * DIM * ND;
+        sStrU[fl][s] = ND;
+        sStrG[fl][s] = ND;
+      }
+      if (s == 0) sFc[fl] = fc;
+    }
+    if (s == 0 && ab < 12) sXf[fl][ab] = a.vx[static_cast<long long>(el) * 24 + c_T.face_vert[inf / 64][ab / 3] * 3 + ab % 3];
+  }
+  if (NF2 < 12) {  // p = 1, 2: fewer face nodes than vertex coordinates
+    __syncthreads();
+    for (int t = tid; t < FPB * 12; t += NT) {
+      const int fl = t / 12, q = t % 12, fc = sFc[fl];
+      if (fc >= 0) sXf[fl][q] = a.vx[static_cast<long long>(a.face_el1[fc]) * 24 + c_T.face_vert[a.face_inf1[fc] / 64][q / 3] * 3 + q % 3];
+    }
   }
   __syncthreads();
   // 1. traces at the (a,b) face nodes, both sides, in face (= Elem1-local) coordinates
-  if (active) {
-    const int side1 = c_T.face_side[lf1], cs1 = c_T.face_cstride[lf1];
-    const int side2 = c_T.face_side[lf2], cs2 = c_T.face_cstride[lf2];
-    for (int t = n; t < 2 * NFLD * NF2; t += ND) {
-      const int s = t / (NFLD * NF2), f = (t / NF2) % NFLD, ab = t % NF2;
-      const int lf = s ? lf2 : lf1, side = s ? side2 : side1, cs = s ? cs2 : cs1;
-      const int abl = s ? c_T.perm[ori][ab] : ab;
-      const int b0 = c_T.face_base[lf][abl];
-      double v = 0;
+  for (int t = tid; t < FPB * 2 * NFC * NF2; t += NT) {
+    const int ab = t % NF2, u = (t / NF2) % NFC, s = (t / (NF2 * NFC)) % 2, fl = t / (2 * NFC * NF2);
+    if (sFc[fl] < 0) continue;
+    const double *src = (u < NEQ ? sBaseU[fl][s] + u * sStrU[fl][s] : sBaseG[fl][s] + carried_grad_field(u) * sStrG[fl][s]) +
+                        sOff[fl][s][ab];
+    const int cs = sCs[fl][s], side = sSide[fl][s];
+    double v = 0;
 #pragma unroll
-      for (int c = 0; c < NP; c++) v += c_T.lb[side][c] * sN[lfc][s][f][b0 + c * cs];
-      sT[lfc][s][f][ab] = v;
-    }
+    for (int c = 0; c < NP; c++) v += sLb[side][c] * __ldg(src + c * cs);
+    sT[fl][s][u][ab] = v;
   }
   __syncthreads();
-  // 2. interpolate along a: A[b][alpha] = sum_a P[alpha][a] T[a + NP b]
-  if (active) {
-    for (int t = n; t < 2 * NFLD * NP; t += ND) {
-      const int s = t / (NFLD * NP), f = (t / NP) % NFLD, b = t % NP;
-      double in[NP];
+  // 2. tensor interpolation to the quadrature points, one (face, side, field) per task, in registers:
+  //    A[b][alpha] = sum_a P[alpha][a] T[a + NP b] ;  Q[alpha + NQ beta] = sum_b P[beta][b] A[b][alpha]
+  for (int t = tid; t < FPB * 2 * NFC; t += NT) {
+    const int u = t % NFC, s = (t / NFC) % 2, fl = t / (2 * NFC);
+    if (sFc[fl] < 0) continue;
+    double A[NP][NQ];
+    {
+      double T[NF2];
 #pragma unroll
-      for (int q = 0; q < NP; q++) in[q] = sT[lfc][s][f][q + NP * b];
+      for (int q = 0; q < NF2; q++) T[q] = sT[fl][s][u][q];
+#pragma unroll
+      for (int b = 0; b < NP; b++)
+#pragma unroll
+        for (int al = 0; al < NQ; al++) {
+          double v = 0;
+#pragma unroll
+          for (int q = 0; q < NP; q++) v += c_T.P[al][q] * T[q + NP * b];
+          A[b][al] = v;
+        }
+    }
+#pragma unroll
+    for (int be = 0; be < NQ; be++)
 #pragma unroll
       for (int al = 0; al < NQ; al++) {
         double v = 0;
 #pragma unroll
-        for (int q = 0; q < NP; q++) v += c_T.P[al][q] * in[q];
-        sA[lfc][s][f][b * NQ + al] = v;
+        for (int b = 0; b < NP; b++) v += c_T.P[be][b] * A[b][al];
+        sQ[fl][s][u][al + NQ * be] = v;
       }
-    }
   }
   __syncthreads();
-  // 3. interpolate along b: Q[alpha + NQ beta] = sum_b P[beta][b] A[b][alpha]   (into sN)
-  if (active) {
-    for (int t = n; t < 2 * NFLD * NQ; t += ND) {
-      const int s = t / (NFLD * NQ), f = (t / NQ) % NFLD, al = t % NQ;
-      double in[NP];
-#pragma unroll
-      for (int q = 0; q < NP; q++) in[q] = sA[lfc][s][f][q * NQ + al];
-#pragma unroll
-      for (int be = 0; be < NQ; be++) {
-        double v = 0;
-#pragma unroll
-        for (int q = 0; q < NP; q++) v += c_T.P[be][q] * in[q];
-        sN[lfc][s][f][al + NQ * be] = v;
-      }
-    }
-  }
-  __syncthreads();
-  // 4. numerical flux at the quadrature points
-  for (int qp = n; active && qp < NQ2; qp += ND) {
+  // sT is dead: reuse it for the weighted fluxes and the half-projected fluxes
+  constexpr int FSTR = 2 * NFC * (NF2 + 1);  // doubles per face in sT
+  // 3. numerical flux at the quadrature points
+  for (int t = tid; t < FPB * NQ2; t += NT) {
+    const int qp = t % NQ2, fl = t / NQ2;
+    if (sFc[fl] < 0) continue;
     const int al = qp % NQ, be = qp / NQ;
-    double u1[NEQ], u2[NEQ], g1[NEQ * DIM], g2[NEQ * DIM], nor[3], fl[NEQ];
+    double u1[NEQ], u2[NEQ], nor[3], fl1[NEQ], fl2[NEQ];
 #pragma unroll
     for (int f = 0; f < NEQ; f++) {
-      u1[f] = sN[lfc][0][f][qp];
-      u2[f] = sN[lfc][1][f][qp];
+      u1[f] = sQ[fl][0][f][qp];
+      u2[f] = sQ[fl][1][f][qp];
     }
-    face_normal(sXf[lfc], c_T.xq[al], c_T.xq[be], nor);
-    dry_riemann_lf(a.phys, u1, u2, nor, fl);
-    if (a.phys.eq_system != 0) {
+    face_normal(sXf[fl], c_T.xq[al], c_T.xq[be], nor);
+    const DryPoint q1 = dry_point(a.phys, u1), q2 = dry_point(a.phys, u2);
+    // Rusanov (riemann_solver.cpp:89-114)
+    const double maxE = fmax(dry_char_speed_pt(a.phys, q1), dry_char_speed_pt(a.phys, q2));
+    dry_conv_dot_n(u1, q1, nor, fl1);
+    dry_conv_dot_n(u2, q2, nor, fl2);
+    const double normag = sqrt(nor[0] * nor[0] + nor[1] * nor[1] + nor[2] * nor[2]);
+    double fx[NEQ];
 #pragma unroll
-      for (int f = 0; f < NEQ * DIM; f++) {
-        g1[f] = sN[lfc][0][NEQ + f][qp];
-        g2[f] = sN[lfc][1][NEQ + f][qp];
+    for (int eq = 0; eq < NEQ; eq++) fx[eq] = 0.5 * (fl1[eq] + fl2[eq]) - 0.5 * maxE * (u2[eq] - u1[eq]) * normag;
+    if (a.phys.eq_system != 0) {  // - 1/2 (Fv1 + Fv2).n  (face_integrator.cpp:331-341)
+      double gu[9], gT[3], v1[NEQ], v2[NEQ];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+#pragma unroll
+        for (int i = 0; i < DIM; i++) gu[i + 3 * d] = sQ[fl][0][NEQ + d * (NEQ - 1) + i][qp];
+        gT[d] = sQ[fl][0][NEQ + d * (NEQ - 1) + 3][qp];
       }
-      double v1[NEQ * DIM], v2[NEQ * DIM];
-      dry_visc_flux(a.phys, u1, g1, v1);
-      dry_visc_flux(a.phys, u2, g2, v2);
+      dry_visc_dot_n(a.phys, q1, gu, gT, nor, v1);
 #pragma unroll
-      for (int eq = 0; eq < NEQ; eq++) {
-        double s = 0;
+      for (int d = 0; d < DIM; d++) {
 #pragma unroll
-        for (int d = 0; d < DIM; d++) s += (-0.5 * (v1[eq + d * NEQ] + v2[eq + d * NEQ])) * nor[d];
-        fl[eq] += s;
+        for (int i = 0; i < DIM; i++) gu[i + 3 * d] = sQ[fl][1][NEQ + d * (NEQ - 1) + i][qp];
+        gT[d] = sQ[fl][1][NEQ + d * (NEQ - 1) + 3][qp];
       }
+      dry_visc_dot_n(a.phys, q2, gu, gT, nor, v2);
+#pragma unroll
+      for (int eq = 1; eq < NEQ; eq++) fx[eq] -= 0.5 * (v1[eq] + v2[eq]);
     }
     const double w = c_T.wq[al] * c_T.wq[be];
+    double *dst = &sT[0][0][0][0] + fl * FSTR;
 #pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) sF[lfc][eq][qp] = fl[eq] * w;
+    for (int eq = 0; eq < NEQ; eq++) dst[eq * NQ2 + qp] = fx[eq] * w;
   }
   __syncthreads();
-  // 5. project back along beta: B[b][alpha] = sum_beta P[beta][b] F[alpha + NQ beta]
-  if (active) {
-    for (int t = n; t < NEQ * NQ; t += ND) {
-      const int eq = t / NQ, al = t % NQ;
-      double in[NQ];
+  // 4a. project back along beta: B[b][alpha] = sum_beta P[beta][b] F[alpha + NQ beta]
+  for (int t = tid; t < FPB * NEQ * NQ; t += NT) {
+    const int al = t % NQ, eq = (t / NQ) % NEQ, fl = t / (NEQ * NQ);
+    if (sFc[fl] < 0) continue;
+    double *base = &sT[0][0][0][0] + fl * FSTR;
+    double in[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; q++) in[q] = sF[lfc][eq][al + NQ * q];
+    for (int q = 0; q < NQ; q++) in[q] = base[eq * NQ2 + al + NQ * q];
 #pragma unroll
-      for (int b = 0; b < NP; b++) {
-        double v = 0;
+    for (int b = 0; b < NP; b++) {
+      double v = 0;
 #pragma unroll
-        for (int q = 0; q < NQ; q++) v += c_T.P[q][b] * in[q];
-        sB[lfc][eq][b * NQ + al] = v;
-      }
+      for (int q = 0; q < NQ; q++) v += c_T.P[q][b] * in[q];
+      base[NEQ * NQ2 + eq * NP * NQ + b * NQ + al] = v;
     }
   }
   __syncthreads();
-  // 6. ... and along alpha, straight to global: R[a + NP b] = sum_alpha P[alpha][a] B[b][alpha]
-  if (active) {
-    for (int t = n; t < NEQ * NF2; t += ND) {
-      const int eq = t / NF2, ab = t % NF2, aa = ab % NP, b = ab / NP;
+  // 4b. ... and along alpha, straight to global: R[a + NP b] = sum_alpha P[alpha][a] B[b][alpha]
+  for (int t = tid; t < FPB * NEQ * NP; t += NT) {
+    const int b = t % NP, eq = (t / NP) % NEQ, fl = t / (NEQ * NP);
+    const int fc = sFc[fl];
+    if (fc < 0) continue;
+    const double *base = &sT[0][0][0][0] + fl * FSTR + NEQ * NQ2 + eq * NP * NQ + b * NQ;
+    double in[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) in[q] = base[q];
+#pragma unroll
+    for (int aa = 0; aa < NP; aa++) {
       double v = 0;
 #pragma unroll
-      for (int q = 0; q < NQ; q++) v += c_T.P[q][aa] * sB[lfc][eq][b * NQ + q];
-      a.faceRes[(static_cast<long long>(fc) * NEQ + eq) * NF2 + ab] = v;
+      for (int q = 0; q < NQ; q++) v += c_T.P[q][aa] * in[q];
+      a.faceRes[(static_cast<long long>(fc) * NEQ + eq) * NF2 + aa + NP * b] = v;
     }
   }
 }
@@ -326,47 +436,67 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB) elem_resid_kernel(KernelArgs 
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
   __shared__ double sVx[EPB][24];
+  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
+  __shared__ int sFace[EPB][6], sFcode[EPB][6], sFp[6];
   __shared__ unsigned long long sMaxBits;
   const int le = threadIdx.x / ND, n = threadIdx.x % ND;
   const int e = blockIdx.x * EPB + le;
   const bool active = e < a.NE;
   const long long N = a.N;
-  if (active)
+  if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
+  if (threadIdx.x == 0) sMaxBits = 0ull;
+  if (active) {
     for (int t = n; t < 24; t += ND) sVx[le][t] = a.vx[static_cast<long long>(e) * 24 + t];
+    for (int t = n; t < 6; t += ND) {
+      sFace[le][t] = a.el_face[e * 6 + t];
+      sFcode[le][t] = a.el_face_code[e * 6 + t];
+    }
+  }
   __syncthreads();
   const int i = n % NP, j = (n / NP) % NP, k = n / (NP * NP);
   double det = 1.0, wnode = 1.0, mcs = 0.0;
   if (active) {
     const long long o = static_cast<long long>(e) * ND + n;
-    double s[NEQ], fcv[NEQ * DIM];
+    double s[NEQ];
 #pragma unroll
     for (int eq = 0; eq < NEQ; eq++) s[eq] = a.U[o + eq * N];
-    dry_conv_flux(a.phys, s, fcv);  // GetFlux, rhs_operator.cpp:532
+    const DryPoint q = dry_point(a.phys, s);
+    mcs = dry_char_speed_pt(a.phys, q);  // rhs_operator.cpp:550
+    double gu[9], gT[3];
     if (a.phys.eq_system != 0) {
-      double g[NEQ * DIM], fv[NEQ * DIM];
 #pragma unroll
-      for (int f = 0; f < NEQ * DIM; f++) g[f] = a.gradUp[o + f * N];
-      dry_visc_flux(a.phys, s, g, fv);
+      for (int d = 0; d < DIM; d++) {
 #pragma unroll
-      for (int f = 0; f < NEQ * DIM; f++) fcv[f] -= fv[f];  // f -= fvisc, rhs_operator.cpp:540
+        for (int c = 0; c < DIM; c++) gu[c + 3 * d] = a.gradUp[o + (1 + c + d * NEQ) * N];
+        gT[d] = a.gradUp[o + (4 + d * NEQ) * N];
+      }
     }
-    mcs = dry_max_char_speed(a.phys, s);  // rhs_operator.cpp:550
     double J[9], A[9];
-    hex_jacobian(sVx[le], c_T.xn[i], c_T.xn[j], c_T.xn[k], J);
+    hex_jacobian_affine(sVx[le], J);
     det = det3(J);
     adj3(J, A);
-    wnode = c_T.wn[i] * c_T.wn[j] * c_T.wn[k];
-    // G[eq][r] = w_k sum_d adjJ(r,d) F[eq][d]     (DomainIntegrator, domain_integrator.cpp:71-97)
+    wnode = sWn[i] * sWn[j] * sWn[k];
+    // G[eq][r] = w_k sum_d adjJ(r,d) (F_c - F_v)[eq][d]: the flux of GetFlux (rhs_operator.cpp:532-540)
+    // contracted with row r of adj(J) (DomainIntegrator, domain_integrator.cpp:71-97)
 #pragma unroll
-    for (int eq = 0; eq < NEQ; eq++)
+    for (int r = 0; r < DIM; r++) {
+      const double ar[3] = {A[r + 0], A[r + 3], A[r + 6]};
+      double fc[NEQ];
+      dry_conv_dot_n(s, q, ar, fc);
+      if (a.phys.eq_system != 0) {
+        double fv[NEQ];
+        dry_visc_dot_n(a.phys, q, gu, gT, ar, fv);
 #pragma unroll
-      for (int r = 0; r < DIM; r++)
-        sG[le][eq][r][n] =
-            wnode * (A[r + 0] * fcv[eq + 0 * NEQ] + A[r + 3] * fcv[eq + 1 * NEQ] + A[r + 6] * fcv[eq + 2 * NEQ]);
+        for (int eq = 1; eq < NEQ; eq++) fc[eq] -= fv[eq];
+      }
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) sG[le][eq][r][n] = wnode * fc[eq];
+    }
   }
   // max characteristic speed: block reduction, one global atomic per CTA
-  if (threadIdx.x == 0) sMaxBits = 0ull;
-  __syncthreads();
   if constexpr ((EPB * ND) % 32 == 0) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mcs = fmax(mcs, __shfl_xor_sync(0xffffffffu, mcs, off));
@@ -378,30 +508,47 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB) elem_resid_kernel(KernelArgs 
   if (threadIdx.x == 0) atomicMax(a.maxCharBits, sMaxBits);
   if (!active) return;
   double z[NEQ];
-  // z_j = sum_r sum_m D[m][j_r] G[eq][r][.. m ..]   (transpose of the collocation derivative)
-#pragma unroll
-  for (int eq = 0; eq < NEQ; eq++) {
-    double v = 0;
+  {
+    // z_j = sum_r sum_m D[m][j_r] G[eq][r][.. m ..]   (transpose of the collocation derivative)
+    double tI[NP], tJ[NP], tK[NP];
 #pragma unroll
     for (int m = 0; m < NP; m++) {
-      v += c_T.D[m][i] * sG[le][eq][0][m + NP * j + NP * NP * k];
-      v += c_T.D[m][j] * sG[le][eq][1][i + NP * m + NP * NP * k];
-      v += c_T.D[m][k] * sG[le][eq][2][i + NP * j + NP * NP * m];
+      tI[m] = sD[m][i];
+      tJ[m] = sD[m][j];
+      tK[m] = sD[m][k];
     }
-    z[eq] = v;
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) {
+      double v = 0;
+#pragma unroll
+      for (int m = 0; m < NP; m++) {
+        v += tI[m] * sG[le][eq][0][m + NP * j + NP * NP * k];
+        v += tJ[m] * sG[le][eq][1][i + NP * m + NP * NP * k];
+        v += tK[m] * sG[le][eq][2][i + NP * j + NP * NP * m];
+      }
+      z[eq] = v;
+    }
   }
   // face residuals: elvect1 -= phi1 Fhat w ; elvect2 += phi2 Fhat w   (face_integrator.cpp:348-350)
-  for (int lf = 0; lf < 6; lf++) {
-    const int fc = a.el_face[e * 6 + lf];
-    if (fc < 0) continue;
-    const int code = a.el_face_code[e * 6 + lf];
-    const int side = code & 1, ori = code >> 1;
-    const int abl = c_T.node_ab[lf][n], c = c_T.node_c[lf][n];
-    const int ab = side ? c_T.iperm[ori][abl] : abl;
-    const double coef = (side ? 1.0 : -1.0) * c_T.lb[c_T.face_side[lf]][c];
-    const double *R = a.faceRes + static_cast<long long>(fc) * NEQ * NF2 + ab;
 #pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) z[eq] += coef * R[eq * NF2];
+  for (int lf = 0; lf < 6; lf++) {
+    const int fc = sFace[le][lf];
+    if (fc < 0) continue;
+    const int code = sFcode[le][lf];
+    const int side = code & 1;
+    const FacePar fp = decode_face(sFp[lf]);
+    const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
+    int fa = fp.ss ? ia : NP - 1 - ia, fb = fp.st ? ib : NP - 1 - ib;
+    if (side) {  // own local face coordinates -> face (Elem1) coordinates
+      int a2, b2;
+      apply_perm<NP>(code >> 1, fa, fb, a2, b2);
+      fa = a2;
+      fb = b2;
+    }
+    const double coef = (side ? 1.0 : -1.0) * sLb[fp.side][c];
+    const double *R = a.faceRes + static_cast<long long>(fc) * NEQ * NF2 + fa + NP * fb;
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) z[eq] += coef * __ldg(R + eq * NF2);
   }
   // y = Me^-1 z, Me = diag(w |J|)   (rhs_operator.cpp:432-448)
   const double im = 1.0 / (wnode * det);
@@ -427,12 +574,12 @@ __global__ void rk3_combine_kernel(long long n, const double *x, const double *y
 }
 
 // explicit instantiations (p = 1, 2, 3)
-#define TPSB_INST(NP, EPB, FPB)                                                                        \
+#define TPSB_INST(NP, EPB, FPB, NTF)                                                                        \
   template __global__ void grad_kernel<NP, EPB>(KernelArgs, int, int, const int *);                    \
-  template __global__ void face_flux_kernel<NP, FPB>(KernelArgs, int, int, const int *);               \
+  template __global__ void face_flux_kernel<NP, FPB, NTF>(KernelArgs, int, int, const int *);          \
   template __global__ void elem_resid_kernel<NP, EPB>(KernelArgs);
-TPSB_INST(4, 4, 1)
-TPSB_INST(3, 8, 2)
-TPSB_INST(2, 16, 4)
+TPSB_INST(4, 4, 4, 256)
+TPSB_INST(3, 8, 4, 128)
+TPSB_INST(2, 16, 8, 128)
 
 }  // namespace tpsb

@@ -46,6 +46,14 @@ struct RefTables {
   // (FaceElementTransformations Loc2), iperm = inverse permutation.
   int perm[8][MAX_NP * MAX_NP];
   int iperm[8][MAX_NP * MAX_NP];
+  // Arithmetic forms of the tables above (what the kernels actually use, no divergent table reads):
+  // face_par[lf] = as | at<<2 | an<<4 | ss<<6 | st<<7 | side<<8, with as/at/an the element axes of the
+  // face's s / t / normal directions and ss/st = 1 when s / t run in the +axis direction.
+  int face_par[6];
+  // perm_code[ori] / iperm_code[ori] = swap | flip_a<<1 | flip_b<<2 : (x,y) = swap ? (b,a) : (a,b),
+  // a' = flip_a ? np-1-x : x, b' = flip_b ? np-1-y : y.
+  int perm_code[8];
+  int iperm_code[8];
 };
 
 inline void gauss_legendre01(int n, double *x, double *w) {
@@ -146,6 +154,7 @@ inline bool build_ref_tables(int p, RefTables &T) {
     T.face_axis[lf] = an;
     for (int q = 0; q < 4; q++) T.face_vert[lf][q] = hv[q];
     T.face_side[lf] = o[an];
+    T.face_par[lf] = as | (at << 2) | (an << 4) | ((es[as] > 0 ? 1 : 0) << 6) | ((et[at] > 0 ? 1 : 0) << 7) | (o[an] << 8);
     T.face_cstride[lf] = stride[an];
     for (int b = 0; b < np; b++)
       for (int a = 0; a < np; a++) {
@@ -185,6 +194,24 @@ inline bool build_ref_tables(int p, RefTables &T) {
         T.iperm[ori][dst] = src;
       }
   }
+  // encode the orientation permutations arithmetically and verify the encoding against the tables
+  for (int ori = 0; ori < 8; ori++)
+    for (int inv = 0; inv < 2; inv++) {
+      const int *tab = inv ? T.iperm[ori] : T.perm[ori];
+      int found = -1;
+      for (int code = 0; code < 8 && found < 0; code++) {
+        bool ok = true;
+        for (int b = 0; b < np && ok; b++)
+          for (int a = 0; a < np && ok; a++) {
+            const int x = (code & 1) ? b : a, y = (code & 1) ? a : b;
+            const int a2 = (code & 2) ? np - 1 - x : x, b2 = (code & 4) ? np - 1 - y : y;
+            ok = tab[a + np * b] == a2 + np * b2;
+          }
+        if (ok) found = code;
+      }
+      if (found < 0) return false;
+      (inv ? T.iperm_code : T.perm_code)[ori] = found;
+    }
   return true;
 }
 

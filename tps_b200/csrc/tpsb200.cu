@@ -238,14 +238,14 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
       return fail(nullptr, TPSB_EINVAL, "face info codes out of range on two-sided face %d", fc);
     }
     nbr_elem[e1 * 6 + lf1] = e2;
-    nbr_code[e1 * 6 + lf1] = lf2 | (ori << 3);  // face coords == own coords: perm[ori]
+    nbr_code[e1 * 6 + lf1] = lf2 | (c->T.perm_code[ori] << 3);  // face coords == own coords: perm[ori]
     el_face[e1 * 6 + lf1] = fc;
-    el_face_code[e1 * 6 + lf1] = 0 | (ori << 1);
+    el_face_code[e1 * 6 + lf1] = 0;
     if (e2 < NE) {
       nbr_elem[e2 * 6 + lf2] = e1;
-      nbr_code[e2 * 6 + lf2] = lf1 | ((8 + ori) << 3);  // own coords -> face coords: iperm[ori]
+      nbr_code[e2 * 6 + lf2] = lf1 | (c->T.iperm_code[ori] << 3);  // own coords -> face coords: iperm[ori]
       el_face[e2 * 6 + lf2] = fc;
-      el_face_code[e2 * 6 + lf2] = 1 | (ori << 1);
+      el_face_code[e2 * 6 + lf2] = 1 | (c->T.iperm_code[ori] << 1);
     } else {
       touches_shared[e1] = 1;
     }
@@ -382,7 +382,7 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   return a;
 }
 
-template <int NP, int EPB, int FPB>
+template <int NP, int EPB, int FPB, int NTF>
 struct Launch {
   static void grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
     if (count <= 0) return;
@@ -392,7 +392,7 @@ struct Launch {
   static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
     if (count <= 0) return;
     ProfScope ps(c, K_FACE);
-    face_flux_kernel<NP, FPB><<<(count + FPB - 1) / FPB, NP * NP * NP * FPB, 0, c->stream>>>(a, begin, count, nullptr);
+    face_flux_kernel<NP, FPB, NTF><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
   }
   static void resid(tpsb_ctx *c, const KernelArgs &a) {
     ProfScope ps(c, K_RESID);
@@ -403,9 +403,9 @@ struct Launch {
 #define DISPATCH(c, CALL)                      \
   do {                                         \
     switch ((c)->np) {                         \
-      case 4: Launch<4, 4, 1>::CALL; break;    \
-      case 3: Launch<3, 8, 2>::CALL; break;    \
-      default: Launch<2, 16, 4>::CALL; break;  \
+      case 4: Launch<4, 4, 4, 256>::CALL; break;    \
+      case 3: Launch<3, 8, 4, 128>::CALL; break;    \
+      default: Launch<2, 16, 8, 128>::CALL; break;  \
     }                                          \
   } while (0)
 
