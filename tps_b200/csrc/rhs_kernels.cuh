@@ -34,6 +34,7 @@ struct KernelArgs {
   long long NH;   // NEH * dof
   int NFint;      // faces with two sides (interior + shared)
   int ND;         // dofs per element
+  int vec_ok;     // all field base pointers 32-byte aligned: 256-bit trace loads allowed
   PhysParams phys;
   // geometry / connectivity (device)
   const double *vx;        // [(NE+NEH)][8][3]

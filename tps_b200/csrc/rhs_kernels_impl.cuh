@@ -78,6 +78,23 @@ __device__ __forceinline__ void apply_perm(int code, int a, int b, int &a2, int 
 }
 __device__ __forceinline__ int pick3(int axis, int i, int j, int k) { return axis == 0 ? i : (axis == 1 ? j : k); }
 
+// Extrapolate one line of NP nodal values (stride cs doubles) to the face: sum_c lb[c] * r[c*cs].
+// Faces whose normal is the element's x axis have the NP values contiguous; for p = 3 they are one
+// 32-byte sector, fetched with a single 256-bit load (LDG.E.256 on sm_100a) instead of four strided
+// 8-byte loads that each touch the same sector.  vec_ok: all field base pointers are 32-byte aligned.
+template <int NP>
+__device__ __forceinline__ double trace_line(const double *r, int cs, const double *lb, bool vec_ok) {
+  if (NP == 4 && cs == 1 && vec_ok) {
+    double x0, x1, x2, x3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x0), "=d"(x1), "=d"(x2), "=d"(x3) : "l"(r));
+    return lb[0] * x0 + lb[1] * x1 + lb[2] * x2 + lb[3] * x3;
+  }
+  double v = 0;
+#pragma unroll
+  for (int c = 0; c < NP; c++) v += lb[c] * __ldg(r + c * cs);
+  return v;
+}
+
 // Affine (parallelepiped) element: constant Jacobian from three edge vectors.
 __device__ __forceinline__ void hex_jacobian_affine(const double *v, double *J) {
 #pragma unroll
@@ -189,12 +206,10 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB)
       const long long fstride = local ? N : ND;
 #pragma unroll
       for (int f = 0; f < NEQ; f++) {
-        double own = 0, oth = 0;
+        double own = 0;
 #pragma unroll
-        for (int c = 0; c < NP; c++) {
-          own += sLb[fp.side][c] * sUp[le][f][b0 + c * cs];
-          oth += sLb[fq.side][c] * __ldg(src + f * fstride + c * qs);
-        }
+        for (int c = 0; c < NP; c++) own += sLb[fp.side][c] * sUp[le][f][b0 + c * cs];
+        const double oth = trace_line<NP>(src + f * fstride, qs, sLb[fq.side], a.vec_ok != 0);
         sJ[le][lf][f][ab] = 0.5 * (oth - own);
       }
     }
@@ -301,17 +316,26 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
     }
   }
   __syncthreads();
-  // 1. traces at the (a,b) face nodes, both sides, in face (= Elem1-local) coordinates
-  for (int t = tid; t < FPB * 2 * NFC * NF2; t += NT) {
-    const int ab = t % NF2, u = (t / NF2) % NFC, s = (t / (NF2 * NFC)) % 2, fl = t / (2 * NFC * NF2);
+  // 1. traces at the (a,b) face nodes, both sides, in face (= Elem1-local) coordinates:
+  //    one task per (face, side, face node) sweeping all carried fields, so the index arithmetic is
+  //    paid once per 17 line extrapolations (it was 57 % of the instructions when paid per field)
+  for (int t = tid; t < FPB * 2 * NF2; t += NT) {
+    const int ab = t % NF2, s = (t / NF2) % 2, fl = t / (2 * NF2);
     if (sFc[fl] < 0) continue;
-    const double *src = (u < NEQ ? sBaseU[fl][s] + u * sStrU[fl][s] : sBaseG[fl][s] + carried_grad_field(u) * sStrG[fl][s]) +
-                        sOff[fl][s][ab];
-    const int cs = sCs[fl][s], side = sSide[fl][s];
-    double v = 0;
+    const int off = sOff[fl][s][ab], cs = sCs[fl][s];
+    const double *lb = sLb[sSide[fl][s]];
+    const bool vec = a.vec_ok != 0;
+    const double *pu = sBaseU[fl][s] + off;
+    const long long su = sStrU[fl][s], sg = sStrG[fl][s];
+    double *dst = &sT[fl][s][0][ab];
 #pragma unroll
-    for (int c = 0; c < NP; c++) v += sLb[side][c] * __ldg(src + c * cs);
-    sT[fl][s][u][ab] = v;
+    for (int u = 0; u < NEQ; u++) dst[u * (NF2 + 1)] = trace_line<NP>(pu + u * su, cs, lb, vec);
+    const double *pg = sBaseG[fl][s] + off;
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+      for (int i = 0; i < NEQ - 1; i++)
+        dst[(NEQ + d * (NEQ - 1) + i) * (NF2 + 1)] = trace_line<NP>(pg + (d * NEQ + i + 1) * sg, cs, lb, vec);
   }
   __syncthreads();
   // 2. tensor interpolation to the quadrature points, one (face, side, field) per task, in registers:
@@ -574,12 +598,6 @@ __global__ void rk3_combine_kernel(long long n, const double *x, const double *y
 }
 
 // explicit instantiations (p = 1, 2, 3)
-#define TPSB_INST(NP, EPB, FPB, NTF)                                                                        \
-  template __global__ void grad_kernel<NP, EPB>(KernelArgs, int, int, const int *);                    \
-  template __global__ void face_flux_kernel<NP, FPB, NTF>(KernelArgs, int, int, const int *);          \
-  template __global__ void elem_resid_kernel<NP, EPB>(KernelArgs);
-TPSB_INST(4, 4, 4, 256)
-TPSB_INST(3, 8, 4, 128)
-TPSB_INST(2, 16, 8, 128)
+// (kernels are instantiated implicitly by the launchers in tpsb200.cu)
 
 }  // namespace tpsb

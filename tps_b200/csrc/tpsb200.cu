@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,6 +51,7 @@ struct tpsb_ctx {
   // ODE / host-staging work vectors (lazy)
   double *d_k = nullptr, *d_yv = nullptr, *d_z = nullptr, *d_hx = nullptr, *d_hy = nullptr;
   long long launches = 0;
+  int tune[3] = {0, 0, 0};
   // per-kernel device timers (tpsb_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[TPSB_NUM_KERNEL_CLASSES];
@@ -157,6 +160,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   ctx = c;
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
+  if (const char *tn = getenv("TPSB_TUNE")) sscanf(tn, "%d,%d,%d", &c->tune[0], &c->tune[1], &c->tune[2]);
   c->order = space->order;
   c->np = space->order + 1;
   c->nd = c->np * c->np * c->np;
@@ -379,35 +383,79 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   a.faceRes = c->d_faceRes;
   a.y = d_y;
   a.maxCharBits = c->d_maxBits;
+  auto al32 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+  a.vec_ok = (al32(d_x) && al32(c->d_Up) && al32(c->d_gradUp) && al32(c->d_Uhalo) && al32(c->d_UpHalo) &&
+              al32(c->d_gradUpHalo) && (c->N % 4 == 0))
+                 ? 1
+                 : 0;
   return a;
 }
 
-template <int NP, int EPB, int FPB, int NTF>
-struct Launch {
-  static void grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
-    if (count <= 0) return;
-    ProfScope ps(c, K_GRAD);
-    grad_kernel<NP, EPB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
-  }
-  static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
-    if (count <= 0) return;
-    ProfScope ps(c, K_FACE);
-    face_flux_kernel<NP, FPB, NTF><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
-  }
-  static void resid(tpsb_ctx *c, const KernelArgs &a) {
-    ProfScope ps(c, K_RESID);
-    elem_resid_kernel<NP, EPB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
-  }
-};
+template <int NP, int EPB>
+static void launch_grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_GRAD);
+  grad_kernel<NP, EPB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
+}
+template <int NP, int FPB, int NTF>
+static void launch_face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_FACE);
+  face_flux_kernel<NP, FPB, NTF><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
+}
+template <int NP, int EPB>
+static void launch_resid(tpsb_ctx *c, const KernelArgs &a) {
+  ProfScope ps(c, K_RESID);
+  elem_resid_kernel<NP, EPB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+}
 
-#define DISPATCH(c, CALL)                      \
-  do {                                         \
-    switch ((c)->np) {                         \
-      case 4: Launch<4, 4, 4, 256>::CALL; break;    \
-      case 3: Launch<3, 8, 4, 128>::CALL; break;    \
-      default: Launch<2, 16, 8, 128>::CALL; break;  \
-    }                                          \
-  } while (0)
+// Launch-shape selection.  p = 3 is the tuned case; tune[] (TPSB_TUNE="g,f,r", development knob) picks
+// among pre-instantiated CTA shapes.
+static void grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
+  if (c->np == 4) {
+    switch (c->tune[0]) {
+      case 1: launch_grad<4, 1>(c, a, begin, count, list); break;
+      case 2: launch_grad<4, 2>(c, a, begin, count, list); break;
+      case 4: launch_grad<4, 4>(c, a, begin, count, list); break;
+      default: launch_grad<4, 1>(c, a, begin, count, list); break;
+    }
+  } else if (c->np == 3) {
+    launch_grad<3, 8>(c, a, begin, count, list);
+  } else {
+    launch_grad<2, 16>(c, a, begin, count, list);
+  }
+}
+static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+  if (c->np == 4) {
+    switch (c->tune[1]) {
+      case 1: launch_face<4, 4, 128>(c, a, begin, count); break;
+      case 2: launch_face<4, 2, 96>(c, a, begin, count); break;
+      case 3: launch_face<4, 4, 192>(c, a, begin, count); break;
+      case 4: launch_face<4, 3, 128>(c, a, begin, count); break;
+      case 5: launch_face<4, 4, 256>(c, a, begin, count); break;
+      default: launch_face<4, 4, 160>(c, a, begin, count); break;
+    }
+  } else if (c->np == 3) {
+    launch_face<3, 4, 128>(c, a, begin, count);
+  } else {
+    launch_face<2, 8, 128>(c, a, begin, count);
+  }
+}
+static void resid(tpsb_ctx *c, const KernelArgs &a) {
+  if (c->np == 4) {
+    switch (c->tune[2]) {
+      case 1: launch_resid<4, 1>(c, a); break;
+      case 2: launch_resid<4, 2>(c, a); break;
+      case 4: launch_resid<4, 4>(c, a); break;
+      default: launch_resid<4, 1>(c, a); break;
+    }
+  } else if (c->np == 3) {
+    launch_resid<3, 8>(c, a);
+  } else {
+    launch_resid<2, 16>(c, a);
+  }
+}
+#define DISPATCH(c, CALL) CALL
 
 static void launch_prim(tpsb_ctx *c, const KernelArgs &a, int halo) {
   const long long cnt = halo ? c->NH : c->N;
