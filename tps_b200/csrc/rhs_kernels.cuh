@@ -108,11 +108,11 @@ __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int 
                             double *dst);
 
 // grad_kernel / face_flux_kernel / elem_resid_kernel are templates on NP = p+1; see rhs_kernels.cu
-template <int NP, int EPB>
+template <int NP, int EPB, int MINB>
 __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list);
 template <int NP, int FPB, int NT>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
-template <int NP, int EPB>
+template <int NP, int EPB, int MINB>
 __global__ void elem_resid_kernel(KernelArgs a);
 
 // y = x + a*k ; z = x + b*k  etc. for the ODE stages

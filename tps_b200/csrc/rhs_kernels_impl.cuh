@@ -114,8 +114,8 @@ __device__ __forceinline__ void hex_jacobian_affine(const double *v, double *J) 
 //            (p+1)^2 face nodes]
 // Neighbour traces are extrapolated straight from global memory (L2-resident neighbour data), own
 // traces from shared memory; all six faces are processed between two barriers.
-template <int NP, int EPB>
-__global__ void __launch_bounds__(NP *NP *NP *EPB)
+template <int NP, int EPB, int MINB>
+__global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
     grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sUp[EPB][NEQ][ND];
@@ -455,13 +455,14 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 
 // ------------------------------------------------------------------------------------------------
 // elem_resid_kernel: EPB elements per CTA, one thread per node.
-template <int NP, int EPB>
-__global__ void __launch_bounds__(NP *NP *NP *EPB) elem_resid_kernel(KernelArgs a) {
+template <int NP, int EPB, int MINB>
+__global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(KernelArgs a) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
   __shared__ double sVx[EPB][24];
   __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
   __shared__ int sFace[EPB][6], sFcode[EPB][6], sFp[6];
+  __shared__ __align__(16) double sR[EPB][6][NEQ * NF2];  // face residual blocks of the six faces (cp.async)
   __shared__ unsigned long long sMaxBits;
   const int le = threadIdx.x / ND, n = threadIdx.x % ND;
   const int e = blockIdx.x * EPB + le;
@@ -480,6 +481,25 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB) elem_resid_kernel(KernelArgs 
     }
   }
   __syncthreads();
+  // asynchronous, coalesced staging of the <= 6 contiguous face-residual blocks (NEQ*NF2 doubles each):
+  // issued now, consumed after the flux evaluation below
+  if (active) {
+    // 16-byte copies when a block is an even number of doubles (p = 1, 3), else 8-byte copies (p = 2)
+    constexpr int W = (NEQ * NF2) % 2 == 0 ? 2 : 1;
+    constexpr int CH = NEQ * NF2 / W;
+    for (int t = n; t < 6 * CH; t += ND) {
+      const int lf = t / CH, ch = t % CH, fc = sFace[le][lf];
+      if (fc >= 0) {
+        const double *g = a.faceRes + static_cast<long long>(fc) * NEQ * NF2 + W * ch;
+        const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(&sR[le][lf][W * ch]));
+        if (W == 2)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g));
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g));
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  }
   const int i = n % NP, j = (n / NP) % NP, k = n / (NP * NP);
   double det = 1.0, wnode = 1.0, mcs = 0.0;
   if (active) {
@@ -528,6 +548,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB) elem_resid_kernel(KernelArgs 
   } else {
     atomicMax(&sMaxBits, static_cast<unsigned long long>(__double_as_longlong(mcs)));
   }
+  asm volatile("cp.async.wait_all;");
   __syncthreads();
   if (threadIdx.x == 0) atomicMax(a.maxCharBits, sMaxBits);
   if (!active) return;
@@ -570,9 +591,9 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB) elem_resid_kernel(KernelArgs 
       fb = b2;
     }
     const double coef = (side ? 1.0 : -1.0) * sLb[fp.side][c];
-    const double *R = a.faceRes + static_cast<long long>(fc) * NEQ * NF2 + fa + NP * fb;
+    const double *R = &sR[le][lf][fa + NP * fb];
 #pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) z[eq] += coef * __ldg(R + eq * NF2);
+    for (int eq = 0; eq < NEQ; eq++) z[eq] += coef * R[eq * NF2];
   }
   // y = Me^-1 z, Me = diag(w |J|)   (rhs_operator.cpp:432-448)
   const double im = 1.0 / (wnode * det);

@@ -391,11 +391,11 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   return a;
 }
 
-template <int NP, int EPB>
+template <int NP, int EPB, int MINB = 1>
 static void launch_grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
   if (count <= 0) return;
   ProfScope ps(c, K_GRAD);
-  grad_kernel<NP, EPB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
+  grad_kernel<NP, EPB, MINB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
 }
 template <int NP, int FPB, int NTF>
 static void launch_face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
@@ -403,10 +403,10 @@ static void launch_face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) 
   ProfScope ps(c, K_FACE);
   face_flux_kernel<NP, FPB, NTF><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
 }
-template <int NP, int EPB>
+template <int NP, int EPB, int MINB = 1>
 static void launch_resid(tpsb_ctx *c, const KernelArgs &a) {
   ProfScope ps(c, K_RESID);
-  elem_resid_kernel<NP, EPB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+  elem_resid_kernel<NP, EPB, MINB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
 }
 
 // Launch-shape selection.  p = 3 is the tuned case; tune[] (TPSB_TUNE="g,f,r", development knob) picks
@@ -414,15 +414,17 @@ static void launch_resid(tpsb_ctx *c, const KernelArgs &a) {
 static void grad(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
   if (c->np == 4) {
     switch (c->tune[0]) {
-      case 1: launch_grad<4, 1>(c, a, begin, count, list); break;
-      case 2: launch_grad<4, 2>(c, a, begin, count, list); break;
-      case 4: launch_grad<4, 4>(c, a, begin, count, list); break;
-      default: launch_grad<4, 1>(c, a, begin, count, list); break;
+      case 1: launch_grad<4, 1, 16>(c, a, begin, count, list); break;
+      case 2: launch_grad<4, 2, 6>(c, a, begin, count, list); break;
+      case 3: launch_grad<4, 2, 8>(c, a, begin, count, list); break;
+      case 4: launch_grad<4, 4, 3>(c, a, begin, count, list); break;
+      case 5: launch_grad<4, 1, 8>(c, a, begin, count, list); break;
+      default: launch_grad<4, 1, 12>(c, a, begin, count, list); break;
     }
   } else if (c->np == 3) {
-    launch_grad<3, 8>(c, a, begin, count, list);
+    launch_grad<3, 8, 3>(c, a, begin, count, list);
   } else {
-    launch_grad<2, 16>(c, a, begin, count, list);
+    launch_grad<2, 16, 4>(c, a, begin, count, list);
   }
 }
 static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
@@ -444,15 +446,17 @@ static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
 static void resid(tpsb_ctx *c, const KernelArgs &a) {
   if (c->np == 4) {
     switch (c->tune[2]) {
-      case 1: launch_resid<4, 1>(c, a); break;
-      case 2: launch_resid<4, 2>(c, a); break;
-      case 4: launch_resid<4, 4>(c, a); break;
-      default: launch_resid<4, 1>(c, a); break;
+      case 1: launch_resid<4, 1, 16>(c, a); break;
+      case 2: launch_resid<4, 2, 5>(c, a); break;
+      case 3: launch_resid<4, 1, 12>(c, a); break;
+      case 4: launch_resid<4, 4, 2>(c, a); break;
+      case 5: launch_resid<4, 2, 6>(c, a); break;
+      default: launch_resid<4, 1, 10>(c, a); break;
     }
   } else if (c->np == 3) {
-    launch_resid<3, 8>(c, a);
+    launch_resid<3, 8, 2>(c, a);
   } else {
-    launch_resid<2, 16>(c, a);
+    launch_resid<2, 16, 4>(c, a);
   }
 }
 #define DISPATCH(c, CALL) CALL
