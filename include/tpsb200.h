@@ -140,6 +140,10 @@ int tpsb_get_element_to_faces(const tpsb_ctx *ctx, int *out);
  * of doubles written (<= cap) or a negative error.                                                */
 int tpsb_get_ref_tables(int order, double *out, int cap);
 
+/* Test hook: device views of internal buffers. which = 0: face residuals [two-sided face][neq][(p+1)^2];
+ * 1: face-trace blocks of the fast path [6*num_elems + shared faces][10][(p+1)^2] (NULL on other paths). */
+int tpsb_debug_buffer(tpsb_ctx *ctx, int which, double **d_ptr, int64_t *count);
+
 /* Per-kernel device timers (the role GRVY timers play in the reference, src/M2ulPhyS.cpp:2146-2155):
  * with profiling on, every launch is bracketed by CUDA events on the context stream; the accumulated
  * milliseconds and launch counts per kernel class are returned in the order

@@ -61,7 +61,7 @@ class PartSizes(C.Structure):
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -100,6 +100,7 @@ def lib():
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_ode_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
     L.tpsb_get_element_to_faces.argtypes = [vp, ip]
+    L.tpsb_debug_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
     L.tpsb_launch_count.restype = C.c_int64
     L.tpsb_launch_count.argtypes = [vp]
     L.tpsb_set_profiling.argtypes = [vp, C.c_int]
@@ -277,6 +278,12 @@ class RhsOperator:
         up, g = C.c_void_p(), C.c_void_p()
         self._chk(self.L.tpsb_get_fields(self.ctx, C.byref(up), C.byref(g)), "tpsb_get_fields")
         return self._view(up.value, self.neq * self.N), self._view(g.value, 3 * self.neq * self.N)
+
+    def debug_buffer(self, which):
+        """Test hook: device view of an internal buffer (0 face residuals, 1 face-trace blocks)."""
+        ptr, cnt = C.c_void_p(), C.c_int64(0)
+        self._chk(self.L.tpsb_debug_buffer(self.ctx, which, C.byref(ptr), C.byref(cnt)), "tpsb_debug_buffer")
+        return self._view(ptr.value, cnt.value) if ptr.value else None
 
     def max_char_speed(self):
         out = C.c_double(0.0)

@@ -1,0 +1,495 @@
+// Fast path of RHSoperator::Mult for the headline configuration: 3-D hexahedra whose elements are all
+// parallelepipeds (constant Jacobian), dry air, Gauss-Legendre nodes and rules.  Included once by tpsb200.cu.
+//
+// Three kernels per evaluation (after prim_kernel):
+//
+//   grad_trace_kernel  per element: BR1 gradient (Gradients::computeGradients, src/gradients.cpp:144-232 +
+//                      GradFaceIntegrator, src/faceGradientIntegration.cpp:40-140) AND the face traces the flux
+//                      kernel needs, written as one contiguous block per (element, local face):
+//                        fields 0-4  trace of the conserved state U
+//                        fields 5-9  trace of the normal-contracted viscous fields
+//                                    s_i = sum_j (d_j u_i + d_i u_j) n_j, i=0..2 ; n.grad T ; div u
+//                      (on a parallelepiped the face normal n is constant, the contraction is linear and
+//                      commutes with the trace/interpolation, so 5 viscous fields replace 12 gradient fields)
+//   face_flux_fast_kernel  one WARP per face, no CTA barriers: both sides' blocks -> (p+2)^2 quadrature points
+//                      -> Rusanov + averaged viscous flux (FaceIntegrator, src/face_integrator.cpp:282-351;
+//                      RiemannSolverTPS::Eval_LF, src/riemann_solver.cpp:89-114) -> projected face residual
+//   elem_resid_fast_kernel nodal flux, collocated weak divergence, lift of the six face residuals, diagonal
+//                      Me^-1, max characteristic speed (src/rhs_operator.cpp:379-391,432-448,493-559)
+//
+// Why traces are materialised: extrapolating a face trace needs ALL (p+1)^3 nodes of the element, so a
+// face-centric kernel that reads U/gradUp pulls 17 x 512 B per side through L2 (8.7 KB) -- the element
+// kernel has those values on chip already and emits 1.28 KB per side instead.
+#pragma once
+#include "rhs_kernels.cuh"
+
+namespace tpsb {
+
+constexpr int NTF = 10;  // trace fields per (element, face) block on the affine path
+constexpr int GEO = 12;  // doubles per element in the affine metric table: adj(J) [9], det, 1/det, pad
+
+// local faces at the - / + end of element axis r (MFEM hex face numbering, tables.hpp HEX_FACE_VERT)
+__device__ constexpr int kFaceMinus[3] = {4, 1, 0};
+__device__ constexpr int kFacePlus[3] = {2, 3, 5};
+
+// ------------------------------------------------------------------------------------------------
+template <int NP, int EPB, int MINB>
+__global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
+    grad_trace_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list) {
+  constexpr int ND = NP * NP * NP, NF2 = NP * NP;
+  constexpr int NV = 13;                               // viscous node fields: 3 axes x (s_0..2, n.gradT) + div u
+  constexpr int WRK = 2 * NEQ * ND + 6 * NEQ * NF2;    // sU | sUp | sJ ; sV aliases the front
+  static_assert(NV * ND <= WRK, "sV overlay");
+  __shared__ __align__(16) double sWork[EPB][WRK];
+  __shared__ double sGeo[EPB][GEO];
+  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
+  __shared__ int sNbr[EPB][6], sCode[EPB][6], sFp[6];
+  const int le = threadIdx.x / ND, n = threadIdx.x % ND;
+  const int slot = blockIdx.x * EPB + le;
+  const bool active = slot < elem_count;
+  const int e = active ? (elem_list ? elem_list[elem_begin + slot] : elem_begin + slot) : 0;
+  const long long N = a.N;
+  double *sU = &sWork[le][0], *sUp = sU + NEQ * ND, *sJ = sUp + NEQ * ND, *sV = sU;
+  if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
+  const long long o = static_cast<long long>(e) * ND + n;
+  if (active) {
+#pragma unroll
+    for (int f = 0; f < NEQ; f++) {
+      sU[f * ND + n] = a.U[o + f * N];
+      sUp[f * ND + n] = a.Up[o + f * N];
+    }
+    for (int t = n; t < GEO; t += ND) sGeo[le][t] = a.geo[static_cast<long long>(e) * GEO + t];
+    for (int t = n; t < 6; t += ND) {
+      sNbr[le][t] = a.nbr_elem[e * 6 + t];
+      sCode[le][t] = a.nbr_code[e * 6 + t];
+    }
+  }
+  __syncthreads();
+  const int i = n % NP, j = (n / NP) % NP, k = n / (NP * NP);
+  double rg[NEQ][DIM];  // reference-space gradient: D along each axis (+ face lifts below)
+  double *blk0 = a.tr + static_cast<long long>(e) * 6 * (NTF * NF2);
+  if (active) {
+    double dI[NP], dJ[NP], dK[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+      dI[m] = sD[i][m];
+      dJ[m] = sD[j][m];
+      dK[m] = sD[k][m];
+    }
+#pragma unroll
+    for (int f = 0; f < NEQ; f++) {
+      double d0 = 0, d1 = 0, d2 = 0;
+#pragma unroll
+      for (int m = 0; m < NP; m++) {
+        d0 += dI[m] * sUp[f * ND + m + NP * j + NP * NP * k];
+        d1 += dJ[m] * sUp[f * ND + i + NP * m + NP * NP * k];
+        d2 += dK[m] * sUp[f * ND + i + NP * j + NP * NP * m];
+      }
+      rg[f][0] = d0;
+      rg[f][1] = d1;
+      rg[f][2] = d2;
+    }
+    // traces at the face nodes of all six faces: task = (face, face node)
+    for (int t = n; t < 6 * NF2; t += ND) {
+      const int lf = t / NF2, ab = t % NF2, fa = ab % NP, fb = ab / NP;
+      const FacePar fp = decode_face(sFp[lf]);
+      const int b0 = face_node_base<NP>(fp, fa, fb), cs = axis_stride<NP>(fp.an);
+      double lbo[NP];
+#pragma unroll
+      for (int c = 0; c < NP; c++) lbo[c] = sLb[fp.side][c];
+      double pT[NEQ];
+      double *blk = blk0 + lf * (NTF * NF2) + ab;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) {
+        double u = 0, p = 0;
+#pragma unroll
+        for (int c = 0; c < NP; c++) {
+          u += lbo[c] * sU[f * ND + b0 + c * cs];
+          p += lbo[c] * sUp[f * ND + b0 + c * cs];
+        }
+        blk[f * NF2] = u;
+        pT[f] = p;
+      }
+      const int nbr = sNbr[le][lf];
+      if (nbr < 0) {  // boundary face: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
+#pragma unroll
+        for (int f = 0; f < NEQ; f++) sJ[(lf * NEQ + f) * NF2 + ab] = 0.0;
+        continue;
+      }
+      const int code = sCode[le][lf];
+      const FacePar fq = decode_face(sFp[code & 7]);
+      int a2, b2;
+      apply_perm<NP>(code >> 3, fa, fb, a2, b2);
+      const int q0 = face_node_base<NP>(fq, a2, b2), qs = axis_stride<NP>(fq.an);
+      const bool local = nbr < a.NE;
+      const double *src = local ? a.Up + static_cast<long long>(nbr) * ND + q0
+                                : a.UpHalo + static_cast<long long>(nbr - a.NE) * NEQ * ND + q0;
+      const long long fstride = local ? N : ND;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) {
+        const double oth = trace_line<NP>(src + f * fstride, qs, sLb[fq.side], a.vec_ok != 0);
+        sJ[(lf * NEQ + f) * NF2 + ab] = 0.5 * (oth - pT[f]);
+      }
+    }
+  }
+  __syncthreads();
+  double vf[NV];
+  if (active) {
+    // lift of the face jumps, in reference space: both faces of axis r share the direction adj(J) row r
+    // (outward normal = +-A[r,:]), so  rg[f][r] += (l_c(1) J+ - l_c(0) J-) / w_c
+    const int idx[3] = {i, j, k};
+#pragma unroll
+    for (int r = 0; r < DIM; r++) {
+      const int c = idx[r];
+      const FacePar fm = decode_face(sFp[kFaceMinus[r]]), fpl = decode_face(sFp[kFacePlus[r]]);
+      const int iam = pick3(fm.as, i, j, k), ibm = pick3(fm.at, i, j, k);
+      const int abm = (fm.ss ? iam : NP - 1 - iam) + NP * (fm.st ? ibm : NP - 1 - ibm);
+      const int iap = pick3(fpl.as, i, j, k), ibp = pick3(fpl.at, i, j, k);
+      const int abp = (fpl.ss ? iap : NP - 1 - iap) + NP * (fpl.st ? ibp : NP - 1 - ibp);
+      const double iw = 1.0 / sWn[c];
+      const double cm = sLb[0][c] * iw, cp = sLb[1][c] * iw;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++)
+        rg[f][r] += cp * sJ[(kFacePlus[r] * NEQ + f) * NF2 + abp] - cm * sJ[(kFaceMinus[r] * NEQ + f) * NF2 + abm];
+    }
+    // physical gradient: g[f][d] = sum_r rg[f][r] * inv(J)(r,d), inv(J)(r,d) = A[r + 3 d] / det
+    const double *A = sGeo[le];
+    const double idet = sGeo[le][10];
+    double g[NEQ][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const double a0 = A[0 + 3 * d] * idet, a1 = A[1 + 3 * d] * idet, a2 = A[2 + 3 * d] * idet;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) {
+        g[f][d] = rg[f][0] * a0 + rg[f][1] * a1 + rg[f][2] * a2;
+        a.gradUp[o + (f + d * NEQ) * N] = g[f][d];
+      }
+    }
+    // normal-contracted viscous fields for the three axis directions n^r = A[r,:] (outward at the + face)
+    double sym[DIM][DIM];
+#pragma unroll
+    for (int p = 0; p < DIM; p++)
+#pragma unroll
+      for (int q = 0; q < DIM; q++) sym[p][q] = g[1 + p][q] + g[1 + q][p];
+#pragma unroll
+    for (int r = 0; r < DIM; r++) {
+      const double n0 = A[r + 0], n1 = A[r + 3], n2 = A[r + 6];
+#pragma unroll
+      for (int p = 0; p < DIM; p++) vf[r * 4 + p] = sym[p][0] * n0 + sym[p][1] * n1 + sym[p][2] * n2;
+      vf[r * 4 + 3] = g[4][0] * n0 + g[4][1] * n1 + g[4][2] * n2;
+    }
+    vf[12] = g[1][0] + g[2][1] + g[3][2];
+  }
+  __syncthreads();  // every read of sU / sUp / sJ is done: sV may overwrite them
+  if (active) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) sV[v * ND + n] = vf[v];
+  }
+  __syncthreads();
+  if (active) {
+    for (int t = n; t < 6 * NF2; t += ND) {
+      const int lf = t / NF2, ab = t % NF2, fa = ab % NP, fb = ab / NP;
+      const FacePar fp = decode_face(sFp[lf]);
+      const int b0 = face_node_base<NP>(fp, fa, fb), cs = axis_stride<NP>(fp.an);
+      const double sg = fp.side ? 1.0 : -1.0;  // outward normal of this face = sg * A[an,:]
+      double lbo[NP];
+#pragma unroll
+      for (int c = 0; c < NP; c++) lbo[c] = sLb[fp.side][c];
+      double *blk = blk0 + lf * (NTF * NF2) + ab;
+      const double *row = sV + (fp.an * 4) * ND + b0;
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        double s = 0;
+#pragma unroll
+        for (int c = 0; c < NP; c++) s += lbo[c] * row[v * ND + c * cs];
+        blk[(NEQ + v) * NF2] = sg * s;
+      }
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < NP; c++) s += lbo[c] * sV[12 * ND + b0 + c * cs];
+      blk[(NEQ + 4) * NF2] = s;
+    }
+  }
+}
+
+// gather the trace blocks of the shared faces into the send buffer (one block per shared face, in the
+// order the receiver lists its shared faces with this peer)
+__global__ void pack_blocks_kernel(int nblk, int blk_doubles, const int *src_blk, const double *tr, double *dst) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(nblk) * blk_doubles) return;
+  const int b = static_cast<int>(t / blk_doubles), w = static_cast<int>(t % blk_doubles);
+  dst[t] = tr[static_cast<long long>(src_blk[b]) * blk_doubles + w];
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// branch-free double reciprocal / square root: MUFU seed + Newton steps, ~1 ulp.  The MUFU.RCP64H /
+// MUFU.RSQ64H seeds carry only ~9 good bits (the library routines spend 5-6 DFMAs on them as well), so
+// one cubic step (error e^3) plus one quadratic step (e^6) are needed.  What is saved against the library
+// divide / sqrt is the slow-path branch (BSSY/BSYNC + call) per use; arguments here are positive, O(1)-scaled
+// physical quantities (rho, T, p/rho, |v|^2 >= 0).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, fma(e, e, e), r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+// sqrt(x) for x >= 0 (returns 0 at 0)
+__device__ __forceinline__ double fast_sqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(fmax(x, 1e-300)));
+  // r <- r (1 + e/2 + 3 e^2/8), e = 1 - x r^2 (cubic), one Newton step, then Heron on s = x r
+  double e = fma(-x * r, r, 1.0);
+  r = fma(r * e, fma(0.375, e, 0.5), r);
+  e = fma(-x * r, r, 1.0);
+  r = fma(0.5 * r, e, r);
+  double s = x * r;
+  s = fma(fma(-s, s, x), 0.5 * r, s);
+  return s;
+}
+
+// NP contiguous doubles from shared memory through explicit ld.shared PTX (16-byte vectors when NP is even;
+// p is 16-byte aligned by construction).  Inline PTX, because nvcc 12.9 mis-optimised the plain C++ loads of
+// the unrolled row loop below: it fed v[0] with Y[161] in place of Y[1] (PTX: ld.shared.v2.f64 [..+6400]
+// paired with the scalar load at [..+5120]) -- found by the parity test, kept out of the optimiser's reach here.
+template <int NP>
+__device__ __forceinline__ void load_row(const double *p, double *out) {
+  const unsigned addr = smem_u32(p);
+  if constexpr (NP % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < NP / 2; q++)
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[2 * q]), "=d"(out[2 * q + 1]) : "r"(addr + 16 * q) : "memory");
+  } else {
+#pragma unroll
+    for (int q = 0; q < NP; q++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(out[q]) : "r"(addr + 8 * q) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// face_flux_fast_kernel: one WARP per face, grid-stride over faces, no CTA barriers in the loop.
+//   raw[2] : the two sides' trace blocks of the current / next face, filled by TMA bulk copies
+//            (cp.async.bulk + mbarrier) issued one face ahead by lane 0
+//   Y      : values interpolated along a, [2*NTF][NQ][NP]
+//   F, B   : weighted fluxes at the quadrature points / half-projected fluxes
+// Phases: (1) interpolation along a, task (side*NTF+field, b); side 2 is read through the orientation
+// permutation.  (2) one lane per quadrature point (alpha,beta): finishes the interpolation along b in
+// registers (4 FMAs per field with its own row of P) and evaluates the numerical flux.  (3,4) projection
+// back onto the (p+1)^2 face nodes.
+template <int NP, int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) face_flux_fast_kernel(KernelArgs a, int face_begin, int face_count) {
+  constexpr int NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ;
+  constexpr int RAW = 2 * NTF * NF2, YS = 2 * NTF * NP * NQ;
+  constexpr int FS = ((NEQ * NQ2 + 3) / 4) * 4, BS = NEQ * NQ * NP;
+  constexpr int PER_WARP = 2 * RAW + YS + FS + BS;
+  constexpr unsigned BLKB = NTF * NF2 * sizeof(double);
+  static_assert(NQ2 <= 32, "one lane per quadrature point");
+  static_assert(BLKB % 16 == 0, "bulk copy granularity");
+  extern __shared__ __align__(128) double sDyn[];
+  __shared__ __align__(8) unsigned long long sBar[WPB][2];
+  __shared__ double sWq[NQ2], sP[NQ][NP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < NQ2) sWq[threadIdx.x] = c_T.wq[threadIdx.x % NQ] * c_T.wq[threadIdx.x / NQ];
+  if (threadIdx.x < NQ * NP) sP[threadIdx.x / NP][threadIdx.x % NP] = c_T.P[threadIdx.x / NP][threadIdx.x % NP];
+  double *raw = sDyn + warp * PER_WARP, *Y = raw + 2 * RAW, *F = Y + YS, *B = F + FS;
+  const unsigned bar0 = smem_u32(&sBar[warp][0]), bar1 = smem_u32(&sBar[warp][1]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double wq = lane < NQ2 ? sWq[lane] : 0.0;
+  const int qa = lane % NQ, qb = lane < NQ2 ? lane / NQ : 0;
+  double pb[NP];  // this lane's row of P for the interpolation along b
+#pragma unroll
+  for (int q = 0; q < NP; q++) pb[q] = sP[qb][q];
+  const PhysParams ph = a.phys;
+  const int stride = gridDim.x * WPB;
+  int fi = blockIdx.x * WPB + warp;
+  // descriptors are fetched two faces ahead, blocks one face ahead
+  int4 fd_cur = make_int4(0, 0, 0, 0), fd_nxt = make_int4(0, 0, 0, 0);
+  if (fi < face_count) fd_cur = __ldg(&a.face_desc[face_begin + fi]);
+  if (fi + stride < face_count) fd_nxt = __ldg(&a.face_desc[face_begin + fi + stride]);
+  if (fi < face_count && lane == 0) {
+    mbar_expect_tx(bar0, 2 * BLKB);
+    bulk_g2s(smem_u32(raw), a.tr + static_cast<long long>(fd_cur.x) * (NTF * NF2), BLKB, bar0);
+    bulk_g2s(smem_u32(raw + NTF * NF2), a.tr + static_cast<long long>(fd_cur.y) * (NTF * NF2), BLKB, bar0);
+  }
+  for (int it = 0; fi < face_count; it++, fi += stride) {
+    const int buf = it & 1;
+    const unsigned ph_bit = (it >> 1) & 1;
+    const int fc = face_begin + fi;
+    double *cur = raw + buf * RAW;
+    // prefetch: blocks of the next face into the other buffer, descriptor of the one after
+    int4 fd_n2 = make_int4(0, 0, 0, 0);
+    if (fi + 2 * stride < face_count) fd_n2 = __ldg(&a.face_desc[fc + 2 * stride]);
+    if (fi + stride < face_count && lane == 0) {
+      const unsigned nb = buf ? bar0 : bar1;
+      double *nx = raw + (buf ^ 1) * RAW;
+      mbar_expect_tx(nb, 2 * BLKB);
+      bulk_g2s(smem_u32(nx), a.tr + static_cast<long long>(fd_nxt.x) * (NTF * NF2), BLKB, nb);
+      bulk_g2s(smem_u32(nx + NTF * NF2), a.tr + static_cast<long long>(fd_nxt.y) * (NTF * NF2), BLKB, nb);
+    }
+    const double2 nrm01 = __ldg(reinterpret_cast<const double2 *>(a.face_nor) + 2 * fc);
+    const double2 nrm23 = __ldg(reinterpret_cast<const double2 *>(a.face_nor) + 2 * fc + 1);
+    const int pc = fd_cur.z;  // perm code: face coords -> Elem2 local face coords
+    mbar_wait(buf ? bar1 : bar0, ph_bit);
+    // (1) interpolation along a: Y[sf][alpha][b] = sum_a P[alpha][a] T[sf](a, b)
+    for (int t = lane; t < 2 * NTF * NP; t += 32) {
+      const int sf = t / NP, b = t % NP;
+      int i0 = NP * b, di = 1;
+      if (sf >= NTF) {  // side 2: (a,b) -> Elem2 coords; along a the image is a line of stride +-1 or +-NP
+        const int fa2 = (pc & 2) ? 1 : 0, fb2 = (pc & 4) ? 1 : 0;
+        if (pc & 1) {
+          i0 = (fa2 ? NP - 1 - b : b) + (fb2 ? NP * (NP - 1) : 0);
+          di = fb2 ? -NP : NP;
+        } else {
+          i0 = (fa2 ? NP - 1 : 0) + NP * (fb2 ? NP - 1 - b : b);
+          di = fa2 ? -1 : 1;
+        }
+      }
+      const double *src = cur + sf * NF2 + i0;
+      double in[NP];
+#pragma unroll
+      for (int q = 0; q < NP; q++) in[q] = src[q * di];
+#pragma unroll
+      for (int al = 0; al < NQ; al++) {
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++) v += sP[al][q] * in[q];
+        Y[sf * (NP * NQ) + al * NP + b] = v;
+      }
+    }
+    __syncwarp();
+    // (2) quadrature point (qa, qb): finish the interpolation and evaluate the flux
+    if (lane < NQ2) {
+      double v[2 * NTF];
+#pragma unroll
+      for (int sf = 0; sf < 2 * NTF; sf++) {
+        double row[NP];
+        load_row<NP>(Y + sf * (NP * NQ) + qa * NP, row);
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++) s += pb[q] * row[q];
+        v[sf] = s;
+      }
+      const double *u1 = v, *u2 = v + NTF;
+      const double n0 = nrm01.x, n1 = nrm01.y, n2 = nrm23.x, normag = nrm23.y;
+      // DryAir state (equation_of_state.cpp:279-335) with 1/rho formed once
+      const double ri1 = fast_rcp(u1[0]), ri2 = fast_rcp(u2[0]);
+      const double vx1 = u1[1] * ri1, vy1 = u1[2] * ri1, vz1 = u1[3] * ri1;
+      const double vx2 = u2[1] * ri2, vy2 = u2[2] * ri2, vz2 = u2[3] * ri2;
+      const double vv1 = vx1 * vx1 + vy1 * vy1 + vz1 * vz1, vv2 = vx2 * vx2 + vy2 * vy2 + vz2 * vz2;
+      const double p1 = ph.gm1 * (u1[4] - 0.5 * u1[0] * vv1), p2 = ph.gm1 * (u2[4] - 0.5 * u2[0] * vv2);
+      const double pr1 = p1 * ri1, pr2 = p2 * ri2;  // p / rho = R T
+      const double maxE = fmax(fast_sqrt(vv1) + fast_sqrt(ph.gamma * pr1), fast_sqrt(vv2) + fast_sqrt(ph.gamma * pr2));
+      // Rusanov (riemann_solver.cpp:89-114)
+      const double vn1 = vx1 * n0 + vy1 * n1 + vz1 * n2, vn2 = vx2 * n0 + vy2 * n1 + vz2 * n2;
+      const double diss = 0.5 * maxE * normag;
+      const double psum = 0.5 * (p1 + p2);
+      double fx[NEQ];
+      fx[0] = 0.5 * (u1[0] * vn1 + u2[0] * vn2) - diss * (u2[0] - u1[0]);
+      fx[1] = 0.5 * (u1[1] * vn1 + u2[1] * vn2) + psum * n0 - diss * (u2[1] - u1[1]);
+      fx[2] = 0.5 * (u1[2] * vn1 + u2[2] * vn2) + psum * n1 - diss * (u2[2] - u1[2]);
+      fx[3] = 0.5 * (u1[3] * vn1 + u2[3] * vn2) + psum * n2 - diss * (u2[3] - u1[3]);
+      fx[4] = 0.5 * ((u1[4] + p1) * vn1 + (u2[4] + p2) * vn2) - diss * (u2[4] - u1[4]);
+      if (ph.eq_system != 0) {  // - 1/2 (Fv1 + Fv2).n  (face_integrator.cpp:331-341); side 2 carries n2 = -n
+        // Sutherland (transport_properties.cpp:223-234): mu = C1 mult T^1.5 / (T + S0)
+        const double iR = 1.0 / ph.R;
+        const double T1 = pr1 * iR, T2 = pr2 * iR;
+        const double mu1 = ph.C1 * ph.visc_mult * (T1 * fast_sqrt(T1)) * fast_rcp(T1 + ph.S0);
+        const double mu2 = ph.C1 * ph.visc_mult * (T2 * fast_sqrt(T2)) * fast_rcp(T2 + ph.S0);
+        const double bf = ph.bulk_visc_mult - 2. / 3.;
+        const double bd1 = bf * mu1 * u1[NEQ + 4], bd2 = -bf * mu2 * u2[NEQ + 4];
+        const double t0 = mu1 * u1[NEQ + 0] + bd1 * n0 - (mu2 * u2[NEQ + 0] + bd2 * n0);
+        const double t1 = mu1 * u1[NEQ + 1] + bd1 * n1 - (mu2 * u2[NEQ + 1] + bd2 * n1);
+        const double t2 = mu1 * u1[NEQ + 2] + bd1 * n2 - (mu2 * u2[NEQ + 2] + bd2 * n2);
+        const double e1 = vx1 * (mu1 * u1[NEQ + 0] + bd1 * n0) + vy1 * (mu1 * u1[NEQ + 1] + bd1 * n1) +
+                          vz1 * (mu1 * u1[NEQ + 2] + bd1 * n2) + ph.cp_div_pr * mu1 * u1[NEQ + 3];
+        const double e2 = vx2 * (mu2 * u2[NEQ + 0] + bd2 * n0) + vy2 * (mu2 * u2[NEQ + 1] + bd2 * n1) +
+                          vz2 * (mu2 * u2[NEQ + 2] + bd2 * n2) + ph.cp_div_pr * mu2 * u2[NEQ + 3];
+        fx[1] -= 0.5 * t0;
+        fx[2] -= 0.5 * t1;
+        fx[3] -= 0.5 * t2;
+        fx[4] -= 0.5 * (e1 - e2);
+      }
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) F[eq * NQ2 + lane] = fx[eq] * wq;
+    }
+    __syncwarp();
+    // (3) projection along beta: B[eq][alpha][b] = sum_beta P[beta][b] F[eq][alpha + NQ beta]
+    for (int t = lane; t < NEQ * NQ; t += 32) {
+      const int eq = t / NQ, al = t % NQ;
+      double in[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; q++) in[q] = F[eq * NQ2 + al + NQ * q];
+#pragma unroll
+      for (int b = 0; b < NP; b++) {
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) s += sP[q][b] * in[q];
+        B[t * NP + b] = s;
+      }
+    }
+    __syncwarp();
+    // (4) ... and along alpha, straight to global: R[eq][a + NP b] = sum_alpha P[alpha][a] B[eq][alpha][b]
+    for (int t = lane; t < NEQ * NP; t += 32) {
+      const int eq = t / NP, b = t % NP;
+      double in[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; q++) in[q] = B[(eq * NQ + q) * NP + b];
+      double *dst = a.faceRes + (static_cast<long long>(fc) * NEQ + eq) * NF2 + NP * b;
+#pragma unroll
+      for (int aa = 0; aa < NP; aa++) {
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) s += sP[q][aa] * in[q];
+        dst[aa] = s;
+      }
+    }
+    __syncwarp();  // all reads of cur / Y / F / B done before the next iteration overwrites them
+    fd_cur = fd_nxt;
+    fd_nxt = fd_n2;
+  }
+}
+
+template <int NP>
+constexpr size_t face_fast_smem_bytes(int wpb) {
+  constexpr int NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ;
+  return static_cast<size_t>(wpb) * (2 * (2 * NTF * NF2) + 2 * NTF * NP * NQ + ((NEQ * NQ2 + 3) / 4) * 4 + NEQ * NQ * NP) *
+         sizeof(double);
+}
+
+}  // namespace tpsb

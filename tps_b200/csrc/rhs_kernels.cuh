@@ -53,6 +53,11 @@ struct KernelArgs {
   double *faceRes;         // [NFint][NEQ][np*np]
   double *y;               // [NEQ][N]
   unsigned long long *maxCharBits;  // atomicMax target (bit pattern of a non-negative double)
+  // fast (all-affine) path, rhs_fast.cuh
+  const double *geo;       // [NE][12] adj(J) (A[r + 3 d]), det, 1/det, pad
+  double *tr;              // [6 NE + shared faces][10][np*np] face-trace blocks
+  const int4 *face_desc;   // [NFint] {block of side 1, block of side 2, perm code Elem2 face coords -> face coords, 0}
+  const double *face_nor;  // [NFint][4] CalcOrtho normal (Elem1 -> Elem2, area weighted) and its magnitude
 };
 
 // ---- geometry: trilinear hexahedron from its 8 vertices (mesh nodes of order 1) ----

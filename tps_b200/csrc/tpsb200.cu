@@ -15,6 +15,7 @@
 
 #include "../../include/tpsb200.h"
 #include "rhs_kernels_impl.cuh"
+#include "rhs_fast.cuh"
 
 using namespace tpsb;
 
@@ -43,6 +44,14 @@ struct tpsb_ctx {
   double *d_Uhalo = nullptr, *d_UpHalo = nullptr, *d_gradUpHalo = nullptr, *d_sendU = nullptr, *d_sendG = nullptr;
   unsigned long long *d_maxBits = nullptr;
   double *d_mcs = nullptr;
+  // fast (all-affine) path
+  bool fast = false;
+  double *d_geo = nullptr, *d_tr = nullptr, *d_face_nor = nullptr, *d_sendTr = nullptr;
+  int4 *d_face_desc = nullptr;
+  int *d_send_blk = nullptr;
+  std::vector<int> sendblk_offset, recvblk_offset;  // per peer, in trace blocks
+  int n_send_blk = 0;
+  cudaEvent_t ev_recvT = nullptr;
   // halo description
   ncclComm_t comm = nullptr;
   std::vector<int> nbr_rank, send_offset, recv_offset;
@@ -52,6 +61,7 @@ struct tpsb_ctx {
   double *d_k = nullptr, *d_yv = nullptr, *d_z = nullptr, *d_hx = nullptr, *d_hy = nullptr;
   long long launches = 0;
   int tune[3] = {0, 0, 0};
+  int num_sms = 148, face_ctas_per_sm = 5;
   // per-kernel device timers (tpsb_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[TPSB_NUM_KERNEL_CLASSES];
@@ -160,6 +170,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   ctx = c;
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (const char *fc = getenv("TPSB_FACE_CTAS")) c->face_ctas_per_sm = std::max(1, atoi(fc));
   if (const char *tn = getenv("TPSB_TUNE")) sscanf(tn, "%d,%d,%d", &c->tune[0], &c->tune[1], &c->tune[2]);
   c->order = space->order;
   c->np = space->order + 1;
@@ -263,6 +275,76 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     if (touches_shared[e]) elem_list.push_back(e);
   c->n_pb_elems = NE - c->n_int_elems;
 
+  // ---- fast path tables (rhs_fast.cuh): affine metric per element, per-face block ids / normals ----
+  c->fast = true;
+  if (const char *pth = getenv("TPSB_PATH")) c->fast = strcmp(pth, "legacy") != 0;
+  std::vector<double> geo, face_nor;
+  std::vector<int4> face_desc;
+  std::vector<int> send_blk;
+  const int nshared = c->NFint - c->NFlocal;
+  if (c->fast) {
+    geo.assign(static_cast<size_t>(NE) * GEO, 0.0);
+    for (int e = 0; e < NE; e++) {
+      const double *v = &maps->elem_vertices[static_cast<size_t>(e) * 24];
+      double J[9], A[9];
+      for (int i = 0; i < 3; i++) {
+        J[i + 0] = v[1 * 3 + i] - v[i];
+        J[i + 3] = v[3 * 3 + i] - v[i];
+        J[i + 6] = v[4 * 3 + i] - v[i];
+      }
+      const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[3] * (J[1] * J[8] - J[2] * J[7]) +
+                         J[6] * (J[1] * J[5] - J[2] * J[4]);
+      A[0] = J[4] * J[8] - J[7] * J[5];
+      A[3] = J[6] * J[5] - J[3] * J[8];
+      A[6] = J[3] * J[7] - J[6] * J[4];
+      A[1] = J[7] * J[2] - J[1] * J[8];
+      A[4] = J[0] * J[8] - J[6] * J[2];
+      A[7] = J[6] * J[1] - J[0] * J[7];
+      A[2] = J[1] * J[5] - J[4] * J[2];
+      A[5] = J[3] * J[2] - J[0] * J[5];
+      A[8] = J[0] * J[4] - J[3] * J[1];
+      double *g = &geo[static_cast<size_t>(e) * GEO];
+      for (int q = 0; q < 9; q++) g[q] = A[q];
+      g[9] = det;
+      g[10] = 1.0 / det;
+    }
+    // shared faces: position of each one in the peer-grouped receive order, key (halo element, its local face)
+    std::vector<int> shared_pos(nshared, 0);
+    {
+      std::vector<std::pair<long long, int>> key(nshared);
+      for (int s = 0; s < nshared; s++) {
+        const int fc = c->NFlocal + s;
+        key[s] = {static_cast<long long>(fl_el2[fc] - NE) * 8 + fl_inf2[fc] / 64, s};
+      }
+      std::sort(key.begin(), key.end());
+      for (int pos = 0; pos < nshared; pos++) shared_pos[key[pos].second] = pos;
+    }
+    face_desc.resize(c->NFint);
+    face_nor.assign(static_cast<size_t>(c->NFint) * 4, 0.0);
+    for (int fc = 0; fc < c->NFint; fc++) {
+      const int e1 = fl_el1[fc], e2 = fl_el2[fc], lf1 = fl_inf1[fc] / 64, lf2 = fl_inf2[fc] / 64, ori = fl_inf2[fc] % 64;
+      int4 d;
+      d.x = e1 * 6 + lf1;
+      d.y = e2 < NE ? e2 * 6 + lf2 : 6 * NE + shared_pos[fc - c->NFlocal];
+      d.z = c->T.perm_code[ori];
+      d.w = 0;
+      face_desc[fc] = d;
+      // CalcOrtho of Elem1's face Jacobian (constant on a parallelogram face): (X1 - X0) x (X3 - X0)
+      const double *v = &maps->elem_vertices[static_cast<size_t>(e1) * 24];
+      const int *fv = c->T.face_vert[lf1];
+      double ts[3], tt[3];
+      for (int i = 0; i < 3; i++) {
+        ts[i] = v[fv[1] * 3 + i] - v[fv[0] * 3 + i];
+        tt[i] = v[fv[3] * 3 + i] - v[fv[0] * 3 + i];
+      }
+      double *nr = &face_nor[static_cast<size_t>(fc) * 4];
+      nr[0] = ts[1] * tt[2] - ts[2] * tt[1];
+      nr[1] = ts[2] * tt[0] - ts[0] * tt[2];
+      nr[2] = ts[0] * tt[1] - ts[1] * tt[0];
+      nr[3] = std::sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+    }
+  }
+
   // ---- device allocations ----
   cudaError_t ce = cudaSetDevice(device);
   std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE + NEH) * 24);
@@ -285,6 +367,13 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (ce == cudaSuccess) ce = cudaMemset(c->d_maxBits, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(c_T, &c->T, sizeof(RefTables));
   if (ce == cudaSuccess) g_uploaded_order = c->order;
+  if (c->fast) {
+    if (ce == cudaSuccess) ce = upload(&c->d_geo, geo);
+    if (ce == cudaSuccess) ce = upload(&c->d_face_desc, face_desc);
+    if (ce == cudaSuccess) ce = upload(&c->d_face_nor, face_nor);
+    const size_t blk = static_cast<size_t>(NTF) * c->np * c->np * sizeof(double);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_tr, (static_cast<size_t>(6) * NE + nshared) * blk);
+  }
 
   // ---- halo ----
   if (ce == cudaSuccess && NEH > 0) {
@@ -315,6 +404,40 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvU, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvG, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvT, cudaEventDisableTiming);
+    if (c->fast) {
+      // trace blocks this rank sends to peer p: for each send element (in send order = the receiver's halo
+      // order) its local faces, ascending, whose neighbour is a halo element owned by p.  The receiver sorts
+      // its shared faces by (halo element, that element's local face): the same order.
+      auto peer_of = [&](int h) {
+        for (int q = 0; q < np; q++)
+          if (h >= c->recv_offset[q] && h < c->recv_offset[q + 1]) return q;
+        return -1;
+      };
+      c->sendblk_offset.assign(np + 1, 0);
+      c->recvblk_offset.assign(np + 1, 0);
+      for (int q = 0; q < np; q++) {
+        for (int k = c->send_offset[q]; k < c->send_offset[q + 1]; k++) {
+          const int es = se[k];
+          for (int lf = 0; lf < 6; lf++) {
+            const int nb = nbr_elem[es * 6 + lf];
+            if (nb >= NE && peer_of(nb - NE) == q) send_blk.push_back(es * 6 + lf);
+          }
+        }
+        c->sendblk_offset[q + 1] = static_cast<int>(send_blk.size());
+      }
+      for (int s2 = 0; s2 < nshared; s2++) c->recvblk_offset[peer_of(fl_el2[c->NFlocal + s2] - NE) + 1]++;
+      for (int q = 0; q < np; q++) c->recvblk_offset[q + 1] += c->recvblk_offset[q];
+      c->n_send_blk = static_cast<int>(send_blk.size());
+      if (c->n_send_blk != nshared) {
+        tpsb_destroy(c);
+        return fail(nullptr, TPSB_EINVAL, "halo description inconsistent: %d trace blocks to send, %d shared faces",
+                    c->n_send_blk, nshared);
+      }
+      if (ce == cudaSuccess) ce = upload(&c->d_send_blk, send_blk);
+      if (ce == cudaSuccess)
+        ce = cudaMalloc(&c->d_sendTr, static_cast<size_t>(c->n_send_blk) * NTF * c->np * c->np * sizeof(double));
+    }
   }
   if (ce != cudaSuccess) {
     const std::string msg = cudaGetErrorString(ce);
@@ -333,13 +456,15 @@ void tpsb_destroy(tpsb_ctx *c) {
                   c->d_face_inf2, c->d_el_face,  c->d_el_face_code, c->d_elem_list, c->d_Up,       c->d_gradUp,
                   c->d_faceRes,  c->d_Uhalo,     c->d_UpHalo,       c->d_gradUpHalo, c->d_sendU,   c->d_sendG,
                   c->d_maxBits,  c->d_mcs,       c->d_send_elems,   c->d_k,        c->d_yv,       c->d_z,
-                  c->d_hx,       c->d_hy};
+                  c->d_hx,       c->d_hy,        c->d_geo,          c->d_tr,       c->d_face_nor, c->d_sendTr,
+                  c->d_face_desc, c->d_send_blk};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
   if (c->ev_recvU) cudaEventDestroy(c->ev_recvU);
   if (c->ev_recvG) cudaEventDestroy(c->ev_recvG);
+  if (c->ev_recvT) cudaEventDestroy(c->ev_recvT);
   delete c;
 }
 
@@ -383,6 +508,10 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   a.faceRes = c->d_faceRes;
   a.y = d_y;
   a.maxCharBits = c->d_maxBits;
+  a.geo = c->d_geo;
+  a.tr = c->d_tr;
+  a.face_desc = c->d_face_desc;
+  a.face_nor = c->d_face_nor;
   auto al32 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
   a.vec_ok = (al32(d_x) && al32(c->d_Up) && al32(c->d_gradUp) && al32(c->d_Uhalo) && al32(c->d_UpHalo) &&
               al32(c->d_gradUpHalo) && (c->N % 4 == 0))
@@ -516,8 +645,135 @@ static int run_gradients(tpsb_ctx *ctx, const KernelArgs &a, bool prims_done) {
   return TPSB_OK;
 }
 
+// ---- fast path (rhs_fast.cuh) ----
+template <int NP, int EPB, int MINB>
+static void launch_grad_trace(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_GRAD);
+  grad_trace_kernel<NP, EPB, MINB><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count, list);
+}
+template <int NP, int WPB, int MINB>
+static void launch_face_fast(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_FACE);
+  int grid = (count + WPB - 1) / WPB;
+  const int cap = c->num_sms * c->face_ctas_per_sm;
+  if (grid > cap) grid = cap;
+  const size_t smem = face_fast_smem_bytes<NP>(WPB);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(face_flux_fast_kernel<NP, WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr_set = true;
+  }
+  face_flux_fast_kernel<NP, WPB, MINB><<<grid, 32 * WPB, smem, c->stream>>>(a, begin, count);
+}
+static void grad_trace(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
+  if (c->np == 4) {
+    switch (c->tune[0]) {
+      case 1: launch_grad_trace<4, 1, 12>(c, a, begin, count, list); break;
+      case 2: launch_grad_trace<4, 2, 5>(c, a, begin, count, list); break;
+      case 3: launch_grad_trace<4, 2, 6>(c, a, begin, count, list); break;
+      case 4: launch_grad_trace<4, 4, 3>(c, a, begin, count, list); break;
+      case 5: launch_grad_trace<4, 1, 8>(c, a, begin, count, list); break;
+      default: launch_grad_trace<4, 1, 10>(c, a, begin, count, list); break;
+    }
+  } else if (c->np == 3) {
+    launch_grad_trace<3, 4, 4>(c, a, begin, count, list);
+  } else {
+    launch_grad_trace<2, 16, 4>(c, a, begin, count, list);
+  }
+}
+static void face_fast(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+  if (c->np == 4) {
+    switch (c->tune[1]) {
+      case 1: launch_face_fast<4, 4, 4>(c, a, begin, count); break;
+      case 2: launch_face_fast<4, 2, 10>(c, a, begin, count); break;
+      case 3: launch_face_fast<4, 8, 2>(c, a, begin, count); break;
+      case 4: launch_face_fast<4, 6, 3>(c, a, begin, count); break;
+      default: launch_face_fast<4, 4, 5>(c, a, begin, count); break;
+    }
+  } else if (c->np == 3) {
+    launch_face_fast<3, 8, 2>(c, a, begin, count);
+  } else {
+    launch_face_fast<2, 8, 2>(c, a, begin, count);
+  }
+}
+
+// grouped ncclSend/ncclRecv of the shared faces' trace blocks (replaces the gradUp half of
+// RHSoperator::initNBlockDataTransfer: 1.28 KB per shared face instead of a 7.7 KB element)
+static int exchange_traces(tpsb_ctx *ctx) {
+  tpsb_ctx *c = ctx;
+  const int bd = NTF * c->np * c->np;
+  const long long total = static_cast<long long>(c->n_send_blk) * bd;
+  {
+    ProfScope ps(c, K_PACK);
+    pack_blocks_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(c->n_send_blk, bd, c->d_send_blk,
+                                                                                         c->d_tr, c->d_sendTr);
+  }
+  CU(cudaEventRecord(c->ev_pack, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+  double *recv = c->d_tr + static_cast<size_t>(6) * c->NE * bd;
+  NC(ncclGroupStart());
+  for (size_t p = 0; p < c->nbr_rank.size(); p++) {
+    NC(ncclSend(c->d_sendTr + static_cast<size_t>(c->sendblk_offset[p]) * bd,
+                static_cast<size_t>(c->sendblk_offset[p + 1] - c->sendblk_offset[p]) * bd, ncclDouble, c->nbr_rank[p], c->comm,
+                c->comm_stream));
+    NC(ncclRecv(recv + static_cast<size_t>(c->recvblk_offset[p]) * bd,
+                static_cast<size_t>(c->recvblk_offset[p + 1] - c->recvblk_offset[p]) * bd, ncclDouble, c->nbr_rank[p], c->comm,
+                c->comm_stream));
+  }
+  NC(ncclGroupEnd());
+  CU(cudaEventRecord(c->ev_recvT, c->comm_stream));
+  return TPSB_OK;
+}
+
+static int run_gradients_fast(tpsb_ctx *ctx, const KernelArgs &a, bool prims_done) {
+  tpsb_ctx *c = ctx;
+  if (g_uploaded_order != c->order) {
+    CU(cudaMemcpyToSymbolAsync(c_T, &c->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, c->stream));
+    g_uploaded_order = c->order;
+  }
+  if (!prims_done) launch_prim(c, a, 0);
+  if (c->NEH > 0) {
+    int rc = exchange(c, a.U, NEQ, c->d_sendU, c->d_Uhalo, c->ev_recvU);
+    if (rc) return rc;
+    grad_trace(c, a, 0, c->n_int_elems, c->d_elem_list);
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvU, 0));
+    launch_prim(c, a, 1);
+    grad_trace(c, a, c->n_int_elems, c->n_pb_elems, c->d_elem_list);
+  } else {
+    grad_trace(c, a, 0, c->NE, nullptr);
+  }
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+static void resid(tpsb_ctx *c, const KernelArgs &a);
+
+static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  tpsb_ctx *c = ctx;
+  CU(cudaSetDevice(c->device));
+  KernelArgs a = make_args(c, d_x, d_y);
+  CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
+  int rc = run_gradients_fast(c, a, false);
+  if (rc) return rc;
+  if (c->NEH > 0) {
+    rc = exchange_traces(c);
+    if (rc) return rc;
+    face_fast(c, a, 0, c->NFlocal);
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvT, 0));
+    face_fast(c, a, c->NFlocal, c->NFint - c->NFlocal);
+  } else {
+    face_fast(c, a, 0, c->NFint);
+  }
+  resid(c, a);
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
 static int run_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   tpsb_ctx *c = ctx;
+  if (c->fast) return run_mult_fast(ctx, d_x, d_y);
   CU(cudaSetDevice(c->device));
   KernelArgs a = make_args(c, d_x, d_y);
   CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
@@ -582,6 +838,7 @@ int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updat
   if (!ctx || !d_x) return TPSB_EINVAL;
   CU(cudaSetDevice(ctx->device));
   KernelArgs a = make_args(ctx, d_x, nullptr);
+  if (ctx->fast) return run_gradients_fast(ctx, a, primitives_updated != 0);
   return run_gradients(ctx, a, primitives_updated != 0);
 }
 
@@ -589,6 +846,21 @@ int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp) {
   if (!ctx) return TPSB_EINVAL;
   if (d_Up) *d_Up = ctx->d_Up;
   if (d_gradUp) *d_gradUp = ctx->d_gradUp;
+  return TPSB_OK;
+}
+
+int tpsb_debug_buffer(tpsb_ctx *ctx, int which, double **d_ptr, int64_t *count) {
+  if (!ctx || !d_ptr || !count) return TPSB_EINVAL;
+  const int64_t nf2 = static_cast<int64_t>(ctx->np) * ctx->np;
+  if (which == 0) {
+    *d_ptr = ctx->d_faceRes;
+    *count = static_cast<int64_t>(ctx->NFint) * NEQ * nf2;
+  } else if (which == 1) {
+    *d_ptr = ctx->d_tr;
+    *count = ctx->d_tr ? (static_cast<int64_t>(6) * ctx->NE + (ctx->NFint - ctx->NFlocal)) * NTF * nf2 : 0;
+  } else {
+    return TPSB_EINVAL;
+  }
   return TPSB_OK;
 }
 
