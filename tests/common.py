@@ -40,3 +40,18 @@ def node_coords_from_mesh(elem_xyz, order):
 
 def rel_l2(a, b):
     return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))
+
+
+def warp_mesh(m, amp=0.08, lo=(-np.pi,) * 3, hi=(np.pi,) * 3):
+    """Smooth, box-periodic displacement of every vertex: turns the Cartesian box into a mesh of genuinely
+    trilinear (non-parallelepiped) hexahedra while keeping periodic copies of a vertex consistent."""
+    xyz = m["elem_xyz"]
+    L = np.asarray(hi) - np.asarray(lo)
+    t = 2 * np.pi * (xyz - np.asarray(lo)) / L
+    d = np.empty_like(xyz)
+    d[..., 0] = np.sin(t[..., 0]) * np.cos(t[..., 1]) * np.cos(2 * t[..., 2])
+    d[..., 1] = np.cos(2 * t[..., 0]) * np.sin(t[..., 1]) * np.cos(t[..., 2])
+    d[..., 2] = np.cos(t[..., 0]) * np.cos(2 * t[..., 1]) * np.sin(t[..., 2])
+    out = dict(m)
+    out["elem_xyz"] = np.ascontiguousarray(xyz + amp * L / (2 * np.pi) * d)
+    return out

@@ -7,7 +7,7 @@ import pytest
 import meshref
 import oracle_api
 import tps_b200
-from common import node_coords_from_mesh, rel_l2, tgv_state
+from common import node_coords_from_mesh, rel_l2, tgv_state, warp_mesh
 
 pytestmark = pytest.mark.gpu
 PI = np.pi
@@ -67,6 +67,38 @@ def test_stretched_box_and_blocked_element_order(lib_built, oracle_built):
     torch, m, op, orc, U = _setup((9, 10, 11), visc_mult=1e4, lo=(0.0, -1.0, 2.0), hi=(3.0, 1.5, 2.7), order_mode=1)
     y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
     assert rel_l2(y, orc.mult(U)) < 1e-10
+
+
+@pytest.mark.parametrize("order,eq", [(3, 1), (2, 1), (3, 0), (1, 1)])
+def test_trilinear_mesh_parity(lib_built, oracle_built, order, eq):
+    """Genuinely trilinear (non-parallelepiped) hexahedra: per-node Jacobians, face normals varying over the
+    face -- the general kernels (the cyl3d-type meshes of BASELINE config C2 take this path)."""
+    import torch
+    m = warp_mesh(tps_b200.cartesian_hex_mesh(5, 4, 6, lo=(-PI,) * 3, hi=(PI,) * 3), amp=0.12)
+    op = tps_b200.RhsOperator(m, order=order, physics=tps_b200.Physics.dry_air(eq, 3e4, 0.2))
+    orc = oracle_api.Oracle(order, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(eq, 3e4, 0.2))
+    U = tgv_state(orc.node_coords())
+    x = torch.from_numpy(U).cuda()
+    y = op.Mult(x).cpu().numpy()
+    yo = orc.mult(U)
+    N = orc.N
+    g = op.fields()[1].cpu().numpy()
+    assert rel_l2(g, orc.gradients(U)) < 1e-11
+    for k in range(5):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k
+    assert abs(op.max_char_speed() / orc.max_char_speed - 1) < 1e-13
+
+
+def test_general_path_matches_fast_path_on_affine_mesh(lib_built, oracle_built, monkeypatch):
+    """The two independent kernel sets (rhs_fast.cuh / general) agree to round-off where both apply."""
+    torch, m, op, orc, U = _setup((5, 6, 4), visc_mult=2e4, bulk=0.1)
+    y_fast = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    monkeypatch.setenv("TPSB_PATH", "general")
+    op2 = tps_b200.RhsOperator(m, order=3, physics=tps_b200.Physics.dry_air(1, 2e4, 0.1))
+    y_gen = op2.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    assert rel_l2(y_fast, y_gen) < 1e-12
+    assert rel_l2(y_gen, orc.mult(U)) < 1e-10
 
 
 def test_host_buffer_entry_point_matches_device_entry_point(lib_built, oracle_built):

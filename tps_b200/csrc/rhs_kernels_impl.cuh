@@ -95,23 +95,17 @@ __device__ __forceinline__ double trace_line(const double *r, int cs, const doub
   return v;
 }
 
-// Affine (parallelepiped) element: constant Jacobian from three edge vectors.
-__device__ __forceinline__ void hex_jacobian_affine(const double *v, double *J) {
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    J[i + 0] = v[1 * 3 + i] - v[i];
-    J[i + 3] = v[3 * 3 + i] - v[i];
-    J[i + 6] = v[4 * 3 + i] - v[i];
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // grad_kernel: EPB elements per CTA, one thread per node.
 //   volume : gradUp_j = sum_r inv(J)_rd * (D applied along r)             [= Me^-1 Ke Up, collocated]
-//   faces  : + l_c(face)/(w_c |J|) * 1/2 (Up_nbr - Up_own)(a,b) * n_d     [= Me^-1 of the face term of
-//            GradFaceIntegrator (src/faceGradientIntegration.cpp:119-137); on an affine element the
-//            (p+2)^2-point face rule integrates phi_i * jump exactly, so it collapses onto the
-//            (p+1)^2 face nodes]
+//   faces  : + l_c(face)/(w_c |J|) * 1/2 (Up_nbr - Up_own)(a,b) * n_d(a,b)     [= Me^-1 of the face term of
+//            GradFaceIntegrator (src/faceGradientIntegration.cpp:119-137).  On a trilinear hexahedron the
+//            CalcOrtho normal is bilinear over the face, so phi_i * jump * n has degree 2p+1 per direction:
+//            both the reference's (p+2)^2-point rule and the (p+1)^2 face nodes integrate it exactly, and the
+//            term collapses onto the face nodes with the normal taken AT the face node]
+// Geometry is the general trilinear map (per-node Jacobian from the 8 vertices); this is the path for
+// curved/skewed meshes and boundary conditions, the all-parallelepiped case runs rhs_fast.cuh.
 // Neighbour traces are extrapolated straight from global memory (L2-resident neighbour data), own
 // traces from shared memory; all six faces are processed between two barriers.
 template <int NP, int EPB, int MINB>
@@ -121,9 +115,9 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
   __shared__ double sUp[EPB][NEQ][ND];
   __shared__ double sJ[EPB][6][NEQ][NF2];
   __shared__ double sVx[EPB][24];
-  __shared__ double sNor[EPB][6][3];
-  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
-  __shared__ int sNbr[EPB][6], sCode[EPB][6], sFp[6];
+  __shared__ double sNor[EPB][6][NF2][3];
+  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP], sXn[NP];
+  __shared__ int sNbr[EPB][6], sCode[EPB][6], sFp[6], sFv[6][4];
   const int le = threadIdx.x / ND, n = threadIdx.x % ND;
   const int slot = blockIdx.x * EPB + le;
   const bool active = slot < elem_count;
@@ -132,7 +126,9 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
   if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
   if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
   if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  if (threadIdx.x < NP) sXn[threadIdx.x] = c_T.xn[threadIdx.x];
   if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
+  for (int t = threadIdx.x; t < 24; t += blockDim.x) sFv[t / 4][t % 4] = c_T.face_vert[t / 4][t % 4];
   if (active) {
 #pragma unroll
     for (int f = 0; f < NEQ; f++) sUp[le][f][n] = a.Up[static_cast<long long>(e) * ND + n + f * N];
@@ -147,20 +143,8 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
   double g[NEQ][DIM];
   double det = 1.0;
   if (active) {
-    // outward area-weighted normals of the six faces (affine: constant over the face)
-    for (int lf = n; lf < 6; lf += ND) {
-      double Xf[12], nor[3];
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-#pragma unroll
-        for (int d = 0; d < 3; d++) Xf[q * 3 + d] = sVx[le][c_T.face_vert[lf][q] * 3 + d];
-      face_normal(Xf, 0.5, 0.5, nor);
-      sNor[le][lf][0] = nor[0];
-      sNor[le][lf][1] = nor[1];
-      sNor[le][lf][2] = nor[2];
-    }
     double J[9], A[9];
-    hex_jacobian_affine(sVx[le], J);
+    hex_jacobian(sVx[le], sXn[i], sXn[j], sXn[k], J);
     det = det3(J);
     adj3(J, A);
     const double idet = 1.0 / det;
@@ -188,6 +172,17 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
     for (int t = n; t < 6 * NF2; t += ND) {
       const int lf = t / NF2, ab = t % NF2, fa = ab % NP, fb = ab / NP;
       const int nbr = sNbr[le][lf];
+      {  // outward CalcOrtho normal at this face node (bilinear over the face of a trilinear hexahedron)
+        double Xf[12], nor[3];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int d = 0; d < 3; d++) Xf[q * 3 + d] = sVx[le][sFv[lf][q] * 3 + d];
+        face_normal(Xf, sXn[fa], sXn[fb], nor);
+        sNor[le][lf][ab][0] = nor[0];
+        sNor[le][lf][ab][1] = nor[1];
+        sNor[le][lf][ab][2] = nor[2];
+      }
       if (nbr < 0) {  // boundary face: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
 #pragma unroll
         for (int f = 0; f < NEQ; f++) sJ[le][lf][f][ab] = 0.0;
@@ -222,7 +217,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
       const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
       const int ab = (fp.ss ? ia : NP - 1 - ia) + NP * (fp.st ? ib : NP - 1 - ib);
       const double coef = sLb[fp.side][c] / (sWn[c] * det);
-      const double n0 = sNor[le][lf][0], n1 = sNor[le][lf][1], n2 = sNor[le][lf][2];
+      const double n0 = sNor[le][lf][ab][0], n1 = sNor[le][lf][ab][1], n2 = sNor[le][lf][ab][2];
 #pragma unroll
       for (int f = 0; f < NEQ; f++) {
         const double v = coef * sJ[le][lf][f][ab];
@@ -460,7 +455,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
   __shared__ double sVx[EPB][24];
-  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
+  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP], sXn[NP];
   __shared__ int sFace[EPB][6], sFcode[EPB][6], sFp[6];
   __shared__ __align__(16) double sR[EPB][6][NEQ * NF2];  // face residual blocks of the six faces (cp.async)
   __shared__ unsigned long long sMaxBits;
@@ -471,6 +466,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
   if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
   if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
   if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  if (threadIdx.x < NP) sXn[threadIdx.x] = c_T.xn[threadIdx.x];
   if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
   if (threadIdx.x == 0) sMaxBits = 0ull;
   if (active) {
@@ -519,7 +515,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
       }
     }
     double J[9], A[9];
-    hex_jacobian_affine(sVx[le], J);
+    hex_jacobian(sVx[le], sXn[i], sXn[j], sXn[k], J);
     det = det3(J);
     adj3(J, A);
     wnode = sWn[i] * sWn[j] * sWn[k];

@@ -198,11 +198,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
                       (phys->sutherland_Pr * (phys->specific_heat_ratio - 1.));
 
   const int NE = c->NE, NEH = c->NEH;
-  for (int e = 0; e < NE; e++)
-    if (!element_is_affine(&maps->elem_vertices[static_cast<size_t>(e) * 24])) {
-      delete c;
-      return fail(nullptr, TPSB_ENOTIMPL, "element %d is not a parallelepiped: curved/trilinear metric path not built yet", e);
-    }
+  bool all_affine = true;
+  for (int e = 0; e < NE && all_affine; e++) all_affine = element_is_affine(&maps->elem_vertices[static_cast<size_t>(e) * 24]);
 
   // ---- derive the index maps (M2ulPhyS::initIndirectionArrays, src/M2ulPhyS.cpp:816-1075) ----
   std::vector<int> e2f(static_cast<size_t>(7) * NE, 0);
@@ -276,8 +273,9 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   c->n_pb_elems = NE - c->n_int_elems;
 
   // ---- fast path tables (rhs_fast.cuh): affine metric per element, per-face block ids / normals ----
-  c->fast = true;
-  if (const char *pth = getenv("TPSB_PATH")) c->fast = strcmp(pth, "legacy") != 0;
+  // all-parallelepiped meshes run the fast path; anything else (trilinear/skewed elements) the general one
+  c->fast = all_affine;
+  if (const char *pth = getenv("TPSB_PATH")) c->fast = c->fast && strcmp(pth, "legacy") != 0 && strcmp(pth, "general") != 0;
   std::vector<double> geo, face_nor;
   std::vector<int4> face_desc;
   std::vector<int> send_blk;
