@@ -123,6 +123,10 @@ struct Oracle {
   std::vector<double> vx;  // [NE][8][3]
   std::vector<int> f_el1, f_el2, f_inf1, f_inf2;
   std::vector<std::vector<int>> el_faces;  // interior faces per element, ascending (element_to_faces)
+  std::vector<std::vector<int>> el_bfaces;  // boundary faces per element
+  std::vector<int> f_attr;                  // boundary attribute per face (0 on interior faces)
+  std::vector<OrcBc> bcs;                   // BCintegrator's attribute -> boundary condition maps
+  int use_bc_in_grad = 0;                   // boundaryConditions/useBCinGrad (src/M2ulPhyS.cpp:3480)
   std::vector<double> nodes1d;
   int nqv1 = 0, nqf1 = 0, nqv = 0, nqf = 0;
   std::vector<double> qxv, qwv, qxf, qwf;
@@ -242,6 +246,116 @@ struct Oracle {
     cross3(&Jf[0], &Jf[3], nor);
   }
 
+  // ---- boundary conditions (restated from src/BCintegrator.cpp, wallBC.cpp, inletBC.cpp, outletBC.cpp) ----
+  const OrcBc *bc_of_face(int f) const {
+    for (const OrcBc &b : bcs)
+      if (b.attr == f_attr[f]) return &b;
+    return nullptr;
+  }
+  void set_bcs(const int *face_attr, int nbc, const OrcBc *b, int use_in_grad) {
+    f_attr.assign(face_attr, face_attr + NF);
+    bcs.assign(b, b + nbc);
+    use_bc_in_grad = use_in_grad;
+    el_bfaces.assign(NE, {});
+    for (int f = 0; f < NF; f++)
+      if (f_el2[f] < 0) {
+        el_bfaces[f_el1[f]].push_back(f);
+        shape_table(f_inf1[f]);
+      }
+  }
+  // BoundaryCondition::computeBdrPrimitiveStateForGradient (src/BoundaryCondition.cpp:55: copy) and the
+  // WallBC override (src/wallBC.cpp:241-266: only VISC_ISOTH changes anything)
+  void bc_prim_for_gradient(const OrcBc &b, const double *primIn, double *primBC) const {
+    for (int eq = 0; eq < neq; eq++) primBC[eq] = primIn[eq];
+    if (b.kind == 2 && b.type == 3) {  // WallType VISC_ISOTH
+      for (int i = 0; i < nvel; i++) primBC[1 + i] = 0.0;
+      primBC[nvel + 1] = b.data[0];
+    }
+  }
+  // BCintegrator::computeBdrFlux (src/BCintegrator.cpp:228-242) dispatching to the per-type routines
+  void bc_flux(const OrcBc &b, const double *normal, const double *stateIn, const double *gradState, double *xyz,
+               double delta, double *bdrFlux) const {
+    double state2[16], wallState[16], viscF[48], wallViscF[16], unitN[3], primFlux[16];
+    bool idx[16];
+    for (int i = 0; i < 16; i++) {
+      primFlux[i] = 0.0;
+      idx[i] = false;
+    }
+    const int nsp = ph->num_species();
+    double normN = 0.;
+    for (int d = 0; d < dim; d++) normN += normal[d] * normal[d];
+    for (int d = 0; d < dim; d++) unitN[d] = normal[d] * (1. / sqrt(normN));  // "unitNorm *= 1. / sqrt(normN)"
+    if (b.kind == 0) {
+      if (b.type != 2) return;  // InletType SUB_DENS_VEL only
+      // InletBC::subsonicReflectingDensityVelocity (src/inletBC.cpp:729-756)
+      const double pr = ph->pressure(stateIn);
+      for (int eq = 0; eq < neq; eq++) state2[eq] = stateIn[eq];
+      state2[0] = b.data[0];
+      state2[1] = b.data[0] * b.data[1];
+      state2[2] = b.data[0] * b.data[2];
+      if (nvel == 3) state2[3] = b.data[0] * b.data[3];
+      ph->modify_energy_for_pressure(state2, state2, pr, true);
+      ph->riemann(stateIn, state2, normal, bdrFlux);
+    } else if (b.kind == 1) {
+      if (b.type != 0) return;  // OutletType SUB_P only
+      // OutletBC::subsonicReflectingPressure (src/outletBC.cpp:731-737)
+      ph->modify_energy_for_pressure(stateIn, state2, b.data[0], false);
+      ph->riemann(stateIn, state2, normal, bdrFlux);
+    } else if (b.type == 0) {
+      // WallBC::computeINVwallFlux (src/wallBC.cpp:277-320)
+      double vel[3], un[3];
+      for (int d = 0; d < nvel; d++) vel[d] = stateIn[1 + d] / stateIn[0];
+      double norm = sqrt(normN);
+      for (int d = 0; d < dim; d++) un[d] = normal[d] / norm;
+      double vn = 0;
+      for (int d = 0; d < dim; d++) vn += vel[d] * un[d];
+      for (int eq = 0; eq < neq; eq++) state2[eq] = stateIn[eq];
+      state2[1] = stateIn[0] * (vel[0] - 2. * vn * un[0]);
+      state2[2] = stateIn[0] * (vel[1] - 2. * vn * un[1]);
+      if (dim == 3) state2[3] = stateIn[0] * (vel[2] - 2. * vn * un[2]);
+      ph->riemann(stateIn, state2, normal, bdrFlux);
+      double viscFw[48];
+      ph->visc_flux(state2, gradState, xyz, delta, 0.0, viscFw);
+      for (int eq = 0; eq < neq; eq++) {
+        wallViscF[eq] = 0.;
+        for (int d = 0; d < dim; d++) wallViscF[eq] += viscFw[eq + d * neq] * normal[d];
+      }
+      ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
+      for (int eq = 1; eq < neq; eq++) {
+        bdrFlux[eq] -= 0.5 * wallViscF[eq];
+        for (int d = 0; d < dim; d++) bdrFlux[eq] -= 0.5 * viscF[eq + d * neq] * normal[d];
+      }
+    } else if (b.type == 2 || b.type == 3) {
+      if (b.type == 2) {
+        // WallBC::computeAdiabaticWallFlux (src/wallBC.cpp:430-469); bcFlux_: species + heat flux prescribed 0 (:88-96)
+        ph->stagnation_state(stateIn, wallState);
+        ph->riemann(stateIn, wallState, normal, bdrFlux);
+        ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
+        for (int i = 0; i < nsp; i++) idx[i] = true;
+        idx[nsp + nvel] = true;
+        ph->bdr_visc_flux(wallState, gradState, xyz, delta, 0.0, unitN, primFlux, idx, wallViscF);
+      } else {
+        // WallBC::computeIsothermalWallFlux (src/wallBC.cpp:471-510); bcFlux_: species flux prescribed 0 (:97-110)
+        for (int eq = 0; eq < neq; eq++) wallState[eq] = stateIn[eq];
+        if (use_bc_in_grad) {
+          for (int i = 0; i < nvel; i++) wallState[i + 1] *= -1.0;
+        } else {
+          ph->stagnant_state_with_temp(stateIn, b.data[0], wallState);
+        }
+        ph->riemann(stateIn, wallState, normal, bdrFlux);
+        ph->stagnant_state_with_temp(stateIn, b.data[0], wallState);
+        for (int i = 0; i < nsp; i++) idx[i] = true;
+        ph->bdr_visc_flux(wallState, gradState, xyz, delta, 0.0, unitN, primFlux, idx, wallViscF);
+        ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
+      }
+      for (int eq = 0; eq < neq; eq++) wallViscF[eq] *= sqrt(normN);
+      for (int eq = 1; eq < neq; eq++) {
+        bdrFlux[eq] -= 0.5 * wallViscF[eq];
+        for (int d = 0; d < dim; d++) bdrFlux[eq] -= 0.5 * viscF[eq + d * neq] * normal[d];
+      }
+    }
+  }
+
   void setup() {
     np = p + 1;
     dof = np * np * np;
@@ -343,9 +457,12 @@ struct Oracle {
     std::vector<double> fc(static_cast<size_t>(NF) * 2 * dof * nd, 0.0);
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 16)
     for (int f = 0; f < NF; f++) {
-      if (f_el2[f] < 0) continue;
-      const int e1 = f_el1[f], e2 = f_el2[f];
-      const std::vector<double> &sh1 = shapeTab.at(f_inf1[f]), &sh2 = shapeTab.at(f_inf2[f]);
+      const bool bdr = f_el2[f] < 0;
+      const OrcBc *bc = bdr && !bcs.empty() ? bc_of_face(f) : nullptr;
+      if (bdr && (bcs.empty() || f_attr.empty())) continue;  // no boundary integrator registered
+      const int e1 = f_el1[f], e2 = bdr ? e1 : f_el2[f];
+      // Elem2No < 0: shape2 = shape1 (src/faceGradientIntegration.cpp:88-90)
+      const std::vector<double> &sh1 = shapeTab.at(f_inf1[f]), &sh2 = shapeTab.at(bdr ? f_inf1[f] : f_inf2[f]);
       double *v1 = &fc[(static_cast<size_t>(f) * 2 + 0) * dof * nd];
       double *v2 = &fc[(static_cast<size_t>(f) * 2 + 1) * dof * nd];
       double iUp1[16], iUp2[16], mean[16], du1n[48], du2n[48], nor[3], xyz[3];
@@ -354,11 +471,21 @@ struct Oracle {
         for (int eq = 0; eq < neq; eq++) {
           double a = 0, b = 0;
           for (int k = 0; k < dof; k++) a += Up[static_cast<size_t>(e1) * dof + k + eq * N] * s1[k];
-          for (int k = 0; k < dof; k++) b += Up[static_cast<size_t>(e2) * dof + k + eq * N] * s2[k];
+          if (!bdr)
+            for (int k = 0; k < dof; k++) b += Up[static_cast<size_t>(e2) * dof + k + eq * N] * s2[k];
           iUp1[eq] = a;
           iUp2[eq] = b;
-          mean[eq] = 0.5 * a;
-          mean[eq] += 0.5 * b;
+        }
+        if (bdr) {  // src/faceGradientIntegration.cpp:96-115
+          if (use_bc_in_grad && bc) {
+            bc_prim_for_gradient(*bc, iUp1, iUp2);
+          } else {
+            for (int eq = 0; eq < neq; eq++) iUp2[eq] = iUp1[eq];
+          }
+        }
+        for (int eq = 0; eq < neq; eq++) {
+          mean[eq] = 0.5 * iUp1[eq];
+          mean[eq] += 0.5 * iUp2[eq];
         }
         face_geom(f, q, nor, xyz);
         const double w = qwf[q % nqf1] * qwf[q / nqf1];
@@ -393,6 +520,11 @@ struct Oracle {
         const double *v = &fc[(static_cast<size_t>(f) * 2 + side) * dof * nd];
         for (size_t i = 0; i < fsum.size(); i++) fsum[i] += v[i];
       }
+      if (!el_bfaces.empty())
+        for (int f : el_bfaces[e]) {  // boundary faces: only Elem1's block is added (MFEM NonlinearForm::Mult)
+          const double *v = &fc[(static_cast<size_t>(f) * 2 + 0) * dof * nd];
+          for (size_t i = 0; i < fsum.size(); i++) fsum[i] += v[i];
+        }
       for (size_t i = 0; i < rhs.size(); i++) rhs[i] += fsum[i];
       // Me_inv (src/gradients.cpp:209-227)
       const double *mi = &Me_inv[e * d2];
@@ -470,6 +602,41 @@ struct Oracle {
           }
       }
     }
+    // ---- A->Mult boundary faces: BCintegrator::AssembleFaceVector (src/BCintegrator.cpp:295-441)
+    if (!bcs.empty())
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 16)
+      for (int f = 0; f < NF; f++) {
+        if (f_el2[f] >= 0) continue;
+        const OrcBc *bc = bc_of_face(f);
+        if (!bc) continue;
+        const int e1 = f_el1[f];
+        const std::vector<double> &sh1 = shapeTab.at(f_inf1[f]);
+        double *v1 = &fz[(static_cast<size_t>(f) * 2 + 0) * dof * neq];
+        const double delta = elSize[e1];
+        double u1[16], g1[48], nor[3], xyz[3], fluxN[16];
+        for (int q = 0; q < nqf; q++) {
+          const double *s1 = &sh1[static_cast<size_t>(q) * dof];
+          for (int eq = 0; eq < neq; eq++) {
+            double a = 0;
+            for (int k = 0; k < dof; k++) a += x[static_cast<size_t>(e1) * dof + k + eq * N] * s1[k];
+            const int sp = eq - nvel - 2;
+            u1[eq] = (sp >= 0 && sp < nact) ? std::max(a, 0.0) : a;
+            for (int d = 0; d < 3; d++) {
+              double b = 0;
+              const double *ga = &gradUp[static_cast<size_t>(e1) * dof + eq * N + static_cast<size_t>(d) * neq * N];
+              for (int k = 0; k < dof; k++) b += ga[k] * s1[k];
+              g1[eq + d * neq] = b;
+            }
+          }
+          face_geom(f, q, nor, xyz);
+          for (int eq = 0; eq < neq; eq++) fluxN[eq] = 0.;
+          bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN);
+          const double w = qwf[q % nqf1] * qwf[q / nqf1];
+          for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
+          for (int k = 0; k < dof; k++)
+            for (int eq = 0; eq < neq; eq++) v1[k * neq + eq] -= fluxN[eq] * s1[k];
+        }
+      }
     // ---- GetFlux (src/rhs_operator.cpp:493-559), Aflux->AddMult (:379-391), Me_inv (:432-448)
     const size_t d2 = static_cast<size_t>(dof) * dof;
     std::vector<double> mcs_t(nthreads, 0.0);
@@ -485,6 +652,11 @@ struct Oracle {
         const double *v = &fz[(static_cast<size_t>(f) * 2 + side) * dof * neq];
         for (size_t i = 0; i < z.size(); i++) z[i] += v[i];
       }
+      if (!el_bfaces.empty())
+        for (int f : el_bfaces[e]) {
+          const double *v = &fz[(static_cast<size_t>(f) * 2 + 0) * dof * neq];
+          for (size_t i = 0; i < z.size(); i++) z[i] += v[i];
+        }
       for (int n = 0; n < dof; n++) {
         const size_t i = static_cast<size_t>(e) * dof + n;
         double st[16], g[48], fc[48], fv[48], xyz[3];
@@ -567,6 +739,21 @@ void *orc_create(int order, int NE, const double *vx, int NF, const int *el1, co
   }
   o->setup();
   return o;
+}
+// boundary attribute per face (0 on interior faces) and BCintegrator's attribute maps
+void orc_set_bcs(void *h, const int *face_attr, int nbc, const OrcBc *bcs, int use_bc_in_grad) {
+  static_cast<Oracle *>(h)->set_bcs(face_attr, nbc, bcs, use_bc_in_grad);
+}
+// one boundary flux evaluation (test probe): BCintegrator::computeBdrFlux
+void orc_bc_flux(void *h, const OrcBc *bc, int use_bc_in_grad, const double *normal, const double *stateIn,
+                 const double *gradState, double *flux) {
+  Oracle *o = static_cast<Oracle *>(h);
+  const int save = o->use_bc_in_grad;
+  o->use_bc_in_grad = use_bc_in_grad;
+  double xyz[3] = {0, 0, 0};
+  for (int eq = 0; eq < o->neq; eq++) flux[eq] = 0.;
+  o->bc_flux(*bc, normal, stateIn, gradState, xyz, 0.0, flux);
+  o->use_bc_in_grad = save;
 }
 void orc_destroy(void *h) {
   Oracle *o = static_cast<Oracle *>(h);

@@ -24,6 +24,13 @@ struct OrcPhysParams {
   double bulk_visc_mult;
   double C1, S0, Pr;  // Sutherland data (src/dataStructures.hpp:205-209)
 };
+// One boundary condition of BCintegrator's attribute maps (src/BCintegrator.cpp:64-125).
+// kind: 0 inlet, 1 outlet, 2 wall; type: the reference's InletType / OutletType / WallType value
+// (src/dataStructures.hpp:168-196); data: inlet inputState (rho, u, v, w), outlet inputState (p), wall Th.
+struct OrcBc {
+  int attr, kind, type;
+  double data[8];
+};
 }
 
 namespace orc {
@@ -45,6 +52,18 @@ struct Physics {
   // RiemannSolverTPS::Eval (useRoe = false -> Eval_LF)
   virtual void riemann(const double *U1, const double *U2, const double *nor, double *flux) = 0;
   virtual int num_active_species() const = 0;
+  // ---- used by the boundary conditions ----
+  virtual int num_species() const = 0;
+  // GasMixture::ComputePressure
+  virtual double pressure(const double *U) = 0;
+  // GasMixture::computeStagnationState / computeStagnantStateWithTemp / modifyEnergyForPressure
+  virtual void stagnation_state(const double *U, double *out) = 0;
+  virtual void stagnant_state_with_temp(const double *U, double T, double *out) = 0;
+  virtual void modify_energy_for_pressure(const double *in, double *out, double p, bool modifyElectronEnergy) = 0;
+  // Fluxes::ComputeBdrViscousFluxes with BoundaryViscousFluxData {normal (unit), primFlux, primFluxIdxs}
+  virtual void bdr_visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist,
+                             const double *unit_normal, const double *primFlux, const bool *primFluxIdxs,
+                             double *normalFlux) = 0;
 };
 
 // Implemented by exactly one of orc_physics_port.cpp / orc_physics_ref.cpp per library.

@@ -22,16 +22,81 @@ class DryAirPort : public Physics {
   }
   const char *kind() const override { return "port"; }
   int num_active_species() const override { return 0; }
+  int num_species() const override { return 1; }  // src/equation_of_state.cpp:154 (not NS_PASSIVE)
+  // src/equation_of_state.cpp:365-377
+  void stagnation_state(const double *U, double *out) override {
+    const double p = pressure(U);
+    for (int eq = 0; eq < neq_; eq++) out[eq] = U[eq];
+    for (int d = 0; d < nvel_; d++) out[1 + d] = 0.;
+    out[1 + nvel_] = p / (p_.gamma - 1.);
+  }
+  // src/equation_of_state.cpp:379-386
+  void stagnant_state_with_temp(const double *U, double T, double *out) override {
+    for (int eq = 0; eq < neq_; eq++) out[eq] = U[eq];
+    for (int d = 0; d < nvel_; d++) out[1 + d] = 0.;
+    out[1 + nvel_] = p_.R / (p_.gamma - 1.) * U[0] * T;
+  }
+  // src/equation_of_state.cpp:389-411
+  void modify_energy_for_pressure(const double *in, double *out, double p, bool) override {
+    double tmp[16];
+    for (int eq = 0; eq < neq_; eq++) tmp[eq] = in[eq];
+    double ke = 0.;
+    for (int d = 0; d < nvel_; d++) ke += in[1 + d] * in[1 + d];
+    ke *= 0.5 / in[0];
+    for (int eq = 0; eq < neq_; eq++) out[eq] = tmp[eq];
+    out[1 + nvel_] = p / (p_.gamma - 1.) + ke;
+  }
+  // src/fluxes.cpp:344-504 for dry air: one species with zero diffusion velocity
+  // (src/transport_properties.cpp:236-266), no species enthalpy carried to the heat flux, single temperature.
+  void bdr_visc_flux(const double *s, const double *gradUp, double * /*xyz*/, double /*delta*/, double /*dist*/,
+                     const double *nrm, const double *primFlux, const bool *primFluxIdxs, double *normalFlux) override {
+    for (int eq = 0; eq < neq_; eq++) normalFlux[eq] = 0.;
+    if (p_.eq_system == 0) return;
+    const int numSpecies = 1;
+    double pr = pressure(s);
+    double temp = pr / p_.R / s[0];
+    double visc = (p_.C1 * p_.visc_mult * pow(temp, 1.5) / (temp + p_.S0));
+    double bulkViscosity = p_.bulk_visc_mult * visc;
+    double k = cp_div_pr_ * visc;
+    bulkViscosity -= 2. / 3. * visc;
+    const int primFluxSize = numSpecies + nvel_ + 1;
+    double normalPrimFlux[16];
+    for (int eq = 0; eq < primFluxSize; eq++) normalPrimFlux[eq] = 0.0;
+    for (int i = 0; i < numSpecies; i++)
+      if (primFluxIdxs[i]) normalPrimFlux[i] = primFlux[i];
+    double stress[9];
+    double divV = 0.;
+    for (int i = 0; i < dim_; i++) {
+      for (int j = 0; j < dim_; j++)
+        stress[i + j * dim_] = gradUp[(1 + j) + i * neq_] + gradUp[(1 + i) + j * neq_];
+      divV += gradUp[(1 + i) + i * neq_];
+    }
+    for (int i = 0; i < dim_; i++)
+      for (int j = 0; j < dim_; j++) stress[i + j * dim_] *= visc;
+    for (int i = 0; i < dim_; i++) stress[i + i * dim_] += bulkViscosity * divV;
+    for (int i = 0; i < dim_; i++)
+      for (int j = 0; j < dim_; j++) normalPrimFlux[numSpecies + i] += stress[i + j * dim_] * nrm[j];
+    k += 0.0;  // ke, single temperature
+    for (int d = 0; d < dim_; d++) normalPrimFlux[numSpecies + nvel_] -= k * gradUp[(1 + nvel_) + d * neq_] * nrm[d];
+    // species enthalpy x diffusion flux: DryAir::computeSpeciesEnthalpies returns 0 (equation_of_state.cpp)
+    for (int i = numSpecies; i < primFluxSize; i++)
+      if (primFluxIdxs[i]) normalPrimFlux[i] = primFlux[i];
+    double vel0[3];
+    for (int d = 0; d < nvel_; d++) vel0[d] = s[1 + d] / s[0];
+    for (int d = 0; d < nvel_; d++) normalFlux[d + 1] = normalPrimFlux[numSpecies + d];
+    for (int d = 0; d < nvel_; d++) normalFlux[nvel_ + 1] += normalPrimFlux[numSpecies + d] * vel0[d];
+    normalFlux[nvel_ + 1] -= normalPrimFlux[numSpecies + nvel_];
+  }
 
   // src/equation_of_state.hpp:610-617 (DryAir::ComputePressure)
-  double pressure(const double *s) const {
+  double pressure(const double *s) override {
     double den_vel2 = 0;
     for (int d = 0; d < nvel_; d++) den_vel2 += s[d + 1] * s[d + 1];
     den_vel2 /= s[0];
     return (p_.gamma - 1.0) * (s[1 + nvel_] - 0.5 * den_vel2);
   }
   // src/equation_of_state.hpp:621-627 (DryAir::ComputeTemperature)
-  double temperature(const double *s) const {
+  double temperature(const double *s) {
     double den_vel2 = 0;
     for (int d = 0; d < nvel_; d++) den_vel2 += s[d + 1] * s[d + 1];
     den_vel2 /= s[0];

@@ -41,6 +41,33 @@ class DryAirRef : public Physics {
   }
   const char *kind() const override { return "reference"; }
   int num_active_species() const override { return mix_->GetNumActiveSpecies(); }
+  int num_species() const override { return mix_->GetNumSpecies(); }
+  double pressure(const double *U) override { return mix_->ComputePressure(U); }
+  void stagnation_state(const double *U, double *out) override {
+    Vector a(const_cast<double *>(U), neq_), b(neq_);
+    mix_->computeStagnationState(a, b);  // equation_of_state.cpp:365
+    for (int i = 0; i < neq_; i++) out[i] = b[i];
+  }
+  void stagnant_state_with_temp(const double *U, double T, double *out) override {
+    Vector a(const_cast<double *>(U), neq_), b(neq_);
+    mix_->computeStagnantStateWithTemp(a, T, b);  // equation_of_state.cpp:379
+    for (int i = 0; i < neq_; i++) out[i] = b[i];
+  }
+  void modify_energy_for_pressure(const double *in, double *out, double p, bool mee) override {
+    double tmp[16];
+    for (int i = 0; i < neq_; i++) tmp[i] = in[i];
+    mix_->modifyEnergyForPressure(tmp, out, p, mee);  // equation_of_state.cpp:402
+  }
+  void bdr_visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, const double *nrm,
+                     const double *primFlux, const bool *primFluxIdxs, double *normalFlux) override {
+    BoundaryViscousFluxData bc;
+    for (int d = 0; d < gpudata::MAXDIM; d++) bc.normal[d] = d < dim_ ? nrm[d] : 0.0;
+    for (int i = 0; i < gpudata::MAXEQUATIONS; i++) {
+      bc.primFlux[i] = i < 16 ? primFlux[i] : 0.0;
+      bc.primFluxIdxs[i] = i < 16 ? primFluxIdxs[i] : false;
+    }
+    flux_->ComputeBdrViscousFluxes(U, gradUp, xyz, delta, dist, bc, normalFlux);  // fluxes.cpp:344
+  }
   void prim(const double *U, double *Up) override { mix_->GetPrimitivesFromConservatives(U, Up); }
   void cons(const double *Up, double *U) override { mix_->GetConservativesFromPrimitives(Up, U); }
   double max_char_speed(const double *U) override { return mix_->ComputeMaxCharSpeed(U); }

@@ -55,3 +55,24 @@ def warp_mesh(m, amp=0.08, lo=(-np.pi,) * 3, hi=(np.pi,) * 3):
     out = dict(m)
     out["elem_xyz"] = np.ascontiguousarray(xyz + amp * L / (2 * np.pi) * d)
     return out
+
+
+HEX_FACE_VERT = np.array([[3, 2, 1, 0], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [4, 5, 6, 7]])
+
+
+def box_face_attrs(m, lo, hi):
+    """Boundary attribute per face of a (non-periodic) box mesh: 1/2 = x-/x+, 3/4 = y-/y+, 5/6 = z-/z+;
+    0 on interior faces.  Uses the un-warped vertex coordinates of the face (pass the mesh before warp_mesh)."""
+    el1, el2, inf1 = m["face_el1"], m["face_el2"], m["face_inf1"]
+    attr = np.zeros(len(el1), dtype=np.int32)
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    tol = 1e-9 * np.abs(hi - lo).max()
+    for f in np.nonzero(el2 < 0)[0]:
+        c = m["elem_xyz"][el1[f], HEX_FACE_VERT[inf1[f] // 64]].mean(axis=0)
+        for d in range(3):
+            if abs(c[d] - lo[d]) < tol:
+                attr[f] = 2 * d + 1
+            elif abs(c[d] - hi[d]) < tol:
+                attr[f] = 2 * d + 2
+        assert attr[f] > 0, f
+    return attr

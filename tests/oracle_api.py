@@ -16,6 +16,18 @@ class OrcPhysParams(C.Structure):
                 ("S0", C.c_double), ("Pr", C.c_double)]
 
 
+class OrcBc(C.Structure):
+    """kind 0 inlet / 1 outlet / 2 wall; type = the reference's InletType / OutletType / WallType value."""
+    _fields_ = [("attr", C.c_int), ("kind", C.c_int), ("type", C.c_int), ("data", C.c_double * 8)]
+
+
+def make_bc(attr, kind, type_, data=()):
+    b = OrcBc(attr, kind, type_)
+    for i, v in enumerate(data):
+        b.data[i] = float(v)
+    return b
+
+
 def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0):
     """Defaults of the reference: gamma/R src/equation_of_state.cpp:175-179; Sutherland SURVEY.md 8(d)."""
     return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71)
@@ -44,6 +56,8 @@ def load(kind="port"):
     lib.orc_create.restype = C.c_void_p
     lib.orc_create.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip, _ip, C.POINTER(OrcPhysParams), C.c_int]
     lib.orc_destroy.argtypes = [C.c_void_p]
+    lib.orc_set_bcs.argtypes = [C.c_void_p, _ip, C.c_int, C.POINTER(OrcBc), C.c_int]
+    lib.orc_bc_flux.argtypes = [C.c_void_p, C.POINTER(OrcBc), C.c_int, _dp, _dp, _dp, _dp]
     lib.orc_ndofs.restype = C.c_long
     lib.orc_ndofs.argtypes = [C.c_void_p]
     lib.orc_update_primitives.argtypes = [C.c_void_p, _dp, _dp]
@@ -86,6 +100,18 @@ class Oracle:
         if getattr(self, "h", None):
             self.lib.orc_destroy(self.h)
             self.h = None
+
+    def set_bcs(self, face_attr, bcs, use_bc_in_grad=False):
+        """bcs: list of OrcBc (make_bc); face_attr: boundary attribute per face (0 on interior faces)."""
+        arr = (OrcBc * len(bcs))(*bcs)
+        self._bcs = arr
+        self.lib.orc_set_bcs(self.h, np.ascontiguousarray(face_attr, np.int32), len(bcs), arr, int(use_bc_in_grad))
+
+    def bc_flux(self, bc, normal, state, grad, use_bc_in_grad=False):
+        out = np.zeros(self.neq)
+        self.lib.orc_bc_flux(self.h, C.byref(bc), int(use_bc_in_grad), np.ascontiguousarray(normal, dtype=np.float64),
+                             np.ascontiguousarray(state, dtype=np.float64), np.ascontiguousarray(grad, dtype=np.float64), out)
+        return out
 
     def node_coords(self):
         xyz = np.zeros((self.N, 3))
