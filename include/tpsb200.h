@@ -76,6 +76,27 @@ typedef struct {
   double sutherland_C1, sutherland_S0, sutherland_Pr;
 } tpsb_physics;
 
+/* Boundary conditions: BCintegrator's attribute -> {InletBC, OutletBC, WallBC} maps (src/BCintegrator.cpp:64-125).
+ * kind selects the map, type is the reference's enum value (src/dataStructures.hpp:168-196):
+ *   inlet  : InletType  -- built: SUB_DENS_VEL (2), data = inputState {rho, u, v, w}      (src/inletBC.cpp:729-756)
+ *   outlet : OutletType -- built: SUB_P (0),        data = {p}                             (src/outletBC.cpp:731-737)
+ *   wall   : WallType   -- built: INV (0), VISC_ADIAB (2), VISC_ISOTH (3, data = {Th})     (src/wallBC.cpp:277-510)
+ * Other types return TPSB_ENOTIMPL at create.  use_bc_in_grad = boundaryConditions/useBCinGrad
+ * (src/M2ulPhyS.cpp:3480): the BR1 gradient then uses the wall state at isothermal walls
+ * (src/faceGradientIntegration.cpp:96-115) and the wall Riemann state flips (src/wallBC.cpp:476-479).  */
+enum { TPSB_BC_INLET = 0, TPSB_BC_OUTLET = 1, TPSB_BC_WALL = 2 };
+typedef struct {
+  int attr;        /* boundary attribute (patch number) the condition applies to */
+  int kind;        /* TPSB_BC_*                                                   */
+  int type;        /* InletType / OutletType / WallType value                     */
+  double data[8];
+} tpsb_bc_desc;
+typedef struct {
+  int num_bcs;
+  const tpsb_bc_desc *bcs;
+  int use_bc_in_grad;
+} tpsb_bc_set;
+
 /* Partition neighbours for the face-neighbour exchange that replaces RHSoperator::initNBlockDataTransfer /
  * waitAllDataTransfer (src/rhs_operator.cpp:716-831).  NULL / num_nbr_ranks == 0 for a serial run.  */
 typedef struct {
@@ -98,7 +119,8 @@ const char *tpsb_last_error(const tpsb_ctx *ctx); /* ctx may be NULL: error of t
  * builds every device-side table.  cuda_stream: the caller's cudaStream_t (0 = default stream);
  * all work of this context is enqueued on / ordered against it.                                   */
 int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys,
-                const tpsb_halo_desc *halo, int device, void *cuda_stream, tpsb_ctx **out);
+                const tpsb_bc_set *bcs /* NULL: no boundary faces */, const tpsb_halo_desc *halo, int device,
+                void *cuda_stream, tpsb_ctx **out);
 void tpsb_destroy(tpsb_ctx *ctx);
 
 /* vfes->GetNDofs(), num_equation */

@@ -47,6 +47,22 @@ class Physics(C.Structure):
         return cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71)
 
 
+class BcDesc(C.Structure):
+    """tpsb_bc_desc: kind 0 inlet / 1 outlet / 2 wall, type = the reference's InletType / OutletType / WallType."""
+    _fields_ = [("attr", C.c_int), ("kind", C.c_int), ("type", C.c_int), ("data", C.c_double * 8)]
+
+    @classmethod
+    def make(cls, attr, kind, type_, data=()):
+        b = cls(attr, kind, type_)
+        for i, v in enumerate(data):
+            b.data[i] = float(v)
+        return b
+
+
+class BcSet(C.Structure):
+    _fields_ = [("num_bcs", C.c_int), ("bcs", C.POINTER(BcDesc)), ("use_bc_in_grad", C.c_int)]
+
+
 class HaloDesc(C.Structure):
     _fields_ = [("num_nbr_ranks", C.c_int), ("nbr_rank", C.POINTER(C.c_int)), ("send_offset", C.POINTER(C.c_int)),
                 ("send_elems", C.POINTER(C.c_int)), ("recv_offset", C.POINTER(C.c_int)), ("nccl_comm", C.c_void_p)]
@@ -85,7 +101,7 @@ def lib():
     L.tpsb_version.restype = C.c_char_p
     L.tpsb_last_error.restype = C.c_char_p
     L.tpsb_last_error.argtypes = [vp]
-    L.tpsb_create.argtypes = [C.POINTER(MeshMaps), C.POINTER(SpaceDesc), C.POINTER(Physics), C.POINTER(HaloDesc),
+    L.tpsb_create.argtypes = [C.POINTER(MeshMaps), C.POINTER(SpaceDesc), C.POINTER(Physics), C.POINTER(BcSet), C.POINTER(HaloDesc),
                               C.c_int, vp, C.POINTER(vp)]
     L.tpsb_destroy.argtypes = [vp]
     L.tpsb_destroy.restype = None
@@ -211,7 +227,8 @@ class RhsOperator:
     """Python face of the reference's RHSoperator (src/rhs_operator.hpp:146-184) over the C ABI:
     Mult / updatePrimitives / updateGradients / getGradients, on torch CUDA tensors."""
 
-    def __init__(self, mesh, order=3, physics=None, device=0, halo=None, num_nbr_elems=0, stream=None):
+    def __init__(self, mesh, order=3, physics=None, device=0, halo=None, num_nbr_elems=0, stream=None, bcs=None,
+                 face_attr=None, use_bc_in_grad=False):
         import torch
         self.torch = torch
         self.L = lib()
@@ -221,11 +238,22 @@ class RhsOperator:
             np.ascontiguousarray(mesh[k], dtype=np.int32) for k in ("face_el1", "face_el2", "face_inf1", "face_inf2")]
         xyz, el1, el2, i1, i2 = self._keep
         self.NE = xyz.shape[0] - num_nbr_elems
-        maps = MeshMaps(3, self.NE, num_nbr_elems, _dp(xyz), len(el1), _ip(el1), _ip(el2), _ip(i1), _ip(i2), None)
+        fattr = None
+        if face_attr is not None:
+            fattr = np.ascontiguousarray(face_attr, dtype=np.int32)
+            self._keep.append(fattr)
+        maps = MeshMaps(3, self.NE, num_nbr_elems, _dp(xyz), len(el1), _ip(el1), _ip(el2), _ip(i1), _ip(i2),
+                        _ip(fattr) if fattr is not None else None)
+        bcset = None
+        if bcs:
+            arr = (BcDesc * len(bcs))(*bcs)
+            bcset = BcSet(len(bcs), arr, int(use_bc_in_grad))
+            self._keep.append(arr)
         space = SpaceDesc(order, 0, 0, 5, 3)
         self.ctx = C.c_void_p()
         s = stream if stream is not None else 0
         rc = self.L.tpsb_create(C.byref(maps), C.byref(space), C.byref(self.physics),
+                                C.byref(bcset) if bcset is not None else None,
                                 C.byref(halo) if halo is not None else None, device, C.c_void_p(s), C.byref(self.ctx))
         if rc != 0:
             raise TpsbError(f"tpsb_create failed ({rc}): {self.L.tpsb_last_error(None).decode()}")

@@ -71,10 +71,11 @@ class RHSoperator {
 
  public:
   // The reference constructor takes the FE spaces, integration rules, Fluxes, GasMixture, ... objects
-  // (src/rhs_operator.cpp:38-48); everything the device path needs from them is in these four POD blocks.
+  // (src/rhs_operator.cpp:38-48); everything the device path needs from them is in these POD blocks.
   RHSoperator(const tpsb_mesh_maps &maps, const tpsb_space_desc &space, const tpsb_physics &phys,
-              const tpsb_halo_desc *halo = nullptr, int device = 0, void *cuda_stream = nullptr) {
-    const int rc = tpsb_create(&maps, &space, &phys, halo, device, cuda_stream, &ctx_);
+              const tpsb_bc_set *bcs = nullptr, const tpsb_halo_desc *halo = nullptr, int device = 0,
+              void *cuda_stream = nullptr) {
+    const int rc = tpsb_create(&maps, &space, &phys, bcs, halo, device, cuda_stream, &ctx_);
     if (rc != TPSB_OK) throw std::runtime_error(std::string("RHSoperator: ") + tpsb_last_error(nullptr));
   }
   RHSoperator(const RHSoperator &) = delete;

@@ -184,4 +184,158 @@ __device__ __forceinline__ void dry_visc_dot_n(const PhysParams &p, const DryPoi
           k * (gT[0] * nor[0] + gT[1] * nor[1] + gT[2] * nor[2]);
 }
 
+// ---- boundary conditions (dry air) ----------------------------------------------------------------
+constexpr int MAX_BC = 8;
+struct BcDev {
+  int kind, type;  // kind: 0 inlet, 1 outlet, 2 wall; type: InletType / OutletType / WallType (dataStructures.hpp:168-196)
+  double d[4];
+};
+struct BcTable {
+  int nbc, use_bc_in_grad;
+  BcDev bc[MAX_BC];
+};
+
+// BoundaryCondition::computeBdrPrimitiveStateForGradient (BoundaryCondition.cpp:55) / WallBC override
+// (wallBC.cpp:241-266): only an isothermal wall changes the state used by the BR1 jump.
+__device__ __forceinline__ void dry_bc_prim_for_gradient(const BcDev &bc, const double *primIn, double *primBC) {
+#pragma unroll
+  for (int eq = 0; eq < NEQ; eq++) primBC[eq] = primIn[eq];
+  if (bc.kind == 2 && bc.type == 3) {
+    primBC[1] = 0.0;
+    primBC[2] = 0.0;
+    primBC[3] = 0.0;
+    primBC[4] = bc.d[0];
+  }
+}
+
+// Fluxes::ComputeBdrViscousFluxes (fluxes.cpp:344-504) for dry air: one species with zero diffusion velocity,
+// no species-enthalpy term, single temperature.  nrm = unit normal; heat_prescribed: primFluxIdxs[numSpecies+nvel]
+// with value 0 (adiabatic wall).  g[eq + d*NEQ].
+__device__ __forceinline__ void dry_bdr_visc_flux(const PhysParams &p, const double *s, const double *g, const double *nrm,
+                                                  bool heat_prescribed, double *nf) {
+#pragma unroll
+  for (int eq = 0; eq < NEQ; eq++) nf[eq] = 0.;
+  if (p.eq_system == 0) return;
+  const double pr = dry_pressure(p, s);
+  const double temp = pr / p.R / s[0];
+  const double visc = (p.C1 * p.visc_mult * (temp * sqrt(temp)) / (temp + p.S0));
+  double bulk = p.bulk_visc_mult * visc;
+  const double k = p.cp_div_pr * visc;
+  bulk -= 2. / 3. * visc;
+  double stress[DIM * DIM];
+  double divV = 0.;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) {
+#pragma unroll
+    for (int j = 0; j < DIM; j++) stress[i + j * DIM] = g[(1 + j) + i * NEQ] + g[(1 + i) + j * NEQ];
+    divV += g[(1 + i) + i * NEQ];
+  }
+#pragma unroll
+  for (int i = 0; i < DIM * DIM; i++) stress[i] *= visc;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) stress[i + i * DIM] += bulk * divV;
+  double sn[DIM], q = 0.;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) {
+    sn[i] = 0.;
+#pragma unroll
+    for (int j = 0; j < DIM; j++) sn[i] += stress[i + j * DIM] * nrm[j];
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; d++) q -= k * g[4 + d * NEQ] * nrm[d];
+  if (heat_prescribed) q = 0.;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    nf[1 + d] = sn[d];
+    nf[4] += sn[d] * (s[1 + d] / s[0]);
+  }
+  nf[4] -= q;
+}
+
+// BCintegrator::computeBdrFlux (BCintegrator.cpp:228-242) -> InletBC::subsonicReflectingDensityVelocity
+// (inletBC.cpp:729-756), OutletBC::subsonicReflectingPressure (outletBC.cpp:731-737), WallBC::computeINVwallFlux /
+// computeAdiabaticWallFlux / computeIsothermalWallFlux (wallBC.cpp:277-320, 430-510).  g[eq + d*NEQ] interior
+// gradients of the primitives; nor = CalcOrtho normal (area weighted, outward).
+__device__ __forceinline__ void dry_bc_flux(const PhysParams &p, const BcDev &bc, int use_bc_in_grad, const double *u1,
+                                            const double *g, const double *nor, double *fx) {
+  double s2[NEQ];
+  const double normN = nor[0] * nor[0] + nor[1] * nor[1] + nor[2] * nor[2];
+  if (bc.kind == 0) {
+    const double pr = dry_pressure(p, u1);
+    s2[0] = bc.d[0];
+    s2[1] = bc.d[0] * bc.d[1];
+    s2[2] = bc.d[0] * bc.d[2];
+    s2[3] = bc.d[0] * bc.d[3];
+    double ke = s2[1] * s2[1] + s2[2] * s2[2] + s2[3] * s2[3];
+    ke *= 0.5 / s2[0];
+    s2[4] = pr / p.gm1 + ke;  // DryAir::modifyEnergyForPressure (equation_of_state.cpp:402-411)
+    dry_riemann_lf(p, u1, s2, nor, fx);
+    return;
+  }
+  if (bc.kind == 1) {
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) s2[eq] = u1[eq];
+    double ke = u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3];
+    ke *= 0.5 / u1[0];
+    s2[4] = bc.d[0] / p.gm1 + ke;
+    dry_riemann_lf(p, u1, s2, nor, fx);
+    return;
+  }
+  double viscF[NEQ * DIM], wallViscF[NEQ];
+  if (bc.type == 0) {  // INV: mirror state
+    const double norm = sqrt(normN);
+    const double un[3] = {nor[0] / norm, nor[1] / norm, nor[2] / norm};
+    const double vel[3] = {u1[1] / u1[0], u1[2] / u1[0], u1[3] / u1[0]};
+    const double vn = vel[0] * un[0] + vel[1] * un[1] + vel[2] * un[2];
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) s2[eq] = u1[eq];
+    s2[1] = u1[0] * (vel[0] - 2. * vn * un[0]);
+    s2[2] = u1[0] * (vel[1] - 2. * vn * un[1]);
+    s2[3] = u1[0] * (vel[2] - 2. * vn * un[2]);
+    dry_riemann_lf(p, u1, s2, nor, fx);
+    if (p.eq_system == 0) return;
+    dry_visc_flux(p, s2, g, viscF);
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++)
+      wallViscF[eq] = viscF[eq] * nor[0] + viscF[eq + NEQ] * nor[1] + viscF[eq + 2 * NEQ] * nor[2];
+    dry_visc_flux(p, u1, g, viscF);
+  } else {
+    const double isq = 1. / sqrt(normN);
+    const double un[3] = {nor[0] * isq, nor[1] * isq, nor[2] * isq};
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) s2[eq] = u1[eq];
+    if (bc.type == 2) {  // VISC_ADIAB: stagnation state (equation_of_state.cpp:365-377)
+      const double pr = dry_pressure(p, u1);
+      s2[1] = s2[2] = s2[3] = 0.;
+      s2[4] = pr / p.gm1;
+      dry_riemann_lf(p, u1, s2, nor, fx);
+      if (p.eq_system == 0) return;
+      dry_bdr_visc_flux(p, s2, g, un, true, wallViscF);
+    } else {  // VISC_ISOTH
+      if (use_bc_in_grad) {
+        s2[1] = -u1[1];
+        s2[2] = -u1[2];
+        s2[3] = -u1[3];
+      } else {
+        s2[1] = s2[2] = s2[3] = 0.;
+        s2[4] = p.R / p.gm1 * u1[0] * bc.d[0];  // computeStagnantStateWithTemp (equation_of_state.cpp:379-386)
+      }
+      dry_riemann_lf(p, u1, s2, nor, fx);
+      if (p.eq_system == 0) return;
+      s2[1] = s2[2] = s2[3] = 0.;
+      s2[4] = p.R / p.gm1 * u1[0] * bc.d[0];
+      dry_bdr_visc_flux(p, s2, g, un, false, wallViscF);
+    }
+    const double nm = sqrt(normN);
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) wallViscF[eq] *= nm;
+    dry_visc_flux(p, u1, g, viscF);
+  }
+#pragma unroll
+  for (int eq = 1; eq < NEQ; eq++) {
+    fx[eq] -= 0.5 * wallViscF[eq];
+    fx[eq] -= 0.5 * (viscF[eq] * nor[0] + viscF[eq + NEQ] * nor[1] + viscF[eq + 2 * NEQ] * nor[2]);
+  }
+}
+
 }  // namespace tpsb

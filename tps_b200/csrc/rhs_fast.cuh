@@ -115,8 +115,15 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
       }
       const int nbr = sNbr[le][lf];
       if (nbr < 0) {  // boundary face: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
+        if (a.bct.use_bc_in_grad && nbr <= -2) {
+          double pbc[NEQ];
+          dry_bc_prim_for_gradient(a.bct.bc[-2 - nbr], pT, pbc);
 #pragma unroll
-        for (int f = 0; f < NEQ; f++) sJ[(lf * NEQ + f) * NF2 + ab] = 0.0;
+          for (int f = 0; f < NEQ; f++) sJ[(lf * NEQ + f) * NF2 + ab] = 0.5 * (pbc[f] - pT[f]);
+        } else {
+#pragma unroll
+          for (int f = 0; f < NEQ; f++) sJ[(lf * NEQ + f) * NF2 + ab] = 0.0;
+        }
         continue;
       }
       const int code = sCode[le][lf];

@@ -38,7 +38,7 @@ struct KernelArgs {
   PhysParams phys;
   // geometry / connectivity (device)
   const double *vx;        // [(NE+NEH)][8][3]
-  const int *nbr_elem;     // [NE][6] neighbour element (>= NE: halo), -1 boundary
+  const int *nbr_elem;     // [NE][6] neighbour element (>= NE: halo); boundary face: -2 - (index into bct.bc)
   const int *nbr_code;     // [NE][6] (nbr local face) | (perm code << 3): own face coords -> neighbour face coords
   const int *face_el1, *face_el2, *face_inf1, *face_inf2;  // [NFint] compacted two-sided faces
   const int *el_face;      // [NE][6] compact face id or -1
@@ -58,6 +58,10 @@ struct KernelArgs {
   double *tr;              // [6 NE + shared faces][10][np*np] face-trace blocks
   const int4 *face_desc;   // [NFint] {block of side 1, block of side 2, perm code Elem2 face coords -> face coords, 0}
   const double *face_nor;  // [NFint][4] CalcOrtho normal (Elem1 -> Elem2, area weighted) and its magnitude
+  // boundary faces (BCintegrator): face k lifts into faceRes slot NFint + k
+  int NFbdr;
+  const int *bdr_el1, *bdr_lf, *bdr_bc;  // [NFbdr] element, local face, index into bct.bc
+  BcTable bct;
 };
 
 // ---- geometry: trilinear hexahedron from its 8 vertices (mesh nodes of order 1) ----
@@ -115,7 +119,7 @@ __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int 
 // grad_kernel / face_flux_kernel / elem_resid_kernel are templates on NP = p+1; see rhs_kernels.cu
 template <int NP, int EPB, int MINB>
 __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list);
-template <int NP, int FPB, int NT>
+template <int NP, int FPB, int NT, bool BDR>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
 template <int NP, int EPB, int MINB>
 __global__ void elem_resid_kernel(KernelArgs a);

@@ -183,12 +183,27 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
         sNor[le][lf][ab][1] = nor[1];
         sNor[le][lf][ab][2] = nor[2];
       }
+      const FacePar fp = decode_face(sFp[lf]);
       if (nbr < 0) {  // boundary face: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
+        if (a.bct.use_bc_in_grad && nbr <= -2) {
+          const int b0b = face_node_base<NP>(fp, fa, fb), csb = axis_stride<NP>(fp.an);
+          double own[NEQ], pbc[NEQ];
 #pragma unroll
-        for (int f = 0; f < NEQ; f++) sJ[le][lf][f][ab] = 0.0;
+          for (int f = 0; f < NEQ; f++) {
+            double v = 0;
+#pragma unroll
+            for (int c = 0; c < NP; c++) v += sLb[fp.side][c] * sUp[le][f][b0b + c * csb];
+            own[f] = v;
+          }
+          dry_bc_prim_for_gradient(a.bct.bc[-2 - nbr], own, pbc);
+#pragma unroll
+          for (int f = 0; f < NEQ; f++) sJ[le][lf][f][ab] = 0.5 * (pbc[f] - own[f]);
+        } else {
+#pragma unroll
+          for (int f = 0; f < NEQ; f++) sJ[le][lf][f][ab] = 0.0;
+        }
         continue;
       }
-      const FacePar fp = decode_face(sFp[lf]);
       const int code = sCode[le][lf];
       const FacePar fq = decode_face(sFp[code & 7]);
       int a2, b2;
@@ -250,7 +265,10 @@ __device__ __forceinline__ int carried_grad_field(int u) {  // u in [NEQ, NFC) -
   return (r / (NEQ - 1)) * NEQ + (r % (NEQ - 1)) + 1;
 }
 
-template <int NP, int FPB, int NT>
+// BDR = true: the faces are boundary faces (a.bdr_*): only Elem1's side exists, the numerical flux is the
+// boundary-condition flux of BCintegrator::AssembleFaceVector (src/BCintegrator.cpp:295-441) and the result
+// goes to faceRes slot NFint + k.
+template <int NP, int FPB, int NT, bool BDR>
 __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list) {
   constexpr int NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ, ND = NP * NP * NP;
   __shared__ double sT[FPB][2][NFC][NF2 + 1];  // +1: conflict-free per-(side,field) row reads
@@ -273,8 +291,9 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
       continue;
     }
     const int fc = face_list ? face_list[face_begin + slot] : face_begin + slot;
-    const int el = s ? a.face_el2[fc] : a.face_el1[fc];
-    const int inf = s ? a.face_inf2[fc] : a.face_inf1[fc];
+    if (BDR && s == 1) continue;
+    const int el = BDR ? a.bdr_el1[fc] : (s ? a.face_el2[fc] : a.face_el1[fc]);
+    const int inf = BDR ? 64 * a.bdr_lf[fc] : (s ? a.face_inf2[fc] : a.face_inf1[fc]);
     const FacePar fp = decode_face(c_T.face_par[inf / 64]);
     int fa = ab % NP, fb = ab / NP;
     if (s) {
@@ -307,7 +326,9 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
     __syncthreads();
     for (int t = tid; t < FPB * 12; t += NT) {
       const int fl = t / 12, q = t % 12, fc = sFc[fl];
-      if (fc >= 0) sXf[fl][q] = a.vx[static_cast<long long>(a.face_el1[fc]) * 24 + c_T.face_vert[a.face_inf1[fc] / 64][q / 3] * 3 + q % 3];
+      if (fc >= 0)
+        sXf[fl][q] = BDR ? a.vx[static_cast<long long>(a.bdr_el1[fc]) * 24 + c_T.face_vert[a.bdr_lf[fc]][q / 3] * 3 + q % 3]
+                         : a.vx[static_cast<long long>(a.face_el1[fc]) * 24 + c_T.face_vert[a.face_inf1[fc] / 64][q / 3] * 3 + q % 3];
     }
   }
   __syncthreads();
@@ -316,7 +337,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
   //    paid once per 17 line extrapolations (it was 57 % of the instructions when paid per field)
   for (int t = tid; t < FPB * 2 * NF2; t += NT) {
     const int ab = t % NF2, s = (t / NF2) % 2, fl = t / (2 * NF2);
-    if (sFc[fl] < 0) continue;
+    if (sFc[fl] < 0 || (BDR && s == 1)) continue;
     const int off = sOff[fl][s][ab], cs = sCs[fl][s];
     const double *lb = sLb[sSide[fl][s]];
     const bool vec = a.vec_ok != 0;
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
   //    A[b][alpha] = sum_a P[alpha][a] T[a + NP b] ;  Q[alpha + NQ beta] = sum_b P[beta][b] A[b][alpha]
   for (int t = tid; t < FPB * 2 * NFC; t += NT) {
     const int u = t % NFC, s = (t / NFC) % 2, fl = t / (2 * NFC);
-    if (sFc[fl] < 0) continue;
+    if (sFc[fl] < 0 || (BDR && s == 1)) continue;
     double A[NP][NQ];
     {
       double T[NF2];
@@ -375,9 +396,24 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 #pragma unroll
     for (int f = 0; f < NEQ; f++) {
       u1[f] = sQ[fl][0][f][qp];
-      u2[f] = sQ[fl][1][f][qp];
+      u2[f] = BDR ? 0.0 : sQ[fl][1][f][qp];
     }
     face_normal(sXf[fl], c_T.xq[al], c_T.xq[be], nor);
+    if constexpr (BDR) {
+      double g[NEQ * DIM], fxb[NEQ];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        g[0 + d * NEQ] = 0.0;  // grad(rho) never enters the dry-air fluxes
+#pragma unroll
+        for (int i = 0; i < NEQ - 1; i++) g[1 + i + d * NEQ] = sQ[fl][0][NEQ + d * (NEQ - 1) + i][qp];
+      }
+      dry_bc_flux(a.phys, a.bct.bc[a.bdr_bc[sFc[fl]]], a.bct.use_bc_in_grad, u1, g, nor, fxb);
+      const double wb = c_T.wq[al] * c_T.wq[be];
+      double *dstb = &sT[0][0][0][0] + fl * (2 * NFC * (NF2 + 1));
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) dstb[eq * NQ2 + qp] = fxb[eq] * wb;
+      continue;
+    }
     const DryPoint q1 = dry_point(a.phys, u1), q2 = dry_point(a.phys, u2);
     // Rusanov (riemann_solver.cpp:89-114)
     const double maxE = fmax(dry_char_speed_pt(a.phys, q1), dry_char_speed_pt(a.phys, q2));
@@ -443,7 +479,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
       double v = 0;
 #pragma unroll
       for (int q = 0; q < NQ; q++) v += c_T.P[q][aa] * in[q];
-      a.faceRes[(static_cast<long long>(fc) * NEQ + eq) * NF2 + aa + NP * b] = v;
+      a.faceRes[(static_cast<long long>(BDR ? a.NFint + fc : fc) * NEQ + eq) * NF2 + aa + NP * b] = v;
     }
   }
 }

@@ -44,6 +44,10 @@ struct tpsb_ctx {
   double *d_Uhalo = nullptr, *d_UpHalo = nullptr, *d_gradUpHalo = nullptr, *d_sendU = nullptr, *d_sendG = nullptr;
   unsigned long long *d_maxBits = nullptr;
   double *d_mcs = nullptr;
+  // boundary faces (BCintegrator)
+  int NFbdr = 0;
+  int *d_bdr_el1 = nullptr, *d_bdr_lf = nullptr, *d_bdr_bc = nullptr;
+  BcTable bct;
   // fast (all-affine) path
   bool fast = false;
   double *d_geo = nullptr, *d_tr = nullptr, *d_face_nor = nullptr, *d_sendTr = nullptr;
@@ -146,7 +150,7 @@ const char *tpsb_version(void) { return "tpsb200 0.1 (sm_100a, fp64)"; }
 const char *tpsb_last_error(const tpsb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys,
-                const tpsb_halo_desc *halo, int device, void *cuda_stream, tpsb_ctx **out) {
+                const tpsb_bc_set *bcs, const tpsb_halo_desc *halo, int device, void *cuda_stream, tpsb_ctx **out) {
   tpsb_ctx *ctx = nullptr;  // errors before allocation go to the thread-local create error
   if (!maps || !space || !phys || !out) return fail(ctx, TPSB_EINVAL, "null argument");
   *out = nullptr;
@@ -161,6 +165,24 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (maps->num_elems <= 0 || maps->num_faces <= 0 || !maps->elem_vertices || !maps->face_el1 || !maps->face_el2 ||
       !maps->face_inf1 || !maps->face_inf2)
     return fail(ctx, TPSB_EINVAL, "incomplete mesh maps");
+  BcTable bct;
+  memset(&bct, 0, sizeof(bct));
+  if (bcs) {
+    if (bcs->num_bcs < 0 || bcs->num_bcs > MAX_BC || (bcs->num_bcs > 0 && !bcs->bcs))
+      return fail(ctx, TPSB_EINVAL, "at most %d boundary conditions are supported", MAX_BC);
+    bct.nbc = bcs->num_bcs;
+    bct.use_bc_in_grad = bcs->use_bc_in_grad ? 1 : 0;
+    for (int i = 0; i < bcs->num_bcs; i++) {
+      const tpsb_bc_desc &b = bcs->bcs[i];
+      const bool ok = (b.kind == TPSB_BC_INLET && b.type == 2) || (b.kind == TPSB_BC_OUTLET && b.type == 0) ||
+                      (b.kind == TPSB_BC_WALL && (b.type == 0 || b.type == 2 || b.type == 3));
+      if (!ok)
+        return fail(ctx, TPSB_ENOTIMPL, "boundary condition kind %d type %d (attribute %d) not built yet", b.kind, b.type, b.attr);
+      bct.bc[i].kind = b.kind;
+      bct.bc[i].type = b.type;
+      for (int k = 0; k < 4; k++) bct.bc[i].d[k] = b.data[k];
+    }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(ctx, TPSB_ECUDA, "no CUDA device: libtpsb200 has no CPU fallback");
@@ -185,6 +207,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     delete c;
     return fail(nullptr, TPSB_EINVAL, "reference tables");
   }
+  c->bct = bct;
   c->phys.eq_system = phys->eq_system;
   c->phys.gamma = phys->specific_heat_ratio;
   c->phys.R = phys->gas_constant;
@@ -204,13 +227,26 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   // ---- derive the index maps (M2ulPhyS::initIndirectionArrays, src/M2ulPhyS.cpp:816-1075) ----
   std::vector<int> e2f(static_cast<size_t>(7) * NE, 0);
   std::vector<int> fl_el1, fl_el2, fl_inf1, fl_inf2, sh_el1, sh_el2, sh_inf1, sh_inf2;
+  std::vector<int> b_el1, b_lf, b_bc;
   for (int f = 0; f < c->NF; f++) {
     const int e1 = maps->face_el1[f], e2 = maps->face_el2[f];
     if (e1 < 0 || e1 >= NE || e2 >= NE + NEH) {
       delete c;
       return fail(nullptr, TPSB_EINVAL, "face %d has invalid elements (%d,%d)", f, e1, e2);
     }
-    if (e2 < 0) continue;  // boundary face: handled by the BC integrators
+    if (e2 < 0) {  // boundary face: BCintegrator (src/BCintegrator.cpp:127-197 builds the same per-patch lists)
+      const int attr = maps->face_attr ? maps->face_attr[f] : 0;
+      int ibc = -1;
+      for (int i = 0; bcs && i < bcs->num_bcs; i++)
+        if (bcs->bcs[i].attr == attr) ibc = i;
+      const int lf = maps->face_inf1[f] / 64;
+      if (ibc < 0 || lf < 0 || lf > 5) {
+        delete c;
+        return fail(nullptr, TPSB_EINVAL, "boundary face %d (attribute %d) has no boundary condition", f, attr);
+      }
+      b_el1.push_back(e1), b_lf.push_back(lf), b_bc.push_back(ibc);
+      continue;
+    }
     // element_to_faces: interior (incl. shared) faces in ascending face order
     int nf = e2f[7 * e1];
     if (nf >= 6) {
@@ -262,6 +298,12 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     } else {
       touches_shared[e1] = 1;
     }
+  }
+  c->NFbdr = static_cast<int>(b_el1.size());
+  for (int k = 0; k < c->NFbdr; k++) {
+    nbr_elem[b_el1[k] * 6 + b_lf[k]] = -2 - b_bc[k];
+    el_face[b_el1[k] * 6 + b_lf[k]] = c->NFint + k;  // lifted like Elem1's side: elvect -= phi Fhat w
+    el_face_code[b_el1[k] * 6 + b_lf[k]] = 0;
   }
   std::vector<int> elem_list;
   elem_list.reserve(NE);
@@ -359,7 +401,11 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   const size_t nb = static_cast<size_t>(c->N) * sizeof(double);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * NEQ);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUp, nb * NEQ * DIM);
-  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_faceRes, static_cast<size_t>(c->NFint) * NEQ * c->np * c->np * sizeof(double));
+  if (ce == cudaSuccess)
+    ce = cudaMalloc(&c->d_faceRes, static_cast<size_t>(c->NFint + c->NFbdr) * NEQ * c->np * c->np * sizeof(double));
+  if (ce == cudaSuccess) ce = upload(&c->d_bdr_el1, b_el1);
+  if (ce == cudaSuccess) ce = upload(&c->d_bdr_lf, b_lf);
+  if (ce == cudaSuccess) ce = upload(&c->d_bdr_bc, b_bc);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_maxBits, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_mcs, sizeof(double));
   if (ce == cudaSuccess) ce = cudaMemset(c->d_maxBits, 0, sizeof(unsigned long long));
@@ -455,7 +501,7 @@ void tpsb_destroy(tpsb_ctx *c) {
                   c->d_faceRes,  c->d_Uhalo,     c->d_UpHalo,       c->d_gradUpHalo, c->d_sendU,   c->d_sendG,
                   c->d_maxBits,  c->d_mcs,       c->d_send_elems,   c->d_k,        c->d_yv,       c->d_z,
                   c->d_hx,       c->d_hy,        c->d_geo,          c->d_tr,       c->d_face_nor, c->d_sendTr,
-                  c->d_face_desc, c->d_send_blk};
+                  c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -506,6 +552,11 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   a.faceRes = c->d_faceRes;
   a.y = d_y;
   a.maxCharBits = c->d_maxBits;
+  a.NFbdr = c->NFbdr;
+  a.bdr_el1 = c->d_bdr_el1;
+  a.bdr_lf = c->d_bdr_lf;
+  a.bdr_bc = c->d_bdr_bc;
+  a.bct = c->bct;
   a.geo = c->d_geo;
   a.tr = c->d_tr;
   a.face_desc = c->d_face_desc;
@@ -528,7 +579,19 @@ template <int NP, int FPB, int NTF>
 static void launch_face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (count <= 0) return;
   ProfScope ps(c, K_FACE);
-  face_flux_kernel<NP, FPB, NTF><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
+  face_flux_kernel<NP, FPB, NTF, false><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
+}
+// boundary faces: BCintegrator (src/BCintegrator.cpp:295-441), same kernel in one-sided mode
+static void bdr_faces(tpsb_ctx *c, const KernelArgs &a) {
+  const int count = c->NFbdr;
+  if (count <= 0) return;
+  ProfScope ps(c, K_FACE);
+  if (c->np == 4)
+    face_flux_kernel<4, 4, 160, true><<<(count + 3) / 4, 160, 0, c->stream>>>(a, 0, count, nullptr);
+  else if (c->np == 3)
+    face_flux_kernel<3, 4, 128, true><<<(count + 3) / 4, 128, 0, c->stream>>>(a, 0, count, nullptr);
+  else
+    face_flux_kernel<2, 8, 128, true><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
 }
 template <int NP, int EPB, int MINB = 1>
 static void launch_resid(tpsb_ctx *c, const KernelArgs &a) {
@@ -764,6 +827,7 @@ static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   } else {
     face_fast(c, a, 0, c->NFint);
   }
+  bdr_faces(c, a);
   resid(c, a);
   CU(cudaGetLastError());
   return TPSB_OK;
@@ -786,6 +850,7 @@ static int run_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   } else {
     DISPATCH(c, face(c, a, 0, c->NFint));
   }
+  bdr_faces(c, a);
   DISPATCH(c, resid(c, a));
   CU(cudaGetLastError());
   return TPSB_OK;
