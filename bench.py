@@ -165,6 +165,11 @@ def run_reference(args, rank):
 
 def workload_config(args, grid, sample_n=None):
     n = args.n
+    if getattr(args, "workload", "tgv") == "cyl3d":
+        return {"workload": "C2 cyl3d restated on a hex O-grid (trilinear elements, inlet/outlet/isothermal wall), "
+                            "DG p=3 GL/GL, dry-air Navier-Stokes", "elements_per_gpu": f"{n}x{4 * n}x{n}", "order": 3,
+                "num_equation": 5, "rank_grid": "1x1x1",
+                "l2_policy": "inputs exceed the 126 MB L2 for n >= 32; no flush needed"}
     cfg = {"workload": "C5 synthetic periodic 3-D hex box (compressible Taylor-Green), DG p=3 GL/GL, dry-air "
                        "Navier-Stokes, Re=1600, M0=0.1",
            "elements_per_gpu": f"{n}^3", "global_elements": f"{n * grid[0]}x{n * grid[1]}x{n * grid[2]}",
@@ -185,6 +190,9 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=12, help="elements per direction of the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tgv", choices=["tgv", "cyl3d"],
+                    help="tgv: BASELINE config C5 (the headline line); cyl3d: config C2 restated on a hex O-grid "
+                         "(general trilinear path + boundary conditions), single GPU, development measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -231,7 +239,15 @@ def main():
     hi = tuple(PI * g for g in grid)
     phys = tps_b200.Physics.dry_air(1, tgv_visc_mult())
     t_setup = time.perf_counter()
-    if world == 1:
+    if args.workload == "cyl3d":
+        assert world == 1, "the cyl3d development workload is single-GPU"
+        mesh = tps_b200.cylinder_ogrid_mesh(n, 4 * n, n)
+        specs = [(1, 2, 3, (300.0,)), (2, 0, 2, (1.2, 20.0, 0.0, 0.0)), (3, 1, 0, (101300.0,))]
+        op = tps_b200.RhsOperator(mesh, order=3, physics=tps_b200.Physics.dry_air(1, 50.0), device=local_rank,
+                                  face_attr=mesh["face_attr"], use_bc_in_grad=True,
+                                  bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+        NE = 4 * n ** 3
+    elif world == 1:
         mesh = tps_b200.cartesian_hex_mesh(n, n, n, lo=lo, hi=hi, order_mode=1)
         op = tps_b200.RhsOperator(mesh, order=3, physics=phys, device=local_rank)
         NE = n ** 3
@@ -263,9 +279,15 @@ def main():
         e1 = min(NE, e0 + chunk)
         X = torch.einsum("na,ead->end", shp, ev[e0:e1]).reshape(-1, 3)
         x, y, z = X[:, 0], X[:, 1], X[:, 2]
-        u = V0 * torch.sin(x) * torch.cos(y) * torch.cos(z)
-        v = -V0 * torch.cos(x) * torch.sin(y) * torch.cos(z)
-        p = p0 + rho0 * V0 * V0 / 16.0 * (torch.cos(2 * x) + torch.cos(2 * y)) * (torch.cos(2 * z) + 2.0)
+        if args.workload == "cyl3d":  # potential-flow-like start around the cylinder (u -> 20 m/s far away)
+            r2 = x * x + y * y
+            u = 20.0 * (1.0 - 0.25 / r2)
+            v = 2.0 * torch.sin(3 * x) * torch.cos(2 * y) * (1.0 - 0.25 / r2)
+            p = 102300.0 + 50.0 * torch.cos(x) * torch.cos(y)
+        else:
+            u = V0 * torch.sin(x) * torch.cos(y) * torch.cos(z)
+            v = -V0 * torch.cos(x) * torch.sin(y) * torch.cos(z)
+            p = p0 + rho0 * V0 * V0 / 16.0 * (torch.cos(2 * x) + torch.cos(2 * y)) * (torch.cos(2 * z) + 2.0)
         sl = slice(e0 * 64, e1 * 64)
         U[0 * N:1 * N][sl] = rho0
         U[1 * N:2 * N][sl] = rho0 * u

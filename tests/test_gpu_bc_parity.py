@@ -88,3 +88,31 @@ def test_unsupported_bc_and_missing_bc_are_reported(lib_built):
         tps_b200.RhsOperator(m, order=2, face_attr=attr, bcs=[tps_b200.BcDesc.make(1, 2, 0)])
     with pytest.raises(tps_b200.TpsbError, match="not built"):
         tps_b200.RhsOperator(m, order=2, face_attr=attr, bcs=[tps_b200.BcDesc.make(a, 1, 2) for a in range(1, 7)])
+
+
+def test_cylinder_ogrid_parity(lib_built, oracle_built):
+    """BASELINE config C2 restated on hexahedra: O-grid around a unit-diameter cylinder, p = 3,
+    inlet rho = 1.2, u = (20, 0, 0), outlet p = 101300, isothermal wall 300 K with useBCinGrad
+    (test/inputs/input.4iters.cyl.ini), 2560 trilinear elements."""
+    import torch
+    m = tps_b200.cylinder_ogrid_mesh(10, 32, 8)
+    specs = [(1, 2, 3, (300.0,)), (2, 0, 2, (1.2, 20.0, 0.0, 0.0)), (3, 1, 0, (101300.0,))]
+    phys = tps_b200.Physics.dry_air(1, 50.0, 0.0)
+    op = tps_b200.RhsOperator(m, order=3, physics=phys, face_attr=m["face_attr"], use_bc_in_grad=True,
+                              bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+    orc = oracle_api.Oracle(3, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(1, 50.0, 0.0))
+    orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], True)
+    N = orc.N
+    xyz = orc.node_coords()
+    rng = np.random.default_rng(20261018)
+    rho, p = 1.2, 102300.0
+    r = np.hypot(xyz[:, 0], xyz[:, 1])
+    u = 20.0 * (1.0 - (0.5 / r) ** 2)  # potential-flow-like, vanishing at the wall
+    U = np.concatenate([np.full(N, rho), rho * u, np.zeros(N), np.zeros(N), p / 0.4 + 0.5 * rho * u * u])
+    U *= 1.0 + 0.01 * rng.uniform(-1, 1, size=U.shape)
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    yo = orc.mult(U)
+    for k in range(5):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k
+    assert abs(op.max_char_speed() / orc.max_char_speed - 1) < 1e-13

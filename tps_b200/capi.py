@@ -161,6 +161,37 @@ def cartesian_hex_mesh(nx, ny, nz, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), pe
                 face_inf1=inf1[:nf].copy(), face_inf2=inf2[:nf].copy())
 
 
+HEX_FACE_VERT = np.array([[3, 2, 1, 0], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [4, 5, 6, 7]])
+
+
+def cylinder_ogrid_mesh(nr, nth, nz, r_in=0.5, r_out=10.0, lz=2.0, stretch=1.08, order_mode=0):
+    """meshkit: O-grid of trilinear hexahedra around a cylinder of diameter 2*r_in, extruded (periodic) in z --
+    the hex restatement of the reference's cyl3d case (BASELINE config C2; its tet mesh is an LFS pointer).
+    Built from the (r, theta, z) box: theta periodic, geometric radial stretching.  Returns the mesh dict plus
+    'face_attr': 1 cylinder wall, 2 inlet (outer boundary, x < 0), 3 outlet (outer boundary, x >= 0)."""
+    m = cartesian_hex_mesh(nr, nth, nz, lo=(0.0, 0.0, 0.0), hi=(1.0, 2 * np.pi, lz), periodic=(0, 1, 1),
+                           order_mode=order_mode)
+    s, th, z = m["elem_xyz"][..., 0], m["elem_xyz"][..., 1], m["elem_xyz"][..., 2]
+    k = np.rint(s * nr)  # radial vertex index
+    if abs(stretch - 1.0) < 1e-12:
+        r = r_in + (r_out - r_in) * k / nr
+    else:
+        r = r_in + (r_out - r_in) * (stretch ** k - 1.0) / (stretch ** nr - 1.0)
+    xyz = np.stack([r * np.cos(th), r * np.sin(th), z], axis=-1)
+    el1, el2, inf1 = m["face_el1"], m["face_el2"], m["face_inf1"]
+    attr = np.zeros(len(el1), dtype=np.int32)
+    for f in np.nonzero(el2 < 0)[0]:
+        fv = HEX_FACE_VERT[inf1[f] // 64]
+        kk = k[el1[f], fv]
+        if np.all(kk == 0):
+            attr[f] = 1
+        else:
+            attr[f] = 2 if xyz[el1[f], fv, 0].mean() < 0 else 3
+    m["elem_xyz"] = np.ascontiguousarray(xyz)
+    m["face_attr"] = attr
+    return m
+
+
 def ref_tables(order):
     """Unpack tpsb_get_ref_tables into a dict (test hook)."""
     buf = np.zeros(4096)
