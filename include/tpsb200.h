@@ -189,6 +189,13 @@ int tpsb_mk_cartesian_hex(int nx, int ny, int nz, const double lo[3], const doub
 int tpsb_mk_build_faces(int num_elems, const int *elem_verts, int *face_el1, int *face_el2, int *face_inf1,
                         int *face_inf2);
 
+/* 2-D counterparts (quadrilaterals, Geometry::Constants<SQUARE> vertex/edge order; the meshes utils/beam_mesh.cpp
+ * makes for the 2-D test cases): elem_verts [NE][4], elem_xyz [NE][4][2]; arrays of 4*num_elems ints suffice.   */
+int tpsb_mk_cartesian_quad(int nx, int ny, const double lo[2], const double hi[2], const int periodic[2],
+                           int *elem_verts, double *elem_xyz);
+int tpsb_mk_build_faces2d(int num_elems, const int *elem_verts, int *face_el1, int *face_el2, int *face_inf1,
+                          int *face_inf2);
+
 /* Structured block partition of the same box over a procs[0] x procs[1] x procs[2] rank grid (rank index
  * x-fastest): the stand-in for Mesh::GeneratePartitioning + ParMesh's face-neighbour tables
  * (src/M2ulPhyS.cpp:332,362,421; ExchangeFaceNbrData).  Local elements come first, then the

@@ -3,16 +3,17 @@
 // load it.
 //
 // CPU restatement of the reference's *CPU* branch of RHSoperator::Mult
-// (src/rhs_operator.cpp:343-464) for 3-D hexahedral DG meshes, using the same DENSE
-// per-element operators the reference builds (Me_inv, Ke, the (F,grad w) element blocks of
-// Aflux) and the same per-face / per-quadrature-point loops -- deliberately NOT
-// sum-factorised, so it is independent of the CUDA kernels it checks.
+// (src/rhs_operator.cpp:343-464) for tensor-product DG meshes (quadrilaterals in 2-D, hexahedra in
+// 3-D; Gauss-Legendre or Gauss-Lobatto nodes and rules), using the same DENSE per-element operators
+// the reference builds (Me_inv, Ke, the (F,grad w) element blocks of Aflux) and the same per-face /
+// per-quadrature-point loops -- deliberately NOT sum-factorised, so it is independent of the CUDA
+// kernels it checks.
 //
 // MFEM (third party, >=4.4, absent from /root/reference) supplies the mesh/FE conventions
 // the reference relies on; they are restated here from MFEM's documented behaviour
 //  and are "parity unpinned" until an MFEM build exists:
-//   hex vertex / face-vertex / quad-orientation tables, FaceElementTransformations Loc1/Loc2,
-//   CalcOrtho, IntegrationRules, L2 tensor basis ordering, RK4Solver tableau.
+//   vertex / face-vertex / orientation tables of SQUARE and CUBE, FaceElementTransformations
+//   Loc1/Loc2, CalcOrtho, IntegrationRules, L2 tensor basis ordering, RK4Solver tableau.
 // Per-point physics goes through orc::Physics (port or the reference's own object code).
 #include <algorithm>
 #include <cmath>
@@ -29,13 +30,16 @@
 
 namespace orc {
 
-// ---- MFEM geometry constants [MFEM fem/geom.cpp: Geometry::Constants<CUBE/SQUARE>] ----
+// ---- MFEM geometry constants [MFEM fem/geom.cpp: Geometry::Constants<CUBE/SQUARE/SEGMENT>] ----
 static const double HEX_VERT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
                                       {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
 static const int HEX_FACE_VERT[6][4] = {{3, 2, 1, 0}, {0, 1, 5, 4}, {1, 2, 6, 5},
                                         {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
 static const int QUAD_ORIENT[8][4] = {{0, 1, 2, 3}, {0, 3, 2, 1}, {1, 2, 3, 0}, {1, 0, 3, 2},
                                       {2, 3, 0, 1}, {2, 1, 0, 3}, {3, 0, 1, 2}, {3, 2, 1, 0}};
+static const double QUAD_VERT[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+static const int QUAD_EDGE_VERT[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};
+static const int SEG_ORIENT[2][2] = {{0, 1}, {1, 0}};
 
 static inline void cross3(const double *a, const double *b, double *c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
@@ -80,49 +84,55 @@ static void invert_dense(std::vector<double> &a, int n) {
   a.swap(inv);
 }
 
-// smallest singular value of a 3x3 matrix (Mesh::GetElementSize(e, 1) -> J.CalcSingularvalue(dim-1))
-static double min_singular_3x3(const double *J) {
-  double A[3][3];
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
+// smallest singular value of a dim x dim matrix, column-major with leading dimension dim
+// (Mesh::GetElementSize(e, 1) -> J.CalcSingularvalue(dim-1))
+static double min_singular(const double *J, int dim) {
+  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < dim; i++)
+    for (int j = 0; j < dim; j++) {
       double s = 0;
-      for (int k = 0; k < 3; k++) s += J[k + 3 * i] * J[k + 3 * j];
+      for (int k = 0; k < dim; k++) s += J[k + dim * i] * J[k + dim * j];
       A[i][j] = s;
     }
   // cyclic Jacobi on symmetric A
   for (int sweep = 0; sweep < 50; sweep++) {
-    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    double off = 0;
+    for (int p = 0; p < dim; p++)
+      for (int q = p + 1; q < dim; q++) off += fabs(A[p][q]);
     if (off < 1e-300) break;
-    for (int p = 0; p < 2; p++)
-      for (int q = p + 1; q < 3; q++) {
+    for (int p = 0; p < dim - 1; p++)
+      for (int q = p + 1; q < dim; q++) {
         if (fabs(A[p][q]) < 1e-300) continue;
         double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
         double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < dim; k++) {
           double akp = A[k][p], akq = A[k][q];
           A[k][p] = c * akp - s * akq;
           A[k][q] = s * akp + c * akq;
         }
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < dim; k++) {
           double apk = A[p][k], aqk = A[q][k];
           A[p][k] = c * apk - s * aqk;
           A[q][k] = s * apk + c * aqk;
         }
       }
   }
-  double m = std::min(A[0][0], std::min(A[1][1], A[2][2]));
+  double m = A[0][0];
+  for (int i = 1; i < dim; i++) m = std::min(m, A[i][i]);
   return sqrt(std::max(m, 0.0));
 }
 
 struct Oracle {
   int dim = 3, p = 0, np = 0, dof = 0, NE = 0, NF = 0, neq = 5, nvel = 3, nthreads = 1;
-  long N = 0;  // vfes->GetNDofs()
+  int basis_type = 0, int_rule = 0;  // flow/basisType, flow/integrationRule: 0 Gauss-Legendre, 1 Gauss-Lobatto
+  int nv = 8;                        // vertices per element
+  long N = 0;                        // vfes->GetNDofs()
   OrcPhysParams phys;
   Physics *ph = nullptr;
-  std::vector<double> vx;  // [NE][8][3]
+  std::vector<double> vx;  // [NE][nv][dim]
   std::vector<int> f_el1, f_el2, f_inf1, f_inf2;
-  std::vector<std::vector<int>> el_faces;  // interior faces per element, ascending (element_to_faces)
+  std::vector<std::vector<int>> el_faces;   // interior faces per element, ascending (element_to_faces)
   std::vector<std::vector<int>> el_bfaces;  // boundary faces per element
   std::vector<int> f_attr;                  // boundary attribute per face (0 on interior faces)
   std::vector<OrcBc> bcs;                   // BCintegrator's attribute -> boundary condition maps
@@ -132,44 +142,60 @@ struct Oracle {
   std::vector<double> qxv, qwv, qxf, qwf;
   std::vector<double> Me_inv, Ke, Kfl;  // per element dense
   std::vector<double> elSize;           // per element delta = h_min / order
-  std::vector<double> nodeXYZ;          // [NE][dof][3]
+  std::vector<double> nodeXYZ;          // [NE][dof][dim]
   std::map<int, std::vector<double>> shapeTab;  // inf code -> [nqf][dof]
   // work
   std::vector<double> Up, gradUp;
   double max_char_speed = 0;
 
-  // ---- element geometry: trilinear map from the 8 vertices (mesh nodes of order 1) ----
+  // ---- element geometry: multilinear map from the 2^dim vertices (mesh nodes of order 1) ----
+  double vref(int a, int d) const { return dim == 3 ? HEX_VERT[a][d] : QUAD_VERT[a][d]; }
   void elem_map(int e, const double *xi, double *x, double *J) const {
-    const double *v = &vx[static_cast<size_t>(e) * 24];
-    double N[8], dN[8][3];
-    for (int a = 0; a < 8; a++) {
-      double fx = HEX_VERT[a][0] ? xi[0] : 1 - xi[0], gx = HEX_VERT[a][0] ? 1 : -1;
-      double fy = HEX_VERT[a][1] ? xi[1] : 1 - xi[1], gy = HEX_VERT[a][1] ? 1 : -1;
-      double fz = HEX_VERT[a][2] ? xi[2] : 1 - xi[2], gz = HEX_VERT[a][2] ? 1 : -1;
-      N[a] = fx * fy * fz;
-      dN[a][0] = gx * fy * fz;
-      dN[a][1] = fx * gy * fz;
-      dN[a][2] = fx * fy * gz;
+    const double *v = &vx[static_cast<size_t>(e) * nv * dim];
+    double Nn[8], dN[8][3];
+    for (int a = 0; a < nv; a++) {
+      double f[3], g[3];
+      for (int d = 0; d < dim; d++) {
+        f[d] = vref(a, d) ? xi[d] : 1 - xi[d];
+        g[d] = vref(a, d) ? 1 : -1;
+      }
+      double prod = 1;
+      for (int d = 0; d < dim; d++) prod *= f[d];
+      Nn[a] = prod;
+      for (int d = 0; d < dim; d++) {
+        double q = g[d];
+        for (int d2 = 0; d2 < dim; d2++)
+          if (d2 != d) q *= f[d2];
+        dN[a][d] = q;
+      }
     }
     if (x)
-      for (int i = 0; i < 3; i++) {
+      for (int i = 0; i < dim; i++) {
         double s = 0;
-        for (int a = 0; a < 8; a++) s += N[a] * v[a * 3 + i];
+        for (int a = 0; a < nv; a++) s += Nn[a] * v[a * dim + i];
         x[i] = s;
       }
-    if (J)  // column-major J(i,j) = dx_i/dxi_j at J[i + 3*j]
-      for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
+    if (J)  // column-major J(i,j) = dx_i/dxi_j at J[i + dim*j]
+      for (int i = 0; i < dim; i++)
+        for (int j = 0; j < dim; j++) {
           double s = 0;
-          for (int a = 0; a < 8; a++) s += dN[a][j] * v[a * 3 + i];
-          J[i + 3 * j] = s;
+          for (int a = 0; a < nv; a++) s += dN[a][j] * v[a * dim + i];
+          J[i + dim * j] = s;
         }
   }
-  static double det3(const double *J) {
+  double det(const double *J) const {
+    if (dim == 2) return J[0] * J[3] - J[2] * J[1];
     return J[0] * (J[4] * J[8] - J[5] * J[7]) - J[3] * (J[1] * J[8] - J[2] * J[7]) + J[6] * (J[1] * J[5] - J[2] * J[4]);
   }
   // adjugate, column-major: adj(J) = det(J) * inv(J)
-  static void adj3(const double *J, double *A) {
+  void adj(const double *J, double *A) const {
+    if (dim == 2) {
+      A[0] = J[3];
+      A[1] = -J[1];
+      A[2] = -J[2];
+      A[3] = J[0];
+      return;
+    }
     A[0 + 3 * 0] = J[4] * J[8] - J[7] * J[5];
     A[0 + 3 * 1] = J[6] * J[5] - J[3] * J[8];
     A[0 + 3 * 2] = J[3] * J[7] - J[6] * J[4];
@@ -180,70 +206,95 @@ struct Oracle {
     A[2 + 3 * 1] = J[3] * J[2] - J[0] * J[5];
     A[2 + 3 * 2] = J[0] * J[4] - J[3] * J[1];
   }
-  // L2 tensor basis, lexicographic x fastest
-  void calc_shape(const double *xi, double *shape, double *dshape /*[dof][3] row-major or NULL*/) const {
-    double vx_[16], vy_[16], vz_[16], dx_[16], dy_[16], dz_[16];
-    lagrange(nodes1d, xi[0], vx_, dx_);
-    lagrange(nodes1d, xi[1], vy_, dy_);
-    lagrange(nodes1d, xi[2], vz_, dz_);
-    for (int k = 0; k < np; k++)
-      for (int j = 0; j < np; j++)
-        for (int i = 0; i < np; i++) {
-          int n = i + np * (j + np * k);
-          shape[n] = vx_[i] * vy_[j] * vz_[k];
-          if (dshape) {
-            dshape[n * 3 + 0] = dx_[i] * vy_[j] * vz_[k];
-            dshape[n * 3 + 1] = vx_[i] * dy_[j] * vz_[k];
-            dshape[n * 3 + 2] = vx_[i] * vy_[j] * dz_[k];
-          }
+  // L2 tensor basis, lexicographic x fastest; dshape [dof][dim] row-major or NULL
+  void calc_shape(const double *xi, double *shape, double *dshape) const {
+    double v[3][16], d[3][16];
+    for (int a = 0; a < dim; a++) lagrange(nodes1d, xi[a], v[a], d[a]);
+    for (int n = 0; n < dof; n++) {
+      int idx[3] = {n % np, (n / np) % np, n / (np * np)};
+      double s = 1;
+      for (int a = 0; a < dim; a++) s *= v[a][idx[a]];
+      shape[n] = s;
+      if (dshape)
+        for (int a = 0; a < dim; a++) {
+          double q = d[a][idx[a]];
+          for (int b = 0; b < dim; b++)
+            if (b != a) q *= v[b][idx[b]];
+          dshape[n * dim + a] = q;
         }
+    }
   }
-  // [MFEM Mesh::GetLocalQuadToHexTransformation]: face reference (s,t) -> element reference
-  // point for info code inf = 64*local_face + orientation; dloc = d(xi)/d(s,t) (3x2, col-major).
-  static void loc_map(int inf, double s, double t, double *xi, double *dloc) {
-    const int *hv = HEX_FACE_VERT[inf / 64];
-    const int *qo = QUAD_ORIENT[inf % 64];
-    const double Nq[4] = {(1 - s) * (1 - t), s * (1 - t), s * t, (1 - s) * t};
-    const double dNs[4] = {-(1 - t), (1 - t), t, -t};
-    const double dNt[4] = {-(1 - s), -s, s, (1 - s)};
-    for (int i = 0; i < 3; i++) {
-      double a = 0, b = 0, c = 0;
-      for (int j = 0; j < 4; j++) {
-        const double vj = HEX_VERT[hv[qo[j]]][i];
-        a += Nq[j] * vj;
-        b += dNs[j] * vj;
-        c += dNt[j] * vj;
+  // [MFEM Mesh::GetLocalQuadToHexTransformation / GetLocalSegToQuadTransformation]: face reference point
+  // -> element reference point for info code inf = 64*local_face + orientation; dloc = d(xi)/d(s[,t])
+  // (dim x (dim-1), column-major).
+  void loc_map(int inf, const double *st, double *xi, double *dloc) const {
+    if (dim == 3) {
+      const double s = st[0], t = st[1];
+      const int *hv = HEX_FACE_VERT[inf / 64];
+      const int *qo = QUAD_ORIENT[inf % 64];
+      const double Nq[4] = {(1 - s) * (1 - t), s * (1 - t), s * t, (1 - s) * t};
+      const double dNs[4] = {-(1 - t), (1 - t), t, -t};
+      const double dNt[4] = {-(1 - s), -s, s, (1 - s)};
+      for (int i = 0; i < 3; i++) {
+        double a = 0, b = 0, c = 0;
+        for (int j = 0; j < 4; j++) {
+          const double vj = HEX_VERT[hv[qo[j]]][i];
+          a += Nq[j] * vj;
+          b += dNs[j] * vj;
+          c += dNt[j] * vj;
+        }
+        xi[i] = a;
+        if (dloc) {
+          dloc[i + 3 * 0] = b;
+          dloc[i + 3 * 1] = c;
+        }
       }
-      xi[i] = a;
-      if (dloc) {
-        dloc[i + 3 * 0] = b;
-        dloc[i + 3 * 1] = c;
+    } else {
+      const double s = st[0];
+      const int *ev = QUAD_EDGE_VERT[inf / 64];
+      const int *so = SEG_ORIENT[inf % 64];
+      for (int i = 0; i < 2; i++) {
+        const double v0 = QUAD_VERT[ev[so[0]]][i], v1 = QUAD_VERT[ev[so[1]]][i];
+        xi[i] = (1 - s) * v0 + s * v1;
+        if (dloc) dloc[i] = v1 - v0;
       }
     }
   }
+  void face_point(int q, double *st) const {
+    st[0] = qxf[q % nqf1];
+    st[1] = dim == 3 ? qxf[q / nqf1] : 0.0;
+  }
+  double face_weight(int q) const { return dim == 3 ? qwf[q % nqf1] * qwf[q / nqf1] : qwf[q]; }
   const std::vector<double> &shape_table(int inf) {
     auto it = shapeTab.find(inf);
     if (it != shapeTab.end()) return it->second;
     std::vector<double> tab(static_cast<size_t>(nqf) * dof);
     for (int q = 0; q < nqf; q++) {
-      double s = qxf[q % nqf1], t = qxf[q / nqf1], xi[3];
-      loc_map(inf, s, t, xi, nullptr);
+      double st[2], xi[3];
+      face_point(q, st);
+      loc_map(inf, st, xi, nullptr);
       calc_shape(xi, &tab[static_cast<size_t>(q) * dof], nullptr);
     }
     return shapeTab.emplace(inf, std::move(tab)).first->second;
   }
   // face geometry at quadrature point q of face f: CalcOrtho(Tr.Jacobian()) and Tr.Transform
   void face_geom(int f, int q, double *nor, double *xyz) const {
-    double s = qxf[q % nqf1], t = qxf[q / nqf1], xi[3], dloc[6], J[9], Jf[6];
-    loc_map(f_inf1[f], s, t, xi, dloc);
+    double st[2], xi[3], dloc[6], J[9], Jf[6];
+    face_point(q, st);
+    loc_map(f_inf1[f], st, xi, dloc);
     elem_map(f_el1[f], xi, xyz, J);
-    for (int i = 0; i < 3; i++)
-      for (int c = 0; c < 2; c++) {
+    for (int i = 0; i < dim; i++)
+      for (int c = 0; c < dim - 1; c++) {
         double a = 0;
-        for (int k = 0; k < 3; k++) a += J[i + 3 * k] * dloc[k + 3 * c];
-        Jf[i + 3 * c] = a;
+        for (int k = 0; k < dim; k++) a += J[i + dim * k] * dloc[k + dim * c];
+        Jf[i + dim * c] = a;
       }
-    cross3(&Jf[0], &Jf[3], nor);
+    if (dim == 3) {
+      cross3(&Jf[0], &Jf[3], nor);
+    } else {  // [MFEM CalcOrtho, 2x1 Jacobian]: n = (dy/ds, -dx/ds)
+      nor[0] = Jf[1];
+      nor[1] = -Jf[0];
+    }
   }
 
   // ---- boundary conditions (restated from src/BCintegrator.cpp, wallBC.cpp, inletBC.cpp, outletBC.cpp) ----
@@ -313,6 +364,7 @@ struct Oracle {
       state2[1] = stateIn[0] * (vel[0] - 2. * vn * un[0]);
       state2[2] = stateIn[0] * (vel[1] - 2. * vn * un[1]);
       if (dim == 3) state2[3] = stateIn[0] * (vel[2] - 2. * vn * un[2]);
+      if ((nvel == 3) && (dim == 2)) state2[3] = stateIn[0] * vel[2];
       ph->riemann(stateIn, state2, normal, bdrFlux);
       double viscFw[48];
       ph->visc_flux(state2, gradState, xyz, delta, 0.0, viscFw);
@@ -358,18 +410,31 @@ struct Oracle {
 
   void setup() {
     np = p + 1;
-    dof = np * np * np;
+    nv = 1 << dim;
+    dof = 1;
+    for (int d = 0; d < dim; d++) dof *= np;
     N = static_cast<long>(NE) * dof;
     std::vector<double> wtmp;
-    gauss_legendre01(np, nodes1d, wtmp);  // BasisType::GaussLegendre nodes
+    // DG_FECollection(order, dim, basisType): GaussLegendre (open) or GaussLobatto (closed) nodes
+    if (basis_type == 0)
+      gauss_legendre01(np, nodes1d, wtmp);
+    else
+      gauss_lobatto01(np, nodes1d, wtmp);
     // volume rule: order 2p (src/rhs_operator.cpp:181, src/gradients.cpp:97, src/domain_integrator.cpp:69)
-    nqv1 = gl_npts_for_order(2 * p);
-    gauss_legendre01(nqv1, qxv, qwv);
-    nqv = nqv1 * nqv1 * nqv1;
-    // face rule: min(OrderW1,OrderW2) + 2p, OrderW(trilinear hex) = 1*3-1 = 2 (src/face_integrator.cpp:233-243)
-    nqf1 = gl_npts_for_order(2 + 2 * p);
-    gauss_legendre01(nqf1, qxf, qwf);
-    nqf = nqf1 * nqf1;
+    nqv1 = int_rule == 0 ? gl_npts_for_order(2 * p) : gll_npts_for_order(2 * p);
+    // face rule: min(OrderW1,OrderW2) + 2p, OrderW(multilinear map) = dim - 1 (src/face_integrator.cpp:233-243)
+    nqf1 = int_rule == 0 ? gl_npts_for_order(dim - 1 + 2 * p) : gll_npts_for_order(dim - 1 + 2 * p);
+    if (int_rule == 0) {
+      gauss_legendre01(nqv1, qxv, qwv);
+      gauss_legendre01(nqf1, qxf, qwf);
+    } else {
+      gauss_lobatto01(nqv1, qxv, qwv);
+      gauss_lobatto01(nqf1, qxf, qwf);
+    }
+    nqv = 1;
+    for (int d = 0; d < dim; d++) nqv *= nqv1;
+    nqf = 1;
+    for (int d = 0; d < dim - 1; d++) nqf *= nqf1;
 
     el_faces.assign(NE, {});
     for (int f = 0; f < NF; f++) {
@@ -382,43 +447,46 @@ struct Oracle {
 
     const size_t d2 = static_cast<size_t>(dof) * dof;
     Me_inv.assign(NE * d2, 0.0);
-    Ke.assign(NE * d2 * 3, 0.0);
-    Kfl.assign(NE * d2 * 3, 0.0);
+    Ke.assign(NE * d2 * dim, 0.0);
+    Kfl.assign(NE * d2 * dim, 0.0);
     elSize.assign(NE, 0.0);
-    nodeXYZ.assign(static_cast<size_t>(N) * 3, 0.0);
+    nodeXYZ.assign(static_cast<size_t>(N) * dim, 0.0);
 #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int e = 0; e < NE; e++) {
-      std::vector<double> shape(dof), dshape(dof * 3), Me(d2, 0.0), phys(dof * 3), dsdx(dof * 3);
-      double *ke = &Ke[e * d2 * 3], *kf = &Kfl[e * d2 * 3];
+      std::vector<double> shape(dof), dshape(dof * dim), Me(d2, 0.0), physd(dof * dim), dsdx(dof * dim);
+      double *ke = &Ke[e * d2 * dim], *kf = &Kfl[e * d2 * dim];
       for (int q = 0; q < nqv; q++) {
-        const int qi = q % nqv1, qj = (q / nqv1) % nqv1, qk = q / (nqv1 * nqv1);
-        const double xi[3] = {qxv[qi], qxv[qj], qxv[qk]};
-        const double w = qwv[qi] * qwv[qj] * qwv[qk];
+        const int qi[3] = {q % nqv1, (q / nqv1) % nqv1, q / (nqv1 * nqv1)};
+        double xi[3] = {0, 0, 0}, w = 1;
+        for (int d = 0; d < dim; d++) {
+          xi[d] = qxv[qi[d]];
+          w *= qwv[qi[d]];
+        }
         double J[9], A[9];
         elem_map(e, xi, nullptr, J);
-        const double det = det3(J);
-        adj3(J, A);
+        const double dt = det(J);
+        adj(J, A);
         calc_shape(xi, shape.data(), dshape.data());
         // MassIntegrator (src/rhs_operator.cpp:179-185)
         for (int i = 0; i < dof; i++)
-          for (int j = 0; j < dof; j++) Me[i * dof + j] += w * det * shape[i] * shape[j];
+          for (int j = 0; j < dof; j++) Me[i * dof + j] += w * dt * shape[i] * shape[j];
         // CalcPhysDShape = dshape * inv(J); dshapedx = dshape * adj(J)
         for (int k = 0; k < dof; k++)
-          for (int d = 0; d < 3; d++) {
+          for (int d = 0; d < dim; d++) {
             double a = 0;
-            for (int r = 0; r < 3; r++) a += dshape[k * 3 + r] * A[r + 3 * d];
-            dsdx[k * 3 + d] = a;
-            phys[k * 3 + d] = a / det;
+            for (int r = 0; r < dim; r++) a += dshape[k * dim + r] * A[r + dim * d];
+            dsdx[k * dim + d] = a;
+            physd[k * dim + d] = a / dt;
           }
         // Ke(j, k + d*dof) += shape(j) * dshape(k,d) * detJac  (src/gradients.cpp:112-120)
-        const double detJac = det * w;
-        for (int d = 0; d < 3; d++)
+        const double detJac = dt * w;
+        for (int d = 0; d < dim; d++)
           for (int k = 0; k < dof; k++)
-            for (int j = 0; j < dof; j++) ke[j * (3 * dof) + k + d * dof] += shape[j] * phys[k * 3 + d] * detJac;
+            for (int j = 0; j < dof; j++) ke[j * (dim * dof) + k + d * dof] += shape[j] * physd[k * dim + d] * detJac;
         // elmat(j, k + d*dof) += (shape(k)*w) * dshapedx(j,d)  (src/domain_integrator.cpp:71-97)
-        for (int d = 0; d < 3; d++)
+        for (int d = 0; d < dim; d++)
           for (int j = 0; j < dof; j++)
-            for (int k = 0; k < dof; k++) kf[j * (3 * dof) + k + d * dof] += shape[k] * w * dsdx[j * 3 + d];
+            for (int k = 0; k < dof; k++) kf[j * (dim * dof) + k + d * dof] += shape[k] * w * dsdx[j * dim + d];
       }
       invert_dense(Me, dof);
       std::copy(Me.begin(), Me.end(), &Me_inv[e * d2]);
@@ -427,16 +495,16 @@ struct Oracle {
         const double c[3] = {0.5, 0.5, 0.5};
         double J[9];
         elem_map(e, c, nullptr, J);
-        elSize[e] = min_singular_3x3(J) / p;
+        elSize[e] = min_singular(J, dim) / p;
       }
       // node coordinates (mesh->GetNodes into a byNODES L2 space, src/rhs_operator.cpp:139-142)
       for (int n = 0; n < dof; n++) {
-        const double xi[3] = {nodes1d[n % np], nodes1d[(n / np) % np], nodes1d[n / (np * np)]};
-        elem_map(e, xi, &nodeXYZ[(static_cast<size_t>(e) * dof + n) * 3], nullptr);
+        const double xi[3] = {nodes1d[n % np], nodes1d[(n / np) % np], dim == 3 ? nodes1d[n / (np * np)] : 0.0};
+        elem_map(e, xi, &nodeXYZ[(static_cast<size_t>(e) * dof + n) * dim], nullptr);
       }
     }
     Up.assign(static_cast<size_t>(N) * neq, 0.0);
-    gradUp.assign(static_cast<size_t>(N) * neq * 3, 0.0);
+    gradUp.assign(static_cast<size_t>(N) * neq * dim, 0.0);
   }
 
   // src/rhs_operator.cpp:641-649
@@ -452,7 +520,7 @@ struct Oracle {
 
   // src/gradients.cpp:144-232 with GradFaceIntegrator (src/faceGradientIntegration.cpp:40-140)
   void compute_gradients() {
-    const int nd = neq * 3;
+    const int nd = neq * dim;
     // face contributions, one private buffer per face side, gathered in face order below
     std::vector<double> fc(static_cast<size_t>(NF) * 2 * dof * nd, 0.0);
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 16)
@@ -488,9 +556,9 @@ struct Oracle {
           mean[eq] += 0.5 * iUp2[eq];
         }
         face_geom(f, q, nor, xyz);
-        const double w = qwf[q % nqf1] * qwf[q / nqf1];
-        for (int d = 0; d < 3; d++) nor[d] *= w;
-        for (int d = 0; d < 3; d++)
+        const double w = face_weight(q);
+        for (int d = 0; d < dim; d++) nor[d] *= w;
+        for (int d = 0; d < dim; d++)
           for (int eq = 0; eq < neq; eq++) {
             du1n[eq + d * neq] = (mean[eq] - iUp1[eq]) * nor[d];
             du2n[eq + d * neq] = (iUp2[eq] - mean[eq]) * nor[d];
@@ -506,13 +574,13 @@ struct Oracle {
 #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int e = 0; e < NE; e++) {
       std::vector<double> rhs(static_cast<size_t>(dof) * nd, 0.0), fsum(static_cast<size_t>(dof) * nd, 0.0);
-      const double *ke = &Ke[e * d2 * 3];
+      const double *ke = &Ke[e * d2 * dim];
       // volume: elGradUp(j, eq + d*neq) = sum_k Ke(j, k + d*dof) * elUp(k, eq)  (src/gradients.cpp:174-182)
       for (int eq = 0; eq < neq; eq++)
-        for (int d = 0; d < 3; d++)
+        for (int d = 0; d < dim; d++)
           for (int j = 0; j < dof; j++) {
             double a = 0;
-            for (int k = 0; k < dof; k++) a += ke[j * (3 * dof) + k + d * dof] * Up[static_cast<size_t>(e) * dof + k + eq * N];
+            for (int k = 0; k < dof; k++) a += ke[j * (dim * dof) + k + d * dof] * Up[static_cast<size_t>(e) * dof + k + eq * N];
             rhs[j * nd + eq + d * neq] = a;
           }
       for (int f : el_faces[e]) {
@@ -528,7 +596,7 @@ struct Oracle {
       for (size_t i = 0; i < rhs.size(); i++) rhs[i] += fsum[i];
       // Me_inv (src/gradients.cpp:209-227)
       const double *mi = &Me_inv[e * d2];
-      for (int d = 0; d < 3; d++)
+      for (int d = 0; d < dim; d++)
         for (int eq = 0; eq < neq; eq++)
           for (int j = 0; j < dof; j++) {
             double a = 0;
@@ -570,7 +638,7 @@ struct Oracle {
           u2[eq] = std::max(u2[eq], 0.0);
         }
         for (int eq = 0; eq < neq; eq++)
-          for (int d = 0; d < 3; d++) {
+          for (int d = 0; d < dim; d++) {
             double a = 0, b = 0;
             const double *ga = &gradUp[static_cast<size_t>(e1) * dof + eq * N + static_cast<size_t>(d) * neq * N];
             const double *gb = &gradUp[static_cast<size_t>(e2) * dof + eq * N + static_cast<size_t>(d) * neq * N];
@@ -584,16 +652,16 @@ struct Oracle {
         ph->visc_flux(u1, g1, xyz, delta1, 0.0, vF1);
         ph->visc_flux(u2, g2, xyz, delta2, 0.0, vF2);
         // viscF1 += viscF2; viscF1 *= -0.5; viscF1.AddMult(nor, fluxN); fluxN *= ip.weight
-        for (int i = 0; i < neq * 3; i++) {
+        for (int i = 0; i < neq * dim; i++) {
           vF1[i] += vF2[i];
           vF1[i] *= -0.5;
         }
         for (int eq = 0; eq < neq; eq++) {
           double a = 0;
-          for (int d = 0; d < 3; d++) a += vF1[eq + d * neq] * nor[d];
+          for (int d = 0; d < dim; d++) a += vF1[eq + d * neq] * nor[d];
           fluxN[eq] += a;
         }
-        const double w = qwf[q % nqf1] * qwf[q / nqf1];
+        const double w = face_weight(q);
         for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
         for (int k = 0; k < dof; k++)
           for (int eq = 0; eq < neq; eq++) {
@@ -621,7 +689,7 @@ struct Oracle {
             for (int k = 0; k < dof; k++) a += x[static_cast<size_t>(e1) * dof + k + eq * N] * s1[k];
             const int sp = eq - nvel - 2;
             u1[eq] = (sp >= 0 && sp < nact) ? std::max(a, 0.0) : a;
-            for (int d = 0; d < 3; d++) {
+            for (int d = 0; d < dim; d++) {
               double b = 0;
               const double *ga = &gradUp[static_cast<size_t>(e1) * dof + eq * N + static_cast<size_t>(d) * neq * N];
               for (int k = 0; k < dof; k++) b += ga[k] * s1[k];
@@ -631,7 +699,7 @@ struct Oracle {
           face_geom(f, q, nor, xyz);
           for (int eq = 0; eq < neq; eq++) fluxN[eq] = 0.;
           bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN);
-          const double w = qwf[q % nqf1] * qwf[q / nqf1];
+          const double w = face_weight(q);
           for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
           for (int k = 0; k < dof; k++)
             for (int eq = 0; eq < neq; eq++) v1[k * neq + eq] -= fluxN[eq] * s1[k];
@@ -646,7 +714,7 @@ struct Oracle {
 #ifdef _OPENMP
       tid = omp_get_thread_num();
 #endif
-      std::vector<double> z(static_cast<size_t>(dof) * neq, 0.0), fl(static_cast<size_t>(dof) * 3 * neq);
+      std::vector<double> z(static_cast<size_t>(dof) * neq, 0.0), fl(static_cast<size_t>(dof) * dim * neq);
       for (int f : el_faces[e]) {
         const int side = (f_el1[f] == e) ? 0 : 1;
         const double *v = &fz[(static_cast<size_t>(f) * 2 + side) * dof * neq];
@@ -663,24 +731,24 @@ struct Oracle {
         for (int k = 0; k < neq; k++) st[k] = x[i + k * N];
         for (int sp = 0; sp < nact; sp++) st[nvel + 2 + sp] = std::max(st[nvel + 2 + sp], 0.0);
         for (int eq = 0; eq < neq; eq++)
-          for (int d = 0; d < 3; d++) g[eq + d * neq] = gradUp[i + eq * N + static_cast<size_t>(d) * neq * N];
-        for (int d = 0; d < 3; d++) xyz[d] = nodeXYZ[i * 3 + d];
+          for (int d = 0; d < dim; d++) g[eq + d * neq] = gradUp[i + eq * N + static_cast<size_t>(d) * neq * N];
+        for (int d = 0; d < dim; d++) xyz[d] = nodeXYZ[i * dim + d];
         ph->conv_flux(st, fc);
         if (phys.eq_system != 0) {
           ph->visc_flux(st, g, xyz, elSize[e], 0.0, fv);
-          for (int c = 0; c < neq * 3; c++) fc[c] -= fv[c];
+          for (int c = 0; c < neq * dim; c++) fc[c] -= fv[c];
         }
-        for (int d = 0; d < 3; d++)
-          for (int k = 0; k < neq; k++) fl[(n * 3 + d) * neq + k] = fc[k + d * neq];
+        for (int d = 0; d < dim; d++)
+          for (int k = 0; k < neq; k++) fl[(n * dim + d) * neq + k] = fc[k + d * neq];
         const double mcs = ph->max_char_speed(st);
         if (mcs > mcs_t[tid]) mcs_t[tid] = mcs;
       }
-      const double *kf = &Kfl[e * d2 * 3];
+      const double *kf = &Kfl[e * d2 * dim];
       for (int eq = 0; eq < neq; eq++)
         for (int j = 0; j < dof; j++) {
           double a = 0;
-          for (int d = 0; d < 3; d++)
-            for (int k = 0; k < dof; k++) a += kf[j * (3 * dof) + k + d * dof] * fl[(k * 3 + d) * neq + eq];
+          for (int d = 0; d < dim; d++)
+            for (int k = 0; k < dof; k++) a += kf[j * (dim * dof) + k + d * dof] * fl[(k * dim + d) * neq + eq];
           z[j * neq + eq] += a;
         }
       const double *mi = &Me_inv[e * d2];
@@ -717,28 +785,40 @@ const char *orc_physics_kind() {
   return buf;
 }
 
-// vx: [NE][8][3] element vertex coordinates (MFEM hex vertex order); faces in MFEM convention:
-// el1/el2 = Elem1No/Elem2No (-1 boundary), inf = 64*local_face + orientation.
-void *orc_create(int order, int NE, const double *vx, int NF, const int *el1, const int *el2, const int *inf1,
-                 const int *inf2, const OrcPhysParams *phys, int nthreads) {
+// General constructor.  vx: [NE][2^dim][dim] element vertex coordinates (MFEM vertex order); faces in MFEM
+// convention: el1/el2 = Elem1No/Elem2No (-1 boundary), inf = 64*local_face + orientation.
+void *orc_create_ex(int dim, int order, int basis_type, int int_rule, int neq, int nvel, int NE, const double *vx,
+                    int NF, const int *el1, const int *el2, const int *inf1, const int *inf2, const OrcPhysParams *phys,
+                    int nthreads) {
+  if (dim != 2 && dim != 3) return nullptr;
   Oracle *o = new Oracle;
+  o->dim = dim;
   o->p = order;
+  o->basis_type = basis_type;
+  o->int_rule = int_rule;
+  o->neq = neq;
+  o->nvel = nvel;
   o->NE = NE;
   o->NF = NF;
-  o->vx.assign(vx, vx + static_cast<size_t>(NE) * 24);
+  o->vx.assign(vx, vx + static_cast<size_t>(NE) * (1 << dim) * dim);
   o->f_el1.assign(el1, el1 + NF);
   o->f_el2.assign(el2, el2 + NF);
   o->f_inf1.assign(inf1, inf1 + NF);
   o->f_inf2.assign(inf2, inf2 + NF);
   o->phys = *phys;
   o->nthreads = nthreads > 0 ? nthreads : 1;
-  o->ph = orc::make_physics(*phys, 3, 3, 5);
+  o->ph = orc::make_physics(*phys, dim, nvel, neq);
   if (!o->ph) {
     delete o;
     return nullptr;
   }
   o->setup();
   return o;
+}
+// 3-D hexahedra, Gauss-Legendre nodes and rules, dry air (5 equations)
+void *orc_create(int order, int NE, const double *vx, int NF, const int *el1, const int *el2, const int *inf1,
+                 const int *inf2, const OrcPhysParams *phys, int nthreads) {
+  return orc_create_ex(3, order, 0, 0, 5, 3, NE, vx, NF, el1, el2, inf1, inf2, phys, nthreads);
 }
 // boundary attribute per face (0 on interior faces) and BCintegrator's attribute maps
 void orc_set_bcs(void *h, const int *face_attr, int nbc, const OrcBc *bcs, int use_bc_in_grad) {
@@ -763,6 +843,7 @@ void orc_destroy(void *h) {
 }
 long orc_ndofs(void *h) { return static_cast<Oracle *>(h)->N; }
 int orc_num_equation(void *h) { return static_cast<Oracle *>(h)->neq; }
+int orc_dim(void *h) { return static_cast<Oracle *>(h)->dim; }
 void orc_update_primitives(void *h, const double *x, double *Up_out) {
   Oracle *o = static_cast<Oracle *>(h);
   o->update_primitives(x);
@@ -806,16 +887,16 @@ void orc_rk4_steps(void *h, double *U, double dt, int nsteps) {
   }
 }
 // geometry / table probes for the unit tests
-void orc_node_coords(void *h, double *xyz /*[N][3]*/) {
+void orc_node_coords(void *h, double *xyz /*[N][dim]*/) {
   Oracle *o = static_cast<Oracle *>(h);
   std::copy(o->nodeXYZ.begin(), o->nodeXYZ.end(), xyz);
 }
 int orc_face_nq(void *h) { return static_cast<Oracle *>(h)->nqf; }
-void orc_face_geometry(void *h, int f, double *nor /*[nqf][3]*/, double *xyz /*[nqf][3]*/, double *w /*[nqf]*/) {
+void orc_face_geometry(void *h, int f, double *nor /*[nqf][dim]*/, double *xyz /*[nqf][dim]*/, double *w /*[nqf]*/) {
   Oracle *o = static_cast<Oracle *>(h);
   for (int q = 0; q < o->nqf; q++) {
-    o->face_geom(f, q, &nor[q * 3], &xyz[q * 3]);
-    w[q] = o->qwf[q % o->nqf1] * o->qwf[q / o->nqf1];
+    o->face_geom(f, q, &nor[q * o->dim], &xyz[q * o->dim]);
+    w[q] = o->face_weight(q);
   }
 }
 void orc_elem_size(void *h, double *delta /*[NE]*/) {
@@ -826,12 +907,18 @@ void orc_dense_ops(void *h, int e, double *Me_inv, double *Ke, double *Kfl) {
   Oracle *o = static_cast<Oracle *>(h);
   const size_t d2 = static_cast<size_t>(o->dof) * o->dof;
   if (Me_inv) std::copy(&o->Me_inv[e * d2], &o->Me_inv[(e + 1) * d2], Me_inv);
-  if (Ke) std::copy(&o->Ke[e * d2 * 3], &o->Ke[(e + 1) * d2 * 3], Ke);
-  if (Kfl) std::copy(&o->Kfl[e * d2 * 3], &o->Kfl[(e + 1) * d2 * 3], Kfl);
+  if (Ke) std::copy(&o->Ke[e * d2 * o->dim], &o->Ke[(e + 1) * d2 * o->dim], Ke);
+  if (Kfl) std::copy(&o->Kfl[e * d2 * o->dim], &o->Kfl[(e + 1) * d2 * o->dim], Kfl);
 }
 void orc_gl_rule(int n, double *x, double *w) {
   std::vector<double> xv, wv;
   orc::gauss_legendre01(n, xv, wv);
+  std::copy(xv.begin(), xv.end(), x);
+  std::copy(wv.begin(), wv.end(), w);
+}
+void orc_gll_rule(int n, double *x, double *w) {
+  std::vector<double> xv, wv;
+  orc::gauss_lobatto01(n, xv, wv);
   std::copy(xv.begin(), xv.end(), x);
   std::copy(wv.begin(), wv.end(), w);
 }

@@ -56,6 +56,59 @@ inline void gauss_legendre01(int n, std::vector<double> &x, std::vector<double> 
 
 // Number of 1-D Gauss-Legendre points MFEM uses for a requested order.
 inline int gl_npts_for_order(int order) { return (order | 1) / 2 + 1; }
+// ... and of Gauss-Lobatto points (IntegrationRules(0, Quadrature1D::GaussLobatto): n = order/2 + 2,
+// exact to degree 2n-3; used with flow/integrationRule = 1, src/M2ulPhyS.cpp:558-562)
+inline int gll_npts_for_order(int order) { return order / 2 + 2; }
+
+// n-point Gauss-Lobatto rule on [0,1]: end points plus the roots of P'_{n-1}, w_i = 2 / (n (n-1) P_{n-1}(x_i)^2)
+// on [-1,1].  Also the nodes of BasisType::GaussLobatto (flow/basisType = 1).
+inline void gauss_lobatto01(int n, std::vector<double> &x, std::vector<double> &w) {
+  x.assign(n, 0.0);
+  w.assign(n, 0.0);
+  const int m = n - 1;  // polynomial degree
+  auto legendre = [&](long double z, long double &pm, long double &dpm) {
+    long double p0 = 1.0L, p1 = z;
+    if (m == 0) {
+      pm = 1.0L;
+      dpm = 0.0L;
+      return;
+    }
+    for (int j = 2; j <= m; j++) {
+      const long double p2 = ((2.0L * j - 1.0L) * z * p1 - (j - 1.0L) * p0) / j;
+      p0 = p1;
+      p1 = p2;
+    }
+    pm = p1;
+    dpm = m * (z * p1 - p0) / (z * z - 1.0L);
+  };
+  for (int i = 0; i < n; i++) {
+    long double z;
+    if (i == 0) {
+      z = -1.0L;
+    } else if (i == n - 1) {
+      z = 1.0L;
+    } else {
+      z = -cosl(M_PIl * i / m);  // Chebyshev-Lobatto start
+      for (int it = 0; it < 100; it++) {
+        // Newton on q(z) = (1 - z^2) P'_m(z): q' = -m (m+1) P_m(z)
+        long double pm, dpm;
+        legendre(z, pm, dpm);
+        const long double q = (1.0L - z * z) * dpm, dq = -static_cast<long double>(m) * (m + 1) * pm;
+        const long double dz = q / dq;
+        z -= dz;
+        if (fabsl(dz) < 1e-19L) break;
+      }
+    }
+    long double pm, dpm;
+    if (i == 0 || i == n - 1) {
+      pm = (i == 0 && (m % 2)) ? -1.0L : 1.0L;
+    } else {
+      legendre(z, pm, dpm);
+    }
+    x[i] = static_cast<double>(0.5L * (1.0L + z));
+    w[i] = static_cast<double>(0.5L * 2.0L / (static_cast<long double>(m) * (m + 1) * pm * pm));
+  }
+}
 
 // Lagrange basis on `nodes` evaluated at x: values and derivatives (plain product form).
 inline void lagrange(const std::vector<double> &nodes, double x, double *val, double *der) {

@@ -75,6 +75,49 @@ def build_faces(elem_verts):
     return to32(el1), to32(el2), to32(inf1), to32(inf2)
 
 
+QUAD_VERT = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=np.int64)
+QUAD_EDGE_VERT = np.array([[0, 1], [1, 2], [2, 3], [3, 0]], dtype=np.int64)
+
+
+def cartesian_quad(nx, ny, lo=(-1.0, -1.0), hi=(1.0, 1.0), periodic=(True, True)):
+    """2-D counterpart of cartesian_hex ([MFEM] Mesh::MakeCartesian2D + MakePeriodic, utils/beam_mesh.cpp)."""
+    n = (nx, ny)
+    nv = [n[d] if periodic[d] else n[d] + 1 for d in range(2)]
+    ey, ex = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    ex, ey = ex.ravel(), ey.ravel()
+    ev = np.zeros((nx * ny, 4), dtype=np.int32)
+    xyz = np.zeros((nx * ny, 4, 2))
+    h = [(hi[d] - lo[d]) / n[d] for d in range(2)]
+    for a in range(4):
+        ix, iy = ex + QUAD_VERT[a, 0], ey + QUAD_VERT[a, 1]
+        xyz[:, a, 0] = lo[0] + ix * h[0]
+        xyz[:, a, 1] = lo[1] + iy * h[1]
+        ev[:, a] = (ix % nv[0]) + nv[0] * (iy % nv[1])
+    return ev, xyz
+
+
+def build_faces2d(elem_verts):
+    """Edge tables in MFEM convention: orientation 1 = the second element runs along the edge backwards."""
+    table, base = {}, []
+    el1, el2, inf1, inf2 = [], [], [], []
+    for e in range(elem_verts.shape[0]):
+        v = elem_verts[e]
+        for le in range(4):
+            v0, v1 = int(v[QUAD_EDGE_VERT[le, 0]]), int(v[QUAD_EDGE_VERT[le, 1]])
+            key = (min(v0, v1), max(v0, v1))
+            if key not in table:
+                table[key] = len(base)
+                base.append((v0, v1))
+                el1.append(e), el2.append(-1), inf1.append(64 * le), inf2.append(-1)
+            else:
+                f = table[key]
+                assert el2[f] == -1
+                el2[f] = e
+                inf2[f] = 64 * le + (0 if base[f] == (v0, v1) else 1)
+    to32 = lambda a: np.asarray(a, dtype=np.int32)
+    return to32(el1), to32(el2), to32(inf1), to32(inf2)
+
+
 def element_to_faces(NE, el1, el2):
     """Stride-7 interior-face list per element (src/M2ulPhyS.cpp:878-958)."""
     e2f = np.zeros(7 * NE, dtype=np.int32)

@@ -55,6 +55,8 @@ def load(kind="port"):
     lib.orc_physics_kind.restype = C.c_char_p
     lib.orc_create.restype = C.c_void_p
     lib.orc_create.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip, _ip, C.POINTER(OrcPhysParams), C.c_int]
+    lib.orc_create_ex.restype = C.c_void_p
+    lib.orc_create_ex.argtypes = [C.c_int] * 7 + [_dp, C.c_int, _ip, _ip, _ip, _ip, C.POINTER(OrcPhysParams), C.c_int]
     lib.orc_destroy.argtypes = [C.c_void_p]
     lib.orc_set_bcs.argtypes = [C.c_void_p, _ip, C.c_int, C.POINTER(OrcBc), C.c_int]
     lib.orc_bc_flux.argtypes = [C.c_void_p, C.POINTER(OrcBc), C.c_int, _dp, _dp, _dp, _dp]
@@ -82,17 +84,21 @@ def load(kind="port"):
 class Oracle:
     """Thin object over orc_*: one DG operator on one mesh."""
 
-    def __init__(self, order, elem_xyz, el1, el2, inf1, inf2, phys=None, nthreads=None, kind="port"):
+    def __init__(self, order, elem_xyz, el1, el2, inf1, inf2, phys=None, nthreads=None, kind="port", basis_type=0,
+                 int_rule=0, neq=None, nvel=None):
         self.lib = load(kind)
         self.phys = phys or dry_air_params()
         self.NE = elem_xyz.shape[0]
         self.order = order
-        self.neq = 5
+        self.dim = elem_xyz.shape[2]  # [NE][2^dim][dim]
+        self.nvel = nvel or self.dim
+        self.neq = neq or self.nvel + 2
         nthreads = nthreads or os.cpu_count()
-        self.h = self.lib.orc_create(order, self.NE, np.ascontiguousarray(elem_xyz, dtype=np.float64), len(el1),
-                                     np.ascontiguousarray(el1, np.int32), np.ascontiguousarray(el2, np.int32),
-                                     np.ascontiguousarray(inf1, np.int32), np.ascontiguousarray(inf2, np.int32),
-                                     C.byref(self.phys), nthreads)
+        self.h = self.lib.orc_create_ex(self.dim, order, basis_type, int_rule, self.neq, self.nvel, self.NE,
+                                        np.ascontiguousarray(elem_xyz, dtype=np.float64), len(el1),
+                                        np.ascontiguousarray(el1, np.int32), np.ascontiguousarray(el2, np.int32),
+                                        np.ascontiguousarray(inf1, np.int32), np.ascontiguousarray(inf2, np.int32),
+                                        C.byref(self.phys), nthreads)
         assert self.h, "orc_create failed"
         self.N = self.lib.orc_ndofs(self.h)
 
@@ -114,7 +120,7 @@ class Oracle:
         return out
 
     def node_coords(self):
-        xyz = np.zeros((self.N, 3))
+        xyz = np.zeros((self.N, self.dim))
         self.lib.orc_node_coords(self.h, xyz)
         return xyz
 
@@ -124,13 +130,13 @@ class Oracle:
         return up
 
     def gradients(self, x):
-        g = np.zeros(self.N * self.neq * 3)
+        g = np.zeros(self.N * self.neq * self.dim)
         self.lib.orc_compute_gradients(self.h, x, g)
         return g
 
     def mult(self, x, want_grad=False):
         y = np.zeros_like(x)
-        g = np.zeros(self.N * self.neq * 3) if want_grad else None
+        g = np.zeros(self.N * self.neq * self.dim) if want_grad else None
         mcs = C.c_double(0.0)
         self.lib.orc_rhs_mult(self.h, x, y, g.ctypes.data if want_grad else None, C.byref(mcs))
         self.max_char_speed = mcs.value
@@ -143,6 +149,6 @@ class Oracle:
 
     def face_geometry(self, f):
         nq = self.lib.orc_face_nq(self.h)
-        nor, xyz, w = np.zeros((nq, 3)), np.zeros((nq, 3)), np.zeros(nq)
+        nor, xyz, w = np.zeros((nq, self.dim)), np.zeros((nq, self.dim)), np.zeros(nq)
         self.lib.orc_face_geometry(self.h, f, nor, xyz, w)
         return nor, xyz, w

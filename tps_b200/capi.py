@@ -77,7 +77,7 @@ class PartSizes(C.Structure):
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -124,6 +124,8 @@ def lib():
     L.tpsb_get_ref_tables.argtypes = [C.c_int, dp, C.c_int]
     L.tpsb_mk_cartesian_hex.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, ip, C.c_int, ip, dp]
     L.tpsb_mk_build_faces.argtypes = [C.c_int, ip, ip, ip, ip, ip]
+    L.tpsb_mk_cartesian_quad.argtypes = [C.c_int, C.c_int, dp, dp, ip, ip, dp]
+    L.tpsb_mk_build_faces2d.argtypes = [C.c_int, ip, ip, ip, ip, ip]
     L.tpsb_mk_partition.argtypes = [ip, dp, dp, ip, ip, C.c_int, C.c_int, C.POINTER(PartSizes), ip, dp,
                                     C.POINTER(C.c_int64), ip, ip, ip, ip, ip, ip, ip, ip]
     L.tpsb_comm_get_unique_id.argtypes = [C.c_char_p]
@@ -158,6 +160,26 @@ def cartesian_hex_mesh(nx, ny, nz, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), pe
     if nf < 0:
         raise TpsbError(f"tpsb_mk_build_faces failed with code {nf}")
     return dict(elem_verts=ev, elem_xyz=xyz, face_el1=el1[:nf].copy(), face_el2=el2[:nf].copy(),
+                face_inf1=inf1[:nf].copy(), face_inf2=inf2[:nf].copy())
+
+
+def cartesian_quad_mesh(nx, ny, lo=(-1.0, -1.0), hi=(1.0, 1.0), periodic=(1, 1)):
+    """meshkit: Cartesian quadrilateral box + MFEM-convention edge tables (2-D test cases, utils/beam_mesh.cpp)."""
+    L = lib()
+    NE = nx * ny
+    ev = np.zeros((NE, 4), dtype=np.int32)
+    xyz = np.zeros((NE, 4, 2), dtype=np.float64)
+    lo_a, hi_a = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    per = np.asarray(periodic, dtype=np.int32)
+    rc = L.tpsb_mk_cartesian_quad(nx, ny, _dp(lo_a), _dp(hi_a), _ip(per), _ip(ev), _dp(xyz))
+    if rc != 0:
+        raise TpsbError(f"tpsb_mk_cartesian_quad failed with code {rc}")
+    el1 = np.zeros(4 * NE, dtype=np.int32)
+    el2, inf1, inf2 = np.zeros_like(el1), np.zeros_like(el1), np.zeros_like(el1)
+    nf = L.tpsb_mk_build_faces2d(NE, _ip(ev), _ip(el1), _ip(el2), _ip(inf1), _ip(inf2))
+    if nf < 0:
+        raise TpsbError(f"tpsb_mk_build_faces2d failed with code {nf}")
+    return dict(dim=2, elem_verts=ev, elem_xyz=xyz, face_el1=el1[:nf].copy(), face_el2=el2[:nf].copy(),
                 face_inf1=inf1[:nf].copy(), face_inf2=inf2[:nf].copy())
 
 

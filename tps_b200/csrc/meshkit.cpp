@@ -123,6 +123,70 @@ extern "C" int tpsb_mk_build_faces(int num_elems, const int *elem_verts, int *fa
   return nfaces;
 }
 
+// ---- 2-D: Cartesian quadrilaterals (Mesh::MakeCartesian2D + MakePeriodic as utils/beam_mesh.cpp uses them) ----
+extern "C" int tpsb_mk_cartesian_quad(int nx, int ny, const double lo[2], const double hi[2], const int periodic[2],
+                                      int *elem_verts, double *elem_xyz) {
+  if (nx < 1 || ny < 1 || !elem_verts || !elem_xyz) return TPSB_EINVAL;
+  const int n[2] = {nx, ny};
+  int nv[2];
+  for (int d = 0; d < 2; d++) {
+    if (periodic[d] && n[d] < 3) return TPSB_EINVAL;
+    nv[d] = periodic[d] ? n[d] : n[d] + 1;
+  }
+  static const int QV[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};  // Geometry::Constants<SQUARE> vertex order
+  const double h[2] = {(hi[0] - lo[0]) / nx, (hi[1] - lo[1]) / ny};
+  for (int j = 0; j < ny; j++)
+    for (int i = 0; i < nx; i++) {
+      const size_t e = static_cast<size_t>(i) + static_cast<size_t>(nx) * j;
+      for (int a = 0; a < 4; a++) {
+        const int iv[2] = {i + QV[a][0], j + QV[a][1]};
+        for (int d = 0; d < 2; d++) elem_xyz[(e * 4 + a) * 2 + d] = lo[d] + iv[d] * h[d];
+        elem_verts[e * 4 + a] = (iv[0] % nv[0]) + nv[0] * (iv[1] % nv[1]);
+      }
+    }
+  return TPSB_OK;
+}
+
+// Edges numbered by first appearance over (element, local edge); Elem2Inf = 64*le + 1 when the second element
+// traverses the edge in the opposite direction (always, for consistently oriented quads), else + 0
+// [MFEM Mesh::AddSegmentFaceElement / GenerateFaces].
+extern "C" int tpsb_mk_build_faces2d(int num_elems, const int *elem_verts, int *face_el1, int *face_el2,
+                                     int *face_inf1, int *face_inf2) {
+  if (num_elems < 0 || !elem_verts) return -1;
+  static const int EV[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};  // Geometry::Constants<SQUARE>::Edges
+  std::unordered_map<Key, int, KeyHash> table;
+  table.reserve(static_cast<size_t>(num_elems) * 3);
+  std::vector<int> base;
+  int nfaces = 0;
+  const bool fill = face_el1 && face_el2 && face_inf1 && face_inf2;
+  for (int e = 0; e < num_elems; e++) {
+    const int *v = &elem_verts[static_cast<size_t>(e) * 4];
+    for (int le = 0; le < 4; le++) {
+      const int v0 = v[EV[le][0]], v1 = v[EV[le][1]];
+      const Key key{std::min(v0, v1), std::max(v0, v1), -1};
+      auto it = table.find(key);
+      if (it == table.end()) {
+        table.emplace(key, nfaces);
+        base.push_back(v0);
+        base.push_back(v1);
+        if (fill) {
+          face_el1[nfaces] = e;
+          face_el2[nfaces] = -1;
+          face_inf1[nfaces] = 64 * le;
+          face_inf2[nfaces] = -1;
+        }
+        nfaces++;
+      } else if (fill) {
+        const int f = it->second;
+        if (face_el2[f] != -1) return -2;
+        face_el2[f] = e;
+        face_inf2[f] = 64 * le + ((base[2 * f] == v0 && base[2 * f + 1] == v1) ? 0 : 1);
+      }
+    }
+  }
+  return nfaces;
+}
+
 extern "C" int tpsb_mk_partition(const int n[3], const double lo[3], const double hi[3], const int periodic[3],
                                  const int procs[3], int rank, int order_mode, tpsb_mk_part_sizes *sizes,
                                  int *elem_verts, double *elem_xyz, int64_t *elem_gid, int *face_el1, int *face_el2,
