@@ -281,7 +281,7 @@ class RhsOperator:
     Mult / updatePrimitives / updateGradients / getGradients, on torch CUDA tensors."""
 
     def __init__(self, mesh, order=3, physics=None, device=0, halo=None, num_nbr_elems=0, stream=None, bcs=None,
-                 face_attr=None, use_bc_in_grad=False):
+                 face_attr=None, use_bc_in_grad=False, basis_type=0, int_rule_type=0):
         import torch
         self.torch = torch
         self.L = lib()
@@ -295,14 +295,15 @@ class RhsOperator:
         if face_attr is not None:
             fattr = np.ascontiguousarray(face_attr, dtype=np.int32)
             self._keep.append(fattr)
-        maps = MeshMaps(3, self.NE, num_nbr_elems, _dp(xyz), len(el1), _ip(el1), _ip(el2), _ip(i1), _ip(i2),
+        self.dim = xyz.shape[2]  # elem_xyz is [NE][2^dim][dim]
+        maps = MeshMaps(self.dim, self.NE, num_nbr_elems, _dp(xyz), len(el1), _ip(el1), _ip(el2), _ip(i1), _ip(i2),
                         _ip(fattr) if fattr is not None else None)
         bcset = None
         if bcs:
             arr = (BcDesc * len(bcs))(*bcs)
             bcset = BcSet(len(bcs), arr, int(use_bc_in_grad))
             self._keep.append(arr)
-        space = SpaceDesc(order, 0, 0, 5, 3)
+        space = SpaceDesc(order, basis_type, int_rule_type, self.dim + 2, self.dim)
         self.ctx = C.c_void_p()
         s = stream if stream is not None else 0
         rc = self.L.tpsb_create(C.byref(maps), C.byref(space), C.byref(self.physics),
@@ -358,7 +359,7 @@ class RhsOperator:
         """(Up, gradUp) views of the context-owned primitive and gradient fields."""
         up, g = C.c_void_p(), C.c_void_p()
         self._chk(self.L.tpsb_get_fields(self.ctx, C.byref(up), C.byref(g)), "tpsb_get_fields")
-        return self._view(up.value, self.neq * self.N), self._view(g.value, 3 * self.neq * self.N)
+        return self._view(up.value, self.neq * self.N), self._view(g.value, self.dim * self.neq * self.N)
 
     def debug_buffer(self, which):
         """Test hook: device view of an internal buffer (0 face residuals, 1 face-trace blocks)."""

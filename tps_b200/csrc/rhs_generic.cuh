@@ -1,0 +1,347 @@
+// Generic tensor-product path of RHSoperator::Mult: quadrilaterals or hexahedra, Gauss-Legendre or Gauss-Lobatto
+// nodes and rules (flow/basisType, flow/integrationRule), any order the tables were built for, run-time
+// num_equation.  It serves every configuration the two specialised 3-D paths do not (the reference's 2-D cases:
+// mms.euler_2d runs p = 2, GLL/GLL quads).  Written for generality, not speed: one CTA per element, quadrature
+// done point by point from dense reference-element tables (values/derivatives of the basis at the volume and face
+// quadrature points), metric terms recomputed from the element's vertices, and each face flux evaluated by both
+// of its elements (no face buffers, no atomics).
+//
+//   gen_prim_kernel   Up = prim(U)                                              (rhs_operator.cpp:623-651)
+//   gen_grad_kernel   gradUp = Me^-1 ( sum_q w|J| phi (dphi/dx Up) + face jumps ) (gradients.cpp:144-232,
+//                                                                                 faceGradientIntegration.cpp:40-140)
+//   gen_resid_kernel  y = Me^-1 ( sum_q w (dphi adjJ) . F(q) + face fluxes )      (rhs_operator.cpp:379-448,493-559,
+//                     domain_integrator.cpp:44-99, face_integrator.cpp:194-352)
+// Me is the reference's mass matrix (rule of order 2p): diagonal for GL nodes + GL rule (collocated), dense
+// otherwise -- then its inverse is precomputed per element on the host (Cholesky) and applied as a dense block,
+// exactly like the reference's Me_inv (rhs_operator.cpp:173-189,432-448).
+#pragma once
+#include "gen_physics.cuh"
+
+namespace tpsb {
+
+struct GenArgs {
+  int dim, np, dof, nqv, nqf, nfe, nv, neq, nvel;
+  int NE;
+  long long N;
+  int me_diag;
+  GenPhys phys;
+  // reference-element tables
+  const double *phiV;   // [nqv][dof]
+  const double *dphiV;  // [nqv][dof][dim]   reference-space derivatives
+  const double *wV;     // [nqv]
+  const double *xiV;    // [nqv][dim]
+  const double *phiF;   // [codes][nqf][dof]  code = local_face * (dim == 3 ? 8 : 2) + orientation
+  const double *xiF;    // [codes][nqf][dim]  element reference point of face quadrature point q
+  const double *dlocF;  // [codes][dim*(dim-1)] d(xi)/d(face coordinates), column-major
+  const double *wF;     // [nqf]
+  // mesh
+  const double *vx;     // [NE][nv][dim]
+  const int *el_face;   // [NE][nfe] face id of each local face
+  const int *f_el1, *f_el2, *f_inf1, *f_inf2;
+  const double *me_inv;  // [NE][dof] (me_diag) or [NE][dof][dof]
+  // fields
+  const double *U;
+  double *Up, *gradUp, *y;
+  unsigned long long *maxCharBits;
+};
+
+__device__ __forceinline__ int gen_code(int dim, int inf) { return (inf / 64) * (dim == 3 ? 8 : 2) + inf % 64; }
+
+// Jacobian of the multilinear map at reference point xi: J[i + dim*j] = d x_i / d xi_j
+__device__ __forceinline__ void gen_jacobian(int dim, const double *v, const double *xi, double *J) {
+  if (dim == 2) {
+    const double x = xi[0], y = xi[1];
+    for (int i = 0; i < 2; i++) {
+      const double X0 = v[0 + i], X1 = v[2 + i], X2 = v[4 + i], X3 = v[6 + i];
+      J[i + 0] = (1 - y) * (X1 - X0) + y * (X2 - X3);
+      J[i + 2] = (1 - x) * (X3 - X0) + x * (X2 - X1);
+    }
+  } else {
+    hex_jacobian(v, xi[0], xi[1], xi[2], J);
+  }
+}
+__device__ __forceinline__ double gen_det(int dim, const double *J) {
+  return dim == 2 ? J[0] * J[3] - J[2] * J[1] : det3(J);
+}
+__device__ __forceinline__ void gen_adj(int dim, const double *J, double *A) {
+  if (dim == 2) {
+    A[0] = J[3];
+    A[1] = -J[1];
+    A[2] = -J[2];
+    A[3] = J[0];
+  } else {
+    adj3(J, A);
+  }
+}
+// CalcOrtho of the face Jacobian J * dloc
+__device__ __forceinline__ void gen_face_normal(int dim, const double *J, const double *dloc, double *nor) {
+  double Jf[6];
+  for (int i = 0; i < dim; i++)
+    for (int c = 0; c < dim - 1; c++) {
+      double a = 0;
+      for (int k = 0; k < dim; k++) a += J[i + dim * k] * dloc[k + dim * c];
+      Jf[i + dim * c] = a;
+    }
+  if (dim == 3) {
+    nor[0] = Jf[1] * Jf[5] - Jf[2] * Jf[4];
+    nor[1] = Jf[2] * Jf[3] - Jf[0] * Jf[5];
+    nor[2] = Jf[0] * Jf[4] - Jf[1] * Jf[3];
+  } else {
+    nor[0] = Jf[1];
+    nor[1] = -Jf[0];
+  }
+}
+
+__global__ void gen_prim_kernel(GenArgs a) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  double s[GEN_MAXEQ], up[GEN_MAXEQ];
+  for (int eq = 0; eq < a.neq; eq++) s[eq] = a.U[n + eq * a.N];
+  gen_prim(a.phys, s, up);
+  for (int eq = 0; eq < a.neq; eq++) a.Up[n + eq * a.N] = up[eq];
+}
+
+// y_el = Me^-1 z_el for nc interleaved columns: z[k*nc + c] -> out(global, byNODES with component stride cstride)
+__device__ __forceinline__ void gen_apply_minv(const GenArgs &a, int e, const double *z, int nc, double *out,
+                                               long long cstride) {
+  const int dof = a.dof;
+  for (int t = threadIdx.x; t < dof * nc; t += blockDim.x) {
+    const int j = t % dof, c = t / dof;
+    double v;
+    if (a.me_diag) {
+      v = a.me_inv[static_cast<long long>(e) * dof + j] * z[j * nc + c];
+    } else {
+      const double *mi = a.me_inv + (static_cast<long long>(e) * dof + j) * dof;
+      v = 0;
+      for (int k = 0; k < dof; k++) v += mi[k] * z[k * nc + c];
+    }
+    out[static_cast<long long>(e) * dof + j + c * cstride] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
+  extern __shared__ double sm[];
+  const int e = blockIdx.x, dim = a.dim, dof = a.dof, neq = a.neq, nc = neq * dim;
+  const int nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  double *sUp = sm;                    // [neq][dof]
+  double *sRhs = sUp + neq * dof;      // [dof][nc]
+  double *sQ = sRhs + dof * nc;        // [nqmax][nc]
+  double *sW = sQ + nqmax * nc;        // [nqv]  w |J|
+  const long long N = a.N;
+  const double *vx = a.vx + static_cast<long long>(e) * a.nv * dim;
+  for (int t = threadIdx.x; t < neq * dof; t += blockDim.x)
+    sUp[t] = a.Up[static_cast<long long>(e) * dof + (t % dof) + (t / dof) * N];
+  __syncthreads();
+  // volume: physical gradient of Up at the quadrature points
+  for (int q = threadIdx.x; q < a.nqv; q += blockDim.x) {
+    double J[9], A[9];
+    gen_jacobian(dim, vx, a.xiV + q * dim, J);
+    const double det = gen_det(dim, J);
+    gen_adj(dim, J, A);
+    sW[q] = a.wV[q] * det;
+    const double *dp = a.dphiV + static_cast<long long>(q) * dof * dim;
+    for (int eq = 0; eq < neq; eq++) {
+      double gr[GEN_MAXDIM] = {0, 0, 0};
+      for (int k = 0; k < dof; k++) {
+        const double u = sUp[eq * dof + k];
+        for (int r = 0; r < dim; r++) gr[r] += dp[k * dim + r] * u;
+      }
+      for (int d = 0; d < dim; d++) {
+        double g = 0;
+        for (int r = 0; r < dim; r++) g += gr[r] * A[r + dim * d];
+        sQ[q * nc + eq + d * neq] = g / det;  // CalcPhysDShape = dshape * inv(J)
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < dof * nc; t += blockDim.x) {
+    const int j = t / nc, c = t % nc;
+    double v = 0;
+    for (int q = 0; q < a.nqv; q++) v += a.phiV[q * dof + j] * sW[q] * sQ[q * nc + c];
+    sRhs[j * nc + c] = v;
+  }
+  __syncthreads();
+  // faces: phi_j(q) * 1/2 (Up_other - Up_own)(q) * n_out(q) w_q
+  for (int lf = 0; lf < a.nfe; lf++) {
+    const int f = a.el_face[e * a.nfe + lf];
+    const int e1 = a.f_el1[f], e2 = a.f_el2[f];
+    if (e2 < 0) continue;  // boundary face: Up2 = Up1 (no BC state built on this path yet)
+    const bool first = (e1 == e);
+    const int code_own = gen_code(dim, first ? a.f_inf1[f] : a.f_inf2[f]);
+    const int code_oth = gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
+    const int code1 = gen_code(dim, a.f_inf1[f]);
+    const int eo = first ? e2 : e1;
+    const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
+    for (int q = threadIdx.x; q < a.nqf; q += blockDim.x) {
+      double J[9], nor[3];
+      gen_jacobian(dim, v1, a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim, J);
+      gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
+      const double sg = (first ? 1.0 : -1.0) * a.wF[q];
+      const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
+      const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
+      for (int eq = 0; eq < neq; eq++) {
+        double own = 0, oth = 0;
+        const double *un = a.Up + static_cast<long long>(eo) * dof + eq * N;
+        for (int k = 0; k < dof; k++) {
+          own += po[k] * sUp[eq * dof + k];
+          oth += pn[k] * un[k];
+        }
+        const double jump = 0.5 * (oth - own);
+        for (int d = 0; d < dim; d++) sQ[q * nc + eq + d * neq] = jump * nor[d] * sg;
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < dof * nc; t += blockDim.x) {
+      const int j = t / nc, c = t % nc;
+      const double *po = a.phiF + static_cast<long long>(code_own) * a.nqf * dof;
+      double v = 0;
+      for (int q = 0; q < a.nqf; q++) v += po[q * dof + j] * sQ[q * nc + c];
+      sRhs[j * nc + c] += v;
+    }
+    __syncthreads();
+  }
+  // gradUp[e*dof + j + eq*N + d*neq*N]: component c = eq + d*neq has stride N
+  gen_apply_minv(a, e, sRhs, nc, a.gradUp, N);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
+  extern __shared__ double sm[];
+  const int e = blockIdx.x, dim = a.dim, dof = a.dof, neq = a.neq, nc = neq * dim;
+  const int nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  double *sU = sm;                  // [neq][dof]
+  double *sG = sU + neq * dof;      // [nc][dof]   gradUp of the element
+  double *sF = sG + nc * dof;       // [dof][nc]   nodal flux F_c - F_v
+  double *sQ = sF + dof * nc;       // [nqmax][nc]
+  double *sZ = sQ + nqmax * nc;     // [dof][neq]
+  __shared__ unsigned long long sMaxBits;
+  const long long N = a.N;
+  const double *vx = a.vx + static_cast<long long>(e) * a.nv * dim;
+  if (threadIdx.x == 0) sMaxBits = 0ull;
+  for (int t = threadIdx.x; t < neq * dof; t += blockDim.x) sU[t] = a.U[static_cast<long long>(e) * dof + (t % dof) + (t / dof) * N];
+  for (int t = threadIdx.x; t < nc * dof; t += blockDim.x)
+    sG[t] = a.gradUp[static_cast<long long>(e) * dof + (t % dof) + (t / dof) * N];
+  __syncthreads();
+  // nodal flux (GetFlux, rhs_operator.cpp:493-559) and max characteristic speed
+  for (int k = threadIdx.x; k < dof; k += blockDim.x) {
+    double s[GEN_MAXEQ], gr[GEN_MAXEQ * GEN_MAXDIM], fc[GEN_MAXEQ * GEN_MAXDIM], fv[GEN_MAXEQ * GEN_MAXDIM];
+    for (int eq = 0; eq < neq; eq++) s[eq] = sU[eq * dof + k];
+    for (int c = 0; c < nc; c++) gr[c] = sG[c * dof + k];
+    gen_conv_flux(a.phys, s, fc);
+    if (a.phys.dry.eq_system != 0) {
+      gen_visc_flux(a.phys, s, gr, fv);
+      for (int c = 0; c < nc; c++) fc[c] -= fv[c];
+    }
+    for (int c = 0; c < nc; c++) sF[k * nc + c] = fc[c];
+    atomicMax(&sMaxBits, static_cast<unsigned long long>(__double_as_longlong(gen_max_char_speed(a.phys, s))));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(a.maxCharBits, sMaxBits);
+  // volume: G(q)[eq][r] = w_q sum_d adjJ(q)[r][d] F(q)[eq][d], F(q) interpolated from the nodal fluxes
+  for (int q = threadIdx.x; q < a.nqv; q += blockDim.x) {
+    double J[9], A[9];
+    gen_jacobian(dim, vx, a.xiV + q * dim, J);
+    gen_adj(dim, J, A);
+    const double w = a.wV[q];
+    const double *ph = a.phiV + static_cast<long long>(q) * dof;
+    for (int eq = 0; eq < neq; eq++) {
+      double fq[GEN_MAXDIM] = {0, 0, 0};
+      for (int k = 0; k < dof; k++)
+        for (int d = 0; d < dim; d++) fq[d] += ph[k] * sF[k * nc + eq + d * neq];
+      for (int r = 0; r < dim; r++) {
+        double g = 0;
+        for (int d = 0; d < dim; d++) g += A[r + dim * d] * fq[d];
+        sQ[q * nc + eq * dim + r] = w * g;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < dof * neq; t += blockDim.x) {
+    const int j = t / neq, eq = t % neq;
+    double v = 0;
+    for (int q = 0; q < a.nqv; q++) {
+      const double *dp = a.dphiV + (static_cast<long long>(q) * dof + j) * dim;
+      for (int r = 0; r < dim; r++) v += dp[r] * sQ[q * nc + eq * dim + r];
+    }
+    sZ[j * neq + eq] = v;
+  }
+  __syncthreads();
+  // faces: Fhat = Rusanov(u1,u2,n) - 1/2 (Fv1 + Fv2).n with n = CalcOrtho of Elem1 (face_integrator.cpp:282-351)
+  for (int lf = 0; lf < a.nfe; lf++) {
+    const int f = a.el_face[e * a.nfe + lf];
+    const int e1 = a.f_el1[f], e2 = a.f_el2[f];
+    if (e2 < 0) continue;
+    const bool first = (e1 == e);
+    const int code_own = gen_code(dim, first ? a.f_inf1[f] : a.f_inf2[f]);
+    const int code_oth = gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
+    const int code1 = gen_code(dim, a.f_inf1[f]);
+    const int eo = first ? e2 : e1;
+    const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
+    for (int q = threadIdx.x; q < a.nqf; q += blockDim.x) {
+      double J[9], nor[3];
+      gen_jacobian(dim, v1, a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim, J);
+      gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
+      const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
+      const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
+      double uo[GEN_MAXEQ], un[GEN_MAXEQ], go[GEN_MAXEQ * GEN_MAXDIM], gn[GEN_MAXEQ * GEN_MAXDIM];
+      for (int eq = 0; eq < neq; eq++) {
+        double x = 0, y = 0;
+        const double *src = a.U + static_cast<long long>(eo) * dof + eq * N;
+        for (int k = 0; k < dof; k++) {
+          x += po[k] * sU[eq * dof + k];
+          y += pn[k] * src[k];
+        }
+        uo[eq] = x;
+        un[eq] = y;
+      }
+      for (int c = 0; c < nc; c++) {
+        double x = 0, y = 0;
+        const double *src = a.gradUp + static_cast<long long>(eo) * dof + c * N;
+        for (int k = 0; k < dof; k++) {
+          x += po[k] * sG[c * dof + k];
+          y += pn[k] * src[k];
+        }
+        go[c] = x;
+        gn[c] = y;
+      }
+      const double *u1 = first ? uo : un, *u2 = first ? un : uo, *g1 = first ? go : gn, *g2 = first ? gn : go;
+      double fx[GEN_MAXEQ];
+      gen_riemann_lf(a.phys, u1, u2, nor, fx);
+      if (a.phys.dry.eq_system != 0) {
+        double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM];
+        gen_visc_flux(a.phys, u1, g1, f1);
+        gen_visc_flux(a.phys, u2, g2, f2);
+        for (int eq = 0; eq < neq; eq++) {
+          double v = 0;
+          for (int d = 0; d < dim; d++) v += (-0.5 * (f1[eq + d * neq] + f2[eq + d * neq])) * nor[d];
+          fx[eq] += v;
+        }
+      }
+      const double sg = (first ? -1.0 : 1.0) * a.wF[q];  // elvect1 -= phi1 Fhat w ; elvect2 += phi2 Fhat w
+      for (int eq = 0; eq < neq; eq++) sQ[q * nc + eq] = sg * fx[eq];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < dof * neq; t += blockDim.x) {
+      const int j = t / neq, eq = t % neq;
+      const double *po = a.phiF + static_cast<long long>(code_own) * a.nqf * dof;
+      double v = 0;
+      for (int q = 0; q < a.nqf; q++) v += po[q * dof + j] * sQ[q * nc + eq];
+      sZ[j * neq + eq] += v;
+    }
+    __syncthreads();
+  }
+  gen_apply_minv(a, e, sZ, neq, a.y, N);
+}
+
+inline size_t gen_grad_smem(const GenArgs &a) {
+  const int nc = a.neq * a.dim, nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  return sizeof(double) * (static_cast<size_t>(a.neq) * a.dof + static_cast<size_t>(a.dof) * nc + static_cast<size_t>(nqmax) * nc + a.nqv);
+}
+inline size_t gen_resid_smem(const GenArgs &a) {
+  const int nc = a.neq * a.dim, nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  return sizeof(double) * (static_cast<size_t>(a.neq) * a.dof + 2 * static_cast<size_t>(a.dof) * nc + static_cast<size_t>(nqmax) * nc +
+                           static_cast<size_t>(a.dof) * a.neq);
+}
+
+}  // namespace tpsb

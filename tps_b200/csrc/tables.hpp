@@ -112,6 +112,41 @@ inline void lagrange_ld(const double *nodes, int n, long double x, long double *
   }
 }
 
+// n-point Gauss-Lobatto rule on [0,1] (also the BasisType::GaussLobatto nodes): end points + roots of P'_{n-1},
+// found by Newton on the derivative recurrence; w_i = 1 / (n (n-1) P_{n-1}(z_i)^2) on [0,1].
+inline void gauss_lobatto01(int n, double *x, double *w) {
+  const int m = n - 1;
+  auto eval = [&](long double z, long double &pm, long double &dpm, long double &ddpm) {
+    // P_m, P_m', P_m'' by upward recurrence
+    long double p0 = 1, p1 = z, d0 = 0, d1 = 1, s0 = 0, s1 = 0;
+    if (m == 0) {
+      pm = 1, dpm = 0, ddpm = 0;
+      return;
+    }
+    for (int j = 2; j <= m; j++) {
+      const long double p2 = ((2.0L * j - 1) * z * p1 - (j - 1.0L) * p0) / j;
+      const long double d2 = d0 + (2.0L * j - 1) * p1;
+      const long double s2 = s0 + (2.0L * j - 1) * d1;
+      p0 = p1, p1 = p2, d0 = d1, d1 = d2, s0 = s1, s1 = s2;
+    }
+    pm = p1, dpm = d1, ddpm = s1;
+  };
+  for (int i = 0; i < n; i++) {
+    long double z = (i == 0) ? -1.0L : (i == n - 1 ? 1.0L : -cosl(M_PIl * i / m));
+    long double pm, dpm, ddpm;
+    if (i > 0 && i < n - 1)
+      for (int it = 0; it < 100; it++) {
+        eval(z, pm, dpm, ddpm);
+        const long double dz = dpm / ddpm;
+        z -= dz;
+        if (fabsl(dz) < 1e-19L) break;
+      }
+    eval(z, pm, dpm, ddpm);
+    x[i] = static_cast<double>(0.5L * (1.0L + z));
+    w[i] = static_cast<double>(1.0L / (static_cast<long double>(m) * (m + 1) * pm * pm));
+  }
+}
+
 // order p, Gauss-Legendre basis and rules; trilinear hex mesh (OrderW = 2): face rule order 2 + 2p.
 inline bool build_ref_tables(int p, RefTables &T) {
   memset(&T, 0, sizeof(T));

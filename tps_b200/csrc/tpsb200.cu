@@ -16,6 +16,7 @@
 #include "../../include/tpsb200.h"
 #include "rhs_kernels_impl.cuh"
 #include "rhs_fast.cuh"
+#include "rhs_generic.cuh"
 
 using namespace tpsb;
 
@@ -44,6 +45,11 @@ struct tpsb_ctx {
   double *d_Uhalo = nullptr, *d_UpHalo = nullptr, *d_gradUpHalo = nullptr, *d_sendU = nullptr, *d_sendG = nullptr;
   unsigned long long *d_maxBits = nullptr;
   double *d_mcs = nullptr;
+  // generic tensor-product path (rhs_generic.cuh): 2-D, Gauss-Lobatto, ...
+  bool generic = false;
+  int dim = 3, neq = NEQ;
+  GenArgs gen;
+  std::vector<void *> gen_allocs;
   // boundary faces (BCintegrator)
   int NFbdr = 0;
   int *d_bdr_el1 = nullptr, *d_bdr_lf = nullptr, *d_bdr_bc = nullptr;
@@ -143,6 +149,259 @@ static bool element_is_affine(const double *v) {
   return true;
 }
 
+// ---- generic path setup ---------------------------------------------------------------------------
+namespace {
+
+const int G_HEX_FACE_VERT[6][4] = {{3, 2, 1, 0}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+const int G_QUAD_EDGE_VERT[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};
+const double G_QUAD_VERT[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+
+// face reference point -> element reference point [MFEM GetLocalQuadToHexTransformation / GetLocalSegToQuadTransformation]
+void g_loc_map(int dim, int lf, int ori, const double *st, double *xi, double *dloc) {
+  if (dim == 3) {
+    const double s = st[0], t = st[1];
+    const int *hv = G_HEX_FACE_VERT[lf];
+    const int *qo = QUAD_ORIENT[ori];
+    const double Nq[4] = {(1 - s) * (1 - t), s * (1 - t), s * t, (1 - s) * t};
+    const double dNs[4] = {-(1 - t), (1 - t), t, -t}, dNt[4] = {-(1 - s), -s, s, (1 - s)};
+    for (int i = 0; i < 3; i++) {
+      double a = 0, b = 0, c = 0;
+      for (int j = 0; j < 4; j++) {
+        const double vj = HEX_VERT[hv[qo[j]]][i];
+        a += Nq[j] * vj, b += dNs[j] * vj, c += dNt[j] * vj;
+      }
+      xi[i] = a, dloc[i] = b, dloc[i + 3] = c;
+    }
+  } else {
+    const int *ev = G_QUAD_EDGE_VERT[lf];
+    const int i0 = ori ? 1 : 0, i1 = ori ? 0 : 1;
+    for (int i = 0; i < 2; i++) {
+      const double v0 = G_QUAD_VERT[ev[i0]][i], v1 = G_QUAD_VERT[ev[i1]][i];
+      xi[i] = (1 - st[0]) * v0 + st[0] * v1;
+      dloc[i] = v1 - v0;
+    }
+  }
+}
+
+// tensor Lagrange basis on nodes xn (np per direction) at reference point xi: values and reference derivatives
+void g_shape(int dim, int np, const double *xn, const double *xi, double *phi, double *dphi) {
+  long double v[3][8], d[3][8];
+  for (int a = 0; a < dim; a++) lagrange_ld(xn, np, xi[a], v[a], d[a]);
+  int dof = 1;
+  for (int a = 0; a < dim; a++) dof *= np;
+  for (int n = 0; n < dof; n++) {
+    const int idx[3] = {n % np, (n / np) % np, n / (np * np)};
+    long double s = 1;
+    for (int a = 0; a < dim; a++) s *= v[a][idx[a]];
+    phi[n] = static_cast<double>(s);
+    if (dphi)
+      for (int a = 0; a < dim; a++) {
+        long double q = d[a][idx[a]];
+        for (int b = 0; b < dim; b++)
+          if (b != a) q *= v[b][idx[b]];
+        dphi[n * dim + a] = static_cast<double>(q);
+      }
+  }
+}
+
+template <class T>
+cudaError_t g_upload(tpsb_ctx *c, const T **dst, const std::vector<T> &src) {
+  T *p = nullptr;
+  *dst = nullptr;
+  if (src.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), src.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  c->gen_allocs.push_back(p);
+  *dst = p;
+  return cudaMemcpy(p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// in-place inverse of an SPD matrix (row-major n x n) by Cholesky: A = L L^T, A^-1 = L^-T L^-1
+bool g_spd_inverse(std::vector<double> &A, int n) {
+  std::vector<long double> L(static_cast<size_t>(n) * n, 0.0L), Li(static_cast<size_t>(n) * n, 0.0L);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      long double s = A[i * n + j];
+      for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k];
+      if (i == j) {
+        if (s <= 0) return false;
+        L[i * n + i] = sqrtl(s);
+      } else {
+        L[i * n + j] = s / L[j * n + j];
+      }
+    }
+  for (int c = 0; c < n; c++)  // Li = L^-1 (lower triangular), column by column
+    for (int i = c; i < n; i++) {
+      long double s = (i == c) ? 1.0L : 0.0L;
+      for (int k = c; k < i; k++) s -= L[i * n + k] * Li[k * n + c];
+      Li[i * n + c] = s / L[i * n + i];
+    }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      long double s = 0;
+      for (int k = std::max(i, j); k < n; k++) s += Li[k * n + i] * Li[k * n + j];
+      A[i * n + j] = static_cast<double>(s);
+    }
+  return true;
+}
+
+// Everything the generic kernels need; returns an error string (empty on success).
+std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_space_desc *space) {
+  const int dim = maps->dim, p = space->order, np = p + 1, NE = c->NE, NF = maps->num_faces;
+  const int nv = 1 << dim, nfe = 2 * dim, nori = dim == 3 ? 8 : 2;
+  int dof = 1;
+  for (int d = 0; d < dim; d++) dof *= np;
+  // 1-D nodes and rules (M2ulPhyS.cpp:558-572; MFEM rule sizes: GL n = order/2+1 with order|1, GLL n = order/2+2)
+  double xn[8], wtmp[8], xv[8], wv[8], xf[8], wf[8];
+  if (space->basis_type == 0)
+    gauss_legendre01(np, xn, wtmp);
+  else
+    gauss_lobatto01(np, xn, wtmp);
+  const int ov = 2 * p, of = dim - 1 + 2 * p;
+  const int nqv1 = space->int_rule_type == 0 ? (ov | 1) / 2 + 1 : ov / 2 + 2;
+  const int nqf1 = space->int_rule_type == 0 ? (of | 1) / 2 + 1 : of / 2 + 2;
+  if (nqv1 > 8 || nqf1 > 8) return "quadrature rule too large";
+  if (space->int_rule_type == 0) {
+    gauss_legendre01(nqv1, xv, wv);
+    gauss_legendre01(nqf1, xf, wf);
+  } else {
+    gauss_lobatto01(nqv1, xv, wv);
+    gauss_lobatto01(nqf1, xf, wf);
+  }
+  int nqv = 1, nqf = 1;
+  for (int d = 0; d < dim; d++) nqv *= nqv1;
+  for (int d = 0; d < dim - 1; d++) nqf *= nqf1;
+  std::vector<double> phiV(static_cast<size_t>(nqv) * dof), dphiV(static_cast<size_t>(nqv) * dof * dim), wV(nqv), xiV(static_cast<size_t>(nqv) * dim);
+  for (int q = 0; q < nqv; q++) {
+    const int qi[3] = {q % nqv1, (q / nqv1) % nqv1, q / (nqv1 * nqv1)};
+    double xi[3] = {0, 0, 0}, w = 1;
+    for (int d = 0; d < dim; d++) xi[d] = xv[qi[d]], w *= wv[qi[d]];
+    for (int d = 0; d < dim; d++) xiV[q * dim + d] = xi[d];
+    wV[q] = w;
+    g_shape(dim, np, xn, xi, &phiV[static_cast<size_t>(q) * dof], &dphiV[static_cast<size_t>(q) * dof * dim]);
+  }
+  const int ncode = nfe * nori;
+  std::vector<double> phiF(static_cast<size_t>(ncode) * nqf * dof), xiF(static_cast<size_t>(ncode) * nqf * dim), dlocF(static_cast<size_t>(ncode) * dim * (dim - 1)), wF(nqf);
+  for (int q = 0; q < nqf; q++) wF[q] = dim == 3 ? wf[q % nqf1] * wf[q / nqf1] : wf[q];
+  for (int lf = 0; lf < nfe; lf++)
+    for (int ori = 0; ori < nori; ori++) {
+      const int code = lf * nori + ori;
+      for (int q = 0; q < nqf; q++) {
+        const double st[2] = {xf[q % nqf1], dim == 3 ? xf[q / nqf1] : 0.0};
+        double xi[3], dl[6];
+        g_loc_map(dim, lf, ori, st, xi, dl);
+        for (int d = 0; d < dim; d++) xiF[(static_cast<size_t>(code) * nqf + q) * dim + d] = xi[d];
+        for (int k = 0; k < dim * (dim - 1); k++) dlocF[static_cast<size_t>(code) * dim * (dim - 1) + k] = dl[k];
+        g_shape(dim, np, xn, xi, &phiF[(static_cast<size_t>(code) * nqf + q) * dof], nullptr);
+      }
+    }
+  // element -> faces by local face index
+  std::vector<int> el_face(static_cast<size_t>(NE) * nfe, -1);
+  for (int f = 0; f < NF; f++) {
+    const int e1 = maps->face_el1[f], e2 = maps->face_el2[f];
+    const int lf1 = maps->face_inf1[f] / 64;
+    if (e1 < 0 || e1 >= NE || lf1 < 0 || lf1 >= nfe || maps->face_inf1[f] % 64 != 0) return "invalid face tables";
+    el_face[static_cast<size_t>(e1) * nfe + lf1] = f;
+    if (e2 >= 0) {
+      const int lf2 = maps->face_inf2[f] / 64, ori = maps->face_inf2[f] % 64;
+      if (e2 >= NE) return "partitioned meshes are not built on the generic path yet";
+      if (lf2 < 0 || lf2 >= nfe || ori < 0 || ori >= nori) return "invalid face tables";
+      el_face[static_cast<size_t>(e2) * nfe + lf2] = f;
+    }
+  }
+  for (int v : el_face)
+    if (v < 0) return "an element face is missing from the face tables";
+  // mass matrices (rhs_operator.cpp:173-189): diagonal when nodes and volume rule coincide
+  const bool diag = space->basis_type == 0 && space->int_rule_type == 0;
+  std::vector<double> me(static_cast<size_t>(NE) * (diag ? dof : dof * dof));
+  std::vector<double> M(static_cast<size_t>(dof) * dof);
+  for (int e = 0; e < NE; e++) {
+    const double *v = &maps->elem_vertices[static_cast<size_t>(e) * nv * dim];
+    std::fill(M.begin(), M.end(), 0.0);
+    for (int q = 0; q < nqv; q++) {
+      double J[9];
+      const double *xi = &xiV[static_cast<size_t>(q) * dim];
+      if (dim == 2) {
+        for (int i = 0; i < 2; i++) {
+          J[i] = (1 - xi[1]) * (v[2 + i] - v[i]) + xi[1] * (v[4 + i] - v[6 + i]);
+          J[i + 2] = (1 - xi[0]) * (v[6 + i] - v[i]) + xi[0] * (v[4 + i] - v[2 + i]);
+        }
+      } else {
+        const double x = xi[0], y = xi[1], z = xi[2], x0 = 1 - x, y0 = 1 - y, z0 = 1 - z;
+        for (int i = 0; i < 3; i++) {
+          const double X0 = v[i], X1 = v[3 + i], X2 = v[6 + i], X3 = v[9 + i], X4 = v[12 + i], X5 = v[15 + i], X6 = v[18 + i], X7 = v[21 + i];
+          J[i] = y0 * z0 * (X1 - X0) + y * z0 * (X2 - X3) + y0 * z * (X5 - X4) + y * z * (X6 - X7);
+          J[i + 3] = x0 * z0 * (X3 - X0) + x * z0 * (X2 - X1) + x0 * z * (X7 - X4) + x * z * (X6 - X5);
+          J[i + 6] = x0 * y0 * (X4 - X0) + x * y0 * (X5 - X1) + x * y * (X6 - X2) + x0 * y * (X7 - X3);
+        }
+      }
+      const double det = dim == 2 ? J[0] * J[3] - J[2] * J[1]
+                                  : J[0] * (J[4] * J[8] - J[5] * J[7]) - J[3] * (J[1] * J[8] - J[2] * J[7]) + J[6] * (J[1] * J[5] - J[2] * J[4]);
+      if (!(det > 0)) return "element with non-positive Jacobian";
+      const double wd = wV[q] * det;
+      const double *ph = &phiV[static_cast<size_t>(q) * dof];
+      if (diag) {
+        for (int i = 0; i < dof; i++) M[static_cast<size_t>(i) * dof + i] += wd * ph[i] * ph[i];
+      } else {
+        for (int i = 0; i < dof; i++)
+          for (int j = 0; j < dof; j++) M[static_cast<size_t>(i) * dof + j] += wd * ph[i] * ph[j];
+      }
+    }
+    if (diag) {
+      for (int i = 0; i < dof; i++) me[static_cast<size_t>(e) * dof + i] = 1.0 / M[static_cast<size_t>(i) * dof + i];
+    } else {
+      if (!g_spd_inverse(M, dof)) return "mass matrix is not positive definite";
+      std::copy(M.begin(), M.end(), &me[static_cast<size_t>(e) * dof * dof]);
+    }
+  }
+  GenArgs &g = c->gen;
+  memset(&g, 0, sizeof(g));
+  g.dim = dim, g.np = np, g.dof = dof, g.nqv = nqv, g.nqf = nqf, g.nfe = nfe, g.nv = nv;
+  g.neq = space->num_equation, g.nvel = space->nvel, g.NE = NE, g.N = static_cast<long long>(NE) * dof, g.me_diag = diag ? 1 : 0;
+  g.phys.dim = dim, g.phys.nvel = space->nvel, g.phys.neq = space->num_equation, g.phys.dry = c->phys;
+  std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE) * nv * dim);
+  std::vector<int> fe1(maps->face_el1, maps->face_el1 + NF), fe2(maps->face_el2, maps->face_el2 + NF),
+      fi1(maps->face_inf1, maps->face_inf1 + NF), fi2(maps->face_inf2, maps->face_inf2 + NF);
+  cudaError_t ce = cudaSetDevice(c->device);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.phiV, phiV);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.dphiV, dphiV);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.wV, wV);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.xiV, xiV);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.phiF, phiF);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.xiF, xiF);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.dlocF, dlocF);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.wF, wF);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.vx, vx);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.el_face, el_face);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.f_el1, fe1);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.f_el2, fe2);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.f_inf1, fi1);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.f_inf2, fi2);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.me_inv, me);
+  const size_t nb = static_cast<size_t>(g.N) * sizeof(double);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * g.neq);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUp, nb * g.neq * dim);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_maxBits, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_mcs, sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMemset(c->d_maxBits, 0, sizeof(unsigned long long));
+  if (ce != cudaSuccess) return std::string("device setup failed: ") + cudaGetErrorString(ce);
+  g.Up = c->d_Up, g.gradUp = c->d_gradUp, g.maxCharBits = c->d_maxBits;
+  // element_to_faces (stride 1 + faces per element; 7 in 3-D as in the reference)
+  std::vector<int> e2f(static_cast<size_t>(nfe + 1) * NE, 0);
+  for (int f = 0; f < NF; f++) {
+    if (maps->face_el2[f] < 0) continue;
+    for (int e : {maps->face_el1[f], maps->face_el2[f]}) {
+      const int nf = e2f[static_cast<size_t>(nfe + 1) * e];
+      e2f[static_cast<size_t>(nfe + 1) * e + nf + 1] = f;
+      e2f[static_cast<size_t>(nfe + 1) * e] = nf + 1;
+    }
+  }
+  c->element_to_faces = e2f;
+  return "";
+}
+
+}  // namespace
+
 extern "C" {
 
 const char *tpsb_version(void) { return "tpsb200 0.1 (sm_100a, fp64)"; }
@@ -154,12 +413,21 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   tpsb_ctx *ctx = nullptr;  // errors before allocation go to the thread-local create error
   if (!maps || !space || !phys || !out) return fail(ctx, TPSB_EINVAL, "null argument");
   *out = nullptr;
-  if (maps->dim != 3) return fail(ctx, TPSB_ENOTIMPL, "only dim = 3 (hexahedra) is built; got dim = %d", maps->dim);
-  if (space->basis_type != 0 || space->int_rule_type != 0)
-    return fail(ctx, TPSB_ENOTIMPL, "only basisType = 0 / integrationRule = 0 (Gauss-Legendre) is built");
+  if (maps->dim != 2 && maps->dim != 3) return fail(ctx, TPSB_EINVAL, "dim must be 2 (quadrilaterals) or 3 (hexahedra); got %d", maps->dim);
+  if (space->basis_type < 0 || space->basis_type > 1 || space->int_rule_type < 0 || space->int_rule_type > 1)
+    return fail(ctx, TPSB_EINVAL, "basisType / integrationRule must be 0 (Gauss-Legendre) or 1 (Gauss-Lobatto)");
   if (space->order < 1 || space->order > 3) return fail(ctx, TPSB_ENOTIMPL, "order must be 1..3");
-  if (phys->fluid != TPSB_DRY_AIR || space->num_equation != NEQ || space->nvel != DIM)
-    return fail(ctx, TPSB_ENOTIMPL, "only dry air with 5 equations is built");
+  if (phys->fluid != TPSB_DRY_AIR || space->nvel != maps->dim || space->num_equation != space->nvel + 2)
+    return fail(ctx, TPSB_ENOTIMPL, "only dry air (num_equation = dim + 2, nvel = dim) is built");
+  // 3-D Gauss-Legendre dry air runs the specialised kernels; everything else the generic tensor-product path
+  bool want_generic = maps->dim != 3 || space->basis_type != 0 || space->int_rule_type != 0;
+  if (const char *pth = getenv("TPSB_PATH")) want_generic = want_generic || strcmp(pth, "generic") == 0;
+  if (want_generic) {
+    if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
+    for (int f = 0; f < maps->num_faces; f++)
+      if (maps->face_el2 && maps->face_el2[f] < 0 && bcs && bcs->num_bcs > 0)
+        return fail(ctx, TPSB_ENOTIMPL, "boundary conditions are not built on the generic (2-D / Gauss-Lobatto) path yet");
+  }
   if (phys->eq_system != TPSB_EULER && phys->eq_system != TPSB_NS)
     return fail(ctx, TPSB_ENOTIMPL, "equation system %d not built", phys->eq_system);
   if (maps->num_elems <= 0 || maps->num_faces <= 0 || !maps->elem_vertices || !maps->face_el1 || !maps->face_el2 ||
@@ -220,6 +488,21 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   c->phys.cp_div_pr = phys->specific_heat_ratio * phys->gas_constant /
                       (phys->sutherland_Pr * (phys->specific_heat_ratio - 1.));
 
+  if (want_generic) {
+    c->generic = true;
+    c->dim = maps->dim;
+    c->neq = space->num_equation;
+    c->nd = 1;
+    for (int d = 0; d < maps->dim; d++) c->nd *= c->np;
+    c->N = static_cast<long long>(c->NE) * c->nd;
+    const std::string err = create_generic(c, maps, space);
+    if (!err.empty()) {
+      tpsb_destroy(c);
+      return fail(nullptr, TPSB_EINVAL, "%s", err.c_str());
+    }
+    *out = c;
+    return TPSB_OK;
+  }
   const int NE = c->NE, NEH = c->NEH;
   bool all_affine = true;
   for (int e = 0; e < NE && all_affine; e++) all_affine = element_is_affine(&maps->elem_vertices[static_cast<size_t>(e) * 24]);
@@ -504,6 +787,7 @@ void tpsb_destroy(tpsb_ctx *c) {
                   c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  for (void *p : c->gen_allocs) cudaFree(p);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
   if (c->ev_recvU) cudaEventDestroy(c->ev_recvU);
@@ -513,7 +797,7 @@ void tpsb_destroy(tpsb_ctx *c) {
 }
 
 int64_t tpsb_num_dofs(const tpsb_ctx *c) { return c ? c->N : 0; }
-int tpsb_num_equation(const tpsb_ctx *c) { return c ? NEQ : 0; }
+int tpsb_num_equation(const tpsb_ctx *c) { return c ? c->neq : 0; }
 int64_t tpsb_launch_count(const tpsb_ctx *c) { return c ? c->launches : 0; }
 
 int tpsb_get_element_to_faces(const tpsb_ctx *c, int *out) {
@@ -833,8 +1117,46 @@ static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   return TPSB_OK;
 }
 
+// ---- generic path (rhs_generic.cuh) ----
+static int run_gradients_generic(tpsb_ctx *ctx, const double *d_x, bool prims_done) {
+  tpsb_ctx *c = ctx;
+  GenArgs g = c->gen;
+  g.U = d_x;
+  if (!prims_done) {
+    ProfScope ps(c, K_PRIM);
+    gen_prim_kernel<<<static_cast<unsigned>((g.N + 255) / 256), 256, 0, c->stream>>>(g);
+  }
+  {
+    ProfScope ps(c, K_GRAD);
+    const size_t smem = gen_grad_smem(g);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    gen_grad_kernel<<<g.NE, 128, smem, c->stream>>>(g);
+  }
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  tpsb_ctx *c = ctx;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
+  int rc = run_gradients_generic(c, d_x, false);
+  if (rc) return rc;
+  GenArgs g = c->gen;
+  g.U = d_x;
+  g.y = d_y;
+  {
+    ProfScope ps(c, K_RESID);
+    const size_t smem = gen_resid_smem(g);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    gen_resid_kernel<<<g.NE, 128, smem, c->stream>>>(g);
+  }
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
 static int run_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   tpsb_ctx *c = ctx;
+  if (c->generic) return run_mult_generic(ctx, d_x, d_y);
   if (c->fast) return run_mult_fast(ctx, d_x, d_y);
   CU(cudaSetDevice(c->device));
   KernelArgs a = make_args(c, d_x, d_y);
@@ -862,7 +1184,7 @@ static __global__ void bits_to_double_kernel(const unsigned long long *bits, dou
 
 static int ensure_work(tpsb_ctx *ctx, double **p) {
   if (*p) return TPSB_OK;
-  CU(cudaMalloc(p, static_cast<size_t>(ctx->N) * NEQ * sizeof(double)));
+  CU(cudaMalloc(p, static_cast<size_t>(ctx->N) * ctx->neq * sizeof(double)));
   return TPSB_OK;
 }
 
@@ -879,7 +1201,7 @@ int tpsb_rhs_mult_host(tpsb_ctx *ctx, const double *h_x, double *h_y) {
   int rc = ensure_work(ctx, &ctx->d_hx);
   if (!rc) rc = ensure_work(ctx, &ctx->d_hy);
   if (rc) return rc;
-  const size_t nb = static_cast<size_t>(ctx->N) * NEQ * sizeof(double);
+  const size_t nb = static_cast<size_t>(ctx->N) * ctx->neq * sizeof(double);
   CU(cudaMemcpyAsync(ctx->d_hx, h_x, nb, cudaMemcpyHostToDevice, ctx->stream));
   rc = run_mult(ctx, ctx->d_hx, ctx->d_hy);
   if (rc) return rc;
@@ -891,6 +1213,14 @@ int tpsb_rhs_mult_host(tpsb_ctx *ctx, const double *h_x, double *h_y) {
 int tpsb_update_primitives(tpsb_ctx *ctx, const double *d_x) {
   if (!ctx || !d_x) return TPSB_EINVAL;
   CU(cudaSetDevice(ctx->device));
+  if (ctx->generic) {
+    GenArgs g = ctx->gen;
+    g.U = d_x;
+    ProfScope ps(ctx, K_PRIM);
+    gen_prim_kernel<<<static_cast<unsigned>((g.N + 255) / 256), 256, 0, ctx->stream>>>(g);
+    CU(cudaGetLastError());
+    return TPSB_OK;
+  }
   KernelArgs a = make_args(ctx, d_x, nullptr);
   launch_prim(ctx, a, 0);
   CU(cudaGetLastError());
@@ -900,6 +1230,7 @@ int tpsb_update_primitives(tpsb_ctx *ctx, const double *d_x) {
 int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updated) {
   if (!ctx || !d_x) return TPSB_EINVAL;
   CU(cudaSetDevice(ctx->device));
+  if (ctx->generic) return run_gradients_generic(ctx, d_x, primitives_updated != 0);
   KernelArgs a = make_args(ctx, d_x, nullptr);
   if (ctx->fast) return run_gradients_fast(ctx, a, primitives_updated != 0);
   return run_gradients(ctx, a, primitives_updated != 0);
@@ -949,7 +1280,7 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
   if (!rc) rc = ensure_work(ctx, &ctx->d_yv);
   if (!rc) rc = ensure_work(ctx, &ctx->d_z);
   if (rc) return rc;
-  const long long n = ctx->N * NEQ;
+  const long long n = ctx->N * ctx->neq;
   const unsigned nb = static_cast<unsigned>((n + 255) / 256);
   double *k = ctx->d_k, *y = ctx->d_yv, *z = ctx->d_z, *x = d_U;
   cudaStream_t st = ctx->stream;
