@@ -66,14 +66,41 @@ typedef struct {
 /* Physics parameter block: the POD input structs of the reference flattened
  * (DryAirInput src/dataStructures.hpp:609-622; DryAirTransport ctor src/transport_properties.cpp:208;
  *  SutherlandData :205-209).                                                                     */
+/* Plasma models of a user-defined working fluid (fluid = TPSB_USER_DEFINED): the reference's POD input structs
+ * PerfectMixtureInput, constantTransportData and ChemistryInput (src/dataStructures.hpp:537-546,623-633,690-712)
+ * flattened.  Species are in MIXTURE order: electron second to last, background last (src/M2ulPhyS.cpp:2979-3137). */
+#define TPSB_MAX_SPECIES 8
+#define TPSB_MAX_REACTIONS 34
+typedef struct {
+  /* PerfectMixture (src/equation_of_state.cpp:478-574) */
+  int num_species, ambipolar, two_temperature;
+  double mw[TPSB_MAX_SPECIES];               /* GasParams::SPECIES_MW [kg/mol]                 */
+  double charge[TPSB_MAX_SPECIES];           /* GasParams::SPECIES_CHARGES                     */
+  double formation_energy[TPSB_MAX_SPECIES]; /* GasParams::FORMATION_ENERGY [J/mol]            */
+  double molar_cv[TPSB_MAX_SPECIES];         /* perfect_mixture/constant_molar_cv, units of R  */
+  /* transport_model = constant (src/transport_properties.cpp:303-448); TransportModel value 2 */
+  int transport_model;
+  double viscosity, bulk_viscosity, thermal_conductivity, electron_thermal_conductivity;
+  double diffusivity[TPSB_MAX_SPECIES], mt_freq[TPSB_MAX_SPECIES];
+  /* Chemistry (src/chemistry.cpp:40-300): reaction r uses model[r] = ReactionModel (0 Arrhenius, 1 Hoffert-Lien) */
+  int num_reactions;
+  double min_temperature;
+  int model[TPSB_MAX_REACTIONS], detailed_balance[TPSB_MAX_REACTIONS];
+  double rate_params[TPSB_MAX_REACTIONS][3];         /* A, b, E                               */
+  double reaction_energy[TPSB_MAX_REACTIONS];
+  double equilibrium_params[TPSB_MAX_REACTIONS][3];  /* A, b, E of K_eq = A T^b exp(-E/T)     */
+  int reactant_stoich[TPSB_MAX_REACTIONS][TPSB_MAX_SPECIES], product_stoich[TPSB_MAX_REACTIONS][TPSB_MAX_SPECIES];
+} tpsb_plasma_models;
+
 typedef struct {
   int eq_system;          /* TPSB_EULER / TPSB_NS                              */
-  int fluid;              /* TPSB_DRY_AIR                                      */
+  int fluid;              /* TPSB_DRY_AIR, or TPSB_USER_DEFINED with `plasma`  */
   double specific_heat_ratio;
   double gas_constant;
   double visc_mult;       /* flow/viscosityMultiplier                          */
   double bulk_visc_mult;  /* flow/bulkViscosityMultiplier                      */
   double sutherland_C1, sutherland_S0, sutherland_Pr;
+  const tpsb_plasma_models *plasma; /* fluid == TPSB_USER_DEFINED: gas / transport / chemistry models; else NULL */
 } tpsb_physics;
 
 /* Boundary conditions: BCintegrator's attribute -> {InletBC, OutletBC, WallBC} maps (src/BCintegrator.cpp:64-125).
@@ -142,6 +169,12 @@ int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updat
 /* Views of the context-owned fields: M2ulPhyS::getPrimitiveGF / getGradientGF (src/M2ulPhyS.hpp:368-470).
  * Up: neq*N, gradUp: dim*neq*N doubles, device memory, valid until destroy.                       */
 int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp);
+/* The solution grid function U_ that SourceTerm / AxisymmetricSource read the conserved state from
+ * (src/source_term.cpp:66,77,121): in Runge-Kutta stages it is NOT the stage vector x handed to Mult, while
+ * Up / gradUp are computed from x -- the reference's behaviour, kept (parity trap 1).
+ * NULL (default): use x itself.  tpsb_ode_step sets it to d_U for the duration of the step.        */
+int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U);
+
 /* max_char_speed of the last Mult (src/rhs_operator.cpp:549-558), reduced over this rank's nodes
  * (and over ranks when a communicator is attached); synchronises the stream.                      */
 int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out);
@@ -165,6 +198,12 @@ int tpsb_get_ref_tables(int order, double *out, int cap);
 /* Test hook: device views of internal buffers. which = 0: face residuals [two-sided face][neq][(p+1)^2];
  * 1: face-trace blocks of the fast path [6*num_elems + shared faces][10][(p+1)^2] (NULL on other paths). */
 int tpsb_debug_buffer(tpsb_ctx *ctx, int which, double **d_ptr, int64_t *count);
+
+/* Test hook (generic path): the context's per-point physics on n points, point-major arrays on the device:
+ * which = 0 primitives (GasMixture::GetPrimitivesFromConservatives), 1 max characteristic speed, 2 convective flux
+ * (Fluxes::ComputeConvectiveFluxes), 3 viscous flux (ComputeViscousFluxes; d_aux = gradUp), 4 plasma source
+ * (SourceTerm::updateTerms node body; d_aux = gradUp).                                              */
+int tpsb_debug_point_eval(tpsb_ctx *ctx, int which, int n, const double *d_U, const double *d_aux, double *d_out);
 
 /* Per-kernel device timers (the role GRVY timers play in the reference, src/M2ulPhyS.cpp:2146-2155):
  * with profiling on, every launch is bracketed by CUDA events on the context stream; the accumulated

@@ -147,6 +147,7 @@ struct Oracle {
   // work
   std::vector<double> Up, gradUp;
   double max_char_speed = 0;
+  const double *sol_view = nullptr;  // the solution grid function U_ the forcing terms read (parity trap 1)
 
   // ---- element geometry: multilinear map from the 2^dim vertices (mesh nodes of order 1) ----
   double vref(int a, int d) const { return dim == 3 ? HEX_VERT[a][d] : QUAD_VERT[a][d]; }
@@ -760,6 +761,21 @@ struct Oracle {
         }
     }
     for (double m : mcs_t) max_char_speed = std::max(max_char_speed, m);
+    // ---- forcing terms, added after Me_inv (src/rhs_operator.cpp:451-461): SourceTerm::updateTerms
+    if (ph->has_source()) {
+      const double *Usol = sol_view ? sol_view : x;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+      for (long n = 0; n < N; n++) {
+        double Un[16], upn[16], g[48], src[16];
+        for (int eq = 0; eq < neq; eq++) {
+          upn[eq] = Up[n + eq * N];
+          Un[eq] = Usol[n + eq * N];
+          for (int d = 0; d < dim; d++) g[eq + d * neq] = gradUp[n + eq * N + static_cast<size_t>(d) * neq * N];
+        }
+        ph->source_term(Un, upn, g, static_cast<int>(n), src);
+        for (int eq = 0; eq < neq; eq++) y[n + eq * N] += src[eq];
+      }
+    }
   }
 };
 
@@ -835,6 +851,7 @@ void orc_bc_flux(void *h, const OrcBc *bc, int use_bc_in_grad, const double *nor
   o->bc_flux(*bc, normal, stateIn, gradState, xyz, 0.0, flux);
   o->use_bc_in_grad = save;
 }
+void orc_set_solution_view(void *h, const double *U) { static_cast<Oracle *>(h)->sol_view = U; }
 void orc_destroy(void *h) {
   Oracle *o = static_cast<Oracle *>(h);
   if (!o) return;
@@ -921,6 +938,37 @@ void orc_gll_rule(int n, double *x, double *w) {
   orc::gauss_lobatto01(n, xv, wv);
   std::copy(xv.begin(), xv.end(), x);
   std::copy(wv.begin(), wv.end(), w);
+}
+
+// ---- point-wise probes of the operator's own physics object (any fluid / dim / neq) ----
+void orc_pt_prim(void *h, int n, const double *U, double *Up) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (int i = 0; i < n; i++) o->ph->prim(U + o->neq * i, Up + o->neq * i);
+}
+void orc_pt_cons(void *h, int n, const double *Up, double *U) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (int i = 0; i < n; i++) o->ph->cons(Up + o->neq * i, U + o->neq * i);
+}
+void orc_pt_max_char_speed(void *h, int n, const double *U, double *out) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (int i = 0; i < n; i++) out[i] = o->ph->max_char_speed(U + o->neq * i);
+}
+void orc_pt_conv_flux(void *h, int n, const double *U, double *F) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (int i = 0; i < n; i++) o->ph->conv_flux(U + o->neq * i, F + o->neq * o->dim * i);
+}
+void orc_pt_visc_flux(void *h, int n, const double *U, const double *gradUp, double *F) {
+  Oracle *o = static_cast<Oracle *>(h);
+  double xyz[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++) o->ph->visc_flux(U + o->neq * i, gradUp + o->neq * o->dim * i, xyz, 0.0, 0.0, F + o->neq * o->dim * i);
+}
+void orc_pt_source(void *h, int n, const double *Un, const double *Up, const double *gradUp, double *S) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (int i = 0; i < n; i++) {
+    double a[16], b[16];
+    for (int eq = 0; eq < o->neq; eq++) a[eq] = Un[o->neq * i + eq], b[eq] = Up[o->neq * i + eq];
+    o->ph->source_term(a, b, gradUp + o->neq * o->dim * i, i, S + o->neq * i);
+  }
 }
 
 // ---- point-wise physics probes (tests compare product device physics and port vs reference) ----

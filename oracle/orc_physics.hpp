@@ -15,6 +15,7 @@
 extern "C" {
 // Mirrors the scalar inputs of DryAirInput (src/dataStructures.hpp:609-622) and the
 // DryAirTransport constructor (src/transport_properties.cpp:208-221).
+struct OrcPlasma;
 struct OrcPhysParams {
   int eq_system;  // Equations enum of the reference: 0 EULER, 1 NS (src/dataStructures.hpp:65-69)
   int fluid;      // WorkingFluid: 0 DRY_AIR
@@ -23,6 +24,23 @@ struct OrcPhysParams {
   double visc_mult;
   double bulk_visc_mult;
   double C1, S0, Pr;  // Sutherland data (src/dataStructures.hpp:205-209)
+  const OrcPlasma *plasma;  // fluid == 1 (USER_DEFINED): gas / transport / chemistry models (reference back end only)
+};
+// Plasma models of a user-defined fluid: PerfectMixtureInput + constantTransportData + ChemistryInput
+// (src/dataStructures.hpp:537-546,623-633,690-712) flattened; same layout as tpsb_plasma_models.
+struct OrcPlasma {
+  int num_species, ambipolar, two_temperature;
+  double mw[8], charge[8], formation_energy[8], molar_cv[8];
+  int transport_model;
+  double viscosity, bulk_viscosity, thermal_conductivity, electron_thermal_conductivity;
+  double diffusivity[8], mt_freq[8];
+  int num_reactions;
+  double min_temperature;
+  int model[34], detailed_balance[34];
+  double rate_params[34][3];
+  double reaction_energy[34];
+  double equilibrium_params[34][3];
+  int reactant_stoich[34][8], product_stoich[34][8];
 };
 // One boundary condition of BCintegrator's attribute maps (src/BCintegrator.cpp:64-125).
 // kind: 0 inlet, 1 outlet, 2 wall; type: the reference's InletType / OutletType / WallType value
@@ -52,6 +70,11 @@ struct Physics {
   // RiemannSolverTPS::Eval (useRoe = false -> Eval_LF)
   virtual void riemann(const double *U1, const double *U2, const double *nor, double *flux) = 0;
   virtual int num_active_species() const = 0;
+  // SourceTerm::updateTerms for one node (src/source_term.cpp:117-250): Un = conserved state of the solution
+  // grid function, upn / gradUpn = primitives and their gradients; both may be clamped in place like the
+  // reference does.  Fluids without plasma sources keep the default (no forcing term registered).
+  virtual bool has_source() const { return false; }
+  virtual void source_term(double *Un, double *upn, const double *gradUpn, int node, double *src) {}
   // ---- used by the boundary conditions ----
   virtual int num_species() const = 0;
   // GasMixture::ComputePressure

@@ -5,6 +5,7 @@
 // (equation_of_state.cpp, transport_properties.cpp, fluxes.cpp, riemann_solver.cpp, ...)
 // against the header stub in oracle/refstub/.  Built only into oracle/_ref/ by
 // oracle/Makefile; the resulting shared object travels to the GPU box, the sources do not.
+#include "chemistry.hpp"
 #include "equation_of_state.hpp"
 #include "fluxes.hpp"
 #include "riemann_solver.hpp"
@@ -80,7 +81,174 @@ class DryAirRef : public Physics {
   }
 };
 
+// PerfectMixture + ConstantTransport + Chemistry + Fluxes + RiemannSolverTPS, the reference's own classes.
+class MixtureRef : public Physics {
+  int dim_, nvel_, neq_;
+  PerfectMixture *mix_;
+  ConstantTransport *trans_;
+  Fluxes *flux_;
+  RiemannSolverTPS *rs_;
+  Chemistry *chem_ = nullptr;
+  double rxParams_[34][3];
+
+ public:
+  MixtureRef(const OrcPhysParams &p, int dim, int nvel, int neq) : dim_(dim), nvel_(nvel), neq_(neq) {
+    const OrcPlasma &pm = *p.plasma;
+    PerfectMixtureInput in;
+    in.f = USER_DEFINED;
+    in.numSpecies = pm.num_species;
+    in.isElectronIncluded = true;
+    in.ambipolar = pm.ambipolar != 0;
+    in.twoTemperature = pm.two_temperature != 0;
+    for (int sp = 0; sp < pm.num_species; sp++) {
+      in.gasParams[sp + GasParams::SPECIES_MW * pm.num_species] = pm.mw[sp];
+      in.gasParams[sp + GasParams::SPECIES_CHARGES * pm.num_species] = pm.charge[sp];
+      in.gasParams[sp + GasParams::FORMATION_ENERGY * pm.num_species] = pm.formation_energy[sp];
+      in.gasParams[sp + GasParams::SPECIES_DEGENERACY * pm.num_species] = 1.0;
+      in.molarCV[sp] = pm.molar_cv[sp];
+    }
+    mix_ = new PerfectMixture(in, dim, nvel);  // equation_of_state.cpp:478
+    constantTransportData ct;
+    ct.viscosity = pm.viscosity;
+    ct.bulkViscosity = pm.bulk_viscosity;
+    ct.thermalConductivity = pm.thermal_conductivity;
+    ct.electronThermalConductivity = pm.electron_thermal_conductivity;
+    for (int sp = 0; sp < gpudata::MAXSPECIES; sp++) {
+      ct.diffusivity[sp] = sp < pm.num_species ? pm.diffusivity[sp] : 0.0;
+      ct.mtFreq[sp] = sp < pm.num_species ? pm.mt_freq[sp] : 0.0;
+    }
+    ct.electronIndex = pm.num_species - 2;
+    trans_ = new ConstantTransport(mix_, ct);  // transport_properties.cpp:303
+    const Equations eqs = static_cast<Equations>(p.eq_system);
+    flux_ = new Fluxes(mix_, eqs, trans_, neq, dim, false);
+    rs_ = new RiemannSolverTPS(neq, mix_, eqs, flux_, false, false);
+    if (pm.num_reactions > 0) {
+      ChemistryInput ci;
+      ci.model = NUM_CHEMISTRYMODEL;
+      ci.electronIndex = pm.num_species - 2;
+      ci.numReactions = pm.num_reactions;
+      ci.minimumTemperature = pm.min_temperature;
+      for (int r = 0; r < pm.num_reactions; r++) {
+        ci.reactionEnergies[r] = pm.reaction_energy[r];
+        ci.detailedBalance[r] = pm.detailed_balance[r] != 0;
+        ci.reactionModels[r] = static_cast<ReactionModel>(pm.model[r]);
+        for (int k = 0; k < 3; k++) {
+          rxParams_[r][k] = pm.rate_params[r][k];
+          ci.equilibriumConstantParams[k + r * gpudata::MAXCHEMPARAMS] = pm.equilibrium_params[r][k];
+        }
+        ci.reactionInputs[r].modelParams = rxParams_[r];
+        for (int sp = 0; sp < pm.num_species; sp++) {
+          ci.reactantStoich[sp + r * pm.num_species] = static_cast<int16_t>(pm.reactant_stoich[r][sp]);
+          ci.productStoich[sp + r * pm.num_species] = static_cast<int16_t>(pm.product_stoich[r][sp]);
+        }
+      }
+      chem_ = new Chemistry(mix_, ci);  // chemistry.cpp:40
+    }
+  }
+  ~MixtureRef() {
+    delete chem_;
+    delete rs_;
+    delete flux_;
+    delete trans_;
+    delete mix_;
+  }
+  const char *kind() const override { return "reference"; }
+  int num_active_species() const override { return mix_->GetNumActiveSpecies(); }
+  int num_species() const override { return mix_->GetNumSpecies(); }
+  void prim(const double *U, double *Up) override { mix_->GetPrimitivesFromConservatives(U, Up); }
+  void cons(const double *Up, double *U) override { mix_->GetConservativesFromPrimitives(Up, U); }
+  double max_char_speed(const double *U) override { return mix_->ComputeMaxCharSpeed(U); }
+  void conv_flux(const double *U, double *F) override { flux_->ComputeConvectiveFluxes(U, F); }
+  void visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, double *F) override {
+    flux_->ComputeViscousFluxes(U, gradUp, xyz, delta, dist, F);
+  }
+  void riemann(const double *U1, const double *U2, const double *nor, double *flux) override {
+    rs_->Eval(U1, U2, nor, flux, false);
+  }
+  double pressure(const double *U) override { return mix_->ComputePressure(U); }
+  void stagnation_state(const double *U, double *out) override {
+    Vector a(const_cast<double *>(U), neq_), b(neq_);
+    mix_->computeStagnationState(a, b);
+    for (int i = 0; i < neq_; i++) out[i] = b[i];
+  }
+  void stagnant_state_with_temp(const double *U, double T, double *out) override {
+    Vector a(const_cast<double *>(U), neq_), b(neq_);
+    mix_->computeStagnantStateWithTemp(a, T, b);
+    for (int i = 0; i < neq_; i++) out[i] = b[i];
+  }
+  void modify_energy_for_pressure(const double *in, double *out, double p, bool mee) override {
+    double tmp[16];
+    for (int i = 0; i < neq_; i++) tmp[i] = in[i];
+    mix_->modifyEnergyForPressure(tmp, out, p, mee);
+  }
+  void bdr_visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, const double *nrm,
+                     const double *primFlux, const bool *primFluxIdxs, double *normalFlux) override {
+    BoundaryViscousFluxData bc;
+    for (int d = 0; d < gpudata::MAXDIM; d++) bc.normal[d] = d < dim_ ? nrm[d] : 0.0;
+    for (int i = 0; i < gpudata::MAXEQUATIONS; i++) {
+      bc.primFlux[i] = i < 16 ? primFlux[i] : 0.0;
+      bc.primFluxIdxs[i] = i < 16 ? primFluxIdxs[i] : false;
+    }
+    flux_->ComputeBdrViscousFluxes(U, gradUp, xyz, delta, dist, bc, normalFlux);
+  }
+  bool has_source() const override { return true; }
+  // SourceTerm::updateTerms node body (src/source_term.cpp:117-250) over the reference's transport / chemistry /
+  // mixture objects; no radiation, no EM coupling output.
+  void source_term(double *Un, double *upn, const double *gradUpn, int n, double *srcTerm) override {
+    const int _num_equation = neq_, _nvel = nvel_, _dim = dim_;
+    const int _numSpecies = mix_->GetNumSpecies(), _numActiveSpecies = mix_->GetNumActiveSpecies();
+    const int _numReactions = chem_ ? chem_->getNumReactions() : 0;
+    for (int sp = 0; sp < _numActiveSpecies; sp++) {
+      int eq = 3 + 2 + sp;
+      if (eq >= _num_equation) continue;  // the reference indexes its MAXEQUATIONS-sized scratch; harmless there
+      upn[eq] = max(upn[eq], 0.0);
+      Un[eq] = max(Un[eq], 0.0);
+    }
+    double Efield[gpudata::MAXDIM];
+    for (int v = 0; v < _nvel; v++) Efield[v] = 0.0;
+    double globalTransport[gpudata::MAXSPECIES];
+    double speciesTransport[gpudata::MAXSPECIES * SpeciesTrns::NUM_SPECIES_COEFFS];
+    double diffusionVelocity[gpudata::MAXSPECIES * gpudata::MAXDIM];
+    for (int v = 0; v < _nvel; v++)
+      for (int sp = 0; sp < _numSpecies; sp++) diffusionVelocity[sp + v * _numSpecies] = 0.0;
+    double ns[gpudata::MAXSPECIES];
+    trans_->ComputeSourceTransportProperties(Un, upn, gradUpn, Efield, 0.0, globalTransport, speciesTransport,
+                                             diffusionVelocity, ns);
+    for (int eq = 0; eq < _num_equation; eq++) srcTerm[eq] = 0.0;
+    double Th = upn[1 + _nvel], Te = mix_->IsTwoTemperature() ? upn[_num_equation - 1] : Th;
+    double progressRates[gpudata::MAXREACTIONS], creationRates[gpudata::MAXSPECIES], emissionRates[gpudata::MAXSPECIES];
+    for (int r = 0; r < gpudata::MAXREACTIONS; r++) progressRates[r] = 0.0;
+    if (_numSpecies > 1 && _numReactions > 0) {
+      double kfwd[gpudata::MAXREACTIONS], kC[gpudata::MAXREACTIONS];
+      chem_->computeForwardRateCoeffs(ns, Th, Te, n, kfwd);
+      chem_->computeEquilibriumConstants(Th, Te, kC);
+      for (int sp = 0; sp < _numSpecies; sp++) creationRates[sp] = 0.0;
+      chem_->computeProgressRate(ns, kfwd, kC, progressRates);
+      chem_->computeCreationRate(progressRates, creationRates, emissionRates);
+      for (int sp = 0; sp < _numActiveSpecies; sp++) srcTerm[2 + _nvel + sp] += creationRates[sp];
+    }
+    if (mix_->IsTwoTemperature()) {
+      for (int r = 0; r < _numReactions; r++)
+        if (chem_->isElectronInvolvedAt(r)) srcTerm[_num_equation - 1] -= chem_->getReactionEnergy(r) * progressRates[r];
+      double gradPe[gpudata::MAXDIM];
+      mix_->computeElectronPressureGrad(ns[_numSpecies - 2], Te, gradUpn, gradPe);
+      for (int d = 0; d < _dim; d++) srcTerm[_num_equation - 1] += gradPe[d] * upn[d + 1];
+      const double me = mix_->GetGasParams(_numSpecies - 2, GasParams::SPECIES_MW);
+      const double ne = ns[_numSpecies - 2];
+      for (int sp = 0; sp < _numSpecies; sp++) {
+        if (sp == _numSpecies - 2) continue;
+        double m_sp = mix_->GetGasParams(sp, GasParams::SPECIES_MW);
+        double energy = 1.5 * UNIVERSALGASCONSTANT * (Te - Th);
+        energy *= 2.0 * me * m_sp / (m_sp + me) / (m_sp + me) * ne *
+                  speciesTransport[sp + SpeciesTrns::MF_FREQUENCY * _numSpecies];
+        srcTerm[_num_equation - 1] -= energy;
+      }
+    }
+  }
+};
+
 Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq) {
+  if (p.fluid == 1 && p.plasma) return new MixtureRef(p, dim, nvel, neq);
   if (p.fluid != 0) return nullptr;
   return new DryAirRef(p, dim, nvel, neq);
 }

@@ -13,7 +13,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 class OrcPhysParams(C.Structure):
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("gamma", C.c_double), ("R", C.c_double),
                 ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double), ("C1", C.c_double),
-                ("S0", C.c_double), ("Pr", C.c_double)]
+                ("S0", C.c_double), ("Pr", C.c_double), ("plasma", C.c_void_p)]
 
 
 class OrcBc(C.Structure):
@@ -30,7 +30,15 @@ def make_bc(attr, kind, type_, data=()):
 
 def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0):
     """Defaults of the reference: gamma/R src/equation_of_state.cpp:175-179; Sutherland SURVEY.md 8(d)."""
-    return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71)
+    return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None)
+
+
+def mixture_params(models, eq_system=1):
+    """fluid = user_defined: `models` is a tps_b200.PlasmaModels (same layout as the oracle's OrcPlasma); only the
+    reference-object-code flavour of the oracle (kind='ref') serves mixtures."""
+    p = OrcPhysParams(eq_system, 1, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, C.addressof(models))
+    p._models = models
+    return p
 
 
 def build(ref=False):
@@ -60,6 +68,11 @@ def load(kind="port"):
     lib.orc_destroy.argtypes = [C.c_void_p]
     lib.orc_set_bcs.argtypes = [C.c_void_p, _ip, C.c_int, C.POINTER(OrcBc), C.c_int]
     lib.orc_bc_flux.argtypes = [C.c_void_p, C.POINTER(OrcBc), C.c_int, _dp, _dp, _dp, _dp]
+    lib.orc_set_solution_view.argtypes = [C.c_void_p, C.c_void_p]
+    for nm in ("orc_pt_prim", "orc_pt_cons", "orc_pt_max_char_speed", "orc_pt_conv_flux"):
+        getattr(lib, nm).argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    lib.orc_pt_visc_flux.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+    lib.orc_pt_source.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
     lib.orc_ndofs.restype = C.c_long
     lib.orc_ndofs.argtypes = [C.c_void_p]
     lib.orc_update_primitives.argtypes = [C.c_void_p, _dp, _dp]
@@ -117,6 +130,21 @@ class Oracle:
         out = np.zeros(self.neq)
         self.lib.orc_bc_flux(self.h, C.byref(bc), int(use_bc_in_grad), np.ascontiguousarray(normal, dtype=np.float64),
                              np.ascontiguousarray(state, dtype=np.float64), np.ascontiguousarray(grad, dtype=np.float64), out)
+        return out
+
+    def set_solution_view(self, U):
+        self._sol = None if U is None else np.ascontiguousarray(U, dtype=np.float64)
+        self.lib.orc_set_solution_view(self.h, None if U is None else self._sol.ctypes.data)
+
+    # point-wise probes of this operator's physics object: arrays are [n][neq] / [n][dim][neq] point-major
+    def pt(self, what, *arrs):
+        a0 = np.ascontiguousarray(arrs[0], dtype=np.float64)
+        n = a0.shape[0]
+        shape = {"prim": (n, self.neq), "cons": (n, self.neq), "max_char_speed": (n,), "conv_flux": (n, self.dim * self.neq),
+                 "visc_flux": (n, self.dim * self.neq), "source": (n, self.neq)}[what]
+        out = np.zeros(shape)
+        args = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        getattr(self.lib, "orc_pt_" + what)(self.h, n, *args, out)
         return out
 
     def node_coords(self):

@@ -36,15 +36,69 @@ class SpaceDesc(C.Structure):
                 ("num_equation", C.c_int), ("nvel", C.c_int)]
 
 
+MAX_SPECIES, MAX_REACTIONS = 8, 34
+
+
+class PlasmaModels(C.Structure):
+    """tpsb_plasma_models: PerfectMixtureInput + constantTransportData + ChemistryInput flattened, species in the
+    reference's mixture order (electron second to last, background last)."""
+    _fields_ = [("num_species", C.c_int), ("ambipolar", C.c_int), ("two_temperature", C.c_int),
+                ("mw", C.c_double * MAX_SPECIES), ("charge", C.c_double * MAX_SPECIES),
+                ("formation_energy", C.c_double * MAX_SPECIES), ("molar_cv", C.c_double * MAX_SPECIES),
+                ("transport_model", C.c_int), ("viscosity", C.c_double), ("bulk_viscosity", C.c_double),
+                ("thermal_conductivity", C.c_double), ("electron_thermal_conductivity", C.c_double),
+                ("diffusivity", C.c_double * MAX_SPECIES), ("mt_freq", C.c_double * MAX_SPECIES),
+                ("num_reactions", C.c_int), ("min_temperature", C.c_double),
+                ("model", C.c_int * MAX_REACTIONS), ("detailed_balance", C.c_int * MAX_REACTIONS),
+                ("rate_params", (C.c_double * 3) * MAX_REACTIONS), ("reaction_energy", C.c_double * MAX_REACTIONS),
+                ("equilibrium_params", (C.c_double * 3) * MAX_REACTIONS),
+                ("reactant_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS),
+                ("product_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS)]
+
+    @classmethod
+    def from_dict(cls, d):
+        """d: species = list of dicts (mw, charge, formation_energy, molar_cv, diffusivity, mt_freq) in mixture
+        order, transport scalars, reactions = list of dicts (model, A, b, E, energy, detailed, eqA, eqB, eqE,
+        reactants, products)."""
+        pm = cls()
+        sp = d["species"]
+        pm.num_species, pm.ambipolar, pm.two_temperature = len(sp), int(d["ambipolar"]), int(d["two_temperature"])
+        for i, s_ in enumerate(sp):
+            pm.mw[i], pm.charge[i], pm.formation_energy[i] = s_["mw"], s_["charge"], s_["formation_energy"]
+            pm.molar_cv[i], pm.diffusivity[i], pm.mt_freq[i] = s_["molar_cv"], s_["diffusivity"], s_["mt_freq"]
+        pm.transport_model = 2
+        pm.viscosity, pm.bulk_viscosity = d["viscosity"], d["bulk_viscosity"]
+        pm.thermal_conductivity, pm.electron_thermal_conductivity = d["thermal_conductivity"], d["electron_thermal_conductivity"]
+        rx = d.get("reactions", [])
+        pm.num_reactions, pm.min_temperature = len(rx), d.get("min_temperature", 0.0)
+        for r, q in enumerate(rx):
+            pm.model[r], pm.detailed_balance[r], pm.reaction_energy[r] = q.get("model", 0), int(q["detailed"]), q["energy"]
+            for k, key in enumerate(("A", "b", "E")):
+                pm.rate_params[r][k] = q[key]
+            for k, key in enumerate(("eqA", "eqB", "eqE")):
+                pm.equilibrium_params[r][k] = q.get(key, 0.0)
+            for i in range(len(sp)):
+                pm.reactant_stoich[r][i], pm.product_stoich[r][i] = q["reactants"][i], q["products"][i]
+        return pm
+
+
 class Physics(C.Structure):
     """tpsb_physics; defaults are the reference's dry-air constants."""
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("specific_heat_ratio", C.c_double),
                 ("gas_constant", C.c_double), ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double),
-                ("sutherland_C1", C.c_double), ("sutherland_S0", C.c_double), ("sutherland_Pr", C.c_double)]
+                ("sutherland_C1", C.c_double), ("sutherland_S0", C.c_double), ("sutherland_Pr", C.c_double),
+                ("plasma", C.POINTER(PlasmaModels))]
 
     @classmethod
     def dry_air(cls, eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0):
-        return cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71)
+        return cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None)
+
+    @classmethod
+    def plasma_mixture(cls, models, eq_system=1):
+        """fluid = user_defined with the given PlasmaModels (kept alive on the returned object)."""
+        ph = cls(eq_system, 1, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, C.pointer(models))
+        ph._models = models
+        return ph
 
 
 class BcDesc(C.Structure):
@@ -76,8 +130,8 @@ class PartSizes(C.Structure):
 # every symbol include/tpsb200.h declares (tests check the library exports all of them)
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
-           "tpsb_get_fields", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
+           "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
+           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -114,9 +168,11 @@ def lib():
     L.tpsb_update_gradients.argtypes = [vp, vp, C.c_int]
     L.tpsb_get_fields.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
+    L.tpsb_set_solution_view.argtypes = [vp, vp]
     L.tpsb_ode_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
     L.tpsb_get_element_to_faces.argtypes = [vp, ip]
     L.tpsb_debug_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.tpsb_debug_point_eval.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.tpsb_launch_count.restype = C.c_int64
     L.tpsb_launch_count.argtypes = [vp]
     L.tpsb_set_profiling.argtypes = [vp, C.c_int]
@@ -303,7 +359,11 @@ class RhsOperator:
             arr = (BcDesc * len(bcs))(*bcs)
             bcset = BcSet(len(bcs), arr, int(use_bc_in_grad))
             self._keep.append(arr)
-        space = SpaceDesc(order, basis_type, int_rule_type, self.dim + 2, self.dim)
+        neq = self.dim + 2
+        if self.physics.fluid == 1:
+            pm = self.physics.plasma.contents
+            neq += (pm.num_species - 2 if pm.ambipolar else pm.num_species - 1) + (1 if pm.two_temperature else 0)
+        space = SpaceDesc(order, basis_type, int_rule_type, neq, self.dim)
         self.ctx = C.c_void_p()
         s = stream if stream is not None else 0
         rc = self.L.tpsb_create(C.byref(maps), C.byref(space), C.byref(self.physics),
@@ -360,6 +420,21 @@ class RhsOperator:
         up, g = C.c_void_p(), C.c_void_p()
         self._chk(self.L.tpsb_get_fields(self.ctx, C.byref(up), C.byref(g)), "tpsb_get_fields")
         return self._view(up.value, self.neq * self.N), self._view(g.value, self.dim * self.neq * self.N)
+
+    def set_solution_view(self, U):
+        """The solution grid function U_ the forcing terms read (None: the vector passed to Mult)."""
+        self._sol = U
+        self._chk(self.L.tpsb_set_solution_view(self.ctx, U.data_ptr() if U is not None else None), "tpsb_set_solution_view")
+
+    def point_eval(self, what, U, aux=None):
+        """Test hook: per-point physics of this context on device arrays U [n][neq] (aux: gradUp [n][dim*neq])."""
+        which = {"prim": 0, "max_char_speed": 1, "conv_flux": 2, "visc_flux": 3, "source": 4}[what]
+        n = U.shape[0]
+        shape = {0: (n, self.neq), 1: (n,), 2: (n, self.dim * self.neq), 3: (n, self.dim * self.neq), 4: (n, self.neq)}[which]
+        out = self.torch.zeros(shape, dtype=self.torch.float64, device=U.device)
+        self._chk(self.L.tpsb_debug_point_eval(self.ctx, which, n, U.data_ptr(), aux.data_ptr() if aux is not None else None,
+                                               out.data_ptr()), "tpsb_debug_point_eval")
+        return out
 
     def debug_buffer(self, which):
         """Test hook: device view of an internal buffer (0 face residuals, 1 face-trace blocks)."""

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "mix_physics.cuh"
 #include "physics.cuh"
 
 namespace tpsb {
@@ -14,11 +15,13 @@ constexpr int GEN_MAXDIM = 3;
 
 struct GenPhys {
   int dim, nvel, neq;
-  PhysParams dry;  // gamma, R, Sutherland, multipliers, eq_system
+  int fluid;             // 0 dry air; 1 user-defined plasma mixture (mix != NULL)
+  PhysParams dry;        // gamma, R, Sutherland, multipliers, eq_system
+  const MixParams *mix;  // device (or host, for host-side checks) pointer
 };
 
 // DryAir::ComputePressure (equation_of_state.hpp:610-617)
-__host__ __device__ __forceinline__ double gen_pressure(const GenPhys &g, const double *s) {
+__host__ __device__ __forceinline__ double dry_gen_pressure(const GenPhys &g, const double *s) {
   double den_vel2 = 0;
   for (int d = 0; d < g.nvel; d++) den_vel2 += s[d + 1] * s[d + 1];
   den_vel2 /= s[0];
@@ -26,7 +29,7 @@ __host__ __device__ __forceinline__ double gen_pressure(const GenPhys &g, const 
 }
 
 // DryAir::GetPrimitivesFromConservatives (equation_of_state.cpp:321-335)
-__host__ __device__ __forceinline__ void gen_prim(const GenPhys &g, const double *s, double *up) {
+__host__ __device__ __forceinline__ void dry_gen_prim(const GenPhys &g, const double *s, double *up) {
   double den_vel2 = 0;
   for (int d = 0; d < g.nvel; d++) den_vel2 += s[d + 1] * s[d + 1];
   den_vel2 /= s[0];
@@ -37,7 +40,7 @@ __host__ __device__ __forceinline__ void gen_prim(const GenPhys &g, const double
 }
 
 // DryAir::ComputeMaxCharSpeed (equation_of_state.cpp:279-294)
-__host__ __device__ __forceinline__ double gen_max_char_speed(const GenPhys &g, const double *s) {
+__host__ __device__ __forceinline__ double dry_gen_max_char_speed(const GenPhys &g, const double *s) {
   const double den = s[0];
   double den_vel2 = 0;
   for (int d = 0; d < g.nvel; d++) den_vel2 += s[d + 1] * s[d + 1];
@@ -47,8 +50,8 @@ __host__ __device__ __forceinline__ double gen_max_char_speed(const GenPhys &g, 
 }
 
 // Fluxes::ComputeConvectiveFluxes (fluxes.cpp:135-170): f[eq + d*neq]
-__host__ __device__ __forceinline__ void gen_conv_flux(const GenPhys &g, const double *s, double *f) {
-  const double pres = gen_pressure(g, s);
+__host__ __device__ __forceinline__ void dry_gen_conv_flux(const GenPhys &g, const double *s, double *f) {
+  const double pres = dry_gen_pressure(g, s);
   const int neq = g.neq;
   for (int d = 0; d < g.dim; d++) {
     f[0 + d * neq] = s[d + 1];
@@ -65,11 +68,11 @@ __host__ __device__ __forceinline__ void gen_conv_flux(const GenPhys &g, const d
 // `dim` are zero, so sums keep the reference's operation order): nvcc 12.9 -O3 produced wrong stores for the
 // run-time-indexed form once inlined into gen_resid_kernel (caught by the parity test; the stand-alone
 // function was correct, tools/ubench/gen_visc_check.cu).
-__host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double *f) {
+__host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double *f) {
   const int neq = g.neq, dim = g.dim;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (g.dry.eq_system == 0) return;
-  const double pr = gen_pressure(g, s);
+  const double pr = dry_gen_pressure(g, s);
   const double temp = pr / g.dry.R / s[0];
   const double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
   double bulk = g.dry.bulk_visc_mult * visc;
@@ -108,6 +111,21 @@ __host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const d
     }
   }
 }
+
+// ---- dispatch on the working fluid (the reference's virtual GasMixture / TransportProperties calls) ----
+__host__ __device__ __forceinline__ void gen_prim(const GenPhys &g, const double *s, double *up) {
+  if (g.fluid) mix_prim(*g.mix, s, up); else dry_gen_prim(g, s, up);
+}
+__host__ __device__ __forceinline__ double gen_max_char_speed(const GenPhys &g, const double *s) {
+  return g.fluid ? mix_max_char_speed(*g.mix, s) : dry_gen_max_char_speed(g, s);
+}
+__host__ __device__ __forceinline__ void gen_conv_flux(const GenPhys &g, const double *s, double *f) {
+  if (g.fluid) mix_conv_flux(*g.mix, s, f); else dry_gen_conv_flux(g, s, f);
+}
+__host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double *f) {
+  if (g.fluid) mix_visc_flux(*g.mix, s, gr, f); else dry_gen_visc_flux(g, s, gr, f);
+}
+__host__ __device__ __forceinline__ int gen_num_active_species(const GenPhys &g) { return g.fluid ? g.mix->numActive : 0; }
 
 // RiemannSolverTPS::Eval_LF (riemann_solver.cpp:89-114)
 __host__ __device__ __forceinline__ void gen_riemann_lf(const GenPhys &g, const double *s1, const double *s2, const double *nor,

@@ -25,7 +25,7 @@ int main(int argc, char **argv) {
   if (nf < 0) return 2;
   tpsb_mesh_maps maps = {3, NE, 0, xyz.data(), nf, f1.data(), f2.data(), i1.data(), i2.data(), nullptr};
   tpsb_space_desc space = {3, 0, 0, 5, 3};
-  tpsb_physics phys = {TPSB_NS, TPSB_DRY_AIR, 1.4, 287.058, 1420.0, 0.0, 1.458e-6, 110.4, 0.71};
+  tpsb_physics phys = {TPSB_NS, TPSB_DRY_AIR, 1.4, 287.058, 1420.0, 0.0, 1.458e-6, 110.4, 0.71, nullptr};
   try {
     tpsb_host::RHSoperator rhsOperator(maps, space, phys);
     const int64_t N = tpsb_num_dofs(rhsOperator.context());

@@ -20,7 +20,7 @@
 namespace tpsb {
 
 struct GenArgs {
-  int dim, np, dof, nqv, nqf, nfe, nv, neq, nvel;
+  int dim, np, dof, nqv, nqf, nfe, nv, neq, nvel, eq_system;
   int NE;
   long long N;
   int me_diag;
@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   double *sQ = sF + dof * nc;       // [nqmax][nc]
   double *sZ = sQ + nqmax * nc;     // [dof][neq]
   __shared__ unsigned long long sMaxBits;
+  const int nact = gen_num_active_species(a.phys);
   const long long N = a.N;
   const double *vx = a.vx + static_cast<long long>(e) * a.nv * dim;
   if (threadIdx.x == 0) sMaxBits = 0ull;
@@ -227,9 +228,11 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   for (int k = threadIdx.x; k < dof; k += blockDim.x) {
     double s[GEN_MAXEQ], gr[GEN_MAXEQ * GEN_MAXDIM], fc[GEN_MAXEQ * GEN_MAXDIM], fv[GEN_MAXEQ * GEN_MAXDIM];
     for (int eq = 0; eq < neq; eq++) s[eq] = sU[eq * dof + k];
+    // species densities are clamped >= 0 at the nodes of GetFlux (rhs_operator.cpp:512-517)
+    for (int sp = 0; sp < nact; sp++) s[a.nvel + 2 + sp] = fmax(s[a.nvel + 2 + sp], 0.0);
     for (int c = 0; c < nc; c++) gr[c] = sG[c * dof + k];
     gen_conv_flux(a.phys, s, fc);
-    if (a.phys.dry.eq_system != 0) {
+    if (a.eq_system != 0) {
       gen_visc_flux(a.phys, s, gr, fv);
       for (int c = 0; c < nc; c++) fc[c] -= fv[c];
     }
@@ -295,6 +298,10 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         uo[eq] = x;
         un[eq] = y;
       }
+      for (int sp = 0; sp < nact; sp++) {  // face_integrator.cpp:297-301
+        uo[a.nvel + 2 + sp] = fmax(uo[a.nvel + 2 + sp], 0.0);
+        un[a.nvel + 2 + sp] = fmax(un[a.nvel + 2 + sp], 0.0);
+      }
       for (int c = 0; c < nc; c++) {
         double x = 0, y = 0;
         const double *src = a.gradUp + static_cast<long long>(eo) * dof + c * N;
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       const double *u1 = first ? uo : un, *u2 = first ? un : uo, *g1 = first ? go : gn, *g2 = first ? gn : go;
       double fx[GEN_MAXEQ];
       gen_riemann_lf(a.phys, u1, u2, nor, fx);
-      if (a.phys.dry.eq_system != 0) {
+      if (a.eq_system != 0) {
         double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM];
         gen_visc_flux(a.phys, u1, g1, f1);
         gen_visc_flux(a.phys, u2, g2, f2);
@@ -332,6 +339,49 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     __syncthreads();
   }
   gen_apply_minv(a, e, sZ, neq, a.y, N);
+}
+
+// SourceTerm::updateTerms (source_term.cpp:62-255): node-wise plasma sources added to y AFTER Me^-1
+// (rhs_operator.cpp:451-461).  Usol = the solution grid function U_ the reference reads the conserved state from
+// (parity trap 1: in Runge-Kutta stages it differs from the stage vector Up / gradUp were computed from).
+__global__ void gen_source_kernel(GenArgs a, const double *Usol) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  double Un[GEN_MAXEQ], upn[GEN_MAXEQ], gr[GEN_MAXEQ * GEN_MAXDIM], src[GEN_MAXEQ];
+  for (int eq = 0; eq < a.neq; eq++) {
+    Un[eq] = Usol[n + eq * a.N];
+    upn[eq] = a.Up[n + eq * a.N];
+    for (int d = 0; d < a.dim; d++) gr[eq + d * a.neq] = a.gradUp[n + eq * a.N + d * a.neq * a.N];
+  }
+  mix_source(*a.phys.mix, Un, upn, gr, src);
+  for (int eq = 0; eq < a.neq; eq++) a.y[n + eq * a.N] += src[eq];
+}
+
+// test hook: the per-point physics on arrays of points (point-major: U[i*neq + eq], gradUp[i*neq*dim + eq + d*neq])
+__global__ void gen_point_eval_kernel(GenArgs a, int which, int n, const double *U, const double *aux, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int neq = a.neq, nc = a.neq * a.dim;
+  double s[GEN_MAXEQ], up[GEN_MAXEQ], gr[GEN_MAXEQ * GEN_MAXDIM], f[GEN_MAXEQ * GEN_MAXDIM];
+  for (int eq = 0; eq < neq; eq++) s[eq] = U[i * neq + eq];
+  if (which == 0) {
+    gen_prim(a.phys, s, up);
+    for (int eq = 0; eq < neq; eq++) out[i * neq + eq] = up[eq];
+  } else if (which == 1) {
+    out[i] = gen_max_char_speed(a.phys, s);
+  } else if (which == 2) {
+    gen_conv_flux(a.phys, s, f);
+    for (int c = 0; c < nc; c++) out[i * nc + c] = f[c];
+  } else if (which == 3) {
+    for (int c = 0; c < nc; c++) gr[c] = aux[i * nc + c];
+    gen_visc_flux(a.phys, s, gr, f);
+    for (int c = 0; c < nc; c++) out[i * nc + c] = f[c];
+  } else if (which == 4 && a.phys.fluid) {
+    for (int c = 0; c < nc; c++) gr[c] = aux[i * nc + c];
+    gen_prim(a.phys, s, up);
+    mix_source(*a.phys.mix, s, up, gr, f);
+    for (int eq = 0; eq < neq; eq++) out[i * neq + eq] = f[eq];
+  }
 }
 
 inline size_t gen_grad_smem(const GenArgs &a) {

@@ -48,6 +48,7 @@ struct tpsb_ctx {
   // generic tensor-product path (rhs_generic.cuh): 2-D, Gauss-Lobatto, ...
   bool generic = false;
   int dim = 3, neq = NEQ;
+  const double *sol_view = nullptr;  // U_ of the reference's forcing terms (tpsb_set_solution_view)
   GenArgs gen;
   std::vector<void *> gen_allocs;
   // boundary faces (BCintegrator)
@@ -246,7 +247,7 @@ bool g_spd_inverse(std::vector<double> &A, int n) {
 }
 
 // Everything the generic kernels need; returns an error string (empty on success).
-std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_space_desc *space) {
+std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys) {
   const int dim = maps->dim, p = space->order, np = p + 1, NE = c->NE, NF = maps->num_faces;
   const int nv = 1 << dim, nfe = 2 * dim, nori = dim == 3 ? 8 : 2;
   int dof = 1;
@@ -359,6 +360,40 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   g.dim = dim, g.np = np, g.dof = dof, g.nqv = nqv, g.nqf = nqf, g.nfe = nfe, g.nv = nv;
   g.neq = space->num_equation, g.nvel = space->nvel, g.NE = NE, g.N = static_cast<long long>(NE) * dof, g.me_diag = diag ? 1 : 0;
   g.phys.dim = dim, g.phys.nvel = space->nvel, g.phys.neq = space->num_equation, g.phys.dry = c->phys;
+  g.eq_system = phys->eq_system;
+  g.phys.fluid = 0, g.phys.mix = nullptr;
+  std::vector<MixParams> mixv;
+  if (phys->fluid == TPSB_USER_DEFINED) {
+    const tpsb_plasma_models &pm = *phys->plasma;
+    MixParams m;
+    memset(&m, 0, sizeof(m));
+    m.numSpecies = pm.num_species, m.ambipolar = pm.ambipolar ? 1 : 0, m.twoTemp = pm.two_temperature ? 1 : 0;
+    m.numActive = m.ambipolar ? m.numSpecies - 2 : m.numSpecies - 1;                    // equation_of_state.hpp:131
+    m.iBackground = m.numSpecies - 1, m.iElectron = m.numSpecies - 2;                   // :137-146
+    m.dim = dim, m.nvel = space->nvel, m.neq = space->num_equation, m.iTh = space->nvel + 1, m.iTe = space->num_equation - 1;
+    m.eq_system = phys->eq_system;
+    for (int sp = 0; sp < m.numSpecies; sp++) {
+      m.mw[sp] = pm.mw[sp], m.charge[sp] = pm.charge[sp], m.formE[sp] = pm.formation_energy[sp];
+      m.molarCV[sp] = pm.molar_cv[sp] * MIX_RU;                                         // equation_of_state.cpp:568-571
+      m.molarCP[sp] = m.molarCV[sp] + MIX_RU;
+      m.diff[sp] = pm.diffusivity[sp], m.mtFreq[sp] = pm.mt_freq[sp];
+    }
+    m.visc = pm.viscosity, m.bulk = pm.bulk_viscosity, m.kh = pm.thermal_conductivity, m.ke = pm.electron_thermal_conductivity;
+    m.trElectron = m.iElectron, m.chElectron = m.iElectron;
+    m.numReactions = pm.num_reactions, m.minTemp = pm.min_temperature;
+    for (int r = 0; r < pm.num_reactions; r++) {
+      m.rxModel[r] = pm.model[r], m.detailed[r] = pm.detailed_balance[r] ? 1 : 0;
+      m.rxA[r] = pm.rate_params[r][0], m.rxB[r] = pm.rate_params[r][1], m.rxE[r] = pm.rate_params[r][2];
+      m.rxEnergy[r] = pm.reaction_energy[r];
+      m.eqA[r] = pm.equilibrium_params[r][0], m.eqB[r] = pm.equilibrium_params[r][1], m.eqE[r] = pm.equilibrium_params[r][2];
+      for (int sp = 0; sp < m.numSpecies; sp++) {
+        m.reactS[sp + r * m.numSpecies] = pm.reactant_stoich[r][sp];
+        m.prodS[sp + r * m.numSpecies] = pm.product_stoich[r][sp];
+      }
+    }
+    mixv.push_back(m);
+    g.phys.fluid = 1;
+  }
   std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE) * nv * dim);
   std::vector<int> fe1(maps->face_el1, maps->face_el1 + NF), fe2(maps->face_el2, maps->face_el2 + NF),
       fi1(maps->face_inf1, maps->face_inf1 + NF), fi2(maps->face_inf2, maps->face_inf2 + NF);
@@ -378,6 +413,7 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   if (ce == cudaSuccess) ce = g_upload(c, &g.f_inf1, fi1);
   if (ce == cudaSuccess) ce = g_upload(c, &g.f_inf2, fi2);
   if (ce == cudaSuccess) ce = g_upload(c, &g.me_inv, me);
+  if (ce == cudaSuccess && !mixv.empty()) ce = g_upload(c, &g.phys.mix, mixv);
   const size_t nb = static_cast<size_t>(g.N) * sizeof(double);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * g.neq);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUp, nb * g.neq * dim);
@@ -417,10 +453,25 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (space->basis_type < 0 || space->basis_type > 1 || space->int_rule_type < 0 || space->int_rule_type > 1)
     return fail(ctx, TPSB_EINVAL, "basisType / integrationRule must be 0 (Gauss-Legendre) or 1 (Gauss-Lobatto)");
   if (space->order < 1 || space->order > 3) return fail(ctx, TPSB_ENOTIMPL, "order must be 1..3");
-  if (phys->fluid != TPSB_DRY_AIR || space->nvel != maps->dim || space->num_equation != space->nvel + 2)
-    return fail(ctx, TPSB_ENOTIMPL, "only dry air (num_equation = dim + 2, nvel = dim) is built");
+  if (space->nvel != maps->dim) return fail(ctx, TPSB_ENOTIMPL, "axisymmetric runs (nvel = 3 in 2-D) are not built yet");
+  if (phys->fluid == TPSB_DRY_AIR) {
+    if (space->num_equation != space->nvel + 2) return fail(ctx, TPSB_EINVAL, "dry air has num_equation = nvel + 2");
+  } else if (phys->fluid == TPSB_USER_DEFINED) {
+    const tpsb_plasma_models *pm = phys->plasma;
+    if (!pm) return fail(ctx, TPSB_EINVAL, "fluid = user_defined needs tpsb_physics.plasma");
+    if (pm->num_species < 3 || pm->num_species > TPSB_MAX_SPECIES) return fail(ctx, TPSB_EINVAL, "num_species must be 3..%d (electron and background included)", TPSB_MAX_SPECIES);
+    if (pm->transport_model != 2) return fail(ctx, TPSB_ENOTIMPL, "only transport_model = constant is built for mixtures");
+    if (pm->num_reactions < 0 || pm->num_reactions > TPSB_MAX_REACTIONS) return fail(ctx, TPSB_EINVAL, "too many reactions");
+    for (int r = 0; r < pm->num_reactions; r++)
+      if (pm->model[r] != 0 && pm->model[r] != 1) return fail(ctx, TPSB_ENOTIMPL, "reaction model %d not built (Arrhenius / Hoffert-Lien only)", pm->model[r]);
+    const int nact = pm->ambipolar ? pm->num_species - 2 : pm->num_species - 1;
+    if (space->num_equation != space->nvel + 2 + nact + (pm->two_temperature ? 1 : 0) || space->num_equation > GEN_MAXEQ)
+      return fail(ctx, TPSB_EINVAL, "num_equation does not match the mixture (nvel + 2 + active species [+ 1 electron energy])");
+  } else {
+    return fail(ctx, TPSB_ENOTIMPL, "working fluid %d not built", phys->fluid);
+  }
   // 3-D Gauss-Legendre dry air runs the specialised kernels; everything else the generic tensor-product path
-  bool want_generic = maps->dim != 3 || space->basis_type != 0 || space->int_rule_type != 0;
+  bool want_generic = maps->dim != 3 || space->basis_type != 0 || space->int_rule_type != 0 || phys->fluid != TPSB_DRY_AIR;
   if (const char *pth = getenv("TPSB_PATH")) want_generic = want_generic || strcmp(pth, "generic") == 0;
   if (want_generic) {
     if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
@@ -495,7 +546,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     c->nd = 1;
     for (int d = 0; d < maps->dim; d++) c->nd *= c->np;
     c->N = static_cast<long long>(c->NE) * c->nd;
-    const std::string err = create_generic(c, maps, space);
+    const std::string err = create_generic(c, maps, space, phys);
     if (!err.empty()) {
       tpsb_destroy(c);
       return fail(nullptr, TPSB_EINVAL, "%s", err.c_str());
@@ -1150,6 +1201,10 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     gen_resid_kernel<<<g.NE, 128, smem, c->stream>>>(g);
   }
+  if (g.phys.fluid) {  // forcing terms are added after Me^-1 (rhs_operator.cpp:451-461)
+    ProfScope ps(c, K_RESID);
+    gen_source_kernel<<<static_cast<unsigned>((g.N + 127) / 128), 128, 0, c->stream>>>(g, c->sol_view ? c->sol_view : d_x);
+  }
   CU(cudaGetLastError());
   return TPSB_OK;
 }
@@ -1258,6 +1313,22 @@ int tpsb_debug_buffer(tpsb_ctx *ctx, int which, double **d_ptr, int64_t *count) 
   return TPSB_OK;
 }
 
+int tpsb_debug_point_eval(tpsb_ctx *ctx, int which, int n, const double *d_U, const double *d_aux, double *d_out) {
+  if (!ctx || !d_U || !d_out || n < 0 || which < 0 || which > 4) return TPSB_EINVAL;
+  if (!ctx->generic) return fail(ctx, TPSB_ENOTIMPL, "point evaluation is a test hook of the generic path");
+  CU(cudaSetDevice(ctx->device));
+  gen_point_eval_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->gen, which, n, d_U, d_aux, d_out);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U) {
+  if (!ctx) return TPSB_EINVAL;
+  ctx->sol_view = d_U;
+  return TPSB_OK;
+}
+
 int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out) {
   if (!ctx || !out) return TPSB_EINVAL;
   CU(cudaSetDevice(ctx->device));
@@ -1284,6 +1355,8 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
   const unsigned nb = static_cast<unsigned>((n + 255) / 256);
   double *k = ctx->d_k, *y = ctx->d_yv, *z = ctx->d_z, *x = d_U;
   cudaStream_t st = ctx->stream;
+  const double *saved_view = ctx->sol_view;
+  ctx->sol_view = d_U;  // the forcing terms read the solution vector, not the stage vector (parity trap 1)
 #define AXPY(X, K, A, Y, B, Z, ACC)                                    do {                                                                   axpy2_kernel<<<nb, 256, 0, st>>>(n, X, K, A, Y, B, Z, ACC);          ctx->launches++;                                                   } while (0)
   for (int s = 0; s < nsteps; s++) {
     if (scheme == 1) {  // x += dt f(x)
@@ -1323,6 +1396,7 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
     }
   }
 #undef AXPY
+  ctx->sol_view = saved_view;
   CU(cudaGetLastError());
   return TPSB_OK;
 }
