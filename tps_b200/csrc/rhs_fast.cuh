@@ -222,6 +222,233 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core contraction (DMMA, SASS DMMA.884): D(8x8) = A(8x4) B(4x8).  Fragments (PTX ISA, m8n8k4 .f64):
+// A[row = lane/4][k = lane%4], B[k = lane%4][col = lane/4], D[row = lane/4][col = 2 (lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+// grad_trace_mma_kernel (p = 3): same result as grad_trace_kernel<4,...>, but every contraction along an element
+// axis -- the collocation derivative D (4 rows) AND the two end-point extrapolations lb (2 rows) -- is one DMMA
+// with A = [D; lb(0); lb(1); 0; 0] and B = 8 lines of 4 nodal values.  Why: the one-thread-per-node form reads one
+// shared-memory double per DFMA and ncu shows it bound by shared-memory wavefronts (l1tex data pipe 93 %, FP64
+// pipe 17 %, profiles/r1h_*); a DMMA reads one double per lane for 8 FMAs and the B fragments below are
+// bank-conflict free, so the shared-memory traffic of the contractions drops ~6x at the same FP64-pipe cost
+// (B200: DMMA and DFMA share one pipe, 37 TF each, tools/ubench/fp64_pipes.cu).
+//   node p(n) = n + 4 (n / 16): planes of 16 nodes padded to 20 doubles -> the three B-fragment patterns
+//   (x: 32 consecutive nodes, y: 4x4 transposed inside a plane, z: stride one plane) hit 16 distinct banks per
+//   half warp.
+// Two warps per element (lane = node for the per-node phases), EPB elements per CTA.
+__device__ __forceinline__ int pad_node(int n) { return n + 4 * (n >> 4); }
+
+template <int EPB, int MINB>
+__global__ void __launch_bounds__(64 * EPB, MINB)
+    grad_trace_mma_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list) {
+  constexpr int NP = 4, ND = 64, NF2 = 16, PS = 80;  // PS: padded doubles per field
+  __shared__ __align__(16) double sF[EPB][2 * NEQ * PS];    // U (0-4), Up (5-9); later the viscous traces [6][5][16]
+  __shared__ __align__(16) double sDr[EPB][NEQ * DIM * PS];  // reference derivatives of Up; later the 13 viscous fields
+  __shared__ __align__(16) double sJ[EPB][6 * NEQ * NF2];    // own Up traces -> jumps 1/2 (Up_nbr - Up_own)
+  __shared__ __align__(16) double sTU[EPB][6 * NEQ * NF2];   // traces of the conserved state
+  __shared__ double sGeo[EPB][GEO];
+  __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP];
+  __shared__ int sNbr[EPB][6], sCode[EPB][6], sFp[6];
+  const int le = threadIdx.x / ND, n = threadIdx.x % ND;
+  const int lane = threadIdx.x & 31, half = (threadIdx.x >> 5) & 1;
+  const int slot = blockIdx.x * EPB + le;
+  const bool active = slot < elem_count;
+  const int e = active ? (elem_list ? elem_list[elem_begin + slot] : elem_begin + slot) : 0;
+  const long long N = a.N;
+  if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
+  const long long o = static_cast<long long>(e) * ND + n;
+  const int pn = pad_node(n);
+  if (active) {
+#pragma unroll
+    for (int f = 0; f < NEQ; f++) {
+      sF[le][f * PS + pn] = a.U[o + f * N];
+      sF[le][(NEQ + f) * PS + pn] = a.Up[o + f * N];
+    }
+    for (int t = n; t < GEO; t += ND) sGeo[le][t] = a.geo[static_cast<long long>(e) * GEO + t];
+    for (int t = n; t < 6; t += ND) {
+      sNbr[le][t] = a.nbr_elem[e * 6 + t];
+      sCode[le][t] = a.nbr_code[e * 6 + t];
+    }
+  }
+  __syncthreads();
+  // A fragment: rows 0-3 = D, row 4 = lb(xi = 0), row 5 = lb(xi = 1)
+  const int fr = lane >> 2, fk = lane & 3;
+  const double afrag = fr < NP ? sD[fr][fk] : (fr < NP + 2 ? sLb[fr - NP][fk] : 0.0);
+  // per-axis fragment addressing for this lane.  Line L (0..15) of axis d: nodes base_d(L) + m stride_d.
+  //   B fragment : m = lane%4, L = 8 half + lane/4
+  //   D fragment : row = lane/4, lines L0 = 8 half + 2 (lane%4), L0 + 1
+  int bOff[DIM], dOff0[DIM], dOff1[DIM], tOff0[DIM], tOff1[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    const int str = d == 0 ? 1 : (d == 1 ? NP : NP * NP);
+    auto base = [d](int L) { return d == 0 ? 4 * L : (d == 1 ? (L & 3) + 16 * (L >> 2) : L); };
+    bOff[d] = pad_node(base(8 * half + fr) + fk * str);
+    const int L0 = 8 * half + 2 * fk;
+    dOff0[d] = pad_node(base(L0) + (fr & 3) * str);
+    dOff1[d] = pad_node(base(L0 + 1) + (fr & 3) * str);
+    // face node of line L on the -/+ face of axis d (rows 4 / 5)
+    const FacePar fp = decode_face(sFp[(fr & 1) ? kFacePlus[d] : kFaceMinus[d]]);
+    auto abof = [&](int L) {
+      const int nb = base(L), i = nb & 3, j = (nb >> 2) & 3, k = nb >> 4;
+      const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k);
+      return (fp.ss ? ia : NP - 1 - ia) + NP * (fp.st ? ib : NP - 1 - ib);
+    };
+    const int lf = (fr & 1) ? kFacePlus[d] : kFaceMinus[d];
+    tOff0[d] = lf * (NEQ * NF2) + abof(L0);
+    tOff1[d] = lf * (NEQ * NF2) + abof(L0 + 1);
+  }
+  if (active) {
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+#pragma unroll
+      for (int f = 0; f < 2 * NEQ; f++) {
+        double d0, d1;
+        dmma884(d0, d1, afrag, sF[le][f * PS + bOff[d]]);
+        if (f >= NEQ && fr < NP) {
+          sDr[le][((f - NEQ) * DIM + d) * PS + dOff0[d]] = d0;
+          sDr[le][((f - NEQ) * DIM + d) * PS + dOff1[d]] = d1;
+        }
+        if (fr == NP || fr == NP + 1) {
+          double *dst = f < NEQ ? &sTU[le][f * NF2] : &sJ[le][(f - NEQ) * NF2];
+          dst[tOff0[d]] = d0;
+          dst[tOff1[d]] = d1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+    // jumps at the face nodes of all six faces: task = (face, face node)
+    for (int t = n; t < 6 * NF2; t += ND) {
+      const int lf = t / NF2, ab = t % NF2, fa = ab % NP, fb = ab / NP;
+      double pT[NEQ];
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) pT[f] = sJ[le][(lf * NEQ + f) * NF2 + ab];
+      const int nbr = sNbr[le][lf];
+      if (nbr < 0) {  // boundary face: Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
+        if (a.bct.use_bc_in_grad && nbr <= -2) {
+          double pbc[NEQ];
+          dry_bc_prim_for_gradient(a.bct.bc[-2 - nbr], pT, pbc);
+#pragma unroll
+          for (int f = 0; f < NEQ; f++) sJ[le][(lf * NEQ + f) * NF2 + ab] = 0.5 * (pbc[f] - pT[f]);
+        } else {
+#pragma unroll
+          for (int f = 0; f < NEQ; f++) sJ[le][(lf * NEQ + f) * NF2 + ab] = 0.0;
+        }
+        continue;
+      }
+      const int code = sCode[le][lf];
+      const FacePar fq = decode_face(sFp[code & 7]);
+      int a2, b2;
+      apply_perm<NP>(code >> 3, fa, fb, a2, b2);
+      const int q0 = face_node_base<NP>(fq, a2, b2), qs = axis_stride<NP>(fq.an);
+      const bool local = nbr < a.NE;
+      const double *src = local ? a.Up + static_cast<long long>(nbr) * ND + q0
+                                : a.UpHalo + static_cast<long long>(nbr - a.NE) * NEQ * ND + q0;
+      const long long fstride = local ? N : ND;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) {
+        const double oth = trace_line<NP>(src + f * fstride, qs, sLb[fq.side], a.vec_ok != 0);
+        sJ[le][(lf * NEQ + f) * NF2 + ab] = 0.5 * (oth - pT[f]);
+      }
+    }
+  }
+  __syncthreads();
+  const int i = n % NP, j = (n / NP) % NP, k = n / (NP * NP);
+  if (active) {
+    double rg[NEQ][DIM];
+#pragma unroll
+    for (int f = 0; f < NEQ; f++)
+#pragma unroll
+      for (int r = 0; r < DIM; r++) rg[f][r] = sDr[le][(f * DIM + r) * PS + pn];
+    // lift of the face jumps in reference space (see grad_trace_kernel)
+    const int idx[3] = {i, j, k};
+#pragma unroll
+    for (int r = 0; r < DIM; r++) {
+      const int c = idx[r];
+      const FacePar fm = decode_face(sFp[kFaceMinus[r]]), fpl = decode_face(sFp[kFacePlus[r]]);
+      const int iam = pick3(fm.as, i, j, k), ibm = pick3(fm.at, i, j, k);
+      const int abm = (fm.ss ? iam : NP - 1 - iam) + NP * (fm.st ? ibm : NP - 1 - ibm);
+      const int iap = pick3(fpl.as, i, j, k), ibp = pick3(fpl.at, i, j, k);
+      const int abp = (fpl.ss ? iap : NP - 1 - iap) + NP * (fpl.st ? ibp : NP - 1 - ibp);
+      const double iw = 1.0 / sWn[c];
+      const double cm = sLb[0][c] * iw, cp = sLb[1][c] * iw;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++)
+        rg[f][r] += cp * sJ[le][(kFacePlus[r] * NEQ + f) * NF2 + abp] - cm * sJ[le][(kFaceMinus[r] * NEQ + f) * NF2 + abm];
+    }
+    const double *A = sGeo[le];
+    const double idet = sGeo[le][10];
+    double g[NEQ][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const double a0 = A[0 + 3 * d] * idet, a1 = A[1 + 3 * d] * idet, a2 = A[2 + 3 * d] * idet;
+#pragma unroll
+      for (int f = 0; f < NEQ; f++) {
+        g[f][d] = rg[f][0] * a0 + rg[f][1] * a1 + rg[f][2] * a2;
+        a.gradUp[o + (f + d * NEQ) * N] = g[f][d];
+      }
+    }
+    double sym[DIM][DIM];
+#pragma unroll
+    for (int p = 0; p < DIM; p++)
+#pragma unroll
+      for (int q = 0; q < DIM; q++) sym[p][q] = g[1 + p][q] + g[1 + q][p];
+    // thread n only ever touches column pn of sDr, so the viscous fields can overwrite it in place
+    double *sV = sDr[le];
+#pragma unroll
+    for (int r = 0; r < DIM; r++) {
+      const double n0 = A[r + 0], n1 = A[r + 3], n2 = A[r + 6];
+#pragma unroll
+      for (int p = 0; p < DIM; p++) sV[(r * 4 + p) * PS + pn] = sym[p][0] * n0 + sym[p][1] * n1 + sym[p][2] * n2;
+      sV[(r * 4 + 3) * PS + pn] = g[4][0] * n0 + g[4][1] * n1 + g[4][2] * n2;
+    }
+    sV[12 * PS + pn] = g[1][0] + g[2][1] + g[3][2];
+  }
+  __syncthreads();
+  if (active) {
+    // traces of the normal-contracted viscous fields: axis d carries fields 4 d .. 4 d + 3 and div u (12)
+    const double *sV = sDr[le];
+    double *sTV = sF[le];  // U / Up are dead: [6][5][16]
+    const double sg = (fr & 1) ? 1.0 : -1.0;  // outward normal of the -/+ face = -/+ A[d,:]
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+#pragma unroll
+      for (int v = 0; v < 5; v++) {
+        double d0, d1;
+        dmma884(d0, d1, afrag, sV[(v < 4 ? 4 * d + v : 12) * PS + bOff[d]]);
+        if (fr == NP || fr == NP + 1) {
+          const double s = v < 4 ? sg : 1.0;
+          sTV[v * NF2 + tOff0[d]] = s * d0;
+          sTV[v * NF2 + tOff1[d]] = s * d1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+    // one contiguous 7.5 KB block per element: [face][U traces 0-4 | viscous traces 5-9][face node]
+    double2 *dst = reinterpret_cast<double2 *>(a.tr + static_cast<long long>(e) * 6 * (NTF * NF2));
+    const double2 *su = reinterpret_cast<const double2 *>(sTU[le]), *sv = reinterpret_cast<const double2 *>(sF[le]);
+    constexpr int HB = NEQ * NF2 / 2;  // double2 per (face, U | viscous) half block
+#pragma unroll
+    for (int t = n; t < 6 * HB; t += ND) {
+      const int lf = t / HB;
+      dst[t + HB * lf] = su[t];
+      dst[t + HB * lf + HB] = sv[t];
+    }
+  }
+}
+
 // gather the trace blocks of the shared faces into the send buffer (one block per shared face, in the
 // order the receiver lists its shared faces with this peer)
 __global__ void pack_blocks_kernel(int nblk, int blk_doubles, const int *src_blk, const double *tr, double *dst) {

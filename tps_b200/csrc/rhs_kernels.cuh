@@ -121,7 +121,7 @@ template <int NP, int EPB, int MINB>
 __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list);
 template <int NP, int FPB, int NT, bool BDR>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
-template <int NP, int EPB, int MINB>
+template <int NP, int EPB, int MINB, bool AFF>
 __global__ void elem_resid_kernel(KernelArgs a);
 
 // y = x + a*k ; z = x + b*k  etc. for the ODE stages

@@ -486,7 +486,9 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 
 // ------------------------------------------------------------------------------------------------
 // elem_resid_kernel: EPB elements per CTA, one thread per node.
-template <int NP, int EPB, int MINB>
+// AFF: every element is a parallelepiped (fast path): adj(J) and det come from the 12-double table a.geo
+// instead of being rebuilt per node from the 8 vertices (~250 flops per node saved).
+template <int NP, int EPB, int MINB, bool AFF = false>
 __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(KernelArgs a) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
@@ -506,7 +508,11 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
   if (threadIdx.x < 6) sFp[threadIdx.x] = c_T.face_par[threadIdx.x];
   if (threadIdx.x == 0) sMaxBits = 0ull;
   if (active) {
-    for (int t = n; t < 24; t += ND) sVx[le][t] = a.vx[static_cast<long long>(e) * 24 + t];
+    if constexpr (AFF) {
+      for (int t = n; t < 12; t += ND) sVx[le][t] = a.geo[static_cast<long long>(e) * 12 + t];
+    } else {
+      for (int t = n; t < 24; t += ND) sVx[le][t] = a.vx[static_cast<long long>(e) * 24 + t];
+    }
     for (int t = n; t < 6; t += ND) {
       sFace[le][t] = a.el_face[e * 6 + t];
       sFcode[le][t] = a.el_face_code[e * 6 + t];
@@ -550,10 +556,17 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
         gT[d] = a.gradUp[o + (4 + d * NEQ) * N];
       }
     }
-    double J[9], A[9];
-    hex_jacobian(sVx[le], sXn[i], sXn[j], sXn[k], J);
-    det = det3(J);
-    adj3(J, A);
+    double A[9];
+    if constexpr (AFF) {
+#pragma unroll
+      for (int t = 0; t < 9; t++) A[t] = sVx[le][t];
+      det = sVx[le][9];
+    } else {
+      double J[9];
+      hex_jacobian(sVx[le], sXn[i], sXn[j], sXn[k], J);
+      det = det3(J);
+      adj3(J, A);
+    }
     wnode = sWn[i] * sWn[j] * sWn[k];
     // G[eq][r] = w_k sum_d adjJ(r,d) (F_c - F_v)[eq][d]: the flux of GetFlux (rhs_operator.cpp:532-540)
     // contracted with row r of adj(J) (DomainIntegrator, domain_integrator.cpp:71-97)

@@ -931,7 +931,10 @@ static void bdr_faces(tpsb_ctx *c, const KernelArgs &a) {
 template <int NP, int EPB, int MINB = 1>
 static void launch_resid(tpsb_ctx *c, const KernelArgs &a) {
   ProfScope ps(c, K_RESID);
-  elem_resid_kernel<NP, EPB, MINB><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+  if (c->fast)
+    elem_resid_kernel<NP, EPB, MINB, true><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+  else
+    elem_resid_kernel<NP, EPB, MINB, false><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
 }
 
 // Launch-shape selection.  p = 3 is the tuned case; tune[] (TPSB_TUNE="g,f,r", development knob) picks
@@ -1063,15 +1066,24 @@ static void launch_face_fast(tpsb_ctx *c, const KernelArgs &a, int begin, int co
   }
   face_flux_fast_kernel<NP, WPB, MINB><<<grid, 32 * WPB, smem, c->stream>>>(a, begin, count);
 }
+template <int EPB, int MINB>
+static void launch_grad_trace_mma(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_GRAD);
+  grad_trace_mma_kernel<EPB, MINB><<<(count + EPB - 1) / EPB, 64 * EPB, 0, c->stream>>>(a, begin, count, list);
+}
 static void grad_trace(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list) {
   if (c->np == 4) {
     switch (c->tune[0]) {
+      case 6: launch_grad_trace<4, 1, 10>(c, a, begin, count, list); break;  // DFMA form (before the DMMA kernel)
+      case 7: launch_grad_trace_mma<2, 4>(c, a, begin, count, list); break;
+      case 8: launch_grad_trace_mma<1, 6>(c, a, begin, count, list); break;
       case 1: launch_grad_trace<4, 1, 12>(c, a, begin, count, list); break;
       case 2: launch_grad_trace<4, 2, 5>(c, a, begin, count, list); break;
       case 3: launch_grad_trace<4, 2, 6>(c, a, begin, count, list); break;
       case 4: launch_grad_trace<4, 4, 3>(c, a, begin, count, list); break;
       case 5: launch_grad_trace<4, 1, 8>(c, a, begin, count, list); break;
-      default: launch_grad_trace<4, 1, 10>(c, a, begin, count, list); break;
+      default: launch_grad_trace_mma<1, 9>(c, a, begin, count, list); break;
     }
   } else if (c->np == 3) {
     launch_grad_trace<3, 4, 4>(c, a, begin, count, list);
