@@ -40,7 +40,7 @@ enum { TPSB_DRY_AIR = 0, TPSB_USER_DEFINED = 1, TPSB_LTE_FLUID = 2 }; /* Working
 /* Mesh/connectivity tables the MFEM host code hands over (what initIndirectionArrays reads from
  * ParMesh, src/M2ulPhyS.cpp:816-1075).  All arrays are HOST memory, copied at create.          */
 typedef struct {
-  int dim;                      /* 3 (hexahedra); 2-D quads: TPSB_ENOTIMPL for now                          */
+  int dim;                      /* 3 (hexahedra) or 2 (quadrilaterals)                                      */
   int num_elems;                /* vfes->GetNE(), local elements                                           */
   int num_nbr_elems;            /* face-neighbour (halo) elements, pmesh->GetNFaceNeighborElements(); 0 serial */
   const double *elem_vertices;  /* [(num_elems+num_nbr_elems)][2^dim][dim] vertex coordinates, MFEM vertex
@@ -60,7 +60,8 @@ typedef struct {
   int basis_type;     /* flow/basisType: 0 Gauss-Legendre nodes, 1 Gauss-Lobatto      */
   int int_rule_type;  /* flow/integrationRule: 0 Gauss-Legendre, 1 Gauss-Lobatto      */
   int num_equation;   /* vfes vdim                                                    */
-  int nvel;           /* dim, or 3 when axisymmetric                                  */
+  int nvel;           /* dim; 3 on a 2-D mesh = axisymmetric run (x = r, y = z, third velocity u_theta;
+                         config.isAxisymmetric(), src/rhs_operator.cpp:191-205, src/forcing_terms.cpp:255-380) */
 } tpsb_space_desc;
 
 /* Physics parameter block: the POD input structs of the reference flattened
@@ -112,11 +113,13 @@ typedef struct {
  * (src/M2ulPhyS.cpp:3480): the BR1 gradient then uses the wall state at isothermal walls
  * (src/faceGradientIntegration.cpp:96-115) and the wall Riemann state flips (src/wallBC.cpp:476-479).  */
 enum { TPSB_BC_INLET = 0, TPSB_BC_OUTLET = 1, TPSB_BC_WALL = 2 };
+#define TPSB_BC_NDATA 12
 typedef struct {
   int attr;        /* boundary attribute (patch number) the condition applies to */
   int kind;        /* TPSB_BC_*                                                   */
   int type;        /* InletType / OutletType / WallType value                     */
-  double data[8];
+  double data[TPSB_BC_NDATA]; /* inlet: inputState {rho, u, v, w, rho Y_sp (active species, mixture order) ...}
+                                 (src/M2ulPhyS.cpp:3609-3641, src/inletBC.cpp:52-66); outlet {p}; wall {Th}  */
 } tpsb_bc_desc;
 typedef struct {
   int num_bcs;

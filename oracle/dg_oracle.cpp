@@ -140,7 +140,8 @@ struct Oracle {
   std::vector<double> nodes1d;
   int nqv1 = 0, nqf1 = 0, nqv = 0, nqf = 0;
   std::vector<double> qxv, qwv, qxf, qwf;
-  std::vector<double> Me_inv, Ke, Kfl;  // per element dense
+  std::vector<double> Me_inv, Me_inv_rad, Ke, Kfl;  // per element dense
+  bool axisym = false;
   std::vector<double> elSize;           // per element delta = h_min / order
   std::vector<double> nodeXYZ;          // [NE][dof][dim]
   std::map<int, std::vector<double>> shapeTab;  // inf code -> [nqf][dof]
@@ -346,6 +347,8 @@ struct Oracle {
       state2[1] = b.data[0] * b.data[1];
       state2[2] = b.data[0] * b.data[2];
       if (nvel == 3) state2[3] = b.data[0] * b.data[3];
+      // inputState[4 + sp] = rho Y_sp of the active species (src/inletBC.cpp:742-750)
+      for (int sp = 0; sp < ph->num_active_species(); sp++) state2[nvel + 2 + sp] = b.data[4 + sp];
       ph->modify_energy_for_pressure(state2, state2, pr, true);
       ph->riemann(stateIn, state2, normal, bdrFlux);
     } else if (b.kind == 1) {
@@ -386,6 +389,7 @@ struct Oracle {
         ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
         for (int i = 0; i < nsp; i++) idx[i] = true;
         idx[nsp + nvel] = true;
+        if (neq - (nvel + 2) - ph->num_active_species() == 1) idx[nsp + nvel + 1] = true;  // two-temperature (:93)
         ph->bdr_visc_flux(wallState, gradState, xyz, delta, 0.0, unitN, primFlux, idx, wallViscF);
       } else {
         // WallBC::computeIsothermalWallFlux (src/wallBC.cpp:471-510); bcFlux_: species flux prescribed 0 (:97-110)
@@ -447,14 +451,16 @@ struct Oracle {
     }
 
     const size_t d2 = static_cast<size_t>(dof) * dof;
+    axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric(): 2-D mesh (r, z) carrying three velocity components
     Me_inv.assign(NE * d2, 0.0);
+    if (axisym) Me_inv_rad.assign(NE * d2, 0.0);
     Ke.assign(NE * d2 * dim, 0.0);
     Kfl.assign(NE * d2 * dim, 0.0);
     elSize.assign(NE, 0.0);
     nodeXYZ.assign(static_cast<size_t>(N) * dim, 0.0);
 #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int e = 0; e < NE; e++) {
-      std::vector<double> shape(dof), dshape(dof * dim), Me(d2, 0.0), physd(dof * dim), dsdx(dof * dim);
+      std::vector<double> shape(dof), dshape(dof * dim), Me(d2, 0.0), MeR(d2, 0.0), physd(dof * dim), dsdx(dof * dim);
       double *ke = &Ke[e * d2 * dim], *kf = &Kfl[e * d2 * dim];
       for (int q = 0; q < nqv; q++) {
         const int qi[3] = {q % nqv1, (q / nqv1) % nqv1, q / (nqv1 * nqv1)};
@@ -463,14 +469,18 @@ struct Oracle {
           xi[d] = qxv[qi[d]];
           w *= qwv[qi[d]];
         }
-        double J[9], A[9];
-        elem_map(e, xi, nullptr, J);
+        double J[9], A[9], xq[3] = {0, 0, 0};
+        elem_map(e, xi, xq, J);
         const double dt = det(J);
         adj(J, A);
         calc_shape(xi, shape.data(), dshape.data());
         // MassIntegrator (src/rhs_operator.cpp:179-185)
         for (int i = 0; i < dof; i++)
           for (int j = 0; j < dof; j++) Me[i * dof + j] += w * dt * shape[i] * shape[j];
+        // axisymmetric: M_ij = int r phi_i phi_j (MassIntegrator(radiusFcn), src/rhs_operator.cpp:191-205)
+        if (axisym)
+          for (int i = 0; i < dof; i++)
+            for (int j = 0; j < dof; j++) MeR[i * dof + j] += w * dt * xq[0] * shape[i] * shape[j];
         // CalcPhysDShape = dshape * inv(J); dshapedx = dshape * adj(J)
         for (int k = 0; k < dof; k++)
           for (int d = 0; d < dim; d++) {
@@ -484,13 +494,18 @@ struct Oracle {
         for (int d = 0; d < dim; d++)
           for (int k = 0; k < dof; k++)
             for (int j = 0; j < dof; j++) ke[j * (dim * dof) + k + d * dof] += shape[j] * physd[k * dim + d] * detJac;
-        // elmat(j, k + d*dof) += (shape(k)*w) * dshapedx(j,d)  (src/domain_integrator.cpp:71-97)
+        // elmat(j, k + d*dof) += (shape(k)*w [*radius]) * dshapedx(j,d)  (src/domain_integrator.cpp:71-97)
+        const double wk = axisym ? w * xq[0] : w;
         for (int d = 0; d < dim; d++)
           for (int j = 0; j < dof; j++)
-            for (int k = 0; k < dof; k++) kf[j * (dim * dof) + k + d * dof] += shape[k] * w * dsdx[j * dim + d];
+            for (int k = 0; k < dof; k++) kf[j * (dim * dof) + k + d * dof] += shape[k] * wk * dsdx[j * dim + d];
       }
       invert_dense(Me, dof);
       std::copy(Me.begin(), Me.end(), &Me_inv[e * d2]);
+      if (axisym) {
+        invert_dense(MeR, dof);
+        std::copy(MeR.begin(), MeR.end(), &Me_inv_rad[e * d2]);
+      }
       // elSize: GetElementSize(e,1)/order (src/rhs_operator.cpp:149-156)
       {
         const double c[3] = {0.5, 0.5, 0.5};
@@ -664,6 +679,8 @@ struct Oracle {
         }
         const double w = face_weight(q);
         for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
+        if (axisym)  // src/face_integrator.cpp:344-346
+          for (int eq = 0; eq < neq; eq++) fluxN[eq] *= xyz[0];
         for (int k = 0; k < dof; k++)
           for (int eq = 0; eq < neq; eq++) {
             v2[k * neq + eq] += s2[k] * fluxN[eq];
@@ -702,6 +719,8 @@ struct Oracle {
           bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN);
           const double w = face_weight(q);
           for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
+          if (axisym)  // src/BCintegrator.cpp:427-429
+            for (int eq = 0; eq < neq; eq++) fluxN[eq] *= xyz[0];
           for (int k = 0; k < dof; k++)
             for (int eq = 0; eq < neq; eq++) v1[k * neq + eq] -= fluxN[eq] * s1[k];
         }
@@ -752,7 +771,7 @@ struct Oracle {
             for (int k = 0; k < dof; k++) a += kf[j * (dim * dof) + k + d * dof] * fl[(k * dim + d) * neq + eq];
           z[j * neq + eq] += a;
         }
-      const double *mi = &Me_inv[e * d2];
+      const double *mi = axisym ? &Me_inv_rad[e * d2] : &Me_inv[e * d2];  // src/rhs_operator.cpp:441-445
       for (int eq = 0; eq < neq; eq++)
         for (int j = 0; j < dof; j++) {
           double a = 0;
@@ -774,6 +793,49 @@ struct Oracle {
         }
         ph->source_term(Un, upn, g, static_cast<int>(n), src);
         for (int eq = 0; eq < neq; eq++) y[n + eq * N] += src[eq];
+      }
+    }
+    // AxisymmetricSource::updateTerms (src/forcing_terms.cpp:255-380), registered after SourceTerm
+    // (src/rhs_operator.cpp:126-160); reads U_ (the solution grid function), Up and gradUp.
+    if (axisym) {
+      const double *Usol = sol_view ? sol_view : x;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+      for (long n = 0; n < N; n++) {
+        double Un[16], upn[16], g[48];
+        for (int eq = 0; eq < neq; eq++) {
+          Un[eq] = Usol[n + eq * N];
+          upn[eq] = Up[n + eq * N];
+          for (int d = 0; d < dim; d++) g[eq + d * neq] = gradUp[n + eq * N + static_cast<size_t>(d) * neq * N];
+        }
+        for (int sp = 0; sp < nact; sp++) {
+          const int eq = 3 + 2 + sp;
+          Un[eq] = std::max(Un[eq], 0.0);
+          upn[eq] = std::max(upn[eq], 0.0);
+        }
+        const double radius = nodeXYZ[n * dim + 0];
+        const double rho = upn[0], ur = upn[1], ut = upn[3];
+        const double pressure = ph->pressure_from_primitives(upn);
+        const double rurut = rho * ur * ut, rutut = rho * ut * ut;
+        double tau_tt, tau_tr;
+        if (phys.eq_system == 0) {
+          tau_tt = tau_tr = 0.0;
+        } else {
+          const double ur_r = g[1 + 0 * neq], uz_z = g[2 + 1 * neq], ut_r = g[3 + 0 * neq];
+          double visc, bulkVisc, visc_vec[2];
+          ph->get_viscosities(Un, upn, g, radius, 0.0, visc_vec);
+          visc = visc_vec[0];
+          bulkVisc = visc_vec[1];
+          bulkVisc -= 2. / 3. * visc;
+          double divV = ur_r + uz_z;
+          if (radius > 0) divV += ur / radius;
+          tau_tt = (radius > 0) ? 2.0 * ur / radius * visc : 0.0;
+          tau_tt += bulkVisc * divV;
+          tau_tr = ut_r;
+          if (radius > 0) tau_tr -= ut / radius;
+          tau_tr *= visc;
+        }
+        y[n + 1 * N] += (pressure + rutut - tau_tt) / radius;
+        y[n + 3 * N] += (-rurut + tau_tr) / radius;
       }
     }
   }

@@ -44,10 +44,11 @@ struct OrcPlasma {
 };
 // One boundary condition of BCintegrator's attribute maps (src/BCintegrator.cpp:64-125).
 // kind: 0 inlet, 1 outlet, 2 wall; type: the reference's InletType / OutletType / WallType value
-// (src/dataStructures.hpp:168-196); data: inlet inputState (rho, u, v, w), outlet inputState (p), wall Th.
+// (src/dataStructures.hpp:168-196); data: inlet inputState (rho, u, v, w, rho Y_sp of the active species ...),
+// outlet inputState (p), wall Th.
 struct OrcBc {
   int attr, kind, type;
-  double data[8];
+  double data[12];
 };
 }
 
@@ -75,6 +76,12 @@ struct Physics {
   // reference does.  Fluids without plasma sources keep the default (no forcing term registered).
   virtual bool has_source() const { return false; }
   virtual void source_term(double *Un, double *upn, const double *gradUpn, int node, double *src) {}
+  // ---- used by AxisymmetricSource (src/forcing_terms.cpp:255-380) ----
+  // GasMixture::ComputePressureFromPrimitives
+  virtual double pressure_from_primitives(const double *Up) = 0;
+  // TransportProperties::GetViscosities(conserved, primitive, gradUp, radius, distance, visc[2])
+  virtual void get_viscosities(const double *U, const double *Up, const double *gradUp, double radius, double dist,
+                               double *visc) = 0;
   // ---- used by the boundary conditions ----
   virtual int num_species() const = 0;
   // GasMixture::ComputePressure

@@ -48,10 +48,12 @@ class DryAirPort : public Physics {
   }
   // src/fluxes.cpp:344-504 for dry air: one species with zero diffusion velocity
   // (src/transport_properties.cpp:236-266), no species enthalpy carried to the heat flux, single temperature.
-  void bdr_visc_flux(const double *s, const double *gradUp, double * /*xyz*/, double /*delta*/, double /*dist*/,
+  void bdr_visc_flux(const double *s, const double *gradUp, double *xyz, double /*delta*/, double /*dist*/,
                      const double *nrm, const double *primFlux, const bool *primFluxIdxs, double *normalFlux) override {
     for (int eq = 0; eq < neq_; eq++) normalFlux[eq] = 0.;
     if (p_.eq_system == 0) return;
+    const bool axisym = (dim_ == 2 && nvel_ == 3);
+    const double radius = axisym ? xyz[0] : -1;
     const int numSpecies = 1;
     double pr = pressure(s);
     double temp = pr / p_.R / s[0];
@@ -73,9 +75,20 @@ class DryAirPort : public Physics {
     }
     for (int i = 0; i < dim_; i++)
       for (int j = 0; j < dim_; j++) stress[i + j * dim_] *= visc;
+    const double ur = (axisym ? s[1] / s[0] : 0), ut = (axisym ? s[3] / s[0] : 0);
+    if (axisym && radius > 0) divV += ur / radius;
     for (int i = 0; i < dim_; i++) stress[i + i * dim_] += bulkViscosity * divV;
     for (int i = 0; i < dim_; i++)
       for (int j = 0; j < dim_; j++) normalPrimFlux[numSpecies + i] += stress[i + j * dim_] * nrm[j];
+    if (axisym) {  // src/fluxes.cpp:452-464
+      const double ut_r = gradUp[3 + 0 * neq_], ut_z = gradUp[3 + 1 * neq_];
+      double tau_tr = ut_r;
+      if (radius > 0) tau_tr -= ut / radius;
+      tau_tr *= visc;
+      const double tau_tz = visc * ut_z;
+      normalPrimFlux[numSpecies + nvel_ - 1] += tau_tr * nrm[0];
+      normalPrimFlux[numSpecies + nvel_ - 1] += tau_tz * nrm[1];
+    }
     k += 0.0;  // ke, single temperature
     for (int d = 0; d < dim_; d++) normalPrimFlux[numSpecies + nvel_] -= k * gradUp[(1 + nvel_) + d * neq_] * nrm[d];
     // species enthalpy x diffusion flux: DryAir::computeSpeciesEnthalpies returns 0 (equation_of_state.cpp)
@@ -94,6 +107,14 @@ class DryAirPort : public Physics {
     for (int d = 0; d < nvel_; d++) den_vel2 += s[d + 1] * s[d + 1];
     den_vel2 /= s[0];
     return (p_.gamma - 1.0) * (s[1 + nvel_] - 0.5 * den_vel2);
+  }
+  // src/equation_of_state.cpp:360-364 (DryAir::ComputePressureFromPrimitives)
+  double pressure_from_primitives(const double *Up) override { return p_.R * Up[0] * Up[1 + nvel_]; }
+  // src/transport_properties.hpp:264-269 (DryAirTransport::GetViscosities)
+  void get_viscosities(const double *, const double *Up, const double *, double, double, double *visc) override {
+    const double temp = Up[1 + nvel_];
+    visc[0] = (p_.C1 * p_.visc_mult * pow(temp, 1.5) / (temp + p_.S0));
+    visc[1] = p_.bulk_visc_mult * visc[0];
   }
   // src/equation_of_state.hpp:621-627 (DryAir::ComputeTemperature)
   double temperature(const double *s) {
@@ -142,9 +163,11 @@ class DryAirPort : public Physics {
     for (int d = 0; d < dim_; d++) flux[1 + nvel_ + d * neq_] = s[d + 1] * H;
   }
   // src/fluxes.cpp:178-335 with DryAirTransport::ComputeFluxMolecularTransport
-  // (src/transport_properties.cpp:223-234); non-axisymmetric, no SGS, no sponge.
-  void visc_flux(const double *s, const double *gradUp, double * /*xyz*/, double /*delta*/, double /*dist*/,
+  // (src/transport_properties.cpp:223-234); no SGS, no sponge.
+  void visc_flux(const double *s, const double *gradUp, double *xyz, double /*delta*/, double /*dist*/,
                  double *flux) override {
+    const bool axisym = (dim_ == 2 && nvel_ == 3);
+    const double radius = axisym ? xyz[0] : -1;
     for (int d = 0; d < dim_; d++)
       for (int eq = 0; eq < neq_; eq++) flux[eq + d * neq_] = 0.;
     if (p_.eq_system == 0) return;  // EULER, src/fluxes.cpp:185-187
@@ -167,9 +190,21 @@ class DryAirPort : public Physics {
     }
     for (int i = 0; i < dim_; i++)
       for (int j = 0; j < dim_; j++) stress[i + j * dim_] *= visc;
+    const double ur = (axisym ? s[1] / s[0] : 0), ut = (axisym ? s[3] / s[0] : 0);
+    if (axisym && radius > 0) divV += ur / radius;
     for (int i = 0; i < dim_; i++) stress[i + i * dim_] += bulkViscosity * divV;
     for (int i = 0; i < dim_; i++)
       for (int j = 0; j < dim_; j++) flux[(1 + i) + j * neq_] = stress[i + j * dim_];
+    double tau_tr = 0, tau_tz = 0;
+    if (axisym) {  // src/fluxes.cpp:285-297
+      const double ut_r = gradUp[3 + 0 * neq_], ut_z = gradUp[3 + 1 * neq_];
+      tau_tr = ut_r;
+      if (radius > 0) tau_tr -= ut / radius;
+      tau_tr *= visc;
+      tau_tz = visc * ut_z;
+      flux[(1 + 2) + 0 * neq_] = tau_tr;
+      flux[(1 + 2) + 1 * neq_] = tau_tz;
+    }
 
     for (int d = 0; d < dim_; d++) vel[d] = s[1 + d] / s[0];
     for (int i = 0; i < dim_; i++) {
@@ -179,6 +214,10 @@ class DryAirPort : public Physics {
     for (int d = 0; d < dim_; d++) {
       flux[(1 + nvel_) + d * neq_] += vtmp[d];
       flux[(1 + nvel_) + d * neq_] += k * gradUp[(1 + nvel_) + d * neq_];
+    }
+    if (axisym) {  // src/fluxes.cpp:320-323
+      flux[(1 + nvel_) + 0 * neq_] += ut * tau_tr;
+      flux[(1 + nvel_) + 1 * neq_] += ut * tau_tz;
     }
   }
   // src/riemann_solver.cpp:89-114 (Eval_LF) with ComputeFluxDotN :53-64

@@ -31,8 +31,9 @@ class DryAirRef : public Physics {
     in.gas_constant = p.R;
     mix_ = new DryAir(in, dim, nvel);                                                          // equation_of_state.cpp:150
     trans_ = new DryAirTransport(mix_, p.visc_mult, p.bulk_visc_mult, p.C1, p.S0, p.Pr);       // transport_properties.cpp:208
-    flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, false);   // fluxes.cpp:34
-    rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, false, false);  // riemann_solver.cpp:38
+    const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
+    flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym);   // fluxes.cpp:34
+    rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, false, axisym);  // riemann_solver.cpp:38
   }
   ~DryAirRef() {
     delete rs_;
@@ -44,6 +45,11 @@ class DryAirRef : public Physics {
   int num_active_species() const override { return mix_->GetNumActiveSpecies(); }
   int num_species() const override { return mix_->GetNumSpecies(); }
   double pressure(const double *U) override { return mix_->ComputePressure(U); }
+  double pressure_from_primitives(const double *Up) override { return mix_->ComputePressureFromPrimitives(Up); }
+  void get_viscosities(const double *U, const double *Up, const double *gradUp, double radius, double dist,
+                       double *visc) override {
+    trans_->GetViscosities(U, Up, gradUp, radius, dist, visc);
+  }
   void stagnation_state(const double *U, double *out) override {
     Vector a(const_cast<double *>(U), neq_), b(neq_);
     mix_->computeStagnationState(a, b);  // equation_of_state.cpp:365
@@ -120,8 +126,9 @@ class MixtureRef : public Physics {
     ct.electronIndex = pm.num_species - 2;
     trans_ = new ConstantTransport(mix_, ct);  // transport_properties.cpp:303
     const Equations eqs = static_cast<Equations>(p.eq_system);
-    flux_ = new Fluxes(mix_, eqs, trans_, neq, dim, false);
-    rs_ = new RiemannSolverTPS(neq, mix_, eqs, flux_, false, false);
+    const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
+    flux_ = new Fluxes(mix_, eqs, trans_, neq, dim, axisym);
+    rs_ = new RiemannSolverTPS(neq, mix_, eqs, flux_, false, axisym);
     if (pm.num_reactions > 0) {
       ChemistryInput ci;
       ci.model = NUM_CHEMISTRYMODEL;
@@ -166,6 +173,11 @@ class MixtureRef : public Physics {
     rs_->Eval(U1, U2, nor, flux, false);
   }
   double pressure(const double *U) override { return mix_->ComputePressure(U); }
+  double pressure_from_primitives(const double *Up) override { return mix_->ComputePressureFromPrimitives(Up); }
+  void get_viscosities(const double *U, const double *Up, const double *gradUp, double radius, double dist,
+                       double *visc) override {
+    trans_->GetViscosities(U, Up, gradUp, radius, dist, visc);
+  }
   void stagnation_state(const double *U, double *out) override {
     Vector a(const_cast<double *>(U), neq_), b(neq_);
     mix_->computeStagnationState(a, b);

@@ -18,7 +18,7 @@ class OrcPhysParams(C.Structure):
 
 class OrcBc(C.Structure):
     """kind 0 inlet / 1 outlet / 2 wall; type = the reference's InletType / OutletType / WallType value."""
-    _fields_ = [("attr", C.c_int), ("kind", C.c_int), ("type", C.c_int), ("data", C.c_double * 8)]
+    _fields_ = [("attr", C.c_int), ("kind", C.c_int), ("type", C.c_int), ("data", C.c_double * 12)]
 
 
 def make_bc(attr, kind, type_, data=()):

@@ -1,0 +1,89 @@
+"""Generic path through the C ABI against the CPU oracle: boundary conditions on quadrilateral meshes (BCintegrator /
+WallBC / InletBC / OutletBC for dry air and mixtures), axisymmetric runs (nvel = 3 on a 2-D mesh: r-weighted operators,
+Me_inv_rad, axisymmetric viscous terms, AxisymmetricSource) and the six-species two-temperature argon mixture of
+BASELINE config C4 (test/inputs/plasma.ini physics on a restated quad mesh)."""
+import os
+
+import numpy as np
+import pytest
+
+import axisym_cases as ac
+import oracle_api
+from common import rel_l2
+
+pytestmark = pytest.mark.gpu
+HAVE_REF = os.path.exists(os.path.join(oracle_api.ORACLE_DIR, "_ref", "liboracle_ref.so"))
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (reference object code) not built")
+
+
+def _compare(op, orc, U, tol_y=1e-10):
+    import torch
+    N, neq = orc.N, op.neq
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    yo, go = orc.mult(U, want_grad=True)
+    up, g = op.fields()
+    assert rel_l2(up.cpu().numpy(), orc.primitives(U)) < 1e-13
+    assert rel_l2(g.cpu().numpy(), go) < 1e-11
+    for k in range(neq):
+        ref = yo[k * N:(k + 1) * N]
+        assert np.linalg.norm(y[k * N:(k + 1) * N] - ref) <= tol_y * max(np.linalg.norm(ref), 1e-30) + 1e-9, k
+    assert abs(op.max_char_speed() / orc.max_char_speed - 1) < 1e-13
+
+
+@pytest.mark.parametrize("order,bt,ir", [(2, 1, 1), (3, 0, 0), (1, 0, 0)])
+@pytest.mark.parametrize("eq,bc,ubg", [(1, "c4", True), (1, "c4", False), (1, "adiabatic", False), (0, "inviscid", False)])
+def test_quad_boundary_conditions_dry_air(lib_built, oracle_built, order, bt, ir, eq, bc, ubg):
+    m = ac.box(warp=0.06)
+    op, orc = ac.make_pair(m, order, eq, bt, ir, 2, bc, ubg)
+    _compare(op, orc, ac.dry_state(orc.node_coords(), 2))
+
+
+@pytest.mark.parametrize("order,bt,ir", [(3, 0, 0), (2, 1, 1)])
+@pytest.mark.parametrize("eq,bc,ubg", [(1, "c4", True), (1, "adiabatic", False), (0, "inviscid", False), (1, None, False)])
+def test_axisymmetric_dry_air(lib_built, oracle_built, order, bt, ir, eq, bc, ubg):
+    m = ac.box(warp=0.06)
+    op, orc = ac.make_pair(m, order, eq, bt, ir, 3, bc, ubg)
+    assert op.neq == 5
+    _compare(op, orc, ac.dry_state(orc.node_coords(), 3))
+
+
+def test_axisymmetric_vessel_at_rest(lib_built, oracle_built):
+    m = ac.box(n=(4, 3), warp=0.07)
+    op, orc = ac.make_pair(m, 3, 1, 0, 0, 3, "inviscid", False)
+    import torch
+    N = orc.N
+    U = np.concatenate([np.full(N, 1.2), np.zeros(3 * N), np.full(N, 101300.0 / 0.4)])
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    assert np.abs(y).max() < 1e-10 * 101300.0 / 0.5
+
+
+@needs_ref
+@pytest.mark.parametrize("nvel,bc,ubg", [(3, "c4", True), (3, "adiabatic", False), (2, "c4", True), (2, "c4", False)])
+def test_plasma_axisym_configuration_c4(lib_built, oracle_built, nvel, bc, ubg):
+    """Six-species non-ambipolar two-temperature argon (neq = nvel + 8: 11 when axisymmetric), p = 3 GL/GL, inviscid +
+    isothermal walls, subsonic inlet with species, pressure outlet, useBCinGrad."""
+    m = ac.box(n=(4, 3), warp=0.05)
+    op, orc = ac.make_pair(m, 3, 1, 0, 0, nvel, bc, ubg, mixture=ac.argon6_dict())
+    assert op.neq == nvel + 8
+    up = ac.argon6_primitives(orc.node_coords(), nvel)
+    U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+    _compare(op, orc, U)
+
+
+@needs_ref
+def test_ternary_mixture_with_walls(lib_built, oracle_built):
+    import plasma_cases
+    import tps_b200
+    m = ac.box(n=(4, 4), lo=(-1.0, -1.0), hi=(1.0, 1.0))
+    pm = plasma_cases.ternary_models()
+    specs = [(1, 2, 3, (450.0,)), (2, 2, 2, ()), (3, 0, 2, (1.2, 10.0, 2.0, 0.0, 0.3 * (plasma_cases.MW_AR - plasma_cases.MW_E))),
+             (4, 1, 0, (120000.0,))]
+    for ubg in (True, False):
+        op = tps_b200.RhsOperator(m, order=2, physics=tps_b200.Physics.plasma_mixture(pm, 1), basis_type=1, int_rule_type=1,
+                                  face_attr=m["face_attr"], use_bc_in_grad=ubg, bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+        orc = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                                phys=oracle_api.mixture_params(pm, 1), kind="ref", basis_type=1, int_rule=1, neq=6, nvel=2)
+        orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], ubg)
+        up = plasma_cases.smooth_primitives(orc.node_coords() * np.pi)
+        U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+        _compare(op, orc, U)

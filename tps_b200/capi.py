@@ -103,7 +103,7 @@ class Physics(C.Structure):
 
 class BcDesc(C.Structure):
     """tpsb_bc_desc: kind 0 inlet / 1 outlet / 2 wall, type = the reference's InletType / OutletType / WallType."""
-    _fields_ = [("attr", C.c_int), ("kind", C.c_int), ("type", C.c_int), ("data", C.c_double * 8)]
+    _fields_ = [("attr", C.c_int), ("kind", C.c_int), ("type", C.c_int), ("data", C.c_double * 12)]
 
     @classmethod
     def make(cls, attr, kind, type_, data=()):
@@ -239,6 +239,28 @@ def cartesian_quad_mesh(nx, ny, lo=(-1.0, -1.0), hi=(1.0, 1.0), periodic=(1, 1))
                 face_inf1=inf1[:nf].copy(), face_inf2=inf2[:nf].copy())
 
 
+QUAD_EDGE_VERT = np.array([[0, 1], [1, 2], [2, 3], [3, 0]])  # Geometry::Constants<SQUARE>::Edges
+
+
+def quad_box_face_attr(m, lo, hi):
+    """Boundary attribute of every face of a non-periodic Cartesian quad box: 1 x = lo, 2 x = hi, 3 y = lo, 4 y = hi
+    (0 on interior faces)."""
+    el1, el2, inf1 = m["face_el1"], m["face_el2"], m["face_inf1"]
+    attr = np.zeros(len(el1), dtype=np.int32)
+    tol = 1e-9 * max(hi[0] - lo[0], hi[1] - lo[1])
+    for f in np.nonzero(el2 < 0)[0]:
+        c = m["elem_xyz"][el1[f], QUAD_EDGE_VERT[inf1[f] // 64]].mean(axis=0)
+        if abs(c[0] - lo[0]) < tol:
+            attr[f] = 1
+        elif abs(c[0] - hi[0]) < tol:
+            attr[f] = 2
+        elif abs(c[1] - lo[1]) < tol:
+            attr[f] = 3
+        elif abs(c[1] - hi[1]) < tol:
+            attr[f] = 4
+    return attr
+
+
 HEX_FACE_VERT = np.array([[3, 2, 1, 0], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [4, 5, 6, 7]])
 
 
@@ -337,7 +359,7 @@ class RhsOperator:
     Mult / updatePrimitives / updateGradients / getGradients, on torch CUDA tensors."""
 
     def __init__(self, mesh, order=3, physics=None, device=0, halo=None, num_nbr_elems=0, stream=None, bcs=None,
-                 face_attr=None, use_bc_in_grad=False, basis_type=0, int_rule_type=0):
+                 face_attr=None, use_bc_in_grad=False, basis_type=0, int_rule_type=0, nvel=None):
         import torch
         self.torch = torch
         self.L = lib()
@@ -359,11 +381,12 @@ class RhsOperator:
             arr = (BcDesc * len(bcs))(*bcs)
             bcset = BcSet(len(bcs), arr, int(use_bc_in_grad))
             self._keep.append(arr)
-        neq = self.dim + 2
+        self.nvel = nvel or self.dim  # nvel = 3 on a 2-D mesh: axisymmetric run
+        neq = self.nvel + 2
         if self.physics.fluid == 1:
             pm = self.physics.plasma.contents
             neq += (pm.num_species - 2 if pm.ambipolar else pm.num_species - 1) + (1 if pm.two_temperature else 0)
-        space = SpaceDesc(order, basis_type, int_rule_type, neq, self.dim)
+        space = SpaceDesc(order, basis_type, int_rule_type, neq, self.nvel)
         self.ctx = C.c_void_p()
         s = stream if stream is not None else 0
         rc = self.L.tpsb_create(C.byref(maps), C.byref(space), C.byref(self.physics),

@@ -1,6 +1,6 @@
 // Per-point physics with RUN-TIME dimension / equation count for the generic tensor-product path
 // (rhs_generic.cuh): 2-D and 3-D, nvel = dim (or 3 when axisymmetric), num_equation <= GEN_MAXEQ.
-// Dry air only so far; the mixture models plug in behind the same five entry points.
+// Dry air here; the mixture models (mix_physics.cuh) plug in behind the same entry points.
 // Formulas and operation order follow the reference routines cited at each function.
 #pragma once
 #include <cuda_runtime.h>
@@ -15,6 +15,7 @@ constexpr int GEN_MAXDIM = 3;
 
 struct GenPhys {
   int dim, nvel, neq;
+  int axisym;            // config.isAxisymmetric(): dim == 2 with nvel == 3, state [rho, rho u_r, rho u_z, rho u_theta, ...]
   int fluid;             // 0 dry air; 1 user-defined plasma mixture (mix != NULL)
   PhysParams dry;        // gamma, R, Sutherland, multipliers, eq_system
   const MixParams *mix;  // device (or host, for host-side checks) pointer
@@ -63,12 +64,13 @@ __host__ __device__ __forceinline__ void dry_gen_conv_flux(const GenPhys &g, con
 }
 
 // Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335) with DryAirTransport (transport_properties.cpp:223-234);
-// non-axisymmetric, no SGS, no sponge.  gr[eq + d*neq] = d Up_eq / d x_d.
+// no SGS, no sponge.  gr[eq + d*neq] = d Up_eq / d x_d; radius = x[0] of the point (axisymmetric terms only).
 // Written with fixed 3x3 register tiles and guards instead of run-time-indexed local arrays (entries beyond
 // `dim` are zero, so sums keep the reference's operation order): nvcc 12.9 -O3 produced wrong stores for the
 // run-time-indexed form once inlined into gen_resid_kernel (caught by the parity test; the stand-alone
 // function was correct, tools/ubench/gen_visc_check.cu).
-__host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double *f) {
+__host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
+                                                           double *f) {
   const int neq = g.neq, dim = g.dim;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (g.dry.eq_system == 0) return;
@@ -96,6 +98,8 @@ __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, con
       st[i][j] = gu[j][i] + gu[i][j];
       st[i][j] *= visc;
     }
+  const double ur = g.axisym ? s[1] / s[0] : 0.0, ut = g.axisym ? s[3] / s[0] : 0.0;
+  if (g.axisym && radius > 0) divV += ur / radius;
 #pragma unroll
   for (int i = 0; i < 3; i++) st[i][i] += bulk * divV;
 #pragma unroll
@@ -110,6 +114,73 @@ __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, con
       f[(1 + g.nvel) + j * neq] = vtmp + k * gT[j];
     }
   }
+  if (g.axisym) {  // fluxes.cpp:285-297, 320-323
+    double tau_tr = gr[3 + 0 * neq];
+    if (radius > 0) tau_tr -= ut / radius;
+    tau_tr *= visc;
+    const double tau_tz = visc * gr[3 + 1 * neq];
+    f[(1 + 2) + 0 * neq] = tau_tr;
+    f[(1 + 2) + 1 * neq] = tau_tz;
+    f[(1 + g.nvel) + 0 * neq] += ut * tau_tr;
+    f[(1 + g.nvel) + 1 * neq] += ut * tau_tz;
+  }
+}
+
+// Fluxes::ComputeBdrViscousFluxes (fluxes.cpp:344-504) for dry air: one species with zero diffusion velocity, no
+// species-enthalpy term, single temperature.  nrm = unit normal; heat_prescribed: primFluxIdxs[numSpecies + nvel]
+// (prescribed value 0: adiabatic wall).
+__host__ __device__ __forceinline__ void dry_gen_bdr_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
+                                                               const double *nrm, bool heat_prescribed, double *nf) {
+  const int neq = g.neq, dim = g.dim, nvel = g.nvel;
+  for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
+  if (g.dry.eq_system == 0) return;
+  const double pr = dry_gen_pressure(g, s);
+  const double temp = pr / g.dry.R / s[0];
+  const double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
+  double bulk = g.dry.bulk_visc_mult * visc;
+  const double k = g.dry.cp_div_pr * visc;
+  bulk -= 2. / 3. * visc;
+  double gu[3][3], st[3][3], nn[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    nn[i] = i < dim ? nrm[i] : 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) gu[i][d] = (i < dim && d < dim) ? gr[(1 + i) + d * neq] : 0.0;
+  }
+  double divV = 0.;
+#pragma unroll
+  for (int i = 0; i < 3; i++) divV += gu[i][i];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      st[i][j] = gu[j][i] + gu[i][j];
+      st[i][j] *= visc;
+    }
+  const double ur = g.axisym ? s[1] / s[0] : 0.0, ut = g.axisym ? s[3] / s[0] : 0.0;
+  if (g.axisym && radius > 0) divV += ur / radius;
+#pragma unroll
+  for (int i = 0; i < 3; i++) st[i][i] += bulk * divV;
+  double pf[3] = {0, 0, 0};  // normalPrimFlux[numSpecies + i]
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      if (i < dim && j < dim) pf[i] += st[i][j] * nn[j];
+  if (g.axisym) {
+    double tau_tr = gr[3 + 0 * neq];
+    if (radius > 0) tau_tr -= ut / radius;
+    tau_tr *= visc;
+    const double tau_tz = visc * gr[3 + 1 * neq];
+    pf[2] += tau_tr * nn[0];
+    pf[2] += tau_tz * nn[1];
+  }
+  double q = 0.;
+  for (int d = 0; d < dim; d++) q -= k * gr[(1 + nvel) + d * neq] * nrm[d];
+  if (heat_prescribed) q = 0.;
+  for (int d = 0; d < nvel; d++) nf[d + 1] = pf[d];
+  for (int d = 0; d < nvel; d++) nf[nvel + 1] += pf[d] * (s[1 + d] / s[0]);
+  nf[nvel + 1] -= q;
 }
 
 // ---- dispatch on the working fluid (the reference's virtual GasMixture / TransportProperties calls) ----
@@ -122,8 +193,68 @@ __host__ __device__ __forceinline__ double gen_max_char_speed(const GenPhys &g, 
 __host__ __device__ __forceinline__ void gen_conv_flux(const GenPhys &g, const double *s, double *f) {
   if (g.fluid) mix_conv_flux(*g.mix, s, f); else dry_gen_conv_flux(g, s, f);
 }
-__host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double *f) {
-  if (g.fluid) mix_visc_flux(*g.mix, s, gr, f); else dry_gen_visc_flux(g, s, gr, f);
+__host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
+                                                       double *f) {
+  if (g.fluid) mix_visc_flux(*g.mix, s, gr, radius, f); else dry_gen_visc_flux(g, s, gr, radius, f);
+}
+__host__ __device__ __forceinline__ void gen_bdr_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
+                                                           const double *nrm, bool heat_prescribed, double *nf) {
+  if (g.fluid) mix_bdr_visc_flux(*g.mix, s, gr, radius, nrm, heat_prescribed, nf);
+  else dry_gen_bdr_visc_flux(g, s, gr, radius, nrm, heat_prescribed, nf);
+}
+__host__ __device__ __forceinline__ double gen_pressure(const GenPhys &g, const double *s) {
+  return g.fluid ? mix_pressure(*g.mix, s, nullptr) : dry_gen_pressure(g, s);
+}
+// GasMixture::ComputePressureFromPrimitives (equation_of_state.cpp:360-364, 988-1010)
+__host__ __device__ __forceinline__ double gen_pressure_from_prim(const GenPhys &g, const double *up) {
+  return g.fluid ? mix_pressure_from_prim(*g.mix, up) : g.dry.R * up[0] * up[1 + g.nvel];
+}
+// TransportProperties::GetViscosities (transport_properties.hpp:264-269, 305-309): visc[0] shear, visc[1] bulk
+__host__ __device__ __forceinline__ void gen_viscosities(const GenPhys &g, const double *U, const double *up, double *visc) {
+  if (g.fluid) {
+    mix_viscosities(*g.mix, U, up, visc);
+  } else {
+    const double temp = up[1 + g.nvel];
+    visc[0] = (g.dry.C1 * g.dry.visc_mult * pow(temp, 1.5) / (temp + g.dry.S0));
+    visc[1] = g.dry.bulk_visc_mult * visc[0];
+  }
+}
+// GasMixture::computeStagnationState (equation_of_state.cpp:100-116; DryAir :367-377)
+__host__ __device__ __forceinline__ void gen_stagnation_state(const GenPhys &g, const double *in, double *out) {
+  for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];
+  if (g.fluid) {
+    double ke = 0.0;
+    for (int d = 0; d < g.nvel; d++) ke += 0.5 * in[1 + d] * in[1 + d] / in[0];
+    for (int d = 0; d < g.nvel; d++) out[1 + d] = 0.;
+    out[1 + g.nvel] = in[1 + g.nvel] - ke;
+  } else {
+    const double p = dry_gen_pressure(g, in);
+    for (int d = 0; d < g.nvel; d++) out[1 + d] = 0.;
+    out[1 + g.nvel] = p / g.dry.gm1;
+  }
+}
+// GasMixture::computeStagnantStateWithTemp (DryAir :380-387, PerfectMixture :1596-1620)
+__host__ __device__ __forceinline__ void gen_stagnant_state_with_temp(const GenPhys &g, const double *in, double T, double *out) {
+  if (g.fluid) {
+    mix_stagnant_state_with_temp(*g.mix, in, T, out);
+  } else {
+    for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];
+    for (int d = 0; d < g.nvel; d++) out[1 + d] = 0.;
+    out[1 + g.nvel] = g.dry.R / g.dry.gm1 * in[0] * T;
+  }
+}
+// GasMixture::modifyEnergyForPressure (DryAir :402-411, PerfectMixture :1698-1741); in and out may alias
+__host__ __device__ __forceinline__ void gen_modify_energy_for_pressure(const GenPhys &g, const double *in, double *out, double p,
+                                                                        bool modifyElectronEnergy) {
+  if (g.fluid) {
+    mix_modify_energy_for_pressure(*g.mix, in, out, p, modifyElectronEnergy);
+  } else {
+    double ke = 0.;
+    for (int d = 0; d < g.nvel; d++) ke += in[1 + d] * in[1 + d];
+    ke *= 0.5 / in[0];
+    for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];
+    out[1 + g.nvel] = p / g.dry.gm1 + ke;
+  }
 }
 __host__ __device__ __forceinline__ int gen_num_active_species(const GenPhys &g) { return g.fluid ? g.mix->numActive : 0; }
 

@@ -27,7 +27,7 @@ constexpr double MIX_XEPS = 1.0e-30;            // TransportProperties::Xeps_
 struct MixParams {
   // PerfectMixture (equation_of_state.cpp:478-574)
   int numSpecies, numActive, ambipolar, twoTemp, iElectron, iBackground;
-  int dim, nvel, neq, iTh, iTe, eq_system;
+  int dim, nvel, neq, iTh, iTe, eq_system, axisym;
   double mw[MIX_MAXSP], charge[MIX_MAXSP], formE[MIX_MAXSP], molarCV[MIX_MAXSP], molarCP[MIX_MAXSP];
   // ConstantTransport (transport_properties.cpp:303-330)
   double visc, bulk, kh, ke, diff[MIX_MAXSP], mtFreq[MIX_MAXSP];
@@ -316,8 +316,8 @@ MIXBIG void mix_conv_flux(const MixParams &m, const double *s, double *f) {
   }
 }
 
-// Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335), non-axisymmetric, no SGS / sponge, ConstantTransport
-MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr, double *f) {
+// Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335), no SGS / sponge; radius = x[0] (axisymmetric terms only)
+MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, double *f) {
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (m.eq_system == 0) return;
@@ -357,8 +357,17 @@ MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr,
       st[i][j] = gu[j][i] + gu[i][j];
       st[i][j] *= visc;
     }
+  const double ur = m.axisym ? s[1] / s[0] : 0.0, ut = m.axisym ? s[3] / s[0] : 0.0;
+  if (m.axisym && radius > 0) divV += ur / radius;
 #pragma unroll
   for (int i = 0; i < 3; i++) st[i][i] += bulk * divV;
+  double tau_tr = 0, tau_tz = 0;
+  if (m.axisym) {  // fluxes.cpp:285-297
+    tau_tr = gr[3 + 0 * neq];
+    if (radius > 0) tau_tr -= ut / radius;
+    tau_tr *= visc;
+    tau_tz = visc * gr[3 + 1 * neq];
+  }
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     if (j < dim) {
@@ -373,8 +382,152 @@ MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr,
       for (int sp = 0; sp < ns; sp++) f[(1 + nvel) + j * neq] -= hsp[sp] * V[sp + j * ns];
     }
   }
+  if (m.axisym) {  // fluxes.cpp:295-296, 320-323
+    f[(1 + 2) + 0 * neq] = tau_tr;
+    f[(1 + 2) + 1 * neq] = tau_tz;
+    f[(1 + nvel) + 0 * neq] += ut * tau_tr;
+    f[(1 + nvel) + 1 * neq] += ut * tau_tz;
+  }
   for (int sp = 0; sp < m.numActive; sp++)
     for (int d = 0; d < dim; d++) f[(nvel + 2 + sp) + d * neq] = -s[nvel + 2 + sp] * V[sp + d * ns];
+}
+
+// Fluxes::ComputeBdrViscousFluxes (fluxes.cpp:344-504) as the wall conditions use it: every species' normal
+// diffusion flux is prescribed 0 (primFluxIdxs[0..numSpecies) = true, wallBC.cpp:66-110), and with heat_prescribed
+// (adiabatic wall) the heavy and -- two-temperature -- electron heat fluxes are prescribed 0 too.  nrm = unit normal.
+MIXBIG void mix_bdr_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
+                              bool heat_prescribed, double *nf) {
+  const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
+  for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
+  if (m.eq_system == 0) return;
+  const double visc = m.visc;
+  double bulk = m.bulk;
+  bulk -= 2. / 3. * visc;
+  double k = m.kh;
+  const double ke = m.ke;
+  // species part of normalPrimFlux is replaced by the prescribed zeros, so the species-enthalpy terms vanish
+  double gu[3][3], st[3][3], nn[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    nn[i] = i < dim ? nrm[i] : 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) gu[i][d] = (i < dim && d < dim) ? gr[(1 + i) + d * neq] : 0.0;
+  }
+  double divV = 0.;
+#pragma unroll
+  for (int i = 0; i < 3; i++) divV += gu[i][i];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      st[i][j] = gu[j][i] + gu[i][j];
+      st[i][j] *= visc;
+    }
+  const double ur = m.axisym ? s[1] / s[0] : 0.0, ut = m.axisym ? s[3] / s[0] : 0.0;
+  if (m.axisym && radius > 0) divV += ur / radius;
+#pragma unroll
+  for (int i = 0; i < 3; i++) st[i][i] += bulk * divV;
+  double pf[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      if (i < dim && j < dim) pf[i] += st[i][j] * nn[j];
+  if (m.axisym) {
+    double tau_tr = gr[3 + 0 * neq];
+    if (radius > 0) tau_tr -= ut / radius;
+    tau_tr *= visc;
+    const double tau_tz = visc * gr[3 + 1 * neq];
+    pf[2] += tau_tr * nn[0];
+    pf[2] += tau_tz * nn[1];
+  }
+  double qe = 0.0, qh = 0.0;
+  if (m.twoTemp) {
+    for (int d = 0; d < dim; d++) qe -= ke * gr[(neq - 1) + d * neq] * nrm[d];
+    qe += 0.0;  // speciesEnthalpies[electron] * (prescribed zero flux)
+  } else {
+    k += ke;
+  }
+  for (int d = 0; d < dim; d++) qh -= k * gr[(1 + nvel) + d * neq] * nrm[d];
+  if (heat_prescribed) {
+    qh = 0.0;
+    qe = 0.0;
+  }
+  (void)ns;
+  // species equations: -state * (prescribed zero diffusion flux)
+  for (int sp = 0; sp < m.numActive; sp++) nf[nvel + 2 + sp] = -s[nvel + 2 + sp] * 0.0;
+  for (int d = 0; d < nvel; d++) nf[d + 1] = pf[d];
+  for (int d = 0; d < nvel; d++) nf[nvel + 1] += pf[d] * (s[1 + d] / s[0]);
+  nf[nvel + 1] -= qh;
+  if (m.twoTemp) {
+    nf[nvel + 1] -= qe;
+    nf[neq - 1] = -qe;
+  }
+}
+
+// PerfectMixture::ComputePressureFromPrimitives (equation_of_state.cpp:988-1010)
+MIXFN double mix_pressure_from_prim(const MixParams &m, const double *Up) {
+  const double *n_sp = Up + m.nvel + 2;
+  double n_e = m.ambipolar ? mix_ambipolar_ne(m, n_sp) : n_sp[m.iElectron];
+  const double rhoB = mix_background_rho(m, Up[0], n_sp, n_e);
+  const double nB = rhoB / m.mw[m.iBackground];
+  const double T_h = Up[m.iTh], T_e = m.twoTemp ? Up[m.iTe] : Up[m.iTh];
+  return mix_pressure_base(m, n_sp, n_e, nB, T_h, T_e);
+}
+
+// ConstantTransport::GetViscosities (transport_properties.hpp:305-309)
+MIXFN void mix_viscosities(const MixParams &m, const double *, const double *, double *visc) {
+  visc[0] = m.visc;
+  visc[1] = m.bulk;
+}
+
+// PerfectMixture::computeStagnantStateWithTemp (equation_of_state.cpp:1596-1620)
+MIXBIG void mix_stagnant_state_with_temp(const MixParams &m, const double *in, double Temp, double *out) {
+  double n_sp[MIX_MAXSP];
+  mix_number_densities(m, in, n_sp);
+  for (int eq = 0; eq < m.neq; eq++) out[eq] = in[eq];
+  for (int d = 0; d < m.nvel; d++) out[1 + d] = 0.;
+  const double Ch = mix_heavies_cv(m, n_sp, n_sp[m.iBackground]);
+  const double Ue = n_sp[m.iElectron] * m.molarCV[m.iElectron] * Temp;
+  out[m.iTh] = Ch * Temp + Ue;
+  if (m.twoTemp) out[m.iTe] = Ue;
+  for (int sp = 0; sp < m.numSpecies - 2; sp++) out[m.iTh] += n_sp[sp] * m.formE[sp];
+}
+
+// PerfectMixture::modifyEnergyForPressure (equation_of_state.cpp:1698-1741); in and out may alias
+MIXBIG void mix_modify_energy_for_pressure(const MixParams &m, const double *in, double *out, double p, bool modifyElectronEnergy) {
+  double n_sp[MIX_MAXSP];
+  mix_number_densities(m, in, n_sp);
+  const double inTe = m.twoTemp ? in[m.iTe] : 0.0;
+  double ke = 0.0;
+  for (int d = 0; d < m.nvel; d++) ke += 0.5 * in[d + 1] * in[d + 1] / in[0];
+  double vk[MIX_MAXDIM];
+  for (int d = 0; d < m.nvel; d++) vk[d] = 0.5 * in[d + 1] * in[d + 1] / in[0];
+  for (int eq = 0; eq < m.neq; eq++) out[eq] = in[eq];
+  double Th = 0., pe = 0.0;
+  if (m.twoTemp && (!modifyElectronEnergy)) {
+    const double Te = inTe / (n_sp[m.iElectron] + 1.0e-30) / m.molarCV[m.iElectron];
+    pe = n_sp[m.iElectron] * MIX_RU * Te;
+  }
+  for (int sp = 0; sp < m.numSpecies; sp++) {
+    if (m.twoTemp && (!modifyElectronEnergy) && (sp == m.iElectron)) continue;
+    Th += n_sp[sp];
+  }
+  Th = (p - pe) / (Th * MIX_RU);
+  const double totalHeatCapacity = mix_heavies_cv(m, n_sp, n_sp[m.iBackground]);
+  double rE = totalHeatCapacity * Th;
+  double electronEnergy = 0.0;
+  if (m.twoTemp) {
+    electronEnergy = modifyElectronEnergy ? n_sp[m.iElectron] * m.molarCV[m.iElectron] * Th : inTe;
+    out[m.iTe] = electronEnergy;
+  } else {
+    electronEnergy = n_sp[m.iElectron] * m.molarCV[m.iElectron] * Th;
+  }
+  rE += electronEnergy;
+  for (int d = 0; d < m.nvel; d++) rE += vk[d];
+  (void)ke;
+  for (int sp = 0; sp < m.numSpecies - 2; sp++) rE += n_sp[sp] * m.formE[sp];
+  out[m.iTh] = rE;
 }
 
 // Chemistry::isElectronInvolvedAt (chemistry.hpp:136-138)

@@ -19,6 +19,18 @@
 
 namespace tpsb {
 
+// Boundary conditions of the generic path (BCintegrator's attribute maps, BCintegrator.cpp:64-125): same kinds and
+// types as the 3-D dry-air table (physics.cuh: BcDev), with the full inlet inputState (species included).
+constexpr int GEN_BC_NDATA = 12;
+struct GenBc {
+  int kind, type;  // kind: 0 inlet, 1 outlet, 2 wall; type: InletType / OutletType / WallType (dataStructures.hpp:168-196)
+  double d[GEN_BC_NDATA];
+};
+struct GenBcTable {
+  int nbc, use_bc_in_grad;
+  GenBc bc[MAX_BC];
+};
+
 struct GenArgs {
   int dim, np, dof, nqv, nqf, nfe, nv, neq, nvel, eq_system;
   int NE;
@@ -39,6 +51,10 @@ struct GenArgs {
   const int *el_face;   // [NE][nfe] face id of each local face
   const int *f_el1, *f_el2, *f_inf1, *f_inf2;
   const double *me_inv;  // [NE][dof] (me_diag) or [NE][dof][dof]
+  const double *me_inv_rad;  // axisymmetric: inverse of int r phi_i phi_j, applied in Mult (rhs_operator.cpp:441-445)
+  const double *xiN;     // [dof][dim] reference coordinates of the nodes
+  const int *f_bc;       // [NF] boundary face -> index into bct.bc, -1: no boundary condition / interior face
+  GenBcTable bct;
   // fields
   const double *U;
   double *Up, *gradUp, *y;
@@ -59,6 +75,11 @@ __device__ __forceinline__ void gen_jacobian(int dim, const double *v, const dou
   } else {
     hex_jacobian(v, xi[0], xi[1], xi[2], J);
   }
+}
+// x coordinate (the radius of an axisymmetric run) of reference point xi of a quadrilateral
+__device__ __forceinline__ double gen_quad_x(const double *v, const double *xi) {
+  const double x = xi[0], y = xi[1];
+  return (1 - x) * (1 - y) * v[0] + x * (1 - y) * v[2] + x * y * v[4] + (1 - x) * y * v[6];
 }
 __device__ __forceinline__ double gen_det(int dim, const double *J) {
   return dim == 2 ? J[0] * J[3] - J[2] * J[1] : det3(J);
@@ -92,6 +113,95 @@ __device__ __forceinline__ void gen_face_normal(int dim, const double *J, const 
   }
 }
 
+// BoundaryCondition::computeBdrPrimitiveStateForGradient (BoundaryCondition.cpp:55) / WallBC override
+// (wallBC.cpp:241-266): only an isothermal wall changes the state used by the BR1 jump.
+__device__ __forceinline__ void gen_bc_prim_for_gradient(const GenPhys &g, const GenBc &bc, const double *primIn, double *primBC) {
+  for (int eq = 0; eq < g.neq; eq++) primBC[eq] = primIn[eq];
+  if (bc.kind == 2 && bc.type == 3) {
+    for (int i = 0; i < g.nvel; i++) primBC[1 + i] = 0.0;
+    primBC[g.nvel + 1] = bc.d[0];
+  }
+}
+
+// BCintegrator::computeBdrFlux (BCintegrator.cpp:228-242) -> InletBC::subsonicReflectingDensityVelocity
+// (inletBC.cpp:729-756), OutletBC::subsonicReflectingPressure (outletBC.cpp:731-737), WallBC::computeINVwallFlux /
+// computeAdiabaticWallFlux / computeIsothermalWallFlux (wallBC.cpp:277-320, 430-510), any fluid, 2-D / 3-D /
+// axisymmetric.  gr[eq + d*neq]: interior gradients of the primitives; nor: CalcOrtho normal (area weighted, outward).
+__device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int use_bc_in_grad, const double *u1, const double *gr,
+                                         const double *nor, double radius, double *fx) {
+  const int neq = g.neq, dim = g.dim, nvel = g.nvel;
+  double s2[GEN_MAXEQ], viscF[GEN_MAXEQ * GEN_MAXDIM], wallViscF[GEN_MAXEQ], un[3];
+  double normN = 0.;
+  for (int d = 0; d < dim; d++) normN += nor[d] * nor[d];
+  const bool ns = g.dry.eq_system != 0 || (g.fluid && g.mix->eq_system != 0);
+  if (bc.kind == 0) {
+    const double pr = gen_pressure(g, u1);
+    for (int eq = 0; eq < neq; eq++) s2[eq] = u1[eq];
+    s2[0] = bc.d[0];
+    s2[1] = bc.d[0] * bc.d[1];
+    s2[2] = bc.d[0] * bc.d[2];
+    if (nvel == 3) s2[3] = bc.d[0] * bc.d[3];
+    const int nact = gen_num_active_species(g);
+    for (int sp = 0; sp < nact; sp++) s2[nvel + 2 + sp] = bc.d[4 + sp];
+    gen_modify_energy_for_pressure(g, s2, s2, pr, true);
+    gen_riemann_lf(g, u1, s2, nor, fx);
+    return;
+  }
+  if (bc.kind == 1) {
+    gen_modify_energy_for_pressure(g, u1, s2, bc.d[0], false);
+    gen_riemann_lf(g, u1, s2, nor, fx);
+    return;
+  }
+  if (bc.type == 0) {  // INV: mirror state
+    const double norm = sqrt(normN);
+    double vel[3] = {0, 0, 0};
+    for (int d = 0; d < nvel; d++) vel[d] = u1[1 + d] / u1[0];
+    for (int d = 0; d < dim; d++) un[d] = nor[d] / norm;
+    double vn = 0;
+    for (int d = 0; d < dim; d++) vn += vel[d] * un[d];
+    for (int eq = 0; eq < neq; eq++) s2[eq] = u1[eq];
+    s2[1] = u1[0] * (vel[0] - 2. * vn * un[0]);
+    s2[2] = u1[0] * (vel[1] - 2. * vn * un[1]);
+    if (dim == 3) s2[3] = u1[0] * (vel[2] - 2. * vn * un[2]);
+    if (nvel == 3 && dim == 2) s2[3] = u1[0] * vel[2];
+    gen_riemann_lf(g, u1, s2, nor, fx);
+    if (!ns) return;
+    gen_visc_flux(g, s2, gr, radius, viscF);
+    for (int eq = 0; eq < neq; eq++) {
+      wallViscF[eq] = 0.;
+      for (int d = 0; d < dim; d++) wallViscF[eq] += viscF[eq + d * neq] * nor[d];
+    }
+    gen_visc_flux(g, u1, gr, radius, viscF);
+  } else {
+    const double isq = 1. / sqrt(normN);
+    for (int d = 0; d < dim; d++) un[d] = nor[d] * isq;
+    if (bc.type == 2) {  // VISC_ADIAB: stagnation state
+      gen_stagnation_state(g, u1, s2);
+      gen_riemann_lf(g, u1, s2, nor, fx);
+      if (!ns) return;
+      gen_bdr_visc_flux(g, s2, gr, radius, un, true, wallViscF);
+    } else {  // VISC_ISOTH
+      if (use_bc_in_grad) {
+        for (int eq = 0; eq < neq; eq++) s2[eq] = u1[eq];
+        for (int i = 0; i < nvel; i++) s2[i + 1] *= -1.0;
+      } else {
+        gen_stagnant_state_with_temp(g, u1, bc.d[0], s2);
+      }
+      gen_riemann_lf(g, u1, s2, nor, fx);
+      if (!ns) return;
+      gen_stagnant_state_with_temp(g, u1, bc.d[0], s2);
+      gen_bdr_visc_flux(g, s2, gr, radius, un, false, wallViscF);
+    }
+    const double nm = sqrt(normN);
+    for (int eq = 0; eq < neq; eq++) wallViscF[eq] *= nm;
+    gen_visc_flux(g, u1, gr, radius, viscF);
+  }
+  for (int eq = 1; eq < neq; eq++) {
+    fx[eq] -= 0.5 * wallViscF[eq];
+    for (int d = 0; d < dim; d++) fx[eq] -= 0.5 * viscF[eq + d * neq] * nor[d];
+  }
+}
+
 __global__ void gen_prim_kernel(GenArgs a) {
   const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (n >= a.N) return;
@@ -102,16 +212,16 @@ __global__ void gen_prim_kernel(GenArgs a) {
 }
 
 // y_el = Me^-1 z_el for nc interleaved columns: z[k*nc + c] -> out(global, byNODES with component stride cstride)
-__device__ __forceinline__ void gen_apply_minv(const GenArgs &a, int e, const double *z, int nc, double *out,
-                                               long long cstride) {
+__device__ __forceinline__ void gen_apply_minv(const GenArgs &a, const double *me_inv, int e, const double *z, int nc,
+                                               double *out, long long cstride) {
   const int dof = a.dof;
   for (int t = threadIdx.x; t < dof * nc; t += blockDim.x) {
     const int j = t % dof, c = t / dof;
     double v;
     if (a.me_diag) {
-      v = a.me_inv[static_cast<long long>(e) * dof + j] * z[j * nc + c];
+      v = me_inv[static_cast<long long>(e) * dof + j] * z[j * nc + c];
     } else {
-      const double *mi = a.me_inv + (static_cast<long long>(e) * dof + j) * dof;
+      const double *mi = me_inv + (static_cast<long long>(e) * dof + j) * dof;
       v = 0;
       for (int k = 0; k < dof; k++) v += mi[k] * z[k * nc + c];
     }
@@ -166,12 +276,15 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
   for (int lf = 0; lf < a.nfe; lf++) {
     const int f = a.el_face[e * a.nfe + lf];
     const int e1 = a.f_el1[f], e2 = a.f_el2[f];
-    if (e2 < 0) continue;  // boundary face: Up2 = Up1 (no BC state built on this path yet)
+    const bool bdr = e2 < 0;
+    // boundary face: Up2 = Up1 (zero jump) unless useBCinGrad and a boundary condition supplies a state
+    // (faceGradientIntegration.cpp:93-115)
+    if (bdr && !(a.bct.use_bc_in_grad && a.f_bc[f] >= 0)) continue;
     const bool first = (e1 == e);
     const int code_own = gen_code(dim, first ? a.f_inf1[f] : a.f_inf2[f]);
-    const int code_oth = gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
+    const int code_oth = bdr ? code_own : gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
     const int code1 = gen_code(dim, a.f_inf1[f]);
-    const int eo = first ? e2 : e1;
+    const int eo = bdr ? e1 : (first ? e2 : e1);
     const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
     for (int q = threadIdx.x; q < a.nqf; q += blockDim.x) {
       double J[9], nor[3];
@@ -180,6 +293,20 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
       const double sg = (first ? 1.0 : -1.0) * a.wF[q];
       const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
       const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
+      if (bdr) {
+        double own[GEN_MAXEQ], pbc[GEN_MAXEQ];
+        for (int eq = 0; eq < neq; eq++) {
+          double v = 0;
+          for (int k = 0; k < dof; k++) v += po[k] * sUp[eq * dof + k];
+          own[eq] = v;
+        }
+        gen_bc_prim_for_gradient(a.phys, a.bct.bc[a.f_bc[f]], own, pbc);
+        for (int eq = 0; eq < neq; eq++) {
+          const double jump = 0.5 * (pbc[eq] - own[eq]);
+          for (int d = 0; d < dim; d++) sQ[q * nc + eq + d * neq] = jump * nor[d] * sg;
+        }
+        continue;
+      }
       for (int eq = 0; eq < neq; eq++) {
         double own = 0, oth = 0;
         const double *un = a.Up + static_cast<long long>(eo) * dof + eq * N;
@@ -202,7 +329,7 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
     __syncthreads();
   }
   // gradUp[e*dof + j + eq*N + d*neq*N]: component c = eq + d*neq has stride N
-  gen_apply_minv(a, e, sRhs, nc, a.gradUp, N);
+  gen_apply_minv(a, a.me_inv, e, sRhs, nc, a.gradUp, N);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,7 +360,8 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     for (int c = 0; c < nc; c++) gr[c] = sG[c * dof + k];
     gen_conv_flux(a.phys, s, fc);
     if (a.eq_system != 0) {
-      gen_visc_flux(a.phys, s, gr, fv);
+      const double radius = a.phys.axisym ? gen_quad_x(vx, a.xiN + k * dim) : -1.0;  // nodal coordinate (GetFlux :526-528)
+      gen_visc_flux(a.phys, s, gr, radius, fv);
       for (int c = 0; c < nc; c++) fc[c] -= fv[c];
     }
     for (int c = 0; c < nc; c++) sF[k * nc + c] = fc[c];
@@ -246,7 +374,8 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     double J[9], A[9];
     gen_jacobian(dim, vx, a.xiV + q * dim, J);
     gen_adj(dim, J, A);
-    const double w = a.wV[q];
+    // shape *= ip.weight [* radius]  (domain_integrator.cpp:71-90)
+    const double w = a.phys.axisym ? a.wV[q] * gen_quad_x(vx, a.xiV + q * dim) : a.wV[q];
     const double *ph = a.phiV + static_cast<long long>(q) * dof;
     for (int eq = 0; eq < neq; eq++) {
       double fq[GEN_MAXDIM] = {0, 0, 0};
@@ -274,20 +403,42 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   for (int lf = 0; lf < a.nfe; lf++) {
     const int f = a.el_face[e * a.nfe + lf];
     const int e1 = a.f_el1[f], e2 = a.f_el2[f];
-    if (e2 < 0) continue;
+    const bool bdr = e2 < 0;
+    if (bdr && a.f_bc[f] < 0) continue;  // no boundary integrator registered for this attribute
     const bool first = (e1 == e);
     const int code_own = gen_code(dim, first ? a.f_inf1[f] : a.f_inf2[f]);
-    const int code_oth = gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
+    const int code_oth = bdr ? code_own : gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
     const int code1 = gen_code(dim, a.f_inf1[f]);
-    const int eo = first ? e2 : e1;
+    const int eo = bdr ? e1 : (first ? e2 : e1);
     const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
     for (int q = threadIdx.x; q < a.nqf; q += blockDim.x) {
       double J[9], nor[3];
-      gen_jacobian(dim, v1, a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim, J);
+      const double *xi1 = a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim;
+      gen_jacobian(dim, v1, xi1, J);
       gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
+      const double radius = a.phys.axisym ? gen_quad_x(v1, xi1) : -1.0;  // Tr.Transform(ip)[0]
       const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
       const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
       double uo[GEN_MAXEQ], un[GEN_MAXEQ], go[GEN_MAXEQ * GEN_MAXDIM], gn[GEN_MAXEQ * GEN_MAXDIM];
+      if (bdr) {  // BCintegrator::AssembleFaceVector (BCintegrator.cpp:295-441)
+        for (int eq = 0; eq < neq; eq++) {
+          double x = 0;
+          for (int k = 0; k < dof; k++) x += po[k] * sU[eq * dof + k];
+          const int sp = eq - a.nvel - 2;
+          uo[eq] = (sp >= 0 && sp < nact) ? fmax(x, 0.0) : x;
+        }
+        for (int c = 0; c < nc; c++) {
+          double x = 0;
+          for (int k = 0; k < dof; k++) x += po[k] * sG[c * dof + k];
+          go[c] = x;
+        }
+        double fxb[GEN_MAXEQ];
+        for (int eq = 0; eq < neq; eq++) fxb[eq] = 0.0;
+        gen_bc_flux(a.phys, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb);
+        const double sgb = -(a.phys.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
+        for (int eq = 0; eq < neq; eq++) sQ[q * nc + eq] = sgb * fxb[eq];
+        continue;
+      }
       for (int eq = 0; eq < neq; eq++) {
         double x = 0, y = 0;
         const double *src = a.U + static_cast<long long>(eo) * dof + eq * N;
@@ -317,15 +468,16 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       gen_riemann_lf(a.phys, u1, u2, nor, fx);
       if (a.eq_system != 0) {
         double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM];
-        gen_visc_flux(a.phys, u1, g1, f1);
-        gen_visc_flux(a.phys, u2, g2, f2);
+        gen_visc_flux(a.phys, u1, g1, radius, f1);
+        gen_visc_flux(a.phys, u2, g2, radius, f2);
         for (int eq = 0; eq < neq; eq++) {
           double v = 0;
           for (int d = 0; d < dim; d++) v += (-0.5 * (f1[eq + d * neq] + f2[eq + d * neq])) * nor[d];
           fx[eq] += v;
         }
       }
-      const double sg = (first ? -1.0 : 1.0) * a.wF[q];  // elvect1 -= phi1 Fhat w ; elvect2 += phi2 Fhat w
+      // elvect1 -= phi1 Fhat w ; elvect2 += phi2 Fhat w ; axisymmetric: fluxN *= radius (face_integrator.cpp:344-350)
+      const double sg = (first ? -1.0 : 1.0) * (a.phys.axisym ? a.wF[q] * radius : a.wF[q]);
       for (int eq = 0; eq < neq; eq++) sQ[q * nc + eq] = sg * fx[eq];
     }
     __syncthreads();
@@ -338,7 +490,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     }
     __syncthreads();
   }
-  gen_apply_minv(a, e, sZ, neq, a.y, N);
+  gen_apply_minv(a, a.phys.axisym ? a.me_inv_rad : a.me_inv, e, sZ, neq, a.y, N);
 }
 
 // SourceTerm::updateTerms (source_term.cpp:62-255): node-wise plasma sources added to y AFTER Me^-1
@@ -355,6 +507,54 @@ __global__ void gen_source_kernel(GenArgs a, const double *Usol) {
   }
   mix_source(*a.phys.mix, Un, upn, gr, src);
   for (int eq = 0; eq < a.neq; eq++) a.y[n + eq * a.N] += src[eq];
+}
+
+// AxisymmetricSource::updateTerms (forcing_terms.cpp:255-380): (p + rho u_t^2 - tau_tt)/r on the r-momentum and
+// (-rho u_r u_t + tau_tr)/r on the theta-momentum, node-wise after Me^-1, registered after SourceTerm
+// (rhs_operator.cpp:126-160).  Reads U_ (the solution grid function), Up and gradUp; the 1/r is unguarded like the
+// reference's (meshes keep their nodes off the axis: Gauss-Legendre nodes are interior).
+__global__ void gen_axisym_source_kernel(GenArgs a, const double *Usol) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  const int neq = a.neq;
+  double U[GEN_MAXEQ], Up[GEN_MAXEQ], gr[GEN_MAXEQ * GEN_MAXDIM];
+  for (int eq = 0; eq < neq; eq++) {
+    U[eq] = Usol[n + eq * a.N];
+    Up[eq] = a.Up[n + eq * a.N];
+    for (int d = 0; d < a.dim; d++) gr[eq + d * neq] = a.gradUp[n + eq * a.N + d * neq * a.N];
+  }
+  const int nact = gen_num_active_species(a.phys);
+  for (int sp = 0; sp < nact; sp++) {
+    const int eq = 3 + 2 + sp;
+    U[eq] = fmax(U[eq], 0.0);
+    Up[eq] = fmax(Up[eq], 0.0);
+  }
+  const long long e = n / a.dof;
+  const int k = static_cast<int>(n % a.dof);
+  const double radius = gen_quad_x(a.vx + e * a.nv * a.dim, a.xiN + k * a.dim);
+  const double rho = Up[0], ur = Up[1], ut = Up[3];
+  const double pressure = gen_pressure_from_prim(a.phys, Up);
+  const double rurut = rho * ur * ut, rutut = rho * ut * ut;
+  double tau_tt, tau_tr;
+  if (a.eq_system == 0) {
+    tau_tt = tau_tr = 0.0;
+  } else {
+    const double ur_r = gr[1 + 0 * neq], uz_z = gr[2 + 1 * neq], ut_r = gr[3 + 0 * neq];
+    double visc_vec[2];
+    gen_viscosities(a.phys, U, Up, visc_vec);
+    const double visc = visc_vec[0];
+    double bulkVisc = visc_vec[1];
+    bulkVisc -= 2. / 3. * visc;
+    double divV = ur_r + uz_z;
+    if (radius > 0) divV += ur / radius;
+    tau_tt = (radius > 0) ? 2.0 * ur / radius * visc : 0.0;
+    tau_tt += bulkVisc * divV;
+    tau_tr = ut_r;
+    if (radius > 0) tau_tr -= ut / radius;
+    tau_tr *= visc;
+  }
+  a.y[n + 1 * a.N] += (pressure + rutut - tau_tt) / radius;
+  a.y[n + 3 * a.N] += (-rurut + tau_tr) / radius;
 }
 
 // test hook: the per-point physics on arrays of points (point-major: U[i*neq + eq], gradUp[i*neq*dim + eq + d*neq])
@@ -374,7 +574,7 @@ __global__ void gen_point_eval_kernel(GenArgs a, int which, int n, const double 
     for (int c = 0; c < nc; c++) out[i * nc + c] = f[c];
   } else if (which == 3) {
     for (int c = 0; c < nc; c++) gr[c] = aux[i * nc + c];
-    gen_visc_flux(a.phys, s, gr, f);
+    gen_visc_flux(a.phys, s, gr, 1.0, f);  // probe radius 1 (axisymmetric terms)
     for (int c = 0; c < nc; c++) out[i * nc + c] = f[c];
   } else if (which == 4 && a.phys.fluid) {
     for (int c = 0; c < nc; c++) gr[c] = aux[i * nc + c];

@@ -247,7 +247,8 @@ bool g_spd_inverse(std::vector<double> &A, int n) {
 }
 
 // Everything the generic kernels need; returns an error string (empty on success).
-std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys) {
+std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys,
+                           const tpsb_bc_set *bcs) {
   const int dim = maps->dim, p = space->order, np = p + 1, NE = c->NE, NF = maps->num_faces;
   const int nv = 1 << dim, nfe = 2 * dim, nori = dim == 3 ? 8 : 2;
   int dof = 1;
@@ -281,6 +282,12 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
     wV[q] = w;
     g_shape(dim, np, xn, xi, &phiV[static_cast<size_t>(q) * dof], &dphiV[static_cast<size_t>(q) * dof * dim]);
   }
+  std::vector<double> xiN(static_cast<size_t>(dof) * dim);  // reference coordinates of the nodes (x fastest)
+  for (int n = 0; n < dof; n++) {
+    const int ni[3] = {n % np, (n / np) % np, n / (np * np)};
+    for (int d = 0; d < dim; d++) xiN[static_cast<size_t>(n) * dim + d] = xn[ni[d]];
+  }
+  const bool axisym = dim == 2 && space->nvel == 3;
   const int ncode = nfe * nori;
   std::vector<double> phiF(static_cast<size_t>(ncode) * nqf * dof), xiF(static_cast<size_t>(ncode) * nqf * dim), dlocF(static_cast<size_t>(ncode) * dim * (dim - 1)), wF(nqf);
   for (int q = 0; q < nqf; q++) wF[q] = dim == 3 ? wf[q % nqf1] * wf[q / nqf1] : wf[q];
@@ -315,13 +322,19 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   // mass matrices (rhs_operator.cpp:173-189): diagonal when nodes and volume rule coincide
   const bool diag = space->basis_type == 0 && space->int_rule_type == 0;
   std::vector<double> me(static_cast<size_t>(NE) * (diag ? dof : dof * dof));
-  std::vector<double> M(static_cast<size_t>(dof) * dof);
+  // axisymmetric: the inverse of M_ij = int r phi_i phi_j as well (Me_inv_rad, rhs_operator.cpp:191-205)
+  std::vector<double> me_rad(axisym ? me.size() : 0);
+  std::vector<double> M(static_cast<size_t>(dof) * dof), MR(static_cast<size_t>(dof) * dof);
   for (int e = 0; e < NE; e++) {
     const double *v = &maps->elem_vertices[static_cast<size_t>(e) * nv * dim];
     std::fill(M.begin(), M.end(), 0.0);
+    std::fill(MR.begin(), MR.end(), 0.0);
     for (int q = 0; q < nqv; q++) {
       double J[9];
       const double *xi = &xiV[static_cast<size_t>(q) * dim];
+      double radius = 1.0;
+      if (axisym)  // x coordinate of the quadrature point (bilinear map, MFEM quad vertex order)
+        radius = (1 - xi[0]) * (1 - xi[1]) * v[0] + xi[0] * (1 - xi[1]) * v[2] + xi[0] * xi[1] * v[4] + (1 - xi[0]) * xi[1] * v[6];
       if (dim == 2) {
         for (int i = 0; i < 2; i++) {
           J[i] = (1 - xi[1]) * (v[2 + i] - v[i]) + xi[1] * (v[4 + i] - v[6 + i]);
@@ -343,23 +356,55 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
       const double *ph = &phiV[static_cast<size_t>(q) * dof];
       if (diag) {
         for (int i = 0; i < dof; i++) M[static_cast<size_t>(i) * dof + i] += wd * ph[i] * ph[i];
+        if (axisym)
+          for (int i = 0; i < dof; i++) MR[static_cast<size_t>(i) * dof + i] += wd * radius * ph[i] * ph[i];
       } else {
         for (int i = 0; i < dof; i++)
           for (int j = 0; j < dof; j++) M[static_cast<size_t>(i) * dof + j] += wd * ph[i] * ph[j];
+        if (axisym)
+          for (int i = 0; i < dof; i++)
+            for (int j = 0; j < dof; j++) MR[static_cast<size_t>(i) * dof + j] += wd * radius * ph[i] * ph[j];
       }
     }
     if (diag) {
       for (int i = 0; i < dof; i++) me[static_cast<size_t>(e) * dof + i] = 1.0 / M[static_cast<size_t>(i) * dof + i];
+      if (axisym)
+        for (int i = 0; i < dof; i++) me_rad[static_cast<size_t>(e) * dof + i] = 1.0 / MR[static_cast<size_t>(i) * dof + i];
     } else {
       if (!g_spd_inverse(M, dof)) return "mass matrix is not positive definite";
       std::copy(M.begin(), M.end(), &me[static_cast<size_t>(e) * dof * dof]);
+      if (axisym) {
+        if (!g_spd_inverse(MR, dof)) return "radius-weighted mass matrix is not positive definite (element on r <= 0?)";
+        std::copy(MR.begin(), MR.end(), &me_rad[static_cast<size_t>(e) * dof * dof]);
+      }
     }
+  }
+  // boundary faces -> index into the boundary-condition table (BCintegrator's attribute maps, BCintegrator.cpp:64-125)
+  std::vector<int> f_bc(NF, -1);
+  GenBcTable gbt;
+  memset(&gbt, 0, sizeof(gbt));
+  if (bcs && bcs->num_bcs > 0) {
+    gbt.nbc = bcs->num_bcs, gbt.use_bc_in_grad = bcs->use_bc_in_grad ? 1 : 0;
+    for (int i = 0; i < bcs->num_bcs; i++) {
+      gbt.bc[i].kind = bcs->bcs[i].kind, gbt.bc[i].type = bcs->bcs[i].type;
+      for (int k = 0; k < TPSB_BC_NDATA; k++) gbt.bc[i].d[k] = bcs->bcs[i].data[k];
+    }
+    if (maps->face_attr)
+      for (int f = 0; f < NF; f++)
+        if (maps->face_el2[f] < 0)
+          for (int i = 0; i < bcs->num_bcs; i++)
+            if (bcs->bcs[i].attr == maps->face_attr[f]) {
+              f_bc[f] = i;
+              break;
+            }
   }
   GenArgs &g = c->gen;
   memset(&g, 0, sizeof(g));
   g.dim = dim, g.np = np, g.dof = dof, g.nqv = nqv, g.nqf = nqf, g.nfe = nfe, g.nv = nv;
   g.neq = space->num_equation, g.nvel = space->nvel, g.NE = NE, g.N = static_cast<long long>(NE) * dof, g.me_diag = diag ? 1 : 0;
   g.phys.dim = dim, g.phys.nvel = space->nvel, g.phys.neq = space->num_equation, g.phys.dry = c->phys;
+  g.phys.axisym = axisym ? 1 : 0;
+  g.bct = gbt;
   g.eq_system = phys->eq_system;
   g.phys.fluid = 0, g.phys.mix = nullptr;
   std::vector<MixParams> mixv;
@@ -372,6 +417,7 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
     m.iBackground = m.numSpecies - 1, m.iElectron = m.numSpecies - 2;                   // :137-146
     m.dim = dim, m.nvel = space->nvel, m.neq = space->num_equation, m.iTh = space->nvel + 1, m.iTe = space->num_equation - 1;
     m.eq_system = phys->eq_system;
+    m.axisym = axisym ? 1 : 0;
     for (int sp = 0; sp < m.numSpecies; sp++) {
       m.mw[sp] = pm.mw[sp], m.charge[sp] = pm.charge[sp], m.formE[sp] = pm.formation_energy[sp];
       m.molarCV[sp] = pm.molar_cv[sp] * MIX_RU;                                         // equation_of_state.cpp:568-571
@@ -413,6 +459,9 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   if (ce == cudaSuccess) ce = g_upload(c, &g.f_inf1, fi1);
   if (ce == cudaSuccess) ce = g_upload(c, &g.f_inf2, fi2);
   if (ce == cudaSuccess) ce = g_upload(c, &g.me_inv, me);
+  if (ce == cudaSuccess && axisym) ce = g_upload(c, &g.me_inv_rad, me_rad);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.xiN, xiN);
+  if (ce == cudaSuccess) ce = g_upload(c, &g.f_bc, f_bc);
   if (ce == cudaSuccess && !mixv.empty()) ce = g_upload(c, &g.phys.mix, mixv);
   const size_t nb = static_cast<size_t>(g.N) * sizeof(double);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * g.neq);
@@ -453,7 +502,9 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (space->basis_type < 0 || space->basis_type > 1 || space->int_rule_type < 0 || space->int_rule_type > 1)
     return fail(ctx, TPSB_EINVAL, "basisType / integrationRule must be 0 (Gauss-Legendre) or 1 (Gauss-Lobatto)");
   if (space->order < 1 || space->order > 3) return fail(ctx, TPSB_ENOTIMPL, "order must be 1..3");
-  if (space->nvel != maps->dim) return fail(ctx, TPSB_ENOTIMPL, "axisymmetric runs (nvel = 3 in 2-D) are not built yet");
+  // config.isAxisymmetric(): a 2-D (r, z) mesh carrying three velocity components
+  if (space->nvel != maps->dim && !(maps->dim == 2 && space->nvel == 3))
+    return fail(ctx, TPSB_EINVAL, "nvel must equal dim (or 3 on a 2-D mesh for axisymmetric runs)");
   if (phys->fluid == TPSB_DRY_AIR) {
     if (space->num_equation != space->nvel + 2) return fail(ctx, TPSB_EINVAL, "dry air has num_equation = nvel + 2");
   } else if (phys->fluid == TPSB_USER_DEFINED) {
@@ -475,9 +526,6 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (const char *pth = getenv("TPSB_PATH")) want_generic = want_generic || strcmp(pth, "generic") == 0;
   if (want_generic) {
     if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
-    for (int f = 0; f < maps->num_faces; f++)
-      if (maps->face_el2 && maps->face_el2[f] < 0 && bcs && bcs->num_bcs > 0)
-        return fail(ctx, TPSB_ENOTIMPL, "boundary conditions are not built on the generic (2-D / Gauss-Lobatto) path yet");
   }
   if (phys->eq_system != TPSB_EULER && phys->eq_system != TPSB_NS)
     return fail(ctx, TPSB_ENOTIMPL, "equation system %d not built", phys->eq_system);
@@ -500,6 +548,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
       bct.bc[i].kind = b.kind;
       bct.bc[i].type = b.type;
       for (int k = 0; k < 4; k++) bct.bc[i].d[k] = b.data[k];
+      if (b.kind == TPSB_BC_INLET && phys->fluid == TPSB_USER_DEFINED && !want_generic)
+        return fail(ctx, TPSB_EINVAL, "mixture inlets run on the generic path");
     }
   }
   int ndev = 0;
@@ -546,7 +596,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     c->nd = 1;
     for (int d = 0; d < maps->dim; d++) c->nd *= c->np;
     c->N = static_cast<long long>(c->NE) * c->nd;
-    const std::string err = create_generic(c, maps, space, phys);
+    const std::string err = create_generic(c, maps, space, phys, bcs);
     if (!err.empty()) {
       tpsb_destroy(c);
       return fail(nullptr, TPSB_EINVAL, "%s", err.c_str());
@@ -1216,6 +1266,10 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   if (g.phys.fluid) {  // forcing terms are added after Me^-1 (rhs_operator.cpp:451-461)
     ProfScope ps(c, K_RESID);
     gen_source_kernel<<<static_cast<unsigned>((g.N + 127) / 128), 128, 0, c->stream>>>(g, c->sol_view ? c->sol_view : d_x);
+  }
+  if (g.phys.axisym) {  // AxisymmetricSource, registered after SourceTerm (rhs_operator.cpp:159-160)
+    ProfScope ps(c, K_RESID);
+    gen_axisym_source_kernel<<<static_cast<unsigned>((g.N + 127) / 128), 128, 0, c->stream>>>(g, c->sol_view ? c->sol_view : d_x);
   }
   CU(cudaGetLastError());
   return TPSB_OK;
