@@ -79,7 +79,8 @@ typedef struct {
   double charge[TPSB_MAX_SPECIES];           /* GasParams::SPECIES_CHARGES                     */
   double formation_energy[TPSB_MAX_SPECIES]; /* GasParams::FORMATION_ENERGY [J/mol]            */
   double molar_cv[TPSB_MAX_SPECIES];         /* perfect_mixture/constant_molar_cv, units of R  */
-  /* transport_model = constant (src/transport_properties.cpp:303-448); TransportModel value 2 */
+  /* TransportModel value (src/dataStructures.hpp:80-88): 2 constant (src/transport_properties.cpp:303-448),
+   * 0 argon_minimal (fields at the end of this struct)                                              */
   int transport_model;
   double viscosity, bulk_viscosity, thermal_conductivity, electron_thermal_conductivity;
   double diffusivity[TPSB_MAX_SPECIES], mt_freq[TPSB_MAX_SPECIES];
@@ -91,6 +92,13 @@ typedef struct {
   double reaction_energy[TPSB_MAX_REACTIONS];
   double equilibrium_params[TPSB_MAX_REACTIONS][3];  /* A, b, E of K_eq = A T^b exp(-E/T)     */
   int reactant_stoich[TPSB_MAX_REACTIONS][TPSB_MAX_SPECIES], product_stoich[TPSB_MAX_REACTIONS][TPSB_MAX_SPECIES];
+  /* transport_model = argon_minimal (TransportModel value 0): GasMinimalTransport, Chapman-Enskog transport of the
+   * ternary mixture [Ar.+1, E, Ar] from collision integrals (src/gas_transport.cpp:42-870,
+   * src/collision_integrals.cpp:53-201; GasTransportInput src/dataStructures.hpp:644-666).                          */
+  int third_order_k_electron;      /* argon_transport/third_order_thermal_conductivity                              */
+  int multiply;                    /* artificial multipliers on (argonMinimal.multipliers.ini)                       */
+  double flux_trns_multiplier[4];  /* viscosity, bulk viscosity, heavy / electron thermal conductivity               */
+  double mf_freq_multiplier, diff_mult, mobil_mult;
 } tpsb_plasma_models;
 
 typedef struct {

@@ -41,6 +41,9 @@ struct OrcPlasma {
   double reaction_energy[34];
   double equilibrium_params[34][3];
   int reactant_stoich[34][8], product_stoich[34][8];
+  // transport_model == 0 (ARGON_MINIMAL): GasTransportInput scalars (src/dataStructures.hpp:644-666)
+  int third_order_k_electron, multiply;
+  double flux_trns_multiplier[4], mf_freq_multiplier, diff_mult, mobil_mult;
 };
 // One boundary condition of BCintegrator's attribute maps (src/BCintegrator.cpp:64-125).
 // kind: 0 inlet, 1 outlet, 2 wall; type: the reference's InletType / OutletType / WallType value

@@ -5,9 +5,12 @@
 // (equation_of_state.cpp, transport_properties.cpp, fluxes.cpp, riemann_solver.cpp, ...)
 // against the header stub in oracle/refstub/.  Built only into oracle/_ref/ by
 // oracle/Makefile; the resulting shared object travels to the GPU box, the sources do not.
+#include <cstring>
+
 #include "chemistry.hpp"
 #include "equation_of_state.hpp"
 #include "fluxes.hpp"
+#include "gas_transport.hpp"
 #include "riemann_solver.hpp"
 #include "transport_properties.hpp"
 
@@ -91,7 +94,7 @@ class DryAirRef : public Physics {
 class MixtureRef : public Physics {
   int dim_, nvel_, neq_;
   PerfectMixture *mix_;
-  ConstantTransport *trans_;
+  TransportProperties *trans_;
   Fluxes *flux_;
   RiemannSolverTPS *rs_;
   Chemistry *chem_ = nullptr;
@@ -124,7 +127,21 @@ class MixtureRef : public Physics {
       ct.mtFreq[sp] = sp < pm.num_species ? pm.mt_freq[sp] : 0.0;
     }
     ct.electronIndex = pm.num_species - 2;
-    trans_ = new ConstantTransport(mix_, ct);  // transport_properties.cpp:303
+    if (pm.transport_model == 0) {  // ARGON_MINIMAL: GasMinimalTransport (gas_transport.cpp:42)
+      GasTransportInput gi;
+      memset(&gi, 0, sizeof(gi));
+      gi.gas = Ar;
+      gi.ionIndex = 0, gi.electronIndex = pm.num_species - 2, gi.neutralIndex = pm.num_species - 1;
+      gi.neutralIndex2 = -1, gi.ionIndex2 = -1;
+      gi.thirdOrderkElectron = pm.third_order_k_electron != 0;
+      gi.multiply = pm.multiply != 0;
+      for (int t = 0; t < 4; t++) gi.fluxTrnsMultiplier[t] = pm.flux_trns_multiplier[t];
+      gi.spcsTrnsMultiplier[0] = pm.mf_freq_multiplier;
+      gi.diffMult = pm.diff_mult, gi.mobilMult = pm.mobil_mult;
+      trans_ = new GasMinimalTransport(mix_, gi);
+    } else {
+      trans_ = new ConstantTransport(mix_, ct);  // transport_properties.cpp:303
+    }
     const Equations eqs = static_cast<Equations>(p.eq_system);
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
     flux_ = new Fluxes(mix_, eqs, trans_, neq, dim, axisym);

@@ -43,3 +43,26 @@ def smooth_primitives(xy, seed=20261018):
                    1500 + 500 * np.sin(x + y)], axis=1)
     rng = np.random.default_rng(seed)
     return up * (1 + 0.01 * rng.uniform(-1, 1, up.shape))
+
+
+def argon_minimal_dict(third_order=False, multipliers=None, two_temperature=True, ambipolar=True):
+    """Ternary argon with transport_model = argon_minimal (GasMinimalTransport: collision-integral transport,
+    test/inputs/argonMinimal*.ini) and the physical electron mass."""
+    me = 5.48579908782496e-7
+    d = ternary_dict(ambipolar=ambipolar, two_temperature=two_temperature)
+    d["species"][0]["mw"], d["species"][1]["mw"] = MW_AR - me, me
+    d["transport_model"] = "argon_minimal"
+    d["third_order_k_electron"] = third_order
+    if multipliers:
+        d["multipliers"] = multipliers
+    return d
+
+
+def hot_primitives(xy, seed=20261018):
+    """Weakly ionised hot argon: T_h ~ 9000 K, T_e ~ 11000 K, n_ion ~ 0.02 mol/m^3, rho ~ 0.05 kg/m^3 (n_Ar ~ 1.3)."""
+    x, y = xy[:, 0], xy[:, 1]
+    up = np.stack([0.052 + 0.004 * np.sin(x) * np.cos(y), 200 * np.sin(x) * np.cos(y) + 50, -200 * np.cos(x) * np.sin(y) + 20,
+                   9000 + 800 * np.cos(x) * np.cos(2 * y), 0.02 + 0.008 * np.sin(2 * x) * np.sin(y),
+                   11000 + 1500 * np.sin(x + y)], axis=1)
+    rng = np.random.default_rng(seed)
+    return up * (1 + 0.01 * rng.uniform(-1, 1, up.shape))

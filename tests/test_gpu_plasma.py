@@ -86,3 +86,62 @@ def test_source_term_reads_the_solution_vector_not_the_stage_vector(lib_built, o
     y2 = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
     assert rel_l2(y2[5 * N:], y[5 * N:]) > 1e-6  # the electron-energy source really depends on U_
     assert rel_l2(y2, orc.mult(U)) < 1e-10
+
+
+def _pair_models(pm, order=2, n=(5, 4), eq=1):
+    m = tps_b200.cartesian_quad_mesh(*n, lo=(-PI, -PI), hi=(PI, PI))
+    op = tps_b200.RhsOperator(m, order=order, physics=tps_b200.Physics.plasma_mixture(pm, eq), basis_type=1, int_rule_type=1)
+    orc = oracle_api.Oracle(order, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.mixture_params(pm, eq), kind="ref", basis_type=1, int_rule=1, neq=op.neq, nvel=2)
+    return op, orc
+
+
+MULT = dict(viscosity=1.3, bulk_viscosity=1.0, heavy_thermal_conductivity=0.7, electron_thermal_conductivity=1.9,
+            momentum_transfer_frequency=2.5, diffusivity=0.6, mobility=1.4)
+
+
+@needs_ref
+@pytest.mark.parametrize("third,mult,two_t", [(False, None, True), (True, None, True), (True, MULT, True), (False, None, False)])
+def test_argon_minimal_transport_equals_reference_classes(lib_built, oracle_built, third, mult, two_t):
+    """GasMinimalTransport (Chapman-Enskog transport from the collision-integral fits, Debye-length-scaled Coulomb
+    integrals, Curtiss-Hirschfelder diffusion, third-order electron conductivity, artificial multipliers) point-wise
+    against the reference's own gas_transport.cpp / collision_integrals.cpp object code."""
+    import torch
+    pm = tps_b200.PlasmaModels.from_dict(plasma_cases.argon_minimal_dict(third, mult, two_t))
+    op, orc = _pair_models(pm)
+    rng = np.random.default_rng(7)
+    n = 400
+    up = np.zeros((n, op.neq))
+    up[:, 0] = rng.uniform(0.03, 0.08, n)
+    up[:, 1:3] = rng.uniform(-300, 300, (n, 2))
+    up[:, 3] = rng.uniform(3000, 12000, n)
+    up[:, 4] = rng.uniform(1e-4, 0.05, n)
+    if two_t:
+        up[:, 5] = rng.uniform(5000, 15000, n)
+    U = orc.pt("cons", up)
+    g = rng.normal(size=(n, 2 * op.neq)) * np.array(([0.005, 50, 50, 800, 0.01] + ([900] if two_t else [])) * 2)
+    Ud, gd = torch.from_numpy(U).cuda(), torch.from_numpy(g).cuda()
+    # the third-order conductivity divides by L11 - L12^2 / L22, a difference of nearly equal numbers: the 1-2 ulp
+    # differences between device and host pow / log are amplified ~1e4 times there
+    t = 5e-10 if third else 1e-11
+    for what, args, tol in (("visc_flux", (U, g), t), ("source", (U, orc.pt("prim", U), g), 1e-11)):
+        ref = orc.pt(what, *args)
+        got = op.point_eval(what, Ud, gd).cpu().numpy()
+        scale = np.abs(ref).max(axis=0)
+        assert (np.abs(got - ref) <= tol * scale + 1e-300).all(), (what, np.abs(got - ref).max(axis=0) / scale)
+
+
+@needs_ref
+@pytest.mark.parametrize("third", [False, True])
+def test_argon_minimal_ternary_rhs_parity(lib_built, oracle_built, third):
+    import torch
+    pm = tps_b200.PlasmaModels.from_dict(plasma_cases.argon_minimal_dict(third))
+    op, orc = _pair_models(pm, n=(5, 4))
+    up = plasma_cases.hot_primitives(orc.node_coords())
+    U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+    N = orc.N
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    yo, go = orc.mult(U, want_grad=True)
+    assert rel_l2(op.fields()[1].cpu().numpy(), go) < 1e-11
+    for k in range(op.neq):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k

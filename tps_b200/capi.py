@@ -53,7 +53,9 @@ class PlasmaModels(C.Structure):
                 ("rate_params", (C.c_double * 3) * MAX_REACTIONS), ("reaction_energy", C.c_double * MAX_REACTIONS),
                 ("equilibrium_params", (C.c_double * 3) * MAX_REACTIONS),
                 ("reactant_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS),
-                ("product_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS)]
+                ("product_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS),
+                ("third_order_k_electron", C.c_int), ("multiply", C.c_int), ("flux_trns_multiplier", C.c_double * 4),
+                ("mf_freq_multiplier", C.c_double), ("diff_mult", C.c_double), ("mobil_mult", C.c_double)]
 
     @classmethod
     def from_dict(cls, d):
@@ -65,10 +67,17 @@ class PlasmaModels(C.Structure):
         pm.num_species, pm.ambipolar, pm.two_temperature = len(sp), int(d["ambipolar"]), int(d["two_temperature"])
         for i, s_ in enumerate(sp):
             pm.mw[i], pm.charge[i], pm.formation_energy[i] = s_["mw"], s_["charge"], s_["formation_energy"]
-            pm.molar_cv[i], pm.diffusivity[i], pm.mt_freq[i] = s_["molar_cv"], s_["diffusivity"], s_["mt_freq"]
-        pm.transport_model = 2
-        pm.viscosity, pm.bulk_viscosity = d["viscosity"], d["bulk_viscosity"]
-        pm.thermal_conductivity, pm.electron_thermal_conductivity = d["thermal_conductivity"], d["electron_thermal_conductivity"]
+            pm.molar_cv[i], pm.diffusivity[i], pm.mt_freq[i] = s_["molar_cv"], s_.get("diffusivity", 0.0), s_.get("mt_freq", 0.0)
+        pm.transport_model = {"constant": 2, "argon_minimal": 0}[d.get("transport_model", "constant")]
+        pm.third_order_k_electron = int(d.get("third_order_k_electron", False))
+        mult = d.get("multipliers")
+        pm.multiply = int(mult is not None)
+        if mult is not None:
+            for k, key in enumerate(("viscosity", "bulk_viscosity", "heavy_thermal_conductivity", "electron_thermal_conductivity")):
+                pm.flux_trns_multiplier[k] = mult.get(key, 1.0)
+            pm.mf_freq_multiplier, pm.diff_mult, pm.mobil_mult = mult.get("momentum_transfer_frequency", 1.0), mult.get("diffusivity", 1.0), mult.get("mobility", 1.0)
+        pm.viscosity, pm.bulk_viscosity = d.get("viscosity", 0.0), d.get("bulk_viscosity", 0.0)
+        pm.thermal_conductivity, pm.electron_thermal_conductivity = d.get("thermal_conductivity", 0.0), d.get("electron_thermal_conductivity", 0.0)
         rx = d.get("reactions", [])
         pm.num_reactions, pm.min_temperature = len(rx), d.get("min_temperature", 0.0)
         for r, q in enumerate(rx):

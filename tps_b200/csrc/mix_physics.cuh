@@ -29,9 +29,15 @@ struct MixParams {
   int numSpecies, numActive, ambipolar, twoTemp, iElectron, iBackground;
   int dim, nvel, neq, iTh, iTe, eq_system, axisym;
   double mw[MIX_MAXSP], charge[MIX_MAXSP], formE[MIX_MAXSP], molarCV[MIX_MAXSP], molarCP[MIX_MAXSP];
+  // transport model: the reference's TransportModel value (dataStructures.hpp:80-88): 2 CONSTANT, 0 ARGON_MINIMAL
+  int transportModel;
   // ConstantTransport (transport_properties.cpp:303-330)
   double visc, bulk, kh, ke, diff[MIX_MAXSP], mtFreq[MIX_MAXSP];
   int trElectron;
+  // GasMinimalTransport, argon ternary (gas_transport.cpp:42-157): species indices, per-particle masses mw / N_A,
+  // reduced masses, third-order electron conductivity switch, artificial multipliers
+  int gmIon, gmElectron, gmNeutral, thirdOrderKe, multiply;
+  double gmMw[3], gmMuw[9], fluxMult[4], mfFreqMult, diffMult, mobilMult;
   // Chemistry (chemistry.cpp:40-113)
   int numReactions, chElectron;
   double minTemp;
@@ -296,6 +302,232 @@ MIXBIG void mix_const_diffusion(const MixParams &m, const double *U, const doubl
     for (int d = 0; d < m.nvel; d++) V[sp + d * ns] -= Vc[d];
 }
 
+// ---- collision integrals (collision_integrals.cpp:53-201): charged-particle fits in units of pi lambda_D^2 over the
+// Debye-length-scaled temperature, argon fits in m^2 over T [K] ----
+MIXFN double coll_charged(double a, double b, double c, double d, double Tp) {
+  return a * pow(log(1.0 + b * pow(Tp, c)), d) / Tp / Tp;
+}
+MIXFN double coll_att11(double Tp) { return coll_charged(0.2150, 5.2194, 1.0472, 1.2435, Tp); }
+MIXFN double coll_att12(double Tp) { return coll_charged(0.0991, 7.4684, 1.0155, 1.1536, Tp); }
+MIXFN double coll_att13(double Tp) { return coll_charged(0.0616, 7.8271, 0.9452, 1.1105, Tp); }
+MIXFN double coll_att14(double Tp) { return coll_charged(0.0308, 13.9567, 0.9511, 1.1803, Tp); }
+MIXFN double coll_att15(double Tp) { return coll_charged(0.0232, 13.7888, 0.9148, 1.1532, Tp); }
+MIXFN double coll_rep22(double Tp) { return coll_charged(0.4128, 1.2436, 1.1830, 1.0123, Tp); }
+MIXFN double coll_rep23(double Tp) { return coll_charged(0.2203, 1.8832, 1.2059, 0.9851, Tp); }
+MIXFN double coll_rep24(double Tp) { return coll_charged(0.1323, 2.7248, 1.2129, 0.9847, Tp); }
+MIXFN double coll_ArAr22(double T) { return 1.7e-18 * pow(T, -0.25); }
+MIXFN double coll_ArAr1P11(double T) { return 4.574321e-18 * pow(T, -0.1805); }
+// e-Ar (1,r): 9-term polynomial in log T, powers -1 .. 7 (collision_integrals.cpp:124-140)
+__host__ __device__ __noinline__ double coll_eAr(int r, double T) {
+  const double coeff[5][9] = {
+      {6.36254140e-18, 1.84835040e-18, -5.87727093e-18, 3.20023027e-18, -8.50509054e-19, 1.28163820e-19, -1.11712910e-20,
+       5.25649382e-22, -1.03296658e-23},
+      {1.91338172e-17, 5.45418129e-18, -1.78361685e-17, 9.75657946e-18, -2.61115722e-18, 3.98310268e-19, -3.53503678e-20,
+       1.70375066e-21, -3.45211955e-23},
+      {3.04685398e-17, 8.39750994e-18, -2.88132528e-17, 1.60147037e-17, -4.34837891e-18, 6.73136845e-19, -6.06704580e-20,
+       2.97216168e-21, -6.12760944e-23},
+      {3.90777949e-17, 1.04696956e-17, -3.73774204e-17, 2.10610498e-17, -5.79029566e-18, 9.07573157e-19, -8.28466766e-20,
+       4.11188110e-21, -8.59225098e-23},
+      {4.41333290e-17, 1.15696010e-17, -4.25651305e-17, 2.42442440e-17, -6.73359258e-18, 1.06641697e-18, -9.83933863e-20,
+       4.93775812e-21, -1.04362372e-22}};
+  const double logT = log(T);
+  double pw[9];
+  pw[0] = 1. / logT;
+  pw[1] = 1.;
+  for (int k = 0; k < 7; k++) pw[k + 2] = pw[k + 1] * logT;
+  double fit = 0.0;
+  for (int k = 0; k < 9; k++) fit += coeff[r - 1][k] * pw[k];
+  return fit;
+}
+
+constexpr double MIX_PI = 3.14159265358979323846;   // equation_of_state.hpp:67
+constexpr double MIX_EPS0 = 8.8541878128e-12;       // VACUUMPERMITTIVITY
+constexpr double MIX_DEBYE = MIX_KB * MIX_EPS0 / MIX_QE / MIX_QE;  // gas_transport.hpp:74
+
+// Debye-length scales shared by the argon-minimal routines (gas_transport.cpp:224-231)
+struct GmDebye {
+  double length, circle, nondimTe, nondimTh;
+};
+MIXFN GmDebye gm_debye(const MixParams &m, const double *n_sp, double Te, double Th) {
+  GmDebye d;
+  const double nOverT = (n_sp[m.gmElectron] + MIX_XEPS) / Te + (n_sp[m.gmIon] + MIX_XEPS) / Th;
+  d.length = sqrt(MIX_DEBYE / MIX_NA / nOverT);
+  d.circle = MIX_PI * d.length * d.length;
+  d.nondimTe = d.length * 4.0 * MIX_PI * MIX_DEBYE * Te;
+  d.nondimTh = d.length * 4.0 * MIX_PI * MIX_DEBYE * Th;
+  return d;
+}
+// binary diffusivities D_ij = binaryDiff[i + 3 j] of the ternary argon mixture (gas_transport.cpp:275-335)
+MIXFN void gm_binary_diff(const MixParams &m, double Te, double Th, double nTotal, const GmDebye &db, double *bd) {
+  const double diffusivityFactor = 3. / 16. * sqrt(2.0 * MIX_PI * MIX_KB) / MIX_NA;
+  const int e = m.gmElectron, n = m.gmNeutral, i = m.gmIon;
+  for (int k = 0; k < 9; k++) bd[k] = 0.0;
+  bd[e + n * 3] = diffusivityFactor * sqrt(Te / m.gmMuw[e + n * 3]) / nTotal / coll_eAr(1, Te);
+  bd[n + e * 3] = bd[e + n * 3];
+  bd[n + i * 3] = diffusivityFactor * sqrt(Th / m.gmMuw[n + i * 3]) / nTotal / coll_ArAr1P11(Th);
+  bd[i + n * 3] = bd[n + i * 3];
+  bd[e + i * 3] = diffusivityFactor * sqrt(Te / m.gmMuw[i + e * 3]) / nTotal / (coll_att11(db.nondimTe) * db.circle);
+  bd[i + e * 3] = bd[e + i * 3];
+}
+// TransportProperties::CurtissHirschfelder (transport_properties.cpp:188-199) + mobilities + multipliers
+MIXFN void gm_diffusivity_mobility(const MixParams &m, const double *X_sp, const double *Y_sp, const double *bd, double Te,
+                                   double Th, double *diffusivity, double *mobility) {
+  for (int sp = 0; sp < 3; sp++) diffusivity[sp] = 0.0;
+  for (int spI = 0; spI < 3; spI++) {
+    for (int spJ = 0; spJ < 3; spJ++) {
+      if (spI == spJ) continue;
+      diffusivity[spI] += (X_sp[spJ] + MIX_XEPS) / bd[spI + spJ * 3];
+    }
+    diffusivity[spI] = (1.0 - Y_sp[spI]) / diffusivity[spI];
+  }
+  for (int sp = 0; sp < 3; sp++) {
+    const double temp = (sp == m.gmElectron) ? Te : Th;
+    mobility[sp] = MIX_QE_OVER_KB * m.charge[sp] / temp * diffusivity[sp];
+  }
+  if (m.multiply)
+    for (int sp = 0; sp < 3; sp++) {
+      diffusivity[sp] *= m.diffMult;
+      mobility[sp] *= m.mobilMult;
+    }
+}
+// diffusion velocities from diffusivities / mobilities: concentration-driven part, ambipolar field
+// (transport_properties.cpp:131-150), zero external field, mass-flux correction (:59-71)
+MIXFN void mix_diffusion_velocity(const MixParams &m, const double *X_sp, const double *Y_sp, const double *n_sp,
+                                  const double *gradUp, const double *diffusivity, const double *mobility, double *V) {
+  const int ns = m.numSpecies;
+  double gradX[MIX_MAXSP * MIX_MAXDIM];
+  mix_mole_fraction_grad(m, n_sp, gradUp, gradX);
+  for (int v = 0; v < m.nvel; v++)
+    for (int sp = 0; sp < ns; sp++) V[sp + v * ns] = 0.0;
+  for (int sp = 0; sp < ns; sp++)
+    for (int d = 0; d < m.dim; d++) {
+      const double DgradX = diffusivity[sp] * gradX[sp + d * ns];
+      V[sp + d * ns] = -DgradX / (X_sp[sp] + MIX_XEPS);
+    }
+  if (m.ambipolar) {
+    double mho = 0.0;
+    for (int sp = 0; sp < ns; sp++) mho += mobility[sp] * n_sp[sp] * m.charge[sp];
+    double ambE[MIX_MAXDIM];
+    for (int v = 0; v < m.nvel; v++) ambE[v] = 0.0;
+    for (int sp = 0; sp < ns; sp++)
+      for (int d = 0; d < m.nvel; d++) ambE[d] -= V[sp + d * ns] * n_sp[sp] * m.charge[sp];
+    for (int d = 0; d < m.nvel; d++) ambE[d] /= (mho + MIX_XEPS);
+    for (int sp = 0; sp < ns; sp++)
+      for (int d = 0; d < m.nvel; d++) V[sp + d * ns] += mobility[sp] * ambE[d];
+  }
+  for (int sp = 0; sp < ns; sp++) {
+    if (m.charge[sp] == 0.0) continue;
+    for (int d = 0; d < m.nvel; d++) V[sp + d * ns] += mobility[sp] * 0.0;
+  }
+  double Vc[MIX_MAXDIM];
+  for (int v = 0; v < m.nvel; v++) Vc[v] = 0.0;
+  for (int sp = 0; sp < ns; sp++)
+    for (int d = 0; d < m.nvel; d++) Vc[d] += Y_sp[sp] * V[sp + d * ns];
+  for (int sp = 0; sp < ns; sp++)
+    for (int d = 0; d < m.nvel; d++) V[sp + d * ns] -= Vc[d];
+}
+// species viscosities -> mixture viscosity (gas_transport.cpp:233-262; also GetViscosities :775-823)
+MIXFN double gm_viscosity(const MixParams &m, const double *X_sp, double Th, const GmDebye &db, double *speciesViscosity) {
+  const double viscosityFactor = 5. / 16. * sqrt(MIX_PI * MIX_KB);
+  speciesViscosity[m.gmIon] = viscosityFactor * sqrt(m.gmMw[m.gmIon] * Th) / (coll_rep22(db.nondimTh) * db.circle);
+  speciesViscosity[m.gmNeutral] = viscosityFactor * sqrt(m.gmMw[m.gmNeutral] * Th) / coll_ArAr22(Th);
+  speciesViscosity[m.gmElectron] = 0.0;
+  double avg = 0.0;
+  for (int sp = 0; sp < 3; sp++) avg += X_sp[sp] * speciesViscosity[sp];
+  return avg;
+}
+// GasMinimalTransport::computeThirdOrderElectronThermalConductivity (gas_transport.cpp:400-489), argon
+MIXBIG double gm_third_order_ke(const MixParams &m, const double *X_sp, const GmDebye &db, double Te) {
+  const double viscosityFactor = 5. / 16. * sqrt(MIX_PI * MIX_KB), kOverEtaFactor = 15. / 4. * MIX_KB;
+  double Q2[3], Q1Ion[5], Q1N[5];
+  Q2[0] = db.circle * coll_rep22(db.nondimTe);
+  Q2[1] = db.circle * coll_rep23(db.nondimTe);
+  Q2[2] = db.circle * coll_rep24(db.nondimTe);
+  Q1Ion[0] = db.circle * coll_att11(db.nondimTe);
+  Q1Ion[1] = db.circle * coll_att12(db.nondimTe);
+  Q1Ion[2] = db.circle * coll_att13(db.nondimTe);
+  Q1Ion[3] = db.circle * coll_att14(db.nondimTe);
+  Q1Ion[4] = db.circle * coll_att15(db.nondimTe);
+  for (int r = 0; r < 5; r++) Q1N[r] = coll_eAr(r + 1, Te);
+  auto L11ea = [](const double *Q1) { return 6.25 * Q1[0] - 15. * Q1[1] + 12. * Q1[2]; };
+  auto L12ea = [](const double *Q1) { return 10.9375 * Q1[0] - 39.375 * Q1[1] + 57. * Q1[2] - 30. * Q1[3]; };
+  auto L22ea = [](const double *Q1) { return 19.140625 * Q1[0] - 91.875 * Q1[1] + 199.5 * Q1[2] - 210. * Q1[3] + 90. * Q1[4]; };
+  const int e = m.gmElectron, i = m.gmIon, n = m.gmNeutral;
+  double L11 = sqrt(2.0) * X_sp[e] * Q2[0];
+  L11 += X_sp[i] * L11ea(Q1Ion);
+  L11 += X_sp[n] * L11ea(Q1N);
+  double L12 = sqrt(2.0) * X_sp[e] * (1.75 * Q2[0] - 2.0 * Q2[1]);
+  L12 += X_sp[i] * L12ea(Q1Ion);
+  L12 += X_sp[n] * L12ea(Q1N);
+  double L22 = sqrt(2.0) * X_sp[e] * (4.8125 * Q2[0] - 7.0 * Q2[1] + 5. * Q2[2]);
+  L22 += X_sp[i] * L22ea(Q1Ion);
+  L22 += X_sp[n] * L22ea(Q1N);
+  return viscosityFactor * kOverEtaFactor * sqrt(2.0 * Te / m.gmMw[e]) * X_sp[e] / (L11 - L12 * L12 / L22);
+}
+
+// TransportProperties::ComputeFluxTransportProperties -> {Constant, GasMinimal}Transport::ComputeFluxMolecularTransport
+// (transport_properties.cpp:332-383, gas_transport.cpp:206-398): tb = {viscosity, bulk viscosity, heavy thermal
+// conductivity, electron thermal conductivity}, diffusion velocities V[sp + d*numSpecies].
+MIXBIG void mix_flux_transport(const MixParams &m, const double *s, const double *gr, double *tb, double *V) {
+  double n_sp[MIX_MAXSP], mob[MIX_MAXSP];
+  if (m.transportModel == 2) {
+    tb[0] = m.visc, tb[1] = m.bulk, tb[2] = m.kh, tb[3] = m.ke;
+    mix_const_diffusion(m, s, gr, V, n_sp, mob);
+    return;
+  }
+  double prim[MIX_MAXEQ], X_sp[MIX_MAXSP], Y_sp[MIX_MAXSP];
+  mix_prim(m, s, prim);
+  mix_species_primitives(m, s, X_sp, Y_sp, n_sp);
+  double nTotal = 0.0;
+  for (int sp = 0; sp < 3; sp++) nTotal += n_sp[sp];
+  const double Te = m.twoTemp ? prim[m.neq - 1] : prim[m.nvel + 1];
+  const double Th = prim[m.nvel + 1];
+  const GmDebye db = gm_debye(m, n_sp, Te, Th);
+  const double viscosityFactor = 5. / 16. * sqrt(MIX_PI * MIX_KB), kOverEtaFactor = 15. / 4. * MIX_KB;
+  double spVisc[3], spK[3];
+  tb[0] = gm_viscosity(m, X_sp, Th, db, spVisc);
+  for (int sp = 0; sp < 3; sp++) spK[sp] = spVisc[sp] * kOverEtaFactor / m.gmMw[sp];
+  tb[2] = 0.0;
+  for (int sp = 0; sp < 3; sp++) tb[2] += X_sp[sp] * spK[sp];
+  tb[1] = 0.0;
+  if (m.thirdOrderKe) {
+    tb[3] = gm_third_order_ke(m, X_sp, db, Te);
+  } else {
+    tb[3] = viscosityFactor * kOverEtaFactor * sqrt(Te / m.gmMw[m.gmElectron]) * X_sp[m.gmElectron] /
+            (coll_rep22(db.nondimTe) * db.circle);
+  }
+  double bd[9], diffusivity[3];
+  gm_binary_diff(m, Te, Th, nTotal, db, bd);
+  gm_diffusivity_mobility(m, X_sp, Y_sp, bd, Te, Th, diffusivity, mob);
+  if (m.multiply)
+    for (int t = 0; t < 4; t++) tb[t] *= m.fluxMult[t];
+  mix_diffusion_velocity(m, X_sp, Y_sp, n_sp, gr, diffusivity, mob, V);
+}
+
+// ComputeSourceMolecularTransport (transport_properties.cpp:385-448, gas_transport.cpp:592-773): number densities
+// and the electron momentum-transfer collision frequencies the two-temperature source needs
+MIXBIG void mix_source_transport(const MixParams &m, const double *Un, const double *upn, const double *gr, double *n_sp,
+                                 double *mtFreq) {
+  if (m.transportModel == 2) {
+    double V[MIX_MAXSP * MIX_MAXDIM], mob[MIX_MAXSP];
+    mix_const_diffusion(m, Un, gr, V, n_sp, mob);
+    for (int sp = 0; sp < m.numSpecies; sp++) mtFreq[sp] = m.mtFreq[sp];
+    return;
+  }
+  double X_sp[MIX_MAXSP], Y_sp[MIX_MAXSP];
+  mix_species_primitives(m, Un, X_sp, Y_sp, n_sp);
+  const double Te = m.twoTemp ? upn[m.neq - 1] : upn[m.nvel + 1];
+  const double Th = upn[m.nvel + 1];
+  const GmDebye db = gm_debye(m, n_sp, Te, Th);
+  const double mfFreqFactor = 4. / 3. * MIX_NA * sqrt(8. * MIX_KB / MIX_PI);
+  const double Qea = coll_eAr(1, Te), Qie = coll_att11(db.nondimTe) * db.circle;
+  for (int sp = 0; sp < 3; sp++) mtFreq[sp] = 0.0;
+  mtFreq[m.gmIon] = mfFreqFactor * sqrt(Te / m.gmMw[m.gmElectron]) * n_sp[m.gmIon] * Qie;
+  mtFreq[m.gmNeutral] = mfFreqFactor * sqrt(Te / m.gmMw[m.gmElectron]) * n_sp[m.gmNeutral] * Qea;
+  if (m.multiply)
+    for (int sp = 0; sp < 3; sp++) mtFreq[sp] *= m.mfFreqMult;
+}
+
 // Fluxes::ComputeConvectiveFluxes (fluxes.cpp:135-170)
 MIXBIG void mix_conv_flux(const MixParams &m, const double *s, double *f) {
   double Pe = 0.0;
@@ -321,14 +553,14 @@ MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr,
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (m.eq_system == 0) return;
-  double hsp[MIX_MAXSP], V[MIX_MAXSP * MIX_MAXDIM], n_sp[MIX_MAXSP], mob[MIX_MAXSP];
+  double hsp[MIX_MAXSP], V[MIX_MAXSP * MIX_MAXDIM], tb[4];
   mix_species_enthalpies(m, s, hsp);
-  mix_const_diffusion(m, s, gr, V, n_sp, mob);
-  const double visc = m.visc;
-  double bulk = m.bulk;
+  mix_flux_transport(m, s, gr, tb, V);
+  const double visc = tb[0];
+  double bulk = tb[1];
   bulk -= 2. / 3. * visc;
-  double k = m.kh;
-  const double ke = m.ke;
+  double k = tb[2];
+  const double ke = tb[3];
   if (m.twoTemp) {
     for (int d = 0; d < dim; d++) {
       const double qeFlux = ke * gr[neq - 1 + d * neq];
@@ -400,11 +632,13 @@ MIXBIG void mix_bdr_visc_flux(const MixParams &m, const double *s, const double 
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
   if (m.eq_system == 0) return;
-  const double visc = m.visc;
-  double bulk = m.bulk;
+  double tb[4], Vunused[MIX_MAXSP * MIX_MAXDIM];
+  mix_flux_transport(m, s, gr, tb, Vunused);
+  const double visc = tb[0];
+  double bulk = tb[1];
   bulk -= 2. / 3. * visc;
-  double k = m.kh;
-  const double ke = m.ke;
+  double k = tb[2];
+  const double ke = tb[3];
   // species part of normalPrimFlux is replaced by the prescribed zeros, so the species-enthalpy terms vanish
   double gu[3][3], st[3][3], nn[3];
 #pragma unroll
@@ -475,10 +709,25 @@ MIXFN double mix_pressure_from_prim(const MixParams &m, const double *Up) {
   return mix_pressure_base(m, n_sp, n_e, nB, T_h, T_e);
 }
 
-// ConstantTransport::GetViscosities (transport_properties.hpp:305-309)
-MIXFN void mix_viscosities(const MixParams &m, const double *, const double *, double *visc) {
-  visc[0] = m.visc;
-  visc[1] = m.bulk;
+// ConstantTransport::GetViscosities (transport_properties.hpp:305-309) / GasMinimalTransport::GetViscosities
+// (gas_transport.cpp:775-823)
+MIXBIG void mix_viscosities(const MixParams &m, const double *U, const double *Up, double *visc) {
+  if (m.transportModel == 2) {
+    visc[0] = m.visc;
+    visc[1] = m.bulk;
+    return;
+  }
+  double n_sp[MIX_MAXSP], X_sp[MIX_MAXSP], Y_sp[MIX_MAXSP], spVisc[3];
+  mix_species_primitives(m, U, X_sp, Y_sp, n_sp);
+  const double Te = m.twoTemp ? Up[m.neq - 1] : Up[m.nvel + 1];
+  const double Th = Up[m.nvel + 1];
+  const GmDebye db = gm_debye(m, n_sp, Te, Th);
+  visc[0] = gm_viscosity(m, X_sp, Th, db, spVisc);
+  visc[1] = 0.0;
+  if (m.multiply) {
+    visc[0] *= m.fluxMult[0];
+    visc[1] *= m.fluxMult[1];
+  }
 }
 
 // PerfectMixture::computeStagnantStateWithTemp (equation_of_state.cpp:1596-1620)
@@ -548,8 +797,8 @@ MIXBIG void mix_source(const MixParams &m, double *Un, double *upn, const double
       Un[eq] = fmax(Un[eq], 0.0);
     }
   }
-  double V[MIX_MAXSP * MIX_MAXDIM], nsp[MIX_MAXSP], mob[MIX_MAXSP];
-  mix_const_diffusion(m, Un, gr, V, nsp, mob);  // ComputeSourceMolecularTransport: n_sp, mtFreq
+  double nsp[MIX_MAXSP], mtFreq[MIX_MAXSP];
+  mix_source_transport(m, Un, upn, gr, nsp, mtFreq);  // ComputeSourceMolecularTransport: n_sp, mtFreq
   for (int eq = 0; eq < neq; eq++) src[eq] = 0.0;
   const double Th = upn[1 + nvel];
   const double Te = m.twoTemp ? upn[neq - 1] : Th;
@@ -607,7 +856,7 @@ MIXBIG void mix_source(const MixParams &m, double *Un, double *upn, const double
       if (sp == ns - 2) continue;
       const double m_sp = m.mw[sp];
       double energy = 1.5 * MIX_RU * (Te - Th);
-      energy *= 2.0 * me * m_sp / (m_sp + me) / (m_sp + me) * ne * m.mtFreq[sp];
+      energy *= 2.0 * me * m_sp / (m_sp + me) / (m_sp + me) * ne * mtFreq[sp];
       src[neq - 1] -= energy;
     }
   }

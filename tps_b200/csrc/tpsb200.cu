@@ -426,6 +426,19 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
     }
     m.visc = pm.viscosity, m.bulk = pm.bulk_viscosity, m.kh = pm.thermal_conductivity, m.ke = pm.electron_thermal_conductivity;
     m.trElectron = m.iElectron, m.chElectron = m.iElectron;
+    m.transportModel = pm.transport_model;
+    if (pm.transport_model == 0) {  // GasMinimalTransport ctor (gas_transport.cpp:42-157)
+      m.gmIon = 0, m.gmElectron = m.iElectron, m.gmNeutral = m.iBackground;
+      m.thirdOrderKe = pm.third_order_k_electron ? 1 : 0, m.multiply = pm.multiply ? 1 : 0;
+      for (int sp = 0; sp < 3; sp++) m.gmMw[sp] = pm.mw[sp] / MIX_NA;
+      for (int i = 0; i < 3; i++)
+        for (int j = i; j < 3; j++) {
+          m.gmMuw[i + j * 3] = m.gmMw[i] * m.gmMw[j] / (m.gmMw[i] + m.gmMw[j]);
+          if (i != j) m.gmMuw[j + i * 3] = m.gmMuw[i + j * 3];
+        }
+      for (int t = 0; t < 4; t++) m.fluxMult[t] = pm.flux_trns_multiplier[t];
+      m.mfFreqMult = pm.mf_freq_multiplier, m.diffMult = pm.diff_mult, m.mobilMult = pm.mobil_mult;
+    }
     m.numReactions = pm.num_reactions, m.minTemp = pm.min_temperature;
     for (int r = 0; r < pm.num_reactions; r++) {
       m.rxModel[r] = pm.model[r], m.detailed[r] = pm.detailed_balance[r] ? 1 : 0;
@@ -511,7 +524,10 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     const tpsb_plasma_models *pm = phys->plasma;
     if (!pm) return fail(ctx, TPSB_EINVAL, "fluid = user_defined needs tpsb_physics.plasma");
     if (pm->num_species < 3 || pm->num_species > TPSB_MAX_SPECIES) return fail(ctx, TPSB_EINVAL, "num_species must be 3..%d (electron and background included)", TPSB_MAX_SPECIES);
-    if (pm->transport_model != 2) return fail(ctx, TPSB_ENOTIMPL, "only transport_model = constant is built for mixtures");
+    if (pm->transport_model != 2 && pm->transport_model != 0)
+      return fail(ctx, TPSB_ENOTIMPL, "transport_model %d not built (2 constant, 0 argon_minimal)", pm->transport_model);
+    if (pm->transport_model == 0 && (pm->num_species != 3 || !(pm->charge[0] > 0) || !(pm->charge[1] < 0) || pm->charge[2] != 0))
+      return fail(ctx, TPSB_EINVAL, "argon_minimal transport serves the ternary mixture [Ar.+1, E, Ar] only (gas_transport.cpp:51-56)");
     if (pm->num_reactions < 0 || pm->num_reactions > TPSB_MAX_REACTIONS) return fail(ctx, TPSB_EINVAL, "too many reactions");
     for (int r = 0; r < pm->num_reactions; r++)
       if (pm->model[r] != 0 && pm->model[r] != 1) return fail(ctx, TPSB_ENOTIMPL, "reaction model %d not built (Arrhenius / Hoffert-Lien only)", pm->model[r]);
