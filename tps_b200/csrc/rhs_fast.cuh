@@ -719,6 +719,203 @@ __global__ void __launch_bounds__(32 * WPB, MINB) face_flux_fast_kernel(KernelAr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// face_flux_mma_kernel (p = 3): face_flux_fast_kernel with every tensor contraction on the FP64 tensor cores.
+// ncu (profiles/r1h_*): the DFMA form is bound by shared-memory wavefronts (l1tex data pipe 96 %, a third of them
+// bank conflicts of the stride-4 row reads, another fifth broadcast reads of P); as DMMA fragments the same data is
+// read once per 8 FMAs from conflict-free, lane-contiguous addresses.  One WARP per face as before:
+//   A  Y[sf][al][b]  = sum_a  P[al][a] T[sf][a + 4 b]     10 DMMA   (A = P padded to 8 rows; side 2 permuted)
+//   B  V[q][sf]      = sum_b  P[be][b] Y[sf][al][b]       13 DMMA   q = al + 5 be
+//   C  one lane per quadrature point: Rusanov + averaged viscous flux (identical to face_flux_fast_kernel)
+//   D  Bq[eq][al][b] = sum_be P[be][b] F[eq][al + 5 be]    4 x 2 DMMA (K = 5 padded to 8, A = P^T)
+//   E  R[eq][a + 4b] = sum_al P[al][a] Bq[eq][al][b]       3 x 2 DMMA -> global
+__device__ __forceinline__ void dmma884_acc(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) face_flux_mma_kernel(KernelArgs a, int face_begin, int face_count) {
+  constexpr int NP = 4, NF2 = 16, NQ = 5, NQ2 = 25;
+  constexpr int RAW = 2 * NTF * NF2;            // 320: both sides' trace blocks
+  constexpr int YS = 104 * NP;                  // Y: 100 columns (sf, al) x 4, padded to 13 groups of 8
+  constexpr int VS = NQ2 * 21 + 3;              // V[q][21]: q-major, odd stride
+  constexpr int PER_WARP = 2 * RAW + YS + VS;   // 1584 doubles
+  constexpr unsigned BLKB = NTF * NF2 * sizeof(double);
+  extern __shared__ __align__(128) double sDyn[];
+  __shared__ __align__(8) unsigned long long sBar[WPB][2];
+  __shared__ double sWq[NQ2], sP[NQ][NP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < NQ2) sWq[threadIdx.x] = c_T.wq[threadIdx.x % NQ] * c_T.wq[threadIdx.x / NQ];
+  if (threadIdx.x < NQ * NP) sP[threadIdx.x / NP][threadIdx.x % NP] = c_T.P[threadIdx.x / NP][threadIdx.x % NP];
+  double *raw = sDyn + warp * PER_WARP, *Y = raw + 2 * RAW, *V = Y + YS;
+  double *F = Y, *Bq = Y + 128;  // Y is dead once V is complete
+  const unsigned bar0 = smem_u32(&sBar[warp][0]), bar1 = smem_u32(&sBar[warp][1]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int fr = lane >> 2, fk = lane & 3;
+  // A fragments: interpolation P (5 x 4, rows 5-7 zero) and projection P^T (4 x 5 split into k = 0-3 and k = 4)
+  const double aP = fr < NQ ? sP[fr][fk] : 0.0;
+  const double aT0 = fr < NP ? sP[fk][fr] : 0.0;
+  const double aT1 = (fr < NP && fk == 0) ? sP[4][fr] : 0.0;
+  for (int t = lane; t < YS - 400; t += 32) Y[400 + t] = 0.0;  // padding columns of stage B stay finite
+  const double wq = lane < NQ2 ? sWq[lane] : 0.0;
+  const PhysParams ph = a.phys;
+  const int stride = gridDim.x * WPB;
+  int fi = blockIdx.x * WPB + warp;
+  int4 fd_cur = make_int4(0, 0, 0, 0), fd_nxt = make_int4(0, 0, 0, 0);
+  if (fi < face_count) fd_cur = __ldg(&a.face_desc[face_begin + fi]);
+  if (fi + stride < face_count) fd_nxt = __ldg(&a.face_desc[face_begin + fi + stride]);
+  if (fi < face_count && lane == 0) {
+    mbar_expect_tx(bar0, 2 * BLKB);
+    bulk_g2s(smem_u32(raw), a.tr + static_cast<long long>(fd_cur.x) * (NTF * NF2), BLKB, bar0);
+    bulk_g2s(smem_u32(raw + NTF * NF2), a.tr + static_cast<long long>(fd_cur.y) * (NTF * NF2), BLKB, bar0);
+  }
+  // stage-A store offsets: lane (row al = fr, columns 2 fk, 2 fk + 1 of group g) -> Y[(2 g + fk / 2)][al][2 (fk % 2)]
+  const int yOff = (fk >> 1) * (NP * NQ) + fr * NP + 2 * (fk & 1);
+  for (int it = 0; fi < face_count; it++, fi += stride) {
+    const int buf = it & 1;
+    const unsigned ph_bit = (it >> 1) & 1;
+    const int fc = face_begin + fi;
+    const double *cur = raw + buf * RAW;
+    int4 fd_n2 = make_int4(0, 0, 0, 0);
+    if (fi + 2 * stride < face_count) fd_n2 = __ldg(&a.face_desc[fc + 2 * stride]);
+    if (fi + stride < face_count && lane == 0) {
+      const unsigned nb = buf ? bar0 : bar1;
+      double *nx = raw + (buf ^ 1) * RAW;
+      mbar_expect_tx(nb, 2 * BLKB);
+      bulk_g2s(smem_u32(nx), a.tr + static_cast<long long>(fd_nxt.x) * (NTF * NF2), BLKB, nb);
+      bulk_g2s(smem_u32(nx + NTF * NF2), a.tr + static_cast<long long>(fd_nxt.y) * (NTF * NF2), BLKB, nb);
+    }
+    const double2 nrm01 = __ldg(reinterpret_cast<const double2 *>(a.face_nor) + 2 * fc);
+    const double2 nrm23 = __ldg(reinterpret_cast<const double2 *>(a.face_nor) + 2 * fc + 1);
+    // side 2: face coordinates (a, b) -> index in Elem2's block (perm code as in face_flux_fast_kernel)
+    int p2;
+    {
+      const int pc = fd_cur.z, b = fr & 3, fa2 = (pc & 2) ? 1 : 0, fb2 = (pc & 4) ? 1 : 0;
+      int i0, di;
+      if (pc & 1) {
+        i0 = (fa2 ? NP - 1 - b : b) + (fb2 ? NP * (NP - 1) : 0);
+        di = fb2 ? -NP : NP;
+      } else {
+        i0 = (fa2 ? NP - 1 : 0) + NP * (fb2 ? NP - 1 - b : b);
+        di = fa2 ? -1 : 1;
+      }
+      p2 = (lane >> 4) * NF2 + i0 + fk * di;
+    }
+    mbar_wait(buf ? bar1 : bar0, ph_bit);
+    // A: interpolation along a
+#pragma unroll
+    for (int g = 0; g < 10; g++) {
+      const double bv = g < 5 ? cur[32 * g + lane] : cur[NTF * NF2 + 32 * (g - 5) + p2];
+      double d0, d1;
+      dmma884(d0, d1, aP, bv);
+      if (fr < NQ) *reinterpret_cast<double2 *>(&Y[2 * g * (NP * NQ) + yOff]) = make_double2(d0, d1);
+    }
+    __syncwarp();
+    // B: interpolation along b; all fragments are read before V (which does not alias Y) is written
+#pragma unroll
+    for (int g = 0; g < 13; g++) {
+      double d0, d1;
+      dmma884(d0, d1, aP, Y[32 * g + lane]);
+      const int c0 = 8 * g + 2 * fk;  // columns (sf, al) = c / 5, c % 5; row = be
+      if (fr < NQ && c0 < 100) {
+        const int sf0 = (c0 * 52429) >> 18, al0 = c0 - 5 * sf0;
+        V[(al0 + NQ * fr) * 21 + sf0] = d0;
+        const int c1 = c0 + 1, sf1 = (c1 * 52429) >> 18, al1 = c1 - 5 * sf1;
+        V[(al1 + NQ * fr) * 21 + sf1] = d1;
+      }
+    }
+    __syncwarp();
+    // C: numerical flux at quadrature point q = lane
+    if (lane < NQ2) {
+      double v[2 * NTF];
+#pragma unroll
+      for (int sf = 0; sf < 2 * NTF; sf++) v[sf] = V[lane * 21 + sf];
+      const double *u1 = v, *u2 = v + NTF;
+      const double n0 = nrm01.x, n1 = nrm01.y, n2 = nrm23.x, normag = nrm23.y;
+      const double ri1 = fast_rcp(u1[0]), ri2 = fast_rcp(u2[0]);
+      const double vx1 = u1[1] * ri1, vy1 = u1[2] * ri1, vz1 = u1[3] * ri1;
+      const double vx2 = u2[1] * ri2, vy2 = u2[2] * ri2, vz2 = u2[3] * ri2;
+      const double vv1 = vx1 * vx1 + vy1 * vy1 + vz1 * vz1, vv2 = vx2 * vx2 + vy2 * vy2 + vz2 * vz2;
+      const double p1 = ph.gm1 * (u1[4] - 0.5 * u1[0] * vv1), p2v = ph.gm1 * (u2[4] - 0.5 * u2[0] * vv2);
+      const double pr1 = p1 * ri1, pr2 = p2v * ri2;
+      const double maxE = fmax(fast_sqrt(vv1) + fast_sqrt(ph.gamma * pr1), fast_sqrt(vv2) + fast_sqrt(ph.gamma * pr2));
+      const double vn1 = vx1 * n0 + vy1 * n1 + vz1 * n2, vn2 = vx2 * n0 + vy2 * n1 + vz2 * n2;
+      const double diss = 0.5 * maxE * normag;
+      const double psum = 0.5 * (p1 + p2v);
+      double fx[NEQ];
+      fx[0] = 0.5 * (u1[0] * vn1 + u2[0] * vn2) - diss * (u2[0] - u1[0]);
+      fx[1] = 0.5 * (u1[1] * vn1 + u2[1] * vn2) + psum * n0 - diss * (u2[1] - u1[1]);
+      fx[2] = 0.5 * (u1[2] * vn1 + u2[2] * vn2) + psum * n1 - diss * (u2[2] - u1[2]);
+      fx[3] = 0.5 * (u1[3] * vn1 + u2[3] * vn2) + psum * n2 - diss * (u2[3] - u1[3]);
+      fx[4] = 0.5 * ((u1[4] + p1) * vn1 + (u2[4] + p2v) * vn2) - diss * (u2[4] - u1[4]);
+      if (ph.eq_system != 0) {
+        const double iR = 1.0 / ph.R;
+        const double T1 = pr1 * iR, T2 = pr2 * iR;
+        const double mu1 = ph.C1 * ph.visc_mult * (T1 * fast_sqrt(T1)) * fast_rcp(T1 + ph.S0);
+        const double mu2 = ph.C1 * ph.visc_mult * (T2 * fast_sqrt(T2)) * fast_rcp(T2 + ph.S0);
+        const double bf = ph.bulk_visc_mult - 2. / 3.;
+        const double bd1 = bf * mu1 * u1[NEQ + 4], bd2 = -bf * mu2 * u2[NEQ + 4];
+        const double t0 = mu1 * u1[NEQ + 0] + bd1 * n0 - (mu2 * u2[NEQ + 0] + bd2 * n0);
+        const double t1 = mu1 * u1[NEQ + 1] + bd1 * n1 - (mu2 * u2[NEQ + 1] + bd2 * n1);
+        const double t2 = mu1 * u1[NEQ + 2] + bd1 * n2 - (mu2 * u2[NEQ + 2] + bd2 * n2);
+        const double e1 = vx1 * (mu1 * u1[NEQ + 0] + bd1 * n0) + vy1 * (mu1 * u1[NEQ + 1] + bd1 * n1) +
+                          vz1 * (mu1 * u1[NEQ + 2] + bd1 * n2) + ph.cp_div_pr * mu1 * u1[NEQ + 3];
+        const double e2 = vx2 * (mu2 * u2[NEQ + 0] + bd2 * n0) + vy2 * (mu2 * u2[NEQ + 1] + bd2 * n1) +
+                          vz2 * (mu2 * u2[NEQ + 2] + bd2 * n2) + ph.cp_div_pr * mu2 * u2[NEQ + 3];
+        fx[1] -= 0.5 * t0;
+        fx[2] -= 0.5 * t1;
+        fx[3] -= 0.5 * t2;
+        fx[4] -= 0.5 * (e1 - e2);
+      }
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) F[eq * NQ2 + lane] = fx[eq] * wq;
+    }
+    __syncwarp();
+    // D: projection along beta (K = 5: k = 0-3, then k = 4 with a one-column A fragment)
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const int col = min(8 * g + fr, NEQ * NQ - 1), eq = (col * 52429) >> 18, al = col - 5 * eq;
+      const double *fb = F + eq * NQ2 + al;
+      double d0, d1;
+      dmma884(d0, d1, aT0, fb[NQ * fk]);
+      dmma884_acc(d0, d1, aT1, fb[NQ * 4]);
+      const int c0 = 8 * g + 2 * fk;
+      if (fr < NP) {
+        if (c0 < NEQ * NQ) Bq[c0 * NP + fr] = d0;
+        if (c0 + 1 < NEQ * NQ) Bq[(c0 + 1) * NP + fr] = d1;
+      }
+    }
+    __syncwarp();
+    // E: projection along alpha, straight to global: R[eq][a + 4 b]
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const int col = min(8 * g + fr, NEQ * NP - 1), eq = col >> 2, b = col & 3;
+      const double *bb = Bq + eq * (NQ * NP) + b;
+      double d0, d1;
+      dmma884(d0, d1, aT0, bb[NP * fk]);
+      dmma884_acc(d0, d1, aT1, bb[NP * 4]);
+      const int c0 = 8 * g + 2 * fk;
+      if (fr < NP && c0 < NEQ * NP) {
+        double *dst = a.faceRes + static_cast<long long>(fc) * (NEQ * NF2) + (c0 >> 2) * NF2 + fr + NP * (c0 & 3);
+        dst[0] = d0;
+        dst[NP] = d1;  // column c0 + 1: same eq (c0 even), b + 1
+      }
+    }
+    __syncwarp();
+    fd_cur = fd_nxt;
+    fd_nxt = fd_n2;
+  }
+}
+
+constexpr size_t face_mma_smem_bytes(int wpb) { return static_cast<size_t>(wpb) * (2 * 320 + 104 * 4 + 25 * 21 + 3) * sizeof(double); }
+
 template <int NP>
 constexpr size_t face_fast_smem_bytes(int wpb) {
   constexpr int NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ;

@@ -1157,14 +1157,33 @@ static void grad_trace(tpsb_ctx *c, const KernelArgs &a, int begin, int count, c
     launch_grad_trace<2, 16, 4>(c, a, begin, count, list);
   }
 }
+template <int WPB, int MINB>
+static void launch_face_mma(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_FACE);
+  int grid = (count + WPB - 1) / WPB;
+  const int cap = c->num_sms * MINB;
+  if (grid > cap) grid = cap;
+  const size_t smem = face_mma_smem_bytes(WPB);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(face_flux_mma_kernel<WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr_set = true;
+  }
+  face_flux_mma_kernel<WPB, MINB><<<grid, 32 * WPB, smem, c->stream>>>(a, begin, count);
+}
 static void face_fast(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (c->np == 4) {
     switch (c->tune[1]) {
+      case 6: launch_face_fast<4, 4, 5>(c, a, begin, count); break;  // DFMA form (before the DMMA kernel)
+      case 7: launch_face_mma<4, 3>(c, a, begin, count); break;
+      case 8: launch_face_mma<2, 8>(c, a, begin, count); break;
+      case 9: launch_face_mma<8, 2>(c, a, begin, count); break;
       case 1: launch_face_fast<4, 4, 4>(c, a, begin, count); break;
       case 2: launch_face_fast<4, 2, 10>(c, a, begin, count); break;
       case 3: launch_face_fast<4, 8, 2>(c, a, begin, count); break;
       case 4: launch_face_fast<4, 6, 3>(c, a, begin, count); break;
-      default: launch_face_fast<4, 4, 5>(c, a, begin, count); break;
+      default: launch_face_mma<4, 4>(c, a, begin, count); break;
     }
   } else if (c->np == 3) {
     launch_face_fast<3, 8, 2>(c, a, begin, count);
