@@ -84,7 +84,8 @@ typedef struct {
   int transport_model;
   double viscosity, bulk_viscosity, thermal_conductivity, electron_thermal_conductivity;
   double diffusivity[TPSB_MAX_SPECIES], mt_freq[TPSB_MAX_SPECIES];
-  /* Chemistry (src/chemistry.cpp:40-300): reaction r uses model[r] = ReactionModel (0 Arrhenius, 1 Hoffert-Lien) */
+  /* Chemistry (src/chemistry.cpp:40-300): reaction r uses model[r] = ReactionModel (0 Arrhenius, 1 Hoffert-Lien,
+   * 2 tabulated, 3 grid function; fields at the end of this struct) */
   int num_reactions;
   double min_temperature;
   int model[TPSB_MAX_REACTIONS], detailed_balance[TPSB_MAX_REACTIONS];
@@ -99,6 +100,14 @@ typedef struct {
   int multiply;                    /* artificial multipliers on (argonMinimal.multipliers.ini)                       */
   double flux_trns_multiplier[4];  /* viscosity, bulk viscosity, heavy / electron thermal conductivity               */
   double mf_freq_multiplier, diff_mult, mobil_mult;
+  /* reaction model 2 (TABULATED_RXN): rate coefficient k_f(T) by linear interpolation of a table, optionally in log
+   * scale of either axis (TableInput src/dataStructures.hpp:668-676, LinearTable src/table.cpp:52-97,
+   * Tabulated src/reaction.cpp:62-84).  HOST arrays, copied at create; at most 1000 points (gpudata::MAXTABLE).
+   * reaction model 3 (GRIDFUNCTION_RXN): k_f per node from component rate_component[r] of the field handed to
+   * tpsb_set_reaction_rate_field (GridFunctionReaction src/reaction.cpp:86-117).                                      */
+  int table_n[TPSB_MAX_REACTIONS], table_xlog[TPSB_MAX_REACTIONS], table_flog[TPSB_MAX_REACTIONS];
+  const double *table_x[TPSB_MAX_REACTIONS], *table_f[TPSB_MAX_REACTIONS];
+  int rate_component[TPSB_MAX_REACTIONS];
 } tpsb_plasma_models;
 
 typedef struct {
@@ -185,6 +194,16 @@ int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp);
  * Up / gradUp are computed from x -- the reference's behaviour, kept (parity trap 1).
  * NULL (default): use x itself.  tpsb_ode_step sets it to d_U for the duration of the step.        */
 int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U);
+
+/* Chemistry::setGridFunctionRates (src/chemistry.cpp:133-140): the externally computed rate coefficients of the
+ * GRIDFUNCTION_RXN reactions, d_rates[component][N] in DEVICE memory (byNODES), valid until replaced; NULL: those
+ * reactions have k_f = 0 (src/reaction.cpp:113-116).                                                  */
+int tpsb_set_reaction_rate_field(tpsb_ctx *ctx, const double *d_rates, int num_components);
+
+/* RHSoperator::computeMeanTimeDerivatives / getLocalTimeDerivatives (src/rhs_operator.cpp:833-848): mean over the
+ * local nodes of |dU/dt| per equation for a DEVICE vector d_y (neq*N, e.g. the result of tpsb_rhs_mult); out[neq] on
+ * the host.  The reference evaluates it every 100th call; here the caller decides.                     */
+int tpsb_get_mean_time_derivatives(tpsb_ctx *ctx, const double *d_y, double *out);
 
 /* max_char_speed of the last Mult (src/rhs_operator.cpp:549-558), reduced over this rank's nodes
  * (and over ranks when a communicator is attached); synchronises the stream.                      */

@@ -914,6 +914,7 @@ void orc_bc_flux(void *h, const OrcBc *bc, int use_bc_in_grad, const double *nor
   o->use_bc_in_grad = save;
 }
 void orc_set_solution_view(void *h, const double *U) { static_cast<Oracle *>(h)->sol_view = U; }
+void orc_set_rates(void *h, const double *data, int size) { static_cast<Oracle *>(h)->ph->set_rates(data, size); }
 void orc_destroy(void *h) {
   Oracle *o = static_cast<Oracle *>(h);
   if (!o) return;

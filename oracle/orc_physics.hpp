@@ -44,6 +44,10 @@ struct OrcPlasma {
   // transport_model == 0 (ARGON_MINIMAL): GasTransportInput scalars (src/dataStructures.hpp:644-666)
   int third_order_k_electron, multiply;
   double flux_trns_multiplier[4], mf_freq_multiplier, diff_mult, mobil_mult;
+  // TABULATED_RXN tables (TableInput) and GRIDFUNCTION_RXN components
+  int table_n[34], table_xlog[34], table_flog[34];
+  const double *table_x[34], *table_f[34];
+  int rate_component[34];
 };
 // One boundary condition of BCintegrator's attribute maps (src/BCintegrator.cpp:64-125).
 // kind: 0 inlet, 1 outlet, 2 wall; type: the reference's InletType / OutletType / WallType value
@@ -79,6 +83,8 @@ struct Physics {
   // reference does.  Fluids without plasma sources keep the default (no forcing term registered).
   virtual bool has_source() const { return false; }
   virtual void source_term(double *Un, double *upn, const double *gradUpn, int node, double *src) {}
+  // Chemistry::setRates: rate coefficients of the GRIDFUNCTION_RXN reactions, data[component][size]
+  virtual void set_rates(const double *data, int size) {}
   // ---- used by AxisymmetricSource (src/forcing_terms.cpp:255-380) ----
   // GasMixture::ComputePressureFromPrimitives
   virtual double pressure_from_primitives(const double *Up) = 0;

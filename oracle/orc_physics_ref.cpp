@@ -161,6 +161,12 @@ class MixtureRef : public Physics {
           ci.equilibriumConstantParams[k + r * gpudata::MAXCHEMPARAMS] = pm.equilibrium_params[r][k];
         }
         ci.reactionInputs[r].modelParams = rxParams_[r];
+        ci.reactionInputs[r].indexInput = pm.rate_component[r];
+        if (pm.model[r] == TABULATED_RXN) {
+          TableInput &ti = ci.reactionInputs[r].tableInput;
+          ti.Ndata = pm.table_n[r], ti.xdata = pm.table_x[r], ti.fdata = pm.table_f[r];
+          ti.xLogScale = pm.table_xlog[r] != 0, ti.fLogScale = pm.table_flog[r] != 0, ti.order = 1;
+        }
         for (int sp = 0; sp < pm.num_species; sp++) {
           ci.reactantStoich[sp + r * pm.num_species] = static_cast<int16_t>(pm.reactant_stoich[r][sp]);
           ci.productStoich[sp + r * pm.num_species] = static_cast<int16_t>(pm.product_stoich[r][sp]);
@@ -221,6 +227,15 @@ class MixtureRef : public Physics {
     flux_->ComputeBdrViscousFluxes(U, gradUp, xyz, delta, dist, bc, normalFlux);
   }
   bool has_source() const override { return true; }
+  // GridFunctionReaction::setGridFunction semantics (src/reaction.cpp:93-106): component c at data + c * size.
+  // (Chemistry::setRates -> setData offsets by the PREVIOUS size, src/reaction.cpp:88-91; calling it twice gives the
+  // intended offset.)
+  void set_rates(const double *data, int size) override {
+    if (chem_) {
+      chem_->setRates(data, size);
+      chem_->setRates(data, size);
+    }
+  }
   // SourceTerm::updateTerms node body (src/source_term.cpp:117-250) over the reference's transport / chemistry /
   // mixture objects; no radiation, no EM coupling output.
   void source_term(double *Un, double *upn, const double *gradUpn, int n, double *srcTerm) override {

@@ -69,6 +69,7 @@ def load(kind="port"):
     lib.orc_set_bcs.argtypes = [C.c_void_p, _ip, C.c_int, C.POINTER(OrcBc), C.c_int]
     lib.orc_bc_flux.argtypes = [C.c_void_p, C.POINTER(OrcBc), C.c_int, _dp, _dp, _dp, _dp]
     lib.orc_set_solution_view.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_set_rates.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     for nm in ("orc_pt_prim", "orc_pt_cons", "orc_pt_max_char_speed", "orc_pt_conv_flux"):
         getattr(lib, nm).argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.orc_pt_visc_flux.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
@@ -135,6 +136,11 @@ class Oracle:
     def set_solution_view(self, U):
         self._sol = None if U is None else np.ascontiguousarray(U, dtype=np.float64)
         self.lib.orc_set_solution_view(self.h, None if U is None else self._sol.ctypes.data)
+
+    def set_rates(self, rates):
+        """rates[component][N]: rate coefficients of the GRIDFUNCTION_RXN reactions (Chemistry::setGridFunctionRates)."""
+        self._rates = np.ascontiguousarray(rates, dtype=np.float64)
+        self.lib.orc_set_rates(self.h, self._rates.ctypes.data, self._rates.shape[-1])
 
     # point-wise probes of this operator's physics object: arrays are [n][neq] / [n][dim][neq] point-major
     def pt(self, what, *arrs):

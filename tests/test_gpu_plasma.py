@@ -145,3 +145,54 @@ def test_argon_minimal_ternary_rhs_parity(lib_built, oracle_built, third):
     assert rel_l2(op.fields()[1].cpu().numpy(), go) < 1e-11
     for k in range(op.neq):
         assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k
+
+
+def _tab_models(kind):
+    d = plasma_cases.ternary_dict()
+    T = np.geomspace(9.0e3, 1.3e4, 57)  # narrower than the electron temperatures of the test state
+    kf = 4.7 * T ** 1.2 * np.exp(-6.49e4 / 8.3144598 / T) + 1e-30
+    rx = dict(d["reactions"][0])
+    if kind == "table_loglog":
+        rx.update(model=2, table=(T, kf, True, True))
+    elif kind == "table_lin":
+        rx.update(model=2, table=(T, kf, False, False))
+    else:
+        rx.update(model=3, component=1)
+    d["reactions"] = [rx]
+    return tps_b200.PlasmaModels.from_dict(d)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["table_loglog", "table_lin", "gridfunction"])
+def test_tabulated_and_grid_function_reaction_rates(lib_built, oracle_built, kind):
+    """Reaction models TABULATED_RXN (LinearTable, binary search, log/linear scales; out-of-range temperatures
+    extrapolate from the end intervals) and GRIDFUNCTION_RXN (rate coefficient per node from an external field)."""
+    import torch
+    pm = _tab_models(kind)
+    op, orc = _pair_models(pm, n=(4, 4))
+    N = orc.N
+    up = plasma_cases.smooth_primitives(orc.node_coords())
+    up[:, 5] *= 8.0  # electron temperatures 8000 .. 16000 K: inside and on both sides outside the table
+    U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+    if kind == "gridfunction":
+        rates = np.abs(np.random.default_rng(3).normal(size=(2, N))) * 1e-3
+        orc.set_rates(rates)
+        op.set_reaction_rate_field(torch.from_numpy(rates).cuda())
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    yo = orc.mult(U)
+    for k in range(op.neq):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k
+    if kind == "gridfunction":  # without a field the reaction is switched off (reaction.cpp:113-116)
+        op.set_reaction_rate_field(None)
+        y0 = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+        assert rel_l2(y0[4 * N:5 * N], y[4 * N:5 * N]) > 1e-8
+
+
+def test_mean_time_derivatives(lib_built):
+    import torch
+    m = tps_b200.cartesian_hex_mesh(3, 3, 3)
+    op = tps_b200.RhsOperator(m, order=2)
+    y = torch.from_numpy(np.random.default_rng(0).normal(size=5 * op.N)).cuda()
+    got = op.mean_time_derivatives(y)
+    ref = np.abs(y.cpu().numpy()).reshape(5, -1).mean(axis=1)
+    assert np.allclose(got, ref, rtol=1e-13)

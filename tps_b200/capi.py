@@ -55,7 +55,10 @@ class PlasmaModels(C.Structure):
                 ("reactant_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS),
                 ("product_stoich", (C.c_int * MAX_SPECIES) * MAX_REACTIONS),
                 ("third_order_k_electron", C.c_int), ("multiply", C.c_int), ("flux_trns_multiplier", C.c_double * 4),
-                ("mf_freq_multiplier", C.c_double), ("diff_mult", C.c_double), ("mobil_mult", C.c_double)]
+                ("mf_freq_multiplier", C.c_double), ("diff_mult", C.c_double), ("mobil_mult", C.c_double),
+                ("table_n", C.c_int * MAX_REACTIONS), ("table_xlog", C.c_int * MAX_REACTIONS),
+                ("table_flog", C.c_int * MAX_REACTIONS), ("table_x", C.POINTER(C.c_double) * MAX_REACTIONS),
+                ("table_f", C.POINTER(C.c_double) * MAX_REACTIONS), ("rate_component", C.c_int * MAX_REACTIONS)]
 
     @classmethod
     def from_dict(cls, d):
@@ -83,11 +86,17 @@ class PlasmaModels(C.Structure):
         for r, q in enumerate(rx):
             pm.model[r], pm.detailed_balance[r], pm.reaction_energy[r] = q.get("model", 0), int(q["detailed"]), q["energy"]
             for k, key in enumerate(("A", "b", "E")):
-                pm.rate_params[r][k] = q[key]
+                pm.rate_params[r][k] = q.get(key, 0.0)
             for k, key in enumerate(("eqA", "eqB", "eqE")):
                 pm.equilibrium_params[r][k] = q.get(key, 0.0)
             for i in range(len(sp)):
                 pm.reactant_stoich[r][i], pm.product_stoich[r][i] = q["reactants"][i], q["products"][i]
+            if q.get("model", 0) == 2:  # tabulated: table = (x, f, xlog, flog)
+                tx, tf = (np.ascontiguousarray(t, dtype=np.float64) for t in q["table"][:2])
+                pm._keep = getattr(pm, "_keep", []) + [tx, tf]
+                pm.table_n[r], pm.table_xlog[r], pm.table_flog[r] = len(tx), int(q["table"][2]), int(q["table"][3])
+                pm.table_x[r], pm.table_f[r] = _dp(tx), _dp(tf)
+            pm.rate_component[r] = q.get("component", 0)
         return pm
 
 
@@ -139,7 +148,7 @@ class PartSizes(C.Structure):
 # every symbol include/tpsb200.h declares (tests check the library exports all of them)
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
-           "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
+           "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
            "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
@@ -178,6 +187,8 @@ def lib():
     L.tpsb_get_fields.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_set_solution_view.argtypes = [vp, vp]
+    L.tpsb_set_reaction_rate_field.argtypes = [vp, vp, C.c_int]
+    L.tpsb_get_mean_time_derivatives.argtypes = [vp, vp, dp]
     L.tpsb_ode_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
     L.tpsb_get_element_to_faces.argtypes = [vp, ip]
     L.tpsb_debug_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
@@ -457,6 +468,19 @@ class RhsOperator:
         """The solution grid function U_ the forcing terms read (None: the vector passed to Mult)."""
         self._sol = U
         self._chk(self.L.tpsb_set_solution_view(self.ctx, U.data_ptr() if U is not None else None), "tpsb_set_solution_view")
+
+    def set_reaction_rate_field(self, rates):
+        """Chemistry::setGridFunctionRates: device tensor [components][N] (or None)."""
+        self._rates = rates
+        ncomp = 0 if rates is None else rates.numel() // self.N
+        self._chk(self.L.tpsb_set_reaction_rate_field(self.ctx, rates.data_ptr() if rates is not None else None, ncomp),
+                  "tpsb_set_reaction_rate_field")
+
+    def mean_time_derivatives(self, y):
+        """RHSoperator::getLocalTimeDerivatives: mean |dU/dt| per equation."""
+        out = (C.c_double * self.neq)()
+        self._chk(self.L.tpsb_get_mean_time_derivatives(self.ctx, y.data_ptr(), out), "tpsb_get_mean_time_derivatives")
+        return np.array(out[:])
 
     def point_eval(self, what, U, aux=None):
         """Test hook: per-point physics of this context on device arrays U [n][neq] (aux: gradUp [n][dim*neq])."""

@@ -45,7 +45,17 @@ struct MixParams {
   double rxA[MIX_MAXRX], rxB[MIX_MAXRX], rxE[MIX_MAXRX], rxEnergy[MIX_MAXRX];
   double eqA[MIX_MAXRX], eqB[MIX_MAXRX], eqE[MIX_MAXRX];
   double reactS[MIX_MAXRX * MIX_MAXSP], prodS[MIX_MAXRX * MIX_MAXSP];  // [sp + r*numSpecies]
+  // TABULATED_RXN (rxModel 2): LinearTable per reaction (table.cpp:76-97) in one device pool, reaction r at
+  // tbl + tblOff[r]: x[n] | a[n-1] | b[n-1]
+  const double *tbl;
+  int tblOff[MIX_MAXRX], tblN[MIX_MAXRX], tblXlog[MIX_MAXRX], tblFlog[MIX_MAXRX];
+  // GRIDFUNCTION_RXN (rxModel 3): externally supplied rate coefficient per node, component rxComp[r] of
+  // rateField[comp][N] (reaction.cpp:86-117); NULL -> 0 like the reference
+  const double *rateField;
+  long long rateN;
+  int rxComp[MIX_MAXRX];
 };
+
 
 // The larger routines are deliberately NOT inlined (MIXBIG): one compiled body serves every kernel, so the body the
 // point-wise parity test (tpsb_debug_point_eval vs the reference classes) certifies is the body the DG kernels run.
@@ -779,6 +789,30 @@ MIXBIG void mix_modify_energy_for_pressure(const MixParams &m, const double *in,
   out[m.iTh] = rE;
 }
 
+// TableInterpolator::findInterval + LinearTable::eval (table.cpp:52-97)
+__host__ __device__ __noinline__ double mix_table_eval(const MixParams &m, int r, double xEval) {
+  const int n = m.tblN[r];
+  const double *x = m.tbl + m.tblOff[r], *ta = x + n, *tb = ta + n;
+  int count = n, first = 0;
+  while (count > 0) {  // std::upper_bound
+    int it = first;
+    const int step = count / 2;
+    it += step;
+    if (xEval > x[it]) {
+      first = ++it;
+      count -= step + 1;
+    } else {
+      count = step;
+    }
+  }
+  first = max(1, min(n - 1, first));
+  const int index = first - 1;
+  const double xt = m.tblXlog[r] ? log(xEval) : xEval;
+  double ft = ta[index] + tb[index] * xt;
+  if (m.tblFlog[r]) ft = exp(ft);
+  return ft;
+}
+
 // Chemistry::isElectronInvolvedAt (chemistry.hpp:136-138)
 MIXFN bool mix_electron_involved(const MixParams &m, int r) {
   return (m.chElectron < 0) ? false : (m.reactS[m.chElectron + r * m.numSpecies] != 0);
@@ -788,7 +822,7 @@ MIXFN bool mix_electron_involved(const MixParams &m, int r) {
 // temperatures the electron-energy sink of electron-impact reactions, the work u.grad(p_e) and the elastic
 // electron-heavy energy exchange.  Un = conserved state of the SOLUTION grid function, upn / gr from the stage
 // vector (parity trap 1); the species clamp index is the reference's hard-coded 3 + 2 + sp (parity trap 2).
-MIXBIG void mix_source(const MixParams &m, double *Un, double *upn, const double *gr, double *src) {
+MIXBIG void mix_source(const MixParams &m, double *Un, double *upn, const double *gr, long long node, double *src) {
   const int neq = m.neq, nvel = m.nvel, ns = m.numSpecies;
   for (int sp = 0; sp < m.numActive; sp++) {
     const int eq = 3 + 2 + sp;
@@ -812,9 +846,13 @@ MIXBIG void mix_source(const MixParams &m, double *Un, double *upn, const double
       double kf;
       if (m.rxModel[r] == 0) {  // Arrhenius (reaction.cpp:41-48)
         kf = m.rxA[r] * pow(temp, m.rxB[r]) * exp(-m.rxE[r] / MIX_RU / temp);
-      } else {  // Hoffert-Lien (reaction.cpp:53-61)
+      } else if (m.rxModel[r] == 1) {  // Hoffert-Lien (reaction.cpp:53-61)
         const double tf = m.rxE[r] / MIX_KB / temp;
         kf = m.rxA[r] * pow(temp, m.rxB[r]) * (tf + 2.0) * exp(-tf);
+      } else if (m.rxModel[r] == 2) {  // Tabulated (reaction.cpp:78-84)
+        kf = mix_table_eval(m, r, temp);
+      } else {  // GridFunctionReaction (reaction.cpp:108-117)
+        kf = m.rateField ? m.rateField[node + m.rxComp[r] * m.rateN] : 0.;
       }
       double kC = 0.0;
       if (m.detailed[r]) kC = m.eqA[r] * pow(temp, m.eqB[r]) * exp(-m.eqE[r] / temp);  // chemistry.cpp:204-218

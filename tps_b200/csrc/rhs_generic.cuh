@@ -505,7 +505,7 @@ __global__ void gen_source_kernel(GenArgs a, const double *Usol) {
     upn[eq] = a.Up[n + eq * a.N];
     for (int d = 0; d < a.dim; d++) gr[eq + d * a.neq] = a.gradUp[n + eq * a.N + d * a.neq * a.N];
   }
-  mix_source(*a.phys.mix, Un, upn, gr, src);
+  mix_source(*a.phys.mix, Un, upn, gr, n, src);
   for (int eq = 0; eq < a.neq; eq++) a.y[n + eq * a.N] += src[eq];
 }
 
@@ -579,7 +579,7 @@ __global__ void gen_point_eval_kernel(GenArgs a, int which, int n, const double 
   } else if (which == 4 && a.phys.fluid) {
     for (int c = 0; c < nc; c++) gr[c] = aux[i * nc + c];
     gen_prim(a.phys, s, up);
-    mix_source(*a.phys.mix, s, up, gr, f);
+    mix_source(*a.phys.mix, s, up, gr, i, f);
     for (int eq = 0; eq < neq; eq++) out[i * neq + eq] = f[eq];
   }
 }

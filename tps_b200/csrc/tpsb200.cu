@@ -49,6 +49,7 @@ struct tpsb_ctx {
   bool generic = false;
   int dim = 3, neq = NEQ;
   const double *sol_view = nullptr;  // U_ of the reference's forcing terms (tpsb_set_solution_view)
+  MixParams mix_host;                // host copy of the device MixParams (re-uploaded by tpsb_set_reaction_rate_field)
   GenArgs gen;
   std::vector<void *> gen_allocs;
   // boundary faces (BCintegrator)
@@ -450,7 +451,34 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
         m.prodS[sp + r * m.numSpecies] = pm.product_stoich[r][sp];
       }
     }
+    // LinearTable constructor (table.cpp:76-85): slopes / intercepts in the (log) variables
+    std::vector<double> tbl;
+    for (int r = 0; r < pm.num_reactions; r++) {
+      m.rxComp[r] = pm.rate_component[r];
+      if (pm.model[r] != 2) continue;
+      const int n = pm.table_n[r];
+      const bool xl = pm.table_xlog[r] != 0, fl = pm.table_flog[r] != 0;
+      m.tblOff[r] = static_cast<int>(tbl.size()), m.tblN[r] = n, m.tblXlog[r] = xl, m.tblFlog[r] = fl;
+      const double *xd = pm.table_x[r], *fd = pm.table_f[r];
+      tbl.insert(tbl.end(), xd, xd + n);
+      std::vector<double> ta(n, 0.0), tb(n, 0.0);
+      for (int k = 0; k < n - 1; k++) {
+        ta[k] = fl ? log(fd[k]) : fd[k];
+        const double df = fl ? (log(fd[k + 1]) - log(fd[k])) : (fd[k + 1] - fd[k]);
+        tb[k] = xl ? df / (log(xd[k + 1]) - log(xd[k])) : df / (xd[k + 1] - xd[k]);
+        ta[k] -= xl ? tb[k] * log(xd[k]) : tb[k] * xd[k];
+      }
+      tbl.insert(tbl.end(), ta.begin(), ta.end());
+      tbl.insert(tbl.end(), tb.begin(), tb.end());
+    }
+    if (!tbl.empty()) {
+      cudaError_t te = cudaSetDevice(c->device);
+      if (te == cudaSuccess) te = g_upload(c, &m.tbl, tbl);
+      if (te != cudaSuccess) return std::string("device setup failed: ") + cudaGetErrorString(te);
+    }
+    m.rateField = nullptr, m.rateN = static_cast<long long>(NE) * dof;
     mixv.push_back(m);
+    c->mix_host = m;
     g.phys.fluid = 1;
   }
   std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE) * nv * dim);
@@ -530,7 +558,11 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
       return fail(ctx, TPSB_EINVAL, "argon_minimal transport serves the ternary mixture [Ar.+1, E, Ar] only (gas_transport.cpp:51-56)");
     if (pm->num_reactions < 0 || pm->num_reactions > TPSB_MAX_REACTIONS) return fail(ctx, TPSB_EINVAL, "too many reactions");
     for (int r = 0; r < pm->num_reactions; r++)
-      if (pm->model[r] != 0 && pm->model[r] != 1) return fail(ctx, TPSB_ENOTIMPL, "reaction model %d not built (Arrhenius / Hoffert-Lien only)", pm->model[r]);
+      if (pm->model[r] < 0 || pm->model[r] > 3)
+        return fail(ctx, TPSB_ENOTIMPL, "reaction model %d not built (0 Arrhenius, 1 Hoffert-Lien, 2 tabulated, 3 grid function)", pm->model[r]);
+    for (int r = 0; r < pm->num_reactions; r++)
+      if (pm->model[r] == 2 && (pm->table_n[r] < 2 || pm->table_n[r] > 1000 || !pm->table_x[r] || !pm->table_f[r]))
+        return fail(ctx, TPSB_EINVAL, "reaction %d: a tabulated rate needs 2..1000 table points (gpudata::MAXTABLE)", r);
     const int nact = pm->ambipolar ? pm->num_species - 2 : pm->num_species - 1;
     if (space->num_equation != space->nvel + 2 + nact + (pm->two_temperature ? 1 : 0) || space->num_equation > GEN_MAXEQ)
       return fail(ctx, TPSB_EINVAL, "num_equation does not match the mixture (nvel + 2 + active species [+ 1 electron energy])");
@@ -1427,6 +1459,51 @@ int tpsb_debug_point_eval(tpsb_ctx *ctx, int which, int n, const double *d_U, co
 int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U) {
   if (!ctx) return TPSB_EINVAL;
   ctx->sol_view = d_U;
+  return TPSB_OK;
+}
+
+int tpsb_set_reaction_rate_field(tpsb_ctx *ctx, const double *d_rates, int num_components) {
+  if (!ctx) return TPSB_EINVAL;
+  if (!ctx->generic || !ctx->gen.phys.fluid) return fail(ctx, TPSB_EINVAL, "reaction rate fields belong to a plasma mixture");
+  for (int r = 0; r < ctx->mix_host.numReactions; r++)
+    if (ctx->mix_host.rxModel[r] == 3 && d_rates && (ctx->mix_host.rxComp[r] < 0 || ctx->mix_host.rxComp[r] >= num_components))
+      return fail(ctx, TPSB_EINVAL, "reaction %d reads component %d of a %d-component rate field", r, ctx->mix_host.rxComp[r], num_components);
+  CU(cudaSetDevice(ctx->device));
+  ctx->mix_host.rateField = d_rates;
+  CU(cudaMemcpyAsync(const_cast<MixParams *>(ctx->gen.phys.mix), &ctx->mix_host, sizeof(MixParams), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPSB_OK;
+}
+
+static __global__ void mean_abs_kernel(long long N, int neq, const double *y, double *out) {
+  __shared__ double sm[256];
+  const int eq = blockIdx.y;
+  double s = 0;
+  for (long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; n < N; n += static_cast<long long>(gridDim.x) * blockDim.x)
+    s += fabs(y[n + eq * N]);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(&out[eq], sm[0] / static_cast<double>(N));
+}
+
+int tpsb_get_mean_time_derivatives(tpsb_ctx *ctx, const double *d_y, double *out) {
+  if (!ctx || !d_y || !out) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  const int neq = tpsb_num_equation(ctx);
+  const long long N = tpsb_num_dofs(ctx);
+  double *d_out = nullptr;
+  CU(cudaMalloc(&d_out, neq * sizeof(double)));
+  CU(cudaMemsetAsync(d_out, 0, neq * sizeof(double), ctx->stream));
+  const int nb = static_cast<int>(std::min<long long>((N + 255) / 256, 1024));
+  mean_abs_kernel<<<dim3(nb, neq), 256, 0, ctx->stream>>>(N, neq, d_y, d_out);
+  cudaError_t e = cudaMemcpyAsync(out, d_out, neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  CU(e);
   return TPSB_OK;
 }
 
