@@ -119,6 +119,9 @@ typedef struct {
   double bulk_visc_mult;  /* flow/bulkViscosityMultiplier                      */
   double sutherland_C1, sutherland_S0, sutherland_Pr;
   const tpsb_plasma_models *plasma; /* fluid == TPSB_USER_DEFINED: gas / transport / chemistry models; else NULL */
+  int use_roe;            /* flow/useRoe: RiemannSolverTPS::Eval_Roe (src/riemann_solver.cpp:117-206) on interior
+                             faces and inviscid walls; as in the reference it is written for two velocity
+                             components with gamma - 1 = 0.4 hard-coded, so only 2-D dry air accepts it           */
 } tpsb_physics;
 
 /* Boundary conditions: BCintegrator's attribute -> {InletBC, OutletBC, WallBC} maps (src/BCintegrator.cpp:64-125).

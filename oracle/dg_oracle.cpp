@@ -350,12 +350,12 @@ struct Oracle {
       // inputState[4 + sp] = rho Y_sp of the active species (src/inletBC.cpp:742-750)
       for (int sp = 0; sp < ph->num_active_species(); sp++) state2[nvel + 2 + sp] = b.data[4 + sp];
       ph->modify_energy_for_pressure(state2, state2, pr, true);
-      ph->riemann(stateIn, state2, normal, bdrFlux);
+      ph->riemann(stateIn, state2, normal, bdrFlux, true);  // rsolver->Eval(..., true): forced Lax-Friedrichs
     } else if (b.kind == 1) {
       if (b.type != 0) return;  // OutletType SUB_P only
       // OutletBC::subsonicReflectingPressure (src/outletBC.cpp:731-737)
       ph->modify_energy_for_pressure(stateIn, state2, b.data[0], false);
-      ph->riemann(stateIn, state2, normal, bdrFlux);
+      ph->riemann(stateIn, state2, normal, bdrFlux, true);  // rsolver->Eval(..., true): forced Lax-Friedrichs
     } else if (b.type == 0) {
       // WallBC::computeINVwallFlux (src/wallBC.cpp:277-320)
       double vel[3], un[3];
@@ -385,7 +385,7 @@ struct Oracle {
       if (b.type == 2) {
         // WallBC::computeAdiabaticWallFlux (src/wallBC.cpp:430-469); bcFlux_: species + heat flux prescribed 0 (:88-96)
         ph->stagnation_state(stateIn, wallState);
-        ph->riemann(stateIn, wallState, normal, bdrFlux);
+        ph->riemann(stateIn, wallState, normal, bdrFlux, true);  // rsolver->Eval(..., true): forced Lax-Friedrichs
         ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
         for (int i = 0; i < nsp; i++) idx[i] = true;
         idx[nsp + nvel] = true;
@@ -399,7 +399,7 @@ struct Oracle {
         } else {
           ph->stagnant_state_with_temp(stateIn, b.data[0], wallState);
         }
-        ph->riemann(stateIn, wallState, normal, bdrFlux);
+        ph->riemann(stateIn, wallState, normal, bdrFlux, true);  // rsolver->Eval(..., true): forced Lax-Friedrichs
         ph->stagnant_state_with_temp(stateIn, b.data[0], wallState);
         for (int i = 0; i < nsp; i++) idx[i] = true;
         ph->bdr_visc_flux(wallState, gradState, xyz, delta, 0.0, unitN, primFlux, idx, wallViscF);

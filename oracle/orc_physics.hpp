@@ -25,6 +25,7 @@ struct OrcPhysParams {
   double bulk_visc_mult;
   double C1, S0, Pr;  // Sutherland data (src/dataStructures.hpp:205-209)
   const OrcPlasma *plasma;  // fluid == 1 (USER_DEFINED): gas / transport / chemistry models (reference back end only)
+  int use_roe;              // flow/useRoe: RiemannSolverTPS::Eval_Roe on interior faces and inviscid walls (2-D dry air)
 };
 // Plasma models of a user-defined fluid: PerfectMixtureInput + constantTransportData + ChemistryInput
 // (src/dataStructures.hpp:537-546,623-633,690-712) flattened; same layout as tpsb_plasma_models.
@@ -75,8 +76,8 @@ struct Physics {
   // Fluxes::ComputeViscousFluxes
   virtual void visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist,
                          double *F) = 0;
-  // RiemannSolverTPS::Eval (useRoe = false -> Eval_LF)
-  virtual void riemann(const double *U1, const double *U2, const double *nor, double *flux) = 0;
+  // RiemannSolverTPS::Eval(state1, state2, nor, flux, LF): Eval_Roe when useRoe && !LF, else Eval_LF
+  virtual void riemann(const double *U1, const double *U2, const double *nor, double *flux, bool LF = false) = 0;
   virtual int num_active_species() const = 0;
   // SourceTerm::updateTerms for one node (src/source_term.cpp:117-250): Un = conserved state of the solution
   // grid function, upn / gradUpn = primitives and their gradients; both may be clamped in place like the

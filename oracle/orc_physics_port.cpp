@@ -220,8 +220,66 @@ class DryAirPort : public Physics {
       flux[(1 + nvel_) + 1 * neq_] += ut * tau_tz;
     }
   }
+  // src/riemann_solver.cpp:117-206 (Eval_Roe, Roe-Lohner): two velocity components, gamma - 1 = 0.4 hard-coded (:153)
+  void roe(const double *state1, const double *state2, const double *nor, double *flux) {
+    const int dim = dim_, NS_eq = 2 + dim;
+    double normag = 0;
+    for (int i = 0; i < dim; i++) normag += nor[i] * nor[i];
+    normag = sqrt(normag);
+    double unitN[3], f1[48], f2[48], meanFlux[16], vel[3];
+    for (int d = 0; d < dim; d++) unitN[d] = nor[d] / normag;
+    conv_flux(state1, f1);
+    conv_flux(state2, f2);
+    for (int eq = 0; eq < NS_eq; eq++) {
+      meanFlux[eq] = 0.;
+      for (int d = 0; d < dim; d++) meanFlux[eq] += (f1[eq + d * neq_] + f2[eq + d * neq_]) * unitN[d];
+    }
+    const double r = sqrt(state1[0] * state2[0]);
+    for (int i = 0; i < dim; i++) {
+      vel[i] = state1[i + 1] / sqrt(state1[0]) + state2[i + 1] / sqrt(state2[0]);
+      vel[i] /= sqrt(state1[0]) + sqrt(state2[0]);
+    }
+    double qk = 0.;
+    for (int d = 0; d < dim; d++) qk += vel[d] * unitN[d];
+    const double p1 = pressure(state1), p2 = pressure(state2);
+    double H = (state1[1 + dim] + p1) / sqrt(state1[0]) + (state2[1 + dim] + p2) / sqrt(state2[0]);
+    H /= sqrt(state1[0]) + sqrt(state2[0]);
+    const double a2 = 0.4 * (H - 0.5 * (vel[0] * vel[0] + vel[1] * vel[1]));
+    const double a = sqrt(a2);
+    double lamb[3] = {qk, qk + a, qk - a};
+    if (fabs(lamb[0]) < 1e-4) lamb[0] = 1e-4;
+    const double deltaP = p2 - p1;
+    const double deltaU = state2[1] / state2[0] - state1[1] / state1[0];
+    const double deltaV = state2[2] / state2[0] - state1[2] / state1[0];
+    const double deltaQk = deltaU * unitN[0] + deltaV * unitN[1];
+    double DF1[4], DF4[4], DF5[4];
+    DF1[0] = 1.;
+    DF1[1] = vel[0];
+    DF1[2] = vel[1];
+    DF1[3] = 0.5 * (vel[0] * vel[0] + vel[1] * vel[1]);
+    for (int i = 0; i < 4; i++) DF1[i] *= state2[0] - state1[0] - deltaP / a2;
+    DF1[1] += r * (deltaU - unitN[0] * deltaQk);
+    DF1[2] += r * (deltaV - unitN[1] * deltaQk);
+    DF1[3] += r * (vel[0] * deltaU + vel[1] * deltaV - qk * deltaQk);
+    for (int i = 0; i < 4; i++) DF1[i] *= fabs(lamb[0]);
+    DF4[0] = 1.;
+    DF4[1] = vel[0] + unitN[0] * a;
+    DF4[2] = vel[1] + unitN[1] * a;
+    DF4[3] = H + qk * a;
+    for (int i = 0; i < 4; i++) DF4[i] *= fabs(lamb[1]) * (deltaP + r * a * deltaQk) * 0.5 / a2;
+    DF5[0] = 1.;
+    DF5[1] = vel[0] - unitN[0] * a;
+    DF5[2] = vel[1] - unitN[1] * a;
+    DF5[3] = H - qk * a;
+    for (int i = 0; i < 4; i++) DF5[i] *= fabs(lamb[2]) * (deltaP - r * a * deltaQk) * 0.5 / a2;
+    for (int i = 0; i < NS_eq; i++) flux[i] = (meanFlux[i] - (DF1[i] + DF4[i] + DF5[i])) * 0.5 * normag;
+  }
   // src/riemann_solver.cpp:89-114 (Eval_LF) with ComputeFluxDotN :53-64
-  void riemann(const double *s1, const double *s2, const double *nor, double *flux) override {
+  void riemann(const double *s1, const double *s2, const double *nor, double *flux, bool LF) override {
+    if (p_.use_roe && !LF) {
+      roe(s1, s2, nor, flux);
+      return;
+    }
     const double maxE1 = max_char_speed(s1);
     const double maxE2 = max_char_speed(s2);
     const double maxE = fmax(maxE1, maxE2);
@@ -245,6 +303,7 @@ class DryAirPort : public Physics {
 
 Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq) {
   if (p.fluid != 0) return nullptr;
+  if (p.use_roe && dim != 2) return nullptr;  // Eval_Roe is written for two velocity components (riemann_solver.cpp:153-170)
   return new DryAirPort(p, dim, nvel, neq);
 }
 

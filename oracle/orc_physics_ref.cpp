@@ -24,6 +24,7 @@ class DryAirRef : public Physics {
   DryAirTransport *trans_;
   Fluxes *flux_;
   RiemannSolverTPS *rs_;
+  bool use_roe_ = false;
 
  public:
   DryAirRef(const OrcPhysParams &p, int dim, int nvel, int neq) : dim_(dim), nvel_(nvel), neq_(neq) {
@@ -36,7 +37,8 @@ class DryAirRef : public Physics {
     trans_ = new DryAirTransport(mix_, p.visc_mult, p.bulk_visc_mult, p.C1, p.S0, p.Pr);       // transport_properties.cpp:208
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
     flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym);   // fluxes.cpp:34
-    rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, false, axisym);  // riemann_solver.cpp:38
+    rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, p.use_roe != 0, axisym);  // riemann_solver.cpp:38
+    use_roe_ = p.use_roe != 0;
   }
   ~DryAirRef() {
     delete rs_;
@@ -85,8 +87,14 @@ class DryAirRef : public Physics {
   void visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, double *F) override {
     flux_->ComputeViscousFluxes(U, gradUp, xyz, delta, dist, F);
   }
-  void riemann(const double *U1, const double *U2, const double *nor, double *flux) override {
-    rs_->Eval(U1, U2, nor, flux, false);
+  void riemann(const double *U1, const double *U2, const double *nor, double *flux, bool LF) override {
+    if (use_roe_ && !LF) {  // Eval_Roe exists only behind the Vector overload (riemann_solver.cpp:66-83,117-206)
+      Vector a(const_cast<double *>(U1), neq_), b(const_cast<double *>(U2), neq_), n(const_cast<double *>(nor), dim_), f(neq_);
+      rs_->Eval(a, b, n, f, false);
+      for (int i = 0; i < neq_; i++) flux[i] = f[i];
+    } else {
+      rs_->Eval(U1, U2, nor, flux, true);
+    }
   }
 };
 
@@ -192,7 +200,7 @@ class MixtureRef : public Physics {
   void visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, double *F) override {
     flux_->ComputeViscousFluxes(U, gradUp, xyz, delta, dist, F);
   }
-  void riemann(const double *U1, const double *U2, const double *nor, double *flux) override {
+  void riemann(const double *U1, const double *U2, const double *nor, double *flux, bool) override {
     rs_->Eval(U1, U2, nor, flux, false);
   }
   double pressure(const double *U) override { return mix_->ComputePressure(U); }

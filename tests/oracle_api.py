@@ -13,7 +13,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 class OrcPhysParams(C.Structure):
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("gamma", C.c_double), ("R", C.c_double),
                 ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double), ("C1", C.c_double),
-                ("S0", C.c_double), ("Pr", C.c_double), ("plasma", C.c_void_p)]
+                ("S0", C.c_double), ("Pr", C.c_double), ("plasma", C.c_void_p), ("use_roe", C.c_int)]
 
 
 class OrcBc(C.Structure):
@@ -28,15 +28,15 @@ def make_bc(attr, kind, type_, data=()):
     return b
 
 
-def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0):
+def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False):
     """Defaults of the reference: gamma/R src/equation_of_state.cpp:175-179; Sutherland SURVEY.md 8(d)."""
-    return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None)
+    return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None, int(use_roe))
 
 
 def mixture_params(models, eq_system=1):
     """fluid = user_defined: `models` is a tps_b200.PlasmaModels (same layout as the oracle's OrcPlasma); only the
     reference-object-code flavour of the oracle (kind='ref') serves mixtures."""
-    p = OrcPhysParams(eq_system, 1, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, C.addressof(models))
+    p = OrcPhysParams(eq_system, 1, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, C.addressof(models), 0)
     p._models = models
     return p
 

@@ -71,3 +71,26 @@ def test_port_physics_equals_reference_object_code_2d_and_axisymmetric(lib_cpu, 
     N = a.N
     for k in range(nvel + 2):
         assert rel_l2(ya[k * N:(k + 1) * N], yb[k * N:(k + 1) * N]) < 1e-12, k
+
+
+@needs_ref
+@pytest.mark.parametrize("bc", [None, "inviscid", "c4"])
+def test_roe_port_equals_reference_object_code(lib_cpu, oracle_built, bc):
+    """flow/useRoe = 1: the restated Eval_Roe (2-D, gamma - 1 = 0.4 hard-coded) against the reference's own
+    RiemannSolverTPS::Eval_Roe; inviscid walls use it too, the other boundary conditions force Lax-Friedrichs."""
+    import tps_b200
+    m = ac.box(n=(4, 3), warp=0.05) if bc else tps_b200.cartesian_quad_mesh(4, 3, lo=(-np.pi, -np.pi), hi=(np.pi, np.pi))
+    out = []
+    for kind in ("port", "ref"):
+        orc = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                                phys=oracle_api.dry_air_params(1, 3e4, 0.2, use_roe=True), kind=kind, basis_type=1, int_rule=1)
+        if bc:
+            orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in ac.bcs(bc)], True)
+        U = ac.dry_state(orc.node_coords(), 2)
+        out.append(orc.mult(U))
+    lf = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                           phys=oracle_api.dry_air_params(1, 3e4, 0.2), kind="port", basis_type=1, int_rule=1)
+    if bc:
+        lf.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in ac.bcs(bc)], True)
+    assert rel_l2(out[0], out[1]) < 1e-12
+    assert rel_l2(out[0], lf.mult(U)) > 1e-4  # and it really is a different solver than Lax-Friedrichs

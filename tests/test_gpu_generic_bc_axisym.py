@@ -87,3 +87,21 @@ def test_ternary_mixture_with_walls(lib_built, oracle_built):
         up = plasma_cases.smooth_primitives(orc.node_coords() * np.pi)
         U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
         _compare(op, orc, U)
+
+
+@pytest.mark.parametrize("bc", [None, "inviscid", "c4"])
+def test_roe_riemann_solver_2d(lib_built, oracle_built, bc):
+    """flow/useRoe = 1 (RiemannSolverTPS::Eval_Roe, 2-D dry air) on interior faces and inviscid walls."""
+    import tps_b200
+    m = ac.box(n=(5, 4), warp=0.05) if bc else tps_b200.cartesian_quad_mesh(5, 4, lo=(-np.pi, -np.pi), hi=(np.pi, np.pi))
+    specs = ac.bcs(bc) if bc else []
+    orc = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(1, 3e4, 0.2, use_roe=True), basis_type=1, int_rule=1)
+    if specs:
+        orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], True)
+    op = tps_b200.RhsOperator(m, order=2, physics=tps_b200.Physics.dry_air(1, 3e4, 0.2, use_roe=True), basis_type=1,
+                              int_rule_type=1, face_attr=m.get("face_attr") if specs else None, use_bc_in_grad=True,
+                              bcs=[tps_b200.BcDesc.make(*b) for b in specs] if specs else None)
+    _compare(op, orc, ac.dry_state(orc.node_coords(), 2))
+    with pytest.raises(tps_b200.TpsbError):  # the reference's Roe solver has no 3-D form
+        tps_b200.RhsOperator(tps_b200.cartesian_hex_mesh(2, 2, 2), order=1, physics=tps_b200.Physics.dry_air(1, 1.0, 0.0, use_roe=True))

@@ -105,16 +105,16 @@ class Physics(C.Structure):
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("specific_heat_ratio", C.c_double),
                 ("gas_constant", C.c_double), ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double),
                 ("sutherland_C1", C.c_double), ("sutherland_S0", C.c_double), ("sutherland_Pr", C.c_double),
-                ("plasma", C.POINTER(PlasmaModels))]
+                ("plasma", C.POINTER(PlasmaModels)), ("use_roe", C.c_int)]
 
     @classmethod
-    def dry_air(cls, eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0):
-        return cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None)
+    def dry_air(cls, eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False):
+        return cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None, int(use_roe))
 
     @classmethod
     def plasma_mixture(cls, models, eq_system=1):
         """fluid = user_defined with the given PlasmaModels (kept alive on the returned object)."""
-        ph = cls(eq_system, 1, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, C.pointer(models))
+        ph = cls(eq_system, 1, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, C.pointer(models), 0)
         ph._models = models
         return ph
 

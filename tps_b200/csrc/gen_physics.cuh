@@ -15,6 +15,7 @@ constexpr int GEN_MAXDIM = 3;
 
 struct GenPhys {
   int dim, nvel, neq;
+  int use_roe;           // flow/useRoe (2-D dry air): Eval_Roe unless a caller forces Lax-Friedrichs
   int axisym;            // config.isAxisymmetric(): dim == 2 with nvel == 3, state [rho, rho u_r, rho u_z, rho u_theta, ...]
   int fluid;             // 0 dry air; 1 user-defined plasma mixture (mix != NULL)
   PhysParams dry;        // gamma, R, Sutherland, multipliers, eq_system
@@ -258,6 +259,62 @@ __host__ __device__ __forceinline__ void gen_modify_energy_for_pressure(const Ge
 }
 __host__ __device__ __forceinline__ int gen_num_active_species(const GenPhys &g) { return g.fluid ? g.mix->numActive : 0; }
 
+// RiemannSolverTPS::Eval_Roe (riemann_solver.cpp:117-206), Roe-Lohner: two velocity components, gamma - 1 = 0.4
+// hard-coded (:153), entropy fix |lambda_0| >= 1e-4 -- restated as is (parity trap 9).
+__host__ __device__ __noinline__ void dry_gen_riemann_roe(const GenPhys &g, const double *state1, const double *state2,
+                                                          const double *nor, double *flux) {
+  const int neq = g.neq;
+  const double normag = sqrt(nor[0] * nor[0] + nor[1] * nor[1]);
+  const double unitN[2] = {nor[0] / normag, nor[1] / normag};
+  double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM], meanFlux[4];
+  dry_gen_conv_flux(g, state1, f1);
+  dry_gen_conv_flux(g, state2, f2);
+  for (int eq = 0; eq < 4; eq++) {
+    meanFlux[eq] = 0.;
+    for (int d = 0; d < 2; d++) meanFlux[eq] += (f1[eq + d * neq] + f2[eq + d * neq]) * unitN[d];
+  }
+  const double r = sqrt(state1[0] * state2[0]);
+  double vel[2];
+  for (int i = 0; i < 2; i++) {
+    vel[i] = state1[i + 1] / sqrt(state1[0]) + state2[i + 1] / sqrt(state2[0]);
+    vel[i] /= sqrt(state1[0]) + sqrt(state2[0]);
+  }
+  const double qk = vel[0] * unitN[0] + vel[1] * unitN[1];
+  const double p1 = dry_gen_pressure(g, state1), p2 = dry_gen_pressure(g, state2);
+  double H = (state1[3] + p1) / sqrt(state1[0]) + (state2[3] + p2) / sqrt(state2[0]);
+  H /= sqrt(state1[0]) + sqrt(state2[0]);
+  const double a2 = 0.4 * (H - 0.5 * (vel[0] * vel[0] + vel[1] * vel[1]));
+  const double a = sqrt(a2);
+  double lamb0 = qk;
+  const double lamb1 = qk + a, lamb2 = qk - a;
+  if (fabs(lamb0) < 1e-4) lamb0 = 1e-4;
+  const double deltaP = p2 - p1;
+  const double deltaU = state2[1] / state2[0] - state1[1] / state1[0];
+  const double deltaV = state2[2] / state2[0] - state1[2] / state1[0];
+  const double deltaQk = deltaU * unitN[0] + deltaV * unitN[1];
+  double DF1[4], DF4[4], DF5[4];
+  DF1[0] = 1.;
+  DF1[1] = vel[0];
+  DF1[2] = vel[1];
+  DF1[3] = 0.5 * (vel[0] * vel[0] + vel[1] * vel[1]);
+  for (int i = 0; i < 4; i++) DF1[i] *= state2[0] - state1[0] - deltaP / a2;
+  DF1[1] += r * (deltaU - unitN[0] * deltaQk);
+  DF1[2] += r * (deltaV - unitN[1] * deltaQk);
+  DF1[3] += r * (vel[0] * deltaU + vel[1] * deltaV - qk * deltaQk);
+  for (int i = 0; i < 4; i++) DF1[i] *= fabs(lamb0);
+  DF4[0] = 1.;
+  DF4[1] = vel[0] + unitN[0] * a;
+  DF4[2] = vel[1] + unitN[1] * a;
+  DF4[3] = H + qk * a;
+  for (int i = 0; i < 4; i++) DF4[i] *= fabs(lamb1) * (deltaP + r * a * deltaQk) * 0.5 / a2;
+  DF5[0] = 1.;
+  DF5[1] = vel[0] - unitN[0] * a;
+  DF5[2] = vel[1] - unitN[1] * a;
+  DF5[3] = H - qk * a;
+  for (int i = 0; i < 4; i++) DF5[i] *= fabs(lamb2) * (deltaP - r * a * deltaQk) * 0.5 / a2;
+  for (int i = 0; i < 4; i++) flux[i] = (meanFlux[i] - (DF1[i] + DF4[i] + DF5[i])) * 0.5 * normag;
+}
+
 // RiemannSolverTPS::Eval_LF (riemann_solver.cpp:89-114)
 __host__ __device__ __forceinline__ void gen_riemann_lf(const GenPhys &g, const double *s1, const double *s2, const double *nor,
                                                double *flux) {
@@ -276,6 +333,12 @@ __host__ __device__ __forceinline__ void gen_riemann_lf(const GenPhys &g, const 
     }
     flux[eq] = 0.5 * (a + b) - 0.5 * maxE * (s2[eq] - s1[eq]) * normag;
   }
+}
+
+// RiemannSolverTPS::Eval (riemann_solver.cpp:66-83): Roe when useRoe and the caller does not force Lax-Friedrichs
+__host__ __device__ __forceinline__ void gen_riemann(const GenPhys &g, const double *s1, const double *s2, const double *nor,
+                                                     double *flux) {
+  if (g.use_roe) dry_gen_riemann_roe(g, s1, s2, nor, flux); else gen_riemann_lf(g, s1, s2, nor, flux);
 }
 
 }  // namespace tpsb

@@ -164,7 +164,7 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
     s2[2] = u1[0] * (vel[1] - 2. * vn * un[1]);
     if (dim == 3) s2[3] = u1[0] * (vel[2] - 2. * vn * un[2]);
     if (nvel == 3 && dim == 2) s2[3] = u1[0] * vel[2];
-    gen_riemann_lf(g, u1, s2, nor, fx);
+    gen_riemann(g, u1, s2, nor, fx);  // the inviscid wall does not force Lax-Friedrichs (wallBC.cpp:301)
     if (!ns) return;
     gen_visc_flux(g, s2, gr, radius, viscF);
     for (int eq = 0; eq < neq; eq++) {
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       }
       const double *u1 = first ? uo : un, *u2 = first ? un : uo, *g1 = first ? go : gn, *g2 = first ? gn : go;
       double fx[GEN_MAXEQ];
-      gen_riemann_lf(a.phys, u1, u2, nor, fx);
+      gen_riemann(a.phys, u1, u2, nor, fx);
       if (a.eq_system != 0) {
         double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM];
         gen_visc_flux(a.phys, u1, g1, radius, f1);

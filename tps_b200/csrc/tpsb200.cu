@@ -405,6 +405,7 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   g.neq = space->num_equation, g.nvel = space->nvel, g.NE = NE, g.N = static_cast<long long>(NE) * dof, g.me_diag = diag ? 1 : 0;
   g.phys.dim = dim, g.phys.nvel = space->nvel, g.phys.neq = space->num_equation, g.phys.dry = c->phys;
   g.phys.axisym = axisym ? 1 : 0;
+  g.phys.use_roe = phys->use_roe ? 1 : 0;
   g.bct = gbt;
   g.eq_system = phys->eq_system;
   g.phys.fluid = 0, g.phys.mix = nullptr;
@@ -572,6 +573,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   // 3-D Gauss-Legendre dry air runs the specialised kernels; everything else the generic tensor-product path
   bool want_generic = maps->dim != 3 || space->basis_type != 0 || space->int_rule_type != 0 || phys->fluid != TPSB_DRY_AIR;
   if (const char *pth = getenv("TPSB_PATH")) want_generic = want_generic || strcmp(pth, "generic") == 0;
+  if (phys->use_roe && !(maps->dim == 2 && space->nvel == 2 && phys->fluid == TPSB_DRY_AIR))
+    return fail(ctx, TPSB_ENOTIMPL, "useRoe: Eval_Roe of the reference is written for 2-D dry air only (riemann_solver.cpp:117-206)");
   if (want_generic) {
     if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
   }
