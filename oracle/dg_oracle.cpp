@@ -30,6 +30,77 @@
 
 namespace orc {
 
+#define SLIPFN static inline
+// WallBC::computeSlipWallFlux (wallBC.cpp:326-428): velocity in a wall-aligned basis (outward unit normal, an arbitrary
+// tangent built around the dominant normal component, their cross product), normal component mirrored, transformed
+// back with the inverse basis matrix.  [MFEM CalcInverse: adjugate / determinant for 2 x 2 and 3 x 3.]
+SLIPFN void slip_mirror_velocity(int dim, const double *normal, const double *vel, double *nVel) {
+  const double sml = 1.0e-15;
+  double unitNorm[3] = {0, 0, 0}, tangent1[3] = {0, 0, 0}, tangent2[3] = {0, 0, 0};
+  double normN = 0.;
+  for (int d = 0; d < dim; d++) normN += normal[d] * normal[d];
+  normN = sqrt(fmax(normN, sml));
+  for (int d = 0; d < dim; d++) unitNorm[d] = normal[d] * (1. / normN);
+  int dir = 0;
+  if (dim == 3) {
+    if (fabs(unitNorm[0]) >= fabs(unitNorm[1]) && fabs(unitNorm[0]) >= fabs(unitNorm[2])) dir = 0;
+    if (fabs(unitNorm[1]) >= fabs(unitNorm[0]) && fabs(unitNorm[1]) >= fabs(unitNorm[2])) dir = 1;
+    if (fabs(unitNorm[2]) >= fabs(unitNorm[0]) && fabs(unitNorm[2]) >= fabs(unitNorm[1])) dir = 2;
+  } else {
+    if (fabs(unitNorm[0]) >= fabs(unitNorm[1])) dir = 0;
+    if (fabs(unitNorm[1]) >= fabs(unitNorm[0])) dir = 1;
+  }
+  const int next_dir = (dir + 1) % dim, previous_dir = (dir + 2) % dim;
+  tangent1[next_dir] = +1.;
+  tangent1[previous_dir] = -1.;
+  tangent1[dir] = unitNorm[previous_dir] * tangent1[previous_dir] + unitNorm[next_dir] * tangent1[next_dir];
+  tangent1[dir] *= -1. / unitNorm[dir];
+  double mod = 0.;
+  for (int d = 0; d < dim; d++) mod += tangent1[d] * tangent1[d];
+  for (int d = 0; d < dim; d++) tangent1[d] *= 1. / fmax(sqrt(mod), sml);
+  if (dim == 3) {
+    tangent2[0] = +(unitNorm[1] * tangent1[2] - unitNorm[2] * tangent1[1]);
+    tangent2[1] = -(unitNorm[0] * tangent1[2] - unitNorm[2] * tangent1[0]);
+    tangent2[2] = +(unitNorm[0] * tangent1[1] - unitNorm[1] * tangent1[0]);
+    mod = 0.;
+    for (int d = 0; d < dim; d++) mod += tangent2[d] * tangent2[d];
+    for (int d = 0; d < dim; d++) tangent2[d] *= 1. / fmax(sqrt(mod), sml);
+  }
+  double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, inv[3][3], w[3] = {0, 0, 0};
+  for (int d = 0; d < dim; d++) {
+    M[0][d] = unitNorm[d];
+    M[1][d] = tangent1[d];
+    if (dim == 3) M[2][d] = tangent2[d];
+  }
+  for (int r = 0; r < dim; r++)
+    for (int d = 0; d < dim; d++) w[r] += M[r][d] * vel[d];
+  w[0] = -w[0];  // mirror the normal component
+  if (dim == 2) {
+    const double t = 1.0 / (M[0][0] * M[1][1] - M[0][1] * M[1][0]);
+    inv[0][0] = M[1][1] * t;
+    inv[0][1] = -M[0][1] * t;
+    inv[1][0] = -M[1][0] * t;
+    inv[1][1] = M[0][0] * t;
+  } else {
+    const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                       M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+    const double t = 1.0 / det;
+    inv[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) * t;
+    inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * t;
+    inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * t;
+    inv[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) * t;
+    inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * t;
+    inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * t;
+    inv[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) * t;
+    inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * t;
+    inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * t;
+  }
+  for (int r = 0; r < dim; r++) {
+    nVel[r] = 0.;
+    for (int d = 0; d < dim; d++) nVel[r] += inv[r][d] * w[d];
+  }
+}
+
 // ---- MFEM geometry constants [MFEM fem/geom.cpp: Geometry::Constants<CUBE/SQUARE/SEGMENT>] ----
 static const double HEX_VERT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
                                       {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
@@ -381,6 +452,16 @@ struct Oracle {
         bdrFlux[eq] -= 0.5 * wallViscF[eq];
         for (int d = 0; d < dim; d++) bdrFlux[eq] -= 0.5 * viscF[eq + d * neq] * normal[d];
       }
+    } else if (b.type == 1) {
+      // WallBC::computeSlipWallFlux (src/wallBC.cpp:326-428): mirror state, Riemann flux only
+      double vel[3] = {0, 0, 0}, nVel[3];
+      for (int d = 0; d < nvel; d++) vel[d] = stateIn[1 + d] / stateIn[0];
+      slip_mirror_velocity(dim, normal, vel, nVel);
+      for (int eq = 0; eq < neq; eq++) state2[eq] = stateIn[eq];
+      state2[1] = stateIn[0] * nVel[0];
+      state2[2] = stateIn[0] * nVel[1];
+      if (dim == 3) state2[3] = stateIn[0] * nVel[2];
+      ph->riemann(stateIn, state2, normal, bdrFlux);
     } else if (b.type == 2 || b.type == 3) {
       if (b.type == 2) {
         // WallBC::computeAdiabaticWallFlux (src/wallBC.cpp:430-469); bcFlux_: species + heat flux prescribed 0 (:88-96)

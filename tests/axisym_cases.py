@@ -31,6 +31,7 @@ def bcs(kind, nvel=2, species=()):
         "c4": [(1, 2, 0, ()), (2, 2, 3, (298.15,)), (3, 0, 2, inlet), (4, 1, 0, (101000.0,))],
         "adiabatic": [(1, 2, 2, ()), (2, 2, 2, ()), (3, 2, 0, ()), (4, 2, 3, (350.0,))],
         "inviscid": [(1, 2, 0, ()), (2, 2, 0, ()), (3, 2, 0, ()), (4, 2, 0, ())],
+        "slip": [(1, 2, 1, ()), (2, 2, 1, ()), (3, 2, 1, ()), (4, 2, 0, ())],
     }
     return sets[kind]
 

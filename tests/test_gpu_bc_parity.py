@@ -116,3 +116,26 @@ def test_cylinder_ogrid_parity(lib_built, oracle_built):
     for k in range(5):
         assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k
     assert abs(op.max_char_speed() / orc.max_char_speed - 1) < 1e-13
+
+
+@pytest.mark.parametrize("warp", [False, True])
+def test_slip_wall_3d(lib_built, oracle_built, warp):
+    """WallType SLIP (wallBC.cpp:326-428) on the z and y sides of the channel, fast and general 3-D paths."""
+    import torch
+    specs = [(1, 0, 2, (1.2, 25.0, 1.0, -2.0)), (2, 1, 0, (101300.0,)), (3, 2, 1, ()), (4, 2, 1, ()), (5, 2, 1, ()),
+             (6, 2, 3, (290.0,))]
+    m = tps_b200.cartesian_hex_mesh(4, 3, 3, lo=LO, hi=HI, periodic=(0, 0, 0))
+    attr = box_face_attrs(m, LO, HI)
+    if warp:
+        m = warp_mesh(m, amp=0.1, lo=LO, hi=HI)
+    op = tps_b200.RhsOperator(m, order=3, physics=tps_b200.Physics.dry_air(1, 4e3, 0.2), face_attr=attr,
+                              bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+    orc = oracle_api.Oracle(3, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(1, 4e3, 0.2))
+    orc.set_bcs(attr, [oracle_api.make_bc(*b) for b in specs], False)
+    U = tgv_state(orc.node_coords() * np.pi)
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    yo = orc.mult(U)
+    N = orc.N
+    for k in range(5):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k

@@ -31,7 +31,8 @@ def _compare(op, orc, U, tol_y=1e-10):
 
 
 @pytest.mark.parametrize("order,bt,ir", [(2, 1, 1), (3, 0, 0), (1, 0, 0)])
-@pytest.mark.parametrize("eq,bc,ubg", [(1, "c4", True), (1, "c4", False), (1, "adiabatic", False), (0, "inviscid", False)])
+@pytest.mark.parametrize("eq,bc,ubg", [(1, "c4", True), (1, "c4", False), (1, "adiabatic", False), (0, "inviscid", False),
+                                       (1, "slip", False)])
 def test_quad_boundary_conditions_dry_air(lib_built, oracle_built, order, bt, ir, eq, bc, ubg):
     m = ac.box(warp=0.06)
     op, orc = ac.make_pair(m, order, eq, bt, ir, 2, bc, ubg)

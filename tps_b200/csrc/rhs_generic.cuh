@@ -152,6 +152,17 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
     gen_riemann_lf(g, u1, s2, nor, fx);
     return;
   }
+  if (bc.type == 1) {  // SLIP (wallBC.cpp:326-428): mirror state, Riemann flux only (Roe when useRoe)
+    double vel[3] = {0, 0, 0}, nVel[3];
+    for (int d = 0; d < nvel; d++) vel[d] = u1[1 + d] / u1[0];
+    slip_mirror_velocity(dim, nor, vel, nVel);
+    for (int eq = 0; eq < neq; eq++) s2[eq] = u1[eq];
+    s2[1] = u1[0] * nVel[0];
+    s2[2] = u1[0] * nVel[1];
+    if (dim == 3) s2[3] = u1[0] * nVel[2];
+    gen_riemann(g, u1, s2, nor, fx);
+    return;
+  }
   if (bc.type == 0) {  // INV: mirror state
     const double norm = sqrt(normN);
     double vel[3] = {0, 0, 0};
