@@ -108,6 +108,11 @@ typedef struct {
   int table_n[TPSB_MAX_REACTIONS], table_xlog[TPSB_MAX_REACTIONS], table_flog[TPSB_MAX_REACTIONS];
   const double *table_x[TPSB_MAX_REACTIONS], *table_f[TPSB_MAX_REACTIONS];
   int rate_component[TPSB_MAX_REACTIONS];
+  /* Radiation model NET_EMISSION with a tabulated net emission coefficient (RadiationInput
+   * src/dataStructures.hpp:724-729, NetEmission src/radiation.hpp:57-70): energy sink -4 pi eps_N(T_h) on the total
+   * energy equation (src/source_term.cpp:205-207).  nec_table_n = 0: no radiation.  HOST arrays, copied at create. */
+  int nec_table_n, nec_table_xlog, nec_table_flog;
+  const double *nec_table_x, *nec_table_f;
 } tpsb_plasma_models;
 
 typedef struct {

@@ -11,6 +11,7 @@
 #include "equation_of_state.hpp"
 #include "fluxes.hpp"
 #include "gas_transport.hpp"
+#include "radiation.hpp"
 #include "riemann_solver.hpp"
 #include "transport_properties.hpp"
 
@@ -106,6 +107,7 @@ class MixtureRef : public Physics {
   Fluxes *flux_;
   RiemannSolverTPS *rs_;
   Chemistry *chem_ = nullptr;
+  NetEmission *rad_ = nullptr;
   double rxParams_[34][3];
 
  public:
@@ -182,8 +184,18 @@ class MixtureRef : public Physics {
       }
       chem_ = new Chemistry(mix_, ci);  // chemistry.cpp:40
     }
+    if (pm.nec_table_n > 0) {  // RadiationInput -> NetEmission (radiation.cpp:35)
+      RadiationInput ri;
+      ri.model = NET_EMISSION;
+      ri.necModel = TABULATED_NEC;
+      ri.necTableInput.Ndata = pm.nec_table_n, ri.necTableInput.xdata = pm.nec_table_x, ri.necTableInput.fdata = pm.nec_table_f;
+      ri.necTableInput.xLogScale = pm.nec_table_xlog != 0, ri.necTableInput.fLogScale = pm.nec_table_flog != 0;
+      ri.necTableInput.order = 1;
+      rad_ = new NetEmission(ri);
+    }
   }
   ~MixtureRef() {
+    delete rad_;
     delete chem_;
     delete rs_;
     delete flux_;
@@ -279,6 +291,7 @@ class MixtureRef : public Physics {
       chem_->computeCreationRate(progressRates, creationRates, emissionRates);
       for (int sp = 0; sp < _numActiveSpecies; sp++) srcTerm[2 + _nvel + sp] += creationRates[sp];
     }
+    if (rad_) srcTerm[1 + _nvel] += rad_->computeEnergySink(Th);  // source_term.cpp:205-207
     if (mix_->IsTwoTemperature()) {
       for (int r = 0; r < _numReactions; r++)
         if (chem_->isElectronInvolvedAt(r)) srcTerm[_num_equation - 1] -= chem_->getReactionEnergy(r) * progressRates[r];

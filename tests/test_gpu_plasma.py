@@ -196,3 +196,28 @@ def test_mean_time_derivatives(lib_built):
     got = op.mean_time_derivatives(y)
     ref = np.abs(y.cpu().numpy()).reshape(5, -1).mean(axis=1)
     assert np.allclose(got, ref, rtol=1e-13)
+
+
+@needs_ref
+def test_net_emission_radiation_sink(lib_built, oracle_built):
+    """RadiationInput NET_EMISSION / TABULATED_NEC: -4 pi eps_N(T_h) on the total-energy equation."""
+    import torch
+    d = plasma_cases.ternary_dict()
+    T = np.linspace(300.0, 600.0, 31)
+    d["nec_table"] = (T, 1e3 * (T / 300.0) ** 4, False, False)
+    pm = tps_b200.PlasmaModels.from_dict(d)
+    op, orc = _pair_models(pm, n=(4, 4))
+    op0, _ = _pair_models(plasma_cases.ternary_models(), n=(4, 4))
+    N = orc.N
+    U = np.ascontiguousarray(orc.pt("cons", plasma_cases.smooth_primitives(orc.node_coords())).T).reshape(-1)
+    x = torch.from_numpy(U).cuda()
+    y = op.Mult(x).cpu().numpy()
+    yo = orc.mult(U)
+    for k in range(op.neq):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k
+    y0 = op0.Mult(x).cpu().numpy()
+    Th = op.fields()[0].cpu().numpy()[3 * N:4 * N]
+    sink = -4 * np.pi * np.interp(Th, T, 1e3 * (T / 300.0) ** 4)
+    inside = (Th > 300) & (Th < 600)
+    assert inside.any()
+    assert np.allclose((y - y0)[3 * N:4 * N][inside], sink[inside], rtol=1e-9, atol=1e-6 * np.abs(y0[3 * N:4 * N]).max())

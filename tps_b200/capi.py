@@ -58,7 +58,9 @@ class PlasmaModels(C.Structure):
                 ("mf_freq_multiplier", C.c_double), ("diff_mult", C.c_double), ("mobil_mult", C.c_double),
                 ("table_n", C.c_int * MAX_REACTIONS), ("table_xlog", C.c_int * MAX_REACTIONS),
                 ("table_flog", C.c_int * MAX_REACTIONS), ("table_x", C.POINTER(C.c_double) * MAX_REACTIONS),
-                ("table_f", C.POINTER(C.c_double) * MAX_REACTIONS), ("rate_component", C.c_int * MAX_REACTIONS)]
+                ("table_f", C.POINTER(C.c_double) * MAX_REACTIONS), ("rate_component", C.c_int * MAX_REACTIONS),
+                ("nec_table_n", C.c_int), ("nec_table_xlog", C.c_int), ("nec_table_flog", C.c_int),
+                ("nec_table_x", C.POINTER(C.c_double)), ("nec_table_f", C.POINTER(C.c_double))]
 
     @classmethod
     def from_dict(cls, d):
@@ -81,6 +83,11 @@ class PlasmaModels(C.Structure):
             pm.mf_freq_multiplier, pm.diff_mult, pm.mobil_mult = mult.get("momentum_transfer_frequency", 1.0), mult.get("diffusivity", 1.0), mult.get("mobility", 1.0)
         pm.viscosity, pm.bulk_viscosity = d.get("viscosity", 0.0), d.get("bulk_viscosity", 0.0)
         pm.thermal_conductivity, pm.electron_thermal_conductivity = d.get("thermal_conductivity", 0.0), d.get("electron_thermal_conductivity", 0.0)
+        if d.get("nec_table") is not None:  # net emission coefficient table (x, f, xlog, flog)
+            tx, tf = (np.ascontiguousarray(t, dtype=np.float64) for t in d["nec_table"][:2])
+            pm._keep = getattr(pm, "_keep", []) + [tx, tf]
+            pm.nec_table_n, pm.nec_table_xlog, pm.nec_table_flog = len(tx), int(d["nec_table"][2]), int(d["nec_table"][3])
+            pm.nec_table_x, pm.nec_table_f = _dp(tx), _dp(tf)
         rx = d.get("reactions", [])
         pm.num_reactions, pm.min_temperature = len(rx), d.get("min_temperature", 0.0)
         for r, q in enumerate(rx):

@@ -48,7 +48,8 @@ struct MixParams {
   // TABULATED_RXN (rxModel 2): LinearTable per reaction (table.cpp:76-97) in one device pool, reaction r at
   // tbl + tblOff[r]: x[n] | a[n-1] | b[n-1]
   const double *tbl;
-  int tblOff[MIX_MAXRX], tblN[MIX_MAXRX], tblXlog[MIX_MAXRX], tblFlog[MIX_MAXRX];
+  int tblOff[MIX_MAXRX + 1], tblN[MIX_MAXRX + 1], tblXlog[MIX_MAXRX + 1], tblFlog[MIX_MAXRX + 1];
+  int radiation;  // NetEmission (radiation.hpp:57-70): the net-emission-coefficient table sits in slot MIX_MAXRX
   // GRIDFUNCTION_RXN (rxModel 3): externally supplied rate coefficient per node, component rxComp[r] of
   // rateField[comp][N] (reaction.cpp:86-117); NULL -> 0 like the reference
   const double *rateField;
@@ -872,6 +873,7 @@ MIXBIG void mix_source(const MixParams &m, double *Un, double *upn, const double
       src[2 + nvel + sp] += c;
     }
   }
+  if (m.radiation) src[1 + nvel] += -4.0 * MIX_PI * mix_table_eval(m, MIX_MAXRX, Th);  // source_term.cpp:205-207
   if (m.twoTemp) {
     for (int r = 0; r < m.numReactions; r++)
       if (mix_electron_involved(m, r)) src[neq - 1] -= m.rxEnergy[r] * progress[r];

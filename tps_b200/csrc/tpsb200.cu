@@ -454,13 +454,17 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
     }
     // LinearTable constructor (table.cpp:76-85): slopes / intercepts in the (log) variables
     std::vector<double> tbl;
-    for (int r = 0; r < pm.num_reactions; r++) {
-      m.rxComp[r] = pm.rate_component[r];
-      if (pm.model[r] != 2) continue;
-      const int n = pm.table_n[r];
-      const bool xl = pm.table_xlog[r] != 0, fl = pm.table_flog[r] != 0;
-      m.tblOff[r] = static_cast<int>(tbl.size()), m.tblN[r] = n, m.tblXlog[r] = xl, m.tblFlog[r] = fl;
-      const double *xd = pm.table_x[r], *fd = pm.table_f[r];
+    m.radiation = pm.nec_table_n > 0 ? 1 : 0;
+    for (int r = 0; r <= pm.num_reactions; r++) {
+      const bool nec = r == pm.num_reactions;  // last pass: the net-emission table into slot MIX_MAXRX
+      if (nec && !m.radiation) break;
+      if (!nec) m.rxComp[r] = pm.rate_component[r];
+      if (!nec && pm.model[r] != 2) continue;
+      const int slot = nec ? MIX_MAXRX : r;
+      const int n = nec ? pm.nec_table_n : pm.table_n[r];
+      const bool xl = (nec ? pm.nec_table_xlog : pm.table_xlog[r]) != 0, fl = (nec ? pm.nec_table_flog : pm.table_flog[r]) != 0;
+      m.tblOff[slot] = static_cast<int>(tbl.size()), m.tblN[slot] = n, m.tblXlog[slot] = xl, m.tblFlog[slot] = fl;
+      const double *xd = nec ? pm.nec_table_x : pm.table_x[r], *fd = nec ? pm.nec_table_f : pm.table_f[r];
       tbl.insert(tbl.end(), xd, xd + n);
       std::vector<double> ta(n, 0.0), tb(n, 0.0);
       for (int k = 0; k < n - 1; k++) {
@@ -561,6 +565,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     for (int r = 0; r < pm->num_reactions; r++)
       if (pm->model[r] < 0 || pm->model[r] > 3)
         return fail(ctx, TPSB_ENOTIMPL, "reaction model %d not built (0 Arrhenius, 1 Hoffert-Lien, 2 tabulated, 3 grid function)", pm->model[r]);
+    if (pm->nec_table_n != 0 && (pm->nec_table_n < 2 || pm->nec_table_n > 1000 || !pm->nec_table_x || !pm->nec_table_f))
+      return fail(ctx, TPSB_EINVAL, "the net-emission-coefficient table needs 2..1000 points");
     for (int r = 0; r < pm->num_reactions; r++)
       if (pm->model[r] == 2 && (pm->table_n[r] < 2 || pm->table_n[r] > 1000 || !pm->table_x[r] || !pm->table_f[r]))
         return fail(ctx, TPSB_EINVAL, "reaction %d: a tabulated rate needs 2..1000 table points (gpudata::MAXTABLE)", r);
