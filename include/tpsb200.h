@@ -80,7 +80,7 @@ typedef struct {
   double formation_energy[TPSB_MAX_SPECIES]; /* GasParams::FORMATION_ENERGY [J/mol]            */
   double molar_cv[TPSB_MAX_SPECIES];         /* perfect_mixture/constant_molar_cv, units of R  */
   /* TransportModel value (src/dataStructures.hpp:80-88): 2 constant (src/transport_properties.cpp:303-448),
-   * 0 argon_minimal (fields at the end of this struct)                                              */
+   * 0 argon_minimal, 1 argon_mixture (fields at the end of this struct)                                              */
   int transport_model;
   double viscosity, bulk_viscosity, thermal_conductivity, electron_thermal_conductivity;
   double diffusivity[TPSB_MAX_SPECIES], mt_freq[TPSB_MAX_SPECIES];
@@ -108,6 +108,13 @@ typedef struct {
   int table_n[TPSB_MAX_REACTIONS], table_xlog[TPSB_MAX_REACTIONS], table_flog[TPSB_MAX_REACTIONS];
   const double *table_x[TPSB_MAX_REACTIONS], *table_f[TPSB_MAX_REACTIONS];
   int rate_component[TPSB_MAX_REACTIONS];
+  /* transport_model = argon_mixture (TransportModel value 1): GasMixtureTransport (src/gas_transport.cpp:877-1650),
+   * argon mixtures of up to 7 species.  collision_index[spI + spJ*num_species] (spI <= spJ) = GasColl value
+   * (src/dataStructures.hpp:122-143: 0 CLMB_ATT, 1 CLMB_REP, 2 AR_AR1P, 3 AR_E, 4 AR_AR), as
+   * M2ulPhyS::identifyCollisionType fills GasTransportInput::collisionIndex (src/M2ulPhyS.cpp:3925-3970);
+   * ion_index / neutral_index: the species 'Ar.+1' and 'Ar' (GasTransportInput::ionIndex / neutralIndex).            */
+  int collision_index[TPSB_MAX_SPECIES * TPSB_MAX_SPECIES];
+  int ion_index, neutral_index;
   /* Radiation model NET_EMISSION with a tabulated net emission coefficient (RadiationInput
    * src/dataStructures.hpp:724-729, NetEmission src/radiation.hpp:57-70): energy sink -4 pi eps_N(T_h) on the total
    * energy equation (src/source_term.cpp:205-207).  nec_table_n = 0: no radiation.  HOST arrays, copied at create. */

@@ -49,6 +49,9 @@ struct OrcPlasma {
   int table_n[34], table_xlog[34], table_flog[34];
   const double *table_x[34], *table_f[34];
   int rate_component[34];
+  // transport_model == 1 (ARGON_MIXTURE): GasTransportInput::collisionIndex / ionIndex / neutralIndex
+  int collision_index[64];
+  int ion_index, neutral_index;
   // RadiationInput: NET_EMISSION / TABULATED_NEC table (nec_table_n = 0: none)
   int nec_table_n, nec_table_xlog, nec_table_flog;
   const double *nec_table_x, *nec_table_f;

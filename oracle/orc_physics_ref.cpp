@@ -137,18 +137,27 @@ class MixtureRef : public Physics {
       ct.mtFreq[sp] = sp < pm.num_species ? pm.mt_freq[sp] : 0.0;
     }
     ct.electronIndex = pm.num_species - 2;
-    if (pm.transport_model == 0) {  // ARGON_MINIMAL: GasMinimalTransport (gas_transport.cpp:42)
+    if (pm.transport_model == 0 || pm.transport_model == 1) {  // ARGON_MINIMAL / ARGON_MIXTURE (gas_transport.cpp:42, 877)
       GasTransportInput gi;
       memset(&gi, 0, sizeof(gi));
       gi.gas = Ar;
       gi.ionIndex = 0, gi.electronIndex = pm.num_species - 2, gi.neutralIndex = pm.num_species - 1;
+      if (pm.transport_model == 1) {
+        gi.ionIndex = pm.ion_index, gi.neutralIndex = pm.neutral_index;
+        for (int i = 0; i < pm.num_species; i++)
+          for (int j = i; j < pm.num_species; j++)
+            gi.collisionIndex[i + j * pm.num_species] = static_cast<GasColl>(pm.collision_index[i + j * pm.num_species]);
+      }
       gi.neutralIndex2 = -1, gi.ionIndex2 = -1;
       gi.thirdOrderkElectron = pm.third_order_k_electron != 0;
       gi.multiply = pm.multiply != 0;
       for (int t = 0; t < 4; t++) gi.fluxTrnsMultiplier[t] = pm.flux_trns_multiplier[t];
       gi.spcsTrnsMultiplier[0] = pm.mf_freq_multiplier;
       gi.diffMult = pm.diff_mult, gi.mobilMult = pm.mobil_mult;
-      trans_ = new GasMinimalTransport(mix_, gi);
+      if (pm.transport_model == 1)
+        trans_ = new GasMixtureTransport(mix_, gi);
+      else
+        trans_ = new GasMinimalTransport(mix_, gi);
     } else {
       trans_ = new ConstantTransport(mix_, ct);  // transport_properties.cpp:303
     }

@@ -72,6 +72,21 @@ def test_plasma_axisym_configuration_c4(lib_built, oracle_built, nvel, bc, ubg):
 
 
 @needs_ref
+def test_plasma_axisym_c4_with_argon_mixture_transport(lib_built, oracle_built):
+    """Config C4 with the collision-integral transport variant (transport_model = argon_mixture) instead of constants."""
+    m = ac.box(n=(4, 3), warp=0.05)
+    d = ac.argon6_dict()
+    d.update(transport_model="argon_mixture", third_order_k_electron=True)
+    op, orc = ac.make_pair(m, 3, 1, 0, 0, 3, "c4", True, mixture=d)
+    up = ac.argon6_primitives(orc.node_coords(), 3)
+    up[:, 4] *= 8.0   # T_h ~ 7000 K
+    up[:, 10] *= 3.0  # T_e ~ 9000 K
+    up[:, 9] = up[:, 5]  # quasi-neutral
+    U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+    _compare(op, orc, U)
+
+
+@needs_ref
 def test_ternary_mixture_with_walls(lib_built, oracle_built):
     import plasma_cases
     import tps_b200

@@ -221,3 +221,38 @@ def test_net_emission_radiation_sink(lib_built, oracle_built):
     inside = (Th > 300) & (Th < 600)
     assert inside.any()
     assert np.allclose((y - y0)[3 * N:4 * N][inside], sink[inside], rtol=1e-9, atol=1e-6 * np.abs(y0[3 * N:4 * N]).max())
+
+
+@needs_ref
+@pytest.mark.parametrize("third,mult", [(False, None), (True, None), (True, MULT)])
+def test_argon_mixture_transport_equals_reference_classes(lib_built, oracle_built, third, mult):
+    """GasMixtureTransport (generic collision-integral transport over the species-pair collision types: screened
+    Coulomb attractive / repulsive, Ar-Ar, Ar-Ar.+1, Ar-E) for the six-species argon mixture of config C4, point-wise
+    against the reference's own gas_transport.cpp object code."""
+    import axisym_cases as ac
+    import torch
+    d = ac.argon6_dict()
+    d.update(transport_model="argon_mixture", third_order_k_electron=third)
+    if mult:
+        d["multipliers"] = mult
+    pm = tps_b200.PlasmaModels.from_dict(d)
+    op, orc = _pair_models(pm, order=2, n=(3, 3))
+    assert op.neq == 10
+    rng = np.random.default_rng(11)
+    n = 300
+    up = np.zeros((n, 10))
+    up[:, 0] = rng.uniform(0.04, 0.08, n)
+    up[:, 1:3] = rng.uniform(-300, 300, (n, 2))
+    up[:, 3] = rng.uniform(3000, 12000, n)
+    up[:, 4:9] = rng.uniform(1e-4, 0.03, (n, 5))
+    up[:, 8] = up[:, 4]  # quasi-neutral: n_e = n_ion
+    up[:, 9] = rng.uniform(5000, 15000, n)
+    U = orc.pt("cons", up)
+    g = rng.normal(size=(n, 20)) * np.array(([0.005, 50, 50, 800] + [0.01] * 5 + [900]) * 2)
+    Ud, gd = torch.from_numpy(U).cuda(), torch.from_numpy(g).cuda()
+    t = 5e-10 if third else 1e-11
+    for what, args, tol in (("visc_flux", (U, g), t), ("source", (U, orc.pt("prim", U), g), 1e-11)):
+        ref = orc.pt(what, *args)
+        got = op.point_eval(what, Ud, gd).cpu().numpy()
+        scale = np.abs(ref).max(axis=0)
+        assert (np.abs(got - ref) <= tol * scale + 1e-300).all(), (what, np.abs(got - ref).max(axis=0) / (scale + 1e-300))

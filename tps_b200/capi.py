@@ -59,6 +59,7 @@ class PlasmaModels(C.Structure):
                 ("table_n", C.c_int * MAX_REACTIONS), ("table_xlog", C.c_int * MAX_REACTIONS),
                 ("table_flog", C.c_int * MAX_REACTIONS), ("table_x", C.POINTER(C.c_double) * MAX_REACTIONS),
                 ("table_f", C.POINTER(C.c_double) * MAX_REACTIONS), ("rate_component", C.c_int * MAX_REACTIONS),
+                ("collision_index", C.c_int * (MAX_SPECIES * MAX_SPECIES)), ("ion_index", C.c_int), ("neutral_index", C.c_int),
                 ("nec_table_n", C.c_int), ("nec_table_xlog", C.c_int), ("nec_table_flog", C.c_int),
                 ("nec_table_x", C.POINTER(C.c_double)), ("nec_table_f", C.POINTER(C.c_double))]
 
@@ -73,7 +74,20 @@ class PlasmaModels(C.Structure):
         for i, s_ in enumerate(sp):
             pm.mw[i], pm.charge[i], pm.formation_energy[i] = s_["mw"], s_["charge"], s_["formation_energy"]
             pm.molar_cv[i], pm.diffusivity[i], pm.mt_freq[i] = s_["molar_cv"], s_.get("diffusivity", 0.0), s_.get("mt_freq", 0.0)
-        pm.transport_model = {"constant": 2, "argon_minimal": 0}[d.get("transport_model", "constant")]
+        pm.transport_model = {"constant": 2, "argon_minimal": 0, "argon_mixture": 1}[d.get("transport_model", "constant")]
+        if pm.transport_model == 1:
+            # M2ulPhyS::identifyCollisionType (src/M2ulPhyS.cpp:3925-3970); species kinds 'ion' (Ar.+1), 'electron',
+            # 'neutral' (Ar and its excited states)
+            ns = len(sp)
+            kinds = [("electron" if q["charge"] < 0 else "ion" if q["charge"] > 0 else "neutral") for q in sp]
+            for i in range(ns):
+                for j in range(i, ns):
+                    zz = sp[i]["charge"] * sp[j]["charge"]
+                    pair = {kinds[i], kinds[j]}
+                    pm.collision_index[i + j * ns] = (1 if zz > 0 else 0 if zz < 0 else 4 if pair == {"neutral"} else
+                                                      2 if pair == {"neutral", "ion"} else 3)
+            pm.ion_index = d.get("ion_index", kinds.index("ion"))
+            pm.neutral_index = d.get("neutral_index", ns - 1)
         pm.third_order_k_electron = int(d.get("third_order_k_electron", False))
         mult = d.get("multipliers")
         pm.multiply = int(mult is not None)

@@ -37,7 +37,10 @@ struct MixParams {
   // GasMinimalTransport, argon ternary (gas_transport.cpp:42-157): species indices, per-particle masses mw / N_A,
   // reduced masses, third-order electron conductivity switch, artificial multipliers
   int gmIon, gmElectron, gmNeutral, thirdOrderKe, multiply;
-  double gmMw[3], gmMuw[9], fluxMult[4], mfFreqMult, diffMult, mobilMult;
+  double gmMw[MIX_MAXSP], gmMuw[MIX_MAXSP * MIX_MAXSP], fluxMult[4], mfFreqMult, diffMult, mobilMult;
+  // GasMixtureTransport (transportModel 1, gas_transport.cpp:877-1650): collision type per species pair,
+  // GasColl values (dataStructures.hpp:122-143) at [spI + spJ*numSpecies], spI <= spJ
+  int collIdx[MIX_MAXSP * MIX_MAXSP];
   // Chemistry (chemistry.cpp:40-113)
   int numReactions, chElectron;
   double minTemp;
@@ -323,6 +326,15 @@ MIXFN double coll_att12(double Tp) { return coll_charged(0.0991, 7.4684, 1.0155,
 MIXFN double coll_att13(double Tp) { return coll_charged(0.0616, 7.8271, 0.9452, 1.1105, Tp); }
 MIXFN double coll_att14(double Tp) { return coll_charged(0.0308, 13.9567, 0.9511, 1.1803, Tp); }
 MIXFN double coll_att15(double Tp) { return coll_charged(0.0232, 13.7888, 0.9148, 1.1532, Tp); }
+MIXFN double coll_att22(double Tp) { return coll_charged(0.2423, 4.6796, 1.3290, 1.1279, Tp); }
+MIXFN double coll_att23(double Tp) { return coll_charged(0.1221, 8.7542, 1.3875, 1.1110, Tp); }
+MIXFN double coll_att24(double Tp) { return coll_charged(0.0619, 18.2538, 1.4341, 1.1618, Tp); }
+MIXFN double coll_rep11(double Tp) { return coll_charged(0.3904, 0.9100, 1.1025, 1.0544, Tp); }
+MIXFN double coll_rep12(double Tp) { return coll_charged(0.1547, 1.6597, 1.1725, 0.9792, Tp); }
+MIXFN double coll_rep13(double Tp) { return coll_charged(0.0814, 2.5815, 1.1948, 0.9570, Tp); }
+MIXFN double coll_rep14(double Tp) { return coll_charged(0.0683, 1.9774, 1.2033, 0.8264, Tp); }
+MIXFN double coll_rep15(double Tp) { return coll_charged(0.0346, 4.5177, 1.2132, 0.9294, Tp); }
+MIXFN double coll_ArAr11(double T) { return 2.2910e-18 * pow(T, -0.3032); }
 MIXFN double coll_rep22(double Tp) { return coll_charged(0.4128, 1.2436, 1.1830, 1.0123, Tp); }
 MIXFN double coll_rep23(double Tp) { return coll_charged(0.2203, 1.8832, 1.2059, 0.9851, Tp); }
 MIXFN double coll_rep24(double Tp) { return coll_charged(0.1323, 2.7248, 1.2129, 0.9847, Tp); }
@@ -476,6 +488,139 @@ MIXBIG double gm_third_order_ke(const MixParams &m, const double *X_sp, const Gm
   return viscosityFactor * kOverEtaFactor * sqrt(2.0 * Te / m.gmMw[e]) * X_sp[e] / (L11 - L12 * L12 / L22);
 }
 
+// ---- GasMixtureTransport (argon mixtures of up to 7 species: Ar, Ar.+1, excited states, E) ----
+// GasMinimalTransport::computeCollisionInputs (gas_transport.cpp:185-204): Debye length from ALL charged species at T_e
+struct GmxColl {
+  double Te, Th, debyeCircle, ndimTe, ndimTh;
+};
+MIXFN GmxColl gmx_collision_inputs(const MixParams &m, double Te, double Th, const double *n_sp) {
+  GmxColl c;
+  c.Te = Te, c.Th = Th;
+  double nOverT = 0.0;
+  for (int sp = 0; sp < m.numSpecies; sp++) nOverT += (n_sp[sp] + MIX_XEPS) / Te * m.charge[sp] * m.charge[sp];
+  const double debyeLength = sqrt(MIX_DEBYE / MIX_NA / nOverT);
+  c.debyeCircle = MIX_PI * debyeLength * debyeLength;
+  c.ndimTe = debyeLength * 4.0 * MIX_PI * MIX_DEBYE * Te;
+  c.ndimTh = debyeLength * 4.0 * MIX_PI * MIX_DEBYE * Th;
+  return c;
+}
+// GasMixtureTransport::collisionIntegral (gas_transport.cpp:995-1283), charged and argon pairs.  Unsupported (l, r)
+// return NaN (the reference asserts).
+MIXBIG double gmx_collision_integral(const MixParams &m, int _spI, int _spJ, int l, int r, const GmxColl &ci) {
+  const int spI = (_spI > _spJ) ? _spJ : _spI, spJ = (_spI > _spJ) ? _spI : _spJ;
+  const int e = m.gmElectron;
+  const int collIdx = m.collIdx[spI + spJ * m.numSpecies];
+  double temp;
+  if (collIdx == 0 || collIdx == 1) {
+    temp = ((spI == e) || (spJ == e)) ? ci.ndimTe : ci.ndimTh;
+  } else {
+    temp = ((spI == e) || (spJ == e)) ? ci.Te : ci.Th;
+  }
+  const double nan = NAN;
+  switch (collIdx) {
+    case 0:  // CLMB_ATT
+      if (l == 1) {
+        switch (r) {
+          case 1: return ci.debyeCircle * coll_att11(temp);
+          case 2: return ci.debyeCircle * coll_att12(temp);
+          case 3: return ci.debyeCircle * coll_att13(temp);
+          case 4: return ci.debyeCircle * coll_att14(temp);
+          case 5: return ci.debyeCircle * coll_att15(temp);
+        }
+      } else if (l == 2) {
+        switch (r) {
+          case 2: return ci.debyeCircle * coll_att22(temp);
+          case 3: return ci.debyeCircle * coll_att23(temp);
+          case 4: return ci.debyeCircle * coll_att24(temp);
+        }
+      }
+      return nan;
+    case 1:  // CLMB_REP
+      if (l == 1) {
+        switch (r) {
+          case 1: return ci.debyeCircle * coll_rep11(temp);
+          case 2: return ci.debyeCircle * coll_rep12(temp);
+          case 3: return ci.debyeCircle * coll_rep13(temp);
+          case 4: return ci.debyeCircle * coll_rep14(temp);
+          case 5: return ci.debyeCircle * coll_rep15(temp);
+        }
+      } else if (l == 2) {
+        switch (r) {
+          case 2: return ci.debyeCircle * coll_rep22(temp);
+          case 3: return ci.debyeCircle * coll_rep23(temp);
+          case 4: return ci.debyeCircle * coll_rep24(temp);
+        }
+      }
+      return nan;
+    case 2:  // AR_AR1P
+      return (l == 1 && r == 1) ? coll_ArAr1P11(temp) : nan;
+    case 3:  // AR_E
+      return (l == 1 && r >= 1 && r <= 5) ? coll_eAr(r, temp) : nan;
+    case 4:  // AR_AR
+      return (l == 1 && r == 1) ? coll_ArAr11(temp) : ((l == 2 && r == 2) ? coll_ArAr22(temp) : nan);
+  }
+  return nan;
+}
+// binary diffusivities, Curtiss-Hirschfelder, mobilities, multipliers (gas_transport.cpp:1323-1349)
+MIXBIG void gmx_diffusivity_mobility(const MixParams &m, const double *X_sp, const double *Y_sp, double nTotal, const GmxColl &ci,
+                                     double *diffusivity, double *mobility) {
+  const int ns = m.numSpecies, e = m.gmElectron;
+  const double diffusivityFactor = 3. / 16. * sqrt(2.0 * MIX_PI * MIX_KB) / MIX_NA;
+  double bd[MIX_MAXSP * MIX_MAXSP];
+  for (int spI = 0; spI < ns - 1; spI++)
+    for (int spJ = spI + 1; spJ < ns; spJ++) {
+      const double temp = ((spI == e) || (spJ == e)) ? ci.Te : ci.Th;
+      bd[spI + spJ * ns] = diffusivityFactor * sqrt(temp / m.gmMuw[spI + spJ * ns]) / nTotal / gmx_collision_integral(m, spI, spJ, 1, 1, ci);
+      bd[spJ + spI * ns] = bd[spI + spJ * ns];
+    }
+  for (int sp = 0; sp < ns; sp++) diffusivity[sp] = 0.0;
+  for (int spI = 0; spI < ns; spI++) {
+    for (int spJ = 0; spJ < ns; spJ++) {
+      if (spI == spJ) continue;
+      diffusivity[spI] += (X_sp[spJ] + MIX_XEPS) / bd[spI + spJ * ns];
+    }
+    diffusivity[spI] = (1.0 - Y_sp[spI]) / diffusivity[spI];
+  }
+  for (int sp = 0; sp < ns; sp++) {
+    const double temp = (sp == e) ? ci.Te : ci.Th;
+    mobility[sp] = MIX_QE_OVER_KB * m.charge[sp] / temp * diffusivity[sp];
+  }
+  if (m.multiply)
+    for (int sp = 0; sp < ns; sp++) {
+      diffusivity[sp] *= m.diffMult;
+      mobility[sp] *= m.mobilMult;
+    }
+}
+// species viscosities -> mixture viscosity (gas_transport.cpp:1300-1312, 1508-1520)
+MIXFN double gmx_viscosity(const MixParams &m, const double *X_sp, const GmxColl &ci, double *speciesViscosity) {
+  const double viscosityFactor = 5. / 16. * sqrt(MIX_PI * MIX_KB);
+  double avg = 0.0;
+  for (int sp = 0; sp < m.numSpecies; sp++) {
+    speciesViscosity[sp] = (sp == m.gmElectron) ? 0.0 : viscosityFactor * sqrt(m.gmMw[sp] * ci.Th) / gmx_collision_integral(m, sp, sp, 2, 2, ci);
+  }
+  for (int sp = 0; sp < m.numSpecies; sp++) avg += X_sp[sp] * speciesViscosity[sp];
+  return avg;
+}
+// GasMixtureTransport::computeThirdOrderElectronThermalConductivity (gas_transport.cpp:1388-1407)
+MIXBIG double gmx_third_order_ke(const MixParams &m, const double *X_sp, const GmxColl &ci) {
+  const double viscosityFactor = 5. / 16. * sqrt(MIX_PI * MIX_KB), kOverEtaFactor = 15. / 4. * MIX_KB;
+  const int e = m.gmElectron;
+  double Q2[3];
+  for (int r = 0; r < 3; r++) Q2[r] = gmx_collision_integral(m, e, e, 2, r + 2, ci);
+  double L11 = sqrt(2.0) * X_sp[e] * Q2[0];
+  double L12 = sqrt(2.0) * X_sp[e] * (1.75 * Q2[0] - 2.0 * Q2[1]);
+  double L22 = sqrt(2.0) * X_sp[e] * (4.8125 * Q2[0] - 7.0 * Q2[1] + 5. * Q2[2]);
+  for (int sp = 0; sp < m.numSpecies; sp++) {
+    if (sp == e) continue;
+    double Q1[5];
+    for (int r = 0; r < 5; r++) Q1[r] = gmx_collision_integral(m, sp, e, 1, r + 1, ci);
+    L11 += X_sp[sp] * (6.25 * Q1[0] - 15. * Q1[1] + 12. * Q1[2]);
+    L12 += X_sp[sp] * (10.9375 * Q1[0] - 39.375 * Q1[1] + 57. * Q1[2] - 30. * Q1[3]);
+    L22 += X_sp[sp] * (19.140625 * Q1[0] - 91.875 * Q1[1] + 199.5 * Q1[2] - 210. * Q1[3] + 90. * Q1[4]);
+  }
+  return viscosityFactor * kOverEtaFactor * sqrt(2.0 * ci.Te / m.gmMw[e]) * X_sp[e] / (L11 - L12 * L12 / L22);
+}
+
 // TransportProperties::ComputeFluxTransportProperties -> {Constant, GasMinimal}Transport::ComputeFluxMolecularTransport
 // (transport_properties.cpp:332-383, gas_transport.cpp:206-398): tb = {viscosity, bulk viscosity, heavy thermal
 // conductivity, electron thermal conductivity}, diffusion velocities V[sp + d*numSpecies].
@@ -490,9 +635,29 @@ MIXBIG void mix_flux_transport(const MixParams &m, const double *s, const double
   mix_prim(m, s, prim);
   mix_species_primitives(m, s, X_sp, Y_sp, n_sp);
   double nTotal = 0.0;
-  for (int sp = 0; sp < 3; sp++) nTotal += n_sp[sp];
+  for (int sp = 0; sp < m.numSpecies; sp++) nTotal += n_sp[sp];
   const double Te = m.twoTemp ? prim[m.neq - 1] : prim[m.nvel + 1];
   const double Th = prim[m.nvel + 1];
+  if (m.transportModel == 1) {  // GasMixtureTransport::ComputeFluxMolecularTransport (gas_transport.cpp:1285-1386)
+    const GmxColl ci = gmx_collision_inputs(m, Te, Th, n_sp);
+    const double vF = 5. / 16. * sqrt(MIX_PI * MIX_KB), kF = 15. / 4. * MIX_KB;
+    double spVisc[MIX_MAXSP], diffusivity[MIX_MAXSP];
+    tb[0] = gmx_viscosity(m, X_sp, ci, spVisc);
+    tb[2] = 0.0;
+    for (int sp = 0; sp < m.numSpecies; sp++) tb[2] += X_sp[sp] * (sp == m.gmElectron ? 0.0 : spVisc[sp] * kF / m.gmMw[sp]);
+    tb[1] = 0.0;
+    if (m.thirdOrderKe) {
+      tb[3] = gmx_third_order_ke(m, X_sp, ci);
+    } else {
+      tb[3] = vF * kF * sqrt(ci.Te / m.gmMw[m.gmElectron]) * X_sp[m.gmElectron] /
+              gmx_collision_integral(m, m.gmElectron, m.gmElectron, 2, 2, ci);
+    }
+    gmx_diffusivity_mobility(m, X_sp, Y_sp, nTotal, ci, diffusivity, mob);
+    if (m.multiply)
+      for (int t = 0; t < 4; t++) tb[t] *= m.fluxMult[t];
+    mix_diffusion_velocity(m, X_sp, Y_sp, n_sp, gr, diffusivity, mob, V);
+    return;
+  }
   const GmDebye db = gm_debye(m, n_sp, Te, Th);
   const double viscosityFactor = 5. / 16. * sqrt(MIX_PI * MIX_KB), kOverEtaFactor = 15. / 4. * MIX_KB;
   double spVisc[3], spK[3];
@@ -529,8 +694,18 @@ MIXBIG void mix_source_transport(const MixParams &m, const double *Un, const dou
   mix_species_primitives(m, Un, X_sp, Y_sp, n_sp);
   const double Te = m.twoTemp ? upn[m.neq - 1] : upn[m.nvel + 1];
   const double Th = upn[m.nvel + 1];
-  const GmDebye db = gm_debye(m, n_sp, Te, Th);
   const double mfFreqFactor = 4. / 3. * MIX_NA * sqrt(8. * MIX_KB / MIX_PI);
+  if (m.transportModel == 1) {  // GasMixtureTransport::ComputeSourceMolecularTransport (gas_transport.cpp:1409-1497)
+    const GmxColl ci = gmx_collision_inputs(m, Te, Th, n_sp);
+    for (int sp = 0; sp < m.numSpecies; sp++) {
+      mtFreq[sp] = (sp == m.gmElectron) ? 0.0
+                                        : mfFreqFactor * sqrt(ci.Te / m.gmMw[m.gmElectron]) * n_sp[sp] *
+                                              gmx_collision_integral(m, sp, m.gmElectron, 1, 1, ci);
+      if (m.multiply) mtFreq[sp] *= m.mfFreqMult;
+    }
+    return;
+  }
+  const GmDebye db = gm_debye(m, n_sp, Te, Th);
   const double Qea = coll_eAr(1, Te), Qie = coll_att11(db.nondimTe) * db.circle;
   for (int sp = 0; sp < 3; sp++) mtFreq[sp] = 0.0;
   mtFreq[m.gmIon] = mfFreqFactor * sqrt(Te / m.gmMw[m.gmElectron]) * n_sp[m.gmIon] * Qie;
@@ -728,12 +903,17 @@ MIXBIG void mix_viscosities(const MixParams &m, const double *U, const double *U
     visc[1] = m.bulk;
     return;
   }
-  double n_sp[MIX_MAXSP], X_sp[MIX_MAXSP], Y_sp[MIX_MAXSP], spVisc[3];
+  double n_sp[MIX_MAXSP], X_sp[MIX_MAXSP], Y_sp[MIX_MAXSP], spVisc[MIX_MAXSP];
   mix_species_primitives(m, U, X_sp, Y_sp, n_sp);
   const double Te = m.twoTemp ? Up[m.neq - 1] : Up[m.nvel + 1];
   const double Th = Up[m.nvel + 1];
-  const GmDebye db = gm_debye(m, n_sp, Te, Th);
-  visc[0] = gm_viscosity(m, X_sp, Th, db, spVisc);
+  if (m.transportModel == 1) {  // GasMixtureTransport::GetViscosities (gas_transport.cpp:1499-1546)
+    const GmxColl ci = gmx_collision_inputs(m, Te, Th, n_sp);
+    visc[0] = gmx_viscosity(m, X_sp, ci, spVisc);
+  } else {
+    const GmDebye db = gm_debye(m, n_sp, Te, Th);
+    visc[0] = gm_viscosity(m, X_sp, Th, db, spVisc);
+  }
   visc[1] = 0.0;
   if (m.multiply) {
     visc[0] *= m.fluxMult[0];

@@ -429,14 +429,17 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
     m.visc = pm.viscosity, m.bulk = pm.bulk_viscosity, m.kh = pm.thermal_conductivity, m.ke = pm.electron_thermal_conductivity;
     m.trElectron = m.iElectron, m.chElectron = m.iElectron;
     m.transportModel = pm.transport_model;
-    if (pm.transport_model == 0) {  // GasMinimalTransport ctor (gas_transport.cpp:42-157)
-      m.gmIon = 0, m.gmElectron = m.iElectron, m.gmNeutral = m.iBackground;
+    if (pm.transport_model == 0 || pm.transport_model == 1) {  // Gas{Minimal,Mixture}Transport ctor (gas_transport.cpp:42-157, 877-985)
+      const int ns = m.numSpecies;
+      m.gmIon = pm.transport_model == 1 ? pm.ion_index : 0, m.gmElectron = m.iElectron;
+      m.gmNeutral = pm.transport_model == 1 ? pm.neutral_index : m.iBackground;
       m.thirdOrderKe = pm.third_order_k_electron ? 1 : 0, m.multiply = pm.multiply ? 1 : 0;
-      for (int sp = 0; sp < 3; sp++) m.gmMw[sp] = pm.mw[sp] / MIX_NA;
-      for (int i = 0; i < 3; i++)
-        for (int j = i; j < 3; j++) {
-          m.gmMuw[i + j * 3] = m.gmMw[i] * m.gmMw[j] / (m.gmMw[i] + m.gmMw[j]);
-          if (i != j) m.gmMuw[j + i * 3] = m.gmMuw[i + j * 3];
+      for (int sp = 0; sp < ns; sp++) m.gmMw[sp] = pm.mw[sp] / MIX_NA;
+      for (int i = 0; i < ns; i++)
+        for (int j = i; j < ns; j++) {
+          m.gmMuw[i + j * ns] = m.gmMw[i] * m.gmMw[j] / (m.gmMw[i] + m.gmMw[j]);
+          if (i != j) m.gmMuw[j + i * ns] = m.gmMuw[i + j * ns];
+          m.collIdx[i + j * ns] = pm.collision_index[i + j * ns];
         }
       for (int t = 0; t < 4; t++) m.fluxMult[t] = pm.flux_trns_multiplier[t];
       m.mfFreqMult = pm.mf_freq_multiplier, m.diffMult = pm.diff_mult, m.mobilMult = pm.mobil_mult;
@@ -557,8 +560,18 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     const tpsb_plasma_models *pm = phys->plasma;
     if (!pm) return fail(ctx, TPSB_EINVAL, "fluid = user_defined needs tpsb_physics.plasma");
     if (pm->num_species < 3 || pm->num_species > TPSB_MAX_SPECIES) return fail(ctx, TPSB_EINVAL, "num_species must be 3..%d (electron and background included)", TPSB_MAX_SPECIES);
-    if (pm->transport_model != 2 && pm->transport_model != 0)
-      return fail(ctx, TPSB_ENOTIMPL, "transport_model %d not built (2 constant, 0 argon_minimal)", pm->transport_model);
+    if (pm->transport_model < 0 || pm->transport_model > 2)
+      return fail(ctx, TPSB_ENOTIMPL, "transport_model %d not built (2 constant, 0 argon_minimal, 1 argon_mixture)", pm->transport_model);
+    if (pm->transport_model == 1) {
+      if (pm->num_species > 7) return fail(ctx, TPSB_EINVAL, "argon_mixture transport serves at most 7 species (gas_transport.cpp:903)");
+      if (pm->ion_index < 0 || pm->ion_index >= pm->num_species || pm->neutral_index < 0 || pm->neutral_index >= pm->num_species)
+        return fail(ctx, TPSB_EINVAL, "argon_mixture transport needs the indices of 'Ar.+1' and 'Ar'");
+      for (int i = 0; i < pm->num_species; i++)
+        for (int j = i; j < pm->num_species; j++)
+          if (pm->collision_index[i + j * pm->num_species] < 0 || pm->collision_index[i + j * pm->num_species] > 4)
+            return fail(ctx, TPSB_ENOTIMPL, "collision type %d of species pair (%d, %d) not built (argon and Coulomb pairs only)",
+                        pm->collision_index[i + j * pm->num_species], i, j);
+    }
     if (pm->transport_model == 0 && (pm->num_species != 3 || !(pm->charge[0] > 0) || !(pm->charge[1] < 0) || pm->charge[2] != 0))
       return fail(ctx, TPSB_EINVAL, "argon_minimal transport serves the ternary mixture [Ar.+1, E, Ar] only (gas_transport.cpp:51-56)");
     if (pm->num_reactions < 0 || pm->num_reactions > TPSB_MAX_REACTIONS) return fail(ctx, TPSB_EINVAL, "too many reactions");
