@@ -126,6 +126,34 @@ __device__ __forceinline__ void dry_visc_flux(const PhysParams &p, const double 
   }
 }
 
+// branch-free double reciprocal / square root: MUFU seed + Newton steps, ~1 ulp.  The MUFU.RCP64H /
+// MUFU.RSQ64H seeds carry only ~9 good bits (the library routines spend 5-6 DFMAs on them as well), so
+// one cubic step (error e^3) plus one quadratic step (e^6) are needed.  What is saved against the library
+// divide / sqrt is the slow-path branch (BSSY/BSYNC + call) per use; arguments here are positive, O(1)-scaled
+// physical quantities (rho, T, p/rho, |v|^2 >= 0).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, fma(e, e, e), r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+// sqrt(x) for x >= 0 (returns 0 at 0)
+__device__ __forceinline__ double fast_sqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(fmax(x, 1e-300)));
+  // r <- r (1 + e/2 + 3 e^2/8), e = 1 - x r^2 (cubic), one Newton step, then Heron on s = x r
+  double e = fma(-x * r, r, 1.0);
+  r = fma(r * e, fma(0.375, e, 0.5), r);
+  e = fma(-x * r, r, 1.0);
+  r = fma(0.5 * r, e, r);
+  double s = x * r;
+  s = fma(fma(-s, s, x), 0.5 * r, s);
+  return s;
+}
+
 // ---- fused / reciprocal forms used by the hot kernels -------------------------------------------
 // Same formulas as above with 1/rho formed once and the normal contraction done analytically; they
 // differ from the reference's operation order by a few ulp (well inside the 1e-10 parity bound) and
@@ -135,7 +163,7 @@ struct DryPoint {
 };
 __device__ __forceinline__ DryPoint dry_point(const PhysParams &p, const double *s) {
   DryPoint q;
-  q.rinv = 1.0 / s[0];
+  q.rinv = fast_rcp(s[0]);
   q.vel[0] = s[1] * q.rinv;
   q.vel[1] = s[2] * q.rinv;
   q.vel[2] = s[3] * q.rinv;
@@ -143,7 +171,7 @@ __device__ __forceinline__ DryPoint dry_point(const PhysParams &p, const double 
   return q;
 }
 __device__ __forceinline__ double dry_char_speed_pt(const PhysParams &p, const DryPoint &q) {
-  return sqrt(q.vel[0] * q.vel[0] + q.vel[1] * q.vel[1] + q.vel[2] * q.vel[2]) + sqrt(p.gamma * q.p * q.rinv);
+  return fast_sqrt(q.vel[0] * q.vel[0] + q.vel[1] * q.vel[1] + q.vel[2] * q.vel[2]) + fast_sqrt(p.gamma * q.p * q.rinv);
 }
 // F_c(s).n
 __device__ __forceinline__ void dry_conv_dot_n(const double *s, const DryPoint &q, const double *nor, double *fn) {
@@ -158,7 +186,7 @@ __device__ __forceinline__ void dry_conv_dot_n(const double *s, const DryPoint &
 __device__ __forceinline__ void dry_transport_pt(const PhysParams &p, const DryPoint &q, double &visc, double &bulk,
                                                  double &k) {
   const double temp = q.p * q.rinv / p.R;
-  visc = p.C1 * p.visc_mult * (temp * sqrt(temp)) / (temp + p.S0);
+  visc = p.C1 * p.visc_mult * (temp * fast_sqrt(temp)) * fast_rcp(temp + p.S0);
   bulk = (p.bulk_visc_mult - 2. / 3.) * visc;
   k = p.cp_div_pr * visc;
 }

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
 #pragma unroll
     for (int r = 0; r < DIM; r++) {
       const int c = idx[r];
-      const FacePar fm = decode_face(sFp[kFaceMinus[r]]), fpl = decode_face(sFp[kFacePlus[r]]);
+      const FacePar fm = decode_face(kFacePar(kFaceMinus[r])), fpl = decode_face(kFacePar(kFacePlus[r]));
       const int iam = pick3(fm.as, i, j, k), ibm = pick3(fm.at, i, j, k);
       const int abm = (fm.ss ? iam : NP - 1 - iam) + NP * (fm.st ? ibm : NP - 1 - ibm);
       const int iap = pick3(fpl.as, i, j, k), ibp = pick3(fpl.at, i, j, k);
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(64 * EPB, MINB)
     dOff0[d] = pad_node(base(L0) + (fr & 3) * str);
     dOff1[d] = pad_node(base(L0 + 1) + (fr & 3) * str);
     // face node of line L on the -/+ face of axis d (rows 4 / 5)
-    const FacePar fp = decode_face(sFp[(fr & 1) ? kFacePlus[d] : kFaceMinus[d]]);
+    const FacePar fp = (fr & 1) ? decode_face(kFacePar(kFacePlus[d])) : decode_face(kFacePar(kFaceMinus[d]));
     auto abof = [&](int L) {
       const int nb = base(L), i = nb & 3, j = (nb >> 2) & 3, k = nb >> 4;
       const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(64 * EPB, MINB)
 #pragma unroll
     for (int r = 0; r < DIM; r++) {
       const int c = idx[r];
-      const FacePar fm = decode_face(sFp[kFaceMinus[r]]), fpl = decode_face(sFp[kFacePlus[r]]);
+      const FacePar fm = decode_face(kFacePar(kFaceMinus[r])), fpl = decode_face(kFacePar(kFacePlus[r]));
       const int iam = pick3(fm.as, i, j, k), ibm = pick3(fm.at, i, j, k);
       const int abm = (fm.ss ? iam : NP - 1 - iam) + NP * (fm.st ? ibm : NP - 1 - ibm);
       const int iap = pick3(fpl.as, i, j, k), ibp = pick3(fpl.at, i, j, k);
@@ -484,34 +484,6 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
-}
-
-// branch-free double reciprocal / square root: MUFU seed + Newton steps, ~1 ulp.  The MUFU.RCP64H /
-// MUFU.RSQ64H seeds carry only ~9 good bits (the library routines spend 5-6 DFMAs on them as well), so
-// one cubic step (error e^3) plus one quadratic step (e^6) are needed.  What is saved against the library
-// divide / sqrt is the slow-path branch (BSSY/BSYNC + call) per use; arguments here are positive, O(1)-scaled
-// physical quantities (rho, T, p/rho, |v|^2 >= 0).
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, fma(e, e, e), r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-// sqrt(x) for x >= 0 (returns 0 at 0)
-__device__ __forceinline__ double fast_sqrt(double x) {
-  double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(fmax(x, 1e-300)));
-  // r <- r (1 + e/2 + 3 e^2/8), e = 1 - x r^2 (cubic), one Newton step, then Heron on s = x r
-  double e = fma(-x * r, r, 1.0);
-  r = fma(r * e, fma(0.375, e, 0.5), r);
-  e = fma(-x * r, r, 1.0);
-  r = fma(0.5 * r, e, r);
-  double s = x * r;
-  s = fma(fma(-s, s, x), 0.5 * r, s);
-  return s;
 }
 
 // NP contiguous doubles from shared memory through explicit ld.shared PTX (16-byte vectors when NP is even;

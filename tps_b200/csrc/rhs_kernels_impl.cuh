@@ -50,15 +50,15 @@ __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int 
 struct FacePar {
   int as, at, an, ss, st, side;
 };
-__device__ __forceinline__ FacePar decode_face(int par) {
-  FacePar f;
-  f.as = par & 3;
-  f.at = (par >> 2) & 3;
-  f.an = (par >> 4) & 3;
-  f.ss = (par >> 6) & 1;
-  f.st = (par >> 7) & 1;
-  f.side = (par >> 8) & 1;
-  return f;
+// RefTables::face_par of the hexahedron (tables.hpp:186-193; MFEM's CUBE face-vertex table, independent of the order)
+// as compile-time constants: with the local face index unrolled, every axis pick / flip below folds away instead of
+// costing integer instructions per node (they were ~45 % of elem_resid_kernel's instruction mix, profiles/r1k_*).
+// tpsb_create checks them against the table built at run time.
+__host__ __device__ constexpr int kFacePar(int lf) {
+  return lf == 0 ? 100 : lf == 1 ? 216 : lf == 2 ? 457 : lf == 3 ? 408 : lf == 4 ? 137 : 484;
+}
+__host__ __device__ __forceinline__ constexpr FacePar decode_face(int par) {
+  return FacePar{par & 3, (par >> 2) & 3, (par >> 4) & 3, (par >> 6) & 1, (par >> 7) & 1, (par >> 8) & 1};
 }
 template <int NP>
 __device__ __forceinline__ int axis_stride(int axis) {
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB)
   if (active) {
 #pragma unroll
     for (int lf = 0; lf < 6; lf++) {
-      const FacePar fp = decode_face(sFp[lf]);
+      const FacePar fp = decode_face(kFacePar(lf));
       const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
       const int ab = (fp.ss ? ia : NP - 1 - ia) + NP * (fp.st ? ib : NP - 1 - ib);
       const double coef = sLb[fp.side][c] / (sWn[c] * det);
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
     if (fc < 0) continue;
     const int code = sFcode[le][lf];
     const int side = code & 1;
-    const FacePar fp = decode_face(sFp[lf]);
+    const FacePar fp = decode_face(kFacePar(lf));
     const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
     int fa = fp.ss ? ia : NP - 1 - ia, fb = fp.st ? ib : NP - 1 - ib;
     if (side) {  // own local face coordinates -> face (Elem1) coordinates

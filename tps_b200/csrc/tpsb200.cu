@@ -646,6 +646,11 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     delete c;
     return fail(nullptr, TPSB_EINVAL, "reference tables");
   }
+  for (int lf = 0; lf < 6; lf++)
+    if (c->T.face_par[lf] != kFacePar(lf)) {
+      delete c;
+      return fail(nullptr, TPSB_EINVAL, "compile-time face parameters disagree with the reference-element tables");
+    }
   c->bct = bct;
   c->phys.eq_system = phys->eq_system;
   c->phys.gamma = phys->specific_heat_ratio;
@@ -1099,7 +1104,8 @@ static void resid(tpsb_ctx *c, const KernelArgs &a) {
       case 3: launch_resid<4, 1, 12>(c, a); break;
       case 4: launch_resid<4, 4, 2>(c, a); break;
       case 5: launch_resid<4, 2, 6>(c, a); break;
-      default: launch_resid<4, 1, 10>(c, a); break;
+      case 6: launch_resid<4, 1, 10>(c, a); break;
+      default: launch_resid<4, 1, 12>(c, a); break;
     }
   } else if (c->np == 3) {
     launch_resid<3, 8, 2>(c, a);
