@@ -140,7 +140,10 @@ typedef struct {
  * kind selects the map, type is the reference's enum value (src/dataStructures.hpp:168-196):
  *   inlet  : InletType  -- built: SUB_DENS_VEL (2), data = inputState {rho, u, v, w}      (src/inletBC.cpp:729-756)
  *   outlet : OutletType -- built: SUB_P (0),        data = {p}                             (src/outletBC.cpp:731-737)
- *   wall   : WallType   -- built: INV (0), SLIP (1), VISC_ADIAB (2), VISC_ISOTH (3, data = {Th}) (src/wallBC.cpp:277-510)
+ *   wall   : WallType   -- built: INV (0), SLIP (1), VISC_ADIAB (2), VISC_ISOTH (3, data = {Th}) (src/wallBC.cpp:277-510),
+ *                          VISC_GNRL (4, generic path; data = {hvyThermalCond, elecThermalCond, Th, Te} with
+ *                          ThermalCondition 0 ADIAB / 1 ISOTH / 2 SHTH sheath; src/wallBC.cpp:112-147,512-543,
+ *                          PerfectMixture::computeSheathBdrFlux src/equation_of_state.cpp:1909-1942)
  * Other types return TPSB_ENOTIMPL at create.  use_bc_in_grad = boundaryConditions/useBCinGrad
  * (src/M2ulPhyS.cpp:3480): the BR1 gradient then uses the wall state at isothermal walls
  * (src/faceGradientIntegration.cpp:96-115) and the wall Riemann state flips (src/wallBC.cpp:476-479).  */

@@ -491,6 +491,43 @@ struct Oracle {
         bdrFlux[eq] -= 0.5 * wallViscF[eq];
         for (int d = 0; d < dim; d++) bdrFlux[eq] -= 0.5 * viscF[eq + d * neq] * normal[d];
       }
+    } else if (b.type == 4) {
+      // WallType VISC_GNRL: WallBC constructor (src/wallBC.cpp:112-147) + computeGeneralWallFlux (:512-543).
+      // data = {hvyThermalCond, elecThermalCond, Th, Te}; ThermalCondition 0 ADIAB, 1 ISOTH, 2 SHTH
+      const int hvy = static_cast<int>(b.data[0]), elec = static_cast<int>(b.data[1]);
+      const bool twoT = neq - (nvel + 2) - ph->num_active_species() == 1;
+      double bprim[16];
+      bool pidx[16];
+      for (int i = 0; i < 16; i++) {
+        bprim[i] = 0.0;
+        pidx[i] = false;
+      }
+      for (int d = 0; d < nvel; d++) pidx[d + 1] = true;
+      for (int i = 0; i < nsp; i++) idx[i] = true;
+      if (hvy == 1) {
+        bprim[nvel + 1] = b.data[2];
+        pidx[nvel + 1] = true;
+      } else {
+        idx[nsp + nvel] = true;
+      }
+      if (elec == 1) {  // index num_equation - 1 whether or not there is an electron-energy equation (:133-134)
+        bprim[neq - 1] = b.data[3];
+        pidx[neq - 1] = true;
+      } else if (elec == 0) {
+        idx[nsp + nvel + 1] = true;
+      } else if (twoT) {
+        idx[nsp + nvel + 1] = true;
+      }
+      ph->modify_state_from_primitive(stateIn, bprim, pidx, wallState);
+      ph->riemann(stateIn, wallState, normal, bdrFlux, true);
+      if (elec == 2) ph->sheath_bdr_flux(wallState, primFlux);
+      ph->bdr_visc_flux(wallState, gradState, xyz, delta, 0.0, unitN, primFlux, idx, wallViscF);
+      for (int eq = 0; eq < neq; eq++) wallViscF[eq] *= sqrt(normN);
+      ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
+      for (int eq = 1; eq < neq; eq++) {
+        bdrFlux[eq] -= 0.5 * wallViscF[eq];
+        for (int d = 0; d < dim; d++) bdrFlux[eq] -= 0.5 * viscF[eq + d * neq] * normal[d];
+      }
     }
   }
 

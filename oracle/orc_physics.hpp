@@ -106,6 +106,11 @@ struct Physics {
   virtual void stagnation_state(const double *U, double *out) = 0;
   virtual void stagnant_state_with_temp(const double *U, double T, double *out) = 0;
   virtual void modify_energy_for_pressure(const double *in, double *out, double p, bool modifyElectronEnergy) = 0;
+  // GasMixture::modifyStateFromPrimitive (src/equation_of_state.cpp:118-143): primitives of U, entries flagged in
+  // primIdxs replaced by prim, back to conserved
+  virtual void modify_state_from_primitive(const double *U, const double *prim, const bool *primIdxs, double *out) = 0;
+  // GasMixture::computeSheathBdrFlux (PerfectMixture: src/equation_of_state.cpp:1909-1942): fills primFlux
+  virtual void sheath_bdr_flux(const double *wallState, double *primFlux) {}
   // Fluxes::ComputeBdrViscousFluxes with BoundaryViscousFluxData {normal (unit), primFlux, primFluxIdxs}
   virtual void bdr_visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist,
                              const double *unit_normal, const double *primFlux, const bool *primFluxIdxs,

@@ -46,6 +46,14 @@ class DryAirPort : public Physics {
     for (int eq = 0; eq < neq_; eq++) out[eq] = tmp[eq];
     out[1 + nvel_] = p / (p_.gamma - 1.) + ke;
   }
+  // src/equation_of_state.cpp:134-143
+  void modify_state_from_primitive(const double *U, const double *bprim, const bool *primIdxs, double *out) override {
+    double pr[16];
+    prim(U, pr);
+    for (int i = 0; i < neq_; i++)
+      if (primIdxs[i]) pr[i] = bprim[i];
+    cons(pr, out);
+  }
   // src/fluxes.cpp:344-504 for dry air: one species with zero diffusion velocity
   // (src/transport_properties.cpp:236-266), no species enthalpy carried to the heat flux, single temperature.
   void bdr_visc_flux(const double *s, const double *gradUp, double *xyz, double /*delta*/, double /*dist*/,

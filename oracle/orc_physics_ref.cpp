@@ -71,6 +71,14 @@ class DryAirRef : public Physics {
     for (int i = 0; i < neq_; i++) tmp[i] = in[i];
     mix_->modifyEnergyForPressure(tmp, out, p, mee);  // equation_of_state.cpp:402
   }
+  void modify_state_from_primitive(const double *U, const double *prim, const bool *primIdxs, double *out) override {
+    BoundaryPrimitiveData bc;
+    for (int i = 0; i < gpudata::MAXEQUATIONS; i++) {
+      bc.prim[i] = i < 16 ? prim[i] : 0.0;
+      bc.primIdxs[i] = i < 16 ? primIdxs[i] : false;
+    }
+    mix_->modifyStateFromPrimitive(U, bc, out);  // equation_of_state.cpp:134
+  }
   void bdr_visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, const double *nrm,
                      const double *primFlux, const bool *primFluxIdxs, double *normalFlux) override {
     BoundaryViscousFluxData bc;
@@ -244,6 +252,23 @@ class MixtureRef : public Physics {
     double tmp[16];
     for (int i = 0; i < neq_; i++) tmp[i] = in[i];
     mix_->modifyEnergyForPressure(tmp, out, p, mee);
+  }
+  void modify_state_from_primitive(const double *U, const double *prim, const bool *primIdxs, double *out) override {
+    BoundaryPrimitiveData bc;
+    for (int i = 0; i < gpudata::MAXEQUATIONS; i++) {
+      bc.prim[i] = i < 16 ? prim[i] : 0.0;
+      bc.primIdxs[i] = i < 16 ? primIdxs[i] : false;
+    }
+    mix_->modifyStateFromPrimitive(U, bc, out);  // equation_of_state.cpp:134
+  }
+  void sheath_bdr_flux(const double *wallState, double *primFlux) override {
+    BoundaryViscousFluxData bc;
+    for (int i = 0; i < gpudata::MAXEQUATIONS; i++) {
+      bc.primFlux[i] = i < 16 ? primFlux[i] : 0.0;
+      bc.primFluxIdxs[i] = false;
+    }
+    mix_->computeSheathBdrFlux(wallState, bc);  // equation_of_state.cpp:1909
+    for (int i = 0; i < 16 && i < gpudata::MAXEQUATIONS; i++) primFlux[i] = bc.primFlux[i];
   }
   void bdr_visc_flux(const double *U, const double *gradUp, double *xyz, double delta, double dist, const double *nrm,
                      const double *primFlux, const bool *primFluxIdxs, double *normalFlux) override {

@@ -121,3 +121,41 @@ def test_roe_riemann_solver_2d(lib_built, oracle_built, bc):
     _compare(op, orc, ac.dry_state(orc.node_coords(), 2))
     with pytest.raises(tps_b200.TpsbError):  # the reference's Roe solver has no 3-D form
         tps_b200.RhsOperator(tps_b200.cartesian_hex_mesh(2, 2, 2), order=1, physics=tps_b200.Physics.dry_air(1, 1.0, 0.0, use_roe=True))
+
+
+@needs_ref
+@pytest.mark.parametrize("hvy,elec,two_t", [(1, 1, True), (0, 0, True), (1, 2, True), (0, 2, True), (1, 0, False), (0, 2, False),
+                                            (1, 2, False)])
+def test_general_wall_and_sheath(lib_built, oracle_built, hvy, elec, two_t):
+    """WallType VISC_GNRL (wallBC.cpp:112-147, 512-543): no-slip wall with independent heavy-species and electron
+    thermal conditions (ADIAB / ISOTH / SHTH), PerfectMixture::computeSheathBdrFlux for the sheath.  (An isothermal
+    electron condition on a single-temperature mixture is not a valid input of the reference either: it writes T_e
+    into primitive num_equation - 1, the last species, wallBC.cpp:133-134.)"""
+    import plasma_cases
+    import tps_b200
+    m = ac.box(n=(4, 4), lo=(-1.0, -1.0), hi=(1.0, 1.0), warp=0.04)
+    pm = plasma_cases.ternary_models(two_temperature=two_t)
+    wall = (float(hvy), float(elec), 420.0, 1800.0)
+    specs = [(1, 2, 4, wall), (2, 2, 4, wall), (3, 2, 4, wall), (4, 1, 0, (120000.0,))]
+    neq = 6 if two_t else 5
+    op = tps_b200.RhsOperator(m, order=2, physics=tps_b200.Physics.plasma_mixture(pm, 1), basis_type=1, int_rule_type=1,
+                              face_attr=m["face_attr"], use_bc_in_grad=True, bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+    orc = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.mixture_params(pm, 1), kind="ref", basis_type=1, int_rule=1, neq=neq, nvel=2)
+    orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], True)
+    up = plasma_cases.smooth_primitives(orc.node_coords() * np.pi)[:, :neq]
+    U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+    _compare(op, orc, U)
+
+
+def test_general_wall_dry_air(lib_built, oracle_built):
+    import tps_b200
+    m = ac.box(warp=0.05)
+    for wall in ((1.0, 0.0, 330.0, 0.0), (0.0, 0.0, 0.0, 0.0), (1.0, 1.0, 330.0, 360.0)):
+        specs = [(1, 2, 4, wall), (2, 2, 4, wall), (3, 0, 2, (1.25, 12.0, 3.0, 1.5)), (4, 1, 0, (101000.0,))]
+        op = tps_b200.RhsOperator(m, order=3, physics=tps_b200.Physics.dry_air(1, 3e4, 0.2), face_attr=m["face_attr"],
+                                  bcs=[tps_b200.BcDesc.make(*b) for b in specs], basis_type=1, int_rule_type=1)
+        orc = oracle_api.Oracle(3, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                                phys=oracle_api.dry_air_params(1, 3e4, 0.2), basis_type=1, int_rule=1)
+        orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], False)
+        _compare(op, orc, ac.dry_state(orc.node_coords(), 2))

@@ -220,6 +220,20 @@ __host__ __device__ __forceinline__ void gen_viscosities(const GenPhys &g, const
     visc[1] = g.dry.bulk_visc_mult * visc[0];
   }
 }
+// GasMixture::GetConservativesFromPrimitives (DryAir equation_of_state.cpp:298-315, PerfectMixture :744-783)
+__host__ __device__ __forceinline__ void gen_cons(const GenPhys &g, const double *up, double *U) {
+  if (g.fluid) {
+    mix_cons(*g.mix, up, U);
+  } else {
+    for (int eq = 0; eq < g.neq; eq++) U[eq] = up[eq];
+    double v2 = 0.;
+    for (int d = 0; d < g.nvel; d++) {
+      v2 += up[1 + d] * up[1 + d];
+      U[1 + d] *= up[0];
+    }
+    U[1 + g.nvel] = g.dry.R * up[0] * up[1 + g.nvel] / g.dry.gm1 + 0.5 * up[0] * v2;
+  }
+}
 // GasMixture::computeStagnationState (equation_of_state.cpp:100-116; DryAir :367-377)
 __host__ __device__ __forceinline__ void gen_stagnation_state(const GenPhys &g, const double *in, double *out) {
   for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];

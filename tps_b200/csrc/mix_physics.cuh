@@ -813,8 +813,16 @@ MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr,
 // Fluxes::ComputeBdrViscousFluxes (fluxes.cpp:344-504) as the wall conditions use it: every species' normal
 // diffusion flux is prescribed 0 (primFluxIdxs[0..numSpecies) = true, wallBC.cpp:66-110), and with heat_prescribed
 // (adiabatic wall) the heavy and -- two-temperature -- electron heat fluxes are prescribed 0 too.  nrm = unit normal.
+// General form: pf[0..numSpecies) are the prescribed species diffusion velocities (NULL: zeros), hvy_prescribed /
+// elec_prescribed select the prescribed heat fluxes pf[numSpecies + nvel] / pf[numSpecies + nvel + 1].
+MIXBIG void mix_bdr_visc_flux_general(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
+                                      const double *pf, bool hvy_prescribed, bool elec_prescribed, double *nf);
 MIXBIG void mix_bdr_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
                               bool heat_prescribed, double *nf) {
+  mix_bdr_visc_flux_general(m, s, gr, radius, nrm, nullptr, heat_prescribed, heat_prescribed, nf);
+}
+MIXBIG void mix_bdr_visc_flux_general(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
+                                      const double *pfl, bool hvy_prescribed, bool elec_prescribed, double *nf) {
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
   if (m.eq_system == 0) return;
@@ -861,27 +869,81 @@ MIXBIG void mix_bdr_visc_flux(const MixParams &m, const double *s, const double 
     pf[2] += tau_tr * nn[0];
     pf[2] += tau_tz * nn[1];
   }
+  double vsp[MIX_MAXSP], hsp[MIX_MAXSP];  // normalPrimFlux[sp]: every wall type prescribes all of them
+  for (int sp = 0; sp < ns; sp++) vsp[sp] = pfl ? pfl[sp] : 0.0;
+  mix_species_enthalpies(m, s, hsp);
   double qe = 0.0, qh = 0.0;
   if (m.twoTemp) {
     for (int d = 0; d < dim; d++) qe -= ke * gr[(neq - 1) + d * neq] * nrm[d];
-    qe += 0.0;  // speciesEnthalpies[electron] * (prescribed zero flux)
+    qe += hsp[ns - 2] * vsp[ns - 2];
   } else {
     k += ke;
   }
   for (int d = 0; d < dim; d++) qh -= k * gr[(1 + nvel) + d * neq] * nrm[d];
-  if (heat_prescribed) {
-    qh = 0.0;
-    qe = 0.0;
+  for (int sp = 0; sp < ns; sp++) {
+    if (m.twoTemp && (sp == ns - 2)) continue;
+    qh += hsp[sp] * vsp[sp];
   }
-  (void)ns;
-  // species equations: -state * (prescribed zero diffusion flux)
-  for (int sp = 0; sp < m.numActive; sp++) nf[nvel + 2 + sp] = -s[nvel + 2 + sp] * 0.0;
+  if (hvy_prescribed) qh = pfl ? pfl[ns + nvel] : 0.0;
+  if (elec_prescribed) qe = pfl ? pfl[ns + nvel + 1] : 0.0;
+  for (int sp = 0; sp < m.numActive; sp++) nf[nvel + 2 + sp] = -s[nvel + 2 + sp] * vsp[sp];
   for (int d = 0; d < nvel; d++) nf[d + 1] = pf[d];
   for (int d = 0; d < nvel; d++) nf[nvel + 1] += pf[d] * (s[1 + d] / s[0]);
   nf[nvel + 1] -= qh;
   if (m.twoTemp) {
     nf[nvel + 1] -= qe;
     nf[neq - 1] = -qe;
+  }
+}
+
+// PerfectMixture::GetConservativesFromPrimitives (equation_of_state.cpp:744-783)
+MIXBIG void mix_cons(const MixParams &m, const double *primit, double *conserv) {
+  const int nvel = m.nvel;
+  conserv[0] = primit[0];
+  for (int d = 0; d < nvel; d++) conserv[d + 1] = primit[d + 1] * primit[0];
+  for (int sp = 0; sp < m.numActive; sp++) conserv[nvel + 2 + sp] = primit[nvel + 2 + sp] * m.mw[sp];
+  const double *n_sp = primit + nvel + 2;
+  const double n_e = m.ambipolar ? mix_ambipolar_ne(m, n_sp) : n_sp[m.iElectron];
+  const double rhoB = mix_background_rho(m, primit[0], n_sp, n_e);
+  const double nB = rhoB / m.mw[m.iBackground];
+  if (m.twoTemp) conserv[m.iTe] = n_e * m.molarCV[m.iElectron] * primit[m.iTe];
+  double totalHeatCapacity = mix_heavies_cv(m, n_sp, nB);
+  if (!m.twoTemp) totalHeatCapacity += n_e * m.molarCV[m.iElectron];
+  double totalEnergy = 0.0;
+  for (int d = 0; d < nvel; d++) totalEnergy += primit[d + 1] * primit[d + 1];
+  totalEnergy *= 0.5 * primit[0];
+  totalEnergy += totalHeatCapacity * primit[m.iTh];
+  if (m.twoTemp) totalEnergy += conserv[m.iTe];
+  for (int sp = 0; sp < m.numSpecies - 2; sp++) totalEnergy += primit[nvel + 2 + sp] * m.formE[sp];
+  conserv[m.iTh] = totalEnergy;
+}
+
+// PerfectMixture::computeSheathBdrFlux (equation_of_state.cpp:1909-1942): Bohm velocities of the positive ions, the
+// electron flux that keeps the wall current-free, a fully catalytic wall for the background, and (two temperatures)
+// the sheath electron heat flux.  pf[numSpecies + nvel + 2].
+MIXBIG void mix_sheath_bdr_flux(const MixParams &m, const double *state, double *pf) {
+  const int ns = m.numSpecies;
+  double n_sp[MIX_MAXSP], T_h, T_e;
+  mix_number_densities(m, state, n_sp);
+  mix_temperatures(m, state, n_sp, n_sp[m.iElectron], n_sp[m.iBackground], T_h, T_e);
+  for (int sp = 0; sp < ns; sp++) pf[sp] = 0.0;
+  for (int sp = 0; sp < ns; sp++) {
+    const double Zsp = m.charge[sp];
+    if (Zsp > 0.0) {
+      const double msp = m.mw[sp];
+      const double VB = sqrt((T_h + Zsp * T_e) * MIX_RU / msp);
+      pf[sp] = VB;
+      pf[m.iElectron] += Zsp * n_sp[sp] * VB;
+      pf[m.iBackground] -= msp * n_sp[sp] * VB;
+    }
+  }
+  pf[m.iElectron] /= n_sp[m.iElectron];
+  pf[m.iBackground] -= m.mw[m.iElectron] * n_sp[m.iElectron] * pf[m.iElectron];
+  pf[m.iBackground] /= m.mw[m.iBackground] * n_sp[m.iBackground];
+  if (m.twoTemp) {
+    const double vTe = sqrt(8.0 * MIX_RU * T_e / MIX_PI / m.mw[m.iElectron]);
+    const double gamma = -log(4.0 / vTe * pf[m.iElectron]);
+    pf[ns + m.nvel + 1] = pf[m.iElectron] * (gamma + 2.0) * n_sp[m.iElectron] * MIX_RU * T_e;
   }
 }
 

@@ -163,6 +163,39 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
     gen_riemann(g, u1, s2, nor, fx);
     return;
   }
+  if (bc.type == 4) {
+    // VISC_GNRL: WallBC constructor (wallBC.cpp:112-147) + computeGeneralWallFlux (:512-543).
+    // d = {hvyThermalCond, elecThermalCond, Th, Te}; ThermalCondition 0 ADIAB, 1 ISOTH, 2 SHTH
+    const int hvy = static_cast<int>(bc.d[0]), elec = static_cast<int>(bc.d[1]);
+    const bool twoT = g.fluid && g.mix->twoTemp;
+    const int nsp = g.fluid ? g.mix->numSpecies : 1;
+    double prim[GEN_MAXEQ], pf[GEN_MAXEQ + 4];
+    gen_prim(g, u1, prim);
+    for (int d = 0; d < nvel; d++) prim[1 + d] = 0.0;
+    if (hvy == 1) prim[nvel + 1] = bc.d[2];
+    if (elec == 1) prim[neq - 1] = bc.d[3];  // index num_equation - 1 in either temperature model (wallBC.cpp:133-134)
+    gen_cons(g, prim, s2);
+    gen_riemann_lf(g, u1, s2, nor, fx);
+    if (!ns) return;
+    for (int i = 0; i < GEN_MAXEQ + 4; i++) pf[i] = 0.0;
+    if (elec == 2 && g.fluid) mix_sheath_bdr_flux(*g.mix, s2, pf);
+    const double isq = 1. / sqrt(normN);
+    for (int d = 0; d < dim; d++) un[d] = nor[d] * isq;
+    const bool hvy_presc = hvy != 1, elec_presc = (elec == 0) || (elec == 2 && twoT);
+    if (g.fluid)
+      mix_bdr_visc_flux_general(*g.mix, s2, gr, radius, un, pf, hvy_presc, elec_presc, wallViscF);
+    else
+      dry_gen_bdr_visc_flux(g, s2, gr, radius, un, hvy_presc, wallViscF);
+    (void)nsp;
+    const double nm = sqrt(normN);
+    for (int eq = 0; eq < neq; eq++) wallViscF[eq] *= nm;
+    gen_visc_flux(g, u1, gr, radius, viscF);
+    for (int eq = 1; eq < neq; eq++) {
+      fx[eq] -= 0.5 * wallViscF[eq];
+      for (int d = 0; d < dim; d++) fx[eq] -= 0.5 * viscF[eq + d * neq] * nor[d];
+    }
+    return;
+  }
   if (bc.type == 0) {  // INV: mirror state
     const double norm = sqrt(normN);
     double vel[3] = {0, 0, 0};

@@ -612,7 +612,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     for (int i = 0; i < bcs->num_bcs; i++) {
       const tpsb_bc_desc &b = bcs->bcs[i];
       const bool ok = (b.kind == TPSB_BC_INLET && b.type == 2) || (b.kind == TPSB_BC_OUTLET && b.type == 0) ||
-                      (b.kind == TPSB_BC_WALL && b.type >= 0 && b.type <= 3);
+                      (b.kind == TPSB_BC_WALL && b.type >= 0 && b.type <= 3) ||
+                      (b.kind == TPSB_BC_WALL && b.type == 4 && want_generic);  // VISC_GNRL: generic path
       if (!ok)
         return fail(ctx, TPSB_ENOTIMPL, "boundary condition kind %d type %d (attribute %d) not built yet", b.kind, b.type, b.attr);
       bct.bc[i].kind = b.kind;
