@@ -113,6 +113,28 @@ def test_host_buffer_entry_point_matches_device_entry_point(lib_built, oracle_bu
     assert np.array_equal(y2, y_dev)
 
 
+@pytest.mark.parametrize("n3,chunks,order", [((6, 6, 6), 4, 3), ((5, 4, 7), 7, 3), ((8, 8, 8), 32, 2), ((4, 4, 4), 3, 1)])
+def test_chunked_host_pipeline_is_bit_identical(lib_built, monkeypatch, n3, chunks, order):
+    """tpsb_rhs_mult_host overlaps copy-in / kernels / copy-out per element chunk (periodic single-rank fast path);
+    the chunked schedule must reproduce the one-shot evaluation bit for bit, max characteristic speed included."""
+    import torch
+    monkeypatch.setenv("TPSB_HOST_CHUNKS", str(chunks))
+    m = tps_b200.cartesian_hex_mesh(*n3, lo=(-PI,) * 3, hi=(PI,) * 3)
+    op = tps_b200.RhsOperator(m, order=order, physics=tps_b200.Physics.dry_air(1, 3e3, 0.2))
+    U = tgv_state(node_coords_from_mesh(m["elem_xyz"], order))
+    y_dev = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    mcs = op.max_char_speed()
+    hx = torch.from_numpy(U).pin_memory()
+    for _ in range(2):  # second call reuses the streams / events
+        hy = torch.zeros_like(hx).pin_memory()
+        op.mult_host(hx, hy)
+        assert np.array_equal(hy.numpy(), y_dev)
+        assert op.max_char_speed() == mcs
+    y2 = np.zeros_like(U)
+    op.mult_host(U, y2)  # pageable buffers
+    assert np.array_equal(y2, y_dev)
+
+
 def test_hundred_rk4_steps(lib_built, oracle_built):
     """Solution after 100 RK steps agrees to 1e-8 (BASELINE.json north star)."""
     torch, m, op, orc, U = _setup(4, visc_mult=1e3)

@@ -122,7 +122,7 @@ __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const 
 template <int NP, int FPB, int NT, bool BDR>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
 template <int NP, int EPB, int MINB, bool AFF>
-__global__ void elem_resid_kernel(KernelArgs a);
+__global__ void elem_resid_kernel(KernelArgs a, int elem_begin, int elem_count);
 
 // y = x + a*k ; z = x + b*k  etc. for the ODE stages
 __global__ void axpy2_kernel(long long n, const double *x, const double *k, double a, double *y, double b, double *z,

@@ -30,6 +30,20 @@ __global__ void prim_kernel(KernelArgs a, int halo) {
   }
 }
 
+// prim_range_kernel: updatePrimitives of the nodes [begin, begin + count) -- the chunked host-buffer pipeline
+// (tpsb_rhs_mult_host) converts each element chunk as soon as its host-to-device copy has landed
+__global__ void prim_range_kernel(KernelArgs a, long long begin, long long count) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long long n = begin + t;
+  double s[NEQ], up[NEQ];
+#pragma unroll
+  for (int eq = 0; eq < NEQ; eq++) s[eq] = a.U[n + eq * a.N];
+  dry_prim(a.phys, s, up);
+#pragma unroll
+  for (int eq = 0; eq < NEQ; eq++) a.Up[n + eq * a.N] = up[eq];
+}
+
 // pack_kernel: gather the dofs of the elements in send_elems into an element-major send buffer
 // (replaces the pack loop of RHSoperator::initNBlockDataTransfer, src/rhs_operator.cpp:786-805)
 __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int *send_elems, const double *src,
@@ -489,7 +503,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 // AFF: every element is a parallelepiped (fast path): adj(J) and det come from the 12-double table a.geo
 // instead of being rebuilt per node from the 8 vertices (~250 flops per node saved).
 template <int NP, int EPB, int MINB, bool AFF = false>
-__global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(KernelArgs a) {
+__global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(KernelArgs a, int elem_begin, int elem_count) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
   __shared__ double sVx[EPB][24];
@@ -498,8 +512,9 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
   __shared__ __align__(16) double sR[EPB][6][NEQ * NF2];  // face residual blocks of the six faces (cp.async)
   __shared__ unsigned long long sMaxBits;
   const int le = threadIdx.x / ND, n = threadIdx.x % ND;
-  const int e = blockIdx.x * EPB + le;
-  const bool active = e < a.NE;
+  const int slot = blockIdx.x * EPB + le;
+  const bool active = slot < elem_count;
+  const int e = active ? elem_begin + slot : 0;
   const long long N = a.N;
   if (threadIdx.x < NP * NP) sD[threadIdx.x / NP][threadIdx.x % NP] = c_T.D[threadIdx.x / NP][threadIdx.x % NP];
   if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];

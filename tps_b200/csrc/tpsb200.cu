@@ -71,6 +71,17 @@ struct tpsb_ctx {
   int n_send = 0;
   // ODE / host-staging work vectors (lazy)
   double *d_k = nullptr, *d_yv = nullptr, *d_z = nullptr, *d_hx = nullptr, *d_hy = nullptr;
+  // chunked host-buffer pipeline of tpsb_rhs_mult_host (single rank, periodic fast path): host->device copies,
+  // kernels and device->host copies of different element chunks overlap on three streams
+  struct PipeOp {
+    int kind, chunk;  // 0 prim (after the chunk's copy landed), 1 gradient, 2 face fluxes, 3 residual + copy out
+  };
+  int pipe_chunks = 0;
+  std::vector<int> pipe_eb, pipe_fb;  // element / face range of each chunk
+  std::vector<PipeOp> pipe_ops;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_out;
+  cudaEvent_t ev_pipe0 = nullptr, ev_pipe1 = nullptr;
   long long launches = 0;
   int tune[3] = {0, 0, 0};
   int num_sms = 148, face_ctas_per_sm = 5;
@@ -534,6 +545,72 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   return "";
 }
 
+
+// Static schedule of the chunked host-buffer pipeline.  Elements are cut into C contiguous chunks, the two-sided
+// faces into the C ranges "Elem1 lies in chunk k" (contiguous because faces are numbered by first appearance over
+// the elements).  A chunk's gradient needs the primitives of its face neighbours' chunks, a face range the trace
+// blocks of both sides' chunks, a chunk's residual the face residuals of all its faces; the op list below is the
+// greedy order in which those become available while the chunks arrive 0, 1, 2, ...
+void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
+                     const std::vector<int> &fl_el1, const std::vector<int> &fl_el2) {
+  const int NE = c->NE;
+  int C = std::min(32, NE / 2048);
+  if (const char *ev = getenv("TPSB_HOST_CHUNKS")) C = atoi(ev);
+  C = std::min(C, 64);
+  if (C < 3 || C > NE) return;
+  std::vector<int> eb(C + 1), fb(C + 1, c->NFint);
+  for (int k = 0; k <= C; k++) eb[k] = static_cast<int>(static_cast<long long>(NE) * k / C);
+  auto chunk_of = [&](int e) { return static_cast<int>(std::upper_bound(eb.begin(), eb.end(), e) - eb.begin()) - 1; };
+  fb[0] = 0;
+  int cur = 0;
+  for (int f = 0; f < c->NFint; f++) {
+    const int cf = chunk_of(fl_el1[f]);
+    if (cf < cur) return;  // face order not monotone in Elem1: keep the unchunked path
+    while (cur < cf) fb[++cur] = f;
+  }
+  while (cur < C) fb[++cur] = c->NFint;
+  using mask = unsigned long long;
+  std::vector<mask> need_prim(C, 0), need_grad(C, 0), need_face(C, 0);
+  for (int e = 0; e < NE; e++) {
+    const int ce = chunk_of(e);
+    need_prim[ce] |= mask(1) << ce;
+    for (int lf = 0; lf < 6; lf++) {
+      const int nb = nbr_elem[static_cast<size_t>(e) * 6 + lf], fc = el_face[static_cast<size_t>(e) * 6 + lf];
+      if (nb >= 0) need_prim[ce] |= mask(1) << chunk_of(nb);
+      if (fc >= 0 && fc < c->NFint)
+        need_face[ce] |= mask(1) << (static_cast<int>(std::upper_bound(fb.begin(), fb.end(), fc) - fb.begin()) - 1);
+    }
+  }
+  for (int f = 0; f < c->NFint; f++) {
+    const int cf = chunk_of(fl_el1[f]);
+    need_grad[cf] |= (mask(1) << cf) | (mask(1) << chunk_of(fl_el2[f]));
+  }
+  std::vector<tpsb_ctx::PipeOp> ops;
+  mask primd = 0, gradd = 0, faced = 0, resd = 0;
+  for (int k = 0; k < C; k++) {
+    ops.push_back({0, k});
+    primd |= mask(1) << k;
+    for (bool progress = true; progress;) {
+      progress = false;
+      for (int g = 0; g < C; g++)
+        if (!(gradd >> g & 1) && (need_prim[g] & ~primd) == 0) ops.push_back({1, g}), gradd |= mask(1) << g, progress = true;
+      for (int f = 0; f < C; f++)
+        if (!(faced >> f & 1) && (need_grad[f] & ~gradd) == 0) {
+          if (fb[f + 1] > fb[f]) ops.push_back({2, f});
+          faced |= mask(1) << f, progress = true;
+        }
+      for (int r = 0; r < C; r++)
+        if (!(resd >> r & 1) && (gradd >> r & 1) && (need_face[r] & ~faced) == 0)
+          ops.push_back({3, r}), resd |= mask(1) << r, progress = true;
+    }
+  }
+  if (resd != (C == 64 ? ~mask(0) : (mask(1) << C) - 1)) return;
+  c->pipe_chunks = C;
+  c->pipe_eb = eb;
+  c->pipe_fb = fb;
+  c->pipe_ops = ops;
+}
+
 }  // namespace
 
 extern "C" {
@@ -845,6 +922,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     }
   }
 
+  if (c->fast && NEH == 0 && c->NFbdr == 0) build_host_pipe(c, nbr_elem, el_face, fl_el1, fl_el2);
+
   // ---- device allocations ----
   cudaError_t ce = cudaSetDevice(device);
   std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE + NEH) * 24);
@@ -970,6 +1049,12 @@ void tpsb_destroy(tpsb_ctx *c) {
   if (c->ev_recvU) cudaEventDestroy(c->ev_recvU);
   if (c->ev_recvG) cudaEventDestroy(c->ev_recvG);
   if (c->ev_recvT) cudaEventDestroy(c->ev_recvT);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
+  if (c->ev_pipe0) cudaEventDestroy(c->ev_pipe0);
+  if (c->ev_pipe1) cudaEventDestroy(c->ev_pipe1);
   delete c;
 }
 
@@ -1055,12 +1140,13 @@ static void bdr_faces(tpsb_ctx *c, const KernelArgs &a) {
     face_flux_kernel<2, 8, 128, true><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
 }
 template <int NP, int EPB, int MINB = 1>
-static void launch_resid(tpsb_ctx *c, const KernelArgs &a) {
+static void launch_resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
+  if (count <= 0) return;
   ProfScope ps(c, K_RESID);
   if (c->fast)
-    elem_resid_kernel<NP, EPB, MINB, true><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+    elem_resid_kernel<NP, EPB, MINB, true><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
   else
-    elem_resid_kernel<NP, EPB, MINB, false><<<(c->NE + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a);
+    elem_resid_kernel<NP, EPB, MINB, false><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
 }
 
 // Launch-shape selection.  p = 3 is the tuned case; tune[] (TPSB_TUNE="g,f,r", development knob) picks
@@ -1097,21 +1183,22 @@ static void face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
     launch_face<2, 8, 128>(c, a, begin, count);
   }
 }
-static void resid(tpsb_ctx *c, const KernelArgs &a) {
+static void resid(tpsb_ctx *c, const KernelArgs &a, int begin = 0, int count = -1) {
+  if (count < 0) count = c->NE;
   if (c->np == 4) {
     switch (c->tune[2]) {
-      case 1: launch_resid<4, 1, 16>(c, a); break;
-      case 2: launch_resid<4, 2, 5>(c, a); break;
-      case 3: launch_resid<4, 1, 12>(c, a); break;
-      case 4: launch_resid<4, 4, 2>(c, a); break;
-      case 5: launch_resid<4, 2, 6>(c, a); break;
-      case 6: launch_resid<4, 1, 10>(c, a); break;
-      default: launch_resid<4, 1, 12>(c, a); break;
+      case 1: launch_resid<4, 1, 16>(c, a, begin, count); break;
+      case 2: launch_resid<4, 2, 5>(c, a, begin, count); break;
+      case 3: launch_resid<4, 1, 12>(c, a, begin, count); break;
+      case 4: launch_resid<4, 4, 2>(c, a, begin, count); break;
+      case 5: launch_resid<4, 2, 6>(c, a, begin, count); break;
+      case 6: launch_resid<4, 1, 10>(c, a, begin, count); break;
+      default: launch_resid<4, 1, 12>(c, a, begin, count); break;
     }
   } else if (c->np == 3) {
-    launch_resid<3, 8, 2>(c, a);
+    launch_resid<3, 8, 2>(c, a, begin, count);
   } else {
-    launch_resid<2, 16, 4>(c, a);
+    launch_resid<2, 16, 4>(c, a, begin, count);
   }
 }
 #define DISPATCH(c, CALL) CALL
@@ -1302,7 +1389,7 @@ static int run_gradients_fast(tpsb_ctx *ctx, const KernelArgs &a, bool prims_don
   return TPSB_OK;
 }
 
-static void resid(tpsb_ctx *c, const KernelArgs &a);
+static void resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count);
 
 static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   tpsb_ctx *c = ctx;
@@ -1405,6 +1492,71 @@ static int ensure_work(tpsb_ctx *ctx, double **p) {
   return TPSB_OK;
 }
 
+// tpsb_rhs_mult_host on the periodic single-rank fast path: the evaluation is PCIe-bound (2 x 40 B per node against
+// ~0.23 ns of kernel time per node), so the three legs are overlapped chunk by chunk -- copies in on s_in, kernels on
+// the context stream in the order of ctx->pipe_ops, copies out on s_out (PCIe is full duplex).  Same kernels, same
+// per-element arithmetic: the result is bit-identical to tpsb_rhs_mult.
+static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y) {
+  tpsb_ctx *c = ctx;
+  const int C = c->pipe_chunks;
+  if (!c->s_in) {
+    CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    c->ev_in.assign(C, nullptr);
+    c->ev_out.assign(C, nullptr);
+    for (int k = 0; k < C; k++) {
+      CU(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_pipe0, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_pipe1, cudaEventDisableTiming));
+  }
+  KernelArgs a = make_args(c, c->d_hx, c->d_hy);
+  if (g_uploaded_order != c->order) {
+    CU(cudaMemcpyToSymbolAsync(c_T, &c->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, c->stream));
+    g_uploaded_order = c->order;
+  }
+  CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
+  CU(cudaEventRecord(c->ev_pipe0, c->stream));  // earlier work on the caller's stream may still use d_hx / d_hy
+  CU(cudaStreamWaitEvent(c->s_in, c->ev_pipe0, 0));
+  CU(cudaStreamWaitEvent(c->s_out, c->ev_pipe0, 0));
+  const size_t pitch = static_cast<size_t>(c->N) * sizeof(double);  // byNODES: one row per equation
+  for (int k = 0; k < C; k++) {
+    const size_t off = static_cast<size_t>(c->pipe_eb[k]) * c->nd;
+    const size_t width = static_cast<size_t>(c->pipe_eb[k + 1] - c->pipe_eb[k]) * c->nd * sizeof(double);
+    CU(cudaMemcpy2DAsync(c->d_hx + off, pitch, h_x + off, pitch, width, NEQ, cudaMemcpyHostToDevice, c->s_in));
+    CU(cudaEventRecord(c->ev_in[k], c->s_in));
+  }
+  for (const tpsb_ctx::PipeOp &op : c->pipe_ops) {
+    const int k = op.chunk, e0 = c->pipe_eb[k], ne = c->pipe_eb[k + 1] - e0;
+    switch (op.kind) {
+      case 0: {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        const long long cnt = static_cast<long long>(ne) * c->nd;
+        ProfScope ps(c, K_PRIM);
+        prim_range_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, c->stream>>>(a, static_cast<long long>(e0) * c->nd, cnt);
+        break;
+      }
+      case 1: grad_trace(c, a, e0, ne, nullptr); break;
+      case 2: face_fast(c, a, c->pipe_fb[k], c->pipe_fb[k + 1] - c->pipe_fb[k]); break;
+      default: {
+        resid(c, a, e0, ne);
+        CU(cudaEventRecord(c->ev_out[k], c->stream));
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_out[k], 0));
+        const size_t off = static_cast<size_t>(e0) * c->nd;
+        CU(cudaMemcpy2DAsync(h_y + off, pitch, c->d_hy + off, pitch, static_cast<size_t>(ne) * c->nd * sizeof(double), NEQ,
+                             cudaMemcpyDeviceToHost, c->s_out));
+        break;
+      }
+    }
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev_pipe1, c->s_out));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_pipe1, 0));
+  CU(cudaStreamSynchronize(c->stream));
+  return TPSB_OK;
+}
+
 extern "C" {
 
 int tpsb_rhs_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
@@ -1418,6 +1570,7 @@ int tpsb_rhs_mult_host(tpsb_ctx *ctx, const double *h_x, double *h_y) {
   int rc = ensure_work(ctx, &ctx->d_hx);
   if (!rc) rc = ensure_work(ctx, &ctx->d_hy);
   if (rc) return rc;
+  if (ctx->pipe_chunks > 0) return run_mult_host_pipelined(ctx, h_x, h_y);
   const size_t nb = static_cast<size_t>(ctx->N) * ctx->neq * sizeof(double);
   CU(cudaMemcpyAsync(ctx->d_hx, h_x, nb, cudaMemcpyHostToDevice, ctx->stream));
   rc = run_mult(ctx, ctx->d_hx, ctx->d_hy);
