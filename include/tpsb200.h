@@ -134,6 +134,18 @@ typedef struct {
   int use_roe;            /* flow/useRoe: RiemannSolverTPS::Eval_Roe (src/riemann_solver.cpp:117-206) on interior
                              faces and inviscid walls; as in the reference it is written for two velocity
                              components with gamma - 1 = 0.4 hard-coded, so only 2-D dry air accepts it           */
+  /* Sub-grid-scale eddy viscosity of Fluxes::ComputeViscousFluxes / ComputeBdrViscousFluxes (src/fluxes.cpp:224-231,
+   * 386-392): flow/sgsModel 0 none, 1 smagorinsky (Fluxes::sgsSmag :513-541), 2 sigma (Fluxes::sgsSigma :543-650, the
+   * closed-form branch a device build runs); flow/sgsModelConstant (reference defaults 0.12 / 0.135,
+   * src/M2ulPhyS.cpp:2693-2699), flow/sgsFloor.  The element size is Mesh::GetElementSize(e, 1) / order, derived
+   * from the vertices at create.  3-D dry air, Gauss-Legendre path.                                               */
+  int sgs_model;
+  double sgs_const, sgs_floor;
+  /* Planar viscous sponge (viscosityMultiplierFunction/*, Fluxes::viscSpongePlanar src/fluxes.cpp:664-684): viscosity,
+   * bulk viscosity and conductivity times 1 + (max(ratio,1) - 1) (tanh(dist/width - 2) + 1)/2, dist = (x - point).n
+   * with n normalised as Fluxes' constructor does (src/fluxes.cpp:73-83).                                          */
+  int sponge_enabled;
+  double sponge_normal[3], sponge_point[3], sponge_ratio, sponge_width;
 } tpsb_physics;
 
 /* Boundary conditions: BCintegrator's attribute -> {InletBC, OutletBC, WallBC} maps (src/BCintegrator.cpp:64-125).

@@ -26,6 +26,11 @@ struct OrcPhysParams {
   double C1, S0, Pr;  // Sutherland data (src/dataStructures.hpp:205-209)
   const OrcPlasma *plasma;  // fluid == 1 (USER_DEFINED): gas / transport / chemistry models (reference back end only)
   int use_roe;              // flow/useRoe: RiemannSolverTPS::Eval_Roe on interior faces and inviscid walls (2-D dry air)
+  // Fluxes' SGS model and planar viscous sponge (src/fluxes.cpp:97-128; reference back end only)
+  int sgs_model;            // flow/sgsModel: 0 none, 1 smagorinsky, 2 sigma
+  double sgs_const, sgs_floor;
+  int sponge_enabled;       // viscosityMultiplierFunction/isEnabled
+  double sponge_normal[3], sponge_point[3], sponge_ratio, sponge_width;
 };
 // Plasma models of a user-defined fluid: PerfectMixtureInput + constantTransportData + ChemistryInput
 // (src/dataStructures.hpp:537-546,623-633,690-712) flattened; same layout as tpsb_plasma_models.

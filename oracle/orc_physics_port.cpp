@@ -4,6 +4,8 @@
 // closure.  Each function cites the reference lines it follows.  It is validated against
 // the reference's own object code (orc_physics_ref.cpp) by tests/test_oracle_physics.py.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "orc_physics.hpp"
@@ -310,6 +312,10 @@ class DryAirPort : public Physics {
 };
 
 Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq) {
+  if (p.sgs_model != 0 || p.sponge_enabled != 0) {
+    fprintf(stderr, "oracle (port back end): SGS models / viscous sponge are served by the reference back end only\n");
+    abort();
+  }
   if (p.fluid != 0) return nullptr;
   if (p.use_roe && dim != 2) return nullptr;  // Eval_Roe is written for two velocity components (riemann_solver.cpp:153-170)
   return new DryAirPort(p, dim, nvel, neq);

@@ -37,7 +37,25 @@ class DryAirRef : public Physics {
     mix_ = new DryAir(in, dim, nvel);                                                          // equation_of_state.cpp:150
     trans_ = new DryAirTransport(mix_, p.visc_mult, p.bulk_visc_mult, p.C1, p.S0, p.Pr);       // transport_properties.cpp:208
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
-    flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym);   // fluxes.cpp:34
+    if (p.sgs_model != 0 || p.sponge_enabled != 0) {
+      // the constructor M2ulPhyS uses (fluxes.cpp:57-95) reads these from RunConfiguration and normalises the sponge
+      // normal; the device constructor (fluxes.cpp:97-128) takes them as given
+      viscositySpongeData vsd;
+      vsd.enabled = p.sponge_enabled != 0;
+      double nm = 0;
+      for (int d = 0; d < 3; d++) nm += p.sponge_normal[d] * p.sponge_normal[d];
+      nm = std::sqrt(nm);
+      for (int d = 0; d < 3; d++) {
+        vsd.n[d] = vsd.enabled ? p.sponge_normal[d] / nm : 0.0;
+        vsd.p[d] = p.sponge_point[d];
+      }
+      vsd.ratio = p.sponge_ratio;
+      vsd.width = p.sponge_width;
+      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym, p.sgs_model, p.sgs_floor,
+                         p.sgs_const, vsd);
+    } else {
+      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym);   // fluxes.cpp:34
+    }
     rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, p.use_roe != 0, axisym);  // riemann_solver.cpp:38
     use_roe_ = p.use_roe != 0;
   }

@@ -13,7 +13,10 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 class OrcPhysParams(C.Structure):
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("gamma", C.c_double), ("R", C.c_double),
                 ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double), ("C1", C.c_double),
-                ("S0", C.c_double), ("Pr", C.c_double), ("plasma", C.c_void_p), ("use_roe", C.c_int)]
+                ("S0", C.c_double), ("Pr", C.c_double), ("plasma", C.c_void_p), ("use_roe", C.c_int),
+                ("sgs_model", C.c_int), ("sgs_const", C.c_double), ("sgs_floor", C.c_double), ("sponge_enabled", C.c_int),
+                ("sponge_normal", C.c_double * 3), ("sponge_point", C.c_double * 3), ("sponge_ratio", C.c_double),
+                ("sponge_width", C.c_double)]
 
 
 class OrcBc(C.Structure):
@@ -28,9 +31,23 @@ def make_bc(attr, kind, type_, data=()):
     return b
 
 
-def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False):
-    """Defaults of the reference: gamma/R src/equation_of_state.cpp:175-179; Sutherland SURVEY.md 8(d)."""
-    return OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None, int(use_roe))
+def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False, sgs=None, sponge=None):
+    """Defaults of the reference: gamma/R src/equation_of_state.cpp:175-179; Sutherland SURVEY.md 8(d).
+    sgs = (model, constant, floor); sponge = (normal, point, ratio, width) -- reference back end only."""
+    p = OrcPhysParams(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None, int(use_roe))
+    set_visc_mods(p, sgs, sponge)
+    return p
+
+
+def set_visc_mods(p, sgs=None, sponge=None):
+    """Fill the SGS / viscous-sponge fields shared by OrcPhysParams and tps_b200.Physics."""
+    if sgs:
+        p.sgs_model, p.sgs_const, p.sgs_floor = int(sgs[0]), float(sgs[1]), float(sgs[2])
+    if sponge:
+        p.sponge_enabled = 1
+        for d in range(3):
+            p.sponge_normal[d], p.sponge_point[d] = float(sponge[0][d]), float(sponge[1][d])
+        p.sponge_ratio, p.sponge_width = float(sponge[2]), float(sponge[3])
 
 
 def mixture_params(models, eq_system=1):

@@ -126,11 +126,23 @@ class Physics(C.Structure):
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("specific_heat_ratio", C.c_double),
                 ("gas_constant", C.c_double), ("visc_mult", C.c_double), ("bulk_visc_mult", C.c_double),
                 ("sutherland_C1", C.c_double), ("sutherland_S0", C.c_double), ("sutherland_Pr", C.c_double),
-                ("plasma", C.POINTER(PlasmaModels)), ("use_roe", C.c_int)]
+                ("plasma", C.POINTER(PlasmaModels)), ("use_roe", C.c_int),
+                ("sgs_model", C.c_int), ("sgs_const", C.c_double), ("sgs_floor", C.c_double), ("sponge_enabled", C.c_int),
+                ("sponge_normal", C.c_double * 3), ("sponge_point", C.c_double * 3), ("sponge_ratio", C.c_double),
+                ("sponge_width", C.c_double)]
 
     @classmethod
-    def dry_air(cls, eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False):
-        return cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None, int(use_roe))
+    def dry_air(cls, eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False, sgs=None, sponge=None):
+        """sgs = (model 1 smagorinsky / 2 sigma, constant, floor); sponge = (normal, point, ratio, width)."""
+        ph = cls(eq_system, 0, 1.4, 287.058, visc_mult, bulk_visc_mult, 1.458e-6, 110.4, 0.71, None, int(use_roe))
+        if sgs:
+            ph.sgs_model, ph.sgs_const, ph.sgs_floor = int(sgs[0]), float(sgs[1]), float(sgs[2])
+        if sponge:
+            ph.sponge_enabled = 1
+            for d in range(3):
+                ph.sponge_normal[d], ph.sponge_point[d] = float(sponge[0][d]), float(sponge[1][d])
+            ph.sponge_ratio, ph.sponge_width = float(sponge[2]), float(sponge[3])
+        return ph
 
     @classmethod
     def plasma_mixture(cls, models, eq_system=1):

@@ -16,6 +16,16 @@ struct PhysParams {
   double gamma, R, gm1;
   double visc_mult, bulk_visc_mult, C1, S0, Pr;
   double cp_div_pr;  // gamma R / (Pr (gamma-1))   transport_properties.cpp:220
+  // Fluxes' sub-grid-scale model and planar viscous sponge (fluxes.cpp:224-246)
+  int sgs_model;  // flow/sgsModel: 0 none, 1 smagorinsky, 2 sigma
+  double sgs_const, sgs_floor;
+  int sponge;  // viscosityMultiplierFunction/isEnabled
+  double sp_n[3], sp_p[3], sp_ratio, sp_width;
+};
+// what the modified transport needs besides the state: delta = h_min / order of the element the gradient belongs to
+// (Mesh::GetElementSize(e, 1) / order, rhs_operator.cpp:149-156, face_integrator.cpp:253-276) and the physical point
+struct DryAux {
+  double delta, x[3];
 };
 
 // DryAir::ComputePressure   equation_of_state.hpp:610-617
@@ -91,14 +101,19 @@ __device__ __forceinline__ void dry_riemann_lf(const PhysParams &p, const double
 // Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335) with DryAirTransport::ComputeFluxMolecularTransport
 // (transport_properties.cpp:223-234): non-axisymmetric, no SGS, no viscous sponge, single temperature.
 // g[eq + d*NEQ] = d(Up_eq)/dx_d ; f[eq + d*NEQ].
-__device__ __forceinline__ void dry_visc_flux(const PhysParams &p, const double *s, const double *g, double *f) {
+struct DryAux;
+__device__ __forceinline__ void dry_modify_transport(const PhysParams &p, double rho, const double *gv, int ds, const DryAux &ax,
+                                                     double &visc, double &bulk, double &k);
+__device__ __forceinline__ void dry_visc_flux(const PhysParams &p, const double *s, const double *g, double *f,
+                                              const DryAux *ax = nullptr) {
   const double pr = dry_pressure(p, s);
   const double temp = pr / p.R / s[0];
   // pow(temp, 1.5) of the reference evaluated as temp*sqrt(temp) (agrees to an ulp)
-  const double visc = (p.C1 * p.visc_mult * (temp * sqrt(temp)) / (temp + p.S0));
+  double visc = (p.C1 * p.visc_mult * (temp * sqrt(temp)) / (temp + p.S0));
   double bulk = p.bulk_visc_mult * visc;
-  const double k = p.cp_div_pr * visc;
+  double k = p.cp_div_pr * visc;
   bulk -= 2. / 3. * visc;
+  if (ax && (p.sgs_model | p.sponge)) dry_modify_transport(p, s[0], g + 1, NEQ, *ax, visc, bulk, k);
   double stress[DIM * DIM];
   double divV = 0.;
 #pragma unroll
@@ -123,6 +138,88 @@ __device__ __forceinline__ void dry_visc_flux(const PhysParams &p, const double 
 #pragma unroll
     for (int j = 0; j < DIM; j++) vtmp += stress[d + j * DIM] * vel[j];
     f[4 + d * NEQ] = vtmp + k * g[4 + d * NEQ];
+  }
+}
+
+// Fluxes::sgsSmag (fluxes.cpp:513-541): mu_sgs = rho (C_d max(delta - floor, 0))^2 sqrt(2 S_ij S_ij).
+// gv[i + ds*d] = d u_i / d x_d
+__device__ __forceinline__ double dry_sgs_smag(const PhysParams &p, double rho, const double *gv, int ds, double delta) {
+  const double s3 = 0.5 * (gv[0 + ds] + gv[1]), s4 = 0.5 * (gv[0 + 2 * ds] + gv[2]), s5 = 0.5 * (gv[1 + 2 * ds] + gv[2 + ds]);
+  double sm = 0.;
+  sm += gv[0] * gv[0];
+  sm += gv[1 + ds] * gv[1 + ds];
+  sm += gv[2 + 2 * ds] * gv[2 + 2 * ds];
+  sm += 2.0 * s3 * s3;
+  sm += 2.0 * s4 * s4;
+  sm += 2.0 * s5 * s5;
+  sm = sqrt(2.0 * sm);
+  const double dm = p.sgs_const * fmax(delta - p.sgs_floor, 0.0);
+  return rho * dm * dm * sm;
+}
+// Fluxes::sgsSigma (fluxes.cpp:543-650), the branch without LAPACK (the one a device build and the oracle's
+// reference object code run): singular values of grad u from the closed-form eigenvalues of d^4 g^T g
+// (Nicoud et al. 2011); the reference's truncated pi and its 1e-12 guards are kept.
+__device__ __noinline__ double dry_sgs_sigma(const PhysParams &p, double rho, const double *gv, int ds, double delta) {
+  const double sml = 1.0e-12, pi = 3.14159265359, third = 1. / 3.;
+  const double dm = fmax(delta - p.sgs_floor, sml);
+  const double d4 = pow(dm, 4);
+  double Q[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double a = 0;
+      for (int k = 0; k < 3; k++) a += gv[k + ds * i] * gv[k + ds * j];
+      Q[i][j] = a * d4;
+    }
+  const double p1 = Q[0][1] * Q[0][1] + Q[0][2] * Q[0][2] + Q[1][2] * Q[1][2];
+  const double q = third * (Q[0][0] + Q[1][1] + Q[2][2]);
+  const double p2 = (Q[0][0] - q) * (Q[0][0] - q) + (Q[1][1] - q) * (Q[1][1] - q) + (Q[2][2] - q) * (Q[2][2] - q) + 2.0 * p1;
+  const double pp = sqrt(fmax(p2, 0.0) / 6.0);
+  double B[3][3];
+  const double ip = 1.0 / fmax(pp, sml);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) B[i][j] = (Q[i][j] - (i == j ? q : 0.0)) * ip;
+  const double detB = B[0][0] * (B[1][1] * B[2][2] - B[2][1] * B[1][2]) - B[0][1] * (B[1][0] * B[2][2] - B[2][0] * B[1][2]) +
+                      B[0][2] * (B[1][0] * B[2][1] - B[2][0] * B[1][1]);
+  const double r = 0.5 * detB;
+  const double phi = r <= -1.0 ? third * pi : (r >= 1.0 ? 0.0 : third * acos(r));
+  const double e0 = q + 2.0 * pp * cos(phi), e2 = q + 2.0 * pp * cos(phi + (2.0 * third * pi));
+  const double e1 = 3.0 * q - e0 - e2;
+  const double g0 = sqrt(fmax(e0, sml)), g1 = sqrt(fmax(e1, sml)), g2 = sqrt(fmax(e2, sml));
+  double mu = g2 * (g0 - g1) * (g1 - g2);
+  mu = fmax(mu, 0.0);
+  mu /= (g0 * g0);
+  mu *= (p.sgs_const * p.sgs_const);
+  mu *= rho;
+  if (mu != mu) mu = 0.0;
+  return mu;
+}
+// Fluxes::viscSpongePlanar (fluxes.cpp:664-684)
+__device__ __forceinline__ double dry_sponge_weight(const PhysParams &p, const double *x) {
+  const double factor = fmax(p.sp_ratio, 1.0);
+  double dist = 0.;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) dist += (x[d] - p.sp_p[d]) * p.sp_n[d];
+  double wgt = 0.5 * (tanh(dist / p.sp_width - 2.0) + 1.0);
+  wgt *= (factor - 1.0);
+  wgt += 1.0;
+  return wgt;
+}
+// the modification block of Fluxes::ComputeViscousFluxes / ComputeBdrViscousFluxes (fluxes.cpp:224-246, 386-407):
+// bulk arrives as (bulk_mult - 2/3) visc
+__device__ __forceinline__ void dry_modify_transport(const PhysParams &p, double rho, const double *gv, int ds, const DryAux &ax,
+                                                     double &visc, double &bulk, double &k) {
+  if (p.sgs_model > 0) {
+    const double pr_cp = visc / k;
+    const double mu_sgs = p.sgs_model == 1 ? dry_sgs_smag(p, rho, gv, ds, ax.delta) : dry_sgs_sigma(p, rho, gv, ds, ax.delta);
+    bulk *= (1.0 + mu_sgs / visc);
+    visc += mu_sgs;
+    k += (mu_sgs / pr_cp);
+  }
+  if (p.sponge) {
+    const double wgt = dry_sponge_weight(p, ax.x);
+    visc *= wgt;
+    bulk *= wgt;
+    k *= wgt;
   }
 }
 
@@ -190,11 +287,15 @@ __device__ __forceinline__ void dry_transport_pt(const PhysParams &p, const DryP
   bulk = (p.bulk_visc_mult - 2. / 3.) * visc;
   k = p.cp_div_pr * visc;
 }
-// F_v(s, g).n ; gu[i + 3*d] = d u_i / d x_d, gT[d] = dT/dx_d ; fn[0] = 0
-__device__ __forceinline__ void dry_visc_dot_n(const PhysParams &p, const DryPoint &q, const double *gu,
-                                               const double *gT, const double *nor, double *fn) {
-  double visc, bulk, k;
+// transport coefficients with the SGS model / sponge applied when ax is given
+__device__ __forceinline__ void dry_visc_coeffs(const PhysParams &p, const DryPoint &q, const double *gu, const DryAux *ax,
+                                                double rho, double &visc, double &bulk, double &k) {
   dry_transport_pt(p, q, visc, bulk, k);
+  if (ax && (p.sgs_model | p.sponge)) dry_modify_transport(p, rho, gu, 3, *ax, visc, bulk, k);
+}
+// F_v(s, g).n ; gu[i + 3*d] = d u_i / d x_d, gT[d] = dT/dx_d ; fn[0] = 0
+__device__ __forceinline__ void dry_visc_dot_n_c(const DryPoint &q, double visc, double bulk, double k, const double *gu,
+                                                 const double *gT, const double *nor, double *fn) {
   const double divV = gu[0 + 3 * 0] + gu[1 + 3 * 1] + gu[2 + 3 * 2];
   double tn[DIM];
 #pragma unroll
@@ -210,6 +311,13 @@ __device__ __forceinline__ void dry_visc_dot_n(const PhysParams &p, const DryPoi
   fn[3] = tn[2];
   fn[4] = q.vel[0] * tn[0] + q.vel[1] * tn[1] + q.vel[2] * tn[2] +
           k * (gT[0] * nor[0] + gT[1] * nor[1] + gT[2] * nor[2]);
+}
+__device__ __forceinline__ void dry_visc_dot_n(const PhysParams &p, const DryPoint &q, const double *gu,
+                                               const double *gT, const double *nor, double *fn, const DryAux *ax = nullptr,
+                                               double rho = 0.0) {
+  double visc, bulk, k;
+  dry_visc_coeffs(p, q, gu, ax, rho, visc, bulk, k);
+  dry_visc_dot_n_c(q, visc, bulk, k, gu, gT, nor, fn);
 }
 
 #define SLIPFN __host__ __device__ __noinline__
@@ -311,16 +419,17 @@ __device__ __forceinline__ void dry_bc_prim_for_gradient(const BcDev &bc, const 
 // no species-enthalpy term, single temperature.  nrm = unit normal; heat_prescribed: primFluxIdxs[numSpecies+nvel]
 // with value 0 (adiabatic wall).  g[eq + d*NEQ].
 __device__ __forceinline__ void dry_bdr_visc_flux(const PhysParams &p, const double *s, const double *g, const double *nrm,
-                                                  bool heat_prescribed, double *nf) {
+                                                  bool heat_prescribed, double *nf, const DryAux *ax = nullptr) {
 #pragma unroll
   for (int eq = 0; eq < NEQ; eq++) nf[eq] = 0.;
   if (p.eq_system == 0) return;
   const double pr = dry_pressure(p, s);
   const double temp = pr / p.R / s[0];
-  const double visc = (p.C1 * p.visc_mult * (temp * sqrt(temp)) / (temp + p.S0));
+  double visc = (p.C1 * p.visc_mult * (temp * sqrt(temp)) / (temp + p.S0));
   double bulk = p.bulk_visc_mult * visc;
-  const double k = p.cp_div_pr * visc;
+  double k = p.cp_div_pr * visc;
   bulk -= 2. / 3. * visc;
+  if (ax && (p.sgs_model | p.sponge)) dry_modify_transport(p, s[0], g + 1, NEQ, *ax, visc, bulk, k);
   double stress[DIM * DIM];
   double divV = 0.;
 #pragma unroll
@@ -356,7 +465,7 @@ __device__ __forceinline__ void dry_bdr_visc_flux(const PhysParams &p, const dou
 // computeAdiabaticWallFlux / computeIsothermalWallFlux (wallBC.cpp:277-320, 430-510).  g[eq + d*NEQ] interior
 // gradients of the primitives; nor = CalcOrtho normal (area weighted, outward).
 __device__ __forceinline__ void dry_bc_flux(const PhysParams &p, const BcDev &bc, int use_bc_in_grad, const double *u1,
-                                            const double *g, const double *nor, double *fx) {
+                                            const double *g, const double *nor, double *fx, const DryAux *ax = nullptr) {
   double s2[NEQ];
   const double normN = nor[0] * nor[0] + nor[1] * nor[1] + nor[2] * nor[2];
   if (bc.kind == 0) {
@@ -405,11 +514,11 @@ __device__ __forceinline__ void dry_bc_flux(const PhysParams &p, const BcDev &bc
     s2[3] = u1[0] * (vel[2] - 2. * vn * un[2]);
     dry_riemann_lf(p, u1, s2, nor, fx);
     if (p.eq_system == 0) return;
-    dry_visc_flux(p, s2, g, viscF);
+    dry_visc_flux(p, s2, g, viscF, ax);
 #pragma unroll
     for (int eq = 0; eq < NEQ; eq++)
       wallViscF[eq] = viscF[eq] * nor[0] + viscF[eq + NEQ] * nor[1] + viscF[eq + 2 * NEQ] * nor[2];
-    dry_visc_flux(p, u1, g, viscF);
+    dry_visc_flux(p, u1, g, viscF, ax);
   } else {
     const double isq = 1. / sqrt(normN);
     const double un[3] = {nor[0] * isq, nor[1] * isq, nor[2] * isq};
@@ -421,7 +530,7 @@ __device__ __forceinline__ void dry_bc_flux(const PhysParams &p, const BcDev &bc
       s2[4] = pr / p.gm1;
       dry_riemann_lf(p, u1, s2, nor, fx);
       if (p.eq_system == 0) return;
-      dry_bdr_visc_flux(p, s2, g, un, true, wallViscF);
+      dry_bdr_visc_flux(p, s2, g, un, true, wallViscF, ax);
     } else {  // VISC_ISOTH
       if (use_bc_in_grad) {
         s2[1] = -u1[1];
@@ -435,12 +544,12 @@ __device__ __forceinline__ void dry_bc_flux(const PhysParams &p, const BcDev &bc
       if (p.eq_system == 0) return;
       s2[1] = s2[2] = s2[3] = 0.;
       s2[4] = p.R / p.gm1 * u1[0] * bc.d[0];
-      dry_bdr_visc_flux(p, s2, g, un, false, wallViscF);
+      dry_bdr_visc_flux(p, s2, g, un, false, wallViscF, ax);
     }
     const double nm = sqrt(normN);
 #pragma unroll
     for (int eq = 0; eq < NEQ; eq++) wallViscF[eq] *= nm;
-    dry_visc_flux(p, u1, g, viscF);
+    dry_visc_flux(p, u1, g, viscF, ax);
   }
 #pragma unroll
   for (int eq = 1; eq < NEQ; eq++) {

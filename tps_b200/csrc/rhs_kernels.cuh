@@ -57,6 +57,7 @@ struct KernelArgs {
   const double *geo;       // [NE][12] adj(J) (A[r + 3 d]), det, 1/det, pad
   double *tr;              // [6 NE + shared faces][10][np*np] face-trace blocks
   const int4 *face_desc;   // [NFint] {block of side 1, block of side 2, perm code Elem2 face coords -> face coords, 0}
+  const double *elem_delta;  // [NE+NEH] h_min / order (Mesh::GetElementSize(e, 1) / order): SGS models
   const double *face_nor;  // [NFint][4] CalcOrtho normal (Elem1 -> Elem2, area weighted) and its magnitude
   // boundary faces (BCintegrator): face k lifts into faceRes slot NFint + k
   int NFbdr;
@@ -105,6 +106,20 @@ __device__ __forceinline__ void face_normal(const double *Xf, double s, double t
   nor[2] = ts[0] * tt[1] - ts[1] * tt[0];
 }
 
+// physical point of a bilinear face / trilinear hexahedron
+__device__ __forceinline__ void face_point(const double *Xf, double s, double t, double *x) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    x[i] = (1.0 - s) * (1.0 - t) * Xf[0 * 3 + i] + s * (1.0 - t) * Xf[1 * 3 + i] + s * t * Xf[2 * 3 + i] + (1.0 - s) * t * Xf[3 * 3 + i];
+}
+__device__ __forceinline__ void hex_point(const double *v, double x, double y, double z, double *X) {
+  const double x0 = 1.0 - x, y0 = 1.0 - y, z0 = 1.0 - z;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    X[i] = z0 * (y0 * (x0 * v[0 * 3 + i] + x * v[1 * 3 + i]) + y * (x * v[2 * 3 + i] + x0 * v[3 * 3 + i])) +
+           z * (y0 * (x0 * v[4 * 3 + i] + x * v[5 * 3 + i]) + y * (x * v[6 * 3 + i] + x0 * v[7 * 3 + i]));
+}
+
 __device__ __forceinline__ void atomic_max_double(unsigned long long *addr, double v) {
   // v >= 0: IEEE bit patterns of non-negative doubles are ordered like unsigned integers
   atomicMax(addr, static_cast<unsigned long long>(__double_as_longlong(v)));
@@ -119,9 +134,9 @@ __global__ void pack_kernel(int nsend, int nd, int nfld, long long N, const int 
 // grad_kernel / face_flux_kernel / elem_resid_kernel are templates on NP = p+1; see rhs_kernels.cu
 template <int NP, int EPB, int MINB>
 __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list);
-template <int NP, int FPB, int NT, bool BDR>
+template <int NP, int FPB, int NT, bool BDR, bool MOD>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
-template <int NP, int EPB, int MINB, bool AFF>
+template <int NP, int EPB, int MINB, bool AFF, bool MOD>
 __global__ void elem_resid_kernel(KernelArgs a, int elem_begin, int elem_count);
 
 // y = x + a*k ; z = x + b*k  etc. for the ODE stages

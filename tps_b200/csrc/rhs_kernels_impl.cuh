@@ -282,7 +282,7 @@ __device__ __forceinline__ int carried_grad_field(int u) {  // u in [NEQ, NFC) -
 // BDR = true: the faces are boundary faces (a.bdr_*): only Elem1's side exists, the numerical flux is the
 // boundary-condition flux of BCintegrator::AssembleFaceVector (src/BCintegrator.cpp:295-441) and the result
 // goes to faceRes slot NFint + k.
-template <int NP, int FPB, int NT, bool BDR>
+template <int NP, int FPB, int NT, bool BDR, bool MOD>
 __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list) {
   constexpr int NF2 = NP * NP, NQ = NP + 1, NQ2 = NQ * NQ, ND = NP * NP * NP;
   __shared__ double sT[FPB][2][NFC][NF2 + 1];  // +1: conflict-free per-(side,field) row reads
@@ -413,6 +413,16 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
       u2[f] = BDR ? 0.0 : sQ[fl][1][f][qp];
     }
     face_normal(sXf[fl], c_T.xq[al], c_T.xq[be], nor);
+    // SGS model / viscous sponge: same physical point for both sides, each side's own element size (parity trap 5)
+    constexpr bool mod = MOD;  // compiled out of the plain instantiation (it cost ~15 % there as a run-time branch)
+    DryAux ax1, ax2;
+    if constexpr (MOD) {
+      const int fcm = sFc[fl];
+      face_point(sXf[fl], c_T.xq[al], c_T.xq[be], ax1.x);
+      ax2.x[0] = ax1.x[0], ax2.x[1] = ax1.x[1], ax2.x[2] = ax1.x[2];
+      ax1.delta = a.elem_delta[BDR ? a.bdr_el1[fcm] : a.face_el1[fcm]];
+      ax2.delta = BDR ? ax1.delta : a.elem_delta[a.face_el2[fcm]];
+    }
     if constexpr (BDR) {
       double g[NEQ * DIM], fxb[NEQ];
 #pragma unroll
@@ -421,7 +431,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 #pragma unroll
         for (int i = 0; i < NEQ - 1; i++) g[1 + i + d * NEQ] = sQ[fl][0][NEQ + d * (NEQ - 1) + i][qp];
       }
-      dry_bc_flux(a.phys, a.bct.bc[a.bdr_bc[sFc[fl]]], a.bct.use_bc_in_grad, u1, g, nor, fxb);
+      dry_bc_flux(a.phys, a.bct.bc[a.bdr_bc[sFc[fl]]], a.bct.use_bc_in_grad, u1, g, nor, fxb, mod ? &ax1 : nullptr);
       const double wb = c_T.wq[al] * c_T.wq[be];
       double *dstb = &sT[0][0][0][0] + fl * (2 * NFC * (NF2 + 1));
 #pragma unroll
@@ -445,14 +455,14 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
         for (int i = 0; i < DIM; i++) gu[i + 3 * d] = sQ[fl][0][NEQ + d * (NEQ - 1) + i][qp];
         gT[d] = sQ[fl][0][NEQ + d * (NEQ - 1) + 3][qp];
       }
-      dry_visc_dot_n(a.phys, q1, gu, gT, nor, v1);
+      dry_visc_dot_n(a.phys, q1, gu, gT, nor, v1, mod ? &ax1 : nullptr, u1[0]);
 #pragma unroll
       for (int d = 0; d < DIM; d++) {
 #pragma unroll
         for (int i = 0; i < DIM; i++) gu[i + 3 * d] = sQ[fl][1][NEQ + d * (NEQ - 1) + i][qp];
         gT[d] = sQ[fl][1][NEQ + d * (NEQ - 1) + 3][qp];
       }
-      dry_visc_dot_n(a.phys, q2, gu, gT, nor, v2);
+      dry_visc_dot_n(a.phys, q2, gu, gT, nor, v2, mod ? &ax2 : nullptr, u2[0]);
 #pragma unroll
       for (int eq = 1; eq < NEQ; eq++) fx[eq] -= 0.5 * (v1[eq] + v2[eq]);
     }
@@ -502,7 +512,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 // elem_resid_kernel: EPB elements per CTA, one thread per node.
 // AFF: every element is a parallelepiped (fast path): adj(J) and det come from the 12-double table a.geo
 // instead of being rebuilt per node from the 8 vertices (~250 flops per node saved).
-template <int NP, int EPB, int MINB, bool AFF = false>
+template <int NP, int EPB, int MINB, bool AFF = false, bool MOD = false>
 __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(KernelArgs a, int elem_begin, int elem_count) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
@@ -583,6 +593,17 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
       adj3(J, A);
     }
     wnode = sWn[i] * sWn[j] * sWn[k];
+    // SGS model / viscous sponge (general path only; the fast path never carries them)
+    DryAux ax;
+    constexpr bool mod = MOD && !AFF;
+    if constexpr (mod) {
+      ax.delta = a.elem_delta[e];
+      hex_point(sVx[le], sXn[i], sXn[j], sXn[k], ax.x);
+    }
+    double visc = 0, bulk = 0, kth = 0;
+    if constexpr (mod) {
+      if (a.phys.eq_system != 0) dry_visc_coeffs(a.phys, q, gu, &ax, s[0], visc, bulk, kth);
+    }
     // G[eq][r] = w_k sum_d adjJ(r,d) (F_c - F_v)[eq][d]: the flux of GetFlux (rhs_operator.cpp:532-540)
     // contracted with row r of adj(J) (DomainIntegrator, domain_integrator.cpp:71-97)
 #pragma unroll
@@ -592,7 +613,10 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
       dry_conv_dot_n(s, q, ar, fc);
       if (a.phys.eq_system != 0) {
         double fv[NEQ];
-        dry_visc_dot_n(a.phys, q, gu, gT, ar, fv);
+        if constexpr (mod)
+          dry_visc_dot_n_c(q, visc, bulk, kth, gu, gT, ar, fv);
+        else
+          dry_visc_dot_n(a.phys, q, gu, gT, ar, fv);
 #pragma unroll
         for (int eq = 1; eq < NEQ; eq++) fc[eq] -= fv[eq];
       }

@@ -35,7 +35,7 @@ struct tpsb_ctx {
   PhysParams phys;
   std::vector<int> element_to_faces;  // reference layout, stride 7
   // device tables
-  double *d_vx = nullptr;
+  double *d_vx = nullptr, *d_elem_delta = nullptr;
   int *d_nbr_elem = nullptr, *d_nbr_code = nullptr, *d_face_el1 = nullptr, *d_face_el2 = nullptr,
       *d_face_inf1 = nullptr, *d_face_inf2 = nullptr, *d_el_face = nullptr, *d_el_face_code = nullptr;
   int *d_elem_list = nullptr;  // interior elements first, then elements touching a shared face
@@ -146,6 +146,42 @@ static cudaError_t upload(T **dst, const std::vector<T> &src) {
   cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), src.size() * sizeof(T));
   if (e != cudaSuccess) return e;
   return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// h_min of a trilinear hexahedron as MFEM's Mesh::GetElementSize(e, 1) defines it: the smallest singular value of the
+// Jacobian at the element centre (the cube is its own "perfect" element).  One-sided Jacobi (Hestenes) SVD: rotate
+// column pairs until orthogonal; the singular values are the column norms.
+static double hex_min_size(const double *v) {
+  double J[3][3];  // J[i][j] = d x_i / d xi_j at (1/2, 1/2, 1/2)
+  static const int lo[3][4] = {{0, 3, 4, 7}, {0, 1, 4, 5}, {0, 1, 2, 3}}, hi[3][4] = {{1, 2, 5, 6}, {3, 2, 7, 6}, {4, 5, 6, 7}};
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) {
+      double s = 0;
+      for (int q = 0; q < 4; q++) s += v[hi[j][q] * 3 + i] - v[lo[j][q] * 3 + i];
+      J[i][j] = 0.25 * s;
+    }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        double a = 0, b = 0, g = 0;
+        for (int i = 0; i < 3; i++) a += J[i][p] * J[i][p], b += J[i][q] * J[i][q], g += J[i][p] * J[i][q];
+        if (std::fabs(g) <= 1e-17 * std::sqrt(a * b)) continue;
+        off = std::max(off, std::fabs(g) / std::sqrt(a * b));
+        const double zeta = (b - a) / (2.0 * g);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+        for (int i = 0; i < 3; i++) {
+          const double xp = J[i][p], xq = J[i][q];
+          J[i][p] = cs * xp - sn * xq;
+          J[i][q] = sn * xp + cs * xq;
+        }
+      }
+    if (off == 0) break;
+  }
+  double m = 1e300;
+  for (int j = 0; j < 3; j++) m = std::min(m, std::sqrt(J[0][j] * J[0][j] + J[1][j] * J[1][j] + J[2][j] * J[2][j]));
+  return m;
 }
 
 static bool element_is_affine(const double *v) {
@@ -674,6 +710,15 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (want_generic) {
     if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
   }
+  const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
+  if (phys->sgs_model < 0 || phys->sgs_model > 2) return fail(ctx, TPSB_EINVAL, "sgs_model %d: 0 none, 1 smagorinsky, 2 sigma", phys->sgs_model);
+  if (visc_mod && want_generic)
+    return fail(ctx, TPSB_ENOTIMPL, "SGS models and the viscous sponge are built on the 3-D dry-air Gauss-Legendre path only");
+  if (phys->sponge_enabled) {
+    const double *n = phys->sponge_normal;
+    if (!(n[0] * n[0] + n[1] * n[1] + n[2] * n[2] > 0) || !(phys->sponge_width > 0))
+      return fail(ctx, TPSB_EINVAL, "viscous sponge needs a non-zero normal and a positive width");
+  }
   if (phys->eq_system != TPSB_EULER && phys->eq_system != TPSB_NS)
     return fail(ctx, TPSB_ENOTIMPL, "equation system %d not built", phys->eq_system);
   if (maps->num_elems <= 0 || maps->num_faces <= 0 || !maps->elem_vertices || !maps->face_el1 || !maps->face_el2 ||
@@ -739,6 +784,19 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   c->phys.C1 = phys->sutherland_C1;
   c->phys.S0 = phys->sutherland_S0;
   c->phys.Pr = phys->sutherland_Pr;
+  c->phys.sgs_model = phys->sgs_model;
+  c->phys.sgs_const = phys->sgs_const;
+  c->phys.sgs_floor = phys->sgs_floor;
+  c->phys.sponge = phys->sponge_enabled ? 1 : 0;
+  c->phys.sp_ratio = 1.0, c->phys.sp_width = 1.0;
+  for (int d = 0; d < 3; d++) c->phys.sp_n[d] = c->phys.sp_p[d] = 0.0;
+  if (phys->sponge_enabled) {  // Fluxes' constructor normalises the normal (fluxes.cpp:73-83)
+    const double *n = phys->sponge_normal;
+    const double nm = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int d = 0; d < 3; d++) c->phys.sp_n[d] = n[d] / nm, c->phys.sp_p[d] = phys->sponge_point[d];
+    c->phys.sp_ratio = phys->sponge_ratio;
+    c->phys.sp_width = phys->sponge_width;
+  }
   c->phys.cp_div_pr = phys->specific_heat_ratio * phys->gas_constant /
                       (phys->sutherland_Pr * (phys->specific_heat_ratio - 1.));
 
@@ -853,7 +911,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
 
   // ---- fast path tables (rhs_fast.cuh): affine metric per element, per-face block ids / normals ----
   // all-parallelepiped meshes run the fast path; anything else (trilinear/skewed elements) the general one
-  c->fast = all_affine;
+  c->fast = all_affine && !visc_mod;  // the SGS models need the full velocity gradient at the face points
   if (const char *pth = getenv("TPSB_PATH")) c->fast = c->fast && strcmp(pth, "legacy") != 0 && strcmp(pth, "general") != 0;
   std::vector<double> geo, face_nor;
   std::vector<int4> face_desc;
@@ -928,6 +986,12 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   cudaError_t ce = cudaSetDevice(device);
   std::vector<double> vx(maps->elem_vertices, maps->elem_vertices + static_cast<size_t>(NE + NEH) * 24);
   if (ce == cudaSuccess) ce = upload(&c->d_vx, vx);
+  if (ce == cudaSuccess && visc_mod) {
+    // delta = Mesh::GetElementSize(e, 1) / order: smallest singular value of the Jacobian at the element centre
+    std::vector<double> delta(static_cast<size_t>(NE + NEH));
+    for (int e = 0; e < NE + NEH; e++) delta[e] = hex_min_size(&maps->elem_vertices[static_cast<size_t>(e) * 24]) / c->order;
+    ce = upload(&c->d_elem_delta, delta);
+  }
   if (ce == cudaSuccess) ce = upload(&c->d_nbr_elem, nbr_elem);
   if (ce == cudaSuccess) ce = upload(&c->d_nbr_code, nbr_code);
   if (ce == cudaSuccess) ce = upload(&c->d_face_el1, fl_el1);
@@ -1040,7 +1104,7 @@ void tpsb_destroy(tpsb_ctx *c) {
                   c->d_faceRes,  c->d_Uhalo,     c->d_UpHalo,       c->d_gradUpHalo, c->d_sendU,   c->d_sendG,
                   c->d_maxBits,  c->d_mcs,       c->d_send_elems,   c->d_k,        c->d_yv,       c->d_z,
                   c->d_hx,       c->d_hy,        c->d_geo,          c->d_tr,       c->d_face_nor, c->d_sendTr,
-                  c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc};
+                  c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc,   c->d_elem_delta};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (void *p : c->gen_allocs) cudaFree(p);
@@ -1104,6 +1168,7 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   a.bdr_bc = c->d_bdr_bc;
   a.bct = c->bct;
   a.geo = c->d_geo;
+  a.elem_delta = c->d_elem_delta;
   a.tr = c->d_tr;
   a.face_desc = c->d_face_desc;
   a.face_nor = c->d_face_nor;
@@ -1125,28 +1190,38 @@ template <int NP, int FPB, int NTF>
 static void launch_face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (count <= 0) return;
   ProfScope ps(c, K_FACE);
-  face_flux_kernel<NP, FPB, NTF, false><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
+  if (c->phys.sgs_model | c->phys.sponge)
+    face_flux_kernel<NP, FPB, NTF, false, true><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
+  else
+    face_flux_kernel<NP, FPB, NTF, false, false><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
 }
 // boundary faces: BCintegrator (src/BCintegrator.cpp:295-441), same kernel in one-sided mode
 static void bdr_faces(tpsb_ctx *c, const KernelArgs &a) {
   const int count = c->NFbdr;
   if (count <= 0) return;
   ProfScope ps(c, K_FACE);
-  if (c->np == 4)
-    face_flux_kernel<4, 4, 160, true><<<(count + 3) / 4, 160, 0, c->stream>>>(a, 0, count, nullptr);
-  else if (c->np == 3)
-    face_flux_kernel<3, 4, 128, true><<<(count + 3) / 4, 128, 0, c->stream>>>(a, 0, count, nullptr);
-  else
-    face_flux_kernel<2, 8, 128, true><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
+  const bool mod = (c->phys.sgs_model | c->phys.sponge) != 0;
+  if (c->np == 4) {
+    if (mod) face_flux_kernel<4, 4, 160, true, true><<<(count + 3) / 4, 160, 0, c->stream>>>(a, 0, count, nullptr);
+    else face_flux_kernel<4, 4, 160, true, false><<<(count + 3) / 4, 160, 0, c->stream>>>(a, 0, count, nullptr);
+  } else if (c->np == 3) {
+    if (mod) face_flux_kernel<3, 4, 128, true, true><<<(count + 3) / 4, 128, 0, c->stream>>>(a, 0, count, nullptr);
+    else face_flux_kernel<3, 4, 128, true, false><<<(count + 3) / 4, 128, 0, c->stream>>>(a, 0, count, nullptr);
+  } else {
+    if (mod) face_flux_kernel<2, 8, 128, true, true><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
+    else face_flux_kernel<2, 8, 128, true, false><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
+  }
 }
 template <int NP, int EPB, int MINB = 1>
 static void launch_resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (count <= 0) return;
   ProfScope ps(c, K_RESID);
   if (c->fast)
-    elem_resid_kernel<NP, EPB, MINB, true><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
+    elem_resid_kernel<NP, EPB, MINB, true, false><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
+  else if (c->phys.sgs_model | c->phys.sponge)
+    elem_resid_kernel<NP, EPB, MINB, false, true><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
   else
-    elem_resid_kernel<NP, EPB, MINB, false><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
+    elem_resid_kernel<NP, EPB, MINB, false, false><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
 }
 
 // Launch-shape selection.  p = 3 is the tuned case; tune[] (TPSB_TUNE="g,f,r", development knob) picks
@@ -1193,7 +1268,11 @@ static void resid(tpsb_ctx *c, const KernelArgs &a, int begin = 0, int count = -
       case 4: launch_resid<4, 4, 2>(c, a, begin, count); break;
       case 5: launch_resid<4, 2, 6>(c, a, begin, count); break;
       case 6: launch_resid<4, 1, 10>(c, a, begin, count); break;
-      default: launch_resid<4, 1, 12>(c, a, begin, count); break;
+      default:
+        // the trilinear instantiation rebuilds the metric per node: 102 registers (10 CTAs / SM) beat 80 with spills
+        if (c->fast) launch_resid<4, 1, 12>(c, a, begin, count);
+        else launch_resid<4, 1, 10>(c, a, begin, count);
+        break;
     }
   } else if (c->np == 3) {
     launch_resid<3, 8, 2>(c, a, begin, count);
