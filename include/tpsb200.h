@@ -109,8 +109,9 @@ typedef struct {
   const double *table_x[TPSB_MAX_REACTIONS], *table_f[TPSB_MAX_REACTIONS];
   int rate_component[TPSB_MAX_REACTIONS];
   /* transport_model = argon_mixture (TransportModel value 1): GasMixtureTransport (src/gas_transport.cpp:877-1650),
-   * argon mixtures of up to 7 species.  collision_index[spI + spJ*num_species] (spI <= spJ) = GasColl value
-   * (src/dataStructures.hpp:122-143: 0 CLMB_ATT, 1 CLMB_REP, 2 AR_AR1P, 3 AR_E, 4 AR_AR), as
+   * argon or nitrogen mixtures of up to 7 species.  collision_index[spI + spJ*num_species] (spI <= spJ) = GasColl value
+   * (src/dataStructures.hpp:122-143: 0 CLMB_ATT, 1 CLMB_REP, 2 AR_AR1P, 3 AR_E, 4 AR_AR; nitrogen 6 NI_NI1P, 7 NI_E,
+   * 8 NI_NI, 10 N2_NI1P, 11 N2_E, 12 N2_N2, 13 N2_NI with the curve fits of src/collision_integrals.cpp:210-625), as
    * M2ulPhyS::identifyCollisionType fills GasTransportInput::collisionIndex (src/M2ulPhyS.cpp:3925-3970);
    * ion_index / neutral_index: the species 'Ar.+1' and 'Ar' (GasTransportInput::ionIndex / neutralIndex).            */
   int collision_index[TPSB_MAX_SPECIES * TPSB_MAX_SPECIES];

@@ -256,3 +256,59 @@ def test_argon_mixture_transport_equals_reference_classes(lib_built, oracle_buil
         got = op.point_eval(what, Ud, gd).cpu().numpy()
         scale = np.abs(ref).max(axis=0)
         assert (np.abs(got - ref) <= tol * scale + 1e-300).all(), (what, np.abs(got - ref).max(axis=0) / (scale + 1e-300))
+
+
+def nitrogen6_dict():
+    """Six-species nitrogen mixture in mixture order [Ni.+1, Ni_e, N2_e, Ni, E, N2] with the species data of
+    test/inputs/input.reactNitrogen.ini (formation energies, molar heat capacities); 'kind' = GasSpcs."""
+    MW_N, MW_E = 14.0067e-3, 5.48579908782496e-7
+    names = ["NI1P", "NI", "N2", "NI", "E", "N2"]
+    mw = [MW_N - MW_E, MW_N, 2 * MW_N, MW_N, MW_E, 2 * MW_N]
+    ch = [1.0, 0.0, 0.0, 0.0, -1.0, 0.0]
+    fe = [1873823.43223, 758424.8665, 812408.331926, 470723.5922, 0.0, 0.0]
+    cv = [1.5, 1.5, 2.5, 1.5, 1.5, 2.5]
+    sp = [dict(mw=mw[i], charge=ch[i], formation_energy=fe[i], molar_cv=cv[i], diffusivity=1e-3, mt_freq=1e3, kind=names[i])
+          for i in range(6)]
+    return dict(ambipolar=False, two_temperature=True, viscosity=2.2e-3, bulk_viscosity=4.0e-4, thermal_conductivity=0.12,
+                electron_thermal_conductivity=0.3, species=sp, reactions=[], ion_index=0, neutral_index=3)
+
+
+@needs_ref
+@pytest.mark.parametrize("third", [False, True])
+def test_nitrogen_mixture_transport_equals_reference_classes(lib_built, oracle_built, third):
+    """GasMixtureTransport over the nitrogen collision types (N-N, N2-N2, N2-N, N-N.+1, N2-N.+1, e-N, e-N2 curve fits of
+    src/collision_integrals.cpp:210-625), point-wise against the reference's own object code."""
+    import torch
+    d = nitrogen6_dict()
+    d.update(transport_model="argon_mixture", third_order_k_electron=third)
+    pm = tps_b200.PlasmaModels.from_dict(d)
+    ns = 6
+    got_types = {pm.collision_index[i + j * ns] for i in range(ns) for j in range(i, ns)}
+    assert got_types == {0, 1, 6, 7, 8, 10, 11, 12, 13}
+    op, orc = _pair_models(pm, order=2, n=(3, 3))
+    assert op.neq == 10
+    rng = np.random.default_rng(12)
+    n = 300
+    up = np.zeros((n, 10))
+    up[:, 0] = rng.uniform(0.04, 0.08, n)
+    up[:, 1:3] = rng.uniform(-300, 300, (n, 2))
+    up[:, 3] = rng.uniform(3000, 12000, n)
+    up[:, 4:9] = rng.uniform(1e-4, 0.03, (n, 5))
+    up[:, 8] = up[:, 4]  # quasi-neutral: n_e = n_ion
+    up[:, 9] = rng.uniform(5000, 15000, n)
+    # density consistent with a positive background (N2) number density
+    MW_N, MW_E = 14.0067e-3, 5.48579908782496e-7
+    mw = np.array([MW_N - MW_E, MW_N, 2 * MW_N, MW_N, MW_E])
+    up[:, 0] = (up[:, 4:9] * mw).sum(axis=1) + rng.uniform(0.5, 2.0, n) * 2 * MW_N
+    U = orc.pt("cons", up)
+    g = rng.normal(size=(n, 20)) * np.array(([0.005, 50, 50, 800] + [0.01] * 5 + [900]) * 2)
+    Ud, gd = torch.from_numpy(U).cuda(), torch.from_numpy(g).cuda()
+    # the e-N / e-N2 fits are sums of terms ~1e4 cancelling to ~-45 (round-off ~1e-12 relative in each integral); the
+    # third-order electron conductivity L11 - L12^2 / L22 cancels another 3-4 digits (measured 1.9e-9 on the energy flux)
+    t = 5e-9 if third else 1e-10
+    for what, args, tol in (("visc_flux", (U, g), t), ("source", (U, orc.pt("prim", U), g), 1e-10)):
+        ref = orc.pt(what, *args)
+        got = op.point_eval(what, Ud, gd).cpu().numpy()
+        assert np.isfinite(ref).all()
+        scale = np.abs(ref).max(axis=0)
+        assert (np.abs(got - ref) <= tol * scale + 1e-300).all(), (what, np.abs(got - ref).max(axis=0) / (scale + 1e-300))

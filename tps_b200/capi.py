@@ -80,10 +80,17 @@ class PlasmaModels(C.Structure):
             # 'neutral' (Ar and its excited states)
             ns = len(sp)
             kinds = [("electron" if q["charge"] < 0 else "ion" if q["charge"] > 0 else "neutral") for q in sp]
+            # nitrogen mixtures name each species' GasSpcs kind: 'N2', 'NI', 'NI1P', 'E' (the nitrogen branch of
+            # identifyCollisionType, src/reactingFlow.cpp:3641-3676); GasColl values src/dataStructures.hpp:122-144
+            nit = {("N2", "N2"): 12, ("N2", "NI"): 13, ("N2", "NI1P"): 10, ("E", "N2"): 11, ("NI", "NI"): 8, ("NI", "NI1P"): 6,
+                   ("E", "NI"): 7}
             for i in range(ns):
                 for j in range(i, ns):
                     zz = sp[i]["charge"] * sp[j]["charge"]
                     pair = {kinds[i], kinds[j]}
+                    if zz == 0 and "kind" in sp[i]:
+                        pm.collision_index[i + j * ns] = nit[tuple(sorted((sp[i]["kind"], sp[j]["kind"])))]
+                        continue
                     pm.collision_index[i + j * ns] = (1 if zz > 0 else 0 if zz < 0 else 4 if pair == {"neutral"} else
                                                       2 if pair == {"neutral", "ion"} else 3)
             pm.ion_index = d.get("ion_index", kinds.index("ion"))

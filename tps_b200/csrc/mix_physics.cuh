@@ -362,6 +362,33 @@ __host__ __device__ __noinline__ double coll_eAr(int r, double T) {
   for (int k = 0; k < 9; k++) fit += coeff[r - 1][k] * pw[k];
   return fit;
 }
+// Nitrogen pairs (collision_integrals.cpp:210-625): every fit is Q(T) = pre exp(s_sum sum_k (s_coef c_k) (ln T)^k) with
+// 2 to 7 terms; the scalings are applied where the reference applies them (to the coefficients for e-N / e-N2, to the
+// sum for N2-N.+1) and the powers are formed with pow() term by term, so the round-off of the strongly cancelling sums
+// (|terms| ~ 1e4 against a result ~ -45) follows the reference's.  Data table generated by tools/gen_nitrogen_fits.py.
+struct NitFit {
+  int n;
+  double s_coef, s_sum;
+  int pi;
+  double c[7];
+};
+enum { NIT_NiNi11 = 0, NIT_NiNi22, NIT_NiNi1P11, NIT_N2N211, NIT_N2N222, NIT_N2N21P11, NIT_N2Ni1P11, NIT_NiN21P11, NIT_N2Ni11,
+       NIT_N2Ni22, NIT_eNi11, NIT_eNi12, NIT_eNi13, NIT_eNi14, NIT_eNi15, NIT_eN211, NIT_eN212, NIT_eN213, NIT_eN214, NIT_eN215 };
+__host__ __device__ __noinline__ double coll_nitrogen(int which, double T) {
+  const NitFit fits[20] = {
+#include "nitrogen_fits.inc"
+  };
+  const NitFit &f = fits[which];
+  const double logT = log(T);
+  double sum = f.s_coef == 1.0 ? f.c[0] : f.c[0] * f.s_coef;
+  for (int k = 1; k < f.n; k++) {
+    const double ck = f.s_coef == 1.0 ? f.c[k] : f.c[k] * f.s_coef;
+    sum += ck * (k == 1 ? logT : pow(logT, static_cast<double>(k)));
+  }
+  if (f.s_sum != 1.0) sum *= f.s_sum;
+  const double q = exp(sum);
+  return f.pi ? 3.14159265358979323846 * q : q;
+}
 
 constexpr double MIX_PI = 3.14159265358979323846;   // equation_of_state.hpp:67
 constexpr double MIX_EPS0 = 8.8541878128e-12;       // VACUUMPERMITTIVITY
@@ -504,7 +531,7 @@ MIXFN GmxColl gmx_collision_inputs(const MixParams &m, double Te, double Th, con
   c.ndimTh = debyeLength * 4.0 * MIX_PI * MIX_DEBYE * Th;
   return c;
 }
-// GasMixtureTransport::collisionIntegral (gas_transport.cpp:995-1283), charged and argon pairs.  Unsupported (l, r)
+// GasMixtureTransport::collisionIntegral (gas_transport.cpp:995-1283), charged, argon and nitrogen pairs.  Unsupported (l, r)
 // return NaN (the reference asserts).
 MIXBIG double gmx_collision_integral(const MixParams &m, int _spI, int _spJ, int l, int r, const GmxColl &ci) {
   const int spI = (_spI > _spJ) ? _spJ : _spI, spJ = (_spI > _spJ) ? _spI : _spJ;
@@ -558,8 +585,23 @@ MIXBIG double gmx_collision_integral(const MixParams &m, int _spI, int _spJ, int
       return (l == 1 && r >= 1 && r <= 5) ? coll_eAr(r, temp) : nan;
     case 4:  // AR_AR
       return (l == 1 && r == 1) ? coll_ArAr11(temp) : ((l == 2 && r == 2) ? coll_ArAr22(temp) : nan);
+    // nitrogen ("Ni") pairs, GasColl values of src/dataStructures.hpp:133-143 (gas_transport.cpp:1160-1277)
+    case 6:  // NI_NI1P
+      return (l == 1 && r == 1) ? coll_nitrogen(NIT_NiNi1P11, temp) : nan;
+    case 10:  // N2_NI1P
+      return (l == 1 && r == 1) ? coll_nitrogen(NIT_N2Ni1P11, temp) : nan;
+    case 11:  // N2_E
+      return (l == 1 && r >= 1 && r <= 5) ? coll_nitrogen(NIT_eN211 + r - 1, temp) : nan;
+    case 7:  // NI_E
+      return (l == 1 && r >= 1 && r <= 5) ? coll_nitrogen(NIT_eNi11 + r - 1, temp) : nan;
+    case 8:  // NI_NI
+      return (l == 1 && r == 1) ? coll_nitrogen(NIT_NiNi11, temp) : ((l == 2 && r == 2) ? coll_nitrogen(NIT_NiNi22, temp) : nan);
+    case 12:  // N2_N2
+      return (l == 1 && r == 1) ? coll_nitrogen(NIT_N2N211, temp) : ((l == 2 && r == 2) ? coll_nitrogen(NIT_N2N222, temp) : nan);
+    case 13:  // N2_NI
+      return (l == 1 && r == 1) ? coll_nitrogen(NIT_N2Ni11, temp) : ((l == 2 && r == 2) ? coll_nitrogen(NIT_N2Ni22, temp) : nan);
   }
-  return nan;
+  return -1.0;  // NI_N21P / N2_N21P have no case in the reference either: it returns -1
 }
 // binary diffusivities, Curtiss-Hirschfelder, mobilities, multipliers (gas_transport.cpp:1323-1349)
 MIXBIG void gmx_diffusivity_mobility(const MixParams &m, const double *X_sp, const double *Y_sp, double nTotal, const GmxColl &ci,

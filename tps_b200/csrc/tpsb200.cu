@@ -681,8 +681,9 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
         return fail(ctx, TPSB_EINVAL, "argon_mixture transport needs the indices of 'Ar.+1' and 'Ar'");
       for (int i = 0; i < pm->num_species; i++)
         for (int j = i; j < pm->num_species; j++)
-          if (pm->collision_index[i + j * pm->num_species] < 0 || pm->collision_index[i + j * pm->num_species] > 4)
-            return fail(ctx, TPSB_ENOTIMPL, "collision type %d of species pair (%d, %d) not built (argon and Coulomb pairs only)",
+          if (pm->collision_index[i + j * pm->num_species] < 0 || pm->collision_index[i + j * pm->num_species] > 14 ||
+              pm->collision_index[i + j * pm->num_species] == 5)
+            return fail(ctx, TPSB_EINVAL, "collision type %d of species pair (%d, %d) is not a GasColl value (src/dataStructures.hpp:122-144)",
                         pm->collision_index[i + j * pm->num_species], i, j);
     }
     if (pm->transport_model == 0 && (pm->num_species != 3 || !(pm->charge[0] > 0) || !(pm->charge[1] < 0) || pm->charge[2] != 0))
