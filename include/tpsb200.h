@@ -147,6 +147,13 @@ typedef struct {
    * with n normalised as Fluxes' constructor does (src/fluxes.cpp:73-83).                                          */
   int sponge_enabled;
   double sponge_normal[3], sponge_point[3], sponge_ratio, sponge_width;
+  /* flow/useMixingLength: MixingLengthTransport wrapped around the molecular transport (src/M2ulPhyS.cpp:265-283,
+   * src/mixing_length_transport.cpp:62-121): mu_t = rho l^2 |S|, l = min(0.41 d_wall, max_mixing_length);
+   * mixing-length/Pr_ratio scales the eddy conductivity, mixing-length/bulk-multiplier the eddy bulk viscosity.  The wall
+   * distance d_wall is the nodal field handed over with tpsb_set_distance_field (zero until then).  Runs on the
+   * generic path (any fluid, 2-D / axisymmetric / 3-D).                                                            */
+  int use_mixing_length;
+  double max_mixing_length, mixing_length_Prt, mixing_length_bulk_mult;
 } tpsb_physics;
 
 /* Boundary conditions: BCintegrator's attribute -> {InletBC, OutletBC, WallBC} maps (src/BCintegrator.cpp:64-125).
@@ -225,6 +232,11 @@ int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp);
  * Up / gradUp are computed from x -- the reference's behaviour, kept (parity trap 1).
  * NULL (default): use x itself.  tpsb_ode_step sets it to d_U for the duration of the step.        */
 int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U);
+/* The wall-distance grid function (M2ulPhyS::distance_, src/M2ulPhyS.cpp:265-283, computed by the host's distance
+ * solver or read from a file): d_distance[N] in DEVICE memory, nodal, valid until replaced.  RHSoperator::GetFlux reads
+ * it at the nodes (src/rhs_operator.cpp:534-537), FaceIntegrator / BCintegrator interpolate it to the face points with
+ * each side's own shape functions (src/face_integrator.cpp:304-309, src/BCintegrator.cpp:408-411).  NULL: zero.     */
+int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance);
 
 /* Chemistry::setGridFunctionRates (src/chemistry.cpp:133-140): the externally computed rate coefficients of the
  * GRIDFUNCTION_RXN reactions, d_rates[component][N] in DEVICE memory (byNODES), valid until replaced; NULL: those

@@ -214,6 +214,7 @@ struct Oracle {
   std::vector<double> Me_inv, Me_inv_rad, Ke, Kfl;  // per element dense
   bool axisym = false;
   std::vector<double> elSize;           // per element delta = h_min / order
+  std::vector<double> distance;         // nodal wall distance (M2ulPhyS::distance_, src/M2ulPhyS.cpp:265-283); empty: 0
   std::vector<double> nodeXYZ;          // [NE][dof][dim]
   std::map<int, std::vector<double>> shapeTab;  // inf code -> [nqf][dof]
   // work
@@ -398,7 +399,7 @@ struct Oracle {
   }
   // BCintegrator::computeBdrFlux (src/BCintegrator.cpp:228-242) dispatching to the per-type routines
   void bc_flux(const OrcBc &b, const double *normal, const double *stateIn, const double *gradState, double *xyz,
-               double delta, double *bdrFlux) const {
+               double delta, double *bdrFlux, double dist = 0.0) const {
     double state2[16], wallState[16], viscF[48], wallViscF[16], unitN[3], primFlux[16];
     bool idx[16];
     for (int i = 0; i < 16; i++) {
@@ -442,12 +443,12 @@ struct Oracle {
       if ((nvel == 3) && (dim == 2)) state2[3] = stateIn[0] * vel[2];
       ph->riemann(stateIn, state2, normal, bdrFlux);
       double viscFw[48];
-      ph->visc_flux(state2, gradState, xyz, delta, 0.0, viscFw);
+      ph->visc_flux(state2, gradState, xyz, delta, dist, viscFw);
       for (int eq = 0; eq < neq; eq++) {
         wallViscF[eq] = 0.;
         for (int d = 0; d < dim; d++) wallViscF[eq] += viscFw[eq + d * neq] * normal[d];
       }
-      ph->visc_flux(stateIn, gradState, xyz, delta, 0.0, viscF);
+      ph->visc_flux(stateIn, gradState, xyz, delta, dist, viscF);
       for (int eq = 1; eq < neq; eq++) {
         bdrFlux[eq] -= 0.5 * wallViscF[eq];
         for (int d = 0; d < dim; d++) bdrFlux[eq] -= 0.5 * viscF[eq + d * neq] * normal[d];
@@ -783,8 +784,13 @@ struct Oracle {
           }
         face_geom(f, q, nor, xyz);
         ph->riemann(u1, u2, nor, fluxN);
-        ph->visc_flux(u1, g1, xyz, delta1, 0.0, vF1);
-        ph->visc_flux(u2, g2, xyz, delta2, 0.0, vF2);
+        double d1 = 0.0, d2 = 0.0;  // wall distance, each side's own interpolation (src/face_integrator.cpp:304-309)
+        if (!distance.empty()) {
+          for (int k = 0; k < dof; k++) d1 += distance[static_cast<size_t>(e1) * dof + k] * s1[k];
+          for (int k = 0; k < dof; k++) d2 += distance[static_cast<size_t>(e2) * dof + k] * s2[k];
+        }
+        ph->visc_flux(u1, g1, xyz, delta1, d1, vF1);
+        ph->visc_flux(u2, g2, xyz, delta2, d2, vF2);
         // viscF1 += viscF2; viscF1 *= -0.5; viscF1.AddMult(nor, fluxN); fluxN *= ip.weight
         for (int i = 0; i < neq * dim; i++) {
           vF1[i] += vF2[i];
@@ -834,7 +840,10 @@ struct Oracle {
           }
           face_geom(f, q, nor, xyz);
           for (int eq = 0; eq < neq; eq++) fluxN[eq] = 0.;
-          bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN);
+          double d1 = 0.0;  // src/BCintegrator.cpp:416-424
+          if (!distance.empty())
+            for (int k = 0; k < dof; k++) d1 += distance[static_cast<size_t>(e1) * dof + k] * s1[k];
+          bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN, d1);
           const double w = face_weight(q);
           for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
           if (axisym)  // src/BCintegrator.cpp:427-429
@@ -873,7 +882,7 @@ struct Oracle {
         for (int d = 0; d < dim; d++) xyz[d] = nodeXYZ[i * dim + d];
         ph->conv_flux(st, fc);
         if (phys.eq_system != 0) {
-          ph->visc_flux(st, g, xyz, elSize[e], 0.0, fv);
+          ph->visc_flux(st, g, xyz, elSize[e], distance.empty() ? 0.0 : distance[i], fv);  // rhs_operator.cpp:519-533
           for (int c = 0; c < neq * dim; c++) fc[c] -= fv[c];
         }
         for (int d = 0; d < dim; d++)
@@ -1096,6 +1105,12 @@ void orc_face_geometry(void *h, int f, double *nor /*[nqf][dim]*/, double *xyz /
     o->face_geom(f, q, &nor[q * o->dim], &xyz[q * o->dim]);
     w[q] = o->face_weight(q);
   }
+}
+// wall-distance grid function the mixing-length model reads (nullptr: none)
+void orc_set_distance(void *h, const double *dist /*[N]*/) {
+  Oracle *o = static_cast<Oracle *>(h);
+  if (dist) o->distance.assign(dist, dist + o->N);
+  else o->distance.clear();
 }
 void orc_elem_size(void *h, double *delta /*[NE]*/) {
   Oracle *o = static_cast<Oracle *>(h);

@@ -31,6 +31,10 @@ struct OrcPhysParams {
   double sgs_const, sgs_floor;
   int sponge_enabled;       // viscosityMultiplierFunction/isEnabled
   double sponge_normal[3], sponge_point[3], sponge_ratio, sponge_width;
+  // flow/useMixingLength: MixingLengthTransport wrapped around the molecular transport (src/M2ulPhyS.cpp:265-283,
+  // mixingLengthTransportData src/dataStructures.hpp:548-554; reference back end only)
+  int use_mixing_length;
+  double max_mixing_length, mixing_length_Prt, mixing_length_bulk_mult;
 };
 // Plasma models of a user-defined fluid: PerfectMixtureInput + constantTransportData + ChemistryInput
 // (src/dataStructures.hpp:537-546,623-633,690-712) flattened; same layout as tpsb_plasma_models.

@@ -312,8 +312,8 @@ class DryAirPort : public Physics {
 };
 
 Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq) {
-  if (p.sgs_model != 0 || p.sponge_enabled != 0) {
-    fprintf(stderr, "oracle (port back end): SGS models / viscous sponge are served by the reference back end only\n");
+  if (p.sgs_model != 0 || p.sponge_enabled != 0 || p.use_mixing_length != 0) {
+    fprintf(stderr, "oracle (port back end): SGS models / viscous sponge / mixing length are served by the reference back end only\n");
     abort();
   }
   if (p.fluid != 0) return nullptr;

@@ -12,10 +12,23 @@
 #include "fluxes.hpp"
 #include "gas_transport.hpp"
 #include "radiation.hpp"
+#include "mixing_length_transport.hpp"
 #include "riemann_solver.hpp"
 #include "transport_properties.hpp"
 
 #include "orc_physics.hpp"
+
+// flow/useMixingLength (src/M2ulPhyS.cpp:265-283): the flux class sees the molecular transport through MixingLengthTransport
+static TransportProperties *wrap_mixing_length(const OrcPhysParams &p, GasMixture *mix, MolecularTransport *molecular) {
+  if (!p.use_mixing_length) return molecular;
+  mixingLengthTransportData d;
+  d.max_mixing_length_ = p.max_mixing_length;
+  d.Prt_ = p.mixing_length_Prt;
+  d.Let_ = 1.0;
+  d.bulk_multiplier_ = p.mixing_length_bulk_mult;
+  return new MixingLengthTransport(mix, d, molecular);
+}
+
 
 namespace orc {
 
@@ -51,10 +64,10 @@ class DryAirRef : public Physics {
       }
       vsd.ratio = p.sponge_ratio;
       vsd.width = p.sponge_width;
-      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym, p.sgs_model, p.sgs_floor,
-                         p.sgs_const, vsd);
+      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), wrap_mixing_length(p, mix_, trans_), neq, dim, axisym,
+                         p.sgs_model, p.sgs_floor, p.sgs_const, vsd);
     } else {
-      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), trans_, neq, dim, axisym);   // fluxes.cpp:34
+      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), wrap_mixing_length(p, mix_, trans_), neq, dim, axisym);   // fluxes.cpp:34
     }
     rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, p.use_roe != 0, axisym);  // riemann_solver.cpp:38
     use_roe_ = p.use_roe != 0;
@@ -189,7 +202,7 @@ class MixtureRef : public Physics {
     }
     const Equations eqs = static_cast<Equations>(p.eq_system);
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
-    flux_ = new Fluxes(mix_, eqs, trans_, neq, dim, axisym);
+    flux_ = new Fluxes(mix_, eqs, wrap_mixing_length(p, mix_, static_cast<MolecularTransport *>(trans_)), neq, dim, axisym);
     rs_ = new RiemannSolverTPS(neq, mix_, eqs, flux_, false, axisym);
     if (pm.num_reactions > 0) {
       ChemistryInput ci;

@@ -77,8 +77,9 @@ def argon6_primitives(xy, nvel=3, seed=20261018):
     return up * (1 + 0.01 * rng.uniform(-1, 1, up.shape))
 
 
-def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None, gpu=True, kind=None):
-    """(RhsOperator or None, Oracle) on mesh m with boundary-condition set bc_kind."""
+def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None, gpu=True, kind=None, mixing_length=None):
+    """(RhsOperator or None, Oracle) on mesh m with boundary-condition set bc_kind.
+    mixing_length = (max-mixing-length, Pr_ratio, bulk-multiplier): flow/useMixingLength (reference back end)."""
     nsp_in = ()
     if mixture is not None:
         nsp_in = (0.02 * (MW_AR - MW_E), 0.05 * MW_AR, 0.03 * MW_AR, 0.04 * MW_AR, 0.02 * MW_E)
@@ -92,6 +93,11 @@ def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None,
         phys_o, phys_g = oracle_api.dry_air_params(eq, 3e4, 0.2), tps_b200.Physics.dry_air(eq, 3e4, 0.2)
         neq = nvel + 2
         kind = kind or "port"
+    if mixing_length is not None:
+        kind = "ref"
+        phys_g.with_mixing_length(*mixing_length)
+        phys_o.use_mixing_length = 1
+        phys_o.max_mixing_length, phys_o.mixing_length_Prt, phys_o.mixing_length_bulk_mult = mixing_length
     orc = oracle_api.Oracle(order, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
                             phys=phys_o, kind=kind, basis_type=bt, int_rule=ir, neq=neq, nvel=nvel)
     if specs:

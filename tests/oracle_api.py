@@ -16,7 +16,8 @@ class OrcPhysParams(C.Structure):
                 ("S0", C.c_double), ("Pr", C.c_double), ("plasma", C.c_void_p), ("use_roe", C.c_int),
                 ("sgs_model", C.c_int), ("sgs_const", C.c_double), ("sgs_floor", C.c_double), ("sponge_enabled", C.c_int),
                 ("sponge_normal", C.c_double * 3), ("sponge_point", C.c_double * 3), ("sponge_ratio", C.c_double),
-                ("sponge_width", C.c_double)]
+                ("sponge_width", C.c_double), ("use_mixing_length", C.c_int), ("max_mixing_length", C.c_double),
+                ("mixing_length_Prt", C.c_double), ("mixing_length_bulk_mult", C.c_double)]
 
 
 class OrcBc(C.Structure):
@@ -101,6 +102,7 @@ def load(kind="port"):
     lib.orc_face_nq.argtypes = [C.c_void_p]
     lib.orc_face_geometry.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
     lib.orc_elem_size.argtypes = [C.c_void_p, _dp]
+    lib.orc_set_distance.argtypes = [C.c_void_p, _dp]
     lib.orc_dense_ops.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.orc_gl_rule.argtypes = [C.c_int, _dp, _dp]
     lib.orc_phys_init.argtypes = [C.POINTER(OrcPhysParams)]
@@ -137,6 +139,11 @@ class Oracle:
         if getattr(self, "h", None):
             self.lib.orc_destroy(self.h)
             self.h = None
+
+    def set_distance(self, dist):
+        """Nodal wall distance read by the mixing-length model (kind='ref')."""
+        self._dist = np.ascontiguousarray(dist, np.float64)
+        self.lib.orc_set_distance(self.h, self._dist)
 
     def set_bcs(self, face_attr, bcs, use_bc_in_grad=False):
         """bcs: list of OrcBc (make_bc); face_attr: boundary attribute per face (0 on interior faces)."""

@@ -136,7 +136,14 @@ class Physics(C.Structure):
                 ("plasma", C.POINTER(PlasmaModels)), ("use_roe", C.c_int),
                 ("sgs_model", C.c_int), ("sgs_const", C.c_double), ("sgs_floor", C.c_double), ("sponge_enabled", C.c_int),
                 ("sponge_normal", C.c_double * 3), ("sponge_point", C.c_double * 3), ("sponge_ratio", C.c_double),
-                ("sponge_width", C.c_double)]
+                ("sponge_width", C.c_double), ("use_mixing_length", C.c_int), ("max_mixing_length", C.c_double),
+                ("mixing_length_Prt", C.c_double), ("mixing_length_bulk_mult", C.c_double)]
+
+    def with_mixing_length(self, max_mixing_length, pr_ratio=1.0, bulk_multiplier=0.0):
+        """flow/useMixingLength = True with mixing-length/{max-mixing-length, Pr_ratio, bulk-multiplier}."""
+        self.use_mixing_length, self.max_mixing_length = 1, float(max_mixing_length)
+        self.mixing_length_Prt, self.mixing_length_bulk_mult = float(pr_ratio), float(bulk_multiplier)
+        return self
 
     @classmethod
     def dry_air(cls, eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False, sgs=None, sponge=None):
@@ -189,7 +196,7 @@ class PartSizes(C.Structure):
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -227,6 +234,7 @@ def lib():
     L.tpsb_get_fields.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_set_solution_view.argtypes = [vp, vp]
+    L.tpsb_set_distance_field.argtypes = [vp, vp]
     L.tpsb_set_reaction_rate_field.argtypes = [vp, vp, C.c_int]
     L.tpsb_get_mean_time_derivatives.argtypes = [vp, vp, dp]
     L.tpsb_ode_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
@@ -508,6 +516,11 @@ class RhsOperator:
         """The solution grid function U_ the forcing terms read (None: the vector passed to Mult)."""
         self._sol = U
         self._chk(self.L.tpsb_set_solution_view(self.ctx, U.data_ptr() if U is not None else None), "tpsb_set_solution_view")
+
+    def set_distance_field(self, dist):
+        """Nodal wall distance (device tensor of N doubles, kept alive here) for the mixing-length model; None: zero."""
+        self._dist = dist
+        self._chk(self.L.tpsb_set_distance_field(self.ctx, dist.data_ptr() if dist is not None else None), "tpsb_set_distance_field")
 
     def set_reaction_rate_field(self, rates):
         """Chemistry::setGridFunctionRates: device tensor [components][N] (or None)."""

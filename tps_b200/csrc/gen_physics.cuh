@@ -20,6 +20,9 @@ struct GenPhys {
   int fluid;             // 0 dry air; 1 user-defined plasma mixture (mix != NULL)
   PhysParams dry;        // gamma, R, Sutherland, multipliers, eq_system
   const MixParams *mix;  // device (or host, for host-side checks) pointer
+  // flow/useMixingLength for dry air (mixtures carry it in MixParams): MixingLengthTransport (mixing_length_transport.cpp)
+  int ml_on;
+  double ml_max, ml_prt, ml_bulk;
 };
 
 // DryAir::ComputePressure (equation_of_state.hpp:610-617)
@@ -71,15 +74,16 @@ __host__ __device__ __forceinline__ void dry_gen_conv_flux(const GenPhys &g, con
 // run-time-indexed form once inlined into gen_resid_kernel (caught by the parity test; the stand-alone
 // function was correct, tools/ubench/gen_visc_check.cu).
 __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
-                                                           double *f) {
+                                                           double *f, double distance = 0.0) {
   const int neq = g.neq, dim = g.dim;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (g.dry.eq_system == 0) return;
   const double pr = dry_gen_pressure(g, s);
   const double temp = pr / g.dry.R / s[0];
-  const double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
+  double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
   double bulk = g.dry.bulk_visc_mult * visc;
-  const double k = g.dry.cp_div_pr * visc;
+  double k = g.dry.cp_div_pr * visc;
+  if (g.ml_on) mixlen_add(dim, g.nvel, neq, g.ml_max, g.ml_prt, g.ml_bulk, s, gr, radius, distance, visc, bulk, k);
   bulk -= 2. / 3. * visc;
   double gu[3][3], st[3][3], vel[3], gT[3];  // gu[i][d] = d u_i / d x_d
 #pragma unroll
@@ -194,9 +198,10 @@ __host__ __device__ __forceinline__ double gen_max_char_speed(const GenPhys &g, 
 __host__ __device__ __forceinline__ void gen_conv_flux(const GenPhys &g, const double *s, double *f) {
   if (g.fluid) mix_conv_flux(*g.mix, s, f); else dry_gen_conv_flux(g, s, f);
 }
+// distance: wall distance at the point (mixing-length model only; the viscous walls pass 0 as the reference does)
 __host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
-                                                       double *f) {
-  if (g.fluid) mix_visc_flux(*g.mix, s, gr, radius, f); else dry_gen_visc_flux(g, s, gr, radius, f);
+                                                       double *f, double distance = 0.0) {
+  if (g.fluid) mix_visc_flux(*g.mix, s, gr, radius, f, distance); else dry_gen_visc_flux(g, s, gr, radius, f, distance);
 }
 __host__ __device__ __forceinline__ void gen_bdr_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
                                                            const double *nrm, bool heat_prescribed, double *nf) {

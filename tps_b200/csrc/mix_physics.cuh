@@ -58,6 +58,9 @@ struct MixParams {
   const double *rateField;
   long long rateN;
   int rxComp[MIX_MAXRX];
+  // flow/useMixingLength: MixingLengthTransport around the molecular transport (mixing_length_transport.cpp:44-57)
+  int mlOn;
+  double mlMax, mlPrt, mlBulk;
 };
 
 
@@ -67,6 +70,41 @@ struct MixParams {
 // contexts (NaN species sources inside gen_source_kernel while the same call in gen_point_eval_kernel was exact).
 #define MIXFN __host__ __device__ __forceinline__
 #define MIXBIG __host__ __device__ __noinline__
+
+// MixingLengthTransport::ComputeFluxTransportProperties (mixing_length_transport.cpp:62-121): eddy viscosity
+// rho l^2 |S| with l = min(0.41 d_wall, l_max), |S| = sqrt(2 S_ij S_ij) including the axisymmetric swirl terms, added to
+// the molecular viscosity; bulk += bulk_mult mu_t; kappa += mu_t (kappa / mu) Pr_ratio.  bulk is the raw buffer entry
+// (before Fluxes subtracts 2/3 mu).  gr[eq + d*neq]; velocities are momentum / rho in every gas model.
+MIXFN void mixlen_add(int dim, int nvel, int neq, double max_len, double prt, double bulk_mult, const double *s, const double *gr,
+                      double radius, double distance, double &visc, double &bulk, double &kappa) {
+  const double cp_over_Pr = kappa / visc;
+  const double rho = s[0];
+  double ur = 0;
+  if (nvel != dim) ur = s[1] / s[0];
+  double S = 0;
+  for (int i = 0; i < dim; i++)
+    for (int j = 0; j < dim; j++) {
+      const double Sij = 0.5 * (gr[(1 + i) + j * neq] + gr[(1 + j) + i * neq]);
+      S += 2 * Sij * Sij;
+    }
+  if (nvel != dim) {
+    const double ut = s[3] / s[0];
+    const double ut_r = gr[3 + 0 * neq], ut_z = gr[3 + 1 * neq];
+    double Szx = 0.5 * ut_r;
+    if (radius > 0) Szx -= 0.5 * ut / radius;
+    const double Szy = 0.5 * ut_z;
+    double Szz = 0.0;
+    if (radius > 0) Szz += ur / radius;
+    S += 2 * (2 * Szx * Szx + 2 * Szy * Szy + Szz * Szz);
+  }
+  S = sqrt(S);
+  double mixing_length = 0.41 * distance;
+  if (mixing_length > max_len) mixing_length = max_len;
+  const double mut = rho * mixing_length * mixing_length * S;
+  visc += mut;
+  bulk += bulk_mult * mut;
+  kappa += mut * cp_over_Pr * prt;
+}
 
 // PerfectMixture::computeAmbipolarElectronNumberDensity (equation_of_state.cpp:607-618)
 MIXFN double mix_ambipolar_ne(const MixParams &m, const double *n_sp) {
@@ -777,13 +815,14 @@ MIXBIG void mix_conv_flux(const MixParams &m, const double *s, double *f) {
 }
 
 // Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335), no SGS / sponge; radius = x[0] (axisymmetric terms only)
-MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, double *f) {
+MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, double *f, double distance = 0.0) {
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (m.eq_system == 0) return;
   double hsp[MIX_MAXSP], V[MIX_MAXSP * MIX_MAXDIM], tb[4];
   mix_species_enthalpies(m, s, hsp);
   mix_flux_transport(m, s, gr, tb, V);
+  if (m.mlOn) mixlen_add(dim, nvel, neq, m.mlMax, m.mlPrt, m.mlBulk, s, gr, radius, distance, tb[0], tb[1], tb[2]);
   const double visc = tb[0];
   double bulk = tb[1];
   bulk -= 2. / 3. * visc;

@@ -59,6 +59,7 @@ struct GenArgs {
   const double *U;
   double *Up, *gradUp, *y;
   unsigned long long *maxCharBits;
+  const double *dist;  // nodal wall distance (tpsb_set_distance_field; mixing-length model), NULL: 0
 };
 
 __device__ __forceinline__ int gen_code(int dim, int inf) { return (inf / 64) * (dim == 3 ? 8 : 2) + inf % 64; }
@@ -128,7 +129,7 @@ __device__ __forceinline__ void gen_bc_prim_for_gradient(const GenPhys &g, const
 // computeAdiabaticWallFlux / computeIsothermalWallFlux (wallBC.cpp:277-320, 430-510), any fluid, 2-D / 3-D /
 // axisymmetric.  gr[eq + d*neq]: interior gradients of the primitives; nor: CalcOrtho normal (area weighted, outward).
 __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int use_bc_in_grad, const double *u1, const double *gr,
-                                         const double *nor, double radius, double *fx) {
+                                         const double *nor, double radius, double *fx, double distance = 0.0) {
   const int neq = g.neq, dim = g.dim, nvel = g.nvel;
   double s2[GEN_MAXEQ], viscF[GEN_MAXEQ * GEN_MAXDIM], wallViscF[GEN_MAXEQ], un[3];
   double normN = 0.;
@@ -210,12 +211,12 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
     if (nvel == 3 && dim == 2) s2[3] = u1[0] * vel[2];
     gen_riemann(g, u1, s2, nor, fx);  // the inviscid wall does not force Lax-Friedrichs (wallBC.cpp:301)
     if (!ns) return;
-    gen_visc_flux(g, s2, gr, radius, viscF);
+    gen_visc_flux(g, s2, gr, radius, viscF, distance);  // only the inviscid wall passes the wall distance on (wallBC.cpp:309-313)
     for (int eq = 0; eq < neq; eq++) {
       wallViscF[eq] = 0.;
       for (int d = 0; d < dim; d++) wallViscF[eq] += viscF[eq + d * neq] * nor[d];
     }
-    gen_visc_flux(g, u1, gr, radius, viscF);
+    gen_visc_flux(g, u1, gr, radius, viscF, distance);
   } else {
     const double isq = 1. / sqrt(normN);
     for (int d = 0; d < dim; d++) un[d] = nor[d] * isq;
@@ -405,7 +406,8 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     gen_conv_flux(a.phys, s, fc);
     if (a.eq_system != 0) {
       const double radius = a.phys.axisym ? gen_quad_x(vx, a.xiN + k * dim) : -1.0;  // nodal coordinate (GetFlux :526-528)
-      gen_visc_flux(a.phys, s, gr, radius, fv);
+      const double dw = a.dist ? a.dist[static_cast<long long>(e) * dof + k] : 0.0;  // rhs_operator.cpp:534-537
+      gen_visc_flux(a.phys, s, gr, radius, fv, dw);
       for (int c = 0; c < nc; c++) fc[c] -= fv[c];
     }
     for (int c = 0; c < nc; c++) sF[k * nc + c] = fc[c];
@@ -478,7 +480,10 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         }
         double fxb[GEN_MAXEQ];
         for (int eq = 0; eq < neq; eq++) fxb[eq] = 0.0;
-        gen_bc_flux(a.phys, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb);
+        double dwb = 0.0;  // BCintegrator.cpp:408-411
+        if (a.dist)
+          for (int k = 0; k < dof; k++) dwb += po[k] * a.dist[static_cast<long long>(e1) * dof + k];
+        gen_bc_flux(a.phys, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb);
         const double sgb = -(a.phys.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
         for (int eq = 0; eq < neq; eq++) sQ[q * nc + eq] = sgb * fxb[eq];
         continue;
@@ -512,8 +517,14 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       gen_riemann(a.phys, u1, u2, nor, fx);
       if (a.eq_system != 0) {
         double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM];
-        gen_visc_flux(a.phys, u1, g1, radius, f1);
-        gen_visc_flux(a.phys, u2, g2, radius, f2);
+        double dwo = 0.0, dwn = 0.0;  // each side's own interpolation of the wall distance (face_integrator.cpp:304-309)
+        if (a.dist)
+          for (int k = 0; k < dof; k++) {
+            dwo += po[k] * a.dist[static_cast<long long>(e) * dof + k];
+            dwn += pn[k] * a.dist[static_cast<long long>(eo) * dof + k];
+          }
+        gen_visc_flux(a.phys, u1, g1, radius, f1, first ? dwo : dwn);
+        gen_visc_flux(a.phys, u2, g2, radius, f2, first ? dwn : dwo);
         for (int eq = 0; eq < neq; eq++) {
           double v = 0;
           for (int d = 0; d < dim; d++) v += (-0.5 * (f1[eq + d * neq] + f2[eq + d * neq])) * nor[d];

@@ -456,6 +456,8 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   g.bct = gbt;
   g.eq_system = phys->eq_system;
   g.phys.fluid = 0, g.phys.mix = nullptr;
+  g.phys.ml_on = phys->use_mixing_length ? 1 : 0;
+  g.phys.ml_max = phys->max_mixing_length, g.phys.ml_prt = phys->mixing_length_Prt, g.phys.ml_bulk = phys->mixing_length_bulk_mult;
   std::vector<MixParams> mixv;
   if (phys->fluid == TPSB_USER_DEFINED) {
     const tpsb_plasma_models &pm = *phys->plasma;
@@ -532,6 +534,8 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
       if (te != cudaSuccess) return std::string("device setup failed: ") + cudaGetErrorString(te);
     }
     m.rateField = nullptr, m.rateN = static_cast<long long>(NE) * dof;
+    m.mlOn = phys->use_mixing_length ? 1 : 0;
+    m.mlMax = phys->max_mixing_length, m.mlPrt = phys->mixing_length_Prt, m.mlBulk = phys->mixing_length_bulk_mult;
     mixv.push_back(m);
     c->mix_host = m;
     g.phys.fluid = 1;
@@ -711,6 +715,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (want_generic) {
     if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
   }
+  if (phys->use_mixing_length) want_generic = true;  // the mixing-length model lives on the generic path
   const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
   if (phys->sgs_model < 0 || phys->sgs_model > 2) return fail(ctx, TPSB_EINVAL, "sgs_model %d: 0 none, 1 smagorinsky, 2 sigma", phys->sgs_model);
   if (visc_mod && want_generic)
@@ -1721,6 +1726,13 @@ int tpsb_debug_point_eval(tpsb_ctx *ctx, int which, int n, const double *d_U, co
 int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U) {
   if (!ctx) return TPSB_EINVAL;
   ctx->sol_view = d_U;
+  return TPSB_OK;
+}
+
+int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance) {
+  if (!ctx) return TPSB_EINVAL;
+  if (!ctx->generic) return fail(ctx, TPSB_EINVAL, "the wall distance is read by the mixing-length model (generic path) only");
+  ctx->gen.dist = d_distance;
   return TPSB_OK;
 }
 
