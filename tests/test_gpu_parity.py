@@ -200,3 +200,35 @@ def test_full_size_properties(lib_built):
         total = float((yk * w[None, :]).sum())
         scale = float((yk.abs() * w[None, :]).sum())
         assert abs(total) < 1e-9 * scale, (k, total, scale)
+
+
+@pytest.mark.parametrize("scheme", [1, 2, 3, 4])
+def test_graph_replayed_ode_steps_equal_eager_steps(lib_built, monkeypatch, scheme):
+    """tpsb_ode_step replays one captured Runge-Kutta step as a CUDA graph from the second step on; the replay must
+    reproduce eager stepping bit for bit, also when dt / the solution vector change between calls (re-capture) and on
+    a side stream."""
+    import torch
+    m = tps_b200.cartesian_hex_mesh(4, 3, 3, lo=(-PI,) * 3, hi=(PI,) * 3)
+    U = tgv_state(node_coords_from_mesh(m["elem_xyz"], 3))
+
+    def run(graph, stream=None):
+        monkeypatch.setenv("TPSB_ODE_GRAPH", "1" if graph else "0")
+        op = tps_b200.RhsOperator(m, order=3, physics=tps_b200.Physics.dry_air(1, 2e3, 0.1), stream=stream)
+        x = torch.from_numpy(U.copy()).cuda()
+        n0 = op.launch_count()
+        op.ode_step(x, 2e-6, scheme=scheme, nsteps=7)
+        n1 = op.launch_count()
+        op.ode_step(x, 1e-6, scheme=scheme, nsteps=5)   # new dt: the graph is re-captured
+        x2 = x.clone()
+        op.ode_step(x2, 1e-6, scheme=scheme, nsteps=4)  # new solution vector
+        torch.cuda.synchronize()
+        return x.cpu().numpy(), x2.cpu().numpy(), n1 - n0
+
+    e1, e2, ne = run(False)
+    g1, g2, ng = run(True)
+    assert np.array_equal(e1, g1) and np.array_equal(e2, g2)
+    assert ne == ng  # the launch counter counts replayed kernels too
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        s1, s2, _ = run(True, stream=s.cuda_stream)
+    assert np.array_equal(e1, s1) and np.array_equal(e2, s2)

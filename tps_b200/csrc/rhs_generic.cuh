@@ -278,10 +278,10 @@ __device__ __forceinline__ void gen_apply_minv(const GenArgs &a, const double *m
 __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
   extern __shared__ double sm[];
   const int e = blockIdx.x, dim = a.dim, dof = a.dof, neq = a.neq, nc = neq * dim;
-  const int nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  const int nqmax = a.nqv > a.nfe * a.nqf ? a.nqv : a.nfe * a.nqf;
   double *sUp = sm;                    // [neq][dof]
   double *sRhs = sUp + neq * dof;      // [dof][nc]
-  double *sQ = sRhs + dof * nc;        // [nqmax][nc]
+  double *sQ = sRhs + dof * nc;        // [max(nqv, nfe * nqf)][nc]
   double *sW = sQ + nqmax * nc;        // [nqv]  w |J|
   const long long N = a.N;
   const double *vx = a.vx + static_cast<long long>(e) * a.nv * dim;
@@ -317,8 +317,12 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
     sRhs[j * nc + c] = v;
   }
   __syncthreads();
-  // faces: phi_j(q) * 1/2 (Up_other - Up_own)(q) * n_out(q) w_q
-  for (int lf = 0; lf < a.nfe; lf++) {
+  // faces: phi_j(q) * 1/2 (Up_other - Up_own)(q) * n_out(q) w_q.  One task per (local face, face point): all faces of
+  // the element are in flight at once (a p = 2 quadrilateral has 4 points per face -- looping over the faces left 4
+  // threads busy), then one lift pass that adds the faces in local-face order, as the face-by-face loop did.
+  double *sQF = sQ;  // [nfe * nqf][nc]  (the volume values in sQ are consumed)
+  for (int it = threadIdx.x; it < a.nfe * a.nqf; it += blockDim.x) {
+    const int lf = it / a.nqf, q = it - lf * a.nqf;
     const int f = a.el_face[e * a.nfe + lf];
     const int e1 = a.f_el1[f], e2 = a.f_el2[f];
     const bool bdr = e2 < 0;
@@ -331,48 +335,55 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
     const int code1 = gen_code(dim, a.f_inf1[f]);
     const int eo = bdr ? e1 : (first ? e2 : e1);
     const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
-    for (int q = threadIdx.x; q < a.nqf; q += blockDim.x) {
-      double J[9], nor[3];
-      gen_jacobian(dim, v1, a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim, J);
-      gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
-      const double sg = (first ? 1.0 : -1.0) * a.wF[q];
-      const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
-      const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
-      if (bdr) {
-        double own[GEN_MAXEQ], pbc[GEN_MAXEQ];
-        for (int eq = 0; eq < neq; eq++) {
-          double v = 0;
-          for (int k = 0; k < dof; k++) v += po[k] * sUp[eq * dof + k];
-          own[eq] = v;
-        }
-        gen_bc_prim_for_gradient(a.phys, a.bct.bc[a.f_bc[f]], own, pbc);
-        for (int eq = 0; eq < neq; eq++) {
-          const double jump = 0.5 * (pbc[eq] - own[eq]);
-          for (int d = 0; d < dim; d++) sQ[q * nc + eq + d * neq] = jump * nor[d] * sg;
-        }
-        continue;
-      }
+    double J[9], nor[3];
+    gen_jacobian(dim, v1, a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim, J);
+    gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
+    const double sg = (first ? 1.0 : -1.0) * a.wF[q];
+    const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
+    const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
+    double *dst = sQF + static_cast<long long>(it) * nc;
+    if (bdr) {
+      double own[GEN_MAXEQ], pbc[GEN_MAXEQ];
       for (int eq = 0; eq < neq; eq++) {
-        double own = 0, oth = 0;
-        const double *un = a.Up + static_cast<long long>(eo) * dof + eq * N;
-        for (int k = 0; k < dof; k++) {
-          own += po[k] * sUp[eq * dof + k];
-          oth += pn[k] * un[k];
-        }
-        const double jump = 0.5 * (oth - own);
-        for (int d = 0; d < dim; d++) sQ[q * nc + eq + d * neq] = jump * nor[d] * sg;
+        double v = 0;
+        for (int k = 0; k < dof; k++) v += po[k] * sUp[eq * dof + k];
+        own[eq] = v;
       }
+      gen_bc_prim_for_gradient(a.phys, a.bct.bc[a.f_bc[f]], own, pbc);
+      for (int eq = 0; eq < neq; eq++) {
+        const double jump = 0.5 * (pbc[eq] - own[eq]);
+        for (int d = 0; d < dim; d++) dst[eq + d * neq] = jump * nor[d] * sg;
+      }
+      continue;
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < dof * nc; t += blockDim.x) {
-      const int j = t / nc, c = t % nc;
-      const double *po = a.phiF + static_cast<long long>(code_own) * a.nqf * dof;
-      double v = 0;
-      for (int q = 0; q < a.nqf; q++) v += po[q * dof + j] * sQ[q * nc + c];
-      sRhs[j * nc + c] += v;
+    for (int eq = 0; eq < neq; eq++) {
+      double own = 0, oth = 0;
+      const double *un = a.Up + static_cast<long long>(eo) * dof + eq * N;
+      for (int k = 0; k < dof; k++) {
+        own += po[k] * sUp[eq * dof + k];
+        oth += pn[k] * un[k];
+      }
+      const double jump = 0.5 * (oth - own);
+      for (int d = 0; d < dim; d++) dst[eq + d * neq] = jump * nor[d] * sg;
     }
-    __syncthreads();
   }
+  __syncthreads();
+  for (int t = threadIdx.x; t < dof * nc; t += blockDim.x) {
+    const int j = t / nc, c = t % nc;
+    double acc = sRhs[j * nc + c];
+    for (int lf = 0; lf < a.nfe; lf++) {
+      const int f = a.el_face[e * a.nfe + lf];
+      if (a.f_el2[f] < 0 && !(a.bct.use_bc_in_grad && a.f_bc[f] >= 0)) continue;
+      const int code_own = gen_code(dim, a.f_el1[f] == e ? a.f_inf1[f] : a.f_inf2[f]);
+      const double *po = a.phiF + static_cast<long long>(code_own) * a.nqf * dof;
+      const double *src = sQF + static_cast<long long>(lf) * a.nqf * nc;
+      double v = 0;
+      for (int q = 0; q < a.nqf; q++) v += po[q * dof + j] * src[q * nc + c];
+      acc += v;
+    }
+    sRhs[j * nc + c] = acc;
+  }
+  __syncthreads();
   // gradUp[e*dof + j + eq*N + d*neq*N]: component c = eq + d*neq has stride N
   gen_apply_minv(a, a.me_inv, e, sRhs, nc, a.gradUp, N);
 }
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
 __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   extern __shared__ double sm[];
   const int e = blockIdx.x, dim = a.dim, dof = a.dof, neq = a.neq, nc = neq * dim;
-  const int nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  const int nqmax = a.nqv > a.nfe * a.nqf ? a.nqv : a.nfe * a.nqf;
   double *sU = sm;                  // [neq][dof]
   double *sG = sU + neq * dof;      // [nc][dof]   gradUp of the element
   double *sF = sG + nc * dof;       // [dof][nc]   nodal flux F_c - F_v
@@ -446,18 +457,22 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   }
   __syncthreads();
   // faces: Fhat = Rusanov(u1,u2,n) - 1/2 (Fv1 + Fv2).n with n = CalcOrtho of Elem1 (face_integrator.cpp:282-351)
-  for (int lf = 0; lf < a.nfe; lf++) {
-    const int f = a.el_face[e * a.nfe + lf];
-    const int e1 = a.f_el1[f], e2 = a.f_el2[f];
-    const bool bdr = e2 < 0;
-    if (bdr && a.f_bc[f] < 0) continue;  // no boundary integrator registered for this attribute
-    const bool first = (e1 == e);
-    const int code_own = gen_code(dim, first ? a.f_inf1[f] : a.f_inf2[f]);
-    const int code_oth = bdr ? code_own : gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
-    const int code1 = gen_code(dim, a.f_inf1[f]);
-    const int eo = bdr ? e1 : (first ? e2 : e1);
-    const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
-    for (int q = threadIdx.x; q < a.nqf; q += blockDim.x) {
+  // One task per (local face, face point), all faces in flight at once; the lift below adds them in local-face order.
+  double *sQF = sQ;  // [nfe * nqf][neq]  (the volume values in sQ are consumed)
+  {
+    for (int it = threadIdx.x; it < a.nfe * a.nqf; it += blockDim.x) {
+      const int lf = it / a.nqf, q = it - lf * a.nqf;
+      const int f = a.el_face[e * a.nfe + lf];
+      const int e1 = a.f_el1[f], e2 = a.f_el2[f];
+      const bool bdr = e2 < 0;
+      if (bdr && a.f_bc[f] < 0) continue;  // no boundary integrator registered for this attribute
+      const bool first = (e1 == e);
+      const int code_own = gen_code(dim, first ? a.f_inf1[f] : a.f_inf2[f]);
+      const int code_oth = bdr ? code_own : gen_code(dim, first ? a.f_inf2[f] : a.f_inf1[f]);
+      const int code1 = gen_code(dim, a.f_inf1[f]);
+      const int eo = bdr ? e1 : (first ? e2 : e1);
+      const double *v1 = a.vx + static_cast<long long>(e1) * a.nv * dim;
+      double *dstq = sQF + static_cast<long long>(it) * neq;
       double J[9], nor[3];
       const double *xi1 = a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim;
       gen_jacobian(dim, v1, xi1, J);
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
           for (int k = 0; k < dof; k++) dwb += po[k] * a.dist[static_cast<long long>(e1) * dof + k];
         gen_bc_flux(a.phys, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb);
         const double sgb = -(a.phys.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
-        for (int eq = 0; eq < neq; eq++) sQ[q * nc + eq] = sgb * fxb[eq];
+        for (int eq = 0; eq < neq; eq++) dstq[eq] = sgb * fxb[eq];
         continue;
       }
       for (int eq = 0; eq < neq; eq++) {
@@ -533,18 +548,26 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       }
       // elvect1 -= phi1 Fhat w ; elvect2 += phi2 Fhat w ; axisymmetric: fluxN *= radius (face_integrator.cpp:344-350)
       const double sg = (first ? -1.0 : 1.0) * (a.phys.axisym ? a.wF[q] * radius : a.wF[q]);
-      for (int eq = 0; eq < neq; eq++) sQ[q * nc + eq] = sg * fx[eq];
+      for (int eq = 0; eq < neq; eq++) dstq[eq] = sg * fx[eq];
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < dof * neq; t += blockDim.x) {
-      const int j = t / neq, eq = t % neq;
-      const double *po = a.phiF + static_cast<long long>(code_own) * a.nqf * dof;
-      double v = 0;
-      for (int q = 0; q < a.nqf; q++) v += po[q * dof + j] * sQ[q * nc + eq];
-      sZ[j * neq + eq] += v;
-    }
-    __syncthreads();
   }
+  __syncthreads();
+  for (int t = threadIdx.x; t < dof * neq; t += blockDim.x) {
+    const int j = t / neq, eq = t % neq;
+    double acc = sZ[j * neq + eq];
+    for (int lf = 0; lf < a.nfe; lf++) {
+      const int f = a.el_face[e * a.nfe + lf];
+      if (a.f_el2[f] < 0 && a.f_bc[f] < 0) continue;
+      const int code_own = gen_code(dim, a.f_el1[f] == e ? a.f_inf1[f] : a.f_inf2[f]);
+      const double *po = a.phiF + static_cast<long long>(code_own) * a.nqf * dof;
+      const double *src = sQF + static_cast<long long>(lf) * a.nqf * neq;
+      double v = 0;
+      for (int q = 0; q < a.nqf; q++) v += po[q * dof + j] * src[q * neq + eq];
+      acc += v;
+    }
+    sZ[j * neq + eq] = acc;
+  }
+  __syncthreads();
   gen_apply_minv(a, a.phys.axisym ? a.me_inv_rad : a.me_inv, e, sZ, neq, a.y, N);
 }
 
@@ -640,11 +663,11 @@ __global__ void gen_point_eval_kernel(GenArgs a, int which, int n, const double 
 }
 
 inline size_t gen_grad_smem(const GenArgs &a) {
-  const int nc = a.neq * a.dim, nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  const int nc = a.neq * a.dim, nqmax = a.nqv > a.nfe * a.nqf ? a.nqv : a.nfe * a.nqf;
   return sizeof(double) * (static_cast<size_t>(a.neq) * a.dof + static_cast<size_t>(a.dof) * nc + static_cast<size_t>(nqmax) * nc + a.nqv);
 }
 inline size_t gen_resid_smem(const GenArgs &a) {
-  const int nc = a.neq * a.dim, nqmax = a.nqv > a.nqf ? a.nqv : a.nqf;
+  const int nc = a.neq * a.dim, nqmax = a.nqv > a.nfe * a.nqf ? a.nqv : a.nfe * a.nqf;
   return sizeof(double) * (static_cast<size_t>(a.neq) * a.dof + 2 * static_cast<size_t>(a.dof) * nc + static_cast<size_t>(nqmax) * nc +
                            static_cast<size_t>(a.dof) * a.neq);
 }

@@ -82,6 +82,14 @@ struct tpsb_ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_out;
   cudaEvent_t ev_pipe0 = nullptr, ev_pipe1 = nullptr;
+  // tpsb_ode_step: one Runge-Kutta step captured as a CUDA graph and replayed (keyed by solution pointer, dt, scheme)
+  cudaGraphExec_t ode_exec = nullptr;
+  cudaStream_t ode_stream = nullptr;
+  cudaEvent_t ode_ev0 = nullptr, ode_ev1 = nullptr;
+  double *ode_U = nullptr;
+  double ode_dt = 0.0;
+  int ode_scheme = 0;
+  long long ode_launches = 0;
   long long launches = 0;
   int tune[3] = {0, 0, 0};
   int num_sms = 148, face_ctas_per_sm = 5;
@@ -1119,6 +1127,10 @@ void tpsb_destroy(tpsb_ctx *c) {
   if (c->ev_recvU) cudaEventDestroy(c->ev_recvU);
   if (c->ev_recvG) cudaEventDestroy(c->ev_recvG);
   if (c->ev_recvT) cudaEventDestroy(c->ev_recvT);
+  if (c->ode_exec) cudaGraphExecDestroy(c->ode_exec);
+  if (c->ode_stream) cudaStreamDestroy(c->ode_stream);
+  if (c->ode_ev0) cudaEventDestroy(c->ode_ev0);
+  if (c->ode_ev1) cudaEventDestroy(c->ode_ev1);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
@@ -1499,6 +1511,15 @@ static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
 }
 
 // ---- generic path (rhs_generic.cuh) ----
+// One CTA per element; the per-point loops have max(dof, nqv) independent items (9 / 16 on a p = 2 quadrilateral), and
+// the kernels hold 96-128 registers per thread: sizing the CTA to the element instead of a fixed 128 threads keeps
+// 2-4x more elements resident per SM (C1, 25 600 quads: 4.6 -> see DESIGN.md ms per evaluation).
+static int gen_block_threads(const GenArgs &g) {
+  static const int forced = getenv("TPSB_GEN_THREADS") ? atoi(getenv("TPSB_GEN_THREADS")) : 0;
+  if (forced >= 32 && forced <= 128) return (forced / 32) * 32;
+  const int items = std::max(std::max(g.dof, g.nqv), g.nfe * g.nqf);
+  return std::min(128, std::max(32, ((items + 31) / 32) * 32));
+}
 static int run_gradients_generic(tpsb_ctx *ctx, const double *d_x, bool prims_done) {
   tpsb_ctx *c = ctx;
   GenArgs g = c->gen;
@@ -1511,7 +1532,7 @@ static int run_gradients_generic(tpsb_ctx *ctx, const double *d_x, bool prims_do
     ProfScope ps(c, K_GRAD);
     const size_t smem = gen_grad_smem(g);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    gen_grad_kernel<<<g.NE, 128, smem, c->stream>>>(g);
+    gen_grad_kernel<<<g.NE, gen_block_threads(g), smem, c->stream>>>(g);
   }
   CU(cudaGetLastError());
   return TPSB_OK;
@@ -1529,7 +1550,7 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
     ProfScope ps(c, K_RESID);
     const size_t smem = gen_resid_smem(g);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    gen_resid_kernel<<<g.NE, 128, smem, c->stream>>>(g);
+    gen_resid_kernel<<<g.NE, gen_block_threads(g), smem, c->stream>>>(g);
   }
   if (g.phys.fluid) {  // forcing terms are added after Me^-1 (rhs_operator.cpp:451-461)
     ProfScope ps(c, K_RESID);
@@ -1569,6 +1590,11 @@ static int run_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
 
 static __global__ void bits_to_double_kernel(const unsigned long long *bits, double *out) {
   *out = __longlong_as_double(static_cast<long long>(*bits));
+}
+
+static void ode_graph_invalidate(tpsb_ctx *ctx) {
+  if (ctx->ode_exec) cudaGraphExecDestroy(ctx->ode_exec);
+  ctx->ode_exec = nullptr;
 }
 
 static int ensure_work(tpsb_ctx *ctx, double **p) {
@@ -1733,6 +1759,7 @@ int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance) {
   if (!ctx) return TPSB_EINVAL;
   if (!ctx->generic) return fail(ctx, TPSB_EINVAL, "the wall distance is read by the mixing-length model (generic path) only");
   ctx->gen.dist = d_distance;
+  ode_graph_invalidate(ctx);  // the pointer is baked into the captured launches
   return TPSB_OK;
 }
 
@@ -1795,6 +1822,57 @@ int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out) {
 
 // MFEM ODESolver::Step restated (third party): ForwardEuler, RK2(a=1) (Heun),
 // RK3SSP, RK4 -- the solvers M2ulPhyS::initVariables can select (src/M2ulPhyS.cpp:721-739).
+// One step, enqueued on ctx->stream.
+static int ode_one_step(tpsb_ctx *ctx, double *x, double dt, int scheme) {
+  int rc;
+  const long long n = ctx->N * ctx->neq;
+  const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+  double *k = ctx->d_k, *y = ctx->d_yv, *z = ctx->d_z;
+  cudaStream_t st = ctx->stream;
+#define AXPY(X, K, A, Y, B, Z, ACC)                                    do {                                                                   axpy2_kernel<<<nb, 256, 0, st>>>(n, X, K, A, Y, B, Z, ACC);          ctx->launches++;                                                   } while (0)
+  if (scheme == 1) {  // x += dt f(x)
+    if ((rc = run_mult(ctx, x, k))) return rc;
+    AXPY(x, k, dt, x, 0.0, nullptr, 0);
+  } else if (scheme == 2) {  // RK2Solver(a = 1): y = x + dt k1; x += dt/2 (k1 + k2)
+    if ((rc = run_mult(ctx, x, k))) return rc;
+    AXPY(x, k, dt, y, 0.5 * dt, z, 0);
+    if ((rc = run_mult(ctx, y, k))) return rc;
+    AXPY(z, k, 0.5 * dt, x, 0.0, nullptr, 0);
+  } else if (scheme == 3) {  // RK3SSPSolver
+    if ((rc = run_mult(ctx, x, k))) return rc;
+    AXPY(x, k, dt, y, 0.0, nullptr, 0);  // y = x + dt k
+    if ((rc = run_mult(ctx, y, k))) return rc;
+    // y = 3/4 x + 1/4 (y + dt k)
+    AXPY(y, k, dt, y, 0.0, nullptr, 0);
+    {
+      ProfScope ps(ctx, K_AXPY);
+      rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 0.75, 0.25, y);
+    }
+    if ((rc = run_mult(ctx, y, k))) return rc;
+    // x = 1/3 x + 2/3 (y + dt k)
+    AXPY(y, k, dt, y, 0.0, nullptr, 0);
+    {
+      ProfScope ps(ctx, K_AXPY);
+      rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 1.0 / 3.0, 2.0 / 3.0, x);
+    }
+  } else {  // RK4Solver
+    if ((rc = run_mult(ctx, x, k))) return rc;
+    AXPY(x, k, dt / 2, y, dt / 6, z, 0);
+    if ((rc = run_mult(ctx, y, k))) return rc;
+    AXPY(x, k, dt / 2, y, dt / 3, z, 1);
+    if ((rc = run_mult(ctx, y, k))) return rc;
+    AXPY(x, k, dt, y, dt / 3, z, 1);
+    if ((rc = run_mult(ctx, y, k))) return rc;
+    AXPY(z, k, dt / 6, x, 0.0, nullptr, 0);
+  }
+#undef AXPY
+  return TPSB_OK;
+}
+
+// The first step runs eagerly on the caller's stream (lazy allocations, function attributes, constant tables); the
+// remaining ones replay one captured step: a Runge-Kutta step is 20-30 short launches, and on the small 2-D / plasma
+// configurations their launch latency, not the kernels, sets the step time.  Single rank only
+// (the halo exchange keeps its own stream and events); TPSB_ODE_GRAPH=0 switches the replay off.
 int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps) {
   if (!ctx || !d_U || nsteps < 0) return TPSB_EINVAL;
   if (scheme < 1 || scheme > 4) return fail(ctx, TPSB_ENOTIMPL, "ODE scheme %d not built", scheme);
@@ -1803,52 +1881,60 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
   if (!rc) rc = ensure_work(ctx, &ctx->d_yv);
   if (!rc) rc = ensure_work(ctx, &ctx->d_z);
   if (rc) return rc;
-  const long long n = ctx->N * ctx->neq;
-  const unsigned nb = static_cast<unsigned>((n + 255) / 256);
-  double *k = ctx->d_k, *y = ctx->d_yv, *z = ctx->d_z, *x = d_U;
-  cudaStream_t st = ctx->stream;
   const double *saved_view = ctx->sol_view;
   ctx->sol_view = d_U;  // the forcing terms read the solution vector, not the stage vector (parity trap 1)
-#define AXPY(X, K, A, Y, B, Z, ACC)                                    do {                                                                   axpy2_kernel<<<nb, 256, 0, st>>>(n, X, K, A, Y, B, Z, ACC);          ctx->launches++;                                                   } while (0)
-  for (int s = 0; s < nsteps; s++) {
-    if (scheme == 1) {  // x += dt f(x)
-      if ((rc = run_mult(ctx, x, k))) return rc;
-      AXPY(x, k, dt, x, 0.0, nullptr, 0);
-    } else if (scheme == 2) {  // RK2Solver(a = 1): y = x + dt k1; x += dt/2 (k1 + k2)
-      if ((rc = run_mult(ctx, x, k))) return rc;
-      AXPY(x, k, dt, y, 0.5 * dt, z, 0);
-      if ((rc = run_mult(ctx, y, k))) return rc;
-      AXPY(z, k, 0.5 * dt, x, 0.0, nullptr, 0);
-    } else if (scheme == 3) {  // RK3SSPSolver
-      if ((rc = run_mult(ctx, x, k))) return rc;
-      AXPY(x, k, dt, y, 0.0, nullptr, 0);  // y = x + dt k
-      if ((rc = run_mult(ctx, y, k))) return rc;
-      // y = 3/4 x + 1/4 (y + dt k)
-      AXPY(y, k, dt, y, 0.0, nullptr, 0);
-      {
-        ProfScope ps(ctx, K_AXPY);
-        rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 0.75, 0.25, y);
-      }
-      if ((rc = run_mult(ctx, y, k))) return rc;
-      // x = 1/3 x + 2/3 (y + dt k)
-      AXPY(y, k, dt, y, 0.0, nullptr, 0);
-      {
-        ProfScope ps(ctx, K_AXPY);
-        rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 1.0 / 3.0, 2.0 / 3.0, x);
-      }
-    } else {  // RK4Solver
-      if ((rc = run_mult(ctx, x, k))) return rc;
-      AXPY(x, k, dt / 2, y, dt / 6, z, 0);
-      if ((rc = run_mult(ctx, y, k))) return rc;
-      AXPY(x, k, dt / 2, y, dt / 3, z, 1);
-      if ((rc = run_mult(ctx, y, k))) return rc;
-      AXPY(x, k, dt, y, dt / 3, z, 1);
-      if ((rc = run_mult(ctx, y, k))) return rc;
-      AXPY(z, k, dt / 6, x, 0.0, nullptr, 0);
+  const char *env = getenv("TPSB_ODE_GRAPH");
+  const bool use_graph = !ctx->comm && !ctx->profiling && nsteps >= 3 && !(env && atoi(env) == 0);
+  int done = 0;
+  for (; done < nsteps && (!use_graph || done < 1); done++)
+    if ((rc = ode_one_step(ctx, d_U, dt, scheme))) break;
+  if (!rc && use_graph && done < nsteps) {
+    cudaStream_t caller = ctx->stream;
+    if (!ctx->ode_stream) {
+      CU(cudaStreamCreateWithFlags(&ctx->ode_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->ode_ev0, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->ode_ev1, cudaEventDisableTiming));
     }
+    if (ctx->ode_exec && (ctx->ode_U != d_U || ctx->ode_dt != dt || ctx->ode_scheme != scheme)) ode_graph_invalidate(ctx);
+    if (!ctx->ode_exec) {
+      const long long l0 = ctx->launches;
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(ctx->ode_stream, cudaStreamCaptureModeThreadLocal));
+      ctx->stream = ctx->ode_stream;
+      rc = ode_one_step(ctx, d_U, dt, scheme);
+      ctx->stream = caller;
+      const cudaError_t ce = cudaStreamEndCapture(ctx->ode_stream, &graph);
+      ctx->ode_launches = ctx->launches - l0;
+      ctx->launches = l0;  // nothing ran yet
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        ctx->sol_view = saved_view;
+        return rc ? rc : fail(ctx, TPSB_ECUDA, "capturing the Runge-Kutta step failed: %s", cudaGetErrorString(ce));
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&ctx->ode_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        ctx->ode_exec = nullptr;
+        ctx->sol_view = saved_view;
+        return fail(ctx, TPSB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+      }
+      ctx->ode_U = d_U, ctx->ode_dt = dt, ctx->ode_scheme = scheme;
+    }
+    if (g_uploaded_order != ctx->order) {  // another context switched the __constant__ tables since the capture
+      CU(cudaMemcpyToSymbolAsync(c_T, &ctx->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, caller));
+      g_uploaded_order = ctx->order;
+    }
+    CU(cudaEventRecord(ctx->ode_ev0, caller));
+    CU(cudaStreamWaitEvent(ctx->ode_stream, ctx->ode_ev0, 0));
+    for (; done < nsteps; done++) {
+      CU(cudaGraphLaunch(ctx->ode_exec, ctx->ode_stream));
+      ctx->launches += ctx->ode_launches;
+    }
+    CU(cudaEventRecord(ctx->ode_ev1, ctx->ode_stream));
+    CU(cudaStreamWaitEvent(caller, ctx->ode_ev1, 0));
   }
-#undef AXPY
   ctx->sol_view = saved_view;
+  if (rc) return rc;
   CU(cudaGetLastError());
   return TPSB_OK;
 }
