@@ -488,9 +488,10 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
           const int sp = eq - a.nvel - 2;
           uo[eq] = (sp >= 0 && sp < nact) ? fmax(x, 0.0) : x;
         }
-        for (int c = 0; c < nc; c++) {
+        for (int c = 0; c < nc; c++) {  // the Euler boundary fluxes never read the gradients
           double x = 0;
-          for (int k = 0; k < dof; k++) x += po[k] * sG[c * dof + k];
+          if (a.eq_system != 0)
+            for (int k = 0; k < dof; k++) x += po[k] * sG[c * dof + k];
           go[c] = x;
         }
         double fxb[GEN_MAXEQ];
@@ -517,15 +518,17 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         uo[a.nvel + 2 + sp] = fmax(uo[a.nvel + 2 + sp], 0.0);
         un[a.nvel + 2 + sp] = fmax(un[a.nvel + 2 + sp], 0.0);
       }
-      for (int c = 0; c < nc; c++) {
-        double x = 0, y = 0;
-        const double *src = a.gradUp + static_cast<long long>(eo) * dof + c * N;
-        for (int k = 0; k < dof; k++) {
-          x += po[k] * sG[c * dof + k];
-          y += pn[k] * src[k];
+      if (a.eq_system != 0) {  // gradients enter the viscous fluxes only
+        for (int c = 0; c < nc; c++) {
+          double x = 0, y = 0;
+          const double *src = a.gradUp + static_cast<long long>(eo) * dof + c * N;
+          for (int k = 0; k < dof; k++) {
+            x += po[k] * sG[c * dof + k];
+            y += pn[k] * src[k];
+          }
+          go[c] = x;
+          gn[c] = y;
         }
-        go[c] = x;
-        gn[c] = y;
       }
       const double *u1 = first ? uo : un, *u2 = first ? un : uo, *g1 = first ? go : gn, *g2 = first ? gn : go;
       double fx[GEN_MAXEQ];
