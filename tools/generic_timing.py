@@ -29,7 +29,7 @@ def run(name, op, U, reps=20):
     torch.cuda.synchronize()
     kt = op.kernel_times()
     op.set_profiling(False)
-    print(f"{name}: N={op.N} neq={op.neq}  {ms:.3f} ms/eval  {op.N / ms / 1e3:.3e} DOF-evals/s  kernels(ms total of 5): {kt}")
+    print(f"{name}: N={op.N} neq={op.neq}  {ms:.3f} ms/eval  {op.N / (ms * 1e-3):.3e} DOF-evals/s  kernels(ms total of 5): {kt}")
 
 
 if __name__ == "__main__":
