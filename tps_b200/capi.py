@@ -196,7 +196,7 @@ class PartSizes(C.Structure):
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -235,6 +235,7 @@ def lib():
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_set_solution_view.argtypes = [vp, vp]
     L.tpsb_set_distance_field.argtypes = [vp, vp]
+    L.tpsb_debug_host_pipe_schedule.argtypes = [C.POINTER(MeshMaps), C.c_int, ip, ip, ip, C.c_int, C.POINTER(C.c_int)]
     L.tpsb_set_reaction_rate_field.argtypes = [vp, vp, C.c_int]
     L.tpsb_get_mean_time_derivatives.argtypes = [vp, vp, dp]
     L.tpsb_ode_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
@@ -358,6 +359,21 @@ def cylinder_ogrid_mesh(nr, nth, nz, r_in=0.5, r_out=10.0, lz=2.0, stretch=1.08,
     m["elem_xyz"] = np.ascontiguousarray(xyz)
     m["face_attr"] = attr
     return m
+
+
+def host_pipe_schedule(mesh, chunks):
+    """Test hook: (elem_begin, face_begin, [(kind, chunk), ...]) of the chunked host-buffer pipeline, or None when the
+    mesh cannot be chunked (tpsb_debug_host_pipe_schedule; host only)."""
+    L = lib()
+    xyz = np.ascontiguousarray(mesh["elem_xyz"], dtype=np.float64)
+    arr = [np.ascontiguousarray(mesh[k], dtype=np.int32) for k in ("face_el1", "face_el2", "face_inf1", "face_inf2")]
+    maps = MeshMaps(xyz.shape[2], xyz.shape[0], 0, _dp(xyz), len(arr[0]), _ip(arr[0]), _ip(arr[1]), _ip(arr[2]), _ip(arr[3]), None)
+    eb, fb = np.zeros(chunks + 1, np.int32), np.zeros(chunks + 1, np.int32)
+    ops, n = np.zeros(2 * 8 * max(chunks, 1), np.int32), C.c_int(0)
+    rc = L.tpsb_debug_host_pipe_schedule(C.byref(maps), chunks, _ip(eb), _ip(fb), _ip(ops), len(ops) // 2, C.byref(n))
+    if rc != 0:
+        return None
+    return eb, fb, [(int(ops[2 * k]), int(ops[2 * k + 1])) for k in range(n.value)]
 
 
 def ref_tables(order):

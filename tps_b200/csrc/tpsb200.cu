@@ -599,24 +599,22 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
 // the elements).  A chunk's gradient needs the primitives of its face neighbours' chunks, a face range the trace
 // blocks of both sides' chunks, a chunk's residual the face residuals of all its faces; the op list below is the
 // greedy order in which those become available while the chunks arrive 0, 1, 2, ...
-void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
-                     const std::vector<int> &fl_el1, const std::vector<int> &fl_el2) {
-  const int NE = c->NE;
-  int C = std::min(32, NE / 2048);
-  if (const char *ev = getenv("TPSB_HOST_CHUNKS")) C = atoi(ev);
-  C = std::min(C, 64);
-  if (C < 3 || C > NE) return;
-  std::vector<int> eb(C + 1), fb(C + 1, c->NFint);
+bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
+                        const std::vector<int> &fl_el1, const std::vector<int> &fl_el2, std::vector<int> &eb, std::vector<int> &fb,
+                        std::vector<tpsb_ctx::PipeOp> &ops) {
+  if (C < 3 || C > 64 || C > NE) return false;
+  eb.assign(C + 1, 0);
+  fb.assign(C + 1, NFint);
   for (int k = 0; k <= C; k++) eb[k] = static_cast<int>(static_cast<long long>(NE) * k / C);
   auto chunk_of = [&](int e) { return static_cast<int>(std::upper_bound(eb.begin(), eb.end(), e) - eb.begin()) - 1; };
   fb[0] = 0;
   int cur = 0;
-  for (int f = 0; f < c->NFint; f++) {
+  for (int f = 0; f < NFint; f++) {
     const int cf = chunk_of(fl_el1[f]);
-    if (cf < cur) return;  // face order not monotone in Elem1: keep the unchunked path
+    if (cf < cur) return false;  // face order not monotone in Elem1: keep the unchunked path
     while (cur < cf) fb[++cur] = f;
   }
-  while (cur < C) fb[++cur] = c->NFint;
+  while (cur < C) fb[++cur] = NFint;
   using mask = unsigned long long;
   std::vector<mask> need_prim(C, 0), need_grad(C, 0), need_face(C, 0);
   for (int e = 0; e < NE; e++) {
@@ -625,15 +623,15 @@ void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::v
     for (int lf = 0; lf < 6; lf++) {
       const int nb = nbr_elem[static_cast<size_t>(e) * 6 + lf], fc = el_face[static_cast<size_t>(e) * 6 + lf];
       if (nb >= 0) need_prim[ce] |= mask(1) << chunk_of(nb);
-      if (fc >= 0 && fc < c->NFint)
+      if (fc >= 0 && fc < NFint)
         need_face[ce] |= mask(1) << (static_cast<int>(std::upper_bound(fb.begin(), fb.end(), fc) - fb.begin()) - 1);
     }
   }
-  for (int f = 0; f < c->NFint; f++) {
+  for (int f = 0; f < NFint; f++) {
     const int cf = chunk_of(fl_el1[f]);
     need_grad[cf] |= (mask(1) << cf) | (mask(1) << chunk_of(fl_el2[f]));
   }
-  std::vector<tpsb_ctx::PipeOp> ops;
+  ops.clear();
   mask primd = 0, gradd = 0, faced = 0, resd = 0;
   for (int k = 0; k < C; k++) {
     ops.push_back({0, k});
@@ -652,7 +650,17 @@ void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::v
           ops.push_back({3, r}), resd |= mask(1) << r, progress = true;
     }
   }
-  if (resd != (C == 64 ? ~mask(0) : (mask(1) << C) - 1)) return;
+  return resd == (C == 64 ? ~mask(0) : (mask(1) << C) - 1);
+}
+
+void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
+                     const std::vector<int> &fl_el1, const std::vector<int> &fl_el2) {
+  int C = std::min(32, c->NE / 2048);
+  if (const char *ev = getenv("TPSB_HOST_CHUNKS")) C = atoi(ev);
+  C = std::min(C, 64);
+  std::vector<int> eb, fb;
+  std::vector<tpsb_ctx::PipeOp> ops;
+  if (!host_pipe_schedule(c->NE, c->NFint, C, nbr_elem, el_face, fl_el1, fl_el2, eb, fb, ops)) return;
   c->pipe_chunks = C;
   c->pipe_eb = eb;
   c->pipe_fb = fb;
@@ -1138,6 +1146,31 @@ void tpsb_destroy(tpsb_ctx *c) {
   if (c->ev_pipe0) cudaEventDestroy(c->ev_pipe0);
   if (c->ev_pipe1) cudaEventDestroy(c->ev_pipe1);
   delete c;
+}
+
+// Test hook (host only, no device needed): the chunk schedule of the host-buffer pipeline for a single-rank mesh whose
+// faces are all two-sided.  ops = (kind, chunk) pairs: 0 copy-in + primitives, 1 gradient, 2 face range, 3 residual + copy-out.
+int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *elem_begin, int *face_begin, int *ops, int max_ops,
+                                  int *num_ops) {
+  if (!maps || maps->dim != 3 || !elem_begin || !face_begin || !ops || !num_ops) return TPSB_EINVAL;
+  const int NE = maps->num_elems, NF = maps->num_faces;
+  std::vector<int> nbr(static_cast<size_t>(NE) * 6, -1), elf(static_cast<size_t>(NE) * 6, -1), e1(NF), e2(NF);
+  for (int f = 0; f < NF; f++) {
+    e1[f] = maps->face_el1[f], e2[f] = maps->face_el2[f];
+    if (e1[f] < 0 || e2[f] < 0 || e2[f] >= NE) return TPSB_EINVAL;
+    const int lf1 = maps->face_inf1[f] / 64, lf2 = maps->face_inf2[f] / 64;
+    nbr[static_cast<size_t>(e1[f]) * 6 + lf1] = e2[f], nbr[static_cast<size_t>(e2[f]) * 6 + lf2] = e1[f];
+    elf[static_cast<size_t>(e1[f]) * 6 + lf1] = f, elf[static_cast<size_t>(e2[f]) * 6 + lf2] = f;
+  }
+  std::vector<int> eb, fb;
+  std::vector<tpsb_ctx::PipeOp> po;
+  if (!host_pipe_schedule(NE, NF, chunks, nbr, elf, e1, e2, eb, fb, po)) return TPSB_ENOTIMPL;
+  if (static_cast<int>(po.size()) > max_ops) return TPSB_EINVAL;
+  std::copy(eb.begin(), eb.end(), elem_begin);
+  std::copy(fb.begin(), fb.end(), face_begin);
+  for (size_t k = 0; k < po.size(); k++) ops[2 * k] = po[k].kind, ops[2 * k + 1] = po[k].chunk;
+  *num_ops = static_cast<int>(po.size());
+  return TPSB_OK;
 }
 
 int64_t tpsb_num_dofs(const tpsb_ctx *c) { return c ? c->N : 0; }
