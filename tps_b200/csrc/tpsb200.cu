@@ -655,7 +655,7 @@ bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_el
 
 void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
                      const std::vector<int> &fl_el1, const std::vector<int> &fl_el2) {
-  int C = std::min(32, c->NE / 2048);
+  int C = std::min(64, c->NE / 2048);
   if (const char *ev = getenv("TPSB_HOST_CHUNKS")) C = atoi(ev);
   C = std::min(C, 64);
   std::vector<int> eb, fb;
@@ -1661,15 +1661,34 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
     g_uploaded_order = c->order;
   }
   CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
+  static const bool dbg = getenv("TPSB_PIPE_DEBUG") != nullptr;  // development: where the three legs end
+  static cudaEvent_t dbg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  static cudaEvent_t dbg_r[64] = {}, dbg_o[64] = {}, dbg_i[64] = {};
+  if (dbg) {
+    for (auto &e : dbg_ev)
+      if (!e) cudaEventCreate(&e);
+    CU(cudaEventRecord(dbg_ev[0], c->stream));
+  }
   CU(cudaEventRecord(c->ev_pipe0, c->stream));  // earlier work on the caller's stream may still use d_hx / d_hy
   CU(cudaStreamWaitEvent(c->s_in, c->ev_pipe0, 0));
   CU(cudaStreamWaitEvent(c->s_out, c->ev_pipe0, 0));
   const size_t pitch = static_cast<size_t>(c->N) * sizeof(double);  // byNODES: one row per equation
+  static const bool row_copies = !(getenv("TPSB_HOST_COPY2D") && atoi(getenv("TPSB_HOST_COPY2D")) != 0);
   for (int k = 0; k < C; k++) {
     const size_t off = static_cast<size_t>(c->pipe_eb[k]) * c->nd;
     const size_t width = static_cast<size_t>(c->pipe_eb[k + 1] - c->pipe_eb[k]) * c->nd * sizeof(double);
-    CU(cudaMemcpy2DAsync(c->d_hx + off, pitch, h_x + off, pitch, width, NEQ, cudaMemcpyHostToDevice, c->s_in));
+    if (row_copies) {  // one contiguous copy per equation row (TPSB_HOST_COPY2D=1 selects the pitched form)
+      for (int eq = 0; eq < NEQ; eq++)
+        CU(cudaMemcpyAsync(c->d_hx + off + static_cast<size_t>(eq) * c->N, h_x + off + static_cast<size_t>(eq) * c->N, width,
+                           cudaMemcpyHostToDevice, c->s_in));
+    } else {
+      CU(cudaMemcpy2DAsync(c->d_hx + off, pitch, h_x + off, pitch, width, NEQ, cudaMemcpyHostToDevice, c->s_in));
+    }
     CU(cudaEventRecord(c->ev_in[k], c->s_in));
+    if (dbg && k < 64) {
+      if (!dbg_i[k]) cudaEventCreate(&dbg_i[k]);
+      CU(cudaEventRecord(dbg_i[k], c->s_in));
+    }
   }
   for (const tpsb_ctx::PipeOp &op : c->pipe_ops) {
     const int k = op.chunk, e0 = c->pipe_eb[k], ne = c->pipe_eb[k + 1] - e0;
@@ -1686,10 +1705,21 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
       default: {
         resid(c, a, e0, ne);
         CU(cudaEventRecord(c->ev_out[k], c->stream));
+        if (dbg && k < 64) {
+          if (!dbg_r[k]) cudaEventCreate(&dbg_r[k]), cudaEventCreate(&dbg_o[k]);
+          CU(cudaEventRecord(dbg_r[k], c->stream));
+        }
         CU(cudaStreamWaitEvent(c->s_out, c->ev_out[k], 0));
         const size_t off = static_cast<size_t>(e0) * c->nd;
-        CU(cudaMemcpy2DAsync(h_y + off, pitch, c->d_hy + off, pitch, static_cast<size_t>(ne) * c->nd * sizeof(double), NEQ,
-                             cudaMemcpyDeviceToHost, c->s_out));
+        const size_t wout = static_cast<size_t>(ne) * c->nd * sizeof(double);
+        if (row_copies) {
+          for (int eq = 0; eq < NEQ; eq++)
+            CU(cudaMemcpyAsync(h_y + off + static_cast<size_t>(eq) * c->N, c->d_hy + off + static_cast<size_t>(eq) * c->N, wout,
+                               cudaMemcpyDeviceToHost, c->s_out));
+        } else {
+          CU(cudaMemcpy2DAsync(h_y + off, pitch, c->d_hy + off, pitch, wout, NEQ, cudaMemcpyDeviceToHost, c->s_out));
+        }
+        if (dbg && k < 64) CU(cudaEventRecord(dbg_o[k], c->s_out));
         break;
       }
     }
@@ -1697,7 +1727,28 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev_pipe1, c->s_out));
   CU(cudaStreamWaitEvent(c->stream, c->ev_pipe1, 0));
+  if (dbg) {
+    CU(cudaEventRecord(dbg_ev[1], c->s_in));
+    CU(cudaEventRecord(dbg_ev[2], c->s_out));
+    CU(cudaEventRecord(dbg_ev[3], c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));
+  if (dbg) {
+    float t_in = 0, t_out = 0, t_all = 0;
+    cudaEventSynchronize(dbg_ev[1]);
+    cudaEventElapsedTime(&t_in, dbg_ev[0], dbg_ev[1]);
+    cudaEventElapsedTime(&t_out, dbg_ev[0], dbg_ev[2]);
+    cudaEventElapsedTime(&t_all, dbg_ev[0], dbg_ev[3]);
+    fprintf(stderr, "[tpsb pipe] copy-in done %.2f ms, copy-out done %.2f ms, all %.2f ms after the start\n", t_in, t_out, t_all);
+    for (int k = 0; k < C && k < 64; k++) {
+      float tr = 0, to = 0;
+      cudaEventElapsedTime(&tr, dbg_ev[0], dbg_r[k]);
+      cudaEventElapsedTime(&to, dbg_ev[0], dbg_o[k]);
+      float ti = 0;
+      cudaEventElapsedTime(&ti, dbg_ev[0], dbg_i[k]);
+      fprintf(stderr, "[tpsb pipe]   chunk %2d: copied in %.2f ms, residual done %.2f ms, copied out %.2f ms\n", k, ti, tr, to);
+    }
+  }
   return TPSB_OK;
 }
 
