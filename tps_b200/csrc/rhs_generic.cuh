@@ -275,9 +275,16 @@ __device__ __forceinline__ void gen_apply_minv(const GenArgs &a, const double *m
 }
 
 // ------------------------------------------------------------------------------------------------
+template <int DIM, int NVEL, int NEQ>
 __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
   extern __shared__ double sm[];
-  const int e = blockIdx.x, dim = a.dim, dof = a.dof, neq = a.neq, nc = neq * dim;
+  GenPhys phl;
+  if (DIM > 0) {  // dry-air instantiation: sizes and the fluid switch become constants the inlined physics folds
+    phl = a.phys;
+    phl.dim = DIM, phl.nvel = NVEL, phl.neq = NEQ, phl.fluid = 0, phl.mix = nullptr;
+  }
+  const GenPhys &ph = DIM > 0 ? phl : a.phys;
+  const int e = blockIdx.x, dim = DIM > 0 ? DIM : a.dim, dof = a.dof, neq = DIM > 0 ? NEQ : a.neq, nc = neq * dim;
   const int nqmax = a.nqv > a.nfe * a.nqf ? a.nqv : a.nfe * a.nqf;
   double *sUp = sm;                    // [neq][dof]
   double *sRhs = sUp + neq * dof;      // [dof][nc]
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
         for (int k = 0; k < dof; k++) v += po[k] * sUp[eq * dof + k];
         own[eq] = v;
       }
-      gen_bc_prim_for_gradient(a.phys, a.bct.bc[a.f_bc[f]], own, pbc);
+      gen_bc_prim_for_gradient(ph, a.bct.bc[a.f_bc[f]], own, pbc);
       for (int eq = 0; eq < neq; eq++) {
         const double jump = 0.5 * (pbc[eq] - own[eq]);
         for (int d = 0; d < dim; d++) dst[eq + d * neq] = jump * nor[d] * sg;
@@ -389,9 +396,20 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// DIM / NVEL / NEQ > 0: compile-time copies of the run-time sizes (dry-air instantiations).  The per-point routines are
+// inlined, so with constant sizes their equation / dimension loops unroll and the small per-thread arrays live in
+// registers instead of run-time-indexed local memory; <0,0,0> is the fully run-time form (mixtures).
+template <int DIM, int NVEL, int NEQ>
 __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   extern __shared__ double sm[];
-  const int e = blockIdx.x, dim = a.dim, dof = a.dof, neq = a.neq, nc = neq * dim;
+  GenPhys phl;
+  if (DIM > 0) {  // dry-air instantiation: sizes and the fluid switch become constants the inlined physics folds
+    phl = a.phys;
+    phl.dim = DIM, phl.nvel = NVEL, phl.neq = NEQ, phl.fluid = 0, phl.mix = nullptr;
+  }
+  const GenPhys &ph = DIM > 0 ? phl : a.phys;
+  const int nvel = DIM > 0 ? NVEL : a.nvel;
+  const int e = blockIdx.x, dim = DIM > 0 ? DIM : a.dim, dof = a.dof, neq = DIM > 0 ? NEQ : a.neq, nc = neq * dim;
   const int nqmax = a.nqv > a.nfe * a.nqf ? a.nqv : a.nfe * a.nqf;
   double *sU = sm;                  // [neq][dof]
   double *sG = sU + neq * dof;      // [nc][dof]   gradUp of the element
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   double *sQ = sF + dof * nc;       // [nqmax][nc]
   double *sZ = sQ + nqmax * nc;     // [dof][neq]
   __shared__ unsigned long long sMaxBits;
-  const int nact = gen_num_active_species(a.phys);
+  const int nact = gen_num_active_species(ph);
   const long long N = a.N;
   const double *vx = a.vx + static_cast<long long>(e) * a.nv * dim;
   if (threadIdx.x == 0) sMaxBits = 0ull;
@@ -412,17 +430,17 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     double s[GEN_MAXEQ], gr[GEN_MAXEQ * GEN_MAXDIM], fc[GEN_MAXEQ * GEN_MAXDIM], fv[GEN_MAXEQ * GEN_MAXDIM];
     for (int eq = 0; eq < neq; eq++) s[eq] = sU[eq * dof + k];
     // species densities are clamped >= 0 at the nodes of GetFlux (rhs_operator.cpp:512-517)
-    for (int sp = 0; sp < nact; sp++) s[a.nvel + 2 + sp] = fmax(s[a.nvel + 2 + sp], 0.0);
+    for (int sp = 0; sp < nact; sp++) s[nvel + 2 + sp] = fmax(s[nvel + 2 + sp], 0.0);
     for (int c = 0; c < nc; c++) gr[c] = sG[c * dof + k];
-    gen_conv_flux(a.phys, s, fc);
+    gen_conv_flux(ph, s, fc);
     if (a.eq_system != 0) {
-      const double radius = a.phys.axisym ? gen_quad_x(vx, a.xiN + k * dim) : -1.0;  // nodal coordinate (GetFlux :526-528)
+      const double radius = ph.axisym ? gen_quad_x(vx, a.xiN + k * dim) : -1.0;  // nodal coordinate (GetFlux :526-528)
       const double dw = a.dist ? a.dist[static_cast<long long>(e) * dof + k] : 0.0;  // rhs_operator.cpp:534-537
-      gen_visc_flux(a.phys, s, gr, radius, fv, dw);
+      gen_visc_flux(ph, s, gr, radius, fv, dw);
       for (int c = 0; c < nc; c++) fc[c] -= fv[c];
     }
     for (int c = 0; c < nc; c++) sF[k * nc + c] = fc[c];
-    atomicMax(&sMaxBits, static_cast<unsigned long long>(__double_as_longlong(gen_max_char_speed(a.phys, s))));
+    atomicMax(&sMaxBits, static_cast<unsigned long long>(__double_as_longlong(gen_max_char_speed(ph, s))));
   }
   __syncthreads();
   if (threadIdx.x == 0) atomicMax(a.maxCharBits, sMaxBits);
@@ -432,7 +450,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     gen_jacobian(dim, vx, a.xiV + q * dim, J);
     gen_adj(dim, J, A);
     // shape *= ip.weight [* radius]  (domain_integrator.cpp:71-90)
-    const double w = a.phys.axisym ? a.wV[q] * gen_quad_x(vx, a.xiV + q * dim) : a.wV[q];
+    const double w = ph.axisym ? a.wV[q] * gen_quad_x(vx, a.xiV + q * dim) : a.wV[q];
     const double *ph = a.phiV + static_cast<long long>(q) * dof;
     for (int eq = 0; eq < neq; eq++) {
       double fq[GEN_MAXDIM] = {0, 0, 0};
@@ -477,7 +495,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       const double *xi1 = a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim;
       gen_jacobian(dim, v1, xi1, J);
       gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
-      const double radius = a.phys.axisym ? gen_quad_x(v1, xi1) : -1.0;  // Tr.Transform(ip)[0]
+      const double radius = ph.axisym ? gen_quad_x(v1, xi1) : -1.0;  // Tr.Transform(ip)[0]
       const double *po = a.phiF + (static_cast<long long>(code_own) * a.nqf + q) * dof;
       const double *pn = a.phiF + (static_cast<long long>(code_oth) * a.nqf + q) * dof;
       double uo[GEN_MAXEQ], un[GEN_MAXEQ], go[GEN_MAXEQ * GEN_MAXDIM], gn[GEN_MAXEQ * GEN_MAXDIM];
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         for (int eq = 0; eq < neq; eq++) {
           double x = 0;
           for (int k = 0; k < dof; k++) x += po[k] * sU[eq * dof + k];
-          const int sp = eq - a.nvel - 2;
+          const int sp = eq - nvel - 2;
           uo[eq] = (sp >= 0 && sp < nact) ? fmax(x, 0.0) : x;
         }
         for (int c = 0; c < nc; c++) {  // the Euler boundary fluxes never read the gradients
@@ -499,8 +517,8 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         double dwb = 0.0;  // BCintegrator.cpp:408-411
         if (a.dist)
           for (int k = 0; k < dof; k++) dwb += po[k] * a.dist[static_cast<long long>(e1) * dof + k];
-        gen_bc_flux(a.phys, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb);
-        const double sgb = -(a.phys.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
+        gen_bc_flux(ph, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb);
+        const double sgb = -(ph.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
         for (int eq = 0; eq < neq; eq++) dstq[eq] = sgb * fxb[eq];
         continue;
       }
@@ -515,8 +533,8 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         un[eq] = y;
       }
       for (int sp = 0; sp < nact; sp++) {  // face_integrator.cpp:297-301
-        uo[a.nvel + 2 + sp] = fmax(uo[a.nvel + 2 + sp], 0.0);
-        un[a.nvel + 2 + sp] = fmax(un[a.nvel + 2 + sp], 0.0);
+        uo[nvel + 2 + sp] = fmax(uo[nvel + 2 + sp], 0.0);
+        un[nvel + 2 + sp] = fmax(un[nvel + 2 + sp], 0.0);
       }
       if (a.eq_system != 0) {  // gradients enter the viscous fluxes only
         for (int c = 0; c < nc; c++) {
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       }
       const double *u1 = first ? uo : un, *u2 = first ? un : uo, *g1 = first ? go : gn, *g2 = first ? gn : go;
       double fx[GEN_MAXEQ];
-      gen_riemann(a.phys, u1, u2, nor, fx);
+      gen_riemann(ph, u1, u2, nor, fx);
       if (a.eq_system != 0) {
         double f1[GEN_MAXEQ * GEN_MAXDIM], f2[GEN_MAXEQ * GEN_MAXDIM];
         double dwo = 0.0, dwn = 0.0;  // each side's own interpolation of the wall distance (face_integrator.cpp:304-309)
@@ -541,8 +559,8 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
             dwo += po[k] * a.dist[static_cast<long long>(e) * dof + k];
             dwn += pn[k] * a.dist[static_cast<long long>(eo) * dof + k];
           }
-        gen_visc_flux(a.phys, u1, g1, radius, f1, first ? dwo : dwn);
-        gen_visc_flux(a.phys, u2, g2, radius, f2, first ? dwn : dwo);
+        gen_visc_flux(ph, u1, g1, radius, f1, first ? dwo : dwn);
+        gen_visc_flux(ph, u2, g2, radius, f2, first ? dwn : dwo);
         for (int eq = 0; eq < neq; eq++) {
           double v = 0;
           for (int d = 0; d < dim; d++) v += (-0.5 * (f1[eq + d * neq] + f2[eq + d * neq])) * nor[d];
@@ -550,7 +568,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         }
       }
       // elvect1 -= phi1 Fhat w ; elvect2 += phi2 Fhat w ; axisymmetric: fluxN *= radius (face_integrator.cpp:344-350)
-      const double sg = (first ? -1.0 : 1.0) * (a.phys.axisym ? a.wF[q] * radius : a.wF[q]);
+      const double sg = (first ? -1.0 : 1.0) * (ph.axisym ? a.wF[q] * radius : a.wF[q]);
       for (int eq = 0; eq < neq; eq++) dstq[eq] = sg * fx[eq];
     }
   }
@@ -571,7 +589,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     sZ[j * neq + eq] = acc;
   }
   __syncthreads();
-  gen_apply_minv(a, a.phys.axisym ? a.me_inv_rad : a.me_inv, e, sZ, neq, a.y, N);
+  gen_apply_minv(a, ph.axisym ? a.me_inv_rad : a.me_inv, e, sZ, neq, a.y, N);
 }
 
 // SourceTerm::updateTerms (source_term.cpp:62-255): node-wise plasma sources added to y AFTER Me^-1

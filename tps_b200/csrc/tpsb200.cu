@@ -1547,6 +1547,15 @@ static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
 // One CTA per element; the per-point loops have max(dof, nqv) independent items (9 / 16 on a p = 2 quadrilateral), and
 // the kernels hold 96-128 registers per thread: sizing the CTA to the element instead of a fixed 128 threads keeps
 // 2-4x more elements resident per SM (C1, 25 600 quads: 4.6 -> see DESIGN.md ms per evaluation).
+// dry-air size combinations with compile-time instantiations of the generic kernels: 1 planar 2-D, 2 axisymmetric, 3 3-D
+static int gen_specialisation(const GenArgs &g) {
+  static const bool off = getenv("TPSB_GEN_SPEC") && atoi(getenv("TPSB_GEN_SPEC")) == 0;
+  if (off || g.phys.fluid) return 0;
+  if (g.dim == 2 && g.nvel == 2 && g.neq == 4) return 1;
+  if (g.dim == 2 && g.nvel == 3 && g.neq == 5) return 2;
+  if (g.dim == 3 && g.nvel == 3 && g.neq == 5) return 3;
+  return 0;
+}
 static int gen_block_threads(const GenArgs &g) {
   static const int forced = getenv("TPSB_GEN_THREADS") ? atoi(getenv("TPSB_GEN_THREADS")) : 0;
   if (forced >= 32 && forced <= 128) return (forced / 32) * 32;
@@ -1564,8 +1573,18 @@ static int run_gradients_generic(tpsb_ctx *ctx, const double *d_x, bool prims_do
   {
     ProfScope ps(c, K_GRAD);
     const size_t smem = gen_grad_smem(g);
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    gen_grad_kernel<<<g.NE, gen_block_threads(g), smem, c->stream>>>(g);
+    const int spec = gen_specialisation(g);
+#define GEN_LAUNCH_GRAD(D, V, Q)                                                                                          \
+  do {                                                                                                                    \
+    if (smem > 48 * 1024)                                                                                                 \
+      CU(cudaFuncSetAttribute(gen_grad_kernel<D, V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    gen_grad_kernel<D, V, Q><<<g.NE, gen_block_threads(g), smem, c->stream>>>(g);                                       \
+  } while (0)
+    if (spec == 1) GEN_LAUNCH_GRAD(2, 2, 4);
+    else if (spec == 2) GEN_LAUNCH_GRAD(2, 3, 5);
+    else if (spec == 3) GEN_LAUNCH_GRAD(3, 3, 5);
+    else GEN_LAUNCH_GRAD(0, 0, 0);
+#undef GEN_LAUNCH_GRAD
   }
   CU(cudaGetLastError());
   return TPSB_OK;
@@ -1582,8 +1601,18 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   {
     ProfScope ps(c, K_RESID);
     const size_t smem = gen_resid_smem(g);
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(gen_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    gen_resid_kernel<<<g.NE, gen_block_threads(g), smem, c->stream>>>(g);
+    const int spec = gen_specialisation(g);
+#define GEN_LAUNCH_RESID(D, V, Q)                                                                                          \
+  do {                                                                                                                     \
+    if (smem > 48 * 1024)                                                                                                  \
+      CU(cudaFuncSetAttribute(gen_resid_kernel<D, V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    gen_resid_kernel<D, V, Q><<<g.NE, gen_block_threads(g), smem, c->stream>>>(g);                                       \
+  } while (0)
+    if (spec == 1) GEN_LAUNCH_RESID(2, 2, 4);
+    else if (spec == 2) GEN_LAUNCH_RESID(2, 3, 5);
+    else if (spec == 3) GEN_LAUNCH_RESID(3, 3, 5);
+    else GEN_LAUNCH_RESID(0, 0, 0);
+#undef GEN_LAUNCH_RESID
   }
   if (g.phys.fluid) {  // forcing terms are added after Me^-1 (rhs_operator.cpp:451-461)
     ProfScope ps(c, K_RESID);
