@@ -239,10 +239,11 @@ int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U);
 int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance);
 
 /* Test hook, host only: the static chunk schedule tpsb_rhs_mult_host uses to overlap copy-in / kernels / copy-out on a
- * single-rank mesh without boundary faces.  elem_begin / face_begin: chunks + 1 entries; ops: (kind, chunk) pairs, kind
- * 0 copy-in + primitives, 1 gradient, 2 face fluxes of the chunk's face range, 3 residual + copy-out.               */
-int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *elem_begin, int *face_begin, int *ops,
-                                  int max_ops, int *num_ops);
+ * single-rank 3-D mesh.  elem_begin / face_begin (two-sided faces, in their order) / bdr_begin (boundary faces, in their
+ * order; may be NULL): chunks + 1 entries; ops: (kind, chunk) pairs, kind 0 copy-in + primitives, 1 gradient, 2 face
+ * fluxes of the chunk's two-sided and boundary face ranges, 3 residual + copy-out.                                   */
+int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *elem_begin, int *face_begin, int *bdr_begin,
+                                  int *ops, int max_ops, int *num_ops);
 
 /* Chemistry::setGridFunctionRates (src/chemistry.cpp:133-140): the externally computed rate coefficients of the
  * GRIDFUNCTION_RXN reactions, d_rates[component][N] in DEVICE memory (byNODES), valid until replaced; NULL: those

@@ -68,5 +68,37 @@ def test_unchunkable_inputs_are_refused(lib_built):
     m = tps_b200.cartesian_hex_mesh(3, 3, 3)
     assert tps_b200.host_pipe_schedule(m, 2) is None      # fewer than 3 chunks: not worth a pipeline
     assert tps_b200.host_pipe_schedule(m, 28) is None     # more chunks than elements
-    mb = tps_b200.cartesian_hex_mesh(3, 3, 3, periodic=(0, 0, 0))
-    assert tps_b200.host_pipe_schedule(mb, 3) is None     # boundary faces: the pipeline serves periodic meshes only
+
+
+@pytest.mark.parametrize("n,periodic,chunks", [((4, 4, 6), (0, 0, 0), 5), ((5, 3, 8), (1, 0, 1), 8), ((3, 3, 3), (0, 0, 0), 3)])
+def test_schedule_with_boundary_faces(lib_built, n, periodic, chunks):
+    """Boundary faces (BCintegrator) ride in the face range of their element's chunk: every chunk's residual comes after
+    the face op of each chunk holding one of its two-sided faces and after its own boundary-face range."""
+    m = tps_b200.cartesian_hex_mesh(*n, periodic=periodic)
+    sched = tps_b200.host_pipe_schedule(m, chunks, with_bdr=True)
+    assert sched is not None
+    eb, fb, ops, bb = sched
+    el1, el2 = np.asarray(m["face_el1"]), np.asarray(m["face_el2"])
+    two = np.flatnonzero(el2 >= 0)
+    bdr = np.flatnonzero(el2 < 0)
+    assert fb[-1] == len(two) and bb[-1] == len(bdr) and len(bdr) > 0
+    chunk_of = lambda e: int(np.searchsorted(eb, e, side="right") - 1)
+    for k, f in enumerate(bdr):  # boundary face k sits in the boundary range of its element's chunk
+        assert bb[chunk_of(el1[f])] <= k < bb[chunk_of(el1[f]) + 1]
+    need = [set() for _ in range(chunks)]
+    for i, f in enumerate(two):
+        cf = int(np.searchsorted(fb, i, side="right") - 1)
+        assert cf == chunk_of(el1[f])
+        need[chunk_of(el1[f])].add(cf), need[chunk_of(el2[f])].add(cf)
+    for f in bdr:
+        need[chunk_of(el1[f])].add(chunk_of(el1[f]))
+    faced, graded = set(), set()
+    for kind, c in ops:
+        if kind == 1:
+            graded.add(c)
+        elif kind == 2:
+            assert c in graded
+            faced.add(c)
+        elif kind == 3:
+            assert need[c] <= faced, (c, need[c], faced)
+    assert {c for k, c in ops if k == 3} == set(range(chunks))

@@ -235,7 +235,7 @@ def lib():
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_set_solution_view.argtypes = [vp, vp]
     L.tpsb_set_distance_field.argtypes = [vp, vp]
-    L.tpsb_debug_host_pipe_schedule.argtypes = [C.POINTER(MeshMaps), C.c_int, ip, ip, ip, C.c_int, C.POINTER(C.c_int)]
+    L.tpsb_debug_host_pipe_schedule.argtypes = [C.POINTER(MeshMaps), C.c_int, ip, ip, ip, ip, C.c_int, C.POINTER(C.c_int)]
     L.tpsb_set_reaction_rate_field.argtypes = [vp, vp, C.c_int]
     L.tpsb_get_mean_time_derivatives.argtypes = [vp, vp, dp]
     L.tpsb_ode_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int]
@@ -361,19 +361,20 @@ def cylinder_ogrid_mesh(nr, nth, nz, r_in=0.5, r_out=10.0, lz=2.0, stretch=1.08,
     return m
 
 
-def host_pipe_schedule(mesh, chunks):
+def host_pipe_schedule(mesh, chunks, with_bdr=False):
     """Test hook: (elem_begin, face_begin, [(kind, chunk), ...]) of the chunked host-buffer pipeline, or None when the
     mesh cannot be chunked (tpsb_debug_host_pipe_schedule; host only)."""
     L = lib()
     xyz = np.ascontiguousarray(mesh["elem_xyz"], dtype=np.float64)
     arr = [np.ascontiguousarray(mesh[k], dtype=np.int32) for k in ("face_el1", "face_el2", "face_inf1", "face_inf2")]
     maps = MeshMaps(xyz.shape[2], xyz.shape[0], 0, _dp(xyz), len(arr[0]), _ip(arr[0]), _ip(arr[1]), _ip(arr[2]), _ip(arr[3]), None)
-    eb, fb = np.zeros(chunks + 1, np.int32), np.zeros(chunks + 1, np.int32)
+    eb, fb, bb = (np.zeros(chunks + 1, np.int32) for _ in range(3))
     ops, n = np.zeros(2 * 8 * max(chunks, 1), np.int32), C.c_int(0)
-    rc = L.tpsb_debug_host_pipe_schedule(C.byref(maps), chunks, _ip(eb), _ip(fb), _ip(ops), len(ops) // 2, C.byref(n))
+    rc = L.tpsb_debug_host_pipe_schedule(C.byref(maps), chunks, _ip(eb), _ip(fb), _ip(bb), _ip(ops), len(ops) // 2, C.byref(n))
     if rc != 0:
         return None
-    return eb, fb, [(int(ops[2 * k]), int(ops[2 * k + 1])) for k in range(n.value)]
+    sched = (eb, fb, [(int(ops[2 * k]), int(ops[2 * k + 1])) for k in range(n.value)])
+    return sched + (bb,) if with_bdr else sched
 
 
 def ref_tables(order):

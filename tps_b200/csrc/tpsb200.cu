@@ -77,7 +77,7 @@ struct tpsb_ctx {
     int kind, chunk;  // 0 prim (after the chunk's copy landed), 1 gradient, 2 face fluxes, 3 residual + copy out
   };
   int pipe_chunks = 0;
-  std::vector<int> pipe_eb, pipe_fb;  // element / face range of each chunk
+  std::vector<int> pipe_eb, pipe_fb, pipe_bb;  // element / two-sided face / boundary face range of each chunk
   std::vector<PipeOp> pipe_ops;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_out;
@@ -599,12 +599,16 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
 // the elements).  A chunk's gradient needs the primitives of its face neighbours' chunks, a face range the trace
 // blocks of both sides' chunks, a chunk's residual the face residuals of all its faces; the op list below is the
 // greedy order in which those become available while the chunks arrive 0, 1, 2, ...
+// bdr_el1: elements of the boundary faces (face-residual slots NFint + k), in slot order; a boundary face belongs to the
+// face range of its element's chunk and needs that chunk's gradient only.
 bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
-                        const std::vector<int> &fl_el1, const std::vector<int> &fl_el2, std::vector<int> &eb, std::vector<int> &fb,
-                        std::vector<tpsb_ctx::PipeOp> &ops) {
+                        const std::vector<int> &fl_el1, const std::vector<int> &fl_el2, const std::vector<int> &bdr_el1,
+                        std::vector<int> &eb, std::vector<int> &fb, std::vector<int> &bb, std::vector<tpsb_ctx::PipeOp> &ops) {
   if (C < 3 || C > 64 || C > NE) return false;
+  const int NB = static_cast<int>(bdr_el1.size());
   eb.assign(C + 1, 0);
   fb.assign(C + 1, NFint);
+  bb.assign(C + 1, NB);
   for (int k = 0; k <= C; k++) eb[k] = static_cast<int>(static_cast<long long>(NE) * k / C);
   auto chunk_of = [&](int e) { return static_cast<int>(std::upper_bound(eb.begin(), eb.end(), e) - eb.begin()) - 1; };
   fb[0] = 0;
@@ -615,6 +619,14 @@ bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_el
     while (cur < cf) fb[++cur] = f;
   }
   while (cur < C) fb[++cur] = NFint;
+  bb[0] = 0;
+  cur = 0;
+  for (int k = 0; k < NB; k++) {
+    const int cb = chunk_of(bdr_el1[k]);
+    if (cb < cur) return false;
+    while (cur < cb) bb[++cur] = k;
+  }
+  while (cur < C) bb[++cur] = NB;
   using mask = unsigned long long;
   std::vector<mask> need_prim(C, 0), need_grad(C, 0), need_face(C, 0);
   for (int e = 0; e < NE; e++) {
@@ -625,6 +637,8 @@ bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_el
       if (nb >= 0) need_prim[ce] |= mask(1) << chunk_of(nb);
       if (fc >= 0 && fc < NFint)
         need_face[ce] |= mask(1) << (static_cast<int>(std::upper_bound(fb.begin(), fb.end(), fc) - fb.begin()) - 1);
+      else if (fc >= NFint)
+        need_face[ce] |= mask(1) << ce;  // its own boundary faces
     }
   }
   for (int f = 0; f < NFint; f++) {
@@ -642,7 +656,7 @@ bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_el
         if (!(gradd >> g & 1) && (need_prim[g] & ~primd) == 0) ops.push_back({1, g}), gradd |= mask(1) << g, progress = true;
       for (int f = 0; f < C; f++)
         if (!(faced >> f & 1) && (need_grad[f] & ~gradd) == 0) {
-          if (fb[f + 1] > fb[f]) ops.push_back({2, f});
+          if (fb[f + 1] > fb[f] || bb[f + 1] > bb[f]) ops.push_back({2, f});
           faced |= mask(1) << f, progress = true;
         }
       for (int r = 0; r < C; r++)
@@ -654,16 +668,17 @@ bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_el
 }
 
 void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::vector<int> &el_face,
-                     const std::vector<int> &fl_el1, const std::vector<int> &fl_el2) {
+                     const std::vector<int> &fl_el1, const std::vector<int> &fl_el2, const std::vector<int> &bdr_el1) {
   int C = std::min(64, c->NE / 2048);
   if (const char *ev = getenv("TPSB_HOST_CHUNKS")) C = atoi(ev);
   C = std::min(C, 64);
-  std::vector<int> eb, fb;
+  std::vector<int> eb, fb, bb;
   std::vector<tpsb_ctx::PipeOp> ops;
-  if (!host_pipe_schedule(c->NE, c->NFint, C, nbr_elem, el_face, fl_el1, fl_el2, eb, fb, ops)) return;
+  if (!host_pipe_schedule(c->NE, c->NFint, C, nbr_elem, el_face, fl_el1, fl_el2, bdr_el1, eb, fb, bb, ops)) return;
   c->pipe_chunks = C;
   c->pipe_eb = eb;
   c->pipe_fb = fb;
+  c->pipe_bb = bb;
   c->pipe_ops = ops;
 }
 
@@ -1002,7 +1017,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     }
   }
 
-  if (c->fast && NEH == 0 && c->NFbdr == 0) build_host_pipe(c, nbr_elem, el_face, fl_el1, fl_el2);
+  if (NEH == 0) build_host_pipe(c, nbr_elem, el_face, fl_el1, fl_el2, b_el1);
 
   // ---- device allocations ----
   cudaError_t ce = cudaSetDevice(device);
@@ -1150,24 +1165,33 @@ void tpsb_destroy(tpsb_ctx *c) {
 
 // Test hook (host only, no device needed): the chunk schedule of the host-buffer pipeline for a single-rank mesh whose
 // faces are all two-sided.  ops = (kind, chunk) pairs: 0 copy-in + primitives, 1 gradient, 2 face range, 3 residual + copy-out.
-int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *elem_begin, int *face_begin, int *ops, int max_ops,
-                                  int *num_ops) {
+int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *elem_begin, int *face_begin, int *bdr_begin,
+                                  int *ops, int max_ops, int *num_ops) {
   if (!maps || maps->dim != 3 || !elem_begin || !face_begin || !ops || !num_ops) return TPSB_EINVAL;
   const int NE = maps->num_elems, NF = maps->num_faces;
-  std::vector<int> nbr(static_cast<size_t>(NE) * 6, -1), elf(static_cast<size_t>(NE) * 6, -1), e1(NF), e2(NF);
-  for (int f = 0; f < NF; f++) {
-    e1[f] = maps->face_el1[f], e2[f] = maps->face_el2[f];
-    if (e1[f] < 0 || e2[f] < 0 || e2[f] >= NE) return TPSB_EINVAL;
-    const int lf1 = maps->face_inf1[f] / 64, lf2 = maps->face_inf2[f] / 64;
-    nbr[static_cast<size_t>(e1[f]) * 6 + lf1] = e2[f], nbr[static_cast<size_t>(e2[f]) * 6 + lf2] = e1[f];
-    elf[static_cast<size_t>(e1[f]) * 6 + lf1] = f, elf[static_cast<size_t>(e2[f]) * 6 + lf2] = f;
+  std::vector<int> nbr(static_cast<size_t>(NE) * 6, -1), elf(static_cast<size_t>(NE) * 6, -1), e1, e2, b1, blf;
+  for (int f = 0; f < NF; f++) {  // two-sided faces keep their order; boundary faces (el2 < 0) follow as slots NFint + k
+    const int a1 = maps->face_el1[f], a2 = maps->face_el2[f];
+    if (a1 < 0 || a2 >= NE) return TPSB_EINVAL;
+    const int lf1 = maps->face_inf1[f] / 64;
+    if (a2 < 0) {
+      b1.push_back(a1), blf.push_back(lf1);
+      continue;
+    }
+    const int lf2 = maps->face_inf2[f] / 64, fc = static_cast<int>(e1.size());
+    nbr[static_cast<size_t>(a1) * 6 + lf1] = a2, nbr[static_cast<size_t>(a2) * 6 + lf2] = a1;
+    elf[static_cast<size_t>(a1) * 6 + lf1] = fc, elf[static_cast<size_t>(a2) * 6 + lf2] = fc;
+    e1.push_back(a1), e2.push_back(a2);
   }
-  std::vector<int> eb, fb;
+  const int NFint = static_cast<int>(e1.size());
+  for (size_t k = 0; k < b1.size(); k++) elf[static_cast<size_t>(b1[k]) * 6 + blf[k]] = NFint + static_cast<int>(k);
+  std::vector<int> eb, fb, bb;
   std::vector<tpsb_ctx::PipeOp> po;
-  if (!host_pipe_schedule(NE, NF, chunks, nbr, elf, e1, e2, eb, fb, po)) return TPSB_ENOTIMPL;
+  if (!host_pipe_schedule(NE, NFint, chunks, nbr, elf, e1, e2, b1, eb, fb, bb, po)) return TPSB_ENOTIMPL;
   if (static_cast<int>(po.size()) > max_ops) return TPSB_EINVAL;
   std::copy(eb.begin(), eb.end(), elem_begin);
   std::copy(fb.begin(), fb.end(), face_begin);
+  if (bdr_begin) std::copy(bb.begin(), bb.end(), bdr_begin);
   for (size_t k = 0; k < po.size(); k++) ops[2 * k] = po[k].kind, ops[2 * k + 1] = po[k].chunk;
   *num_ops = static_cast<int>(po.size());
   return TPSB_OK;
@@ -1247,20 +1271,20 @@ static void launch_face(tpsb_ctx *c, const KernelArgs &a, int begin, int count) 
     face_flux_kernel<NP, FPB, NTF, false, false><<<(count + FPB - 1) / FPB, NTF, 0, c->stream>>>(a, begin, count, nullptr);
 }
 // boundary faces: BCintegrator (src/BCintegrator.cpp:295-441), same kernel in one-sided mode
-static void bdr_faces(tpsb_ctx *c, const KernelArgs &a) {
-  const int count = c->NFbdr;
+static void bdr_faces(tpsb_ctx *c, const KernelArgs &a, int begin = 0, int count = -1) {
+  if (count < 0) count = c->NFbdr;
   if (count <= 0) return;
   ProfScope ps(c, K_FACE);
   const bool mod = (c->phys.sgs_model | c->phys.sponge) != 0;
   if (c->np == 4) {
-    if (mod) face_flux_kernel<4, 4, 160, true, true><<<(count + 3) / 4, 160, 0, c->stream>>>(a, 0, count, nullptr);
-    else face_flux_kernel<4, 4, 160, true, false><<<(count + 3) / 4, 160, 0, c->stream>>>(a, 0, count, nullptr);
+    if (mod) face_flux_kernel<4, 4, 160, true, true><<<(count + 3) / 4, 160, 0, c->stream>>>(a, begin, count, nullptr);
+    else face_flux_kernel<4, 4, 160, true, false><<<(count + 3) / 4, 160, 0, c->stream>>>(a, begin, count, nullptr);
   } else if (c->np == 3) {
-    if (mod) face_flux_kernel<3, 4, 128, true, true><<<(count + 3) / 4, 128, 0, c->stream>>>(a, 0, count, nullptr);
-    else face_flux_kernel<3, 4, 128, true, false><<<(count + 3) / 4, 128, 0, c->stream>>>(a, 0, count, nullptr);
+    if (mod) face_flux_kernel<3, 4, 128, true, true><<<(count + 3) / 4, 128, 0, c->stream>>>(a, begin, count, nullptr);
+    else face_flux_kernel<3, 4, 128, true, false><<<(count + 3) / 4, 128, 0, c->stream>>>(a, begin, count, nullptr);
   } else {
-    if (mod) face_flux_kernel<2, 8, 128, true, true><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
-    else face_flux_kernel<2, 8, 128, true, false><<<(count + 7) / 8, 128, 0, c->stream>>>(a, 0, count, nullptr);
+    if (mod) face_flux_kernel<2, 8, 128, true, true><<<(count + 7) / 8, 128, 0, c->stream>>>(a, begin, count, nullptr);
+    else face_flux_kernel<2, 8, 128, true, false><<<(count + 7) / 8, 128, 0, c->stream>>>(a, begin, count, nullptr);
   }
 }
 template <int NP, int EPB, int MINB = 1>
@@ -1665,7 +1689,7 @@ static int ensure_work(tpsb_ctx *ctx, double **p) {
   return TPSB_OK;
 }
 
-// tpsb_rhs_mult_host on the periodic single-rank fast path: the evaluation is PCIe-bound (2 x 40 B per node against
+// tpsb_rhs_mult_host on a single rank (3-D dry-air paths, with or without boundary faces): the evaluation is PCIe-bound (2 x 40 B per node against
 // ~0.23 ns of kernel time per node), so the three legs are overlapped chunk by chunk -- copies in on s_in, kernels on
 // the context stream in the order of ctx->pipe_ops, copies out on s_out (PCIe is full duplex).  Same kernels, same
 // per-element arithmetic: the result is bit-identical to tpsb_rhs_mult.
@@ -1729,8 +1753,15 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
         prim_range_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, c->stream>>>(a, static_cast<long long>(e0) * c->nd, cnt);
         break;
       }
-      case 1: grad_trace(c, a, e0, ne, nullptr); break;
-      case 2: face_fast(c, a, c->pipe_fb[k], c->pipe_fb[k + 1] - c->pipe_fb[k]); break;
+      case 1:
+        if (c->fast) grad_trace(c, a, e0, ne, nullptr);
+        else grad(c, a, e0, ne, nullptr);
+        break;
+      case 2:
+        if (c->fast) face_fast(c, a, c->pipe_fb[k], c->pipe_fb[k + 1] - c->pipe_fb[k]);
+        else face(c, a, c->pipe_fb[k], c->pipe_fb[k + 1] - c->pipe_fb[k]);
+        bdr_faces(c, a, c->pipe_bb[k], c->pipe_bb[k + 1] - c->pipe_bb[k]);  // BCintegrator faces of this chunk's elements
+        break;
       default: {
         resid(c, a, e0, ne);
         CU(cudaEventRecord(c->ev_out[k], c->stream));
