@@ -182,6 +182,10 @@ def workload_config(args, grid, sample_n=None):
            "elements_per_gpu": f"{n}^3", "global_elements": f"{n * grid[0]}x{n * grid[1]}x{n * grid[2]}",
            "order": 3, "num_equation": 5, "rank_grid": "x".join(map(str, grid)),
            "l2_policy": "inputs (2.3 GB per state vector at 96^3) exceed the 126 MB L2; no flush needed"}
+    if getattr(args, "strong", 0):
+        g = args.strong
+        cfg["elements_per_gpu"] = f"{g // grid[0]}x{g // grid[1]}x{g // grid[2]}"
+        cfg["global_elements"] = f"{g}x{g}x{g}"
     if sample_n is not None:
         cfg["cpu_sample_elements"] = f"{sample_n}^3"
     return cfg
@@ -196,6 +200,9 @@ def main():
     ap.add_argument("--n", type=int, default=96, help="elements per direction per GPU")
     ap.add_argument("--cpu-n", type=int, default=20, help="elements per direction of the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--strong", type=int, default=0, metavar="G",
+                    help="strong scaling: a fixed global G^3 box split over the ranks (SURVEY.md 8d: 128); "
+                         "default 0 = weak scaling with --n elements per direction per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="tgv", choices=["tgv", "cyl3d"],
                     help="tgv: BASELINE config C5 (the headline line); cyl3d: config C2 restated on a hex O-grid "
@@ -250,6 +257,10 @@ def main():
     gn = (n * grid[0], n * grid[1], n * grid[2])
     lo = tuple(-PI * g for g in grid)
     hi = tuple(PI * g for g in grid)
+    if args.strong:  # fixed global box: the per-rank block shrinks with the rank grid
+        assert all(args.strong % g == 0 for g in grid), "global size must divide by the rank grid"
+        gn = (args.strong,) * 3
+        lo, hi = (-PI,) * 3, (PI,) * 3
     phys = tps_b200.Physics.dry_air(1, tgv_visc_mult())
     t_setup = time.perf_counter()
     if args.workload == "cyl3d":
@@ -261,9 +272,9 @@ def main():
                                   bcs=[tps_b200.BcDesc.make(*b) for b in specs])
         NE = 4 * n ** 3
     elif world == 1:
-        mesh = tps_b200.cartesian_hex_mesh(n, n, n, lo=lo, hi=hi, order_mode=1)
+        mesh = tps_b200.cartesian_hex_mesh(gn[0], gn[1], gn[2], lo=lo, hi=hi, order_mode=1)
         op = tps_b200.RhsOperator(mesh, order=3, physics=phys, device=local_rank)
-        NE = n ** 3
+        NE = gn[0] * gn[1] * gn[2]
     else:
         mesh = tps_b200.cartesian_hex_partition(gn, grid, rank, lo=lo, hi=hi, order_mode=1)
         halo = tps_b200.make_halo_desc(mesh, comm)
@@ -407,7 +418,8 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, grid),
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "finite": finite, "setup_s": t_setup, "dofs_per_gpu": N,
