@@ -33,8 +33,8 @@ B_PER_DOF = 360.0  # 8*neq*(3+2*dim): U + write gradUp + U + gradUp + write dU/d
 # algorithmic bytes per DOF for each kernel class ("kernels and rooflines")
 KERNEL_BYTES = {"prim": 80.0, "grad": 160.0, "face_flux": 160.0, "elem_resid": 200.0}
 # DRAM bytes per DOF (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of each fast-path kernel, from the
-# `ncu --set full` capture summarised in profiles/r1p_ncu_full_summary.txt (TGV 64^3, 16.8 M DG nodes)
-NCU_DRAM_BYTES_PER_DOF = {"prim": 77.3, "grad": 335.3, "face_flux": 151.4, "elem_resid": 209.2}
+# `ncu --set full` capture summarised in profiles/r1q_ncu_full_summary.txt (TGV 64^3, 16.8 M DG nodes)
+NCU_DRAM_BYTES_PER_DOF = {"prim": 77.1, "grad": 347.5, "face_flux": 151.3, "elem_resid": 211.0}
 PROC_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 PI = float(np.pi)
 
@@ -372,7 +372,7 @@ def main():
     if args.workload == "tgv" and dom in NCU_DRAM_BYTES_PER_DOF:
         traffic = NCU_DRAM_BYTES_PER_DOF[dom] * N / dom_launches_per_step  # bytes per launch, like `achieved`
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1p_ncu_full_summary.txt (ncu --set full, bytes/DOF x DOFs of this launch)",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1q_ncu_full_summary.txt (ncu --set full, bytes/DOF x DOFs of this launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes_per_launch, "launch_ms": per_launch[dom],
                 "kernel_share_of_step": per_step[dom] / sum(per_step.values()),
