@@ -77,7 +77,8 @@ def argon6_primitives(xy, nvel=3, seed=20261018):
     return up * (1 + 0.01 * rng.uniform(-1, 1, up.shape))
 
 
-def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None, gpu=True, kind=None, mixing_length=None):
+def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None, gpu=True, kind=None, mixing_length=None,
+              want_oracle=True):
     """(RhsOperator or None, Oracle) on mesh m with boundary-condition set bc_kind.
     mixing_length = (max-mixing-length, Pr_ratio, bulk-multiplier): flow/useMixingLength (reference back end)."""
     nsp_in = ()
@@ -98,9 +99,11 @@ def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None,
         phys_g.with_mixing_length(*mixing_length)
         phys_o.use_mixing_length = 1
         phys_o.max_mixing_length, phys_o.mixing_length_Prt, phys_o.mixing_length_bulk_mult = mixing_length
-    orc = oracle_api.Oracle(order, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
-                            phys=phys_o, kind=kind, basis_type=bt, int_rule=ir, neq=neq, nvel=nvel)
-    if specs:
+    orc = None
+    if want_oracle:
+        orc = oracle_api.Oracle(order, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                                phys=phys_o, kind=kind, basis_type=bt, int_rule=ir, neq=neq, nvel=nvel)
+    if specs and orc is not None:
         orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], use_bc_in_grad)
     op = None
     if gpu:
