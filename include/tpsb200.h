@@ -263,6 +263,16 @@ int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out);
  * scheme 1 ForwardEuler, 2 RK2(1.0), 3 RK3SSP, 4 RK4.  d_U is advanced in place nsteps times with a
  * constant dt, stage vectors stay on the device.                                                   */
 int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps);
+/* hmin of M2ulPhyS (src/M2ulPhyS.cpp:756-761): min over all elements (all ranks) of Mesh::GetElementSize(e, 1).   */
+int tpsb_get_hmin(tpsb_ctx *ctx, double *hmin);
+/* M2ulPhyS::Check_NAN (src/M2ulPhyS.cpp:2463-2519) and Check_Undershoot (:2526-2549) of a device solution vector:
+ * *num_nan = NaN entries over all ranks; mixtures: negative active-species densities are set to zero in place.     */
+int tpsb_check_state(tpsb_ctx *ctx, double *d_U, int *num_nan);
+/* M2ulPhyS::solveStep without the I/O (src/M2ulPhyS.cpp:2004-2016): one ODESolver::Step on the device solution vector,
+ * Check_NAN (:2463-2519; *num_nan = NaN entries over all ranks), Check_Undershoot for mixtures (:2526-2549: active
+ * species densities clamped at 0) and, when cfl > 0, the next adaptive time step
+ * *dt_next = cfl * hmin / max_char_speed / dim (:2013-2016); cfl <= 0: constant time step, *dt_next = dt.         */
+int tpsb_solve_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, double cfl, int *num_nan, double *dt_next);
 
 /* Index maps derived at create, in the layout of the reference's precomputedIntegrationData
  * (src/dataStructures.hpp:297-517) -- exported so they can be compared bit-for-bit.

@@ -196,7 +196,7 @@ class PartSizes(C.Structure):
 EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tpsb_num_dofs", "tpsb_num_equation",
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
-           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
+           "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_get_hmin", "tpsb_solve_step", "tpsb_check_state", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy"]
 
 
@@ -235,6 +235,9 @@ def lib():
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_set_solution_view.argtypes = [vp, vp]
     L.tpsb_set_distance_field.argtypes = [vp, vp]
+    L.tpsb_get_hmin.argtypes = [vp, dp]
+    L.tpsb_check_state.argtypes = [vp, vp, ip]
+    L.tpsb_solve_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_double, ip, dp]
     L.tpsb_debug_host_pipe_schedule.argtypes = [C.POINTER(MeshMaps), C.c_int, ip, ip, ip, ip, C.c_int, C.POINTER(C.c_int)]
     L.tpsb_set_reaction_rate_field.argtypes = [vp, vp, C.c_int]
     L.tpsb_get_mean_time_derivatives.argtypes = [vp, vp, dp]
@@ -576,6 +579,23 @@ class RhsOperator:
     def ode_step(self, U, dt, scheme=4, nsteps=1):
         self._chk(self.L.tpsb_ode_step(self.ctx, U.data_ptr(), dt, scheme, nsteps), "tpsb_ode_step")
         return U
+
+    def hmin(self):
+        out = C.c_double(0.0)
+        self._chk(self.L.tpsb_get_hmin(self.ctx, C.byref(out)), "tpsb_get_hmin")
+        return out.value
+
+    def check_state(self, U):
+        """Check_NAN + Check_Undershoot: number of NaN entries; mixtures get negative species densities clamped."""
+        nan = C.c_int(0)
+        self._chk(self.L.tpsb_check_state(self.ctx, U.data_ptr(), C.byref(nan)), "tpsb_check_state")
+        return nan.value
+
+    def solve_step(self, U, dt, scheme=4, cfl=0.0):
+        """M2ulPhyS::solveStep without the I/O: (number of NaN entries, next time step)."""
+        nan, nxt = C.c_int(0), C.c_double(0.0)
+        self._chk(self.L.tpsb_solve_step(self.ctx, U.data_ptr(), dt, scheme, cfl, C.byref(nan), C.byref(nxt)), "tpsb_solve_step")
+        return nan.value, nxt.value
 
     def element_to_faces(self):
         out = np.zeros(7 * self.NE, dtype=np.int32)

@@ -36,6 +36,8 @@ struct tpsb_ctx {
   std::vector<int> element_to_faces;  // reference layout, stride 7
   // device tables
   double *d_vx = nullptr, *d_elem_delta = nullptr;
+  double hmin = 0.0;            // min element size h_min over the local elements (adaptive time step)
+  int *d_nan_count = nullptr;   // tpsb_solve_step: NaN counter
   int *d_nbr_elem = nullptr, *d_nbr_code = nullptr, *d_face_el1 = nullptr, *d_face_el2 = nullptr,
       *d_face_inf1 = nullptr, *d_face_inf2 = nullptr, *d_el_face = nullptr, *d_el_face_code = nullptr;
   int *d_elem_list = nullptr;  // interior elements first, then elements touching a shared face
@@ -190,6 +192,14 @@ static double hex_min_size(const double *v) {
   double m = 1e300;
   for (int j = 0; j < 3; j++) m = std::min(m, std::sqrt(J[0][j] * J[0][j] + J[1][j] * J[1][j] + J[2][j] * J[2][j]));
   return m;
+}
+
+// the same for a bilinear quadrilateral: smaller singular value of the 2 x 2 centre Jacobian, closed form
+static double quad_min_size(const double *v) {
+  const double a = 0.5 * ((v[2] - v[0]) + (v[4] - v[6])), c = 0.5 * ((v[3] - v[1]) + (v[5] - v[7]));  // d x / d xi
+  const double b = 0.5 * ((v[6] - v[0]) + (v[4] - v[2])), d = 0.5 * ((v[7] - v[1]) + (v[5] - v[3]));  // d x / d eta
+  const double s1 = std::hypot(a + d, c - b), s2 = std::hypot(a - d, c + b);  // sigma_max,min = (s1 +- s2) / 2
+  return 0.5 * std::fabs(s1 - s2);
 }
 
 static bool element_is_affine(const double *v) {
@@ -837,6 +847,12 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   c->phys.cp_div_pr = phys->specific_heat_ratio * phys->gas_constant /
                       (phys->sutherland_Pr * (phys->specific_heat_ratio - 1.));
 
+  // hmin = min over the local elements of Mesh::GetElementSize(e, 1) (src/M2ulPhyS.cpp:756-761): the adaptive time step
+  c->hmin = 1.0e18;
+  for (int e = 0; e < c->NE; e++)
+    c->hmin = std::min(c->hmin, maps->dim == 3 ? hex_min_size(&maps->elem_vertices[static_cast<size_t>(e) * 24])
+                                               : quad_min_size(&maps->elem_vertices[static_cast<size_t>(e) * 8]));
+
   if (want_generic) {
     c->generic = true;
     c->dim = maps->dim;
@@ -1141,7 +1157,8 @@ void tpsb_destroy(tpsb_ctx *c) {
                   c->d_faceRes,  c->d_Uhalo,     c->d_UpHalo,       c->d_gradUpHalo, c->d_sendU,   c->d_sendG,
                   c->d_maxBits,  c->d_mcs,       c->d_send_elems,   c->d_k,        c->d_yv,       c->d_z,
                   c->d_hx,       c->d_hy,        c->d_geo,          c->d_tr,       c->d_face_nor, c->d_sendTr,
-                  c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc,   c->d_elem_delta};
+                  c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc,   c->d_elem_delta,
+                  c->d_nan_count};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (void *p : c->gen_allocs) cudaFree(p);
@@ -2080,6 +2097,76 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
   ctx->sol_view = saved_view;
   if (rc) return rc;
   CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+// M2ulPhyS::Check_NAN (src/M2ulPhyS.cpp:2463-2519: count the NaNs of the solution) and Check_Undershoot (:2526-2549:
+// active species densities clamped at zero, mixtures only) in one sweep over the solution vector
+static __global__ void check_state_kernel(long long N, int neq, int clamp_begin, int clamp_end, double *U, int *nan_count) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (n < N) {
+    for (int eq = 0; eq < neq; eq++) {
+      const double v = U[n + eq * N];
+      if (v != v) bad++;
+      if (eq >= clamp_begin && eq < clamp_end && v < 0.0) U[n + eq * N] = 0.0;  // max(v, 0): a NaN stays a NaN
+    }
+  }
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nan_count, bad);
+}
+
+int tpsb_get_hmin(tpsb_ctx *ctx, double *hmin) {
+  if (!ctx || !hmin) return TPSB_EINVAL;
+  *hmin = ctx->hmin;
+  if (ctx->comm) {  // MPI_Allreduce(MIN) of src/M2ulPhyS.cpp:761
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->d_mcs, hmin, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NC(ncclAllReduce(ctx->d_mcs, ctx->d_mcs, 1, ncclDouble, ncclMin, ctx->comm, ctx->stream));
+    CU(cudaMemcpyAsync(hmin, ctx->d_mcs, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return TPSB_OK;
+}
+
+// tpsb_check_state: Check_NAN + Check_Undershoot of one solution vector.
+// M2ulPhyS::solveStep (src/M2ulPhyS.cpp:2004-2016) without the I/O: one ODESolver::Step, Check_NAN, Check_Undershoot
+// for mixtures, and -- when cfl > 0 -- the next adaptive time step CFL hmin / max_char_speed / dim with the
+// characteristic speed of the step's last stage, reduced over the ranks.  cfl <= 0: constant time step, *dt_next = dt.
+int tpsb_check_state(tpsb_ctx *ctx, double *d_U, int *num_nan) {
+  if (!ctx || !d_U) return TPSB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->d_nan_count) CU(cudaMalloc(&ctx->d_nan_count, sizeof(int)));
+  CU(cudaMemsetAsync(ctx->d_nan_count, 0, sizeof(int), ctx->stream));
+  int cb = 0, ce = 0;
+  if (ctx->generic && ctx->gen.phys.fluid) {
+    cb = ctx->gen.nvel + 2;
+    ce = cb + (ctx->mix_host.ambipolar ? ctx->mix_host.numSpecies - 2 : ctx->mix_host.numSpecies - 1);
+  }
+  check_state_kernel<<<static_cast<unsigned>((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(ctx->N, ctx->neq, cb, ce, d_U, ctx->d_nan_count);
+  ctx->launches++;
+  if (ctx->comm) NC(ncclAllReduce(ctx->d_nan_count, ctx->d_nan_count, 1, ncclInt, ncclSum, ctx->comm, ctx->stream));
+  int count = 0;
+  CU(cudaMemcpyAsync(&count, ctx->d_nan_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (num_nan) *num_nan = count;
+  return TPSB_OK;
+}
+
+int tpsb_solve_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, double cfl, int *num_nan, double *dt_next) {
+  if (!ctx || !d_U) return TPSB_EINVAL;
+  int rc = tpsb_ode_step(ctx, d_U, dt, scheme, 1);
+  if (rc) return rc;
+  if ((rc = tpsb_check_state(ctx, d_U, num_nan))) return rc;
+  if (dt_next) {
+    *dt_next = dt;
+    if (cfl > 0.0) {
+      double mcs = 0.0, hmin = 0.0;
+      if ((rc = tpsb_get_max_char_speed(ctx, &mcs))) return rc;
+      if ((rc = tpsb_get_hmin(ctx, &hmin))) return rc;
+      *dt_next = cfl * hmin / mcs / static_cast<double>(ctx->dim);
+    }
+  }
   return TPSB_OK;
 }
 
