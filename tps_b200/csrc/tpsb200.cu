@@ -1100,7 +1100,14 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUpHalo, hb * NEQ * DIM);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendU, sb * NEQ);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendG, sb * NEQ * DIM);
-    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) {
+      // highest priority: the exchange kernels must get SM slots while the interior gradient / face kernels (hundreds of
+      // thousands of queued CTAs) run, or the "overlapped" exchange only starts when they drain
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      static const bool flat = getenv("TPSB_COMM_PRIO") && atoi(getenv("TPSB_COMM_PRIO")) == 0;
+      ce = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, flat ? prio_lo : prio_hi);
+    }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvU, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvG, cudaEventDisableTiming);
