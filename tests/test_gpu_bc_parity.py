@@ -162,3 +162,25 @@ def test_chunked_host_pipeline_with_boundary_conditions(lib_built, monkeypatch, 
     op.mult_host(hx, hy)
     assert np.array_equal(hy.numpy(), y_dev)
     assert np.isfinite(y_dev).all() and np.abs(y_dev).max() > 0
+
+
+def test_general_wall_in_3d_runs_on_the_generic_path(lib_built, oracle_built):
+    """WallType VISC_GNRL (independent heavy-species / electron thermal conditions, wallBC.cpp:512-543) is built on the
+    generic path: a 3-D dry-air Gauss-Legendre run that asks for it is routed there instead of being refused."""
+    import torch
+    m = tps_b200.cartesian_hex_mesh(3, 3, 3, lo=LO, hi=HI, periodic=(0, 0, 0))
+    attr = box_face_attrs(m, LO, HI)
+    m = warp_mesh(m, amp=0.1, lo=LO, hi=HI)
+    specs = [(1, 0, 2, (1.2, 25.0, 1.0, -2.0)), (2, 1, 0, (101300.0,)), (3, 2, 4, (1.0, 0.0, 310.0, 0.0)), (4, 2, 4, (0.0, 0.0, 0.0, 0.0)),
+             (5, 2, 0, ()), (6, 2, 3, (290.0,))]
+    op = tps_b200.RhsOperator(m, order=2, physics=tps_b200.Physics.dry_air(1, 4e3, 0.2), face_attr=attr,
+                              bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+    orc = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                            phys=oracle_api.dry_air_params(1, 4e3, 0.2))
+    orc.set_bcs(attr, [oracle_api.make_bc(*b) for b in specs], False)
+    U = tgv_state(orc.node_coords() * np.pi)
+    y = op.Mult(torch.from_numpy(U).cuda()).cpu().numpy()
+    yo = orc.mult(U)
+    N = orc.N
+    for k in range(5):
+        assert rel_l2(y[k * N:(k + 1) * N], yo[k * N:(k + 1) * N]) < 1e-10, k

@@ -757,6 +757,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
   }
   if (phys->use_mixing_length) want_generic = true;  // the mixing-length model lives on the generic path
+  for (int i = 0; bcs && bcs->bcs && i < bcs->num_bcs; i++)  // ... and so does the general wall (WallType VISC_GNRL)
+    if (bcs->bcs[i].kind == TPSB_BC_WALL && bcs->bcs[i].type == 4) want_generic = true;
   const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
   if (phys->sgs_model < 0 || phys->sgs_model > 2) return fail(ctx, TPSB_EINVAL, "sgs_model %d: 0 none, 1 smagorinsky, 2 sigma", phys->sgs_model);
   if (visc_mod && want_generic)
