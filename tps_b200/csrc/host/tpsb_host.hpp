@@ -109,6 +109,16 @@ class RHSoperator {
     check(tpsb_get_max_char_speed(ctx_, &v), "getMaxCharSpeed");
     return v;
   }
+  // the solution grid function U_ the forcing terms read (src/source_term.cpp:66) and the wall-distance grid function
+  // distance_ of the mixing-length model (src/M2ulPhyS.cpp:265-283); device vectors owned by the caller
+  void setSolutionView(const Vector *U) const { check(tpsb_set_solution_view(ctx_, U ? U->Read() : nullptr), "setSolutionView"); }
+  void setDistance(const Vector *d) const { check(tpsb_set_distance_field(ctx_, d ? d->Read() : nullptr), "setDistance"); }
+  // hmin of M2ulPhyS (src/M2ulPhyS.cpp:756-761)
+  double getMinElementSize() const {
+    double h = 0;
+    check(tpsb_get_hmin(ctx_, &h), "getMinElementSize");
+    return h;
+  }
   tpsb_ctx *context() const { return ctx_; }
 };
 
@@ -129,6 +139,18 @@ class ODESolver {
     f_->SetTime(t);
   }
 };
+// M2ulPhyS::solveStep without the I/O (src/M2ulPhyS.cpp:2004-2016): Step + Check_NAN + Check_Undershoot + adaptive dt.
+// cfl <= 0: constant time step.  Returns the number of NaN entries found (the reference aborts when it is non-zero).
+inline int solveStep(RHSoperator &rhs, int scheme, Vector &U, double &t, double &dt, double cfl) {
+  int nan = 0;
+  double next = dt;
+  const int rc = tpsb_solve_step(rhs.context(), U.ReadWrite(), dt, scheme, cfl, &nan, &next);
+  if (rc != TPSB_OK) throw std::runtime_error(std::string("solveStep: ") + tpsb_last_error(rhs.context()));
+  t += dt;
+  rhs.SetTime(t);
+  dt = next;
+  return nan;
+}
 struct ForwardEulerSolver : ODESolver { ForwardEulerSolver() : ODESolver(1) {} };
 struct RK2Solver : ODESolver { explicit RK2Solver(double /*a = 1.0*/ = 1.0) : ODESolver(2) {} };
 struct RK3SSPSolver : ODESolver { RK3SSPSolver() : ODESolver(3) {} };
