@@ -63,6 +63,15 @@ struct KernelArgs {
   int NFbdr;
   const int *bdr_el1, *bdr_lf, *bdr_bc;  // [NFbdr] element, local face, index into bct.bc
   BcTable bct;
+  // Runge-Kutta stage update fused into the residual kernel (tpsb_ode_step): with k = dU/dt of this evaluation,
+  // Y = X + A k and Z = (zacc ? Z : X) + B k are written instead of k itself (Y may be the vector being evaluated: a
+  // CTA reads only its own nodes of U and writes them last).  X == nullptr: plain Mult, y = k.
+  struct RkStage {
+    const double *X;
+    double *Y, *Z;
+    double A, B;
+    int zacc;
+  } rk;
 };
 
 // ---- geometry: trilinear hexahedron from its 8 vertices (mesh nodes of order 1) ----
@@ -136,7 +145,7 @@ template <int NP, int EPB, int MINB>
 __global__ void grad_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list);
 template <int NP, int FPB, int NT, bool BDR, bool MOD>
 __global__ void face_flux_kernel(KernelArgs a, int face_begin, int face_count, const int *face_list);
-template <int NP, int EPB, int MINB, bool AFF, bool MOD>
+template <int NP, int EPB, int MINB, bool AFF, bool MOD, bool RK>
 __global__ void elem_resid_kernel(KernelArgs a, int elem_begin, int elem_count);
 
 // y = x + a*k ; z = x + b*k  etc. for the ODE stages

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(NT) face_flux_kernel(KernelArgs a, int face_be
 // elem_resid_kernel: EPB elements per CTA, one thread per node.
 // AFF: every element is a parallelepiped (fast path): adj(J) and det come from the 12-double table a.geo
 // instead of being rebuilt per node from the 8 vertices (~250 flops per node saved).
-template <int NP, int EPB, int MINB, bool AFF = false, bool MOD = false>
+template <int NP, int EPB, int MINB, bool AFF = false, bool MOD = false, bool RK = false>
 __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(KernelArgs a, int elem_begin, int elem_count) {
   constexpr int ND = NP * NP * NP, NF2 = NP * NP;
   __shared__ double sG[EPB][NEQ][DIM][ND];
@@ -682,8 +682,17 @@ __global__ void __launch_bounds__(NP *NP *NP *EPB, MINB) elem_resid_kernel(Kerne
   // y = Me^-1 z, Me = diag(w |J|)   (rhs_operator.cpp:432-448)
   const double im = 1.0 / (wnode * det);
   const long long o = static_cast<long long>(e) * ND + n;
+  if constexpr (RK) {  // fused Runge-Kutta stage update (same FMAs the separate axpy kernel would issue)
 #pragma unroll
-  for (int eq = 0; eq < NEQ; eq++) a.y[o + eq * N] = z[eq] * im;
+    for (int eq = 0; eq < NEQ; eq++) {
+      const double ki = z[eq] * im, xi = a.rk.X[o + eq * N];
+      if (a.rk.Z) a.rk.Z[o + eq * N] = (a.rk.zacc ? a.rk.Z[o + eq * N] : xi) + a.rk.B * ki;
+      a.rk.Y[o + eq * N] = xi + a.rk.A * ki;
+    }
+  } else {
+#pragma unroll
+    for (int eq = 0; eq < NEQ; eq++) a.y[o + eq * N] = z[eq] * im;
+  }
 }
 
 __global__ void axpy2_kernel(long long n, const double *x, const double *k, double a, double *y, double b, double *z,

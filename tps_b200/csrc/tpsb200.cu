@@ -92,6 +92,7 @@ struct tpsb_ctx {
   double ode_dt = 0.0;
   int ode_scheme = 0;
   long long ode_launches = 0;
+  KernelArgs::RkStage rk = {nullptr, nullptr, nullptr, 0.0, 0.0, 0};  // stage update fused into the residual kernel
   long long launches = 0;
   int tune[3] = {0, 0, 0};
   int num_sms = 148, face_ctas_per_sm = 5;
@@ -1270,6 +1271,7 @@ static KernelArgs make_args(tpsb_ctx *c, const double *d_x, double *d_y) {
   a.bct = c->bct;
   a.geo = c->d_geo;
   a.elem_delta = c->d_elem_delta;
+  a.rk = c->rk;
   a.tr = c->d_tr;
   a.face_desc = c->d_face_desc;
   a.face_nor = c->d_face_nor;
@@ -1317,12 +1319,20 @@ template <int NP, int EPB, int MINB = 1>
 static void launch_resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (count <= 0) return;
   ProfScope ps(c, K_RESID);
-  if (c->fast)
-    elem_resid_kernel<NP, EPB, MINB, true, false><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
-  else if (c->phys.sgs_model | c->phys.sponge)
-    elem_resid_kernel<NP, EPB, MINB, false, true><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
-  else
-    elem_resid_kernel<NP, EPB, MINB, false, false><<<(count + EPB - 1) / EPB, NP * NP * NP * EPB, 0, c->stream>>>(a, begin, count);
+  const dim3 grid((count + EPB - 1) / EPB), block(NP * NP * NP * EPB);
+  const bool mod = (c->phys.sgs_model | c->phys.sponge) != 0, rk = a.rk.X != nullptr;
+#define RESID_LAUNCH(AFF, MOD, RK) elem_resid_kernel<NP, EPB, MINB, AFF, MOD, RK><<<grid, block, 0, c->stream>>>(a, begin, count)
+  if (c->fast) {
+    if (rk) RESID_LAUNCH(true, false, true);
+    else RESID_LAUNCH(true, false, false);
+  } else if (mod) {
+    if (rk) RESID_LAUNCH(false, true, true);
+    else RESID_LAUNCH(false, true, false);
+  } else {
+    if (rk) RESID_LAUNCH(false, false, true);
+    else RESID_LAUNCH(false, false, false);
+  }
+#undef RESID_LAUNCH
 }
 
 // Launch-shape selection.  p = 3 is the tuned case; tune[] (TPSB_TUNE="g,f,r", development knob) picks
@@ -1999,43 +2009,49 @@ static int ode_one_step(tpsb_ctx *ctx, double *x, double dt, int scheme) {
   const unsigned nb = static_cast<unsigned>((n + 255) / 256);
   double *k = ctx->d_k, *y = ctx->d_yv, *z = ctx->d_z;
   cudaStream_t st = ctx->stream;
-#define AXPY(X, K, A, Y, B, Z, ACC)                                    do {                                                                   axpy2_kernel<<<nb, 256, 0, st>>>(n, X, K, A, Y, B, Z, ACC);          ctx->launches++;                                                   } while (0)
+  // One stage: k = f(in), then Y = X + A k and (Z given) Z = (ACC ? Z : X) + B k.  On the 3-D dry-air paths the update
+  // is the epilogue of the residual kernel (no k round trip, no axpy sweep: 240 -> 120 B per node and stage less);
+  // the generic path runs its forcing-term kernels after the residual, so it keeps the separate sweep.
+  static const bool no_fuse = getenv("TPSB_ODE_FUSE") && atoi(getenv("TPSB_ODE_FUSE")) == 0;
+  const bool fuse = !ctx->generic && !no_fuse;
+  auto stage = [&](const double *in, const double *X, double A, double *Y, double B, double *Z, int ACC) -> int {
+    if (fuse) {
+      ctx->rk = {X, Y, Z, A, B, ACC};
+      const int r = run_mult(ctx, in, k);
+      ctx->rk = {nullptr, nullptr, nullptr, 0.0, 0.0, 0};
+      return r;
+    }
+    const int r = run_mult(ctx, in, k);
+    if (r) return r;
+    axpy2_kernel<<<nb, 256, 0, st>>>(n, X, k, A, Y, B, Z, ACC);
+    ctx->launches++;
+    return TPSB_OK;
+  };
   if (scheme == 1) {  // x += dt f(x)
-    if ((rc = run_mult(ctx, x, k))) return rc;
-    AXPY(x, k, dt, x, 0.0, nullptr, 0);
+    if ((rc = stage(x, x, dt, x, 0.0, nullptr, 0))) return rc;
   } else if (scheme == 2) {  // RK2Solver(a = 1): y = x + dt k1; x += dt/2 (k1 + k2)
-    if ((rc = run_mult(ctx, x, k))) return rc;
-    AXPY(x, k, dt, y, 0.5 * dt, z, 0);
-    if ((rc = run_mult(ctx, y, k))) return rc;
-    AXPY(z, k, 0.5 * dt, x, 0.0, nullptr, 0);
+    if ((rc = stage(x, x, dt, y, 0.5 * dt, z, 0))) return rc;
+    if ((rc = stage(y, z, 0.5 * dt, x, 0.0, nullptr, 0))) return rc;
   } else if (scheme == 3) {  // RK3SSPSolver
-    if ((rc = run_mult(ctx, x, k))) return rc;
-    AXPY(x, k, dt, y, 0.0, nullptr, 0);  // y = x + dt k
-    if ((rc = run_mult(ctx, y, k))) return rc;
+    if ((rc = stage(x, x, dt, y, 0.0, nullptr, 0))) return rc;  // y = x + dt k
     // y = 3/4 x + 1/4 (y + dt k)
-    AXPY(y, k, dt, y, 0.0, nullptr, 0);
+    if ((rc = stage(y, y, dt, y, 0.0, nullptr, 0))) return rc;
     {
       ProfScope ps(ctx, K_AXPY);
       rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 0.75, 0.25, y);
     }
-    if ((rc = run_mult(ctx, y, k))) return rc;
     // x = 1/3 x + 2/3 (y + dt k)
-    AXPY(y, k, dt, y, 0.0, nullptr, 0);
+    if ((rc = stage(y, y, dt, y, 0.0, nullptr, 0))) return rc;
     {
       ProfScope ps(ctx, K_AXPY);
       rk3_combine_kernel<<<nb, 256, 0, st>>>(n, x, y, 1.0 / 3.0, 2.0 / 3.0, x);
     }
   } else {  // RK4Solver
-    if ((rc = run_mult(ctx, x, k))) return rc;
-    AXPY(x, k, dt / 2, y, dt / 6, z, 0);
-    if ((rc = run_mult(ctx, y, k))) return rc;
-    AXPY(x, k, dt / 2, y, dt / 3, z, 1);
-    if ((rc = run_mult(ctx, y, k))) return rc;
-    AXPY(x, k, dt, y, dt / 3, z, 1);
-    if ((rc = run_mult(ctx, y, k))) return rc;
-    AXPY(z, k, dt / 6, x, 0.0, nullptr, 0);
+    if ((rc = stage(x, x, dt / 2, y, dt / 6, z, 0))) return rc;
+    if ((rc = stage(y, x, dt / 2, y, dt / 3, z, 1))) return rc;
+    if ((rc = stage(y, x, dt, y, dt / 3, z, 1))) return rc;
+    if ((rc = stage(y, z, dt / 6, x, 0.0, nullptr, 0))) return rc;
   }
-#undef AXPY
   return TPSB_OK;
 }
 
