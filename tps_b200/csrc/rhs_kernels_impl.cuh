@@ -5,7 +5,10 @@
 
 namespace tpsb {
 
-__constant__ RefTables c_T;
+// one slot per polynomial order (NP = 2, 3, 4), immutable after the first tpsb_create on the device: contexts of
+// different order can run concurrently.  Every kernel has NP in scope (template parameter or constexpr).
+__constant__ RefTables c_Tab[3];
+#define c_T c_Tab[NP - 2]
 
 // ------------------------------------------------------------------------------------------------
 __global__ void prim_kernel(KernelArgs a, int halo) {

@@ -10,18 +10,25 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/tpsb200.h"
 #include "rhs_kernels_impl.cuh"
 #include "rhs_fast.cuh"
+#include "rhs_fused.cuh"
 #include "rhs_generic.cuh"
 
 using namespace tpsb;
 
 static thread_local std::string g_create_error;
-static int g_uploaded_order = -1;  // order whose RefTables currently sit in __constant__ memory
+constexpr int MAX_DEV = 64;
+// The reference-element tables of orders 1..3 sit side by side in each device's __constant__ memory (c_Tab, one slot
+// per order, uploaded once per device by the first tpsb_create on it); per-device flags, because cudaFuncSetAttribute
+// and __constant__ memory are per device.
+static std::mutex g_dev_mutex;
+static bool g_tables_uploaded[MAX_DEV] = {};
 
 struct tpsb_ctx {
   int device = 0;
@@ -60,6 +67,9 @@ struct tpsb_ctx {
   BcTable bct;
   // fast (all-affine) path
   bool fast = false;
+  bool fused = false;               // p = 3 fast path in three launches (rhs_fused.cuh): Up / gradUp are not materialised
+  const double *fields_x = nullptr;  // fused path: vector of the last evaluation (tpsb_get_fields refreshes from it)
+  bool fields_stale = false;
   double *d_geo = nullptr, *d_tr = nullptr, *d_face_nor = nullptr, *d_sendTr = nullptr;
   int4 *d_face_desc = nullptr;
   int *d_send_blk = nullptr;
@@ -798,7 +808,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(ctx, TPSB_ECUDA, "no CUDA device: libtpsb200 has no CPU fallback");
-  if (device < 0 || device >= ndev) return fail(ctx, TPSB_EINVAL, "device %d out of range", device);
+  if (device < 0 || device >= ndev || device >= MAX_DEV) return fail(ctx, TPSB_EINVAL, "device %d out of range", device);
 
   tpsb_ctx *c = new tpsb_ctx;
   ctx = c;
@@ -969,6 +979,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   // all-parallelepiped meshes run the fast path; anything else (trilinear/skewed elements) the general one
   c->fast = all_affine && !visc_mod;  // the SGS models need the full velocity gradient at the face points
   if (const char *pth = getenv("TPSB_PATH")) c->fast = c->fast && strcmp(pth, "legacy") != 0 && strcmp(pth, "general") != 0;
+  c->fused = c->fast && c->np == 4;
+  if (const char *pth = getenv("TPSB_PATH")) c->fused = c->fused && strcmp(pth, "unfused") != 0;
   std::vector<double> geo, face_nor;
   std::vector<int4> face_desc;
   std::vector<int> send_blk;
@@ -1068,8 +1080,17 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_maxBits, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_mcs, sizeof(double));
   if (ce == cudaSuccess) ce = cudaMemset(c->d_maxBits, 0, sizeof(unsigned long long));
-  if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(c_T, &c->T, sizeof(RefTables));
-  if (ce == cudaSuccess) g_uploaded_order = c->order;
+  if (ce == cudaSuccess && device < MAX_DEV) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (!g_tables_uploaded[device]) {
+      for (int p = 1; p <= 3 && ce == cudaSuccess; p++) {
+        RefTables Tp;
+        build_ref_tables(p, Tp);
+        ce = cudaMemcpyToSymbol(c_Tab, &Tp, sizeof(RefTables), static_cast<size_t>(p - 1) * sizeof(RefTables));
+      }
+      g_tables_uploaded[device] = ce == cudaSuccess;
+    }
+  }
   if (c->fast) {
     if (ce == cudaSuccess) ce = upload(&c->d_geo, geo);
     if (ce == cudaSuccess) ce = upload(&c->d_face_desc, face_desc);
@@ -1429,10 +1450,6 @@ static int exchange(tpsb_ctx *ctx, const double *src, int nfld, double *sendbuf,
 // the reference's GPU branch (src/rhs_operator.cpp:349-361)
 static int run_gradients(tpsb_ctx *ctx, const KernelArgs &a, bool prims_done) {
   tpsb_ctx *c = ctx;
-  if (g_uploaded_order != c->order) {  // __constant__ tables are per process: re-upload on an order switch
-    CU(cudaMemcpyToSymbolAsync(c_T, &c->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, c->stream));
-    g_uploaded_order = c->order;
-  }
   if (!prims_done) launch_prim(c, a, 0);
   if (c->NEH > 0) {
     int rc = exchange(c, a.U, NEQ, c->d_sendU, c->d_Uhalo, c->ev_recvU);
@@ -1463,10 +1480,10 @@ static void launch_face_fast(tpsb_ctx *c, const KernelArgs &a, int begin, int co
   const int cap = c->num_sms * c->face_ctas_per_sm;
   if (grid > cap) grid = cap;
   const size_t smem = face_fast_smem_bytes<NP>(WPB);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static bool attr_set[MAX_DEV] = {};  // per instantiation and device (cudaFuncSetAttribute acts on the current device)
+  if (!attr_set[c->device]) {
     cudaFuncSetAttribute(face_flux_fast_kernel<NP, WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    attr_set = true;
+    attr_set[c->device] = true;
   }
   face_flux_fast_kernel<NP, WPB, MINB><<<grid, 32 * WPB, smem, c->stream>>>(a, begin, count);
 }
@@ -1503,10 +1520,10 @@ static void launch_face_mma(tpsb_ctx *c, const KernelArgs &a, int begin, int cou
   const int cap = c->num_sms * MINB;
   if (grid > cap) grid = cap;
   const size_t smem = face_mma_smem_bytes(WPB);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static bool attr_set[MAX_DEV] = {};  // per instantiation and device
+  if (!attr_set[c->device]) {
     cudaFuncSetAttribute(face_flux_mma_kernel<WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    attr_set = true;
+    attr_set[c->device] = true;
   }
   face_flux_mma_kernel<WPB, MINB><<<grid, 32 * WPB, smem, c->stream>>>(a, begin, count);
 }
@@ -1560,10 +1577,6 @@ static int exchange_traces(tpsb_ctx *ctx) {
 
 static int run_gradients_fast(tpsb_ctx *ctx, const KernelArgs &a, bool prims_done) {
   tpsb_ctx *c = ctx;
-  if (g_uploaded_order != c->order) {
-    CU(cudaMemcpyToSymbolAsync(c_T, &c->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, c->stream));
-    g_uploaded_order = c->order;
-  }
   if (!prims_done) launch_prim(c, a, 0);
   if (c->NEH > 0) {
     int rc = exchange(c, a.U, NEQ, c->d_sendU, c->d_Uhalo, c->ev_recvU);
@@ -1581,8 +1594,76 @@ static int run_gradients_fast(tpsb_ctx *ctx, const KernelArgs &a, bool prims_don
 
 static void resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count);
 
+// ---- fused fast path (rhs_fused.cuh) ----
+static void elem_fused(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list, int mode) {
+  if (count <= 0) return;
+  ProfScope ps(c, K_GRAD);
+#define FUSED_LAUNCH(MINB) elem_fused_kernel<MINB><<<std::min(count, c->num_sms * MINB), 64, 0, c->stream>>>(a, begin, count, list, mode)
+  switch (c->tune[0]) {
+    case 1: FUSED_LAUNCH(8); break;
+    case 2: FUSED_LAUNCH(6); break;
+    case 3: FUSED_LAUNCH(11); break;
+    default: FUSED_LAUNCH(10); break;
+  }
+#undef FUSED_LAUNCH
+}
+static void lift(tpsb_ctx *c, const KernelArgs &a, int begin = 0, int count = -1) {
+  if (count < 0) count = c->NE;
+  if (count <= 0) return;
+  ProfScope ps(c, K_RESID);
+  if (a.rk.X) lift_kernel<true><<<(count + 3) / 4, 256, 0, c->stream>>>(a, begin, count);
+  else lift_kernel<false><<<(count + 3) / 4, 256, 0, c->stream>>>(a, begin, count);
+}
+// element pass with the exchange of the partition-boundary elements' state overlapped (src/rhs_operator.cpp:349-361)
+static int run_elem_fused(tpsb_ctx *ctx, const KernelArgs &a, int mode) {
+  tpsb_ctx *c = ctx;
+  if (c->NEH > 0) {
+    int rc = exchange(c, a.U, NEQ, c->d_sendU, c->d_Uhalo, c->ev_recvU);
+    if (rc) return rc;
+    elem_fused(c, a, 0, c->n_int_elems, c->d_elem_list, mode);
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvU, 0));
+    elem_fused(c, a, c->n_int_elems, c->n_pb_elems, c->d_elem_list, mode);
+  } else {
+    elem_fused(c, a, 0, c->NE, nullptr, mode);
+  }
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+static int run_mult_fused(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  tpsb_ctx *c = ctx;
+  CU(cudaSetDevice(c->device));
+  KernelArgs a = make_args(c, d_x, d_y);
+  CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
+  int rc = run_elem_fused(c, a, FUSED_WRITE);
+  if (rc) return rc;
+  c->fields_x = d_x;
+  c->fields_stale = true;
+  if (c->NEH > 0) {
+    rc = exchange_traces(c);
+    if (rc) return rc;
+    face_fast(c, a, 0, c->NFlocal);
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvT, 0));
+    face_fast(c, a, c->NFlocal, c->NFint - c->NFlocal);
+  } else {
+    face_fast(c, a, 0, c->NFint);
+  }
+  bdr_faces(c, a);
+  lift(c, a);
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+// primitives and gradients on request (RHSoperator::updatePrimitives / updateGradients, getGradientGF)
+static int run_gradients_fused(tpsb_ctx *ctx, const KernelArgs &a, bool prims_done) {
+  tpsb_ctx *c = ctx;
+  if (!prims_done) launch_prim(c, a, 0);
+  const int rc = run_elem_fused(c, a, FUSED_EXPORT);
+  c->fields_stale = false;
+  return rc;
+}
+
 static int run_mult_fast(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   tpsb_ctx *c = ctx;
+  if (c->fused) return run_mult_fused(ctx, d_x, d_y);
   CU(cudaSetDevice(c->device));
   KernelArgs a = make_args(c, d_x, d_y);
   CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
@@ -1745,10 +1826,6 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
     CU(cudaEventCreateWithFlags(&c->ev_pipe1, cudaEventDisableTiming));
   }
   KernelArgs a = make_args(c, c->d_hx, c->d_hy);
-  if (g_uploaded_order != c->order) {
-    CU(cudaMemcpyToSymbolAsync(c_T, &c->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, c->stream));
-    g_uploaded_order = c->order;
-  }
   CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
   static const bool dbg = getenv("TPSB_PIPE_DEBUG") != nullptr;  // development: where the three legs end
   static cudaEvent_t dbg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1785,12 +1862,14 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
       case 0: {
         CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
         const long long cnt = static_cast<long long>(ne) * c->nd;
+        if (c->fused) break;  // primitives are rebuilt inside the element kernel
         ProfScope ps(c, K_PRIM);
         prim_range_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, c->stream>>>(a, static_cast<long long>(e0) * c->nd, cnt);
         break;
       }
       case 1:
-        if (c->fast) grad_trace(c, a, e0, ne, nullptr);
+        if (c->fused) elem_fused(c, a, e0, ne, nullptr, FUSED_WRITE);
+        else if (c->fast) grad_trace(c, a, e0, ne, nullptr);
         else grad(c, a, e0, ne, nullptr);
         break;
       case 2:
@@ -1799,7 +1878,8 @@ static int run_mult_host_pipelined(tpsb_ctx *ctx, const double *h_x, double *h_y
         bdr_faces(c, a, c->pipe_bb[k], c->pipe_bb[k + 1] - c->pipe_bb[k]);  // BCintegrator faces of this chunk's elements
         break;
       default: {
-        resid(c, a, e0, ne);
+        if (c->fused) lift(c, a, e0, ne);
+        else resid(c, a, e0, ne);
         CU(cudaEventRecord(c->ev_out[k], c->stream));
         if (dbg && k < 64) {
           if (!dbg_r[k]) cudaEventCreate(&dbg_r[k]), cudaEventCreate(&dbg_o[k]);
@@ -1893,12 +1973,21 @@ int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updat
   CU(cudaSetDevice(ctx->device));
   if (ctx->generic) return run_gradients_generic(ctx, d_x, primitives_updated != 0);
   KernelArgs a = make_args(ctx, d_x, nullptr);
+  if (ctx->fused) return run_gradients_fused(ctx, a, primitives_updated != 0);
   if (ctx->fast) return run_gradients_fast(ctx, a, primitives_updated != 0);
   return run_gradients(ctx, a, primitives_updated != 0);
 }
 
 int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp) {
   if (!ctx) return TPSB_EINVAL;
+  if (ctx->fused && ctx->fields_stale && ctx->fields_x) {
+    // the fused evaluation keeps Up / gradUp on chip: rebuild them from the vector of the last tpsb_rhs_mult
+    // (which must still be alive; call tpsb_update_gradients(x) instead to be explicit)
+    CU(cudaSetDevice(ctx->device));
+    KernelArgs a = make_args(ctx, ctx->fields_x, nullptr);
+    const int rc = run_gradients_fused(ctx, a, false);
+    if (rc) return rc;
+  }
   if (d_Up) *d_Up = ctx->d_Up;
   if (d_gradUp) *d_gradUp = ctx->d_gradUp;
   return TPSB_OK;
@@ -2105,10 +2194,6 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
         return fail(ctx, TPSB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
       }
       ctx->ode_U = d_U, ctx->ode_dt = dt, ctx->ode_scheme = scheme;
-    }
-    if (g_uploaded_order != ctx->order) {  // another context switched the __constant__ tables since the capture
-      CU(cudaMemcpyToSymbolAsync(c_T, &ctx->T, sizeof(RefTables), 0, cudaMemcpyHostToDevice, caller));
-      g_uploaded_order = ctx->order;
     }
     CU(cudaEventRecord(ctx->ode_ev0, caller));
     CU(cudaStreamWaitEvent(ctx->ode_stream, ctx->ode_ev0, 0));
