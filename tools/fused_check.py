@@ -43,8 +43,9 @@ def small():
 def timing(n):
     m = tps_b200.cartesian_hex_mesh(n, n, n, lo=(-PI,) * 3, hi=(PI,) * 3, order_mode=1)
     phys = tps_b200.Physics.dry_air(1, 100.0)
-    for label, env in (("fused default", {}), ("fused tune 1", {"TPSB_TUNE": "1,0,0"}), ("fused tune 2", {"TPSB_TUNE": "2,0,0"}),
-                       ("fused tune 3", {"TPSB_TUNE": "3,0,0"}), ("unfused", {"TPSB_PATH": "unfused"})):
+    cases = [("fused default", {})] + [(f"fused tune {t}", {"TPSB_TUNE": f"{t},0,0"}) for t in range(1, 6)]
+    cases += [(f"lift ctas {q}", {"TPSB_LIFT_CTAS": str(q)}) for q in (1, 3, 4)] + [("unfused", {"TPSB_PATH": "unfused"})]
+    for label, env in cases:
         os.environ.update(env)
         op = tps_b200.RhsOperator(m, order=3, physics=phys)
         for k in env:

@@ -48,21 +48,44 @@ __device__ __forceinline__ unsigned long long warp_max_bits(double v) {
   return (static_cast<unsigned long long>(mh) << 32) | ml;
 }
 
+// ---- shared-memory layout of elem_fused_kernel ---------------------------------------------------------------------
+// Fields live in PAIRS: one 16-byte unit per node holds two fields, so the per-node and per-line accesses are 128-bit
+// (ncu, profiles/r2b: a 64-bit shared access of a full warp costs 4 wavefronts like a 128-bit one -- the data pipe
+// works on quarter warps -- and the first fused kernel sat at 85 % of that pipe).  Node n of a pair field sits in unit
+// swz(n): an XOR swizzle of the low three bits with (j1, k0, k1) that makes EVERY access pattern of the kernel hit 8
+// distinct 16-byte bank groups per quarter warp without padding: node order, the DMMA B fragments and D-fragment
+// stores along x / y / z, and the line tasks (8 lines at one position) along x / y / z (checked exhaustively by
+// tests/test_cpu_capi.py::test_fused_swizzle_is_conflict_free).
+__host__ __device__ constexpr int fused_swz(int n) {
+  return (n & 0x38) | ((n & 7) ^ ((n >> 2) & 2) ^ (((n >> 4) & 1) * 5) ^ ((n >> 4) & 2));
+}
+constexpr int FPU = 128;                 // doubles per pair field (64 units x 2)
+constexpr int F_S0 = 0 * FPU;            // (rho, u)
+constexpr int F_S1 = 1 * FPU;            // (v, w)
+constexpr int F_S2 = 2 * FPU;            // (T, -)
+constexpr int F_S3 = 3 * FPU;            // (rho u, rho v)
+constexpr int F_S4 = 4 * FPU;            // (rho w, rho E)
+constexpr int F_SJ = 5 * FPU;            // jump block [6 faces][16 face nodes][6]: (rho, u, v, w, T, -) own trace -> jump
+constexpr int F_DR = F_SJ + 6 * 16 * 6;  // 8 pair fields: (d rho, d u)_r, (d v, d w)_r for r = 0,1,2; (dT_0, dT_1); (dT_2, -)
+constexpr int F_TOTAL = F_DR + 8 * FPU;  // 2240 doubles = 17.9 KB
+// later in the element: G = flux . adj(J) row r in pair fields 0-7 of the front region ((G0,G1)_r, (G2,G3)_r at 2 r,
+// 2 r + 1; (G4_0, G4_1) at 6; (G4_2, -) at 7; pairs 5-7 overlay the dead jump block), and the viscous fields in
+// place of the derivatives ((s0,s1)_r, (s2, n.gradT)_r at F_DR + 2 r, 2 r + 1; (div u, -) at F_DR + 6)
+
+__device__ __forceinline__ double2 lds128(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void sts128(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
+
 // Persistent: gridDim.x CTAs of 64 threads (two warps = one element at a time) stride over the element range, so the
 // fragment / line-task addressing and the 1-D tables are set up once per CTA, not once per element.
-template <int MINB>
-__global__ void __launch_bounds__(64, MINB)
+template <int REGS>
+__global__ void __launch_bounds__(64) __maxnreg__(REGS)
     elem_fused_kernel(KernelArgs a, int elem_begin, int elem_count, const int *elem_list, int mode) {
-  constexpr int NP = 4, ND = 64, NF2 = 16, PS = 80;  // PS: padded doubles per field (pad_node)
-  constexpr int BLK = NTF * NF2;                      // doubles per (element, face) trace block
-  // sm[0 .. 16 PS): fields 0-4 U, 5-9 Up, 10-15 the jump block sJ[6][5][16]; later G[eq][r] = flux . adj(J) row r in
-  //                 field 3 eq + r, overwritten in place by its transposed derivative
-  // sm[16 PS .. 31 PS): reference derivatives of Up [f][r]; later the 13 viscous fields
-  __shared__ __align__(16) double sm[31 * PS];
+  constexpr int NP = 4, ND = 64, NF2 = 16;
+  constexpr int BLK = NTF * NF2;  // doubles per (element, face) trace block
+  __shared__ __align__(16) double sm[F_TOTAL];
   __shared__ double sGeo[GEO];
   __shared__ double sD[NP][NP], sLb[2][NP], sWn[NP], sLw[2][NP];
   __shared__ int sNbr[6], sCode[6], sFp[6];
-  double *sF = sm, *sJ = sm + 10 * PS, *sDr = sm + 16 * PS;
   const int n = threadIdx.x;
   const int lane = n & 31, half = n >> 5;
   const long long N = a.N;
@@ -74,25 +97,27 @@ __global__ void __launch_bounds__(64, MINB)
   if (n < NP) sWn[n] = c_T.wn[n];
   if (n < 6) sFp[n] = c_T.face_par[n];
   __syncthreads();
-  const int pn = pad_node(n);
+  const int un = 2 * fused_swz(n);  // this thread's node: offset of its unit inside a pair field
   const double cT = a.phys.gm1 / a.phys.R;
-  // ---- fragment addressing (see grad_trace_mma_kernel)
+  // ---- DMMA fragment addressing.  Line L (0..15) of axis d: nodes base_d(L) + m stride_d.
+  //   B fragment : m = lane%4, L = 8 half + lane/4
+  //   D fragment : row = lane/4 (0-3 derivative at position row, 4 / 5 trace at the - / + end), lines L0 = 8 half + 2 (lane%4), L0 + 1
   const int fr = lane >> 2, fk = lane & 3;
   const double afrag = fr < NP ? sD[fr][fk] : (fr < NP + 2 ? sLb[fr - NP][fk] : 0.0);
   // transposed derivative with the quadrature weights folded in: Dt[j][m] = D[m][j] w_m / w_j, so that
   // (1 / w_j) sum_m D[m][j] (w_m G_m) needs no separate weighting of G
   const double afragT = fr < NP ? sD[fk][fr] * sWn[fk] / sWn[fr] : 0.0;
-  int bOff[DIM];
-  int sOff0[DIM], sOff1[DIM];  // P1 store targets of this lane in sm: rows 0-3 -> derivative field, rows 4-5 -> own trace
-  const int sFld = fr < NP ? DIM * PS : NF2;  // ... and their stride per field
-  const bool sAct = fr < NP + 2;
+  int bU[DIM];             // B-fragment unit offset (doubles) inside a pair field
+  int o0[DIM], o1[DIM];    // P1 store target of (rho, u): derivative pair 2 d at the D-fragment node (rows 0-3), or the jump
+                           // block entry of the line's face node on the - / + face (rows 4 / 5)
+  const bool isD = fr < NP, sAct = fr < NP + 2;
+  const int pst = isD ? FPU : 2;  // ... offset of the (v, w) store from it
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
     const int str = d == 0 ? 1 : (d == 1 ? NP : NP * NP);
     auto base = [d](int L) { return d == 0 ? 4 * L : (d == 1 ? (L & 3) + 16 * (L >> 2) : L); };
-    bOff[d] = pad_node(base(8 * half + fr) + fk * str);
+    bU[d] = 2 * fused_swz(base(8 * half + fr) + fk * str);
     const int L0 = 8 * half + 2 * fk;
-    const int dOff0 = pad_node(base(L0) + (fr & 3) * str), dOff1 = pad_node(base(L0 + 1) + (fr & 3) * str);
     const FacePar fp = (fr & 1) ? decode_face(kFacePar(kFacePlus[d])) : decode_face(kFacePar(kFaceMinus[d]));
     auto abof = [&](int L) {
       const int nb = base(L), i = nb & 3, j = (nb >> 2) & 3, k = nb >> 4;
@@ -100,19 +125,21 @@ __global__ void __launch_bounds__(64, MINB)
       return (fp.ss ? ia : NP - 1 - ia) + NP * (fp.st ? ib : NP - 1 - ib);
     };
     const int lf = (fr & 1) ? kFacePlus[d] : kFaceMinus[d];
-    sOff0[d] = fr < NP ? 16 * PS + d * PS + dOff0 : 10 * PS + lf * (NEQ * NF2) + abof(L0);
-    sOff1[d] = fr < NP ? 16 * PS + d * PS + dOff1 : 10 * PS + lf * (NEQ * NF2) + abof(L0 + 1);
+    o0[d] = isD ? F_DR + 2 * d * FPU + 2 * fused_swz(base(L0) + (fr & 3) * str) : F_SJ + (lf * NF2 + abof(L0)) * 6;
+    o1[d] = isD ? F_DR + 2 * d * FPU + 2 * fused_swz(base(L0 + 1) + (fr & 3) * str) : F_SJ + (lf * NF2 + abof(L0 + 1)) * 6;
   }
   // ---- line tasks: thread t < 48 owns line L = t % 16 of axis t / 16 and extrapolates it to both ends (DFMA)
-  const int lax = n >> 4, lL = n & 15;
-  int lOff = 0, lStr = 0, lFm = 0, lFp = 0;  // padded base / stride of the line, trace slot on the - / + face
   // end-point coefficients l_m(0), l_m(1) are read straight from the constant bank (compile-time addresses: free operands)
 #define LB0(m) c_T.lb[0][m]
 #define LB1(m) c_T.lb[1][m]
+  const int lax = n >> 4, lL = n & 15;
+  int lU[NP] = {0, 0, 0, 0};  // unit offsets (doubles) of the line's four nodes
+  int lFm = 0, lFp = 0;       // trace slot on the - / + face
   if (n < 48) {
     const int nb = lax == 0 ? 4 * lL : (lax == 1 ? (lL & 3) + 16 * (lL >> 2) : lL);
-    lOff = pad_node(nb);
-    lStr = lax == 0 ? 1 : (lax == 1 ? 4 : 20);
+    const int ls = lax == 0 ? 1 : (lax == 1 ? 4 : 16);
+#pragma unroll
+    for (int m = 0; m < NP; m++) lU[m] = 2 * fused_swz(nb + m * ls);
     const int i = nb & 3, j = (nb >> 2) & 3, k = nb >> 4;
     const int fm = lax == 0 ? kFaceMinus[0] : (lax == 1 ? kFaceMinus[1] : kFaceMinus[2]);
     const int fpl = lax == 0 ? kFacePlus[0] : (lax == 1 ? kFacePlus[1] : kFacePlus[2]);
@@ -122,19 +149,15 @@ __global__ void __launch_bounds__(64, MINB)
     lFm = fm * BLK + (pm.ss ? iam : NP - 1 - iam) + NP * (pm.st ? ibm : NP - 1 - ibm);
     lFp = fpl * BLK + (pp.ss ? iap : NP - 1 - iap) + NP * (pp.st ? ibp : NP - 1 - ibp);
   }
-  // ---- neighbour tasks (P2): (face, face node); faces are taken in axis pairs (4,2 | 1,3 | 0,5) so that on a
-  // structured mesh a warp's 32 tasks see one neighbour axis (the x-normal pair takes the 256-bit loads)
   const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
-  int liftP[DIM], liftM[DIM];  // jump slots of this node on the + / - face of each axis
-  {
+  int liftP[DIM], liftM[DIM];  // jump-block entries of this node on the + / - face of each axis
 #pragma unroll
-    for (int r = 0; r < DIM; r++) {
-      const FacePar fm = decode_face(kFacePar(kFaceMinus[r])), fpl = decode_face(kFacePar(kFacePlus[r]));
-      const int iam = pick3(fm.as, i, j, k), ibm = pick3(fm.at, i, j, k);
-      const int iap = pick3(fpl.as, i, j, k), ibp = pick3(fpl.at, i, j, k);
-      liftM[r] = kFaceMinus[r] * (NEQ * NF2) + (fm.ss ? iam : NP - 1 - iam) + NP * (fm.st ? ibm : NP - 1 - ibm);
-      liftP[r] = kFacePlus[r] * (NEQ * NF2) + (fpl.ss ? iap : NP - 1 - iap) + NP * (fpl.st ? ibp : NP - 1 - ibp);
-    }
+  for (int r = 0; r < DIM; r++) {
+    const FacePar fm = decode_face(kFacePar(kFaceMinus[r])), fpl = decode_face(kFacePar(kFacePlus[r]));
+    const int iam = pick3(fm.as, i, j, k), ibm = pick3(fm.at, i, j, k);
+    const int iap = pick3(fpl.as, i, j, k), ibp = pick3(fpl.at, i, j, k);
+    liftM[r] = F_SJ + (kFaceMinus[r] * NF2 + (fm.ss ? iam : NP - 1 - iam) + NP * (fm.st ? ibm : NP - 1 - ibm)) * 6;
+    liftP[r] = F_SJ + (kFacePlus[r] * NF2 + (fpl.ss ? iap : NP - 1 - iap) + NP * (fpl.st ? ibp : NP - 1 - ibp)) * 6;
   }
   unsigned long long mcs_bits = 0ull;
   const bool ns = a.phys.eq_system != 0;
@@ -154,41 +177,59 @@ __global__ void __launch_bounds__(64, MINB)
     {
       double u, v, w, T;
       dry_prim_fast(cT, s[0], s[1], s[2], s[3], s[4], u, v, w, T);
-#pragma unroll
-      for (int f = 0; f < NEQ; f++) sF[f * PS + pn] = s[f];
-      sF[5 * PS + pn] = s[0];
-      sF[6 * PS + pn] = u;
-      sF[7 * PS + pn] = v;
-      sF[8 * PS + pn] = w;
-      sF[9 * PS + pn] = T;
+      sts128(&sm[F_S0 + un], s[0], u);
+      sts128(&sm[F_S1 + un], v, w);
+      sm[F_S2 + un] = T;
+      sts128(&sm[F_S3 + un], s[1], s[2]);
+      sts128(&sm[F_S4 + un], s[3], s[4]);
     }
     __syncthreads();
     // ---- P1: D and both end-point extrapolations of the primitives: one DMMA per (axis, field, 8 lines)
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
-#pragma unroll
-      for (int f = 0; f < NEQ; f++) {
-        double d0, d1;
-        dmma884(d0, d1, afrag, sF[(NEQ + f) * PS + bOff[d]]);
-        if (sAct) {
-          sm[sOff0[d] + f * sFld] = d0;
-          sm[sOff1[d] + f * sFld] = d1;
-        }
+      double a0, a1, b0, b1;
+      double2 x = lds128(&sm[F_S0 + bU[d]]);
+      dmma884(a0, a1, afrag, x.x);
+      dmma884(b0, b1, afrag, x.y);
+      if (sAct) {
+        sts128(&sm[o0[d]], a0, b0);
+        sts128(&sm[o1[d]], a1, b1);
+      }
+      x = lds128(&sm[F_S1 + bU[d]]);
+      dmma884(a0, a1, afrag, x.x);
+      dmma884(b0, b1, afrag, x.y);
+      if (sAct) {
+        sts128(&sm[o0[d] + pst], a0, b0);
+        sts128(&sm[o1[d] + pst], a1, b1);
+      }
+      dmma884(a0, a1, afrag, sm[F_S2 + bU[d]]);
+      // dT_d: derivative pairs 6 (d = 0, 1) / 7 (d = 2); trace: slot 4 of the jump-block entry
+      const int td = isD ? (6 + (d >> 1) - 2 * d) * FPU + (d & 1) : 4;
+      if (sAct) {
+        sm[o0[d] + td] = a0;
+        sm[o1[d] + td] = a1;
       }
     }
     double *blk0 = a.tr + static_cast<long long>(e) * 6 * BLK;
-    if (n < 48 && (mode & FUSED_WRITE)) {  // traces of the conserved state, straight to the trace blocks
-#pragma unroll
-      for (int f = 0; f < NEQ; f++) {
-        const double *p = &sF[f * PS + lOff];
-        const double x0 = p[0], x1 = p[lStr], x2 = p[2 * lStr], x3 = p[3 * lStr];
-        blk0[lFm + f * NF2] = LB0(0) * x0 + LB0(1) * x1 + LB0(2) * x2 + LB0(3) * x3;
-        blk0[lFp + f * NF2] = LB1(0) * x0 + LB1(1) * x1 + LB1(2) * x2 + LB1(3) * x3;
-      }
+    if (n < 48 && (mode & FUSED_WRITE)) {  // traces of rho u, rho v, rho w, rho E, straight to the trace blocks
+      const double2 p0 = lds128(&sm[F_S3 + lU[0]]), p1 = lds128(&sm[F_S3 + lU[1]]), p2 = lds128(&sm[F_S3 + lU[2]]),
+                    p3 = lds128(&sm[F_S3 + lU[3]]);
+      blk0[lFm + 1 * NF2] = LB0(0) * p0.x + LB0(1) * p1.x + LB0(2) * p2.x + LB0(3) * p3.x;
+      blk0[lFp + 1 * NF2] = LB1(0) * p0.x + LB1(1) * p1.x + LB1(2) * p2.x + LB1(3) * p3.x;
+      blk0[lFm + 2 * NF2] = LB0(0) * p0.y + LB0(1) * p1.y + LB0(2) * p2.y + LB0(3) * p3.y;
+      blk0[lFp + 2 * NF2] = LB1(0) * p0.y + LB1(1) * p1.y + LB1(2) * p2.y + LB1(3) * p3.y;
+      const double2 q0 = lds128(&sm[F_S4 + lU[0]]), q1 = lds128(&sm[F_S4 + lU[1]]), q2 = lds128(&sm[F_S4 + lU[2]]),
+                    q3 = lds128(&sm[F_S4 + lU[3]]);
+      blk0[lFm + 3 * NF2] = LB0(0) * q0.x + LB0(1) * q1.x + LB0(2) * q2.x + LB0(3) * q3.x;
+      blk0[lFp + 3 * NF2] = LB1(0) * q0.x + LB1(1) * q1.x + LB1(2) * q2.x + LB1(3) * q3.x;
+      blk0[lFm + 4 * NF2] = LB0(0) * q0.y + LB0(1) * q1.y + LB0(2) * q2.y + LB0(3) * q3.y;
+      blk0[lFp + 4 * NF2] = LB1(0) * q0.y + LB1(1) * q1.y + LB1(2) * q2.y + LB1(3) * q3.y;
     }
-    __syncthreads();  // own traces (P1) are in sJ
+    __syncthreads();  // own traces (P1) are in the jump block
     // ---- P2: neighbour primitive traces at my face nodes -> jumps 1/2 (Up_nbr - Up_own) in place; boundary face:
-    // Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115)
+    // Up2 = Up1 unless useBCinGrad (faceGradientIntegration.cpp:96-115).  Task = (face, face node); faces are taken in
+    // axis pairs (4,2 | 1,3 | 0,5) so that on a structured mesh a warp's 32 tasks see one neighbour axis (the x-normal
+    // pair takes the 256-bit loads).  The trace of rho (conserved = primitive) goes to the trace block from here.
 #pragma unroll
     for (int rd = 0; rd < 2; rd++) {
       if (rd == 1 && half != 0) break;
@@ -197,19 +238,23 @@ __global__ void __launch_bounds__(64, MINB)
       const int hi = lane >> 4;
       const int lf = pair == 0 ? (hi ? 2 : 4) : (pair == 1 ? (hi ? 3 : 1) : (hi ? 5 : 0));
       const int ab = lane & 15, fa = ab & 3, fb = ab >> 2;
-      double *pj = &sJ[lf * (NEQ * NF2) + ab];
+      double *pj = &sm[F_SJ + (lf * NF2 + ab) * 6];
+      const double2 own01 = lds128(pj), own23 = lds128(pj + 2);
+      const double own4 = pj[4];
+      if (mode & FUSED_WRITE) blk0[lf * BLK + ab] = own01.x;
       const int nbr = sNbr[lf];
       if (nbr < 0) {
         if (a.bct.use_bc_in_grad && nbr <= -2) {
-          double pT[NEQ], pbc[NEQ];
-#pragma unroll
-          for (int f = 0; f < NEQ; f++) pT[f] = pj[f * NF2];
+          const double pT[NEQ] = {own01.x, own01.y, own23.x, own23.y, own4};
+          double pbc[NEQ];
           dry_bc_prim_for_gradient(a.bct.bc[-2 - nbr], pT, pbc);
-#pragma unroll
-          for (int f = 0; f < NEQ; f++) pj[f * NF2] = 0.5 * (pbc[f] - pT[f]);
+          sts128(pj, 0.5 * (pbc[0] - pT[0]), 0.5 * (pbc[1] - pT[1]));
+          sts128(pj + 2, 0.5 * (pbc[2] - pT[2]), 0.5 * (pbc[3] - pT[3]));
+          pj[4] = 0.5 * (pbc[4] - pT[4]);
         } else {
-#pragma unroll
-          for (int f = 0; f < NEQ; f++) pj[f * NF2] = 0.0;
+          sts128(pj, 0.0, 0.0);
+          sts128(pj + 2, 0.0, 0.0);
+          pj[4] = 0.0;
         }
         continue;
       }
@@ -250,8 +295,9 @@ __global__ void __launch_bounds__(64, MINB)
         acc[3] += lm * w;
         acc[4] += lm * T;
       }
-#pragma unroll
-      for (int f = 0; f < NEQ; f++) pj[f * NF2] = 0.5 * (acc[f] - pj[f * NF2]);
+      sts128(pj, 0.5 * (acc[0] - own01.x), 0.5 * (acc[1] - own01.y));
+      sts128(pj + 2, 0.5 * (acc[2] - own23.x), 0.5 * (acc[3] - own23.y));
+      pj[4] = 0.5 * (acc[4] - own4);
     }
     __syncthreads();
     // ---- P3: per node -- lifted physical gradient, viscous face fields, contravariant flux
@@ -260,13 +306,28 @@ __global__ void __launch_bounds__(64, MINB)
     double G[NEQ][DIM];
     {
       double rg[NEQ][DIM];
+      {
+        const double *dr = &sm[F_DR + un];
+#pragma unroll
+        for (int r = 0; r < DIM; r++) {
+          const double2 x0 = lds128(dr + 2 * r * FPU), x1 = lds128(dr + (2 * r + 1) * FPU);
+          rg[0][r] = x0.x, rg[1][r] = x0.y, rg[2][r] = x1.x, rg[3][r] = x1.y;
+        }
+        const double2 t01 = lds128(dr + 6 * FPU);
+        rg[4][0] = t01.x, rg[4][1] = t01.y, rg[4][2] = dr[7 * FPU];
+      }
       const int idx[3] = {i, j, k};
 #pragma unroll
       for (int r = 0; r < DIM; r++) {
         const double lwM = sLw[0][idx[r]], lwP = sLw[1][idx[r]];
-#pragma unroll
-        for (int f = 0; f < NEQ; f++)
-          rg[f][r] = sDr[(f * DIM + r) * PS + pn] + (lwP * sJ[liftP[r] + f * NF2] - lwM * sJ[liftM[r] + f * NF2]);
+        const double *jp = &sm[liftP[r]], *jm = &sm[liftM[r]];
+        const double2 p01 = lds128(jp), p23 = lds128(jp + 2), m01 = lds128(jm), m23 = lds128(jm + 2);
+        const double p4 = jp[4], m4 = jm[4];
+        rg[0][r] += lwP * p01.x - lwM * m01.x;
+        rg[1][r] += lwP * p01.y - lwM * m01.y;
+        rg[2][r] += lwP * p23.x - lwM * m23.x;
+        rg[3][r] += lwP * p23.y - lwM * m23.y;
+        rg[4][r] += lwP * p4 - lwM * m4;
       }
       double g[NEQ][DIM];
       bool wr = (mode & FUSED_EXPORT) != 0;
@@ -297,7 +358,7 @@ __global__ void __launch_bounds__(64, MINB)
 #pragma unroll
         for (int c = 0; c < DIM; c++) sym[p][c] = g[1 + p][c] + g[1 + c][p];
       const double divu = g[1][0] + g[2][1] + g[3][2];
-      double *sV = sDr;  // thread n only ever touches column pn of sDr: in place
+      double *sV = &sm[F_DR + un];  // this thread's own units: the viscous fields replace the derivatives in place
 #pragma unroll
       for (int r = 0; r < DIM; r++) {
         const double nr[3] = {A[r + 0], A[r + 3], A[r + 6]};
@@ -305,9 +366,8 @@ __global__ void __launch_bounds__(64, MINB)
 #pragma unroll
         for (int p = 0; p < DIM; p++) sv[p] = sym[p][0] * nr[0] + sym[p][1] * nr[1] + sym[p][2] * nr[2];
         const double hT = g[4][0] * nr[0] + g[4][1] * nr[1] + g[4][2] * nr[2];
-#pragma unroll
-        for (int p = 0; p < DIM; p++) sV[(r * 4 + p) * PS + pn] = sv[p];
-        sV[(r * 4 + 3) * PS + pn] = hT;
+        sts128(sV + 2 * r * FPU, sv[0], sv[1]);
+        sts128(sV + (2 * r + 1) * FPU, sv[2], hT);
         double fc[NEQ];
         dry_conv_dot_n(s, q, nr, fc);
         if (ns) {  // F_v . n^r from the same contracted fields
@@ -321,30 +381,37 @@ __global__ void __launch_bounds__(64, MINB)
 #pragma unroll
         for (int eq = 0; eq < NEQ; eq++) G[eq][r] = fc[eq];
       }
-      sV[12 * PS + pn] = divu;
-      // fields 0-9 of sF are this thread's own column: U / Up are dead (s[] lives in registers)
-#pragma unroll
-      for (int eq = 0; eq < 3; eq++)
-#pragma unroll
-        for (int r = 0; r < DIM; r++) sF[(eq * DIM + r) * PS + pn] = G[eq][r];
-      sF[9 * PS + pn] = G[3][0];
+      sV[6 * FPU] = divu;
+      // pair fields 0-4 of the front region are this thread's own units: U / Up are dead (s[] lives in registers)
+      double *sG = &sm[un];
+      sts128(sG + 0 * FPU, G[0][0], G[1][0]);
+      sts128(sG + 1 * FPU, G[2][0], G[3][0]);
+      sts128(sG + 2 * FPU, G[0][1], G[1][1]);
+      sts128(sG + 3 * FPU, G[2][1], G[3][1]);
+      sts128(sG + 4 * FPU, G[0][2], G[1][2]);
     }
-    __syncthreads();  // every lift has read sJ: fields 10-14 may be overwritten; the viscous fields are complete
-    sF[10 * PS + pn] = G[3][1];
-    sF[11 * PS + pn] = G[3][2];
-    sF[12 * PS + pn] = G[4][0];
-    sF[13 * PS + pn] = G[4][1];
-    sF[14 * PS + pn] = G[4][2];
-    // ---- P4a: traces of the normal-contracted viscous fields (axis d carries fields 4 d .. 4 d + 3 and div u)
+    __syncthreads();  // every lift has read the jump block: pair fields 5-7 may overwrite it; the viscous fields are complete
+    {
+      double *sG = &sm[un];
+      sts128(sG + 5 * FPU, G[2][2], G[3][2]);
+      sts128(sG + 6 * FPU, G[4][0], G[4][1]);
+      sG[7 * FPU] = G[4][2];
+    }
+    // ---- P4a: traces of the normal-contracted viscous fields (axis d carries (s0,s1)_d, (s2,n.gradT)_d and div u)
     if (n < 48 && (mode & FUSED_WRITE)) {
+      const double *v0 = &sm[F_DR + 2 * lax * FPU], *v1 = v0 + FPU, *v2 = &sm[F_DR + 6 * FPU];
+      double tm[5] = {0, 0, 0, 0, 0}, tp[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+      for (int m = 0; m < NP; m++) {
+        const double2 x = lds128(v0 + lU[m]), y = lds128(v1 + lU[m]);
+        const double z = v2[lU[m]];
+        tm[0] += LB0(m) * x.x, tm[1] += LB0(m) * x.y, tm[2] += LB0(m) * y.x, tm[3] += LB0(m) * y.y, tm[4] += LB0(m) * z;
+        tp[0] += LB1(m) * x.x, tp[1] += LB1(m) * x.y, tp[2] += LB1(m) * y.x, tp[3] += LB1(m) * y.y, tp[4] += LB1(m) * z;
+      }
 #pragma unroll
       for (int v = 0; v < 5; v++) {
-        const double *p = &sDr[(v < 4 ? 4 * lax + v : 12) * PS + lOff];
-        const double x0 = p[0], x1 = p[lStr], x2 = p[2 * lStr], x3 = p[3 * lStr];
-        const double tm = LB0(0) * x0 + LB0(1) * x1 + LB0(2) * x2 + LB0(3) * x3;
-        const double tp = LB1(0) * x0 + LB1(1) * x1 + LB1(2) * x2 + LB1(3) * x3;
-        blk0[lFm + (NEQ + v) * NF2] = v < 4 ? -tm : tm;  // outward normal of the - face = -A[d,:]
-        blk0[lFp + (NEQ + v) * NF2] = tp;
+        blk0[lFm + (NEQ + v) * NF2] = v < 4 ? -tm[v] : tm[v];  // outward normal of the - face = -A[d,:]
+        blk0[lFp + (NEQ + v) * NF2] = tp[v];
       }
     }
     __syncthreads();
@@ -352,93 +419,130 @@ __global__ void __launch_bounds__(64, MINB)
       // ---- P4b: transposed derivative of G along each axis, in place (a warp reads and writes the same 8 lines)
 #pragma unroll
       for (int r = 0; r < DIM; r++) {
+        // rows 0-3: o0 / o1 hold F_DR + 2 r FPU + the D-fragment unit
+        const int u0 = o0[r] - (F_DR + 2 * r * FPU), u1 = o1[r] - (F_DR + 2 * r * FPU);
 #pragma unroll
-        for (int eq = 0; eq < NEQ; eq++) {
-          double d0, d1;
-          double *fld = &sF[(eq * DIM + r) * PS];
-          dmma884(d0, d1, afragT, fld[bOff[r]]);
-          if (fr < NP) {  // rows 0-3: sOff0/1 hold 16 PS + r PS + the D-fragment node offset
-            fld[sOff0[r] - (16 + r) * PS] = d0;
-            fld[sOff1[r] - (16 + r) * PS] = d1;
+        for (int h2 = 0; h2 < 2; h2++) {
+          double *fld = &sm[(2 * r + h2) * FPU];
+          const double2 x = lds128(fld + bU[r]);
+          double a0, a1, b0, b1;
+          dmma884(a0, a1, afragT, x.x);
+          dmma884(b0, b1, afragT, x.y);
+          if (isD) {
+            sts128(fld + u0, a0, b0);
+            sts128(fld + u1, a1, b1);
           }
+        }
+        double *f4 = &sm[(6 + (r >> 1)) * FPU + (r & 1)];
+        double a0, a1;
+        dmma884(a0, a1, afragT, f4[bU[r]]);
+        if (isD) {
+          f4[u0] = a0;
+          f4[u1] = a1;
         }
       }
       __syncthreads();
       // ---- P5: volume part of dU/dt = Me^-1 (sum_r D^T_r G_r), Me = diag(w |J|)
-#pragma unroll
-      for (int eq = 0; eq < NEQ; eq++) {
-        const double z = sF[(eq * DIM + 0) * PS + pn] + sF[(eq * DIM + 1) * PS + pn] + sF[(eq * DIM + 2) * PS + pn];
-        a.y[o + eq * N] = z * idet;
-      }
+      const double *sG = &sm[un];
+      const double2 g00 = lds128(sG), g01 = lds128(sG + 2 * FPU), g02 = lds128(sG + 4 * FPU);
+      const double2 g20 = lds128(sG + FPU), g21 = lds128(sG + 3 * FPU), g22 = lds128(sG + 5 * FPU);
+      const double2 g4a = lds128(sG + 6 * FPU);
+      const double g4b = sG[7 * FPU];
+      a.y[o + 0 * N] = (g00.x + g01.x + g02.x) * idet;
+      a.y[o + 1 * N] = (g00.y + g01.y + g02.y) * idet;
+      a.y[o + 2 * N] = (g20.x + g21.x + g22.x) * idet;
+      a.y[o + 3 * N] = (g20.y + g21.y + g22.y) * idet;
+      a.y[o + 4 * N] = (g4a.x + g4a.y + g4b) * idet;
     }
     __syncthreads();  // the next element overwrites sm / sGeo / sNbr
   }
   if (lane == 0 && mcs_bits > __ldcg(a.maxCharBits)) atomicMax(a.maxCharBits, mcs_bits);
+#undef LB0
+#undef LB1
 }
 
 // lift_kernel: y = y_vol + Me^-1 sum_faces (+-) l_c(face) R_face   (face_integrator.cpp:348-350, rhs_operator.cpp:432-448);
 // y_vol is what elem_fused_kernel left in a.y.  RK: fused Runge-Kutta stage update as in elem_resid_kernel.
-// Streaming kernel (110 B per node): all loads of a thread are independent of each other (absent faces read slot 0
-// with a zero coefficient), so the 35 of them are in flight together.
+// Streaming kernel (110 B per node) whose only hazard is latency: the face ids of an element must arrive before its
+// face residuals can be addressed.  Persistent CTAs of four elements; the ids of the NEXT four elements are fetched
+// while the 35 independent loads per node of the current ones are in flight (absent faces read slot 0 with a zero
+// coefficient, so no load hides behind a branch).
 template <bool RK>
 __global__ void __launch_bounds__(256) lift_kernel(KernelArgs a, int elem_begin, int elem_count) {
   constexpr int NP = 4, ND = 64, NF2 = 16;
-  __shared__ double sLb[2][NP], sWn[NP];
-  __shared__ int sFace[4][6], sFcode[4][6];
-  __shared__ double sDet[4];
-  if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
-  if (threadIdx.x < NP) sWn[threadIdx.x] = c_T.wn[threadIdx.x];
+  __shared__ double sLb[2][NP], sIw[ND];
+  __shared__ int sFace[2][4][6], sFcode[2][4][6];
+  __shared__ double sIdet[2][4];
   const int le = threadIdx.x >> 6, n = threadIdx.x & 63;
-  const int slot = blockIdx.x * 4 + le;
-  const bool active = slot < elem_count;
-  const int e = active ? elem_begin + slot : elem_begin;
-  if (n < 6) {
-    sFace[le][n] = __ldg(&a.el_face[e * 6 + n]);
-    sFcode[le][n] = __ldg(&a.el_face_code[e * 6 + n]);
-  }
-  if (n == 32) sDet[le] = __ldg(&a.geo[static_cast<long long>(e) * GEO + 9]);
+  const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
+  if (threadIdx.x < 2 * NP) sLb[threadIdx.x / NP][threadIdx.x % NP] = c_T.lb[threadIdx.x / NP][threadIdx.x % NP];
+  if (threadIdx.x < ND) sIw[n] = 1.0 / (c_T.wn[i] * c_T.wn[j] * c_T.wn[k]);
   const long long N = a.N;
-  const long long o = static_cast<long long>(e) * ND + n;
-  double yv[NEQ];
-  if (active) {
+  const int nquad = (elem_count + 3) / 4;
+  int q = blockIdx.x;
+  // ids of the first quad
+  int pf = -1, pc = 0;
+  double pd = 0.0;
+  {
+    const int slot = q * 4 + le;
+    if (q < nquad && slot < elem_count) {
+      const int e = elem_begin + slot;
+      if (n < 6) pf = __ldg(&a.el_face[e * 6 + n]), pc = __ldg(&a.el_face_code[e * 6 + n]);
+      if (n == 32) pd = __ldg(&a.geo[static_cast<long long>(e) * GEO + 10]);
+    }
+  }
+  for (int buf = 0; q < nquad; q += gridDim.x, buf ^= 1) {
+    if (n < 6) sFace[buf][le][n] = pf, sFcode[buf][le][n] = pc;
+    if (n == 32) sIdet[buf][le] = pd;
+    __syncthreads();  // also orders the reuse of buffer buf (two iterations ago) behind everybody's reads
+    {  // prefetch the ids of the next quad of this CTA
+      const int slot = (q + gridDim.x) * 4 + le;
+      if (q + gridDim.x < nquad && slot < elem_count) {
+        const int e = elem_begin + slot;
+        if (n < 6) pf = __ldg(&a.el_face[e * 6 + n]), pc = __ldg(&a.el_face_code[e * 6 + n]);
+        if (n == 32) pd = __ldg(&a.geo[static_cast<long long>(e) * GEO + 10]);
+      }
+    }
+    const int slot = q * 4 + le;
+    if (slot >= elem_count) continue;
+    const int e = elem_begin + slot;
+    const long long o = static_cast<long long>(e) * ND + n;
+    double yv[NEQ];
 #pragma unroll
     for (int eq = 0; eq < NEQ; eq++) yv[eq] = a.y[o + eq * N];
-  }
-  __syncthreads();
-  if (!active) return;
-  const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
-  double R[6][NEQ], coef[6];
+    double R[6][NEQ], coef[6];
 #pragma unroll
-  for (int lf = 0; lf < 6; lf++) {
-    const int fc = sFace[le][lf];
-    const int code = sFcode[le][lf];
-    const int side = code & 1;
-    const FacePar fp = decode_face(kFacePar(lf));
-    const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
-    int fa = fp.ss ? ia : NP - 1 - ia, fb = fp.st ? ib : NP - 1 - ib;
-    int a2, b2;  // own local face coordinates -> face (Elem1) coordinates (identity code on side 0)
-    apply_perm<NP>(code >> 1, fa, fb, a2, b2);
-    coef[lf] = fc < 0 ? 0.0 : (side ? sLb[fp.side][c] : -sLb[fp.side][c]);
-    const double *Rp = a.faceRes + static_cast<long long>(fc < 0 ? 0 : fc) * (NEQ * NF2) + a2 + NP * b2;
+    for (int lf = 0; lf < 6; lf++) {
+      const int fc = sFace[buf][le][lf];
+      const int code = sFcode[buf][le][lf];
+      const int side = code & 1;
+      const FacePar fp = decode_face(kFacePar(lf));
+      const int ia = pick3(fp.as, i, j, k), ib = pick3(fp.at, i, j, k), c = pick3(fp.an, i, j, k);
+      const int fa = fp.ss ? ia : NP - 1 - ia, fb = fp.st ? ib : NP - 1 - ib;
+      int a2, b2;  // own local face coordinates -> face (Elem1) coordinates (identity code on side 0)
+      apply_perm<NP>(code >> 1, fa, fb, a2, b2);
+      coef[lf] = fc < 0 ? 0.0 : (side ? sLb[fp.side][c] : -sLb[fp.side][c]);
+      const double *Rp = a.faceRes + static_cast<long long>(fc < 0 ? 0 : fc) * (NEQ * NF2) + a2 + NP * b2;
 #pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) R[lf][eq] = __ldg(Rp + eq * NF2);
-  }
-  double z[NEQ] = {0, 0, 0, 0, 0};
-#pragma unroll
-  for (int lf = 0; lf < 6; lf++)
-#pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) z[eq] += coef[lf] * R[lf][eq];
-  const double im = 1.0 / (sWn[i] * sWn[j] * sWn[k] * sDet[le]);
-  if constexpr (RK) {
-#pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) {
-      const double ki = yv[eq] + z[eq] * im, xi = a.rk.X[o + eq * N];
-      if (a.rk.Z) a.rk.Z[o + eq * N] = (a.rk.zacc ? a.rk.Z[o + eq * N] : xi) + a.rk.B * ki;
-      a.rk.Y[o + eq * N] = xi + a.rk.A * ki;
+      for (int eq = 0; eq < NEQ; eq++) R[lf][eq] = __ldg(Rp + eq * NF2);
     }
-  } else {
+    double z[NEQ] = {0, 0, 0, 0, 0};
 #pragma unroll
-    for (int eq = 0; eq < NEQ; eq++) a.y[o + eq * N] = yv[eq] + z[eq] * im;
+    for (int lf = 0; lf < 6; lf++)
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) z[eq] += coef[lf] * R[lf][eq];
+    const double im = sIw[n] * sIdet[buf][le];
+    if constexpr (RK) {
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) {
+        const double ki = yv[eq] + z[eq] * im, xi = a.rk.X[o + eq * N];
+        if (a.rk.Z) a.rk.Z[o + eq * N] = (a.rk.zacc ? a.rk.Z[o + eq * N] : xi) + a.rk.B * ki;
+        a.rk.Y[o + eq * N] = xi + a.rk.A * ki;
+      }
+    } else {
+#pragma unroll
+      for (int eq = 0; eq < NEQ; eq++) a.y[o + eq * N] = yv[eq] + z[eq] * im;
+    }
   }
 }
 

@@ -1598,12 +1598,23 @@ static void resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count);
 static void elem_fused(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list, int mode) {
   if (count <= 0) return;
   ProfScope ps(c, K_GRAD);
-#define FUSED_LAUNCH(MINB) elem_fused_kernel<MINB><<<std::min(count, c->num_sms * MINB), 64, 0, c->stream>>>(a, begin, count, list, mode)
+// REGS: register cap of the instantiation; the persistent grid is exactly what is resident (occupancy query per device)
+#define FUSED_LAUNCH(REGS)                                                                                             \
+  do {                                                                                                                 \
+    static int per_sm[MAX_DEV] = {};                                                                                   \
+    if (!per_sm[c->device]) {                                                                                          \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[c->device], elem_fused_kernel<REGS>, 64, 0);               \
+      if (per_sm[c->device] < 1) per_sm[c->device] = 1;                                                                \
+    }                                                                                                                  \
+    elem_fused_kernel<REGS><<<std::min(count, c->num_sms * per_sm[c->device]), 64, 0, c->stream>>>(a, begin, count, list, mode); \
+  } while (0)
   switch (c->tune[0]) {
-    case 1: FUSED_LAUNCH(8); break;
-    case 2: FUSED_LAUNCH(6); break;
-    case 3: FUSED_LAUNCH(11); break;
-    default: FUSED_LAUNCH(10); break;
+    case 1: FUSED_LAUNCH(96); break;
+    case 2: FUSED_LAUNCH(104); break;
+    case 3: FUSED_LAUNCH(112); break;
+    case 4: FUSED_LAUNCH(144); break;
+    case 5: FUSED_LAUNCH(168); break;
+    default: FUSED_LAUNCH(128); break;
   }
 #undef FUSED_LAUNCH
 }
@@ -1611,8 +1622,10 @@ static void lift(tpsb_ctx *c, const KernelArgs &a, int begin = 0, int count = -1
   if (count < 0) count = c->NE;
   if (count <= 0) return;
   ProfScope ps(c, K_RESID);
-  if (a.rk.X) lift_kernel<true><<<(count + 3) / 4, 256, 0, c->stream>>>(a, begin, count);
-  else lift_kernel<false><<<(count + 3) / 4, 256, 0, c->stream>>>(a, begin, count);
+  static const int per_sm = getenv("TPSB_LIFT_CTAS") ? std::max(1, atoi(getenv("TPSB_LIFT_CTAS"))) : 2;
+  const int grid = std::min((count + 3) / 4, c->num_sms * per_sm);
+  if (a.rk.X) lift_kernel<true><<<grid, 256, 0, c->stream>>>(a, begin, count);
+  else lift_kernel<false><<<grid, 256, 0, c->stream>>>(a, begin, count);
 }
 // element pass with the exchange of the partition-boundary elements' state overlapped (src/rhs_operator.cpp:349-361)
 static int run_elem_fused(tpsb_ctx *ctx, const KernelArgs &a, int mode) {
