@@ -30,11 +30,21 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 METRIC = "rhs_dof_evals_per_s"
 UNIT = "DOF-evals/s"
 B_PER_DOF = 360.0  # 8*neq*(3+2*dim): U + write gradUp + U + gradUp + write dU/dt
-# algorithmic bytes per DOF for each kernel class ("kernels and rooflines")
-KERNEL_BYTES = {"prim": 80.0, "grad": 160.0, "face_flux": 160.0, "elem_resid": 200.0}
-# DRAM bytes per DOF (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of each fast-path kernel, from the
-# `ncu --set full` capture summarised in profiles/r1q_ncu_full_summary.txt (TGV 64^3, 16.8 M DG nodes)
-NCU_DRAM_BYTES_PER_DOF = {"prim": 77.1, "grad": 347.5, "face_flux": 151.3, "elem_resid": 211.0}
+# algorithmic bytes per DOF for each kernel class ("kernels and rooflines").  The library reports four timer
+# classes; on the fused path (three launches, the default for p = 3 affine meshes) they are
+#   grad       = elem_fused_kernel: U in 40, volume part of dU/dt out 40, face-trace blocks out 120
+#   face_flux  = face_flux_mma_kernel: trace blocks in 120, face residuals out 30
+#   elem_resid = lift_kernel: volume part in 40, face residuals in 30, dU/dt out 40
+KERNEL_BYTES = {"fused": {"grad": 200.0, "face_flux": 150.0, "elem_resid": 110.0},
+                "other": {"prim": 80.0, "grad": 160.0, "face_flux": 160.0, "elem_resid": 200.0}}
+KERNEL_NAMES = {"fused": {"grad": "elem_fused_kernel", "face_flux": "face_flux_mma_kernel", "elem_resid": "lift_kernel"},
+                "other": {"prim": "prim_kernel", "grad": "grad*_kernel", "face_flux": "face_flux*_kernel",
+                          "elem_resid": "elem_resid_kernel"}}
+# DRAM bytes per DOF (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of each kernel, from the
+# `ncu --set full` captures summarised in profiles/ (TGV 64^3, 16.8 M DG nodes)
+NCU_DRAM_BYTES_PER_DOF = {"fused": {"grad": 229.6, "face_flux": 151.6, "elem_resid": 110.2},
+                          "other": {"prim": 77.1, "grad": 347.5, "face_flux": 151.3, "elem_resid": 211.0}}
+NCU_SOURCE = {"fused": "profiles/r2_ncu_full_summary.txt", "other": "profiles/r1q_ncu_full_summary.txt"}
 PROC_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 PI = float(np.pi)
 
@@ -174,8 +184,8 @@ def workload_config(args, grid, sample_n=None):
     n = args.n
     if getattr(args, "workload", "tgv") == "cyl3d":
         return {"workload": "C2 cyl3d restated on a hex O-grid (trilinear elements, inlet/outlet/isothermal wall), "
-                            "DG p=3 GL/GL, dry-air Navier-Stokes", "elements_per_gpu": f"{n}x{4 * n}x{n}", "order": 3,
-                "num_equation": 5, "rank_grid": "1x1x1",
+                            "DG p=3 GL/GL, dry-air Navier-Stokes", "global_elements": f"{n}x{4 * n}x{n}", "order": 3,
+                "num_equation": 5, "rank_grid": "METIS k-way element partition" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "1x1x1",
                 "l2_policy": "inputs exceed the 126 MB L2 for n >= 32; no flush needed"}
     cfg = {"workload": "C5 synthetic periodic 3-D hex box (compressible Taylor-Green), DG p=3 GL/GL, dry-air "
                        "Navier-Stokes, Re=1600, M0=0.1",
@@ -204,6 +214,8 @@ def main():
                     help="strong scaling: a fixed global G^3 box split over the ranks (SURVEY.md 8d: 128); "
                          "default 0 = weak scaling with --n elements per direction per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partitioner", default="metis", choices=["metis", "rcb"], help="element partition of --workload cyl3d at N > 1")
+    ap.add_argument("--no-verify", action="store_true", help="skip the N-rank == 1-rank checksum comparison at N > 1")
     ap.add_argument("--workload", default="tgv", choices=["tgv", "cyl3d"],
                     help="tgv: BASELINE config C5 (the headline line); cyl3d: config C2 restated on a hex O-grid "
                          "(general trilinear path + boundary conditions), single GPU, development measurement")
@@ -264,13 +276,22 @@ def main():
     phys = tps_b200.Physics.dry_air(1, tgv_visc_mult())
     t_setup = time.perf_counter()
     if args.workload == "cyl3d":
-        assert world == 1, "the cyl3d development workload is single-GPU"
-        mesh = tps_b200.cylinder_ogrid_mesh(n, 4 * n, n)
+        # config C2 restated on a hex O-grid; N > 1: STRONG scaling of the one mesh under a METIS k-way element partition
+        # (what MFEM's GeneratePartitioning gives M2ulPhyS, src/M2ulPhyS.cpp:332), irregular halos
+        mesh = tps_b200.cylinder_ogrid_mesh(n, 4 * n, n, order_mode=1)
         specs = [(1, 2, 3, (300.0,)), (2, 0, 2, (1.2, 20.0, 0.0, 0.0)), (3, 1, 0, (101300.0,))]
-        op = tps_b200.RhsOperator(mesh, order=3, physics=tps_b200.Physics.dry_air(1, 50.0), device=local_rank,
-                                  face_attr=mesh["face_attr"], use_bc_in_grad=True,
-                                  bcs=[tps_b200.BcDesc.make(*b) for b in specs])
-        NE = 4 * n ** 3
+        kw = dict(order=3, physics=tps_b200.Physics.dry_air(1, 50.0), device=local_rank, use_bc_in_grad=True,
+                  bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+        if world == 1:
+            op = tps_b200.RhsOperator(mesh, face_attr=mesh["face_attr"], **kw)
+            NE = 4 * n ** 3
+        else:
+            elem_rank, cut = tps_b200.partition_elements(mesh, world, args.partitioner)
+            mesh = tps_b200.partition_mesh(mesh, elem_rank, rank)
+            halo = tps_b200.make_halo_desc(mesh, comm)
+            op = tps_b200.RhsOperator(mesh, face_attr=mesh["face_attr"], halo=halo, num_nbr_elems=mesh["num_nbr_elems"], **kw)
+            NE = mesh["num_elems"]
+            args.partition_info = {"method": args.partitioner, "edge_cut": cut, "elements": np.bincount(elem_rank).tolist()}
     elif world == 1:
         mesh = tps_b200.cartesian_hex_mesh(gn[0], gn[1], gn[2], lo=lo, hi=hi, order_mode=1)
         op = tps_b200.RhsOperator(mesh, order=3, physics=phys, device=local_rank)
@@ -352,7 +373,57 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     finite = bool(torch.isfinite(Y).all().item())
     N_global = N * world
+    if world > 1:
+        ng = torch.tensor([N], dtype=torch.int64, device=dev)
+        dist.all_reduce(ng, op=dist.ReduceOp.SUM)
+        N_global = int(ng.item())
     value = N_global * args.steps / (ms * 1e-3)
+
+    # Order-independent checksums of dU/dt per equation: sum |y| and sum y^2.  In the weak-scaled periodic Taylor-Green
+    # box every rank's block is identical to the N = 1 box (the fields have period 2 pi, the blocks are 2 pi wide), so
+    # at N > 1 each rank must reproduce the single-GPU checksums: rank 0 evaluates the N = 1 operator on the same block
+    # and the run FAILS if any rank differs by more than 1e-12 -- the scaling line carries N-rank == 1-rank parity.
+    def checksums(y, n_local):
+        yy = y.view(5, n_local)
+        return torch.cat([yy.abs().sum(1), (yy * yy).sum(1)])
+    cs = checksums(Y, N)
+    parity = None
+    if world > 1 and args.workload == "tgv" and not args.strong and not args.no_verify:
+        allcs = [torch.empty_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        ref = torch.empty_like(cs)
+        if rank == 0:
+            m1 = tps_b200.cartesian_hex_mesh(n, n, n, lo=(-PI,) * 3, hi=(PI,) * 3, order_mode=1)
+            op1 = tps_b200.RhsOperator(m1, order=3, physics=phys, device=local_rank)
+            ev1 = torch.from_numpy(np.ascontiguousarray(m1["elem_xyz"])).to(dev)
+            U1 = torch.empty_like(U)
+            for e0 in range(0, n ** 3, chunk):
+                e1 = min(n ** 3, e0 + chunk)
+                X = torch.einsum("na,ead->end", shp, ev1[e0:e1]).reshape(-1, 3)
+                x, y, z = X[:, 0], X[:, 1], X[:, 2]
+                u = V0 * torch.sin(x) * torch.cos(y) * torch.cos(z)
+                v = -V0 * torch.cos(x) * torch.sin(y) * torch.cos(z)
+                p = p0 + rho0 * V0 * V0 / 16.0 * (torch.cos(2 * x) + torch.cos(2 * y)) * (torch.cos(2 * z) + 2.0)
+                sl = slice(e0 * 64, e1 * 64)
+                U1[0 * N:1 * N][sl] = rho0
+                U1[1 * N:2 * N][sl] = rho0 * u
+                U1[2 * N:3 * N][sl] = rho0 * v
+                U1[3 * N:4 * N][sl] = 0.0
+                U1[4 * N:5 * N][sl] = p / (gamma - 1.0) + 0.5 * rho0 * (u * u + v * v)
+            Y1 = op1.Mult(U1)
+            ref = checksums(Y1, N)
+            op1.close()
+            del ev1, U1, Y1
+        dist.broadcast(ref, 0)
+        # the w-momentum residual is O(round-off) relative to the others: compare it on the scale of the v-momentum one
+        scale = ref.clone()
+        scale[3], scale[8] = ref[2], ref[7]
+        worst = max(float(((c - ref).abs() / scale).max().item()) for c in allcs)
+        parity = {"criterion": "per-equation sum|dU/dt| and sum (dU/dt)^2 of every rank vs the single-GPU operator on the "
+                               "same block", "max_rel_diff": worst, "tol": 1e-12, "ok": worst <= 1e-12,
+                  "reference_checksum": [float(t) for t in ref.tolist()]}
+        if not parity["ok"]:
+            raise SystemExit(f"multi-rank parity FAILED: max relative checksum difference {worst:.3e} > 1e-12")
 
     # per-kernel device timers (separate, untimed pass): the dominant kernel's own roofline
     op.set_profiling(True)
@@ -363,16 +434,18 @@ def main():
     op.set_profiling(False)
     per_launch = {k: (v[0] / max(v[1], 1)) for k, v in kt.items() if v[1] > 0}
     per_step = {k: v[0] / 3.0 for k, v in kt.items() if v[1] > 0}
-    dom = max((k for k in per_step if k in KERNEL_BYTES), key=lambda k: per_step[k])
+    kind = "fused" if op.path() == "fused" else "other"
+    KB, NCU = KERNEL_BYTES[kind], NCU_DRAM_BYTES_PER_DOF[kind]
+    dom = max((k for k in per_step if k in KB), key=lambda k: per_step[k])
     peak, peak_src = peaks()
     dom_launches_per_step = kt[dom][1] / 3.0
-    dom_bytes_per_launch = KERNEL_BYTES[dom] * N / dom_launches_per_step
+    dom_bytes_per_launch = KB[dom] * N / dom_launches_per_step
     achieved = dom_bytes_per_launch / (per_launch[dom] * 1e-3) / 1e9
     traffic = None
-    if args.workload == "tgv" and dom in NCU_DRAM_BYTES_PER_DOF:
-        traffic = NCU_DRAM_BYTES_PER_DOF[dom] * N / dom_launches_per_step  # bytes per launch, like `achieved`
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r1q_ncu_full_summary.txt (ncu --set full, bytes/DOF x DOFs of this launch)",
+    if args.workload == "tgv" and dom in NCU:
+        traffic = NCU[dom] * N / dom_launches_per_step  # bytes per launch, like `achieved`
+    roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[kind][dom], "timer_class": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": NCU_SOURCE[kind] + " (ncu --set full, bytes/DOF x DOFs of this launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes_per_launch, "launch_ms": per_launch[dom],
                 "kernel_share_of_step": per_step[dom] / sum(per_step.values()),
@@ -419,10 +492,12 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.strong else "weak",
+            "scaling": "strong" if (args.strong or (args.workload == "cyl3d" and world > 1)) else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, grid),
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "finite": finite, "setup_s": t_setup, "dofs_per_gpu": N,
+            "gpu_launches": launches, "finite": finite, "setup_s": t_setup, "dofs_per_gpu": N, "path": op.path(),
+            "checksum": [float(t) for t in cs.tolist()], "multirank_parity": parity,
+            "partition": getattr(args, "partition_info", None),
         }))
     if world > 1:
         dist.barrier()

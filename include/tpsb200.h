@@ -211,6 +211,9 @@ void tpsb_destroy(tpsb_ctx *ctx);
 /* vfes->GetNDofs(), num_equation */
 int64_t tpsb_num_dofs(const tpsb_ctx *ctx);
 int tpsb_num_equation(const tpsb_ctx *ctx);
+/* which kernel set tpsb_create selected: 0 general trilinear 3-D, 1 affine 3-D (four launches), 2 affine 3-D fused
+ * (three launches, p = 3), 3 generic tensor-product path (2-D, Gauss-Lobatto, mixtures)                      */
+int tpsb_get_path(const tpsb_ctx *ctx);
 
 /* RHSoperator::Mult(const Vector &x, Vector &y) const   (src/rhs_operator.cpp:343-464)
  * d_x, d_y: DEVICE pointers, neq*N doubles each, byNODES.  Asynchronous on the context stream.    */
@@ -341,6 +344,21 @@ int tpsb_mk_partition(const int n[3], const double lo[3], const double hi[3], co
                       const int procs[3], int rank, int order_mode, tpsb_mk_part_sizes *sizes, int *elem_verts,
                       double *elem_xyz, int64_t *elem_gid, int *face_el1, int *face_el2, int *face_inf1,
                       int *face_inf2, int *nbr_rank, int *send_offset, int *send_elems, int *recv_offset);
+
+/* General element partitions (any conforming hexahedral mesh): the stand-in for Mesh::GeneratePartitioning(nprocs, 1)
+ * -- METIS 5 k-way on the element dual graph, src/M2ulPhyS.cpp:332,362 -- or recursive coordinate bisection, and for
+ * ParMesh's local numbering + face-neighbour tables (src/M2ulPhyS.cpp:421): local elements in global order, then the
+ * face-neighbour elements grouped by owner and sorted by global element id.  tpsb_mk_partition_general is called
+ * twice like tpsb_mk_partition (all output pointers NULL: sizes only); face_gface[f] is the global (MFEM) number of
+ * local face f, for carrying boundary attributes over.                                                       */
+int tpsb_mk_partition_metis(int num_elems, int num_faces, const int *face_el1, const int *face_el2, int nparts,
+                            int *elem_rank, int64_t *edge_cut);
+int tpsb_mk_partition_rcb(int num_elems, const double *elem_xyz, int nparts, int *elem_rank);
+int tpsb_mk_partition_general(int num_elems, const int *elem_verts, const double *elem_xyz, int num_faces,
+                              const int *gface_el1, const int *gface_el2, const int *elem_rank, int rank,
+                              tpsb_mk_part_sizes *sizes, int *l_elem_verts, double *l_elem_xyz, int64_t *elem_gid,
+                              int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface, int *nbr_rank,
+                              int *send_offset, int *send_elems, int *recv_offset);
 
 /* ---- communicator bootstrap for the NCCL face-neighbour exchange ----
  * unique_id: 128-byte ncclUniqueId produced on rank 0 by tpsb_comm_get_unique_id and broadcast by

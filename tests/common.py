@@ -76,3 +76,44 @@ def box_face_attrs(m, lo, hi):
                 attr[f] = 2 * d + 2
         assert attr[f] > 0, f
     return attr
+
+
+def cube_rotations():
+    """The 24 orientation-preserving symmetries of the reference cube as vertex permutations p: vertex a of the
+    rotated element is vertex p[a] of the original one (MFEM hex vertex order, tables.hpp HEX_VERT)."""
+    import itertools
+    hv = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=float)
+    perms = []
+    for axes in itertools.permutations(range(3)):
+        for signs in itertools.product((1, -1), repeat=3):
+            R = np.zeros((3, 3))
+            for r in range(3):
+                R[r, axes[r]] = signs[r]
+            if np.linalg.det(R) < 0:
+                continue
+            old = (hv - 0.5) @ R.T + 0.5
+            perms.append([int(np.argmin(np.abs(hv - o).sum(axis=1))) for o in old])
+    assert len(perms) == 24 and len({tuple(p) for p in perms}) == 24
+    return np.array(perms)
+
+
+def rotate_elements(m, seed=SEED):
+    """Relabel every element of a hex mesh by a random cube rotation (seeded) and rebuild the face tables: the mesh an
+    unstructured generator would hand over -- all eight face orientations and arbitrary (local face, local face)
+    pairings occur (src/M2ulPhyS.cpp:937-958), unlike on a Cartesian numbering."""
+    import tps_b200
+    from tps_b200 import capi
+    rot = cube_rotations()
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, 24, size=m["elem_verts"].shape[0])
+    idx = rot[pick]                                      # [NE, 8]
+    ev = np.ascontiguousarray(np.take_along_axis(m["elem_verts"], idx, axis=1), dtype=np.int32)
+    xyz = np.ascontiguousarray(np.take_along_axis(m["elem_xyz"], idx[:, :, None], axis=1))
+    NE = ev.shape[0]
+    f = [np.zeros(6 * NE, np.int32) for _ in range(4)]
+    nf = tps_b200.lib().tpsb_mk_build_faces(NE, capi._ip(ev), *(capi._ip(a) for a in f))
+    assert nf > 0
+    out = dict(m)
+    out.update(elem_verts=ev, elem_xyz=xyz, face_el1=f[0][:nf].copy(), face_el2=f[1][:nf].copy(),
+               face_inf1=f[2][:nf].copy(), face_inf2=f[3][:nf].copy())
+    return out

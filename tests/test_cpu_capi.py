@@ -43,3 +43,34 @@ def test_reference_tables_are_consistent(lib_built):
         # exactness that licenses the collapsed gradient face term: (p+2)-pt rule of l_a * l_b = w_a delta_ab
         M = T["P"].T @ np.diag(T["wq"]) @ T["P"]
         assert np.abs(M - np.diag(T["wn"])).max() < 1e-15
+
+
+def test_fused_swizzle_is_conflict_free():
+    """The shared-memory node swizzle of elem_fused_kernel (rhs_fused.cuh: fused_swz) sends every quarter-warp access
+    pattern of the kernel -- node order, DMMA B fragments and D-fragment stores along x / y / z, line tasks along
+    x / y / z -- to eight distinct 16-byte bank groups, and is a permutation of the 64 nodes."""
+    src = open(os.path.join(ROOT, "tps_b200", "csrc", "rhs_fused.cuh")).read()
+    assert "return (n & 0x38) | ((n & 7) ^ ((n >> 2) & 2) ^ (((n >> 4) & 1) * 5) ^ ((n >> 4) & 2));" in src
+
+    def swz(n):
+        return (n & 0x38) | ((n & 7) ^ ((n >> 2) & 2) ^ (((n >> 4) & 1) * 5) ^ ((n >> 4) & 2))
+
+    assert sorted(swz(n) for n in range(64)) == list(range(64))
+    stride = [1, 4, 16]
+
+    def base(d, L):
+        return 4 * L if d == 0 else ((L & 3) + 16 * (L >> 2) if d == 1 else L)
+
+    pats = [[8 * q + t for t in range(8)] for q in range(8)]  # one thread per node
+    for d in range(3):
+        for h in range(2):
+            for t in range(4):  # B fragment: lanes (fr, fk) = (line 8h + fr, position fk), a quarter warp = two lines
+                pats.append([base(d, 8 * h + fr) + fk * stride[d] for fr in (2 * t, 2 * t + 1) for fk in range(4)])
+            for t in range(2):  # D-fragment stores of rows 0-3: lanes (row, fk) -> lines 8h + 2fk (+1)
+                for s in range(2):
+                    pats.append([base(d, 8 * h + 2 * fk + s) + row * stride[d] for row in (2 * t, 2 * t + 1) for fk in range(4)])
+        for m in range(4):  # line tasks: lane = line, all at position m
+            for t in range(2):
+                pats.append([base(d, L) + m * stride[d] for L in range(8 * t, 8 * t + 8)])
+    for nodes in pats:
+        assert len({swz(n) % 8 for n in nodes}) == 8, nodes

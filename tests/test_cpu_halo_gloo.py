@@ -97,3 +97,53 @@ def test_partition_covers_global_mesh_eight_ranks(lib_built):
             qi = list(pq["nbr_rank"]).index(r)
             recv = pq["elem_gid"][pq["num_elems"] + pq["recv_offset"][qi]:pq["num_elems"] + pq["recv_offset"][qi + 1]]
             assert np.array_equal(sent, recv)
+
+
+@pytest.mark.parametrize("method", ["metis", "rcb"])
+@pytest.mark.parametrize("nparts", [2, 4, 8])
+def test_general_partition_of_unstructured_mesh(lib_built, method, nparts):
+    """METIS k-way / RCB element maps of the O-grid (config C2 restated) with every element relabelled by a random cube
+    rotation, split with tpsb_mk_partition_general: the pieces cover the mesh, send lists mirror the peers' halo lists,
+    shared faces agree on both sides, boundary attributes follow their faces."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from common import rotate_elements
+    from meshref import HEX_FACE_VERT
+    g0 = tps_b200.cylinder_ogrid_mesh(5, 16, 3)
+    g = rotate_elements(g0)
+    # carry the boundary attributes over the renumbering through the faces' vertex sets
+    key = {}
+    for f in np.nonzero(g0["face_el2"] < 0)[0]:
+        key[tuple(sorted(g0["elem_verts"][g0["face_el1"][f], HEX_FACE_VERT[g0["face_inf1"][f] // 64]].tolist()))] = g0["face_attr"][f]
+    attr = np.zeros(len(g["face_el1"]), np.int32)
+    for f in np.nonzero(g["face_el2"] < 0)[0]:
+        attr[f] = key[tuple(sorted(g["elem_verts"][g["face_el1"][f], HEX_FACE_VERT[g["face_inf1"][f] // 64]].tolist()))]
+    g["face_attr"] = attr
+    elem_rank, cut = tps_b200.partition_elements(g, nparts, method)
+    sizes = np.bincount(elem_rank, minlength=nparts)
+    assert sizes.min() > 0 and sizes.max() <= 1.1 * sizes.mean() + 2
+    cross = int(((g["face_el2"] >= 0) & (elem_rank[g["face_el1"]] != elem_rank[np.maximum(g["face_el2"], 0)])).sum())
+    if cut is not None:
+        assert cut == cross
+    parts = [tps_b200.partition_mesh(g, elem_rank, r) for r in range(nparts)]
+    gids = np.sort(np.concatenate([p["elem_gid"][:p["num_elems"]] for p in parts]))
+    assert np.array_equal(gids, np.arange(g["elem_xyz"].shape[0]))
+    shared = 0
+    for r, p in enumerate(parts):
+        ne = p["num_elems"]
+        assert (p["face_el1"] < ne).all()
+        assert np.array_equal(p["elem_xyz"][:ne], g["elem_xyz"][p["elem_gid"][:ne]])
+        shared += int((p["face_el2"] >= ne).sum())
+        b = p["face_el2"] < 0
+        assert np.array_equal(p["face_attr"][b], g["face_attr"][p["face_gface"][b]]) and (p["face_attr"][b] > 0).all()
+        assert (p["face_attr"][~b] == 0).all()
+        for pi, qk in enumerate(p["nbr_rank"]):
+            sent = p["elem_gid"][p["send_elems"][p["send_offset"][pi]:p["send_offset"][pi + 1]]]
+            pq = parts[qk]
+            qi = list(pq["nbr_rank"]).index(r)
+            recv = pq["elem_gid"][pq["num_elems"] + pq["recv_offset"][qi]:pq["num_elems"] + pq["recv_offset"][qi + 1]]
+            assert np.array_equal(sent, recv)
+    assert shared == 2 * cross
+    local = sum(int(((p["face_el2"] >= 0) & (p["face_el2"] < p["num_elems"])).sum()) for p in parts)
+    bdr = sum(int((p["face_el2"] < 0).sum()) for p in parts)
+    assert local + cross + bdr == len(g["face_el1"])

@@ -197,7 +197,8 @@ EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tp
            "tpsb_rhs_mult", "tpsb_rhs_mult_host", "tpsb_update_primitives", "tpsb_update_gradients",
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
            "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_get_hmin", "tpsb_solve_step", "tpsb_check_state", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
-           "tpsb_comm_init_rank", "tpsb_comm_destroy"]
+           "tpsb_comm_init_rank", "tpsb_comm_destroy", "tpsb_get_path", "tpsb_mk_partition_metis", "tpsb_mk_partition_rcb",
+           "tpsb_mk_partition_general"]
 
 
 def lib():
@@ -227,6 +228,7 @@ def lib():
     L.tpsb_num_dofs.restype = C.c_int64
     L.tpsb_num_dofs.argtypes = [vp]
     L.tpsb_num_equation.argtypes = [vp]
+    L.tpsb_get_path.argtypes = [vp]
     L.tpsb_rhs_mult.argtypes = [vp, vp, vp]
     L.tpsb_rhs_mult_host.argtypes = [vp, vp, vp]
     L.tpsb_update_primitives.argtypes = [vp, vp]
@@ -256,6 +258,11 @@ def lib():
     L.tpsb_mk_build_faces2d.argtypes = [C.c_int, ip, ip, ip, ip, ip]
     L.tpsb_mk_partition.argtypes = [ip, dp, dp, ip, ip, C.c_int, C.c_int, C.POINTER(PartSizes), ip, dp,
                                     C.POINTER(C.c_int64), ip, ip, ip, ip, ip, ip, ip, ip]
+    i64p = C.POINTER(C.c_int64)
+    L.tpsb_mk_partition_metis.argtypes = [C.c_int, C.c_int, ip, ip, C.c_int, ip, i64p]
+    L.tpsb_mk_partition_rcb.argtypes = [C.c_int, dp, C.c_int, ip]
+    L.tpsb_mk_partition_general.argtypes = [C.c_int, ip, dp, C.c_int, ip, ip, ip, C.c_int, C.POINTER(PartSizes), ip, dp, i64p,
+                                            ip, ip, ip, ip, ip, ip, ip, ip, ip]
     L.tpsb_comm_get_unique_id.argtypes = [C.c_char_p]
     L.tpsb_comm_init_rank.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.tpsb_comm_destroy.argtypes = [vp]
@@ -432,6 +439,60 @@ def cartesian_hex_partition(n, procs, rank, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0,
                 face_el1=f[0][:nf].copy(), face_el2=f[1][:nf].copy(), face_inf1=f[2][:nf].copy(),
                 face_inf2=f[3][:nf].copy(), nbr_rank=nbr[:sz.num_nbr_ranks].copy(), send_offset=so, recv_offset=ro,
                 send_elems=se[:sz.num_send].copy())
+
+
+def partition_elements(mesh, nparts, method="metis"):
+    """Element -> rank map of a hexahedral mesh: METIS k-way on the dual graph (what MFEM's GeneratePartitioning calls,
+    src/M2ulPhyS.cpp:332) or recursive coordinate bisection.  Returns (elem_rank int32[NE], edge cut or None)."""
+    L = lib()
+    ne = mesh["elem_xyz"].shape[0]
+    rank = np.zeros(ne, np.int32)
+    if method == "metis":
+        el1 = np.ascontiguousarray(mesh["face_el1"], np.int32)
+        el2 = np.ascontiguousarray(mesh["face_el2"], np.int32)
+        cut = C.c_int64(0)
+        rc = L.tpsb_mk_partition_metis(ne, len(el1), _ip(el1), _ip(el2), nparts, _ip(rank), C.byref(cut))
+        if rc != 0:
+            raise TpsbError(f"tpsb_mk_partition_metis failed ({rc})")
+        return rank, int(cut.value)
+    xyz = np.ascontiguousarray(mesh["elem_xyz"], np.float64)
+    rc = L.tpsb_mk_partition_rcb(ne, _dp(xyz), nparts, _ip(rank))
+    if rc != 0:
+        raise TpsbError(f"tpsb_mk_partition_rcb failed ({rc})")
+    return rank, None
+
+
+def partition_mesh(mesh, elem_rank, rank):
+    """meshkit: this rank's piece of a global hexahedral mesh under an arbitrary element -> rank map, in ParMesh's local
+    numbering with its face-neighbour (halo) tables; same dict as cartesian_hex_partition plus 'face_attr' when the
+    global mesh carries boundary attributes."""
+    L = lib()
+    ev = np.ascontiguousarray(mesh["elem_verts"], np.int32)
+    xyz = np.ascontiguousarray(mesh["elem_xyz"], np.float64)
+    g1, g2 = np.ascontiguousarray(mesh["face_el1"], np.int32), np.ascontiguousarray(mesh["face_el2"], np.int32)
+    er = np.ascontiguousarray(elem_rank, np.int32)
+    sz = PartSizes()
+    head = (ev.shape[0], _ip(ev), _dp(xyz), len(g1), _ip(g1), _ip(g2), _ip(er), rank, C.byref(sz))
+    rc = L.tpsb_mk_partition_general(*head, *([None] * 12))
+    if rc != 0:
+        raise TpsbError(f"tpsb_mk_partition_general failed ({rc})")
+    ne, nh, nf = sz.num_elems, sz.num_nbr_elems, sz.num_faces
+    lev, lxyz, gid = np.zeros((ne + nh, 8), np.int32), np.zeros((ne + nh, 8, 3)), np.zeros(ne + nh, np.int64)
+    f = [np.zeros(max(nf, 1), np.int32) for _ in range(5)]
+    nbr = np.zeros(max(sz.num_nbr_ranks, 1), np.int32)
+    so, ro = np.zeros(sz.num_nbr_ranks + 1, np.int32), np.zeros(sz.num_nbr_ranks + 1, np.int32)
+    se = np.zeros(max(sz.num_send, 1), np.int32)
+    rc = L.tpsb_mk_partition_general(*head, _ip(lev), _dp(lxyz), gid.ctypes.data_as(C.POINTER(C.c_int64)), _ip(f[0]), _ip(f[1]),
+                                     _ip(f[2]), _ip(f[3]), _ip(f[4]), _ip(nbr), _ip(so), _ip(se), _ip(ro))
+    if rc != 0:
+        raise TpsbError(f"tpsb_mk_partition_general failed ({rc})")
+    out = dict(num_elems=ne, num_nbr_elems=nh, elem_verts=lev, elem_xyz=lxyz, elem_gid=gid,
+               face_el1=f[0][:nf].copy(), face_el2=f[1][:nf].copy(), face_inf1=f[2][:nf].copy(), face_inf2=f[3][:nf].copy(),
+               face_gface=f[4][:nf].copy(), nbr_rank=nbr[:sz.num_nbr_ranks].copy(), send_offset=so, recv_offset=ro,
+               send_elems=se[:sz.num_send].copy())
+    if "face_attr" in mesh:
+        out["face_attr"] = np.ascontiguousarray(np.asarray(mesh["face_attr"], np.int32)[out["face_gface"]])
+    return out
 
 
 def make_halo_desc(part, nccl_comm):
@@ -616,3 +677,9 @@ class RhsOperator:
 
     def launch_count(self):
         return self.L.tpsb_launch_count(self.ctx)
+
+    PATHS = ("general", "fast", "fused", "generic")
+
+    def path(self):
+        """Kernel set selected at create: general | fast | fused | generic."""
+        return self.PATHS[self.L.tpsb_get_path(self.ctx)]

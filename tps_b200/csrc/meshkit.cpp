@@ -335,6 +335,189 @@ extern "C" int tpsb_mk_partition(const int n[3], const double lo[3], const doubl
   return TPSB_OK;
 }
 
+// ---- general element partitions (unstructured meshes: the O-grid of config C2, rotated / warped boxes) ----
+// METIS 5 k-way partition of the element dual graph: what MFEM's Mesh::GeneratePartitioning(nprocs, 1) calls
+// (src/M2ulPhyS.cpp:332,362).  The METIS library is the static one shipped with the CUDA toolkit (cuSOLVER's
+// re-ordering dependency; no header is installed): idx_t = int64, real_t = float, probed with a known graph.
+extern "C" int METIS_PartGraphKway(int64_t *nvtxs, int64_t *ncon, int64_t *xadj, int64_t *adjncy, int64_t *vwgt,
+                                   int64_t *vsize, int64_t *adjwgt, int64_t *nparts, float *tpwgts, float *ubvec,
+                                   int64_t *options, int64_t *edgecut, int64_t *part);
+extern "C" int METIS_SetDefaultOptions(int64_t *options);
+
+extern "C" int tpsb_mk_partition_metis(int num_elems, int num_faces, const int *face_el1, const int *face_el2, int nparts,
+                                       int *elem_rank, int64_t *edge_cut) {
+  if (num_elems <= 0 || nparts < 1 || !face_el1 || !face_el2 || !elem_rank) return TPSB_EINVAL;
+  if (nparts == 1) {
+    std::fill(elem_rank, elem_rank + num_elems, 0);
+    if (edge_cut) *edge_cut = 0;
+    return TPSB_OK;
+  }
+  std::vector<int64_t> xadj(static_cast<size_t>(num_elems) + 1, 0), adj;
+  for (int f = 0; f < num_faces; f++)
+    if (face_el2[f] >= 0 && face_el2[f] < num_elems && face_el2[f] != face_el1[f]) {
+      xadj[face_el1[f] + 1]++;
+      xadj[face_el2[f] + 1]++;
+    }
+  for (int e = 0; e < num_elems; e++) xadj[e + 1] += xadj[e];
+  adj.resize(static_cast<size_t>(xadj[num_elems]));
+  std::vector<int64_t> pos(xadj.begin(), xadj.end() - 1);
+  for (int f = 0; f < num_faces; f++)
+    if (face_el2[f] >= 0 && face_el2[f] < num_elems && face_el2[f] != face_el1[f]) {
+      adj[static_cast<size_t>(pos[face_el1[f]]++)] = face_el2[f];
+      adj[static_cast<size_t>(pos[face_el2[f]]++)] = face_el1[f];
+    }
+  int64_t nv = num_elems, ncon = 1, np = nparts, cut = 0, opts[40];
+  METIS_SetDefaultOptions(opts);
+  std::vector<int64_t> part(static_cast<size_t>(num_elems), 0);
+  const int rc = METIS_PartGraphKway(&nv, &ncon, xadj.data(), adj.data(), nullptr, nullptr, nullptr, &np, nullptr, nullptr,
+                                     opts, &cut, part.data());
+  if (rc != 1) return TPSB_EINVAL;  // METIS_OK == 1
+  for (int e = 0; e < num_elems; e++) elem_rank[e] = static_cast<int>(part[e]);
+  if (edge_cut) *edge_cut = cut;
+  return TPSB_OK;
+}
+
+// Recursive coordinate bisection of the element centroids (nparts a power of two or not: the split is proportional).
+extern "C" int tpsb_mk_partition_rcb(int num_elems, const double *elem_xyz, int nparts, int *elem_rank) {
+  if (num_elems <= 0 || nparts < 1 || !elem_xyz || !elem_rank) return TPSB_EINVAL;
+  std::vector<double> cen(static_cast<size_t>(num_elems) * 3, 0.0);
+  for (int e = 0; e < num_elems; e++)
+    for (int a = 0; a < 8; a++)
+      for (int d = 0; d < 3; d++) cen[static_cast<size_t>(e) * 3 + d] += 0.125 * elem_xyz[(static_cast<size_t>(e) * 8 + a) * 3 + d];
+  std::vector<int> ids(num_elems);
+  for (int e = 0; e < num_elems; e++) ids[e] = e;
+  struct Job {
+    int b, n, r0, np;
+  };
+  std::vector<Job> stack{{0, num_elems, 0, nparts}};
+  while (!stack.empty()) {
+    const Job j = stack.back();
+    stack.pop_back();
+    if (j.np == 1) {
+      for (int t = j.b; t < j.b + j.n; t++) elem_rank[ids[t]] = j.r0;
+      continue;
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int t = j.b; t < j.b + j.n; t++)
+      for (int d = 0; d < 3; d++) {
+        lo[d] = std::min(lo[d], cen[static_cast<size_t>(ids[t]) * 3 + d]);
+        hi[d] = std::max(hi[d], cen[static_cast<size_t>(ids[t]) * 3 + d]);
+      }
+    int ax = 0;
+    for (int d = 1; d < 3; d++)
+      if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+    const int npl = j.np / 2, nl = static_cast<int>(static_cast<int64_t>(j.n) * npl / j.np);
+    std::nth_element(ids.begin() + j.b, ids.begin() + j.b + nl, ids.begin() + j.b + j.n, [&](int x, int y) {
+      const double cx = cen[static_cast<size_t>(x) * 3 + ax], cy = cen[static_cast<size_t>(y) * 3 + ax];
+      return cx < cy || (cx == cy && x < y);
+    });
+    stack.push_back({j.b, nl, j.r0, npl});
+    stack.push_back({j.b + nl, j.n - nl, j.r0 + npl, j.np - npl});
+  }
+  return TPSB_OK;
+}
+
+// This rank's piece of a GLOBAL hexahedral mesh under an arbitrary element -> rank map: ParMesh's local numbering
+// (local elements in global order first, then the face-neighbour elements grouped by owner and sorted by global id,
+// the order in which the owner sends them; src/M2ulPhyS.cpp:421, ExchangeFaceNbrData).  Two calls: sizes, then fill.
+//   face_gface[f]  global face of local face f (so the caller can carry boundary attributes over)
+extern "C" int tpsb_mk_partition_general(int num_elems, const int *elem_verts, const double *elem_xyz, int num_faces,
+                                         const int *gface_el1, const int *gface_el2, const int *elem_rank, int rank,
+                                         tpsb_mk_part_sizes *sizes, int *l_elem_verts, double *l_elem_xyz, int64_t *elem_gid,
+                                         int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface,
+                                         int *nbr_rank, int *send_offset, int *send_elems, int *recv_offset) {
+  if (num_elems <= 0 || !elem_verts || !gface_el1 || !gface_el2 || !elem_rank || !sizes) return TPSB_EINVAL;
+  std::vector<int> loc, lid(static_cast<size_t>(num_elems), -1);
+  for (int e = 0; e < num_elems; e++)
+    if (elem_rank[e] == rank) {
+      lid[e] = static_cast<int>(loc.size());
+      loc.push_back(e);
+    }
+  const int NE = static_cast<int>(loc.size());
+  if (NE == 0) return TPSB_EINVAL;
+  std::vector<std::pair<int, int>> halo, send;  // (owner, global element), (peer, global element)
+  for (int f = 0; f < num_faces; f++) {
+    const int e1 = gface_el1[f], e2 = gface_el2[f];
+    if (e2 < 0) continue;
+    const int r1 = elem_rank[e1], r2 = elem_rank[e2];
+    if (r1 == r2) continue;
+    if (r1 == rank) halo.emplace_back(r2, e2), send.emplace_back(r2, e1);
+    if (r2 == rank) halo.emplace_back(r1, e1), send.emplace_back(r1, e2);
+  }
+  std::sort(halo.begin(), halo.end());
+  halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+  std::sort(send.begin(), send.end());
+  send.erase(std::unique(send.begin(), send.end()), send.end());
+  std::vector<int> peers;
+  for (auto &h : halo)
+    if (peers.empty() || peers.back() != h.first) peers.push_back(h.first);
+  const int NEH = static_cast<int>(halo.size());
+  std::vector<int> ev(static_cast<size_t>(NE + NEH) * 8);
+  for (int e = 0; e < NE + NEH; e++) {
+    const int g = e < NE ? loc[e] : halo[e - NE].second;
+    std::copy(&elem_verts[static_cast<size_t>(g) * 8], &elem_verts[static_cast<size_t>(g) * 8] + 8, &ev[static_cast<size_t>(e) * 8]);
+    if (elem_gid) elem_gid[e] = g;
+    if (l_elem_xyz && elem_xyz)
+      std::copy(&elem_xyz[static_cast<size_t>(g) * 24], &elem_xyz[static_cast<size_t>(g) * 24] + 24, &l_elem_xyz[static_cast<size_t>(e) * 24]);
+  }
+  std::vector<int> f1(static_cast<size_t>(NE + NEH) * 6), f2(f1.size()), i1(f1.size()), i2(f1.size());
+  const int nf_all = tpsb_mk_build_faces(NE + NEH, ev.data(), f1.data(), f2.data(), i1.data(), i2.data());
+  if (nf_all < 0) return TPSB_EINVAL;
+  // global face of (global element, local face): faces are found again through their sorted vertex triple
+  std::unordered_map<Key, int, KeyHash> gtab;
+  if (face_gface) {
+    gtab.reserve(static_cast<size_t>(num_faces) * 2);
+    std::vector<char> done(static_cast<size_t>(num_faces), 0);
+    for (int e = 0; e < num_elems; e++)
+      for (int lf = 0; lf < 6; lf++) {
+        int s[4];
+        for (int k = 0; k < 4; k++) s[k] = elem_verts[static_cast<size_t>(e) * 8 + tpsb::HEX_FACE_VERT[lf][k]];
+        std::sort(s, s + 4);
+        const Key key{s[0], s[1], s[2]};
+        if (gtab.find(key) == gtab.end()) gtab.emplace(key, static_cast<int>(gtab.size()));  // first appearance == MFEM face number
+      }
+  }
+  int nf = 0;
+  for (int f = 0; f < nf_all; f++) {
+    if (f1[f] >= NE) continue;  // face between face-neighbour elements only
+    if (face_el1) {
+      face_el1[nf] = f1[f];
+      face_el2[nf] = f2[f];
+      face_inf1[nf] = i1[f];
+      face_inf2[nf] = i2[f];
+      if (face_gface) {
+        int s[4];
+        for (int k = 0; k < 4; k++) s[k] = ev[static_cast<size_t>(f1[f]) * 8 + tpsb::HEX_FACE_VERT[i1[f] / 64][k]];
+        std::sort(s, s + 4);
+        face_gface[nf] = gtab.at(Key{s[0], s[1], s[2]});
+      }
+    }
+    nf++;
+  }
+  sizes->num_elems = NE;
+  sizes->num_nbr_elems = NEH;
+  sizes->num_faces = nf;
+  sizes->num_nbr_ranks = static_cast<int>(peers.size());
+  sizes->num_send = static_cast<int>(send.size());
+  if (l_elem_verts) std::copy(ev.begin(), ev.end(), l_elem_verts);
+  if (nbr_rank && send_offset && send_elems && recv_offset) {
+    size_t hp = 0, sp = 0;
+    for (size_t p = 0; p < peers.size(); p++) {
+      nbr_rank[p] = peers[p];
+      recv_offset[p] = static_cast<int>(hp);
+      send_offset[p] = static_cast<int>(sp);
+      while (hp < halo.size() && halo[hp].first == peers[p]) hp++;
+      while (sp < send.size() && send[sp].first == peers[p]) {
+        send_elems[sp] = lid[send[sp].second];
+        sp++;
+      }
+    }
+    recv_offset[peers.size()] = static_cast<int>(hp);
+    send_offset[peers.size()] = static_cast<int>(sp);
+  }
+  return TPSB_OK;
+}
+
 // Flattened RefTables for the tests: [np, nq, xn(np), wn(np), D(np*np), lb(2*np), xq(nq), wq(nq), P(nq*np),
 // face_base(6*np^2), face_cstride(6), face_side(6), perm(8*np^2), iperm(8*np^2)]
 extern "C" int tpsb_get_ref_tables(int order, double *out, int cap) {

@@ -1247,6 +1247,7 @@ int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *e
 
 int64_t tpsb_num_dofs(const tpsb_ctx *c) { return c ? c->N : 0; }
 int tpsb_num_equation(const tpsb_ctx *c) { return c ? c->neq : 0; }
+int tpsb_get_path(const tpsb_ctx *c) { return !c ? -1 : c->generic ? 3 : c->fused ? 2 : c->fast ? 1 : 0; }
 int64_t tpsb_launch_count(const tpsb_ctx *c) { return c ? c->launches : 0; }
 
 int tpsb_get_element_to_faces(const tpsb_ctx *c, int *out) {
