@@ -315,7 +315,17 @@ def main():
     shp = torch.ones(64, 8, dtype=torch.float64, device=dev)
     for d in range(3):
         shp = shp * torch.where(hv[None, :, d] > 0, xi[:, None, d], 1.0 - xi[:, None, d])
-    ev = torch.from_numpy(np.ascontiguousarray(mesh["elem_xyz"][:NE])).to(dev)
+    exyz = mesh["elem_xyz"][:NE]
+    if world > 1 and args.workload == "tgv" and not args.strong:
+        # Every block of the weak-scaled box sees the same 2 pi-periodic fields.  Evaluate them at the coordinates the
+        # N = 1 box gives the element (same expression as meshkit: lo + index * h), so that every rank's input is
+        # bit-identical to the single-GPU input and the checksum comparison below tests the operator, not sin(x + 2 pi).
+        gid = mesh["elem_gid"][:NE]
+        gi = np.stack([gid % gn[0], (gid // gn[0]) % gn[1], gid // (gn[0] * gn[1])], 1) % n          # [NE, 3] block-local
+        hvn = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
+        h1 = (PI - (-PI)) / n
+        exyz = -PI + (gi[:, None, :] + hvn[None, :, :]).astype(np.float64) * h1
+    ev = torch.from_numpy(np.ascontiguousarray(exyz)).to(dev)
     U = torch.empty(5 * N, dtype=torch.float64, device=dev)
     rho0, p0, gamma = 1.2, 101300.0, 1.4
     V0 = 0.1 * float(np.sqrt(gamma * p0 / rho0))
@@ -415,12 +425,18 @@ def main():
             op1.close()
             del ev1, U1, Y1
         dist.broadcast(ref, 0)
-        # the w-momentum residual is O(round-off) relative to the others: compare it on the scale of the v-momentum one
+        # d(rho)/dt of the initially solenoidal Taylor-Green field is a ~1e-5 cancellation residue of its flux divergence
+        # (sum|d rho/dt| ~ 1e3 against sum|d(rho u)/dt| / V0 ~ 1e8), so its checksums are compared on the scale of that
+        # flux divergence; every other equation on its own scale
         scale = ref.clone()
-        scale[3], scale[8] = ref[2], ref[7]
-        worst = max(float(((c - ref).abs() / scale).max().item()) for c in allcs)
+        scale[0], scale[5] = ref[1] / V0, ref[6] / (V0 * V0)
+        per_rank = [((c - ref).abs() / scale) for c in allcs]
+        worst = max(float(d.max().item()) for d in per_rank)
+        raw = max(float(((c - ref).abs() / ref).max().item()) for c in allcs)
         parity = {"criterion": "per-equation sum|dU/dt| and sum (dU/dt)^2 of every rank vs the single-GPU operator on the "
-                               "same block", "max_rel_diff": worst, "tol": 1e-12, "ok": worst <= 1e-12,
+                               "same block (bit-identical inputs); d(rho)/dt on the scale sum|d(rho u)/dt| / V0 of its flux "
+                               "divergence", "max_rel_diff": worst, "max_rel_diff_unscaled": raw, "tol": 1e-12,
+                  "ok": worst <= 1e-12, "per_equation_rel_diff": [float(t) for t in torch.stack(per_rank).max(0).values.tolist()],
                   "reference_checksum": [float(t) for t in ref.tolist()]}
         if not parity["ok"]:
             raise SystemExit(f"multi-rank parity FAILED: max relative checksum difference {worst:.3e} > 1e-12")

@@ -230,6 +230,10 @@ int tpsb_update_gradients(tpsb_ctx *ctx, const double *d_x, int primitives_updat
 /* Views of the context-owned fields: M2ulPhyS::getPrimitiveGF / getGradientGF (src/M2ulPhyS.hpp:368-470).
  * Up: neq*N, gradUp: dim*neq*N doubles, device memory, valid until destroy.                       */
 int tpsb_get_fields(tpsb_ctx *ctx, double **d_Up, double **d_gradUp);
+/* Note (fused path, tpsb_get_path() == 2): tpsb_rhs_mult keeps Up and gradUp on chip.  tpsb_get_fields after a
+ * tpsb_rhs_mult therefore re-evaluates them from the vector of that call -- which must still be alive and unchanged
+ * -- exactly as the reference's members would read; tpsb_update_primitives / tpsb_update_gradients are the explicit
+ * form (RHSoperator::updatePrimitives / updateGradients, what M2ulPhyS calls before output and averaging).     */
 /* The solution grid function U_ that SourceTerm / AxisymmetricSource read the conserved state from
  * (src/source_term.cpp:66,77,121): in Runge-Kutta stages it is NOT the stage vector x handed to Mult, while
  * Up / gradUp are computed from x -- the reference's behaviour, kept (parity trap 1).
@@ -259,7 +263,10 @@ int tpsb_set_reaction_rate_field(tpsb_ctx *ctx, const double *d_rates, int num_c
 int tpsb_get_mean_time_derivatives(tpsb_ctx *ctx, const double *d_y, double *out);
 
 /* max_char_speed of the last Mult (src/rhs_operator.cpp:549-558), reduced over this rank's nodes
- * (and over ranks when a communicator is attached); synchronises the stream.                      */
+ * (and over ranks when a communicator is attached); synchronises the stream.
+ * COLLECTIVE when the context has a communicator: tpsb_get_max_char_speed, tpsb_get_hmin, tpsb_check_state and
+ * tpsb_solve_step (which calls them) all-reduce on the context's NCCL communicator, like the MPI_Allreduce calls they
+ * replace -- every rank must call them, in the same order, and not concurrently with another call on the context. */
 int tpsb_get_max_char_speed(tpsb_ctx *ctx, double *out);
 
 /* MFEM ODESolver::Step for the solvers M2ulPhyS selects (src/M2ulPhyS.cpp:721-739, :2005):

@@ -428,6 +428,9 @@ struct Oracle {
       // OutletBC::subsonicReflectingPressure (src/outletBC.cpp:731-737)
       ph->modify_energy_for_pressure(stateIn, state2, b.data[0], false);
       ph->riemann(stateIn, state2, normal, bdrFlux, true);  // rsolver->Eval(..., true): forced Lax-Friedrichs
+    } else if (ph->wall_bc_flux(b.type, b.data, use_bc_in_grad, normal, stateIn, gradState, xyz, delta, dist, bdrFlux)) {
+      // reference back end: WallBC::computeBdrFlux itself (wallBC.cpp compiled into oracle/_ref); the branches below are
+      // the restatement the "port" back end runs (and are checked against the object code by tests/test_cpu_bc_oracle.py)
     } else if (b.type == 0) {
       // WallBC::computeINVwallFlux (src/wallBC.cpp:277-320)
       double vel[3], un[3];
@@ -908,7 +911,7 @@ struct Oracle {
     }
     for (double m : mcs_t) max_char_speed = std::max(max_char_speed, m);
     // ---- forcing terms, added after Me_inv (src/rhs_operator.cpp:451-461): SourceTerm::updateTerms
-    if (ph->has_source()) {
+    if (ph->has_source() && !ph->source_update(sol_view ? sol_view : x, Up.data(), gradUp.data(), N, y)) {
       const double *Usol = sol_view ? sol_view : x;
 #pragma omp parallel for num_threads(nthreads) schedule(static)
       for (long n = 0; n < N; n++) {
@@ -1157,6 +1160,9 @@ void orc_pt_visc_flux(void *h, int n, const double *U, const double *gradUp, dou
   Oracle *o = static_cast<Oracle *>(h);
   double xyz[3] = {0, 0, 0};
   for (int i = 0; i < n; i++) o->ph->visc_flux(U + o->neq * i, gradUp + o->neq * o->dim * i, xyz, 0.0, 0.0, F + o->neq * o->dim * i);
+}
+int orc_pt_mix_diffusivity(void *h, const double *U, double *D /*[numSpecies]*/) {
+  return static_cast<Oracle *>(h)->ph->mixture_average_diffusivity(U, D) ? 0 : 1;
 }
 void orc_pt_source(void *h, int n, const double *Un, const double *Up, const double *gradUp, double *S) {
   Oracle *o = static_cast<Oracle *>(h);

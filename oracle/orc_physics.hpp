@@ -101,6 +101,19 @@ struct Physics {
   virtual void source_term(double *Un, double *upn, const double *gradUpn, int node, double *src) {}
   // Chemistry::setRates: rate coefficients of the GRIDFUNCTION_RXN reactions, data[component][size]
   virtual void set_rates(const double *data, int size) {}
+  // Whole-vector forcing term through the reference's own SourceTerm::updateTerms object code (src/source_term.cpp:62-255):
+  // y += S(Usol, Up, gradUp), byNODES arrays of N nodes.  false: back end has no such object (the per-node restatement runs).
+  virtual bool source_update(const double *Usol, const double *Up, const double *gradUp, long N, double *y) { return false; }
+  // Wall boundary flux through the reference's own WallBC::computeBdrFlux object code (src/wallBC.cpp:268-543).
+  // data = the wall's inputs as in OrcBc (VISC_ISOTH: {Th}; VISC_GNRL: {hvyThermalCond, elecThermalCond, Th, Te}).
+  // false: back end has no such object (the restatement in dg_oracle.cpp runs).
+  virtual bool wall_bc_flux(int wall_type, const double *data, bool use_bc_in_grad, const double *normal, const double *stateIn,
+                            const double *gradState, const double *xyz, double delta, double dist, double *bdrFlux) {
+    return false;
+  }
+  // MolecularTransport::computeMixtureAverageDiffusivity (gas_transport.hpp:132): what utils/binary_mixture_ic.cpp feeds
+  // its analytic solution with; false when the back end has no collision-integral transport
+  virtual bool mixture_average_diffusivity(const double *U, double *D) { return false; }
   // ---- used by AxisymmetricSource (src/forcing_terms.cpp:255-380) ----
   // GasMixture::ComputePressureFromPrimitives
   virtual double pressure_from_primitives(const double *Up) = 0;

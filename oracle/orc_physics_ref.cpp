@@ -6,6 +6,7 @@
 // against the header stub in oracle/refstub/.  Built only into oracle/_ref/ by
 // oracle/Makefile; the resulting shared object travels to the GPU box, the sources do not.
 #include <cstring>
+#include <omp.h>
 
 #include "chemistry.hpp"
 #include "equation_of_state.hpp"
@@ -16,7 +17,82 @@
 #include "riemann_solver.hpp"
 #include "transport_properties.hpp"
 
+#include "source_term.hpp"
+#include "wallBC.hpp"
+
 #include "orc_physics.hpp"
+
+// ---- glue for the two reference classes whose BASE-class constructors live in translation units that need real MFEM
+// (forcing_terms.cpp, BoundaryCondition.cpp): member initialisation only, restated from src/forcing_terms.cpp:36-52 and
+// src/BoundaryCondition.cpp:34-57.  Everything that computes -- SourceTerm::updateTerms, WallBC::computeBdrFlux and the
+// per-type wall routines -- is the reference's own object code (source_term.cpp, wallBC.cpp compiled in place).
+ForcingTerms::ForcingTerms(const int &_dim, const int &_num_equation, const int &_order, const int &_intRuleType,
+                           IntegrationRules *_intRules, ParFiniteElementSpace *_vfes, ParGridFunction *U, ParGridFunction *_Up,
+                           ParGridFunction *_gradUp, const precomputedIntegrationData &gpu_precomputed_data, bool axisym)
+    : dim(_dim), nvel(axisym ? 3 : _dim), num_equation(_num_equation), axisymmetric_(axisym), order(_order),
+      intRuleType(_intRuleType), intRules(_intRules), vfes(_vfes), U_(U), Up_(_Up), gradUp_(_gradUp),
+      gpu_precomputed_data_(gpu_precomputed_data), h_num_elems_of_type(nullptr) {}
+ForcingTerms::~ForcingTerms() {}
+BoundaryCondition::BoundaryCondition(RiemannSolverTPS *_rsolver, GasMixture *_mixture, Equations _eqSystem,
+                                     ParFiniteElementSpace *_vfes, IntegrationRules *_intRules, double &_dt, const int _dim,
+                                     const int _num_equation, const int _patchNumber, const double _refLength, bool axisym)
+    : rsolver(_rsolver), mixture(_mixture), eqSystem(_eqSystem), vfes(_vfes), intRules(_intRules), dt(_dt), dim_(_dim),
+      nvel_(axisym ? 3 : _dim), num_equation_(_num_equation), patchNumber(_patchNumber), refLength(_refLength),
+      axisymmetric_(axisym), BCinit(false) {}
+BoundaryCondition::~BoundaryCondition() {}
+void BoundaryCondition::computeBdrPrimitiveStateForGradient(const Vector &stateIn, Vector &stateBC) const { stateBC = stateIn; }
+
+namespace {
+// one reference WallBC object per (type, inputs, useBCinGrad), built on first use.  WallBC::computeBdrFlux writes its
+// bcFlux_ member (the reference's CPU path is single-threaded per rank), so every OpenMP thread of the oracle owns a cache.
+struct WallCache {
+  struct Entry {
+    int type;
+    bool use;
+    double data[4];
+    WallBC *bc;
+  };
+  std::vector<Entry> entries;
+  boundaryFaceIntegrationData bfd;
+  int maxIntPoints = 64;
+  double dt = 0.0;
+  WallBC *get(RiemannSolverTPS *rs, GasMixture *mix, Equations eqs, Fluxes *flux, int dim, int neq, bool axisym, int type,
+              const double *data, bool use) {
+    for (auto &e : entries)
+      if (e.type == type && e.use == use && e.data[0] == data[0] && e.data[1] == data[1] && e.data[2] == data[2] &&
+          e.data[3] == data[3])
+        return e.bc;
+    WallData wd;
+    wd.hvyThermalCond = NONE_THMCND, wd.elecThermalCond = NONE_THMCND, wd.Th = 0.0, wd.Te = 0.0;
+    if (type == VISC_ISOTH) {  // M2ulPhyS::parseBCInputs: Th = Te = the wall temperature (src/M2ulPhyS.cpp, wall inputs)
+      wd.hvyThermalCond = ISOTH, wd.elecThermalCond = ISOTH, wd.Th = data[0], wd.Te = data[0];
+    } else if (type == VISC_GNRL) {
+      wd.hvyThermalCond = static_cast<ThermalCondition>(static_cast<int>(data[0]));
+      wd.elecThermalCond = static_cast<ThermalCondition>(static_cast<int>(data[1]));
+      wd.Th = data[2], wd.Te = data[3];
+    }
+    WallBC *bc = new WallBC(rs, mix, mix, eqs, flux, nullptr, nullptr, dt, dim, neq, 1, static_cast<WallType>(type), wd, bfd,
+                            maxIntPoints, axisym, use);  // wallBC.cpp:36
+    entries.push_back({type, use, {data[0], data[1], data[2], data[3]}, bc});
+    return bc;
+  }
+  bool flux(RiemannSolverTPS *rs, GasMixture *mix, Equations eqs, Fluxes *fl, int dim, int neq, bool axisym, int type,
+            const double *data, bool use, const double *normal, const double *stateIn, const double *gradState,
+            const double *xyz, double delta, double dist, double *bdrFlux) {
+    WallBC *bc = get(rs, mix, eqs, fl, dim, neq, axisym, type, data, use);
+    Vector n(dim), s(neq), t(3), f(neq);
+    DenseMatrix g(neq, dim);
+    for (int d = 0; d < dim; d++) n[d] = normal[d];
+    for (int i = 0; i < neq; i++) s[i] = stateIn[i];
+    for (int i = 0; i < neq * dim; i++) g.GetData()[i] = gradState[i];
+    for (int d = 0; d < 3; d++) t[d] = d < dim ? xyz[d] : 0.0;
+    f = 0.0;
+    bc->computeBdrFlux(n, s, g, t, delta, 0.0, dist, f);  // wallBC.cpp:268
+    for (int i = 0; i < neq; i++) bdrFlux[i] = f[i];
+    return true;
+  }
+};
+}  // namespace
 
 // flow/useMixingLength (src/M2ulPhyS.cpp:265-283): the flux class sees the molecular transport through MixingLengthTransport
 static TransportProperties *wrap_mixing_length(const OrcPhysParams &p, GasMixture *mix, MolecularTransport *molecular) {
@@ -39,6 +115,8 @@ class DryAirRef : public Physics {
   Fluxes *flux_;
   RiemannSolverTPS *rs_;
   bool use_roe_ = false;
+  Equations eqs_;
+  WallCache walls_[256];
 
  public:
   DryAirRef(const OrcPhysParams &p, int dim, int nvel, int neq) : dim_(dim), nvel_(nvel), neq_(neq) {
@@ -71,6 +149,7 @@ class DryAirRef : public Physics {
     }
     rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, p.use_roe != 0, axisym);  // riemann_solver.cpp:38
     use_roe_ = p.use_roe != 0;
+    eqs_ = static_cast<Equations>(p.eq_system);
   }
   ~DryAirRef() {
     delete rs_;
@@ -79,6 +158,11 @@ class DryAirRef : public Physics {
     delete mix_;
   }
   const char *kind() const override { return "reference"; }
+  bool wall_bc_flux(int wall_type, const double *data, bool use, const double *normal, const double *stateIn,
+                    const double *gradState, const double *xyz, double delta, double dist, double *bdrFlux) override {
+    return walls_[omp_get_thread_num() & 255].flux(rs_, mix_, eqs_, flux_, dim_, neq_, dim_ == 2 && nvel_ == 3, wall_type, data, use, normal, stateIn,
+                       gradState, xyz, delta, dist, bdrFlux);
+  }
   int num_active_species() const override { return mix_->GetNumActiveSpecies(); }
   int num_species() const override { return mix_->GetNumSpecies(); }
   double pressure(const double *U) override { return mix_->ComputePressure(U); }
@@ -148,6 +232,16 @@ class MixtureRef : public Physics {
   Chemistry *chem_ = nullptr;
   NetEmission *rad_ = nullptr;
   double rxParams_[34][3];
+  Equations eqs_;
+  WallCache walls_[256];
+  // the reference's SourceTerm over stub grid functions of the current mesh size (built on first use)
+  RunConfiguration cfg_;
+  precomputedIntegrationData pre_;
+  ParFiniteElementSpace *st_fes_ = nullptr;
+  ParGridFunction *st_U_ = nullptr, *st_Up_ = nullptr, *st_gradUp_ = nullptr;
+  SourceTerm *st_ = nullptr;
+  int st_order_ = 0, st_rule_ = 0;
+  long st_N_ = -1;
 
  public:
   MixtureRef(const OrcPhysParams &p, int dim, int nvel, int neq) : dim_(dim), nvel_(nvel), neq_(neq) {
@@ -204,6 +298,11 @@ class MixtureRef : public Physics {
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
     flux_ = new Fluxes(mix_, eqs, wrap_mixing_length(p, mix_, static_cast<MolecularTransport *>(trans_)), neq, dim, axisym);
     rs_ = new RiemannSolverTPS(neq, mix_, eqs, flux_, false, axisym);
+    eqs_ = eqs;
+    cfg_.workFluid = USER_DEFINED;
+    cfg_.axisymmetric_ = axisym;
+    cfg_.chemistryInput.numReactions = pm.num_reactions;
+    cfg_.radiationInput.model = pm.nec_table_n > 0 ? NET_EMISSION : NONE_RAD;
     if (pm.num_reactions > 0) {
       ChemistryInput ci;
       ci.model = NUM_CHEMISTRYMODEL;
@@ -243,6 +342,11 @@ class MixtureRef : public Physics {
     }
   }
   ~MixtureRef() {
+    delete st_;
+    delete st_U_;
+    delete st_Up_;
+    delete st_gradUp_;
+    delete st_fes_;
     delete rad_;
     delete chem_;
     delete rs_;
@@ -323,6 +427,40 @@ class MixtureRef : public Physics {
   }
   // SourceTerm::updateTerms node body (src/source_term.cpp:117-250) over the reference's transport / chemistry /
   // mixture objects; no radiation, no EM coupling output.
+  bool wall_bc_flux(int wall_type, const double *data, bool use, const double *normal, const double *stateIn,
+                    const double *gradState, const double *xyz, double delta, double dist, double *bdrFlux) override {
+    return walls_[omp_get_thread_num() & 255].flux(rs_, mix_, eqs_, flux_, dim_, neq_, dim_ == 2 && nvel_ == 3, wall_type, data, use, normal, stateIn,
+                       gradState, xyz, delta, dist, bdrFlux);
+  }
+  bool source_update(const double *Usol, const double *Up, const double *gradUp, long N, double *y) override {
+    if (st_N_ != N) {
+      delete st_;
+      delete st_U_;
+      delete st_Up_;
+      delete st_gradUp_;
+      delete st_fes_;
+      st_fes_ = new ParFiniteElementSpace(static_cast<int>(N), neq_);
+      st_U_ = new ParGridFunction(st_fes_, neq_);
+      st_Up_ = new ParGridFunction(st_fes_, neq_);
+      st_gradUp_ = new ParGridFunction(st_fes_, neq_ * dim_);
+      st_ = new SourceTerm(dim_, neq_, st_order_, st_rule_, nullptr, st_fes_, st_U_, st_Up_, st_gradUp_, pre_, cfg_, mix_, mix_,
+                           trans_, chem_, rad_, nullptr, nullptr);  // source_term.cpp:36
+      st_N_ = N;
+    }
+    std::memcpy(st_U_->GetData(), Usol, sizeof(double) * N * neq_);
+    std::memcpy(st_Up_->GetData(), Up, sizeof(double) * N * neq_);
+    std::memcpy(st_gradUp_->GetData(), gradUp, sizeof(double) * N * neq_ * dim_);
+    Vector in(y, static_cast<int>(N) * neq_);
+    st_->updateTerms(in);  // source_term.cpp:62: in += S, node by node
+    return true;
+  }
+  bool mixture_average_diffusivity(const double *U, double *D) override {
+    GasMinimalTransport *g = dynamic_cast<GasMinimalTransport *>(trans_);
+    if (!g) return false;
+    double E[gpudata::MAXDIM] = {0, 0, 0};
+    g->computeMixtureAverageDiffusivity(U, E, D, false);  // gas_transport.cpp, as utils/binary_mixture_ic.cpp:143 calls it
+    return true;
+  }
   void source_term(double *Un, double *upn, const double *gradUpn, int n, double *srcTerm) override {
     const int _num_equation = neq_, _nvel = nvel_, _dim = dim_;
     const int _numSpecies = mix_->GetNumSpecies(), _numActiveSpecies = mix_->GetNumActiveSpecies();

@@ -301,6 +301,34 @@ class DenseMatrix {
   }
 };
 
+// [MFEM CalcInverse, linalg/densemat.cpp]: adjugate / determinant for the 1 x 1, 2 x 2 and 3 x 3 matrices the
+// reference inverts per point (WallBC::computeSlipWallFlux, src/wallBC.cpp:414)
+inline void CalcInverse(const DenseMatrix &a, DenseMatrix &inva) {
+  const int n = a.Height();
+  if (n == 1) {
+    inva(0, 0) = 1.0 / a(0, 0);
+  } else if (n == 2) {
+    const double t = 1.0 / (a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0));
+    inva(0, 0) = a(1, 1) * t;
+    inva(0, 1) = -a(0, 1) * t;
+    inva(1, 0) = -a(1, 0) * t;
+    inva(1, 1) = a(0, 0) * t;
+  } else {
+    const double det = a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) - a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) +
+                       a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
+    const double t = 1.0 / det;
+    inva(0, 0) = (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) * t;
+    inva(0, 1) = (a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2)) * t;
+    inva(0, 2) = (a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1)) * t;
+    inva(1, 0) = (a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2)) * t;
+    inva(1, 1) = (a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0)) * t;
+    inva(1, 2) = (a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2)) * t;
+    inva(2, 0) = (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0)) * t;
+    inva(2, 1) = (a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1)) * t;
+    inva(2, 2) = (a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0)) * t;
+  }
+}
+
 class DenseTensor {
   std::vector<double> d_;
   int ni_ = 0, nj_ = 0, nk_ = 0;

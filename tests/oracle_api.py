@@ -92,6 +92,7 @@ def load(kind="port"):
         getattr(lib, nm).argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.orc_pt_visc_flux.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
     lib.orc_pt_source.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
+    lib.orc_pt_mix_diffusivity.argtypes = [C.c_void_p, _dp, _dp]
     lib.orc_ndofs.restype = C.c_long
     lib.orc_ndofs.argtypes = [C.c_void_p]
     lib.orc_update_primitives.argtypes = [C.c_void_p, _dp, _dp]
@@ -176,6 +177,13 @@ class Oracle:
         args = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
         getattr(self.lib, "orc_pt_" + what)(self.h, n, *args, out)
         return out
+
+    def mixture_average_diffusivity(self, state, num_species):
+        """MolecularTransport::computeMixtureAverageDiffusivity of the reference's transport object (kind='ref')."""
+        D = np.zeros(max(num_species, 8))
+        rc = self.lib.orc_pt_mix_diffusivity(self.h, np.ascontiguousarray(state, dtype=np.float64), D)
+        assert rc == 0, "this physics back end has no collision-integral transport"
+        return D[:num_species]
 
     def node_coords(self):
         xyz = np.zeros((self.N, self.dim))

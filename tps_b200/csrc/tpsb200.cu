@@ -666,6 +666,10 @@ bool host_pipe_schedule(int NE, int NFint, int C, const std::vector<int> &nbr_el
     const int cf = chunk_of(fl_el1[f]);
     need_grad[cf] |= (mask(1) << cf) | (mask(1) << chunk_of(fl_el2[f]));
   }
+  for (int k = 0; k < NB; k++) {  // a chunk's boundary faces ride in its face op and read its elements' gradients
+    const int cb = chunk_of(bdr_el1[k]);
+    need_grad[cb] |= mask(1) << cb;
+  }
   ops.clear();
   mask primd = 0, gradd = 0, faced = 0, resd = 0;
   for (int k = 0; k < C; k++) {
@@ -764,12 +768,12 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (const char *pth = getenv("TPSB_PATH")) want_generic = want_generic || strcmp(pth, "generic") == 0;
   if (phys->use_roe && !(maps->dim == 2 && space->nvel == 2 && phys->fluid == TPSB_DRY_AIR))
     return fail(ctx, TPSB_ENOTIMPL, "useRoe: Eval_Roe of the reference is written for 2-D dry air only (riemann_solver.cpp:117-206)");
-  if (want_generic) {
-    if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
-  }
   if (phys->use_mixing_length) want_generic = true;  // the mixing-length model lives on the generic path
   for (int i = 0; bcs && bcs->bcs && i < bcs->num_bcs; i++)  // ... and so does the general wall (WallType VISC_GNRL)
     if (bcs->bcs[i].kind == TPSB_BC_WALL && bcs->bcs[i].type == 4) want_generic = true;
+  if (want_generic) {
+    if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
+  }
   const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
   if (phys->sgs_model < 0 || phys->sgs_model > 2) return fail(ctx, TPSB_EINVAL, "sgs_model %d: 0 none, 1 smagorinsky, 2 sigma", phys->sgs_model);
   if (visc_mod && want_generic)
@@ -2288,6 +2292,8 @@ int tpsb_solve_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, double cf
       double mcs = 0.0, hmin = 0.0;
       if ((rc = tpsb_get_max_char_speed(ctx, &mcs))) return rc;
       if ((rc = tpsb_get_hmin(ctx, &hmin))) return rc;
+      // a quiescent (mcs == 0) or NaN state has no CFL limit to offer: keep the current step and say so
+      if (!(mcs > 0.0) || !std::isfinite(mcs)) return fail(ctx, TPSB_EINVAL, "adaptive time step: max characteristic speed is %g", mcs);
       *dt_next = cfl * hmin / mcs / static_cast<double>(ctx->dim);
     }
   }
