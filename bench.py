@@ -207,7 +207,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=96, help="elements per direction per GPU")
+    ap.add_argument("--n", "--elems", dest="n", type=int, default=96,
+                    help="elements per direction per GPU (--elems: the spelling torchrun does not mistake for its own --n* flags)")
     ap.add_argument("--cpu-n", type=int, default=20, help="elements per direction of the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--strong", type=int, default=0, metavar="G",
@@ -397,6 +398,9 @@ def main():
         yy = y.view(5, n_local)
         return torch.cat([yy.abs().sum(1), (yy * yy).sum(1)])
     cs = checksums(Y, N)
+    cs_global = cs.clone()
+    if world > 1:  # sums over all ranks: element-order and partition independent, comparable across N for a fixed mesh
+        dist.all_reduce(cs_global, op=dist.ReduceOp.SUM)
     parity = None
     if world > 1 and args.workload == "tgv" and not args.strong and not args.no_verify:
         allcs = [torch.empty_like(cs) for _ in range(world)]
@@ -512,7 +516,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, grid),
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "finite": finite, "setup_s": t_setup, "dofs_per_gpu": N, "path": op.path(),
-            "checksum": [float(t) for t in cs.tolist()], "multirank_parity": parity,
+            "checksum": [float(t) for t in cs.tolist()], "checksum_all_ranks": [float(t) for t in cs_global.tolist()],
+            "multirank_parity": parity,
             "partition": getattr(args, "partition_info", None),
         }))
     if world > 1:
