@@ -367,6 +367,14 @@ int tpsb_mk_partition_general(int num_elems, const int *elem_verts, const double
                               int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface, int *nbr_rank,
                               int *send_offset, int *send_elems, int *recv_offset);
 
+/* the same for quadrilateral (dim = 2: elem_verts [NE][4], elem_xyz [NE][4][2]) or hexahedral (dim = 3) meshes */
+int tpsb_mk_partition_rcb_dim(int dim, int num_elems, const double *elem_xyz, int nparts, int *elem_rank);
+int tpsb_mk_partition_general_dim(int dim, int num_elems, const int *elem_verts, const double *elem_xyz, int num_faces,
+                                  const int *gface_el1, const int *gface_el2, const int *elem_rank, int rank,
+                                  tpsb_mk_part_sizes *sizes, int *l_elem_verts, double *l_elem_xyz, int64_t *elem_gid,
+                                  int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface, int *nbr_rank,
+                                  int *send_offset, int *send_elems, int *recv_offset);
+
 /* ---- communicator bootstrap for the NCCL face-neighbour exchange ----
  * unique_id: 128-byte ncclUniqueId produced on rank 0 by tpsb_comm_get_unique_id and broadcast by
  * the host (MPI_Bcast in TPS, torch.distributed in bench.py).                                      */

@@ -78,7 +78,7 @@ def argon6_primitives(xy, nvel=3, seed=20261018):
 
 
 def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None, gpu=True, kind=None, mixing_length=None,
-              want_oracle=True):
+              want_oracle=True, device=0):
     """(RhsOperator or None, Oracle) on mesh m with boundary-condition set bc_kind.
     mixing_length = (max-mixing-length, Pr_ratio, bulk-multiplier): flow/useMixingLength (reference back end)."""
     nsp_in = ()
@@ -107,7 +107,7 @@ def make_pair(m, order, eq, bt, ir, nvel, bc_kind, use_bc_in_grad, mixture=None,
         orc.set_bcs(m["face_attr"], [oracle_api.make_bc(*b) for b in specs], use_bc_in_grad)
     op = None
     if gpu:
-        op = tps_b200.RhsOperator(m, order=order, physics=phys_g, basis_type=bt, int_rule_type=ir, nvel=nvel,
+        op = tps_b200.RhsOperator(m, order=order, physics=phys_g, basis_type=bt, int_rule_type=ir, nvel=nvel, device=device,
                                   face_attr=m["face_attr"] if specs else None, use_bc_in_grad=use_bc_in_grad,
                                   bcs=[tps_b200.BcDesc.make(*b) for b in specs] if specs else None)
     return op, orc

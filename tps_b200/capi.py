@@ -198,7 +198,7 @@ EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tp
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
            "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_get_hmin", "tpsb_solve_step", "tpsb_check_state", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy", "tpsb_get_path", "tpsb_mk_partition_metis", "tpsb_mk_partition_rcb",
-           "tpsb_mk_partition_general"]
+           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim"]
 
 
 def lib():
@@ -263,6 +263,8 @@ def lib():
     L.tpsb_mk_partition_rcb.argtypes = [C.c_int, dp, C.c_int, ip]
     L.tpsb_mk_partition_general.argtypes = [C.c_int, ip, dp, C.c_int, ip, ip, ip, C.c_int, C.POINTER(PartSizes), ip, dp, i64p,
                                             ip, ip, ip, ip, ip, ip, ip, ip, ip]
+    L.tpsb_mk_partition_general_dim.argtypes = [C.c_int] + L.tpsb_mk_partition_general.argtypes
+    L.tpsb_mk_partition_rcb_dim.argtypes = [C.c_int, C.c_int, dp, C.c_int, ip]
     L.tpsb_comm_get_unique_id.argtypes = [C.c_char_p]
     L.tpsb_comm_init_rank.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.tpsb_comm_destroy.argtypes = [vp]
@@ -456,7 +458,7 @@ def partition_elements(mesh, nparts, method="metis"):
             raise TpsbError(f"tpsb_mk_partition_metis failed ({rc})")
         return rank, int(cut.value)
     xyz = np.ascontiguousarray(mesh["elem_xyz"], np.float64)
-    rc = L.tpsb_mk_partition_rcb(ne, _dp(xyz), nparts, _ip(rank))
+    rc = L.tpsb_mk_partition_rcb_dim(xyz.shape[2], ne, _dp(xyz), nparts, _ip(rank))
     if rc != 0:
         raise TpsbError(f"tpsb_mk_partition_rcb failed ({rc})")
     return rank, None
@@ -472,17 +474,18 @@ def partition_mesh(mesh, elem_rank, rank):
     g1, g2 = np.ascontiguousarray(mesh["face_el1"], np.int32), np.ascontiguousarray(mesh["face_el2"], np.int32)
     er = np.ascontiguousarray(elem_rank, np.int32)
     sz = PartSizes()
-    head = (ev.shape[0], _ip(ev), _dp(xyz), len(g1), _ip(g1), _ip(g2), _ip(er), rank, C.byref(sz))
-    rc = L.tpsb_mk_partition_general(*head, *([None] * 12))
+    dim = xyz.shape[2]
+    head = (dim, ev.shape[0], _ip(ev), _dp(xyz), len(g1), _ip(g1), _ip(g2), _ip(er), rank, C.byref(sz))
+    rc = L.tpsb_mk_partition_general_dim(*head, *([None] * 12))
     if rc != 0:
         raise TpsbError(f"tpsb_mk_partition_general failed ({rc})")
     ne, nh, nf = sz.num_elems, sz.num_nbr_elems, sz.num_faces
-    lev, lxyz, gid = np.zeros((ne + nh, 8), np.int32), np.zeros((ne + nh, 8, 3)), np.zeros(ne + nh, np.int64)
+    lev, lxyz, gid = np.zeros((ne + nh, 1 << dim), np.int32), np.zeros((ne + nh, 1 << dim, dim)), np.zeros(ne + nh, np.int64)
     f = [np.zeros(max(nf, 1), np.int32) for _ in range(5)]
     nbr = np.zeros(max(sz.num_nbr_ranks, 1), np.int32)
     so, ro = np.zeros(sz.num_nbr_ranks + 1, np.int32), np.zeros(sz.num_nbr_ranks + 1, np.int32)
     se = np.zeros(max(sz.num_send, 1), np.int32)
-    rc = L.tpsb_mk_partition_general(*head, _ip(lev), _dp(lxyz), gid.ctypes.data_as(C.POINTER(C.c_int64)), _ip(f[0]), _ip(f[1]),
+    rc = L.tpsb_mk_partition_general_dim(*head, _ip(lev), _dp(lxyz), gid.ctypes.data_as(C.POINTER(C.c_int64)), _ip(f[0]), _ip(f[1]),
                                      _ip(f[2]), _ip(f[3]), _ip(f[4]), _ip(nbr), _ip(so), _ip(se), _ip(ro))
     if rc != 0:
         raise TpsbError(f"tpsb_mk_partition_general failed ({rc})")
@@ -490,6 +493,8 @@ def partition_mesh(mesh, elem_rank, rank):
                face_el1=f[0][:nf].copy(), face_el2=f[1][:nf].copy(), face_inf1=f[2][:nf].copy(), face_inf2=f[3][:nf].copy(),
                face_gface=f[4][:nf].copy(), nbr_rank=nbr[:sz.num_nbr_ranks].copy(), send_offset=so, recv_offset=ro,
                send_elems=se[:sz.num_send].copy())
+    if dim == 2:
+        out["dim"] = 2
     if "face_attr" in mesh:
         out["face_attr"] = np.ascontiguousarray(np.asarray(mesh["face_attr"], np.int32)[out["face_gface"]])
     return out

@@ -378,12 +378,13 @@ extern "C" int tpsb_mk_partition_metis(int num_elems, int num_faces, const int *
 }
 
 // Recursive coordinate bisection of the element centroids (nparts a power of two or not: the split is proportional).
-extern "C" int tpsb_mk_partition_rcb(int num_elems, const double *elem_xyz, int nparts, int *elem_rank) {
-  if (num_elems <= 0 || nparts < 1 || !elem_xyz || !elem_rank) return TPSB_EINVAL;
+extern "C" int tpsb_mk_partition_rcb_dim(int dim, int num_elems, const double *elem_xyz, int nparts, int *elem_rank) {
+  if ((dim != 2 && dim != 3) || num_elems <= 0 || nparts < 1 || !elem_xyz || !elem_rank) return TPSB_EINVAL;
+  const int nv = 1 << dim;
   std::vector<double> cen(static_cast<size_t>(num_elems) * 3, 0.0);
   for (int e = 0; e < num_elems; e++)
-    for (int a = 0; a < 8; a++)
-      for (int d = 0; d < 3; d++) cen[static_cast<size_t>(e) * 3 + d] += 0.125 * elem_xyz[(static_cast<size_t>(e) * 8 + a) * 3 + d];
+    for (int a = 0; a < nv; a++)
+      for (int d = 0; d < dim; d++) cen[static_cast<size_t>(e) * 3 + d] += elem_xyz[(static_cast<size_t>(e) * nv + a) * dim + d] / nv;
   std::vector<int> ids(num_elems);
   for (int e = 0; e < num_elems; e++) ids[e] = e;
   struct Job {
@@ -416,17 +417,34 @@ extern "C" int tpsb_mk_partition_rcb(int num_elems, const double *elem_xyz, int 
   }
   return TPSB_OK;
 }
+extern "C" int tpsb_mk_partition_rcb(int num_elems, const double *elem_xyz, int nparts, int *elem_rank) {
+  return tpsb_mk_partition_rcb_dim(3, num_elems, elem_xyz, nparts, elem_rank);
+}
 
 // This rank's piece of a GLOBAL hexahedral mesh under an arbitrary element -> rank map: ParMesh's local numbering
 // (local elements in global order first, then the face-neighbour elements grouped by owner and sorted by global id,
 // the order in which the owner sends them; src/M2ulPhyS.cpp:421, ExchangeFaceNbrData).  Two calls: sizes, then fill.
 //   face_gface[f]  global face of local face f (so the caller can carry boundary attributes over)
-extern "C" int tpsb_mk_partition_general(int num_elems, const int *elem_verts, const double *elem_xyz, int num_faces,
-                                         const int *gface_el1, const int *gface_el2, const int *elem_rank, int rank,
-                                         tpsb_mk_part_sizes *sizes, int *l_elem_verts, double *l_elem_xyz, int64_t *elem_gid,
-                                         int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface,
-                                         int *nbr_rank, int *send_offset, int *send_elems, int *recv_offset) {
-  if (num_elems <= 0 || !elem_verts || !gface_el1 || !gface_el2 || !elem_rank || !sizes) return TPSB_EINVAL;
+extern "C" int tpsb_mk_build_faces2d(int num_elems, const int *elem_verts, int *face_el1, int *face_el2, int *face_inf1,
+                                     int *face_inf2);
+extern "C" int tpsb_mk_partition_general_dim(int dim, int num_elems, const int *elem_verts, const double *elem_xyz, int num_faces,
+                                             const int *gface_el1, const int *gface_el2, const int *elem_rank, int rank,
+                                             tpsb_mk_part_sizes *sizes, int *l_elem_verts, double *l_elem_xyz, int64_t *elem_gid,
+                                             int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface,
+                                             int *nbr_rank, int *send_offset, int *send_elems, int *recv_offset) {
+  if ((dim != 2 && dim != 3) || num_elems <= 0 || !elem_verts || !gface_el1 || !gface_el2 || !elem_rank || !sizes) return TPSB_EINVAL;
+  const int nv = 1 << dim, nfe = 2 * dim;
+  static const int QUAD_EDGE[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};  // Geometry::Constants<SQUARE>::Edges
+  auto face_key = [&](const int *v, int lf) {
+    int s[4] = {0, 0, 0, 0};
+    if (dim == 3) {
+      for (int k = 0; k < 4; k++) s[k] = v[tpsb::HEX_FACE_VERT[lf][k]];
+      std::sort(s, s + 4);
+      return Key{s[0], s[1], s[2]};
+    }
+    const int a = v[QUAD_EDGE[lf][0]], b = v[QUAD_EDGE[lf][1]];
+    return Key{std::min(a, b), std::max(a, b), -1};
+  };
   std::vector<int> loc, lid(static_cast<size_t>(num_elems), -1);
   for (int e = 0; e < num_elems; e++)
     if (elem_rank[e] == rank) {
@@ -452,28 +470,26 @@ extern "C" int tpsb_mk_partition_general(int num_elems, const int *elem_verts, c
   for (auto &h : halo)
     if (peers.empty() || peers.back() != h.first) peers.push_back(h.first);
   const int NEH = static_cast<int>(halo.size());
-  std::vector<int> ev(static_cast<size_t>(NE + NEH) * 8);
+  std::vector<int> ev(static_cast<size_t>(NE + NEH) * nv);
   for (int e = 0; e < NE + NEH; e++) {
     const int g = e < NE ? loc[e] : halo[e - NE].second;
-    std::copy(&elem_verts[static_cast<size_t>(g) * 8], &elem_verts[static_cast<size_t>(g) * 8] + 8, &ev[static_cast<size_t>(e) * 8]);
+    std::copy(&elem_verts[static_cast<size_t>(g) * nv], &elem_verts[static_cast<size_t>(g) * nv] + nv, &ev[static_cast<size_t>(e) * nv]);
     if (elem_gid) elem_gid[e] = g;
     if (l_elem_xyz && elem_xyz)
-      std::copy(&elem_xyz[static_cast<size_t>(g) * 24], &elem_xyz[static_cast<size_t>(g) * 24] + 24, &l_elem_xyz[static_cast<size_t>(e) * 24]);
+      std::copy(&elem_xyz[static_cast<size_t>(g) * nv * dim], &elem_xyz[static_cast<size_t>(g) * nv * dim] + nv * dim,
+                &l_elem_xyz[static_cast<size_t>(e) * nv * dim]);
   }
-  std::vector<int> f1(static_cast<size_t>(NE + NEH) * 6), f2(f1.size()), i1(f1.size()), i2(f1.size());
-  const int nf_all = tpsb_mk_build_faces(NE + NEH, ev.data(), f1.data(), f2.data(), i1.data(), i2.data());
+  std::vector<int> f1(static_cast<size_t>(NE + NEH) * nfe), f2(f1.size()), i1(f1.size()), i2(f1.size());
+  const int nf_all = dim == 3 ? tpsb_mk_build_faces(NE + NEH, ev.data(), f1.data(), f2.data(), i1.data(), i2.data())
+                              : tpsb_mk_build_faces2d(NE + NEH, ev.data(), f1.data(), f2.data(), i1.data(), i2.data());
   if (nf_all < 0) return TPSB_EINVAL;
-  // global face of (global element, local face): faces are found again through their sorted vertex triple
+  // global face of (global element, local face): faces are found again through their vertex key
   std::unordered_map<Key, int, KeyHash> gtab;
   if (face_gface) {
     gtab.reserve(static_cast<size_t>(num_faces) * 2);
-    std::vector<char> done(static_cast<size_t>(num_faces), 0);
     for (int e = 0; e < num_elems; e++)
-      for (int lf = 0; lf < 6; lf++) {
-        int s[4];
-        for (int k = 0; k < 4; k++) s[k] = elem_verts[static_cast<size_t>(e) * 8 + tpsb::HEX_FACE_VERT[lf][k]];
-        std::sort(s, s + 4);
-        const Key key{s[0], s[1], s[2]};
+      for (int lf = 0; lf < nfe; lf++) {
+        const Key key = face_key(&elem_verts[static_cast<size_t>(e) * nv], lf);
         if (gtab.find(key) == gtab.end()) gtab.emplace(key, static_cast<int>(gtab.size()));  // first appearance == MFEM face number
       }
   }
@@ -485,12 +501,7 @@ extern "C" int tpsb_mk_partition_general(int num_elems, const int *elem_verts, c
       face_el2[nf] = f2[f];
       face_inf1[nf] = i1[f];
       face_inf2[nf] = i2[f];
-      if (face_gface) {
-        int s[4];
-        for (int k = 0; k < 4; k++) s[k] = ev[static_cast<size_t>(f1[f]) * 8 + tpsb::HEX_FACE_VERT[i1[f] / 64][k]];
-        std::sort(s, s + 4);
-        face_gface[nf] = gtab.at(Key{s[0], s[1], s[2]});
-      }
+      if (face_gface) face_gface[nf] = gtab.at(face_key(&ev[static_cast<size_t>(f1[f]) * nv], i1[f] / 64));
     }
     nf++;
   }
@@ -516,6 +527,15 @@ extern "C" int tpsb_mk_partition_general(int num_elems, const int *elem_verts, c
     send_offset[peers.size()] = static_cast<int>(sp);
   }
   return TPSB_OK;
+}
+extern "C" int tpsb_mk_partition_general(int num_elems, const int *elem_verts, const double *elem_xyz, int num_faces,
+                                         const int *gface_el1, const int *gface_el2, const int *elem_rank, int rank,
+                                         tpsb_mk_part_sizes *sizes, int *l_elem_verts, double *l_elem_xyz, int64_t *elem_gid,
+                                         int *face_el1, int *face_el2, int *face_inf1, int *face_inf2, int *face_gface,
+                                         int *nbr_rank, int *send_offset, int *send_elems, int *recv_offset) {
+  return tpsb_mk_partition_general_dim(3, num_elems, elem_verts, elem_xyz, num_faces, gface_el1, gface_el2, elem_rank, rank, sizes,
+                                       l_elem_verts, l_elem_xyz, elem_gid, face_el1, face_el2, face_inf1, face_inf2, face_gface,
+                                       nbr_rank, send_offset, send_elems, recv_offset);
 }
 
 // Flattened RefTables for the tests: [np, nq, xn(np), wn(np), D(np*np), lb(2*np), xq(nq), wq(nq), P(nq*np),

@@ -60,7 +60,18 @@ struct GenArgs {
   double *Up, *gradUp, *y;
   unsigned long long *maxCharBits;
   const double *dist;  // nodal wall distance (tpsb_set_distance_field; mixing-length model), NULL: 0
+  // face-neighbour (halo) elements NE .. NE + NEH - 1 of a partitioned mesh: element-major copies [halo element][field][dof]
+  // received from their owners (RHSoperator::initNBlockDataTransfer / waitAllDataTransfer, src/rhs_operator.cpp:716-831)
+  int NEH;
+  const double *Uhalo, *UpHalo, *gradUpHalo, *distHalo;
 };
+
+// field `fld` (of nfld) of element el: local elements live in the byNODES array, face-neighbour elements in the halo copy
+__device__ __forceinline__ const double *gen_elem_field(const GenArgs &a, const double *local, const double *halo, int el, int fld,
+                                                        int nfld) {
+  return el < a.NE ? local + static_cast<long long>(el) * a.dof + static_cast<long long>(fld) * a.N
+                   : halo + (static_cast<long long>(el - a.NE) * nfld + fld) * a.dof;
+}
 
 __device__ __forceinline__ int gen_code(int dim, int inf) { return (inf / 64) * (dim == 3 ? 8 : 2) + inf % 64; }
 
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(128) gen_grad_kernel(GenArgs a) {
     }
     for (int eq = 0; eq < neq; eq++) {
       double own = 0, oth = 0;
-      const double *un = a.Up + static_cast<long long>(eo) * dof + eq * N;
+      const double *un = gen_elem_field(a, a.Up, a.UpHalo, eo, eq, neq);
       for (int k = 0; k < dof; k++) {
         own += po[k] * sUp[eq * dof + k];
         oth += pn[k] * un[k];
@@ -524,7 +535,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       }
       for (int eq = 0; eq < neq; eq++) {
         double x = 0, y = 0;
-        const double *src = a.U + static_cast<long long>(eo) * dof + eq * N;
+        const double *src = gen_elem_field(a, a.U, a.Uhalo, eo, eq, neq);
         for (int k = 0; k < dof; k++) {
           x += po[k] * sU[eq * dof + k];
           y += pn[k] * src[k];
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
       if (a.eq_system != 0) {  // gradients enter the viscous fluxes only
         for (int c = 0; c < nc; c++) {
           double x = 0, y = 0;
-          const double *src = a.gradUp + static_cast<long long>(eo) * dof + c * N;
+          const double *src = gen_elem_field(a, a.gradUp, a.gradUpHalo, eo, c, nc);
           for (int k = 0; k < dof; k++) {
             x += po[k] * sG[c * dof + k];
             y += pn[k] * src[k];
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         if (a.dist)
           for (int k = 0; k < dof; k++) {
             dwo += po[k] * a.dist[static_cast<long long>(e) * dof + k];
-            dwn += pn[k] * a.dist[static_cast<long long>(eo) * dof + k];
+            dwn += pn[k] * gen_elem_field(a, a.dist, a.distHalo, eo, 0, 1)[k];
           }
         gen_visc_flux(ph, u1, g1, radius, f1, first ? dwo : dwn);
         gen_visc_flux(ph, u2, g2, radius, f2, first ? dwn : dwo);
@@ -590,6 +601,18 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
   }
   __syncthreads();
   gen_apply_minv(a, ph.axisym ? a.me_inv_rad : a.me_inv, e, sZ, neq, a.y, N);
+}
+
+// primitives of the received face-neighbour elements (element-major halo copies)
+__global__ void gen_prim_halo_kernel(GenArgs a) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(a.NEH) * a.dof) return;
+  const long long k = t / a.dof, ln = t % a.dof;
+  double s[GEN_MAXEQ], up[GEN_MAXEQ];
+  for (int eq = 0; eq < a.neq; eq++) s[eq] = a.Uhalo[(k * a.neq + eq) * a.dof + ln];
+  gen_prim(a.phys, s, up);
+  double *dst = const_cast<double *>(a.UpHalo);
+  for (int eq = 0; eq < a.neq; eq++) dst[(k * a.neq + eq) * a.dof + ln] = up[eq];
 }
 
 // SourceTerm::updateTerms (source_term.cpp:62-255): node-wise plasma sources added to y AFTER Me^-1

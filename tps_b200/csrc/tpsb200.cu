@@ -127,6 +127,7 @@ static int fail(tpsb_ctx *c, int code, const char *fmt, ...) {
   return code;
 }
 
+static std::string setup_halo_desc(tpsb_ctx *c, const tpsb_halo_desc *halo, int NEH);
 enum { K_PRIM = 0, K_GRAD, K_FACE, K_RESID, K_PACK, K_AXPY };
 struct ProfScope {  // brackets one launch with events when profiling is on
   tpsb_ctx *c;
@@ -325,7 +326,7 @@ bool g_spd_inverse(std::vector<double> &A, int n) {
 
 // Everything the generic kernels need; returns an error string (empty on success).
 std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const tpsb_physics *phys,
-                           const tpsb_bc_set *bcs) {
+                           const tpsb_bc_set *bcs, const tpsb_halo_desc *halo) {
   const int dim = maps->dim, p = space->order, np = p + 1, NE = c->NE, NF = maps->num_faces;
   const int nv = 1 << dim, nfe = 2 * dim, nori = dim == 3 ? 8 : 2;
   int dof = 1;
@@ -389,9 +390,9 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
     el_face[static_cast<size_t>(e1) * nfe + lf1] = f;
     if (e2 >= 0) {
       const int lf2 = maps->face_inf2[f] / 64, ori = maps->face_inf2[f] % 64;
-      if (e2 >= NE) return "partitioned meshes are not built on the generic path yet";
+      if (e2 >= NE + c->NEH) return "invalid face tables";
       if (lf2 < 0 || lf2 >= nfe || ori < 0 || ori >= nori) return "invalid face tables";
-      el_face[static_cast<size_t>(e2) * nfe + lf2] = f;
+      if (e2 < NE) el_face[static_cast<size_t>(e2) * nfe + lf2] = f;  // shared face: Elem2 is a face-neighbour element
     }
   }
   for (int v : el_face)
@@ -600,11 +601,26 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   if (ce == cudaSuccess) ce = cudaMemset(c->d_maxBits, 0, sizeof(unsigned long long));
   if (ce != cudaSuccess) return std::string("device setup failed: ") + cudaGetErrorString(ce);
   g.Up = c->d_Up, g.gradUp = c->d_gradUp, g.maxCharBits = c->d_maxBits;
+  g.NEH = c->NEH;
+  g.Uhalo = g.UpHalo = g.gradUpHalo = g.distHalo = nullptr;
+  if (c->NEH > 0) {  // partitioned mesh: face-neighbour copies and the exchange description
+    const std::string herr = setup_halo_desc(c, halo, c->NEH);
+    if (!herr.empty()) return herr;
+    const size_t hb = static_cast<size_t>(c->NEH) * dof * sizeof(double), sb = static_cast<size_t>(c->n_send) * dof * sizeof(double);
+    ce = cudaMalloc(&c->d_Uhalo, hb * g.neq);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_UpHalo, hb * g.neq);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUpHalo, hb * g.neq * dim);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendU, sb * g.neq);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendG, sb * g.neq * dim);
+    if (ce != cudaSuccess) return std::string("device setup failed: ") + cudaGetErrorString(ce);
+    g.Uhalo = c->d_Uhalo, g.UpHalo = c->d_UpHalo, g.gradUpHalo = c->d_gradUpHalo;
+  }
   // element_to_faces (stride 1 + faces per element; 7 in 3-D as in the reference)
   std::vector<int> e2f(static_cast<size_t>(nfe + 1) * NE, 0);
   for (int f = 0; f < NF; f++) {
     if (maps->face_el2[f] < 0) continue;
     for (int e : {maps->face_el1[f], maps->face_el2[f]}) {
+      if (e >= NE) continue;  // shared face: the second element lives on another rank
       const int nf = e2f[static_cast<size_t>(nfe + 1) * e];
       e2f[static_cast<size_t>(nfe + 1) * e + nf + 1] = f;
       e2f[static_cast<size_t>(nfe + 1) * e] = nf + 1;
@@ -709,6 +725,39 @@ void build_host_pipe(tpsb_ctx *c, const std::vector<int> &nbr_elem, const std::v
 
 }  // namespace
 
+// Face-neighbour exchange description shared by every path: peers, send / receive offsets, the send-element list on the
+// device, the highest-priority exchange stream and its events.  Returns an error string (empty on success).
+static std::string setup_halo_desc(tpsb_ctx *c, const tpsb_halo_desc *halo, int NEH) {
+  if (!halo || halo->num_nbr_ranks <= 0 || !halo->nccl_comm || !halo->nbr_rank || !halo->send_offset || !halo->send_elems ||
+      !halo->recv_offset)
+    return "mesh has " + std::to_string(NEH) + " face-neighbour elements but no halo description";
+  const int np = halo->num_nbr_ranks;
+  c->comm = static_cast<ncclComm_t>(halo->nccl_comm);
+  c->nbr_rank.assign(halo->nbr_rank, halo->nbr_rank + np);
+  c->send_offset.assign(halo->send_offset, halo->send_offset + np + 1);
+  c->recv_offset.assign(halo->recv_offset, halo->recv_offset + np + 1);
+  c->n_send = c->send_offset[np];
+  if (c->recv_offset[np] != NEH) return "recv_offset does not cover the " + std::to_string(NEH) + " face-neighbour elements";
+  for (int k = 0; k < c->n_send; k++)
+    if (halo->send_elems[k] < 0 || halo->send_elems[k] >= c->NE) return "send_elems out of range";
+  std::vector<int> se(halo->send_elems, halo->send_elems + c->n_send);
+  cudaError_t ce = upload(&c->d_send_elems, se);
+  if (ce == cudaSuccess) {
+    // highest priority: the exchange kernels must get SM slots while the interior gradient / face kernels (hundreds of
+    // thousands of queued CTAs) run, or the "overlapped" exchange only starts when they drain
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    static const bool flat = getenv("TPSB_COMM_PRIO") && atoi(getenv("TPSB_COMM_PRIO")) == 0;
+    ce = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, flat ? prio_lo : prio_hi);
+  }
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvU, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvG, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvT, cudaEventDisableTiming);
+  if (ce != cudaSuccess) return std::string("halo setup failed: ") + cudaGetErrorString(ce);
+  return "";
+}
+
 extern "C" {
 
 const char *tpsb_version(void) { return "tpsb200 0.1 (sm_100a, fp64)"; }
@@ -771,9 +820,6 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (phys->use_mixing_length) want_generic = true;  // the mixing-length model lives on the generic path
   for (int i = 0; bcs && bcs->bcs && i < bcs->num_bcs; i++)  // ... and so does the general wall (WallType VISC_GNRL)
     if (bcs->bcs[i].kind == TPSB_BC_WALL && bcs->bcs[i].type == 4) want_generic = true;
-  if (want_generic) {
-    if (maps->num_nbr_elems > 0 || halo) return fail(ctx, TPSB_ENOTIMPL, "partitioned meshes are not built on the generic path yet");
-  }
   const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
   if (phys->sgs_model < 0 || phys->sgs_model > 2) return fail(ctx, TPSB_EINVAL, "sgs_model %d: 0 none, 1 smagorinsky, 2 sigma", phys->sgs_model);
   if (visc_mod && want_generic)
@@ -877,7 +923,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     c->nd = 1;
     for (int d = 0; d < maps->dim; d++) c->nd *= c->np;
     c->N = static_cast<long long>(c->NE) * c->nd;
-    const std::string err = create_generic(c, maps, space, phys, bcs);
+    const std::string err = create_generic(c, maps, space, phys, bcs, halo);
     if (!err.empty()) {
       tpsb_destroy(c);
       return fail(nullptr, TPSB_EINVAL, "%s", err.c_str());
@@ -1105,41 +1151,19 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
 
   // ---- halo ----
   if (ce == cudaSuccess && NEH > 0) {
-    if (!halo || halo->num_nbr_ranks <= 0 || !halo->nccl_comm || !halo->nbr_rank || !halo->send_offset ||
-        !halo->send_elems || !halo->recv_offset) {
+    const std::string herr = setup_halo_desc(c, halo, NEH);
+    if (!herr.empty()) {
       tpsb_destroy(c);
-      return fail(nullptr, TPSB_EINVAL, "mesh has %d face-neighbour elements but no halo description", NEH);
+      return fail(nullptr, TPSB_EINVAL, "%s", herr.c_str());
     }
     const int np = halo->num_nbr_ranks;
-    c->comm = static_cast<ncclComm_t>(halo->nccl_comm);
-    c->nbr_rank.assign(halo->nbr_rank, halo->nbr_rank + np);
-    c->send_offset.assign(halo->send_offset, halo->send_offset + np + 1);
-    c->recv_offset.assign(halo->recv_offset, halo->recv_offset + np + 1);
-    c->n_send = c->send_offset[np];
-    if (c->recv_offset[np] != NEH) {
-      tpsb_destroy(c);
-      return fail(nullptr, TPSB_EINVAL, "recv_offset does not cover the %d face-neighbour elements", NEH);
-    }
     std::vector<int> se(halo->send_elems, halo->send_elems + c->n_send);
-    ce = upload(&c->d_send_elems, se);
     const size_t hb = static_cast<size_t>(c->NH) * sizeof(double), sb = static_cast<size_t>(c->n_send) * c->nd * sizeof(double);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Uhalo, hb * NEQ);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_UpHalo, hb * NEQ);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUpHalo, hb * NEQ * DIM);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendU, sb * NEQ);
     if (ce == cudaSuccess) ce = cudaMalloc(&c->d_sendG, sb * NEQ * DIM);
-    if (ce == cudaSuccess) {
-      // highest priority: the exchange kernels must get SM slots while the interior gradient / face kernels (hundreds of
-      // thousands of queued CTAs) run, or the "overlapped" exchange only starts when they drain
-      int prio_lo = 0, prio_hi = 0;
-      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-      static const bool flat = getenv("TPSB_COMM_PRIO") && atoi(getenv("TPSB_COMM_PRIO")) == 0;
-      ce = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, flat ? prio_lo : prio_hi);
-    }
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvU, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvG, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_recvT, cudaEventDisableTiming);
     if (c->fast) {
       // trace blocks this rank sends to peer p: for each send element (in send order = the receiver's halo
       // order) its local faces, ascending, whose neighbour is a halo element owned by p.  The receiver sorts
@@ -1721,13 +1745,24 @@ static int gen_block_threads(const GenArgs &g) {
   const int items = std::max(std::max(g.dof, g.nqv), g.nfe * g.nqf);
   return std::min(128, std::max(32, ((items + 31) / 32) * 32));
 }
+static int exchange(tpsb_ctx *ctx, const double *src, int nfld, double *sendbuf, double *recvbuf, cudaEvent_t done);
 static int run_gradients_generic(tpsb_ctx *ctx, const double *d_x, bool prims_done) {
   tpsb_ctx *c = ctx;
   GenArgs g = c->gen;
   g.U = d_x;
+  if (c->NEH > 0) {  // face-neighbour state first (RHSoperator::Mult, src/rhs_operator.cpp:349-361)
+    int rc = exchange(c, d_x, g.neq, c->d_sendU, c->d_Uhalo, c->ev_recvU);
+    if (rc) return rc;
+  }
   if (!prims_done) {
     ProfScope ps(c, K_PRIM);
     gen_prim_kernel<<<static_cast<unsigned>((g.N + 255) / 256), 256, 0, c->stream>>>(g);
+  }
+  if (c->NEH > 0) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvU, 0));
+    ProfScope ps(c, K_PRIM);
+    const long long nh = static_cast<long long>(c->NEH) * g.dof;
+    gen_prim_halo_kernel<<<static_cast<unsigned>((nh + 255) / 256), 256, 0, c->stream>>>(g);
   }
   {
     ProfScope ps(c, K_GRAD);
@@ -1757,6 +1792,11 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   GenArgs g = c->gen;
   g.U = d_x;
   g.y = d_y;
+  if (c->NEH > 0 && g.eq_system != 0) {  // face-neighbour gradients for the viscous face fluxes (rhs_operator.cpp:363-375)
+    rc = exchange(c, c->d_gradUp, g.neq * g.dim, c->d_sendG, c->d_gradUpHalo, c->ev_recvG);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_recvG, 0));
+  }
   {
     ProfScope ps(c, K_RESID);
     const size_t smem = gen_resid_smem(g);
@@ -2047,6 +2087,19 @@ int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance) {
   if (!ctx->generic) return fail(ctx, TPSB_EINVAL, "the wall distance is read by the mixing-length model (generic path) only");
   ctx->gen.dist = d_distance;
   ode_graph_invalidate(ctx);  // the pointer is baked into the captured launches
+  if (ctx->NEH > 0 && d_distance) {  // the neighbours' side of a shared face interpolates ITS distance (face_integrator.cpp:304-309)
+    CU(cudaSetDevice(ctx->device));
+    double *dh = nullptr, *sb = nullptr;
+    CU(cudaMalloc(&dh, static_cast<size_t>(ctx->NEH) * ctx->nd * sizeof(double)));
+    CU(cudaMalloc(&sb, static_cast<size_t>(std::max(ctx->n_send, 1)) * ctx->nd * sizeof(double)));
+    ctx->gen_allocs.push_back(dh);
+    const int rc = exchange(ctx, d_distance, 1, sb, dh, ctx->ev_recvU);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_recvU, 0));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(sb);
+    ctx->gen.distHalo = dh;
+  }
   return TPSB_OK;
 }
 
