@@ -106,6 +106,25 @@ static TransportProperties *wrap_mixing_length(const OrcPhysParams &p, GasMixtur
 }
 
 
+// Fluxes with or without its SGS model / viscous sponge: the constructor M2ulPhyS uses (fluxes.cpp:57-95) reads these from
+// RunConfiguration and normalises the sponge normal; the device constructor (fluxes.cpp:97-128) takes them as given
+static Fluxes *make_fluxes(const OrcPhysParams &p, GasMixture *mix, Equations eqs, TransportProperties *trans, int neq, int dim,
+                           bool axisym) {
+  if (p.sgs_model == 0 && p.sponge_enabled == 0) return new Fluxes(mix, eqs, trans, neq, dim, axisym);  // fluxes.cpp:34
+  viscositySpongeData vsd;
+  vsd.enabled = p.sponge_enabled != 0;
+  double nm = 0;
+  for (int d = 0; d < 3; d++) nm += p.sponge_normal[d] * p.sponge_normal[d];
+  nm = std::sqrt(nm);
+  for (int d = 0; d < 3; d++) {
+    vsd.n[d] = vsd.enabled ? p.sponge_normal[d] / nm : 0.0;
+    vsd.p[d] = p.sponge_point[d];
+  }
+  vsd.ratio = p.sponge_ratio;
+  vsd.width = p.sponge_width;
+  return new Fluxes(mix, eqs, trans, neq, dim, axisym, p.sgs_model, p.sgs_floor, p.sgs_const, vsd);
+}
+
 namespace orc {
 
 class DryAirRef : public Physics {
@@ -128,25 +147,7 @@ class DryAirRef : public Physics {
     mix_ = new DryAir(in, dim, nvel);                                                          // equation_of_state.cpp:150
     trans_ = new DryAirTransport(mix_, p.visc_mult, p.bulk_visc_mult, p.C1, p.S0, p.Pr);       // transport_properties.cpp:208
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
-    if (p.sgs_model != 0 || p.sponge_enabled != 0) {
-      // the constructor M2ulPhyS uses (fluxes.cpp:57-95) reads these from RunConfiguration and normalises the sponge
-      // normal; the device constructor (fluxes.cpp:97-128) takes them as given
-      viscositySpongeData vsd;
-      vsd.enabled = p.sponge_enabled != 0;
-      double nm = 0;
-      for (int d = 0; d < 3; d++) nm += p.sponge_normal[d] * p.sponge_normal[d];
-      nm = std::sqrt(nm);
-      for (int d = 0; d < 3; d++) {
-        vsd.n[d] = vsd.enabled ? p.sponge_normal[d] / nm : 0.0;
-        vsd.p[d] = p.sponge_point[d];
-      }
-      vsd.ratio = p.sponge_ratio;
-      vsd.width = p.sponge_width;
-      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), wrap_mixing_length(p, mix_, trans_), neq, dim, axisym,
-                         p.sgs_model, p.sgs_floor, p.sgs_const, vsd);
-    } else {
-      flux_ = new Fluxes(mix_, static_cast<Equations>(p.eq_system), wrap_mixing_length(p, mix_, trans_), neq, dim, axisym);   // fluxes.cpp:34
-    }
+    flux_ = make_fluxes(p, mix_, static_cast<Equations>(p.eq_system), wrap_mixing_length(p, mix_, trans_), neq, dim, axisym);
     rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, p.use_roe != 0, axisym);  // riemann_solver.cpp:38
     use_roe_ = p.use_roe != 0;
     eqs_ = static_cast<Equations>(p.eq_system);
@@ -296,7 +297,7 @@ class MixtureRef : public Physics {
     }
     const Equations eqs = static_cast<Equations>(p.eq_system);
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
-    flux_ = new Fluxes(mix_, eqs, wrap_mixing_length(p, mix_, static_cast<MolecularTransport *>(trans_)), neq, dim, axisym);
+    flux_ = make_fluxes(p, mix_, eqs, wrap_mixing_length(p, mix_, static_cast<MolecularTransport *>(trans_)), neq, dim, axisym);
     rs_ = new RiemannSolverTPS(neq, mix_, eqs, flux_, false, axisym);
     eqs_ = eqs;
     cfg_.workFluid = USER_DEFINED;

@@ -73,8 +73,10 @@ __host__ __device__ __forceinline__ void dry_gen_conv_flux(const GenPhys &g, con
 // `dim` are zero, so sums keep the reference's operation order): nvcc 12.9 -O3 produced wrong stores for the
 // run-time-indexed form once inlined into gen_resid_kernel (caught by the parity test; the stand-alone
 // function was correct, tools/ubench/gen_visc_check.cu).
+// ax != NULL: Fluxes' sub-grid-scale model / planar viscous sponge (fluxes.cpp:224-246) with the element size delta and the
+// physical point the caller supplies (the SGS models read a 3 x 3 velocity gradient: dim == 3 only, checked at create).
 __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
-                                                           double *f, double distance = 0.0) {
+                                                           double *f, double distance = 0.0, const DryAux *ax = nullptr) {
   const int neq = g.neq, dim = g.dim;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (g.dry.eq_system == 0) return;
@@ -85,6 +87,7 @@ __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, con
   double k = g.dry.cp_div_pr * visc;
   if (g.ml_on) mixlen_add(dim, g.nvel, neq, g.ml_max, g.ml_prt, g.ml_bulk, s, gr, radius, distance, visc, bulk, k);
   bulk -= 2. / 3. * visc;
+  if (ax && (g.dry.sgs_model | g.dry.sponge)) dry_modify_transport(g.dry, s[0], gr + 1, neq, *ax, visc, bulk, k);
   double gu[3][3], st[3][3], vel[3], gT[3];  // gu[i][d] = d u_i / d x_d
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -135,16 +138,18 @@ __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, con
 // species-enthalpy term, single temperature.  nrm = unit normal; heat_prescribed: primFluxIdxs[numSpecies + nvel]
 // (prescribed value 0: adiabatic wall).
 __host__ __device__ __forceinline__ void dry_gen_bdr_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
-                                                               const double *nrm, bool heat_prescribed, double *nf) {
+                                                               const double *nrm, bool heat_prescribed, double *nf,
+                                                               const DryAux *ax = nullptr) {
   const int neq = g.neq, dim = g.dim, nvel = g.nvel;
   for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
   if (g.dry.eq_system == 0) return;
   const double pr = dry_gen_pressure(g, s);
   const double temp = pr / g.dry.R / s[0];
-  const double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
+  double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
   double bulk = g.dry.bulk_visc_mult * visc;
-  const double k = g.dry.cp_div_pr * visc;
+  double k = g.dry.cp_div_pr * visc;
   bulk -= 2. / 3. * visc;
+  if (ax && (g.dry.sgs_model | g.dry.sponge)) dry_modify_transport(g.dry, s[0], gr + 1, neq, *ax, visc, bulk, k);  // fluxes.cpp:386-407
   double gu[3][3], st[3][3], nn[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -200,13 +205,15 @@ __host__ __device__ __forceinline__ void gen_conv_flux(const GenPhys &g, const d
 }
 // distance: wall distance at the point (mixing-length model only; the viscous walls pass 0 as the reference does)
 __host__ __device__ __forceinline__ void gen_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
-                                                       double *f, double distance = 0.0) {
-  if (g.fluid) mix_visc_flux(*g.mix, s, gr, radius, f, distance); else dry_gen_visc_flux(g, s, gr, radius, f, distance);
+                                                       double *f, double distance = 0.0, const DryAux *ax = nullptr) {
+  if (g.fluid) mix_visc_flux(*g.mix, s, gr, radius, f, distance, &g.dry, ax);
+  else dry_gen_visc_flux(g, s, gr, radius, f, distance, ax);
 }
 __host__ __device__ __forceinline__ void gen_bdr_visc_flux(const GenPhys &g, const double *s, const double *gr, double radius,
-                                                           const double *nrm, bool heat_prescribed, double *nf) {
-  if (g.fluid) mix_bdr_visc_flux(*g.mix, s, gr, radius, nrm, heat_prescribed, nf);
-  else dry_gen_bdr_visc_flux(g, s, gr, radius, nrm, heat_prescribed, nf);
+                                                           const double *nrm, bool heat_prescribed, double *nf,
+                                                           const DryAux *ax = nullptr) {
+  if (g.fluid) mix_bdr_visc_flux(*g.mix, s, gr, radius, nrm, heat_prescribed, nf, &g.dry, ax);
+  else dry_gen_bdr_visc_flux(g, s, gr, radius, nrm, heat_prescribed, nf, ax);
 }
 __host__ __device__ __forceinline__ double gen_pressure(const GenPhys &g, const double *s) {
   return g.fluid ? mix_pressure(*g.mix, s, nullptr) : dry_gen_pressure(g, s);

@@ -10,6 +10,8 @@
 
 #include <cmath>
 
+#include "physics.cuh"  // PhysParams / DryAux / dry_modify_transport: the SGS and sponge block is fluid independent
+
 namespace tpsb {
 
 constexpr int MIX_MAXSP = 8;    // gpudata::MAXSPECIES
@@ -815,7 +817,9 @@ MIXBIG void mix_conv_flux(const MixParams &m, const double *s, double *f) {
 }
 
 // Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335), no SGS / sponge; radius = x[0] (axisymmetric terms only)
-MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, double *f, double distance = 0.0) {
+// mod / ax != NULL: the SGS model / viscous sponge block (fluxes.cpp:224-246) with the caller's element size and point
+MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, double *f, double distance = 0.0,
+                          const PhysParams *mod = nullptr, const DryAux *ax = nullptr) {
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (m.eq_system == 0) return;
@@ -823,11 +827,19 @@ MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr,
   mix_species_enthalpies(m, s, hsp);
   mix_flux_transport(m, s, gr, tb, V);
   if (m.mlOn) mixlen_add(dim, nvel, neq, m.mlMax, m.mlPrt, m.mlBulk, s, gr, radius, distance, tb[0], tb[1], tb[2]);
-  const double visc = tb[0];
+  double visc = tb[0];
   double bulk = tb[1];
   bulk -= 2. / 3. * visc;
   double k = tb[2];
   const double ke = tb[3];
+  if (mod && ax && (mod->sgs_model | mod->sponge)) {
+    dry_modify_transport(*mod, s[0], gr + 1, neq, *ax, visc, bulk, k);
+    if (mod->sponge) {  // the sponge also scales the active species' diffusion velocities (fluxes.cpp:241-245)
+      const double wgt = dry_sponge_weight(*mod, ax->x);
+      for (int sp = 0; sp < m.numActive; sp++)
+        for (int d = 0; d < dim; d++) V[sp + d * ns] *= wgt;
+    }
+  }
   if (m.twoTemp) {
     for (int d = 0; d < dim; d++) {
       const double qeFlux = ke * gr[neq - 1 + d * neq];
@@ -897,23 +909,26 @@ MIXBIG void mix_visc_flux(const MixParams &m, const double *s, const double *gr,
 // General form: pf[0..numSpecies) are the prescribed species diffusion velocities (NULL: zeros), hvy_prescribed /
 // elec_prescribed select the prescribed heat fluxes pf[numSpecies + nvel] / pf[numSpecies + nvel + 1].
 MIXBIG void mix_bdr_visc_flux_general(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
-                                      const double *pf, bool hvy_prescribed, bool elec_prescribed, double *nf);
+                                      const double *pf, bool hvy_prescribed, bool elec_prescribed, double *nf,
+                                      const PhysParams *mod = nullptr, const DryAux *ax = nullptr);
 MIXBIG void mix_bdr_visc_flux(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
-                              bool heat_prescribed, double *nf) {
-  mix_bdr_visc_flux_general(m, s, gr, radius, nrm, nullptr, heat_prescribed, heat_prescribed, nf);
+                              bool heat_prescribed, double *nf, const PhysParams *mod = nullptr, const DryAux *ax = nullptr) {
+  mix_bdr_visc_flux_general(m, s, gr, radius, nrm, nullptr, heat_prescribed, heat_prescribed, nf, mod, ax);
 }
 MIXBIG void mix_bdr_visc_flux_general(const MixParams &m, const double *s, const double *gr, double radius, const double *nrm,
-                                      const double *pfl, bool hvy_prescribed, bool elec_prescribed, double *nf) {
+                                      const double *pfl, bool hvy_prescribed, bool elec_prescribed, double *nf,
+                                      const PhysParams *mod, const DryAux *ax) {
   const int neq = m.neq, dim = m.dim, nvel = m.nvel, ns = m.numSpecies;
   for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
   if (m.eq_system == 0) return;
   double tb[4], Vunused[MIX_MAXSP * MIX_MAXDIM];
   mix_flux_transport(m, s, gr, tb, Vunused);
-  const double visc = tb[0];
+  double visc = tb[0];
   double bulk = tb[1];
   bulk -= 2. / 3. * visc;
   double k = tb[2];
   const double ke = tb[3];
+  if (mod && ax && (mod->sgs_model | mod->sponge)) dry_modify_transport(*mod, s[0], gr + 1, neq, *ax, visc, bulk, k);  // fluxes.cpp:386-407
   // species part of normalPrimFlux is replaced by the prescribed zeros, so the species-enthalpy terms vanish
   double gu[3][3], st[3][3], nn[3];
 #pragma unroll

@@ -102,7 +102,7 @@ __device__ __forceinline__ void dry_riemann_lf(const PhysParams &p, const double
 // (transport_properties.cpp:223-234): non-axisymmetric, no SGS, no viscous sponge, single temperature.
 // g[eq + d*NEQ] = d(Up_eq)/dx_d ; f[eq + d*NEQ].
 struct DryAux;
-__device__ __forceinline__ void dry_modify_transport(const PhysParams &p, double rho, const double *gv, int ds, const DryAux &ax,
+__host__ __device__ __forceinline__ void dry_modify_transport(const PhysParams &p, double rho, const double *gv, int ds, const DryAux &ax,
                                                      double &visc, double &bulk, double &k);
 __device__ __forceinline__ void dry_visc_flux(const PhysParams &p, const double *s, const double *g, double *f,
                                               const DryAux *ax = nullptr) {
@@ -143,7 +143,7 @@ __device__ __forceinline__ void dry_visc_flux(const PhysParams &p, const double 
 
 // Fluxes::sgsSmag (fluxes.cpp:513-541): mu_sgs = rho (C_d max(delta - floor, 0))^2 sqrt(2 S_ij S_ij).
 // gv[i + ds*d] = d u_i / d x_d
-__device__ __forceinline__ double dry_sgs_smag(const PhysParams &p, double rho, const double *gv, int ds, double delta) {
+__host__ __device__ __forceinline__ double dry_sgs_smag(const PhysParams &p, double rho, const double *gv, int ds, double delta) {
   const double s3 = 0.5 * (gv[0 + ds] + gv[1]), s4 = 0.5 * (gv[0 + 2 * ds] + gv[2]), s5 = 0.5 * (gv[1 + 2 * ds] + gv[2 + ds]);
   double sm = 0.;
   sm += gv[0] * gv[0];
@@ -159,7 +159,7 @@ __device__ __forceinline__ double dry_sgs_smag(const PhysParams &p, double rho, 
 // Fluxes::sgsSigma (fluxes.cpp:543-650), the branch without LAPACK (the one a device build and the oracle's
 // reference object code run): singular values of grad u from the closed-form eigenvalues of d^4 g^T g
 // (Nicoud et al. 2011); the reference's truncated pi and its 1e-12 guards are kept.
-__device__ __noinline__ double dry_sgs_sigma(const PhysParams &p, double rho, const double *gv, int ds, double delta) {
+__host__ __device__ __noinline__ double dry_sgs_sigma(const PhysParams &p, double rho, const double *gv, int ds, double delta) {
   const double sml = 1.0e-12, pi = 3.14159265359, third = 1. / 3.;
   const double dm = fmax(delta - p.sgs_floor, sml);
   const double d4 = pow(dm, 4);
@@ -194,7 +194,7 @@ __device__ __noinline__ double dry_sgs_sigma(const PhysParams &p, double rho, co
   return mu;
 }
 // Fluxes::viscSpongePlanar (fluxes.cpp:664-684)
-__device__ __forceinline__ double dry_sponge_weight(const PhysParams &p, const double *x) {
+__host__ __device__ __forceinline__ double dry_sponge_weight(const PhysParams &p, const double *x) {
   const double factor = fmax(p.sp_ratio, 1.0);
   double dist = 0.;
 #pragma unroll
@@ -206,8 +206,8 @@ __device__ __forceinline__ double dry_sponge_weight(const PhysParams &p, const d
 }
 // the modification block of Fluxes::ComputeViscousFluxes / ComputeBdrViscousFluxes (fluxes.cpp:224-246, 386-407):
 // bulk arrives as (bulk_mult - 2/3) visc
-__device__ __forceinline__ void dry_modify_transport(const PhysParams &p, double rho, const double *gv, int ds, const DryAux &ax,
-                                                     double &visc, double &bulk, double &k) {
+__host__ __device__ __forceinline__ void dry_modify_transport(const PhysParams &p, double rho, const double *gv, int ds,
+                                                              const DryAux &ax, double &visc, double &bulk, double &k) {
   if (p.sgs_model > 0) {
     const double pr_cp = visc / k;
     const double mu_sgs = p.sgs_model == 1 ? dry_sgs_smag(p, rho, gv, ds, ax.delta) : dry_sgs_sigma(p, rho, gv, ds, ax.delta);

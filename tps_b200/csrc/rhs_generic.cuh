@@ -64,7 +64,20 @@ struct GenArgs {
   // received from their owners (RHSoperator::initNBlockDataTransfer / waitAllDataTransfer, src/rhs_operator.cpp:716-831)
   int NEH;
   const double *Uhalo, *UpHalo, *gradUpHalo, *distHalo;
+  // Fluxes' SGS model / viscous sponge: delta = h_min / order of every element (local, then face-neighbour); NULL: off
+  const double *elem_delta;
 };
+
+// physical point of reference point xi of element vertices v (sponge distance; z = 0 on quadrilaterals)
+__device__ __forceinline__ void gen_point(int dim, const double *v, const double *xi, double *X) {
+  if (dim == 3) {
+    hex_point(v, xi[0], xi[1], xi[2], X);
+  } else {
+    const double x = xi[0], y = xi[1];
+    for (int i = 0; i < 2; i++) X[i] = (1 - x) * (1 - y) * v[0 + i] + x * (1 - y) * v[2 + i] + x * y * v[4 + i] + (1 - x) * y * v[6 + i];
+    X[2] = 0.0;
+  }
+}
 
 // field `fld` (of nfld) of element el: local elements live in the byNODES array, face-neighbour elements in the halo copy
 __device__ __forceinline__ const double *gen_elem_field(const GenArgs &a, const double *local, const double *halo, int el, int fld,
@@ -140,7 +153,8 @@ __device__ __forceinline__ void gen_bc_prim_for_gradient(const GenPhys &g, const
 // computeAdiabaticWallFlux / computeIsothermalWallFlux (wallBC.cpp:277-320, 430-510), any fluid, 2-D / 3-D /
 // axisymmetric.  gr[eq + d*neq]: interior gradients of the primitives; nor: CalcOrtho normal (area weighted, outward).
 __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int use_bc_in_grad, const double *u1, const double *gr,
-                                         const double *nor, double radius, double *fx, double distance = 0.0) {
+                                         const double *nor, double radius, double *fx, double distance = 0.0,
+                                         const DryAux *ax = nullptr) {
   const int neq = g.neq, dim = g.dim, nvel = g.nvel;
   double s2[GEN_MAXEQ], viscF[GEN_MAXEQ * GEN_MAXDIM], wallViscF[GEN_MAXEQ], un[3];
   double normN = 0.;
@@ -195,13 +209,13 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
     for (int d = 0; d < dim; d++) un[d] = nor[d] * isq;
     const bool hvy_presc = hvy != 1, elec_presc = (elec == 0) || (elec == 2 && twoT);
     if (g.fluid)
-      mix_bdr_visc_flux_general(*g.mix, s2, gr, radius, un, pf, hvy_presc, elec_presc, wallViscF);
+      mix_bdr_visc_flux_general(*g.mix, s2, gr, radius, un, pf, hvy_presc, elec_presc, wallViscF, &g.dry, ax);
     else
-      dry_gen_bdr_visc_flux(g, s2, gr, radius, un, hvy_presc, wallViscF);
+      dry_gen_bdr_visc_flux(g, s2, gr, radius, un, hvy_presc, wallViscF, ax);
     (void)nsp;
     const double nm = sqrt(normN);
     for (int eq = 0; eq < neq; eq++) wallViscF[eq] *= nm;
-    gen_visc_flux(g, u1, gr, radius, viscF);
+    gen_visc_flux(g, u1, gr, radius, viscF, 0.0, ax);
     for (int eq = 1; eq < neq; eq++) {
       fx[eq] -= 0.5 * wallViscF[eq];
       for (int d = 0; d < dim; d++) fx[eq] -= 0.5 * viscF[eq + d * neq] * nor[d];
@@ -222,12 +236,12 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
     if (nvel == 3 && dim == 2) s2[3] = u1[0] * vel[2];
     gen_riemann(g, u1, s2, nor, fx);  // the inviscid wall does not force Lax-Friedrichs (wallBC.cpp:301)
     if (!ns) return;
-    gen_visc_flux(g, s2, gr, radius, viscF, distance);  // only the inviscid wall passes the wall distance on (wallBC.cpp:309-313)
+    gen_visc_flux(g, s2, gr, radius, viscF, distance, ax);  // only the inviscid wall passes the wall distance on (wallBC.cpp:309-313)
     for (int eq = 0; eq < neq; eq++) {
       wallViscF[eq] = 0.;
       for (int d = 0; d < dim; d++) wallViscF[eq] += viscF[eq + d * neq] * nor[d];
     }
-    gen_visc_flux(g, u1, gr, radius, viscF, distance);
+    gen_visc_flux(g, u1, gr, radius, viscF, distance, ax);
   } else {
     const double isq = 1. / sqrt(normN);
     for (int d = 0; d < dim; d++) un[d] = nor[d] * isq;
@@ -235,7 +249,7 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
       gen_stagnation_state(g, u1, s2);
       gen_riemann_lf(g, u1, s2, nor, fx);
       if (!ns) return;
-      gen_bdr_visc_flux(g, s2, gr, radius, un, true, wallViscF);
+      gen_bdr_visc_flux(g, s2, gr, radius, un, true, wallViscF, ax);
     } else {  // VISC_ISOTH
       if (use_bc_in_grad) {
         for (int eq = 0; eq < neq; eq++) s2[eq] = u1[eq];
@@ -246,11 +260,11 @@ __device__ __noinline__ void gen_bc_flux(const GenPhys &g, const GenBc &bc, int 
       gen_riemann_lf(g, u1, s2, nor, fx);
       if (!ns) return;
       gen_stagnant_state_with_temp(g, u1, bc.d[0], s2);
-      gen_bdr_visc_flux(g, s2, gr, radius, un, false, wallViscF);
+      gen_bdr_visc_flux(g, s2, gr, radius, un, false, wallViscF, ax);
     }
     const double nm = sqrt(normN);
     for (int eq = 0; eq < neq; eq++) wallViscF[eq] *= nm;
-    gen_visc_flux(g, u1, gr, radius, viscF);
+    gen_visc_flux(g, u1, gr, radius, viscF, 0.0, ax);
   }
   for (int eq = 1; eq < neq; eq++) {
     fx[eq] -= 0.5 * wallViscF[eq];
@@ -447,7 +461,12 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
     if (a.eq_system != 0) {
       const double radius = ph.axisym ? gen_quad_x(vx, a.xiN + k * dim) : -1.0;  // nodal coordinate (GetFlux :526-528)
       const double dw = a.dist ? a.dist[static_cast<long long>(e) * dof + k] : 0.0;  // rhs_operator.cpp:534-537
-      gen_visc_flux(ph, s, gr, radius, fv, dw);
+      DryAux ax;
+      if (a.elem_delta) {  // SGS model / viscous sponge: the element's delta, the node's coordinates (rhs_operator.cpp:526-533)
+        ax.delta = a.elem_delta[e];
+        gen_point(dim, vx, a.xiN + k * dim, ax.x);
+      }
+      gen_visc_flux(ph, s, gr, radius, fv, dw, a.elem_delta ? &ax : nullptr);
       for (int c = 0; c < nc; c++) fc[c] -= fv[c];
     }
     for (int c = 0; c < nc; c++) sF[k * nc + c] = fc[c];
@@ -528,7 +547,12 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
         double dwb = 0.0;  // BCintegrator.cpp:408-411
         if (a.dist)
           for (int k = 0; k < dof; k++) dwb += po[k] * a.dist[static_cast<long long>(e1) * dof + k];
-        gen_bc_flux(ph, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb);
+        DryAux axb;
+        if (a.elem_delta) {  // BCintegrator.cpp:395-411: the face point, the boundary element's delta
+          axb.delta = a.elem_delta[e1];
+          gen_point(dim, v1, xi1, axb.x);
+        }
+        gen_bc_flux(ph, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb, a.elem_delta ? &axb : nullptr);
         const double sgb = -(ph.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
         for (int eq = 0; eq < neq; eq++) dstq[eq] = sgb * fxb[eq];
         continue;
@@ -570,8 +594,16 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
             dwo += po[k] * a.dist[static_cast<long long>(e) * dof + k];
             dwn += pn[k] * gen_elem_field(a, a.dist, a.distHalo, eo, 0, 1)[k];
           }
-        gen_visc_flux(ph, u1, g1, radius, f1, first ? dwo : dwn);
-        gen_visc_flux(ph, u2, g2, radius, f2, first ? dwn : dwo);
+        // same physical point for both sides, each side's own delta (parity trap 5, face_integrator.cpp:251-276, 333-334)
+        DryAux ax1, ax2;
+        if (a.elem_delta) {
+          gen_point(dim, v1, xi1, ax1.x);
+          ax2.x[0] = ax1.x[0], ax2.x[1] = ax1.x[1], ax2.x[2] = ax1.x[2];
+          ax1.delta = a.elem_delta[e1];
+          ax2.delta = a.elem_delta[e2];
+        }
+        gen_visc_flux(ph, u1, g1, radius, f1, first ? dwo : dwn, a.elem_delta ? &ax1 : nullptr);
+        gen_visc_flux(ph, u2, g2, radius, f2, first ? dwn : dwo, a.elem_delta ? &ax2 : nullptr);
         for (int eq = 0; eq < neq; eq++) {
           double v = 0;
           for (int d = 0; d < dim; d++) v += (-0.5 * (f1[eq + d * neq] + f2[eq + d * neq])) * nor[d];

@@ -603,6 +603,17 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   g.Up = c->d_Up, g.gradUp = c->d_gradUp, g.maxCharBits = c->d_maxBits;
   g.NEH = c->NEH;
   g.Uhalo = g.UpHalo = g.gradUpHalo = g.distHalo = nullptr;
+  g.elem_delta = nullptr;
+  if (c->phys.sgs_model | c->phys.sponge) {
+    // delta = Mesh::GetElementSize(e, 1) / order (rhs_operator.cpp:149-156), local then face-neighbour elements
+    std::vector<double> delta(static_cast<size_t>(NE + c->NEH));
+    for (int e = 0; e < NE + c->NEH; e++) {
+      const double *v = &maps->elem_vertices[static_cast<size_t>(e) * nv * dim];
+      delta[e] = (dim == 3 ? hex_min_size(v) : quad_min_size(v)) / p;
+    }
+    ce = g_upload(c, &g.elem_delta, delta);
+    if (ce != cudaSuccess) return std::string("device setup failed: ") + cudaGetErrorString(ce);
+  }
   if (c->NEH > 0) {  // partitioned mesh: face-neighbour copies and the exchange description
     const std::string herr = setup_halo_desc(c, halo, c->NEH);
     if (!herr.empty()) return herr;
@@ -822,8 +833,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     if (bcs->bcs[i].kind == TPSB_BC_WALL && bcs->bcs[i].type == 4) want_generic = true;
   const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
   if (phys->sgs_model < 0 || phys->sgs_model > 2) return fail(ctx, TPSB_EINVAL, "sgs_model %d: 0 none, 1 smagorinsky, 2 sigma", phys->sgs_model);
-  if (visc_mod && want_generic)
-    return fail(ctx, TPSB_ENOTIMPL, "SGS models and the viscous sponge are built on the 3-D dry-air Gauss-Legendre path only");
+  if (phys->sgs_model != 0 && maps->dim != 3)
+    return fail(ctx, TPSB_ENOTIMPL, "the SGS models read a 3 x 3 velocity gradient (fluxes.cpp:513-650): 3-D runs only");
   if (phys->sponge_enabled) {
     const double *n = phys->sponge_normal;
     if (!(n[0] * n[0] + n[1] * n[1] + n[2] * n[2] > 0) || !(phys->sponge_width > 0))
