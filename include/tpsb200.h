@@ -245,6 +245,37 @@ int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U);
  * each side's own shape functions (src/face_integrator.cpp:304-309, src/BCintegrator.cpp:408-411).  NULL: zero.     */
 int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance);
 
+/* ---- forcing terms (ForcingTerms subclasses, src/forcing_terms.hpp:54-330): nodal terms added to dU/dt AFTER Me^-1
+ * (src/rhs_operator.cpp:451-461), in the order they are registered here -- the reference registers them in the order
+ * pressure gradient, sponge zones, heat sources, (SourceTerm, AxisymmetricSource: built in), Joule heating
+ * (src/rhs_operator.cpp:101-167).  Node sets are not stored: every node re-evaluates its membership from its own
+ * coordinates (the trilinear map of its element's vertices), which is what the reference's constructors do once.
+ *   PRESSURE_GRADIENT  ConstantPressureGradient::updateTerms, CPU branch (src/forcing_terms.cpp:115-175):
+ *                      d(rho u_d)/dt -= g_d ; d(rho E)/dt -= sum_d (u_d g_d + p d u_d / d x_d)
+ *   HEAT_SOURCE        HeatSource (:923-1010), type "cylinder": + value on rho E for the nodes within `radius` of the
+ *                      segment point1 -> point2
+ *   JOULE_HEATING      JouleHeating::updateTerms (:443-470): + max(field, 0) on rho E (and on the electron energy of a
+ *                      two-temperature mixture); field = nodal DEVICE array of N doubles, kept by reference
+ *   SPONGE_ZONE        SpongeZone (:472-700), dry air: - a sigma multFactor (U - U_target), sigma from the planar or annular
+ *                      zone geometry, a = speed of sound of the target, U_target user defined from (rho, u, v, w, p) or
+ *                      "mixed out" from the mean normal fluxes over the nodes within tol of the zone's entry plane
+ *                      (computeMixedOutValues, all-reduced over the ranks; DryAir::computeConservedStateFromConvectiveFlux,
+ *                      src/equation_of_state.cpp:414-442)                                                          */
+enum { TPSB_FORCING_PRESSURE_GRADIENT = 0, TPSB_FORCING_HEAT_SOURCE = 1, TPSB_FORCING_JOULE_HEATING = 2, TPSB_FORCING_SPONGE_ZONE = 3 };
+typedef struct {
+  int kind;
+  double pressure_grad[3];                                    /* flow/pressureGrad                                        */
+  double hs_point1[3], hs_point2[3], hs_radius, hs_value;     /* heatSource%d/{point1, point2, radius, value}             */
+  const double *joule_heating;                                /* DEVICE, N doubles                                        */
+  int sz_type;                                                /* spongezone%d/type-like: 0 planar, 1 annulus              */
+  int sz_mixed_out;                                           /* 0 user-defined target, 1 mixed-out target                */
+  double sz_normal[3], sz_point0[3], sz_point_init[3];        /* normal (normalised here), end plane point, entry plane pt */
+  double sz_r1, sz_r2, sz_tol, sz_mult;                       /* annulus radii, plane tolerance, multFactor               */
+  double sz_target[5];                                        /* rho, u, v, w, p of the user-defined target               */
+} tpsb_forcing_desc;
+int tpsb_add_forcing(tpsb_ctx *ctx, const tpsb_forcing_desc *desc);
+int tpsb_clear_forcings(tpsb_ctx *ctx);
+
 /* Test hook, host only: the static chunk schedule tpsb_rhs_mult_host uses to overlap copy-in / kernels / copy-out on a
  * single-rank 3-D mesh.  elem_begin / face_begin (two-sided faces, in their order) / bdr_begin (boundary faces, in their
  * order; may be NULL): chunks + 1 entries; ops: (kind, chunk) pairs, kind 0 copy-in + primitives, 1 gradient, 2 face

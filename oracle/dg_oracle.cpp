@@ -216,6 +216,7 @@ struct Oracle {
   std::vector<double> elSize;           // per element delta = h_min / order
   std::vector<double> distance;         // nodal wall distance (M2ulPhyS::distance_, src/M2ulPhyS.cpp:265-283); empty: 0
   std::vector<double> nodeXYZ;          // [NE][dof][dim]
+  std::vector<OrcForcing> forcings;     // ForcingTerms registered by orc_add_forcing, applied in order after Me^-1
   std::map<int, std::vector<double>> shapeTab;  // inf code -> [nqf][dof]
   // work
   std::vector<double> Up, gradUp;
@@ -968,6 +969,157 @@ struct Oracle {
         y[n + 3 * N] += (-rurut + tau_tr) / radius;
       }
     }
+    for (const OrcForcing &f : forcings) apply_forcing(f, y);
+  }
+
+  // The remaining ForcingTerms subclasses (src/forcing_terms.cpp; the file needs MFEM's mesh / FE-space services in its
+  // constructors, so the short updateTerms bodies are restated here), serial like the reference's CPU path.
+  void apply_forcing(const OrcForcing &f, double *y) {
+    if (f.kind == 0) {  // ConstantPressureGradient::updateTerms, CPU branch (:147-172)
+      for (long n = 0; n < N; n++) {
+        double primi[16];
+        for (int eq = 0; eq < neq; eq++) primi[eq] = Up[n + eq * N];
+        const double p = ph->pressure_from_primitives(primi);
+        double grad_pV = 0.;
+        for (int d = 0; d < dim; d++) {
+          const double vel = Up[n + (d + 1) * N];
+          y[n + (d + 1) * N] -= f.pressure_grad[d];
+          grad_pV -= vel * f.pressure_grad[d];
+          grad_pV -= p * gradUp[n + (d + 1) * N + static_cast<size_t>(d) * N * neq];
+        }
+        y[n + (1 + nvel) * N] += grad_pV;
+      }
+    } else if (f.kind == 1) {  // HeatSource::HeatSource node search (:941-970) + updateTerms (:972-985)
+      double norm[3] = {0, 0, 0}, mod = 0.;
+      for (int d = 0; d < dim; d++) norm[d] = f.hs_point2[d] - f.hs_point1[d];
+      for (int d = 0; d < dim; d++) mod += norm[d] * norm[d];
+      mod = sqrt(mod);
+      for (int d = 0; d < dim; d++) norm[d] /= mod;
+      for (long n = 0; n < N; n++) {
+        double X[3] = {0, 0, 0}, proj = 0, normR = 0;
+        for (int d = 0; d < dim; d++) X[d] = nodeXYZ[n * dim + d] - f.hs_point1[d];
+        for (int d = 0; d < dim; d++) proj += X[d] * norm[d];
+        for (int d = 0; d < dim; d++) {
+          const double r = X[d] - proj * norm[d];
+          normR += r * r;
+        }
+        normR = sqrt(normR);
+        if (normR < f.hs_radius && proj > 0 && proj < mod) y[n + (dim + 1) * N] += f.hs_value;
+      }
+    } else if (f.kind == 2) {  // JouleHeating::updateTerms (:443-470)
+      const bool twoT = neq - (nvel + 2) - ph->num_active_species() == 1;
+      for (long n = 0; n < N; n++) {
+        const double heating = f.joule_heating[n];
+        if (heating > 0.) {
+          y[n + (nvel + 1) * N] += heating;
+          if (twoT) y[n + (neq - 1) * N] += heating;
+        }
+      }
+    } else {  // SpongeZone (:472-760), dry air
+      double nrm[3] = {0, 0, 0}, mod = 0.;
+      for (int d = 0; d < dim; d++) mod += f.sz_normal[d] * f.sz_normal[d];
+      mod = sqrt(mod);
+      for (int d = 0; d < dim; d++) nrm[d] = f.sz_normal[d] / mod;
+      double targetU[16], Upt[16];
+      if (!f.sz_mixed_out) {  // USERDEF (:486-520): conserved from (rho, u, v, w, p) via modifyEnergyForPressure
+        double conserved[16];
+        conserved[0] = f.sz_target[0];
+        for (int d = 0; d < nvel; d++) conserved[1 + d] = f.sz_target[0] * f.sz_target[1 + d];
+        conserved[1 + nvel] = 0.0;
+        ph->modify_energy_for_pressure(conserved, targetU, f.sz_target[4], false);
+      } else {  // computeMixedOutValues (:706-742)
+        double mean[17];
+        for (int i = 0; i <= neq; i++) mean[i] = 0.;
+        for (long n = 0; n < N; n++) {
+          double distInit = 0.;
+          for (int d = 0; d < dim; d++) distInit -= nrm[d] * (nodeXYZ[n * dim + d] - f.sz_point_init[d]);
+          bool in;
+          if (f.sz_type == 0) {
+            in = fabs(distInit) < f.sz_tol;
+          } else {
+            double R = 0.;
+            for (int d = 0; d < dim; d++) {
+              const double t = nodeXYZ[n * dim + d] - f.sz_point_init[d] + distInit * nrm[d];
+              R += t * t;
+            }
+            in = fabs(sqrt(R) - f.sz_r1) < f.sz_tol;
+          }
+          if (!in) continue;
+          double up[16], Un[16], fl[48];
+          for (int eq = 0; eq < neq; eq++) up[eq] = Up[n + eq * N];
+          ph->cons(up, Un);
+          ph->conv_flux(Un, fl);
+          for (int eq = 0; eq < neq; eq++)
+            for (int d = 0; d < dim; d++) mean[eq] += nrm[d] * fl[eq + d * neq];
+          mean[neq] += 1.0;
+        }
+        for (int eq = 0; eq < neq; eq++) mean[eq] /= mean[neq];
+        // DryAir::computeConservedStateFromConvectiveFlux (src/equation_of_state.cpp:414-442)
+        const double gamma = phys.gamma;
+        double temp = 0.;
+        for (int d = 0; d < dim; d++) temp += mean[1 + d] * nrm[d];
+        const double A = 1. - 2. * gamma / (gamma - 1.), B = 2 * temp / (gamma - 1.);
+        double C = -2. * mean[0] * mean[1 + nvel];
+        for (int d = 0; d < nvel; d++) C += mean[1 + d] * mean[1 + d];
+        const double p = (-B - sqrt(B * B - 4. * A * C)) / (2. * A);
+        double up[16];
+        up[0] = mean[0] * mean[0] / (temp - p);
+        up[1 + nvel] = p / (phys.R * up[0]);
+        for (int d = 0; d < nvel; d++) up[1 + d] = d < dim ? (mean[1 + d] - p * nrm[d]) / mean[0] : mean[1 + d] / mean[0];
+        ph->cons(up, targetU);
+      }
+      ph->prim(targetU, Upt);
+      const double speedSound = sqrt(phys.gamma * phys.R * Upt[1 + nvel]);  // DryAir::ComputeSpeedOfSound(Up, true)
+      for (long n = 0; n < N; n++) {  // sigma (:566-607) and addSpongeZoneForcing (:631-700)
+        double distInit = 0., distF = 0., X[3] = {0, 0, 0};
+        for (int d = 0; d < dim; d++) X[d] = nodeXYZ[n * dim + d];
+        for (int d = 0; d < dim; d++) distInit -= nrm[d] * (X[d] - f.sz_point_init[d]);
+        for (int d = 0; d < dim; d++) distF += nrm[d] * (X[d] - f.sz_point0[d]);
+        double sgm = 0., ur[3] = {0, 0, 0};
+        if (f.sz_type == 0) {
+          if (distInit > 0. && distF > 0.) {
+            const double planeDistance = distF + distInit;
+            sgm = distInit / planeDistance / planeDistance;
+          }
+        } else {
+          double R = 0., tmp[3] = {0, 0, 0};
+          for (int d = 0; d < dim; d++) tmp[d] = X[d] - f.sz_point_init[d] + distInit * nrm[d];
+          for (int d = 0; d < dim; d++) R += tmp[d] * tmp[d];
+          R = sqrt(R);
+          if (distInit > 0. && distF > 0. && R - f.sz_r1 > 0.) {
+            const double planeDistance = f.sz_r2 - f.sz_r1;
+            sgm = (R - f.sz_r1) / planeDistance / planeDistance;
+            for (int d = 0; d < dim; d++) ur[d] = tmp[d] / R;
+          }
+        }
+        if (!(sgm > 0.)) continue;
+        sgm *= f.sz_mult;
+        double up[16], Un[16], targetCyl[16];
+        for (int eq = 0; eq < neq; eq++) up[eq] = Up[n + eq * N];
+        ph->cons(up, Un);
+        for (int eq = 0; eq < neq; eq++) targetCyl[eq] = targetU[eq];
+        if (f.sz_type == 1) {  // MM rows (ur, uth, uz); targetCyl(1..3) = MM^-1 targetU(1..3)
+          double uth[3], M[3][3], inv[3][3];
+          uth[0] = nrm[1] * ur[2] - ur[1] * nrm[2];
+          uth[1] = nrm[2] * ur[0] - nrm[0] * ur[2];
+          uth[2] = nrm[0] * ur[1] - ur[0] * nrm[1];
+          for (int d = 0; d < 3; d++) M[0][d] = ur[d], M[1][d] = uth[d], M[2][d] = nrm[d];
+          const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                             M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+          inv[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) / det;
+          inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) / det;
+          inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) / det;
+          inv[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) / det;
+          inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) / det;
+          inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) / det;
+          inv[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) / det;
+          inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) / det;
+          inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) / det;
+          for (int r = 0; r < 3; r++) targetCyl[1 + r] = inv[r][0] * targetU[1] + inv[r][1] * targetU[2] + inv[r][2] * targetU[3];
+        }
+        for (int eq = 0; eq < neq; eq++) y[n + eq * N] -= speedSound * sgm * (Un[eq] - targetCyl[eq]);
+      }
+    }
   }
 };
 
@@ -1044,6 +1196,8 @@ void orc_bc_flux(void *h, const OrcBc *bc, int use_bc_in_grad, const double *nor
   o->use_bc_in_grad = save;
 }
 void orc_set_solution_view(void *h, const double *U) { static_cast<Oracle *>(h)->sol_view = U; }
+void orc_add_forcing(void *h, const OrcForcing *f) { static_cast<Oracle *>(h)->forcings.push_back(*f); }
+void orc_clear_forcings(void *h) { static_cast<Oracle *>(h)->forcings.clear(); }
 void orc_set_rates(void *h, const double *data, int size) { static_cast<Oracle *>(h)->ph->set_rates(data, size); }
 void orc_destroy(void *h) {
   Oracle *o = static_cast<Oracle *>(h);

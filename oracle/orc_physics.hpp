@@ -73,6 +73,17 @@ struct OrcBc {
   int attr, kind, type;
   double data[12];
 };
+// same layout as tpsb_forcing_desc (include/tpsb200.h): kind 0 pressure gradient, 1 heat source, 2 Joule heating, 3 sponge zone
+struct OrcForcing {
+  int kind;
+  double pressure_grad[3];
+  double hs_point1[3], hs_point2[3], hs_radius, hs_value;
+  const double *joule_heating;
+  int sz_type, sz_mixed_out;
+  double sz_normal[3], sz_point0[3], sz_point_init[3];
+  double sz_r1, sz_r2, sz_tol, sz_mult;
+  double sz_target[5];
+};
 }
 
 namespace orc {

@@ -87,6 +87,8 @@ def load(kind="port"):
     lib.orc_set_bcs.argtypes = [C.c_void_p, _ip, C.c_int, C.POINTER(OrcBc), C.c_int]
     lib.orc_bc_flux.argtypes = [C.c_void_p, C.POINTER(OrcBc), C.c_int, _dp, _dp, _dp, _dp]
     lib.orc_set_solution_view.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_add_forcing.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_clear_forcings.argtypes = [C.c_void_p]
     lib.orc_set_rates.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     for nm in ("orc_pt_prim", "orc_pt_cons", "orc_pt_max_char_speed", "orc_pt_conv_flux"):
         getattr(lib, nm).argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -157,6 +159,12 @@ class Oracle:
         self.lib.orc_bc_flux(self.h, C.byref(bc), int(use_bc_in_grad), np.ascontiguousarray(normal, dtype=np.float64),
                              np.ascontiguousarray(state, dtype=np.float64), np.ascontiguousarray(grad, dtype=np.float64), out)
         return out
+
+    def add_forcing(self, desc):
+        """desc: a tps_b200.capi.ForcingDesc (same layout as the oracle's OrcForcing); a Joule-heating field must be a
+        host array kept alive by the caller."""
+        self._forcings = getattr(self, "_forcings", []) + [desc]
+        self.lib.orc_add_forcing(self.h, C.addressof(desc))
 
     def set_solution_view(self, U):
         self._sol = None if U is None else np.ascontiguousarray(U, dtype=np.float64)

@@ -187,6 +187,15 @@ class HaloDesc(C.Structure):
                 ("send_elems", C.POINTER(C.c_int)), ("recv_offset", C.POINTER(C.c_int)), ("nccl_comm", C.c_void_p)]
 
 
+class ForcingDesc(C.Structure):
+    """tpsb_forcing_desc: kind 0 pressure gradient, 1 heat source (cylinder), 2 Joule heating (nodal field), 3 sponge zone."""
+    _fields_ = [("kind", C.c_int), ("pressure_grad", C.c_double * 3), ("hs_point1", C.c_double * 3), ("hs_point2", C.c_double * 3),
+                ("hs_radius", C.c_double), ("hs_value", C.c_double), ("joule_heating", C.c_void_p), ("sz_type", C.c_int),
+                ("sz_mixed_out", C.c_int), ("sz_normal", C.c_double * 3), ("sz_point0", C.c_double * 3),
+                ("sz_point_init", C.c_double * 3), ("sz_r1", C.c_double), ("sz_r2", C.c_double), ("sz_tol", C.c_double),
+                ("sz_mult", C.c_double), ("sz_target", C.c_double * 5)]
+
+
 class PartSizes(C.Structure):
     _fields_ = [("num_elems", C.c_int), ("num_nbr_elems", C.c_int), ("num_faces", C.c_int),
                 ("num_nbr_ranks", C.c_int), ("num_send", C.c_int)]
@@ -198,7 +207,7 @@ EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tp
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
            "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_get_hmin", "tpsb_solve_step", "tpsb_check_state", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy", "tpsb_get_path", "tpsb_mk_partition_metis", "tpsb_mk_partition_rcb",
-           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim"]
+           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim", "tpsb_add_forcing", "tpsb_clear_forcings"]
 
 
 def lib():
@@ -228,6 +237,8 @@ def lib():
     L.tpsb_num_dofs.restype = C.c_int64
     L.tpsb_num_dofs.argtypes = [vp]
     L.tpsb_num_equation.argtypes = [vp]
+    L.tpsb_add_forcing.argtypes = [vp, C.POINTER(ForcingDesc)]
+    L.tpsb_clear_forcings.argtypes = [vp]
     L.tpsb_get_path.argtypes = [vp]
     L.tpsb_rhs_mult.argtypes = [vp, vp, vp]
     L.tpsb_rhs_mult_host.argtypes = [vp, vp, vp]
@@ -614,6 +625,34 @@ class RhsOperator:
         ncomp = 0 if rates is None else rates.numel() // self.N
         self._chk(self.L.tpsb_set_reaction_rate_field(self.ctx, rates.data_ptr() if rates is not None else None, ncomp),
                   "tpsb_set_reaction_rate_field")
+
+    def add_forcing(self, kind, **kw):
+        """Register a forcing term (tpsb_add_forcing): 'pressure_gradient' (g), 'heat_source' (point1, point2, radius, value),
+        'joule_heating' (field: device tensor), 'sponge_zone' (normal, point0, point_init, type, mixed_out, r1, r2, tol, mult,
+        target = (rho, u, v, w, p))."""
+        d = ForcingDesc()
+        d.kind = {"pressure_gradient": 0, "heat_source": 1, "joule_heating": 2, "sponge_zone": 3}[kind]
+
+        def put(dst, src):
+            for i, v in enumerate(src):
+                dst[i] = float(v)
+        if kind == "pressure_gradient":
+            put(d.pressure_grad, kw["g"])
+        elif kind == "heat_source":
+            put(d.hs_point1, kw["point1"]), put(d.hs_point2, kw["point2"])
+            d.hs_radius, d.hs_value = float(kw["radius"]), float(kw["value"])
+        elif kind == "joule_heating":
+            self._jh = kw["field"]
+            d.joule_heating = self._jh.data_ptr()
+        else:
+            put(d.sz_normal, kw["normal"]), put(d.sz_point0, kw["point0"]), put(d.sz_point_init, kw["point_init"])
+            d.sz_type, d.sz_mixed_out = int(kw.get("type", 0)), int(kw.get("mixed_out", False))
+            d.sz_r1, d.sz_r2, d.sz_tol, d.sz_mult = (float(kw.get(k, 0.0)) for k in ("r1", "r2", "tol", "mult"))
+            put(d.sz_target, kw.get("target", (0,) * 5))
+        self._chk(self.L.tpsb_add_forcing(self.ctx, C.byref(d)), "tpsb_add_forcing")
+
+    def clear_forcings(self):
+        self._chk(self.L.tpsb_clear_forcings(self.ctx), "tpsb_clear_forcings")
 
     def mean_time_derivatives(self, y):
         """RHSoperator::getLocalTimeDerivatives: mean |dU/dt| per equation."""

@@ -19,6 +19,7 @@
 #include "rhs_fast.cuh"
 #include "rhs_fused.cuh"
 #include "rhs_generic.cuh"
+#include "rhs_forcing.cuh"
 
 using namespace tpsb;
 
@@ -103,6 +104,10 @@ struct tpsb_ctx {
   int ode_scheme = 0;
   long long ode_launches = 0;
   KernelArgs::RkStage rk = {nullptr, nullptr, nullptr, 0.0, 0.0, 0};  // stage update fused into the residual kernel
+  // forcing terms (tpsb_add_forcing), applied after Me^-1 in registration order
+  std::vector<ForcingDev> forcings;
+  double *d_xiN3 = nullptr;  // [dof][3] reference coordinates of the nodes (3-D dry-air paths; the generic path has its own)
+  bool forcing_needs_grad = false;
   long long launches = 0;
   int tune[3] = {0, 0, 0};
   int num_sms = 148, face_ctas_per_sm = 5;
@@ -1228,9 +1233,11 @@ void tpsb_destroy(tpsb_ctx *c) {
                   c->d_maxBits,  c->d_mcs,       c->d_send_elems,   c->d_k,        c->d_yv,       c->d_z,
                   c->d_hx,       c->d_hy,        c->d_geo,          c->d_tr,       c->d_face_nor, c->d_sendTr,
                   c->d_face_desc, c->d_send_blk, c->d_bdr_el1,      c->d_bdr_lf,   c->d_bdr_bc,   c->d_elem_delta,
-                  c->d_nan_count};
+                  c->d_nan_count, c->d_xiN3};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  for (auto &f : c->forcings)
+    if (f.mix) cudaFree(f.mix);
   for (void *p : c->gen_allocs) cudaFree(p);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
@@ -1687,7 +1694,7 @@ static int run_mult_fused(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   CU(cudaSetDevice(c->device));
   KernelArgs a = make_args(c, d_x, d_y);
   CU(cudaMemsetAsync(c->d_maxBits, 0, sizeof(unsigned long long), c->stream));
-  int rc = run_elem_fused(c, a, FUSED_WRITE);
+  int rc = run_elem_fused(c, a, c->forcing_needs_grad ? (FUSED_WRITE | FUSED_EXPORT) : FUSED_WRITE);
   if (rc) return rc;
   c->fields_x = d_x;
   c->fields_stale = true;
@@ -1836,7 +1843,47 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   return TPSB_OK;
 }
 
+// ForcingTerms::updateTerms of every registered term (src/rhs_operator.cpp:451-461), after Me^-1
+static int apply_forcings(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  tpsb_ctx *c = ctx;
+  if (c->forcings.empty()) return TPSB_OK;
+  ForcingArgs a;
+  memset(&a, 0, sizeof(a));
+  a.NE = c->NE, a.N = c->N, a.dof = c->nd, a.x = d_x, a.y = d_y, a.gradUp = c->d_gradUp;
+  if (c->generic) {
+    a.dim = c->gen.dim, a.nvel = c->gen.nvel, a.neq = c->gen.neq, a.nv = c->gen.nv, a.phys = c->gen.phys;
+    a.vx = c->gen.vx, a.xiN = c->gen.xiN;
+  } else {
+    a.dim = 3, a.nvel = 3, a.neq = NEQ, a.nv = 8, a.vx = c->d_vx, a.xiN = c->d_xiN3;
+    a.phys.dim = 3, a.phys.nvel = 3, a.phys.neq = NEQ, a.phys.fluid = 0, a.phys.dry = c->phys;
+  }
+  a.nf = static_cast<int>(c->forcings.size());
+  for (int i = 0; i < a.nf; i++) a.f[i] = c->forcings[i];
+  const unsigned nb = static_cast<unsigned>((c->N + 127) / 128);
+  for (int i = 0; i < a.nf; i++)
+    if (a.f[i].kind == TPSB_FORCING_SPONGE_ZONE && a.f[i].sz_mixed) {  // SpongeZone::computeMixedOutValues
+      CU(cudaMemsetAsync(a.f[i].mix, 0, sizeof(double) * (a.neq + 1), c->stream));
+      forcing_mixed_out_sum_kernel<<<nb, 128, 0, c->stream>>>(a, i);
+      c->launches++;
+      if (c->comm) NC(ncclAllReduce(a.f[i].mix, a.f[i].mix, a.neq + 1, ncclDouble, ncclSum, c->comm, c->stream));
+      forcing_mixed_out_target_kernel<<<1, 1, 0, c->stream>>>(a, i);
+      c->launches++;
+    }
+  {
+    ProfScope ps(c, K_RESID);
+    forcing_kernel<<<nb, 128, 0, c->stream>>>(a);
+  }
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
+static int run_mult_paths(tpsb_ctx *ctx, const double *d_x, double *d_y);
 static int run_mult(tpsb_ctx *ctx, const double *d_x, double *d_y) {
+  const int rc = run_mult_paths(ctx, d_x, d_y);
+  if (rc || ctx->forcings.empty()) return rc;
+  return apply_forcings(ctx, d_x, d_y);
+}
+static int run_mult_paths(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   tpsb_ctx *c = ctx;
   if (c->generic) return run_mult_generic(ctx, d_x, d_y);
   if (c->fast) return run_mult_fast(ctx, d_x, d_y);
@@ -2010,7 +2057,7 @@ int tpsb_rhs_mult_host(tpsb_ctx *ctx, const double *h_x, double *h_y) {
   int rc = ensure_work(ctx, &ctx->d_hx);
   if (!rc) rc = ensure_work(ctx, &ctx->d_hy);
   if (rc) return rc;
-  if (ctx->pipe_chunks > 0) return run_mult_host_pipelined(ctx, h_x, h_y);
+  if (ctx->pipe_chunks > 0 && ctx->forcings.empty()) return run_mult_host_pipelined(ctx, h_x, h_y);
   const size_t nb = static_cast<size_t>(ctx->N) * ctx->neq * sizeof(double);
   CU(cudaMemcpyAsync(ctx->d_hx, h_x, nb, cudaMemcpyHostToDevice, ctx->stream));
   rc = run_mult(ctx, ctx->d_hx, ctx->d_hy);
@@ -2114,6 +2161,88 @@ int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance) {
   return TPSB_OK;
 }
 
+int tpsb_clear_forcings(tpsb_ctx *ctx) {
+  if (!ctx) return TPSB_EINVAL;
+  for (auto &f : ctx->forcings)
+    if (f.mix) cudaFree(f.mix);
+  ctx->forcings.clear();
+  ctx->forcing_needs_grad = false;
+  ode_graph_invalidate(ctx);
+  return TPSB_OK;
+}
+
+int tpsb_add_forcing(tpsb_ctx *ctx, const tpsb_forcing_desc *d) {
+  if (!ctx || !d) return TPSB_EINVAL;
+  tpsb_ctx *c = ctx;
+  if (c->forcings.size() >= MAX_FORCING) return fail(ctx, TPSB_EINVAL, "at most %d forcing terms", MAX_FORCING);
+  CU(cudaSetDevice(c->device));
+  const int dim = c->generic ? c->gen.dim : 3, nvel = c->generic ? c->gen.nvel : 3, neq = c->neq;
+  const bool mixture = c->generic && c->gen.phys.fluid != 0;
+  ForcingDev f;
+  memset(&f, 0, sizeof(f));
+  f.kind = d->kind;
+  switch (d->kind) {
+    case TPSB_FORCING_PRESSURE_GRADIENT:
+      for (int k = 0; k < 3; k++) f.g[k] = d->pressure_grad[k];
+      if ((c->generic ? c->gen.eq_system : c->phys.eq_system) == 0)
+        return fail(ctx, TPSB_EINVAL, "the pressure-gradient forcing reads gradUp: Navier-Stokes runs only");
+      c->forcing_needs_grad = true;
+      break;
+    case TPSB_FORCING_HEAT_SOURCE: {
+      double len = 0;
+      for (int k = 0; k < dim; k++) len += (d->hs_point2[k] - d->hs_point1[k]) * (d->hs_point2[k] - d->hs_point1[k]);
+      len = std::sqrt(len);
+      if (!(len > 0) || !(d->hs_radius > 0)) return fail(ctx, TPSB_EINVAL, "heat source: degenerate cylinder");
+      for (int k = 0; k < dim; k++) f.p1[k] = d->hs_point1[k], f.axis[k] = (d->hs_point2[k] - d->hs_point1[k]) / len;
+      f.len = len, f.radius = d->hs_radius, f.value = d->hs_value;
+      break;
+    }
+    case TPSB_FORCING_JOULE_HEATING:
+      if (!d->joule_heating) return fail(ctx, TPSB_EINVAL, "Joule heating needs its nodal field");
+      if (nvel != 3) return fail(ctx, TPSB_EINVAL, "JouleHeating asserts nvel == 3 (src/forcing_terms.cpp:444)");
+      f.field = d->joule_heating;
+      break;
+    case TPSB_FORCING_SPONGE_ZONE: {
+      if (mixture) return fail(ctx, TPSB_ENOTIMPL, "sponge zones are built for dry air");
+      double nm = 0;
+      for (int k = 0; k < dim; k++) nm += d->sz_normal[k] * d->sz_normal[k];
+      nm = std::sqrt(nm);
+      if (!(nm > 0)) return fail(ctx, TPSB_EINVAL, "sponge zone: zero normal");
+      for (int k = 0; k < dim; k++) f.n[k] = d->sz_normal[k] / nm, f.p0[k] = d->sz_point0[k], f.pi[k] = d->sz_point_init[k];
+      f.sz_type = d->sz_type, f.sz_mixed = d->sz_mixed_out ? 1 : 0;
+      if (f.sz_type == 1 && dim != 3) return fail(ctx, TPSB_EINVAL, "annular sponge zones are three-dimensional");
+      f.r1 = d->sz_r1, f.r2 = d->sz_r2, f.tol = d->sz_tol, f.mult = d->sz_mult;
+      if (!f.sz_mixed) {  // SpongeZone::SpongeZone, USERDEF (src/forcing_terms.cpp:486-520) with DryAir::modifyEnergyForPressure
+        const PhysParams &ph = c->generic ? c->gen.phys.dry : c->phys;
+        const double rho = d->sz_target[0], p = d->sz_target[4];
+        double ke = 0;
+        f.targetU[0] = rho;
+        for (int k = 0; k < nvel; k++) f.targetU[1 + k] = rho * d->sz_target[1 + k], ke += f.targetU[1 + k] * f.targetU[1 + k];
+        ke *= 0.5 / rho;
+        f.targetU[1 + nvel] = p / ph.gm1 + ke;
+        f.sound = std::sqrt(ph.gamma * p / rho);  // sqrt(gamma R T) of the target
+      } else {
+        CU(cudaMalloc(&f.mix, sizeof(double) * (2 * neq + 2)));
+      }
+      break;
+    }
+    default:
+      return fail(ctx, TPSB_ENOTIMPL, "forcing kind %d not built", d->kind);
+  }
+  if (!c->generic && !c->d_xiN3) {  // reference coordinates of the GL nodes, x fastest
+    std::vector<double> xi(static_cast<size_t>(c->nd) * 3);
+    for (int n = 0; n < c->nd; n++) {
+      xi[3 * n + 0] = c->T.xn[n % c->np];
+      xi[3 * n + 1] = c->T.xn[(n / c->np) % c->np];
+      xi[3 * n + 2] = c->T.xn[n / (c->np * c->np)];
+    }
+    CU(upload(&c->d_xiN3, xi));
+  }
+  c->forcings.push_back(f);
+  ode_graph_invalidate(ctx);
+  return TPSB_OK;
+}
+
 int tpsb_set_reaction_rate_field(tpsb_ctx *ctx, const double *d_rates, int num_components) {
   if (!ctx) return TPSB_EINVAL;
   if (!ctx->generic || !ctx->gen.phys.fluid) return fail(ctx, TPSB_EINVAL, "reaction rate fields belong to a plasma mixture");
@@ -2184,7 +2313,7 @@ static int ode_one_step(tpsb_ctx *ctx, double *x, double dt, int scheme) {
   // is the epilogue of the residual kernel (no k round trip, no axpy sweep: 240 -> 120 B per node and stage less);
   // the generic path runs its forcing-term kernels after the residual, so it keeps the separate sweep.
   static const bool no_fuse = getenv("TPSB_ODE_FUSE") && atoi(getenv("TPSB_ODE_FUSE")) == 0;
-  const bool fuse = !ctx->generic && !no_fuse;
+  const bool fuse = !ctx->generic && !no_fuse && ctx->forcings.empty();  // forcing terms act on k before the update
   auto stage = [&](const double *in, const double *X, double A, double *Y, double B, double *Z, int ACC) -> int {
     if (fuse) {
       ctx->rk = {X, Y, Z, A, B, ACC};
