@@ -245,6 +245,19 @@ int tpsb_set_solution_view(tpsb_ctx *ctx, const double *d_U);
  * each side's own shape functions (src/face_integrator.cpp:304-309, src/BCintegrator.cpp:408-411).  NULL: zero.     */
 int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance);
 
+/* Averaging::addSample -> addSampleInternal (src/averaging.cpp:198-420): running mean and (co)variances of a nodal family.
+ *   d_inst  instantaneous field, DEVICE, num_fields x N doubles byNODES (M2ulPhyS registers Up, src/M2ulPhyS.cpp:634;
+ *           NULL: the context's primitive field of the last tpsb_update_primitives / tpsb_get_fields)
+ *   d_mean  running mean, same shape, updated in place: mean <- (ns_mean mean + inst) / (ns_mean + 1); with
+ *           pressure_slot != 0 component 1 + dim is averaged as the PRESSURE of the instantaneous primitive state
+ *           (the GasMixture overload, :330-420: "the instantaneous field contains temperature, but the averaged quantity is
+ *           pressure")
+ *   d_vari  NULL, or vari_components (vari_components + 1) / 2 fields: variances of fields vari_start .. vari_start +
+ *           vari_components - 1 about the UPDATED mean, then their covariances (i < j), each (ns_vari v + d_i d_j) / (ns_vari + 1)
+ * The caller keeps the sample counters (ns_mean_, ns_vari_ of the reference class) and zeroes mean / vari when they are 0. */
+int tpsb_averaging_add_sample(tpsb_ctx *ctx, const double *d_inst, int num_fields, double *d_mean, double *d_vari, int vari_start,
+                              int vari_components, int ns_mean, int ns_vari, int pressure_slot);
+
 /* ---- forcing terms (ForcingTerms subclasses, src/forcing_terms.hpp:54-330): nodal terms added to dU/dt AFTER Me^-1
  * (src/rhs_operator.cpp:451-461), in the order they are registered here -- the reference registers them in the order
  * pressure gradient, sponge zones, heat sources, (SourceTerm, AxisymmetricSource: built in), Joule heating

@@ -207,7 +207,7 @@ EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tp
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
            "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_get_hmin", "tpsb_solve_step", "tpsb_check_state", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy", "tpsb_get_path", "tpsb_mk_partition_metis", "tpsb_mk_partition_rcb",
-           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim", "tpsb_add_forcing", "tpsb_clear_forcings"]
+           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim", "tpsb_add_forcing", "tpsb_clear_forcings", "tpsb_averaging_add_sample"]
 
 
 def lib():
@@ -239,6 +239,7 @@ def lib():
     L.tpsb_num_equation.argtypes = [vp]
     L.tpsb_add_forcing.argtypes = [vp, C.POINTER(ForcingDesc)]
     L.tpsb_clear_forcings.argtypes = [vp]
+    L.tpsb_averaging_add_sample.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.tpsb_get_path.argtypes = [vp]
     L.tpsb_rhs_mult.argtypes = [vp, vp, vp]
     L.tpsb_rhs_mult_host.argtypes = [vp, vp, vp]
@@ -650,6 +651,14 @@ class RhsOperator:
             d.sz_r1, d.sz_r2, d.sz_tol, d.sz_mult = (float(kw.get(k, 0.0)) for k in ("r1", "r2", "tol", "mult"))
             put(d.sz_target, kw.get("target", (0,) * 5))
         self._chk(self.L.tpsb_add_forcing(self.ctx, C.byref(d)), "tpsb_add_forcing")
+
+    def averaging_add_sample(self, mean, vari, ns_mean, ns_vari, inst=None, vari_start=1, vari_components=None, pressure_slot=True):
+        """Averaging::addSample on device tensors (mean: fields x N; vari: (co)variances or None); inst None = the context's Up."""
+        nf = mean.numel() // self.N
+        vc = vari_components if vari_components is not None else (self.physics_nvel if hasattr(self, "physics_nvel") else 3)
+        self._chk(self.L.tpsb_averaging_add_sample(self.ctx, inst.data_ptr() if inst is not None else None, nf, mean.data_ptr(),
+                                                   vari.data_ptr() if vari is not None else None, vari_start, vc, ns_mean, ns_vari,
+                                                   int(pressure_slot)), "tpsb_averaging_add_sample")
 
     def clear_forcings(self):
         self._chk(self.L.tpsb_clear_forcings(self.ctx), "tpsb_clear_forcings")

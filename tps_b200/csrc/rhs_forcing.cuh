@@ -185,4 +185,35 @@ __global__ void forcing_kernel(ForcingArgs a) {
   }
 }
 
+// Averaging::addSampleInternal (src/averaging.cpp:250-328 plain, :330-420 with a GasMixture): one thread per node
+__global__ void averaging_kernel(long long N, int nf, int dim, const double *inst, double *mean, double *vari, int vstart, int vcomp,
+                                 double ns_mean, double ns_vari, int pressure_slot, GenPhys phys) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double nUp[GEN_MAXEQ + 4], mstate[GEN_MAXEQ + 4];
+  for (int eq = 0; eq < nf; eq++) nUp[eq] = inst[n + eq * N];
+  for (int eq = 0; eq < nf; eq++) {
+    const double N_umean = ns_mean * mean[n + eq * N];
+    double v = nUp[eq];
+    if (pressure_slot && eq == 1 + dim) v = gen_pressure_from_prim(phys, nUp);
+    mstate[eq] = (N_umean + v) / (ns_mean + 1);
+    mean[n + eq * N] = mstate[eq];
+  }
+  if (!vari) return;
+  int vi = 0;
+  for (int i = vstart; i < vstart + vcomp; i++) {
+    const double di = nUp[i] - mstate[i];
+    vari[n + vi * N] = (vari[n + vi * N] * ns_vari + di * di) / (ns_vari + 1);
+    vi++;
+  }
+  for (int i = vstart; i < vstart + vcomp - 1; i++) {
+    const double di = nUp[i] - mstate[i];
+    for (int j = i + 1; j < vstart + vcomp; j++) {
+      const double dj = nUp[j] - mstate[j];
+      vari[n + vi * N] = (vari[n + vi * N] * ns_vari + di * dj) / (ns_vari + 1);
+      vi++;
+    }
+  }
+}
+
 }  // namespace tpsb

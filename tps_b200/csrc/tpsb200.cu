@@ -2161,6 +2161,37 @@ int tpsb_set_distance_field(tpsb_ctx *ctx, const double *d_distance) {
   return TPSB_OK;
 }
 
+int tpsb_averaging_add_sample(tpsb_ctx *ctx, const double *d_inst, int num_fields, double *d_mean, double *d_vari, int vari_start,
+                              int vari_components, int ns_mean, int ns_vari, int pressure_slot) {
+  if (!ctx || !d_mean || ns_mean < 0 || ns_vari < 0) return TPSB_EINVAL;
+  tpsb_ctx *c = ctx;
+  if (num_fields < 1 || num_fields > GEN_MAXEQ + 4) return fail(ctx, TPSB_EINVAL, "1..%d fields per family", GEN_MAXEQ + 4);
+  if (d_vari && (vari_start < 0 || vari_components < 1 || vari_start + vari_components > num_fields))
+    return fail(ctx, TPSB_EINVAL, "variance components out of range");
+  CU(cudaSetDevice(c->device));
+  if (!d_inst) {  // the primitive state, as M2ulPhyS registers it (src/M2ulPhyS.cpp:634)
+    double *up = nullptr;
+    const int rc = tpsb_get_fields(ctx, &up, nullptr);
+    if (rc) return rc;
+    d_inst = up;
+    if (num_fields != c->neq) return fail(ctx, TPSB_EINVAL, "the primitive family has %d fields", c->neq);
+  }
+  GenPhys ph;
+  memset(&ph, 0, sizeof(ph));
+  if (c->generic) {
+    ph = c->gen.phys;
+  } else {
+    ph.dim = 3, ph.nvel = 3, ph.neq = NEQ, ph.fluid = 0, ph.dry = c->phys;
+  }
+  if (pressure_slot && num_fields != c->neq) return fail(ctx, TPSB_EINVAL, "the pressure slot needs the full primitive state");
+  averaging_kernel<<<static_cast<unsigned>((c->N + 127) / 128), 128, 0, c->stream>>>(
+      c->N, num_fields, c->generic ? c->gen.dim : 3, d_inst, d_mean, d_vari, vari_start, vari_components,
+      static_cast<double>(ns_mean), static_cast<double>(ns_vari), pressure_slot, ph);
+  c->launches++;
+  CU(cudaGetLastError());
+  return TPSB_OK;
+}
+
 int tpsb_clear_forcings(tpsb_ctx *ctx) {
   if (!ctx) return TPSB_EINVAL;
   for (auto &f : ctx->forcings)
