@@ -472,6 +472,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// L2 prefetch of a block two faces ahead (no shared-memory buffer needed): the bulk copy issued one face ahead then hits L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -763,6 +767,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) face_flux_mma_kernel(KernelArg
       mbar_expect_tx(nb, 2 * BLKB);
       bulk_g2s(smem_u32(nx), a.tr + static_cast<long long>(fd_nxt.x) * (NTF * NF2), BLKB, nb);
       bulk_g2s(smem_u32(nx + NTF * NF2), a.tr + static_cast<long long>(fd_nxt.y) * (NTF * NF2), BLKB, nb);
+    }
+    if (fi + 2 * stride < face_count && lane == 1) {  // two faces ahead: into L2 only
+      bulk_prefetch_l2(a.tr + static_cast<long long>(fd_n2.x) * (NTF * NF2), BLKB);
+      bulk_prefetch_l2(a.tr + static_cast<long long>(fd_n2.y) * (NTF * NF2), BLKB);
     }
     const double2 nrm01 = __ldg(reinterpret_cast<const double2 *>(a.face_nor) + 2 * fc);
     const double2 nrm23 = __ldg(reinterpret_cast<const double2 *>(a.face_nor) + 2 * fc + 1);
