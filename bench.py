@@ -42,7 +42,7 @@ KERNEL_NAMES = {"fused": {"grad": "elem_fused_kernel", "face_flux": "face_flux_m
                           "elem_resid": "elem_resid_kernel"}}
 # DRAM bytes per DOF (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of each kernel, from the
 # `ncu --set full` captures summarised in profiles/ (TGV 64^3, 16.8 M DG nodes)
-NCU_DRAM_BYTES_PER_DOF = {"fused": {"grad": 229.6, "face_flux": 151.6, "elem_resid": 110.2},
+NCU_DRAM_BYTES_PER_DOF = {"fused": {"grad": 228.9, "face_flux": 151.4, "elem_resid": 110.3},
                           "other": {"prim": 77.1, "grad": 347.5, "face_flux": 151.3, "elem_resid": 211.0}}
 NCU_SOURCE = {"fused": "profiles/r2_ncu_full_summary.txt", "other": "profiles/r1q_ncu_full_summary.txt"}
 PROC_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}

@@ -142,7 +142,7 @@ typedef struct {
    * from the vertices at create.  3-D dry air, Gauss-Legendre path.                                               */
   int sgs_model;
   double sgs_const, sgs_floor;
-  /* Planar viscous sponge (viscosityMultiplierFunction/*, Fluxes::viscSpongePlanar src/fluxes.cpp:664-684): viscosity,
+  /* Planar viscous sponge (viscosityMultiplierFunction/..., Fluxes::viscSpongePlanar src/fluxes.cpp:664-684): viscosity,
    * bulk viscosity and conductivity times 1 + (max(ratio,1) - 1) (tanh(dist/width - 2) + 1)/2, dist = (x - point).n
    * with n normalised as Fluxes' constructor does (src/fluxes.cpp:73-83).                                          */
   int sponge_enabled;

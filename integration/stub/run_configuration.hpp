@@ -1,0 +1,1 @@
+#include "tps_stub_decls.hpp"
