@@ -56,7 +56,7 @@ typedef struct {
 
 /* FE space description (src/M2ulPhyS.cpp:558-579). */
 typedef struct {
-  int order;          /* flow/order                                                   */
+  int order;          /* flow/order, 1..5 (1-3: sum-factorised kernels; 4, 5: generic path) */
   int basis_type;     /* flow/basisType: 0 Gauss-Legendre nodes, 1 Gauss-Lobatto      */
   int int_rule_type;  /* flow/integrationRule: 0 Gauss-Legendre, 1 Gauss-Lobatto      */
   int num_equation;   /* vfes vdim                                                    */

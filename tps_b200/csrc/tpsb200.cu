@@ -788,7 +788,9 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (maps->dim != 2 && maps->dim != 3) return fail(ctx, TPSB_EINVAL, "dim must be 2 (quadrilaterals) or 3 (hexahedra); got %d", maps->dim);
   if (space->basis_type < 0 || space->basis_type > 1 || space->int_rule_type < 0 || space->int_rule_type > 1)
     return fail(ctx, TPSB_EINVAL, "basisType / integrationRule must be 0 (Gauss-Legendre) or 1 (Gauss-Lobatto)");
-  if (space->order < 1 || space->order > 3) return fail(ctx, TPSB_ENOTIMPL, "order must be 1..3");
+  // orders 1-3 have sum-factorised kernels; 4 and 5 run on the generic path (dense reference-element tables of any size:
+  // the largest rule, the 3-D Gauss-Lobatto face rule at p = 5, has 8 points per direction)
+  if (space->order < 1 || space->order > 5) return fail(ctx, TPSB_ENOTIMPL, "order must be 1..5");
   // config.isAxisymmetric(): a 2-D (r, z) mesh carrying three velocity components
   if (space->nvel != maps->dim && !(maps->dim == 2 && space->nvel == 3))
     return fail(ctx, TPSB_EINVAL, "nvel must equal dim (or 3 on a 2-D mesh for axisymmetric runs)");
@@ -829,7 +831,8 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     return fail(ctx, TPSB_ENOTIMPL, "working fluid %d not built", phys->fluid);
   }
   // 3-D Gauss-Legendre dry air runs the specialised kernels; everything else the generic tensor-product path
-  bool want_generic = maps->dim != 3 || space->basis_type != 0 || space->int_rule_type != 0 || phys->fluid != TPSB_DRY_AIR;
+  bool want_generic = maps->dim != 3 || space->basis_type != 0 || space->int_rule_type != 0 || phys->fluid != TPSB_DRY_AIR ||
+                      space->order > 3;
   if (const char *pth = getenv("TPSB_PATH")) want_generic = want_generic || strcmp(pth, "generic") == 0;
   if (phys->use_roe && !(maps->dim == 2 && space->nvel == 2 && phys->fluid == TPSB_DRY_AIR))
     return fail(ctx, TPSB_ENOTIMPL, "useRoe: Eval_Roe of the reference is written for 2-D dry air only (riemann_solver.cpp:117-206)");
@@ -891,7 +894,7 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   c->NF = maps->num_faces;
   c->N = static_cast<long long>(c->NE) * c->nd;
   c->NH = static_cast<long long>(c->NEH) * c->nd;
-  if (!build_ref_tables(c->order, c->T)) {
+  if (!build_ref_tables(std::min(c->order, 3), c->T)) {  // orders 4, 5: generic path only, these tables are not used
     delete c;
     return fail(nullptr, TPSB_EINVAL, "reference tables");
   }
