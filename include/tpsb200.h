@@ -164,6 +164,15 @@ typedef struct {
  *                          VISC_GNRL (4, generic path; data = {hvyThermalCond, elecThermalCond, Th, Te} with
  *                          ThermalCondition 0 ADIAB / 1 ISOTH / 2 SHTH sheath; src/wallBC.cpp:112-147,512-543,
  *                          PerfectMixture::computeSheathBdrFlux src/equation_of_state.cpp:1909-1942)
+ *   non-reflecting / mass-flow conditions (dry air, planar 2-D or 3-D; generic path; the reference refuses them for mixtures):
+ *     inlet  SUB_DENS_VEL_NR (6), SUB_VEL_CONST_ENT (7): data = {rho, u, v, w}            (src/inletBC.cpp:576-727)
+ *     outlet SUB_P_NR (2): data = {p}; SUB_MF_NR (3), SUB_MF_NR_PW (4): data = {mass flow} (src/outletBC.cpp:573-1027)
+ *     with data[8] = flow/refLength (> 0) and data[9..11] = the patch's unit tangent `tangent1` (all zero: derived like the
+ *     reference's constructors do, from the first two quadrature points of the patch's first boundary face in face order).
+ *     These conditions are STATEFUL like the reference's: each keeps a conserved boundary state per face quadrature point
+ *     (`boundaryU`, initialised from the interpolated primitives by the first evaluation and advanced by EVERY evaluation
+ *     with the time step of tpsb_set_time_step / tpsb_ode_step) and the patch mean of the primitives, refreshed at every
+ *     evaluation (InletBC / OutletBC::updateMean, src/rhs_operator.cpp:364) and all-reduced over the ranks.
  * Other types return TPSB_ENOTIMPL at create.  use_bc_in_grad = boundaryConditions/useBCinGrad
  * (src/M2ulPhyS.cpp:3480): the BR1 gradient then uses the wall state at isothermal walls
  * (src/faceGradientIntegration.cpp:96-115) and the wall Riemann state flips (src/wallBC.cpp:476-479).  */
@@ -295,6 +304,14 @@ int tpsb_clear_forcings(tpsb_ctx *ctx);
  * fluxes of the chunk's two-sided and boundary face ranges, 3 residual + copy-out.                                   */
 int tpsb_debug_host_pipe_schedule(const tpsb_mesh_maps *maps, int chunks, int *elem_begin, int *face_begin, int *bdr_begin,
                                   int *ops, int max_ops, int *num_ops);
+
+/* BoundaryCondition::dt (src/BoundaryCondition.hpp: a reference to M2ulPhyS::dt): the time step the non-reflecting inlets /
+ * outlets advance their boundary states with at every evaluation.  tpsb_ode_step / tpsb_solve_step set it themselves. */
+int tpsb_set_time_step(tpsb_ctx *ctx, double dt);
+/* State of the non-reflecting condition on boundary attribute attr (this rank's part): mean_up[num_equation] = meanUp,
+ * boundary_u[min(points, capacity)][num_equation] = boundaryU in face order, *num_points = its boundary quadrature points.
+ * Either output may be NULL.  Synchronises the stream. */
+int tpsb_get_bc_state(tpsb_ctx *ctx, int attr, double *mean_up, double *boundary_u, int capacity, int *num_points);
 
 /* Chemistry::setGridFunctionRates (src/chemistry.cpp:133-140): the externally computed rate coefficients of the
  * GRIDFUNCTION_RXN reactions, d_rates[component][N] in DEVICE memory (byNODES), valid until replaced; NULL: those

@@ -7,6 +7,7 @@
 #ifndef RHS_OPERATOR_B200_HPP_
 #define RHS_OPERATOR_B200_HPP_
 
+#include <cmath>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -20,6 +21,7 @@ class RHSoperatorB200 : public RHSoperator {
   const mfem::ParGridFunction *U_view_ = nullptr;      // the solution grid function the forcing terms read
   const mfem::ParGridFunction *distance_view_ = nullptr;
   mutable bool distance_sent_ = false;
+  const double &dt_;                                  // M2ulPhyS::dt, held by reference like BoundaryCondition::dt
 
   std::vector<double> vx_;                            // [(NE + NEH)][2^dim][dim]
   std::vector<int> el1_, el2_, inf1_, inf2_, attr_;   // MFEM face tables
@@ -77,6 +79,33 @@ class RHSoperatorB200 : public RHSoperator {
     send_el_.assign(J, J + I[nn]);
   }
 
+  // tangent1 of a non-reflecting patch exactly as InletBC / OutletBC's constructors derive it (src/outletBC.cpp:88-176): the
+  // unit vector from the first to the second face quadrature point of the patch's first boundary element
+  static void patch_tangent(mfem::ParMesh *mesh, mfem::ParFiniteElementSpace *vfes, mfem::IntegrationRules *intRules, int attr,
+                            double *t) {
+    t[0] = t[1] = t[2] = 0.;
+    const int dim = mesh->Dimension();
+    for (int bel = 0; bel < mesh->GetNBE(); bel++) {
+      if (mesh->GetBdrAttribute(bel) != attr) continue;
+      mfem::FaceElementTransformations *Tr = mesh->GetBdrFaceTransformations(bel);
+      const int intorder = Tr->Elem1->OrderW() + 2 * vfes->GetFE(Tr->Elem1No)->GetOrder();
+      const mfem::IntegrationRule &ir = intRules->Get(Tr->GetGeometryType(), intorder);
+      double x[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      for (int i = 0; i < 2; i++) {
+        mfem::Vector xi(x[i], 3);
+        Tr->Transform(ir.IntPoint(i), xi);
+      }
+      double m = 0.;
+      for (int d = 0; d < dim; d++) m += (x[1][d] - x[0][d]) * (x[1][d] - x[0][d]);
+      for (int d = 0; d < dim; d++) t[d] = (x[1][d] - x[0][d]) / std::sqrt(m);
+      return;
+    }
+  }
+  static bool is_nr(int kind, int type) {
+    return (kind == TPSB_BC_INLET && (type == SUB_DENS_VEL_NR || type == SUB_VEL_CONST_ENT)) ||
+           (kind == TPSB_BC_OUTLET && (type == SUB_P_NR || type == SUB_MF_NR || type == SUB_MF_NR_PW));
+  }
+
   // (d) BCintegrator's attribute maps (src/BCintegrator.cpp:64-125): inlets, outlets, walls
   void fill_bcs(RunConfiguration &config, int num_species_active) {
     const auto *inl = config.GetInletPatchType();
@@ -108,6 +137,15 @@ class RHSoperatorB200 : public RHSoperator {
       bc_.push_back(b);
     }
     (void)num_species_active;
+  }
+  // non-reflecting / mass-flow conditions: flow/refLength and the patch tangent ride in data[8..11]
+  void fill_nr_data(RunConfiguration &config, mfem::ParMesh *mesh, mfem::ParFiniteElementSpace *vfes,
+                    mfem::IntegrationRules *intRules) {
+    for (tpsb_bc_desc &b : bc_)
+      if (is_nr(b.kind, b.type)) {
+        b.data[8] = config.GetReferenceLength();
+        patch_tangent(mesh, vfes, intRules, b.attr, &b.data[9]);
+      }
   }
 
   // (e) plasma models of a USER_DEFINED working fluid: PerfectMixtureInput, constantTransportData / GasTransportInput,
@@ -213,10 +251,11 @@ class RHSoperatorB200 : public RHSoperator {
   // class keeps owning what the rest of TPS reads from it.  nccl_comm: created once per job with
   // tpsb_comm_get_unique_id (rank 0) + MPI_Bcast of the 128 bytes + tpsb_comm_init_rank; NULL in a serial run.
   template <class... A>
-  RHSoperatorB200(mfem::ParMesh *mesh, mfem::ParFiniteElementSpace *vfes, RunConfiguration &config,
-                  const mfem::ParGridFunction *U, const mfem::ParGridFunction *distance,
-                  const mfem::ParGridFunction *joule_heating, void *nccl_comm, void *cuda_stream, A &&...base_args)
-      : RHSoperator(std::forward<A>(base_args)...), U_view_(U), distance_view_(distance) {
+  RHSoperatorB200(mfem::ParMesh *mesh, mfem::ParFiniteElementSpace *vfes, mfem::IntegrationRules *intRules,
+                  RunConfiguration &config, const double &dt, const mfem::ParGridFunction *U,
+                  const mfem::ParGridFunction *distance, const mfem::ParGridFunction *joule_heating, void *nccl_comm,
+                  void *cuda_stream, A &&...base_args)
+      : RHSoperator(std::forward<A>(base_args)...), U_view_(U), distance_view_(distance), dt_(dt) {
     const int dim = mesh->Dimension(), NE = mesh->GetNE(), NEH = mesh->GetNFaceNeighborElements();
     fill_vertices(mesh);
     fill_faces(mesh);
@@ -249,6 +288,7 @@ class RHSoperatorB200 : public RHSoperator {
     }
 
     fill_bcs(config, config.GetNumSpecies());
+    fill_nr_data(config, mesh, vfes, intRules);
     tpsb_bc_set bcs{int(bc_.size()), bc_.data(), config.useBCinGrad};
     tpsb_halo_desc halo{};
     if (NEH > 0) {
@@ -276,6 +316,7 @@ class RHSoperatorB200 : public RHSoperator {
       if (tpsb_set_distance_field(ctx_, distance_view_->Read())) fail("distance field", ctx_);
       distance_sent_ = true;
     }
+    tpsb_set_time_step(ctx_, dt_);  // the non-reflecting conditions advance their boundary states with it
     if (tpsb_rhs_mult(ctx_, x.Read(), y.Write())) fail("tpsb_rhs_mult", ctx_);
   }
 

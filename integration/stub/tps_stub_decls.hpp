@@ -27,6 +27,7 @@ class Array {
 class Vector {
  public:
   Vector();
+  Vector(double *data, int size);
   int Size() const;
   double &operator[](int i);
   const double &operator[](int i) const;
@@ -49,10 +50,31 @@ class Table {
 class ElementTransformation {
  public:
   const DenseMatrix &GetPointMat() const;
+  int OrderW() const;
+};
+class IntegrationPoint {
+ public:
+  double x, y, z, weight;
+};
+class IntegrationRule {
+ public:
+  int GetNPoints() const;
+  const IntegrationPoint &IntPoint(int i) const;
+};
+class IntegrationRules {
+ public:
+  const IntegrationRule &Get(int GeomType, int Order);
+};
+class FiniteElement {
+ public:
+  int GetOrder() const;
 };
 class FaceElementTransformations {
  public:
   int Elem1No, Elem2No;
+  ElementTransformation *Elem1;
+  int GetGeometryType() const;
+  void Transform(const IntegrationPoint &ip, Vector &x);
 };
 class ParMesh {
  public:
@@ -68,6 +90,7 @@ class ParMesh {
   ElementTransformation *GetElementTransformation(int i);
   ElementTransformation *GetFaceNbrElementTransformation(int i);
   FaceElementTransformations *GetSharedFaceTransformations(int sf, bool fill2 = true);
+  FaceElementTransformations *GetBdrFaceTransformations(int BdrElemNo);
   void GetFaceElements(int Face, int *Elem1, int *Elem2) const;
   void GetFaceInfos(int Face, int *Inf1, int *Inf2) const;
   int GetBdrElementFaceIndex(int be_idx) const;
@@ -78,6 +101,7 @@ class ParMesh {
 class ParFiniteElementSpace {
  public:
   int GetVDim() const;
+  const FiniteElement *GetFE(int i) const;
 };
 class ParGridFunction : public Vector {};
 class Device {
@@ -107,8 +131,8 @@ enum FluxTrns { VISCOSITY, BULK_VISCOSITY, HEAVY_THERMAL_CONDUCTIVITY, ELECTRON_
 enum SpeciesTrns { MF_FREQUENCY, NUM_SPECIES_COEFFS };
 enum GasColl { CLMB_ATT, CLMB_REP, AR_AR1P, AR_E, AR_AR, NONE_GASCOLL };
 enum GasType { ARGON_GAS, NITROGEN_GAS };
-enum InletType { SUB_DENS_VEL, SUB_DENS_VEL_NR, SUB_VEL_CONST_ENT, SUB_MASSFLOW };
-enum OutletType { SUB_P, SUB_P_NR, SUB_MF_NR, SUB_MF_NR_PW };
+enum InletType { UNI_DENS_VEL, INTERPOLATE, SUB_DENS_VEL, SUB_DENS_VEL_FACE_X, SUB_DENS_VEL_FACE_Y, SUB_DENS_VEL_FACE_Z, SUB_DENS_VEL_NR, SUB_VEL_CONST_ENT };
+enum OutletType { SUB_P, RESIST_IN, SUB_P_NR, SUB_MF_NR, SUB_MF_NR_PW };
 enum WallType { INV, SLIP, VISC_ADIAB, VISC_ISOTH, VISC_GNRL };
 enum ThermalCondition { ADIAB, ISOTH, SHTH, NONE_THMCND };
 enum SpongeZoneSolution { USERDEF, MIXEDOUT, NONE_SZSOL };
@@ -220,6 +244,7 @@ class RunConfiguration {
   double GetViscMult();
   double GetBulkViscMult();
   double GetSgsFloor();
+  double GetReferenceLength();
   double GetSgsConstant();
   Equations GetEquationSystem() const;
   bool isAxisymmetric() const;

@@ -392,6 +392,227 @@ struct Oracle {
         el_bfaces[f_el1[f]].push_back(f);
         shape_table(f_inf1[f]);
       }
+    setup_nr();
+  }
+  // ---- non-reflecting / mass-flow inlets and outlets (dry air): the stateful part of InletBC / OutletBC ----
+  // Per patch: boundaryU (a conserved state per boundary quadrature point, advanced by every flux evaluation with the
+  // current time step), meanUp (mean of the interpolated primitives over the patch's points, refreshed by updateMean at
+  // every Mult: src/rhs_operator.cpp:364), tangent1 (first to second quadrature point of the patch's first face, or given),
+  // the patch area (BoundaryCondition::aggregateArea, src/BoundaryCondition.cpp:59-81).
+  // OrcBc::data: inlet {rho, u, v, w}, outlet {p | mass flow}; data[8] = refLength, data[9..11] = tangent1 (all zero: derive).
+  struct NrState {
+    std::vector<int> faces;
+    std::map<int, int> face_off;  // face -> first point
+    std::vector<double> boundaryU;
+    double meanUp[16];
+    double tangent1[3];
+    double area = 0.0;
+    bool init = false;
+  };
+  mutable std::map<int, NrState> nr;  // by index into bcs
+  double bc_dt = 0.0;                 // BoundaryCondition::dt (a reference to M2ulPhyS::dt)
+  static bool is_nr(const OrcBc &b) {
+    return (b.kind == 0 && (b.type == 6 || b.type == 7)) || (b.kind == 1 && b.type >= 2 && b.type <= 4);
+  }
+  void setup_nr() {
+    nr.clear();
+    for (size_t i = 0; i < bcs.size(); i++) {
+      if (!is_nr(bcs[i])) continue;
+      NrState st;
+      int off = 0;
+      for (int f = 0; f < NF; f++)
+        if (f_el2[f] < 0 && f_attr[f] == bcs[i].attr) {
+          st.faces.push_back(f);
+          st.face_off[f] = off;
+          off += nqf;
+        }
+      st.boundaryU.assign(static_cast<size_t>(off) * neq, 0.0);
+      for (int d = 0; d < 3; d++) st.tangent1[d] = bcs[i].data[9 + d];
+      const double tm = st.tangent1[0] * st.tangent1[0] + st.tangent1[1] * st.tangent1[1] + st.tangent1[2] * st.tangent1[2];
+      if (tm == 0.0 && !st.faces.empty()) {  // OutletBC constructor (src/outletBC.cpp:161-176): coords of points 0 and 1
+        double n0[3], x0[3] = {0, 0, 0}, x1[3] = {0, 0, 0};
+        face_geom(st.faces[0], 0, n0, x0);
+        face_geom(st.faces[0], 1, n0, x1);
+        double m = 0;
+        for (int d = 0; d < dim; d++) m += (x1[d] - x0[d]) * (x1[d] - x0[d]);
+        for (int d = 0; d < dim; d++) st.tangent1[d] = (x1[d] - x0[d]) * (1. / sqrt(m));
+      }
+      for (int f : st.faces)
+        for (int q = 0; q < nqf; q++) {
+          double nor[3], xyz[3], m = 0;
+          face_geom(f, q, nor, xyz);
+          for (int d = 0; d < dim; d++) m += nor[d] * nor[d];
+          st.area += sqrt(m) * face_weight(q);
+        }
+      nr[static_cast<int>(i)] = st;
+    }
+  }
+  // InletBC::updateMean / OutletBC::updateMean, CPU branch (src/inletBC.cpp:482-564, src/outletBC.cpp:470-561)
+  void update_bc_mean() {
+    for (auto &kv : nr) {
+      NrState &st = kv.second;
+      double sum[16] = {0};
+      int nb = 0;
+      for (int f : st.faces) {
+        const int e1 = f_el1[f];
+        const std::vector<double> &sh1 = shapeTab.at(f_inf1[f]);
+        for (int q = 0; q < nqf; q++) {
+          const double *s1 = &sh1[static_cast<size_t>(q) * dof];
+          double iUp[16], iState[16];
+          for (int eq = 0; eq < neq; eq++) {
+            double a = 0.;
+            for (int k = 0; k < dof; k++) a += s1[k] * Up[static_cast<size_t>(e1) * dof + k + eq * N];
+            sum[eq] += a;
+            iUp[eq] = a;
+          }
+          if (!st.init) {
+            ph->cons(iUp, iState);
+            for (int eq = 0; eq < neq; eq++) st.boundaryU[static_cast<size_t>(nb) * neq + eq] = iState[eq];
+          }
+          nb++;
+        }
+      }
+      for (int eq = 0; eq < neq; eq++) st.meanUp[eq] = sum[eq] * (1. / static_cast<double>(nb));
+      st.init = true;
+    }
+  }
+  // InletBC::subsonicNonReflectingDensityVelocity (src/inletBC.cpp:576-727; SUB_DENS_VEL_NR, SUB_VEL_CONST_ENT) and
+  // OutletBC::subsonicNonReflectingPressure / subsonicNonRefMassFlow / subsonicNonRefPWMassFlow
+  // (src/outletBC.cpp:573-729, 739-892, 894-1027): characteristic update of the point's boundary state, then the
+  // Lax-Friedrichs flux against the state it had BEFORE the update.
+  void nr_flux(const OrcBc &b, NrState &st, int pt, const double *normal, const double *stateIn, const double *gradState,
+               double *bdrFlux) const {
+    const double gamma = phys.gamma, Rg = phys.R;
+    const bool inlet = b.kind == 0;
+    double unitNorm[3] = {0, 0, 0}, tangent2[3] = {0, 0, 0};
+    const double *tangent1 = st.tangent1, *meanUp = st.meanUp;
+    {
+      double mod = 0.;
+      for (int d = 0; d < dim; d++) mod += normal[d] * normal[d];
+      for (int d = 0; d < dim; d++) unitNorm[d] = normal[d] * ((inlet ? -1. : 1.) / sqrt(mod));  // inlet: into the domain
+    }
+    double meanVel[3] = {0, 0, 0};
+    for (int d = 0; d < dim; d++) {
+      meanVel[0] += unitNorm[d] * meanUp[d + 1];
+      meanVel[1] += tangent1[d] * meanUp[d + 1];
+    }
+    if (dim == 3) {
+      tangent2[0] = unitNorm[1] * tangent1[2] - unitNorm[2] * tangent1[1];
+      tangent2[1] = unitNorm[2] * tangent1[0] - unitNorm[0] * tangent1[2];
+      tangent2[2] = unitNorm[0] * tangent1[1] - unitNorm[1] * tangent1[0];
+      for (int d = 0; d < dim; d++) meanVel[2] += tangent2[d] * meanUp[d + 1];
+    }
+    double normGrad[16];
+    for (int eq = 0; eq < neq; eq++) {
+      normGrad[eq] = 0.;
+      for (int d = 0; d < dim; d++) normGrad[eq] += unitNorm[d] * gradState[eq + d * neq];
+    }
+    // DryAir::ComputePressureDerivative(normGrad, stateIn, false) (src/equation_of_state.cpp:350-359)
+    const double T = ph->pressure(stateIn) / (Rg * stateIn[0]);
+    const double dpdn = Rg * (T * normGrad[0] + stateIn[0] * normGrad[1 + nvel]);
+    const double speedSound = sqrt(gamma * Rg * meanUp[1 + nvel]);
+    double meanK = 0.;
+    for (int d = 0; d < nvel; d++) meanK += meanUp[1 + d] * meanUp[1 + d];
+    meanK *= 0.5;
+    const double refLength = b.data[8];
+    const double sigma = speedSound / refLength;
+    double L1, L2, L3, L4 = 0., L5;
+    if (inlet) {
+      double meanDV[3];
+      for (int d = 0; d < nvel; d++) meanDV[d] = meanUp[1 + d] - b.data[1 + d];
+      L1 = 0.;
+      for (int d = 0; d < dim; d++) L1 += unitNorm[d] * normGrad[1 + d];
+      L1 = dpdn - meanUp[0] * speedSound * L1;
+      L1 *= meanVel[0] - speedSound;
+      L5 = 0.;
+      for (int d = 0; d < dim; d++) L5 += meanDV[d] * unitNorm[d];
+      L5 *= sigma * 2. * meanUp[0] * speedSound;
+      L3 = 0.;
+      for (int d = 0; d < dim; d++) L3 += meanDV[d] * tangent1[d];
+      L3 *= sigma;
+      if (dim == 3) {
+        for (int d = 0; d < dim; d++) L4 += meanDV[d] * tangent2[d];
+        L4 *= sigma;
+      }
+      L2 = sigma * speedSound * speedSound * (meanUp[0] - b.data[0]) - 0.5 * L5;
+      if (b.type == 7) L2 = 0.;  // SUB_VEL_CONST_ENT
+    } else {
+      L2 = speedSound * speedSound * normGrad[0] - dpdn;
+      L2 *= meanVel[0];
+      L3 = 0.;
+      for (int d = 0; d < dim; d++) L3 += tangent1[d] * normGrad[1 + d];
+      L3 *= meanVel[0];
+      if (dim == 3) {
+        for (int d = 0; d < dim; d++) L4 += tangent2[d] * normGrad[1 + d];
+        L4 *= meanVel[0];
+      }
+      L5 = 0.;
+      for (int d = 0; d < dim; d++) L5 += unitNorm[d] * normGrad[1 + d];
+      L5 = dpdn + meanUp[0] * speedSound * L5;
+      L5 *= meanVel[0] + speedSound;
+      if (b.type == 2) {  // SUB_P_NR
+        const double meanP = Rg * meanUp[0] * meanUp[1 + nvel];
+        L1 = sigma * (meanP - b.data[0]);
+      } else {
+        double vn = meanVel[0];  // SUB_MF_NR: the patch mean; SUB_MF_NR_PW: the point's own normal velocity
+        if (b.type == 4) {
+          vn = 0.;
+          for (int d = 0; d < dim; d++) vn += stateIn[1 + d] * unitNorm[d];
+          vn /= stateIn[0];
+        }
+        L1 = -sigma * (vn - b.data[0] / meanUp[0] / st.area);
+        L1 *= meanUp[0] * speedSound;
+      }
+    }
+    const double d1 = (L2 + 0.5 * (L5 + L1)) / speedSound / speedSound;
+    const double d2 = 0.5 * (L5 - L1) / meanUp[0] / speedSound;
+    const double d3 = L3, d4 = L4, d5 = 0.5 * (L5 + L1);
+    double dF[16];
+    for (int eq = 0; eq < neq; eq++) dF[eq] = 0.;
+    dF[0] = d1;
+    dF[1] = meanVel[0] * d1 + meanUp[0] * d2;
+    dF[2] = meanVel[1] * d1 + meanUp[0] * d3;
+    if (dim == 3) dF[3] = meanVel[2] * d1 + meanUp[0] * d4;
+    dF[1 + dim] = meanUp[0] * meanVel[0] * d2;
+    dF[1 + dim] += meanUp[0] * meanVel[1] * d3;
+    if (dim == 3) dF[1 + dim] += meanUp[0] * meanVel[2] * d4;
+    dF[1 + dim] += meanK * d1 + d5 / (gamma - 1.);
+    double state2[16], stateN[16], newU[16];
+    double *bU = &st.boundaryU[static_cast<size_t>(pt) * neq];
+    for (int eq = 0; eq < neq; eq++) state2[eq] = bU[eq], stateN[eq] = bU[eq];
+    for (int d = 0; d < dim; d++) stateN[1 + d] = 0.;
+    for (int d = 0; d < dim; d++) {
+      stateN[1] += state2[1 + d] * unitNorm[d];
+      stateN[2] += state2[1 + d] * tangent1[d];
+      if (dim == 3) stateN[3] += state2[1 + d] * tangent2[d];
+    }
+    for (int i = 0; i < neq; i++) newU[i] = stateN[i] - bc_dt * dF[i];
+    {  // back to Cartesian momentum: inverse of the matrix with rows unitNorm, tangent1, tangent2
+      double M[9], invM[9], momX[3] = {0, 0, 0};
+      for (int d = 0; d < dim; d++) {
+        M[0 + d * dim] = unitNorm[d];
+        M[1 + d * dim] = tangent1[d];
+        if (dim == 3) M[2 + d * dim] = tangent2[d];
+      }
+      small_inverse(dim, M, invM);
+      for (int i = 0; i < dim; i++)
+        for (int j = 0; j < dim; j++) momX[i] += invM[i + j * dim] * newU[1 + j];
+      for (int d = 0; d < dim; d++) newU[1 + d] = momX[d];
+    }
+    for (int eq = 0; eq < neq; eq++) bU[eq] = newU[eq];
+    ph->riemann(stateIn, state2, normal, bdrFlux, true);
+  }
+  // column-major inverse of a 2 x 2 / 3 x 3 matrix (mfem::CalcInverse: adjugate / determinant)
+  static void small_inverse(int n, const double *a, double *inv) {
+    if (n == 2) {
+      const double t = 1.0 / (a[0] * a[3] - a[1] * a[2]);
+      inv[0] = a[3] * t, inv[1] = -a[1] * t, inv[2] = -a[2] * t, inv[3] = a[0] * t;
+      return;
+    }
+    const double t = 1.0 / (a[0] * (a[4] * a[8] - a[5] * a[7]) - a[3] * (a[1] * a[8] - a[2] * a[7]) + a[6] * (a[1] * a[5] - a[2] * a[4]));
+    inv[0] = (a[4] * a[8] - a[5] * a[7]) * t, inv[3] = (a[5] * a[6] - a[3] * a[8]) * t, inv[6] = (a[3] * a[7] - a[4] * a[6]) * t;
+    inv[1] = (a[2] * a[7] - a[1] * a[8]) * t, inv[4] = (a[0] * a[8] - a[2] * a[6]) * t, inv[7] = (a[1] * a[6] - a[0] * a[7]) * t;
+    inv[2] = (a[1] * a[5] - a[2] * a[4]) * t, inv[5] = (a[2] * a[3] - a[0] * a[5]) * t, inv[8] = (a[0] * a[4] - a[1] * a[3]) * t;
   }
   // BoundaryCondition::computeBdrPrimitiveStateForGradient (src/BoundaryCondition.cpp:55: copy) and the
   // WallBC override (src/wallBC.cpp:241-266: only VISC_ISOTH changes anything)
@@ -754,6 +975,7 @@ struct Oracle {
     max_char_speed = 0.;
     update_primitives(x);
     compute_gradients();
+    update_bc_mean();  // bcIntegrator->updateBCMean(Up) (src/rhs_operator.cpp:364)
     const int nact = ph->num_active_species();
     // ---- A->Mult: FaceIntegrator::NonLinearFaceIntegration (src/face_integrator.cpp:194-352)
     std::vector<double> fz(static_cast<size_t>(NF) * 2 * dof * neq, 0.0);
@@ -851,7 +1073,12 @@ struct Oracle {
           double d1 = 0.0;  // src/BCintegrator.cpp:416-424
           if (!distance.empty())
             for (int k = 0; k < dof; k++) d1 += distance[static_cast<size_t>(e1) * dof + k] * s1[k];
-          bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN, d1);
+          if (is_nr(*bc)) {
+            NrState &st = nr.at(static_cast<int>(bc - bcs.data()));
+            nr_flux(*bc, st, st.face_off.at(f) + q, nor, u1, g1, fluxN);
+          } else {
+            bc_flux(*bc, nor, u1, g1, xyz, delta, fluxN, d1);
+          }
           const double w = face_weight(q);
           for (int eq = 0; eq < neq; eq++) fluxN[eq] *= w;
           if (axisym)  // src/BCintegrator.cpp:427-429
@@ -1188,6 +1415,20 @@ void *orc_create(int order, int NE, const double *vx, int NF, const int *el1, co
 void orc_set_bcs(void *h, const int *face_attr, int nbc, const OrcBc *bcs, int use_bc_in_grad) {
   static_cast<Oracle *>(h)->set_bcs(face_attr, nbc, bcs, use_bc_in_grad);
 }
+// BoundaryCondition::dt (the time step the non-reflecting conditions advance their boundary state with)
+void orc_set_bc_time_step(void *h, double dt) { static_cast<Oracle *>(h)->bc_dt = dt; }
+// state of the non-reflecting condition on attribute attr: meanUp[neq], then boundaryU[points][neq]; returns the number of points
+int orc_get_bc_state(void *h, int attr, double *mean_up, double *boundary_u, int capacity) {
+  Oracle *o = static_cast<Oracle *>(h);
+  for (auto &kv : o->nr)
+    if (o->bcs[kv.first].attr == attr) {
+      const int npts = static_cast<int>(kv.second.boundaryU.size()) / o->neq;
+      for (int eq = 0; eq < o->neq; eq++) mean_up[eq] = kv.second.meanUp[eq];
+      for (int i = 0; i < std::min(npts, capacity) * o->neq; i++) boundary_u[i] = kv.second.boundaryU[i];
+      return npts;
+    }
+  return -1;
+}
 // one boundary flux evaluation (test probe): BCintegrator::computeBdrFlux
 void orc_bc_flux(void *h, const OrcBc *bc, int use_bc_in_grad, const double *normal, const double *stateIn,
                  const double *gradState, double *flux) {
@@ -1234,6 +1475,7 @@ void orc_rk4_steps(void *h, double *U, double dt, int nsteps) {
   Oracle *o = static_cast<Oracle *>(h);
   const size_t n = static_cast<size_t>(o->N) * o->neq;
   std::vector<double> k(n), yv(n), z(n);
+  if (!o->nr.empty()) o->bc_dt = dt;  // M2ulPhyS::dt, which the boundary conditions hold by reference
   for (int s = 0; s < nsteps; s++) {
     o->mult(U, k.data());
     for (size_t i = 0; i < n; i++) {

@@ -32,6 +32,9 @@ def bcs(kind, nvel=2, species=()):
         "adiabatic": [(1, 2, 2, ()), (2, 2, 2, ()), (3, 2, 0, ()), (4, 2, 3, (350.0,))],
         "inviscid": [(1, 2, 0, ()), (2, 2, 0, ()), (3, 2, 0, ()), (4, 2, 0, ())],
         "slip": [(1, 2, 1, ()), (2, 2, 1, ()), (3, 2, 1, ()), (4, 2, 0, ())],
+        # non-reflecting inlet (SUB_DENS_VEL_NR) and mass-flow outlet (SUB_MF_NR): data[8] = refLength, data[9..11] = tangent1
+        "nr": [(1, 2, 0, ()), (2, 2, 3, (298.15,)), (3, 0, 6, (1.25, 3.0, 12.0, 0.0, 0, 0, 0, 0, 0.7, 1.0, 0.0, 0.0)),
+               (4, 1, 3, (18.0, 0, 0, 0, 0, 0, 0, 0, 0.7, 1.0, 0.0, 0.0))],
     }
     return sets[kind]
 

@@ -43,6 +43,8 @@ def main():
         cfg = (ac.box(n=(9, 7), warp=0.05), 2, 1, 1, 2, "c4", True, None, None)
     elif case == "quad-gl3":    # Gauss-Legendre p = 3 quadrilaterals, all-wall box
         cfg = (ac.box(n=(8, 6), warp=0.04), 3, 0, 0, 2, "adiabatic", False, None, None)
+    elif case == "quad-nr":     # non-reflecting inlet + mass-flow outlet: patch means and areas all-reduced over the ranks
+        cfg = (ac.box(n=(9, 7), warp=0.05), 3, 0, 0, 2, "nr", True, None, None)
     elif case == "axisym-argon6":  # config C4 type: axisymmetric, six species, two temperatures, mixing length
         cfg = (ac.box(n=(7, 6), warp=0.03), 2, 1, 1, 3, "c4", True, ac.argon6_dict(), (0.05, 0.9, 0.3))
     else:

@@ -86,6 +86,9 @@ def load(kind="port"):
     lib.orc_destroy.argtypes = [C.c_void_p]
     lib.orc_set_bcs.argtypes = [C.c_void_p, _ip, C.c_int, C.POINTER(OrcBc), C.c_int]
     lib.orc_bc_flux.argtypes = [C.c_void_p, C.POINTER(OrcBc), C.c_int, _dp, _dp, _dp, _dp]
+    lib.orc_set_bc_time_step.argtypes = [C.c_void_p, C.c_double]
+    lib.orc_get_bc_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int]
+    lib.orc_get_bc_state.restype = C.c_int
     lib.orc_set_solution_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.orc_add_forcing.argtypes = [C.c_void_p, C.c_void_p]
     lib.orc_clear_forcings.argtypes = [C.c_void_p]
@@ -153,6 +156,17 @@ class Oracle:
         arr = (OrcBc * len(bcs))(*bcs)
         self._bcs = arr
         self.lib.orc_set_bcs(self.h, np.ascontiguousarray(face_attr, np.int32), len(bcs), arr, int(use_bc_in_grad))
+
+    def set_bc_time_step(self, dt):
+        self.lib.orc_set_bc_time_step(self.h, float(dt))
+
+    def bc_state(self, attr):
+        mean = np.zeros(self.neq)
+        n = self.lib.orc_get_bc_state(self.h, int(attr), mean, np.zeros(1), 0)
+        assert n >= 0, "no non-reflecting condition on this attribute"
+        bu = np.zeros((max(n, 1), self.neq))
+        self.lib.orc_get_bc_state(self.h, int(attr), mean, bu, n)
+        return mean, bu[:n]
 
     def bc_flux(self, bc, normal, state, grad, use_bc_in_grad=False):
         out = np.zeros(self.neq)

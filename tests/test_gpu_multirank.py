@@ -23,7 +23,7 @@ def test_partitioned_operator_matches_single_gpu(lib_built, world, case):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("case,method", [("quad-gll", "metis"), ("quad-gl3", "rcb"), ("axisym-argon6", "metis")])
+@pytest.mark.parametrize("case,method", [("quad-gll", "metis"), ("quad-gl3", "rcb"), ("axisym-argon6", "metis"), ("quad-nr", "metis")])
 @pytest.mark.parametrize("world", [2, 4])
 def test_partitioned_generic_path_matches_single_gpu(lib_built, world, case, method):
     """The generic tensor-product path (2-D quadrilaterals / mixtures / axisymmetric) on irregular partitions."""

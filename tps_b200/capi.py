@@ -207,7 +207,8 @@ EXPORTS = ["tpsb_version", "tpsb_last_error", "tpsb_create", "tpsb_destroy", "tp
            "tpsb_get_fields", "tpsb_set_solution_view", "tpsb_set_reaction_rate_field", "tpsb_get_mean_time_derivatives", "tpsb_get_max_char_speed", "tpsb_ode_step", "tpsb_get_element_to_faces",
            "tpsb_launch_count", "tpsb_debug_buffer", "tpsb_debug_point_eval", "tpsb_set_distance_field", "tpsb_get_hmin", "tpsb_solve_step", "tpsb_check_state", "tpsb_debug_host_pipe_schedule", "tpsb_set_profiling", "tpsb_get_kernel_times", "tpsb_get_ref_tables", "tpsb_mk_cartesian_hex", "tpsb_mk_build_faces", "tpsb_mk_cartesian_quad", "tpsb_mk_build_faces2d", "tpsb_mk_partition", "tpsb_comm_get_unique_id",
            "tpsb_comm_init_rank", "tpsb_comm_destroy", "tpsb_get_path", "tpsb_mk_partition_metis", "tpsb_mk_partition_rcb",
-           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim", "tpsb_add_forcing", "tpsb_clear_forcings", "tpsb_averaging_add_sample"]
+           "tpsb_mk_partition_general", "tpsb_mk_partition_rcb_dim", "tpsb_mk_partition_general_dim", "tpsb_add_forcing", "tpsb_clear_forcings", "tpsb_averaging_add_sample",
+           "tpsb_set_time_step", "tpsb_get_bc_state"]
 
 
 def lib():
@@ -249,6 +250,8 @@ def lib():
     L.tpsb_get_max_char_speed.argtypes = [vp, dp]
     L.tpsb_set_solution_view.argtypes = [vp, vp]
     L.tpsb_set_distance_field.argtypes = [vp, vp]
+    L.tpsb_set_time_step.argtypes = [vp, C.c_double]
+    L.tpsb_get_bc_state.argtypes = [vp, C.c_int, dp, dp, C.c_int, ip]
     L.tpsb_get_hmin.argtypes = [vp, dp]
     L.tpsb_check_state.argtypes = [vp, vp, ip]
     L.tpsb_solve_step.argtypes = [vp, vp, C.c_double, C.c_int, C.c_double, ip, dp]
@@ -619,6 +622,19 @@ class RhsOperator:
         """Nodal wall distance (device tensor of N doubles, kept alive here) for the mixing-length model; None: zero."""
         self._dist = dist
         self._chk(self.L.tpsb_set_distance_field(self.ctx, dist.data_ptr() if dist is not None else None), "tpsb_set_distance_field")
+
+    def set_time_step(self, dt):
+        """BoundaryCondition::dt: the step the non-reflecting inlets / outlets advance their boundary states with."""
+        self._chk(self.L.tpsb_set_time_step(self.ctx, float(dt)), "tpsb_set_time_step")
+
+    def bc_state(self, attr):
+        """(meanUp[neq], boundaryU[points, neq]) of the non-reflecting condition on boundary attribute attr."""
+        n = C.c_int(0)
+        mean = np.zeros(self.neq)
+        self._chk(self.L.tpsb_get_bc_state(self.ctx, int(attr), _dp(mean), None, 0, C.byref(n)), "tpsb_get_bc_state")
+        bu = np.zeros((max(n.value, 1), self.neq))
+        self._chk(self.L.tpsb_get_bc_state(self.ctx, int(attr), _dp(mean), _dp(bu), n.value, C.byref(n)), "tpsb_get_bc_state")
+        return mean, bu[:n.value]
 
     def set_reaction_rate_field(self, rates):
         """Chemistry::setGridFunctionRates: device tensor [components][N] (or None)."""

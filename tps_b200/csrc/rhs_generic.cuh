@@ -24,7 +24,21 @@ namespace tpsb {
 constexpr int GEN_BC_NDATA = 12;
 struct GenBc {
   int kind, type;  // kind: 0 inlet, 1 outlet, 2 wall; type: InletType / OutletType / WallType (dataStructures.hpp:168-196)
+  int nr;          // non-reflecting / mass-flow condition: index of its patch state (GenArgs::nr), else -1
   double d[GEN_BC_NDATA];
+};
+// State of one non-reflecting inlet / outlet patch (InletBC / OutletBC members boundaryU, meanUp, tangent1, area_;
+// src/inletBC.cpp:38-221, src/outletBC.cpp:38-212): all device-resident, so an evaluation never synchronises the host.
+struct GenNrPatch {
+  const int *faces;   // the patch's boundary faces on this rank, ascending face id
+  int nfaces;
+  double *boundaryU;  // [nfaces * nqf][neq] conserved boundary state per face quadrature point
+  double *meanUp;     // [neq] mean of the interpolated primitives over the patch's points (all ranks)
+  double *sums;       // [neq + 2] reduction scratch: sum of primitives, number of points, area
+  double *area;       // [1] patch area over all ranks (BoundaryCondition::aggregateArea), set by the first evaluation
+  int *init;          // [1] 0 until boundaryU has been initialised from the interpolated primitives
+  double tangent1[3];
+  double ref_length;
 };
 struct GenBcTable {
   int nbc, use_bc_in_grad;
@@ -66,6 +80,10 @@ struct GenArgs {
   const double *Uhalo, *UpHalo, *gradUpHalo, *distHalo;
   // Fluxes' SGS model / viscous sponge: delta = h_min / order of every element (local, then face-neighbour); NULL: off
   const double *elem_delta;
+  // non-reflecting inlets / outlets: patch states, first boundary-state point of every face (-1: none), BoundaryCondition::dt
+  const GenNrPatch *nr;
+  const int *f_nr_off;
+  double bc_dt;
 };
 
 // physical point of reference point xi of element vertices v (sponge distance; z = 0 on quadrilaterals)
@@ -146,6 +164,142 @@ __device__ __forceinline__ void gen_bc_prim_for_gradient(const GenPhys &g, const
     for (int i = 0; i < g.nvel; i++) primBC[1 + i] = 0.0;
     primBC[g.nvel + 1] = bc.d[0];
   }
+}
+
+// Non-reflecting / mass-flow conditions, dry air (the reference refuses them for mixtures, inletBC.cpp:49-52,
+// outletBC.cpp:50-53): InletBC::subsonicNonReflectingDensityVelocity (inletBC.cpp:576-727; SUB_DENS_VEL_NR = 6,
+// SUB_VEL_CONST_ENT = 7), OutletBC::subsonicNonReflectingPressure / subsonicNonRefMassFlow / subsonicNonRefPWMassFlow
+// (outletBC.cpp:573-729, 739-892, 894-1027; SUB_P_NR = 2, SUB_MF_NR = 3, SUB_MF_NR_PW = 4).  The point's boundary state
+// bU is advanced by dt times the characteristic flux derivative; the face flux is Lax-Friedrichs against the state bU had
+// before.  gr[eq + d*neq]: interior gradients of the primitives; nor: CalcOrtho normal (outward).
+__device__ __noinline__ void gen_nr_flux(const GenPhys &g, const GenBc &bc, const GenNrPatch &pt, double dt, const double *u1,
+                                         const double *gr, const double *nor, double *bU, double *fx) {
+  const int neq = g.neq, dim = g.dim, nvel = g.nvel;
+  const double gamma = g.dry.gamma, Rg = g.dry.R;
+  const bool inlet = bc.kind == 0;
+  double unitNorm[3] = {0, 0, 0}, tangent2[3] = {0, 0, 0}, meanUp[GEN_MAXEQ];
+  const double *tangent1 = pt.tangent1;
+  for (int eq = 0; eq < neq; eq++) meanUp[eq] = pt.meanUp[eq];
+  {
+    double mod = 0.;
+    for (int d = 0; d < dim; d++) mod += nor[d] * nor[d];
+    for (int d = 0; d < dim; d++) unitNorm[d] = nor[d] * ((inlet ? -1. : 1.) / sqrt(mod));  // inlet: into the domain
+  }
+  double meanVel[3] = {0, 0, 0};
+  for (int d = 0; d < dim; d++) {
+    meanVel[0] += unitNorm[d] * meanUp[d + 1];
+    meanVel[1] += tangent1[d] * meanUp[d + 1];
+  }
+  if (dim == 3) {
+    tangent2[0] = unitNorm[1] * tangent1[2] - unitNorm[2] * tangent1[1];
+    tangent2[1] = unitNorm[2] * tangent1[0] - unitNorm[0] * tangent1[2];
+    tangent2[2] = unitNorm[0] * tangent1[1] - unitNorm[1] * tangent1[0];
+    for (int d = 0; d < dim; d++) meanVel[2] += tangent2[d] * meanUp[d + 1];
+  }
+  double normGrad[GEN_MAXEQ];
+  for (int eq = 0; eq < neq; eq++) {
+    normGrad[eq] = 0.;
+    for (int d = 0; d < dim; d++) normGrad[eq] += unitNorm[d] * gr[eq + d * neq];
+  }
+  // DryAir::ComputePressureDerivative(normGrad, stateIn, false) (equation_of_state.cpp:350-359)
+  const double T = dry_gen_pressure(g, u1) / (Rg * u1[0]);
+  const double dpdn = Rg * (T * normGrad[0] + u1[0] * normGrad[1 + nvel]);
+  const double speedSound = sqrt(gamma * Rg * meanUp[1 + nvel]);
+  double meanK = 0.;
+  for (int d = 0; d < nvel; d++) meanK += meanUp[1 + d] * meanUp[1 + d];
+  meanK *= 0.5;
+  const double sigma = speedSound / pt.ref_length;
+  double L1, L2, L3, L4 = 0., L5;
+  if (inlet) {
+    double meanDV[3];
+    for (int d = 0; d < nvel; d++) meanDV[d] = meanUp[1 + d] - bc.d[1 + d];
+    L1 = 0.;
+    for (int d = 0; d < dim; d++) L1 += unitNorm[d] * normGrad[1 + d];
+    L1 = dpdn - meanUp[0] * speedSound * L1;
+    L1 *= meanVel[0] - speedSound;
+    L5 = 0.;
+    for (int d = 0; d < dim; d++) L5 += meanDV[d] * unitNorm[d];
+    L5 *= sigma * 2. * meanUp[0] * speedSound;
+    L3 = 0.;
+    for (int d = 0; d < dim; d++) L3 += meanDV[d] * tangent1[d];
+    L3 *= sigma;
+    if (dim == 3) {
+      for (int d = 0; d < dim; d++) L4 += meanDV[d] * tangent2[d];
+      L4 *= sigma;
+    }
+    L2 = sigma * speedSound * speedSound * (meanUp[0] - bc.d[0]) - 0.5 * L5;
+    if (bc.type == 7) L2 = 0.;
+  } else {
+    L2 = speedSound * speedSound * normGrad[0] - dpdn;
+    L2 *= meanVel[0];
+    L3 = 0.;
+    for (int d = 0; d < dim; d++) L3 += tangent1[d] * normGrad[1 + d];
+    L3 *= meanVel[0];
+    if (dim == 3) {
+      for (int d = 0; d < dim; d++) L4 += tangent2[d] * normGrad[1 + d];
+      L4 *= meanVel[0];
+    }
+    L5 = 0.;
+    for (int d = 0; d < dim; d++) L5 += unitNorm[d] * normGrad[1 + d];
+    L5 = dpdn + meanUp[0] * speedSound * L5;
+    L5 *= meanVel[0] + speedSound;
+    if (bc.type == 2) {
+      const double meanP = Rg * meanUp[0] * meanUp[1 + nvel];
+      L1 = sigma * (meanP - bc.d[0]);
+    } else {
+      double vn = meanVel[0];  // SUB_MF_NR: the patch mean; SUB_MF_NR_PW: the point's own normal velocity
+      if (bc.type == 4) {
+        vn = 0.;
+        for (int d = 0; d < dim; d++) vn += u1[1 + d] * unitNorm[d];
+        vn /= u1[0];
+      }
+      L1 = -sigma * (vn - bc.d[0] / meanUp[0] / pt.area[0]);
+      L1 *= meanUp[0] * speedSound;
+    }
+  }
+  const double d1 = (L2 + 0.5 * (L5 + L1)) / speedSound / speedSound;
+  const double d2 = 0.5 * (L5 - L1) / meanUp[0] / speedSound;
+  const double d3 = L3, d4 = L4, d5 = 0.5 * (L5 + L1);
+  double dF[GEN_MAXEQ];
+  for (int eq = 0; eq < neq; eq++) dF[eq] = 0.;
+  dF[0] = d1;
+  dF[1] = meanVel[0] * d1 + meanUp[0] * d2;
+  dF[2] = meanVel[1] * d1 + meanUp[0] * d3;
+  if (dim == 3) dF[3] = meanVel[2] * d1 + meanUp[0] * d4;
+  dF[1 + dim] = meanUp[0] * meanVel[0] * d2;
+  dF[1 + dim] += meanUp[0] * meanVel[1] * d3;
+  if (dim == 3) dF[1 + dim] += meanUp[0] * meanVel[2] * d4;
+  dF[1 + dim] += meanK * d1 + d5 / (gamma - 1.);
+  double state2[GEN_MAXEQ], stateN[GEN_MAXEQ], newU[GEN_MAXEQ];
+  for (int eq = 0; eq < neq; eq++) state2[eq] = bU[eq], stateN[eq] = bU[eq];
+  for (int d = 0; d < dim; d++) stateN[1 + d] = 0.;
+  for (int d = 0; d < dim; d++) {
+    stateN[1] += state2[1 + d] * unitNorm[d];
+    stateN[2] += state2[1 + d] * tangent1[d];
+    if (dim == 3) stateN[3] += state2[1 + d] * tangent2[d];
+  }
+  for (int i = 0; i < neq; i++) newU[i] = stateN[i] - dt * dF[i];
+  {  // back to Cartesian momentum: inverse (adjugate / determinant, mfem::CalcInverse) of the matrix with rows n, t1, t2
+    double momX[3] = {0, 0, 0};
+    if (dim == 2) {
+      const double a = unitNorm[0], b = tangent1[0], c = unitNorm[1], d = tangent1[1];  // column-major M(0,0), M(1,0), M(0,1), M(1,1)
+      const double t = 1.0 / (a * d - b * c);
+      momX[0] = (d * t) * newU[1] + (-c * t) * newU[2];
+      momX[1] = (-b * t) * newU[1] + (a * t) * newU[2];
+    } else {
+      double a[9], inv[9];
+      for (int d = 0; d < 3; d++) a[0 + d * 3] = unitNorm[d], a[1 + d * 3] = tangent1[d], a[2 + d * 3] = tangent2[d];
+      const double t = 1.0 / (a[0] * (a[4] * a[8] - a[5] * a[7]) - a[3] * (a[1] * a[8] - a[2] * a[7]) + a[6] * (a[1] * a[5] - a[2] * a[4]));
+      inv[0] = (a[4] * a[8] - a[5] * a[7]) * t, inv[3] = (a[5] * a[6] - a[3] * a[8]) * t, inv[6] = (a[3] * a[7] - a[4] * a[6]) * t;
+      inv[1] = (a[2] * a[7] - a[1] * a[8]) * t, inv[4] = (a[0] * a[8] - a[2] * a[6]) * t, inv[7] = (a[1] * a[6] - a[0] * a[7]) * t;
+      inv[2] = (a[1] * a[5] - a[2] * a[4]) * t, inv[5] = (a[2] * a[3] - a[0] * a[5]) * t, inv[8] = (a[0] * a[4] - a[1] * a[3]) * t;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) momX[i] += inv[i + j * 3] * newU[1 + j];
+    }
+    for (int d = 0; d < dim; d++) newU[1 + d] = momX[d];
+  }
+  for (int eq = 0; eq < neq; eq++) bU[eq] = newU[eq];
+  gen_riemann_lf(g, u1, state2, nor, fx);
 }
 
 // BCintegrator::computeBdrFlux (BCintegrator.cpp:228-242) -> InletBC::subsonicReflectingDensityVelocity
@@ -536,9 +690,10 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
           const int sp = eq - nvel - 2;
           uo[eq] = (sp >= 0 && sp < nact) ? fmax(x, 0.0) : x;
         }
-        for (int c = 0; c < nc; c++) {  // the Euler boundary fluxes never read the gradients
+        const GenBc &bcf = a.bct.bc[a.f_bc[f]];
+        for (int c = 0; c < nc; c++) {  // the Euler boundary fluxes never read the gradients (the non-reflecting ones do)
           double x = 0;
-          if (a.eq_system != 0)
+          if (a.eq_system != 0 || bcf.nr >= 0)
             for (int k = 0; k < dof; k++) x += po[k] * sG[c * dof + k];
           go[c] = x;
         }
@@ -552,7 +707,11 @@ __global__ void __launch_bounds__(128) gen_resid_kernel(GenArgs a) {
           axb.delta = a.elem_delta[e1];
           gen_point(dim, v1, xi1, axb.x);
         }
-        gen_bc_flux(ph, a.bct.bc[a.f_bc[f]], a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb, a.elem_delta ? &axb : nullptr);
+        if (bcf.nr >= 0)  // every boundary point is visited by exactly one thread: its state is updated in place
+          gen_nr_flux(ph, bcf, a.nr[bcf.nr], a.bc_dt, uo, go, nor,
+                      a.nr[bcf.nr].boundaryU + static_cast<long long>(a.f_nr_off[f] + q) * neq, fxb);
+        else
+          gen_bc_flux(ph, bcf, a.bct.use_bc_in_grad, uo, go, nor, radius, fxb, dwb, a.elem_delta ? &axb : nullptr);
         const double sgb = -(ph.axisym ? a.wF[q] * radius : a.wF[q]);  // elvect -= fluxN w [r] shape1
         for (int eq = 0; eq < neq; eq++) dstq[eq] = sgb * fxb[eq];
         continue;
@@ -735,6 +894,61 @@ __global__ void gen_point_eval_kernel(GenArgs a, int which, int n, const double 
     gen_prim(a.phys, s, up);
     mix_source(*a.phys.mix, s, up, gr, i, f);
     for (int eq = 0; eq < neq; eq++) out[i * neq + eq] = f[eq];
+  }
+}
+
+// InletBC::updateMean / OutletBC::updateMean (inletBC.cpp:482-564, outletBC.cpp:470-561), called by every Mult after
+// the gradients (rhs_operator.cpp:364): sum of the primitives interpolated to the patch's face quadrature points, their
+// number and (for the first evaluation) the patch area; the first evaluation also initialises the boundary states with
+// the conserved form of the interpolated primitives.  One CTA per patch, fixed-order reduction: run-to-run deterministic.
+__global__ void __launch_bounds__(256) gen_nr_sum_kernel(GenArgs a) {
+  const GenNrPatch &pt = a.nr[blockIdx.x];
+  __shared__ double red[256];
+  const int neq = a.neq, dim = a.dim, dof = a.dof, npts = pt.nfaces * a.nqf;
+  const bool first = pt.init[0] == 0;
+  double acc[GEN_MAXEQ + 2];
+  for (int i = 0; i < neq + 2; i++) acc[i] = 0.0;
+  for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+    const int f = pt.faces[t / a.nqf], q = t % a.nqf, e1 = a.f_el1[f], code1 = gen_code(dim, a.f_inf1[f]);
+    const double *po = a.phiF + (static_cast<long long>(code1) * a.nqf + q) * dof;
+    double up[GEN_MAXEQ], st[GEN_MAXEQ];
+    for (int eq = 0; eq < neq; eq++) {
+      double x = 0.;
+      const double *src = a.Up + static_cast<long long>(e1) * dof + static_cast<long long>(eq) * a.N;
+      for (int k = 0; k < dof; k++) x += po[k] * src[k];
+      up[eq] = x;
+      acc[eq] += x;
+    }
+    acc[neq] += 1.0;
+    if (first) {
+      gen_cons(a.phys, up, st);
+      for (int eq = 0; eq < neq; eq++) pt.boundaryU[static_cast<long long>(t) * neq + eq] = st[eq];
+      double J[9], nor[3], m = 0.;  // BoundaryCondition::aggregateArea (BoundaryCondition.cpp:59-81)
+      gen_jacobian(dim, a.vx + static_cast<long long>(e1) * a.nv * dim, a.xiF + (static_cast<long long>(code1) * a.nqf + q) * dim, J);
+      gen_face_normal(dim, J, a.dlocF + code1 * dim * (dim - 1), nor);
+      for (int d = 0; d < dim; d++) m += nor[d] * nor[d];
+      acc[neq + 1] += sqrt(m) * a.wF[q];
+    }
+  }
+  for (int i = 0; i < neq + 2; i++) {
+    red[threadIdx.x] = acc[i];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) pt.sums[i] = red[0];
+    __syncthreads();
+  }
+}
+// ... after the sums have been all-reduced over the ranks (MPI_Allreduce in the reference): the mean, the area, the flag
+__global__ void gen_nr_finish_kernel(GenArgs a) {
+  const GenNrPatch &pt = a.nr[blockIdx.x];
+  const int neq = a.neq;
+  if (threadIdx.x < neq) pt.meanUp[threadIdx.x] = pt.sums[threadIdx.x] * (1. / pt.sums[neq]);
+  if (threadIdx.x == 0 && pt.init[0] == 0) {
+    pt.area[0] = pt.sums[neq + 1];
+    pt.init[0] = 1;
   }
 }
 

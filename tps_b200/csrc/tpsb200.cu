@@ -106,6 +106,10 @@ struct tpsb_ctx {
   KernelArgs::RkStage rk = {nullptr, nullptr, nullptr, 0.0, 0.0, 0};  // stage update fused into the residual kernel
   // forcing terms (tpsb_add_forcing), applied after Me^-1 in registration order
   std::vector<ForcingDev> forcings;
+  // non-reflecting inlets / outlets (generic path): host copies of the patch descriptors, their attributes, BoundaryCondition::dt
+  std::vector<GenNrPatch> nr_patches;
+  std::vector<int> nr_attr;
+  double bc_dt = 0.0;
   double *d_xiN3 = nullptr;  // [dof][3] reference coordinates of the nodes (3-D dry-air paths; the generic path has its own)
   bool forcing_needs_grad = false;
   long long launches = 0;
@@ -481,6 +485,49 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
               break;
             }
   }
+  // non-reflecting inlets / outlets: per patch the face list, the first boundary-state point of every face, tangent1
+  std::vector<int> f_nr_off(NF, -1);
+  std::vector<std::vector<int>> nr_faces;
+  std::vector<GenNrPatch> nr_host;
+  for (int i = 0; i < gbt.nbc; i++) {
+    GenBc &b = gbt.bc[i];
+    b.nr = -1;
+    const bool is_nr = (b.kind == 0 && (b.type == 6 || b.type == 7)) || (b.kind == 1 && b.type >= 2 && b.type <= 4);
+    if (!is_nr) continue;
+    b.nr = static_cast<int>(nr_host.size());
+    std::vector<int> faces;
+    for (int f = 0; f < NF; f++)
+      if (f_bc[f] == i) {
+        f_nr_off[f] = static_cast<int>(faces.size()) * nqf;
+        faces.push_back(f);
+      }
+    GenNrPatch pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.nfaces = static_cast<int>(faces.size());
+    pt.ref_length = b.d[8];
+    for (int d = 0; d < 3; d++) pt.tangent1[d] = b.d[9 + d];
+    if (pt.tangent1[0] == 0.0 && pt.tangent1[1] == 0.0 && pt.tangent1[2] == 0.0 && !faces.empty()) {
+      // OutletBC / InletBC constructor (src/outletBC.cpp:161-176): unit vector from the first to the second quadrature
+      // point of the patch's first face
+      const int f = faces[0], e1 = maps->face_el1[f], code = (maps->face_inf1[f] / 64) * nori;
+      const double *v = &maps->elem_vertices[static_cast<size_t>(e1) * nv * dim];
+      double X[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      for (int q = 0; q < 2; q++) {
+        const double *xi = &xiF[(static_cast<size_t>(code) * nqf + q) * dim];
+        for (int vtx = 0; vtx < nv; vtx++) {  // multilinear map, MFEM vertex order
+          static const int hv[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+          double w = 1.0;
+          for (int d = 0; d < dim; d++) w *= hv[vtx][d] ? xi[d] : 1.0 - xi[d];
+          for (int d = 0; d < dim; d++) X[q][d] += w * v[vtx * dim + d];
+        }
+      }
+      double m = 0.0;
+      for (int d = 0; d < dim; d++) m += (X[1][d] - X[0][d]) * (X[1][d] - X[0][d]);
+      for (int d = 0; d < dim; d++) pt.tangent1[d] = (X[1][d] - X[0][d]) * (1. / std::sqrt(m));
+    }
+    nr_faces.push_back(faces);
+    nr_host.push_back(pt);
+  }
   GenArgs &g = c->gen;
   memset(&g, 0, sizeof(g));
   g.dim = dim, g.np = np, g.dof = dof, g.nqv = nqv, g.nqf = nqf, g.nfe = nfe, g.nv = nv;
@@ -597,6 +644,29 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
   if (ce == cudaSuccess && axisym) ce = g_upload(c, &g.me_inv_rad, me_rad);
   if (ce == cudaSuccess) ce = g_upload(c, &g.xiN, xiN);
   if (ce == cudaSuccess) ce = g_upload(c, &g.f_bc, f_bc);
+  if (!nr_host.empty()) {
+    const int neq = space->num_equation;
+    if (ce == cudaSuccess) ce = g_upload(c, &g.f_nr_off, f_nr_off);
+    for (size_t i = 0; i < nr_host.size() && ce == cudaSuccess; i++) {
+      GenNrPatch &pt = nr_host[i];
+      const size_t npts = static_cast<size_t>(pt.nfaces) * nqf;
+      double *block = nullptr;  // boundaryU | meanUp | sums | area, one allocation per patch
+      const size_t nd = npts * neq + neq + (neq + 2) + 1;
+      if (!nr_faces[i].empty()) ce = g_upload(c, &pt.faces, nr_faces[i]);
+      if (ce == cudaSuccess) ce = cudaMalloc(&block, nd * sizeof(double));
+      if (ce == cudaSuccess) ce = cudaMemset(block, 0, nd * sizeof(double));
+      if (ce == cudaSuccess) ce = cudaMalloc(&pt.init, sizeof(int));
+      if (ce == cudaSuccess) ce = cudaMemset(pt.init, 0, sizeof(int));
+      if (ce != cudaSuccess) break;
+      c->gen_allocs.push_back(block);
+      c->gen_allocs.push_back(pt.init);
+      pt.boundaryU = block, pt.meanUp = block + npts * neq, pt.sums = pt.meanUp + neq, pt.area = pt.sums + neq + 2;
+    }
+    if (ce == cudaSuccess) ce = g_upload(c, &g.nr, nr_host);
+    c->nr_patches = nr_host;
+    for (int i = 0; i < gbt.nbc; i++)
+      if (gbt.bc[i].nr >= 0) c->nr_attr.push_back(bcs->bcs[i].attr);
+  }
   if (ce == cudaSuccess && !mixv.empty()) ce = g_upload(c, &g.phys.mix, mixv);
   const size_t nb = static_cast<size_t>(g.N) * sizeof(double);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * g.neq);
@@ -837,6 +907,12 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
   if (phys->use_roe && !(maps->dim == 2 && space->nvel == 2 && phys->fluid == TPSB_DRY_AIR))
     return fail(ctx, TPSB_ENOTIMPL, "useRoe: Eval_Roe of the reference is written for 2-D dry air only (riemann_solver.cpp:117-206)");
   if (phys->use_mixing_length) want_generic = true;  // the mixing-length model lives on the generic path
+  auto bc_is_nr = [](const tpsb_bc_desc &b) {  // non-reflecting / mass-flow inlets and outlets: generic path
+    return (b.kind == TPSB_BC_INLET && (b.type == 6 || b.type == 7)) || (b.kind == TPSB_BC_OUTLET && b.type >= 2 && b.type <= 4);
+  };
+  if (bcs && bcs->bcs)
+    for (int i = 0; i < bcs->num_bcs && i < MAX_BC; i++)
+      if (bc_is_nr(bcs->bcs[i])) want_generic = true;
   for (int i = 0; bcs && bcs->bcs && i < bcs->num_bcs; i++)  // ... and so does the general wall (WallType VISC_GNRL)
     if (bcs->bcs[i].kind == TPSB_BC_WALL && bcs->bcs[i].type == 4) want_generic = true;
   const bool visc_mod = phys->sgs_model != 0 || phys->sponge_enabled != 0;
@@ -864,7 +940,15 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
       const tpsb_bc_desc &b = bcs->bcs[i];
       const bool ok = (b.kind == TPSB_BC_INLET && b.type == 2) || (b.kind == TPSB_BC_OUTLET && b.type == 0) ||
                       (b.kind == TPSB_BC_WALL && b.type >= 0 && b.type <= 3) ||
-                      (b.kind == TPSB_BC_WALL && b.type == 4 && want_generic);  // VISC_GNRL: generic path
+                      (b.kind == TPSB_BC_WALL && b.type == 4 && want_generic) ||  // VISC_GNRL: generic path
+                      bc_is_nr(b);
+      if (bc_is_nr(b)) {
+        // the reference refuses them for mixtures (src/inletBC.cpp:49-52, src/outletBC.cpp:50-53) and indexes the energy
+        // with 1 + dim, which is wrong for the three-velocity axisymmetric state
+        if (phys->fluid != TPSB_DRY_AIR || space->nvel != maps->dim)
+          return fail(ctx, TPSB_ENOTIMPL, "non-reflecting boundary conditions: dry air, planar 2-D or 3-D only (attribute %d)", b.attr);
+        if (!(b.data[8] > 0.0)) return fail(ctx, TPSB_EINVAL, "non-reflecting boundary condition on attribute %d needs data[8] = refLength > 0", b.attr);
+      }
       if (!ok)
         return fail(ctx, TPSB_ENOTIMPL, "boundary condition kind %d type %d (attribute %d) not built yet", b.kind, b.type, b.attr);
       bct.bc[i].kind = b.kind;
@@ -1813,6 +1897,16 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
   GenArgs g = c->gen;
   g.U = d_x;
   g.y = d_y;
+  g.bc_dt = c->bc_dt;
+  if (!c->nr_patches.empty()) {  // bcIntegrator->updateBCMean(Up) (rhs_operator.cpp:364): patch means on the device
+    ProfScope ps(c, K_FACE);
+    const int np = static_cast<int>(c->nr_patches.size());
+    gen_nr_sum_kernel<<<np, 256, 0, c->stream>>>(g);
+    if (c->comm)  // the MPI_Allreduce of updateMean; every rank holds every patch (possibly with no faces of it)
+      for (int i = 0; i < np; i++)
+        NC(ncclAllReduce(c->nr_patches[i].sums, c->nr_patches[i].sums, g.neq + 2, ncclDouble, ncclSum, c->comm, c->stream));
+    gen_nr_finish_kernel<<<np, 32, 0, c->stream>>>(g);
+  }
   if (c->NEH > 0 && g.eq_system != 0) {  // face-neighbour gradients for the viscous face fluxes (rhs_operator.cpp:363-375)
     rc = exchange(c, c->d_gradUp, g.neq * g.dim, c->d_sendG, c->d_gradUpHalo, c->ev_recvG);
     if (rc) return rc;
@@ -2277,6 +2371,32 @@ int tpsb_add_forcing(tpsb_ctx *ctx, const tpsb_forcing_desc *d) {
   return TPSB_OK;
 }
 
+int tpsb_set_time_step(tpsb_ctx *ctx, double dt) {
+  if (!ctx) return TPSB_EINVAL;
+  if (!(dt >= 0.0) || !std::isfinite(dt)) return fail(ctx, TPSB_EINVAL, "time step must be finite and >= 0");
+  if (ctx->bc_dt != dt) ode_graph_invalidate(ctx);
+  ctx->bc_dt = dt;
+  return TPSB_OK;
+}
+
+int tpsb_get_bc_state(tpsb_ctx *ctx, int attr, double *mean_up, double *boundary_u, int capacity, int *num_points) {
+  if (!ctx || !num_points) return TPSB_EINVAL;
+  tpsb_ctx *c = ctx;
+  for (size_t i = 0; i < c->nr_patches.size(); i++)
+    if (c->nr_attr[i] == attr) {
+      const GenNrPatch &pt = c->nr_patches[i];
+      const int npts = pt.nfaces * c->gen.nqf, neq = c->gen.neq;
+      *num_points = npts;
+      CU(cudaSetDevice(c->device));
+      CU(cudaStreamSynchronize(c->stream));
+      if (mean_up) CU(cudaMemcpy(mean_up, pt.meanUp, sizeof(double) * neq, cudaMemcpyDeviceToHost));
+      if (boundary_u && capacity > 0 && npts > 0)
+        CU(cudaMemcpy(boundary_u, pt.boundaryU, sizeof(double) * neq * std::min(npts, capacity), cudaMemcpyDeviceToHost));
+      return TPSB_OK;
+    }
+  return fail(ctx, TPSB_EINVAL, "no non-reflecting boundary condition on attribute %d", attr);
+}
+
 int tpsb_set_reaction_rate_field(tpsb_ctx *ctx, const double *d_rates, int num_components) {
   if (!ctx) return TPSB_EINVAL;
   if (!ctx->generic || !ctx->gen.phys.fluid) return fail(ctx, TPSB_EINVAL, "reaction rate fields belong to a plasma mixture");
@@ -2403,6 +2523,7 @@ int tpsb_ode_step(tpsb_ctx *ctx, double *d_U, double dt, int scheme, int nsteps)
   if (rc) return rc;
   const double *saved_view = ctx->sol_view;
   ctx->sol_view = d_U;  // the forcing terms read the solution vector, not the stage vector (parity trap 1)
+  ctx->bc_dt = dt;      // BoundaryCondition::dt is a reference to M2ulPhyS::dt, the step being taken
   const char *env = getenv("TPSB_ODE_GRAPH");
   const bool use_graph = !ctx->comm && !ctx->profiling && nsteps >= 3 && !(env && atoi(env) == 0);
   int done = 0;
