@@ -123,9 +123,27 @@ typedef struct {
   const double *nec_table_x, *nec_table_f;
 } tpsb_plasma_models;
 
+/* LTE working fluid (fluid = TPSB_LTE_FLUID) with 1-D look-up tables, flow/lte/table_dim = 1: LteMixture + LteTransport
+ * (src/lte_mixture.cpp, src/lte_transport_properties.cpp) as M2ulPhyS builds them from the columns of the thermo file
+ * "T_energy_R_c" and the transport file (src/M2ulPhyS.cpp:175-258): one species, one temperature, num_equation = nvel + 2;
+ * T from the conserved state by Newton iteration on e(T) started from the inverse table, p = rho R(T) T, speed of sound c(T),
+ * viscosity mu(T), conductivity kappa(T), no bulk viscosity; optional tabulated net emission coefficient (radiative sink
+ * -4 pi eps_N(T), src/source_term.cpp:205-207).  All tables are linear in both axes (LinearTable src/table.cpp:76-116), HOST
+ * arrays copied at create, 2..1000 rows (gpudata::MAXTABLE); T and energy strictly increasing.  sigma (electrical
+ * conductivity) only feeds the plasma-conductivity output field of the reference, not dU/dt: accepted, not used.  The
+ * reference's 2-D (T, rho) tables need GSL and are CPU-only there (src/M2ulPhyS.cpp:168-170): not built.               */
+typedef struct {
+  int num_thermo;
+  const double *T, *energy, *R, *c;
+  int num_trans;
+  const double *T_trans, *mu, *kappa, *sigma;
+  int nec_table_n, nec_table_xlog, nec_table_flog;
+  const double *nec_table_x, *nec_table_f;
+} tpsb_lte_tables;
+
 typedef struct {
   int eq_system;          /* TPSB_EULER / TPSB_NS                              */
-  int fluid;              /* TPSB_DRY_AIR, or TPSB_USER_DEFINED with `plasma`  */
+  int fluid;              /* TPSB_DRY_AIR, TPSB_USER_DEFINED with `plasma`, or TPSB_LTE_FLUID with `lte` */
   double specific_heat_ratio;
   double gas_constant;
   double visc_mult;       /* flow/viscosityMultiplier                          */
@@ -154,6 +172,7 @@ typedef struct {
    * generic path (any fluid, 2-D / axisymmetric / 3-D).                                                            */
   int use_mixing_length;
   double max_mixing_length, mixing_length_Prt, mixing_length_bulk_mult;
+  const tpsb_lte_tables *lte; /* fluid == TPSB_LTE_FLUID: the look-up tables; else NULL */
 } tpsb_physics;
 
 /* Boundary conditions: BCintegrator's attribute -> {InletBC, OutletBC, WallBC} maps (src/BCintegrator.cpp:64-125).

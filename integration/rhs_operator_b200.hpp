@@ -247,14 +247,15 @@ class RHSoperatorB200 : public RHSoperator {
   }
 
  public:
+  // lte_tables: NULL unless the working fluid is LTE_FLUID.
   // base_args: the arguments M2ulPhyS::initVariables passes to RHSoperator today (src/M2ulPhyS.cpp:692-720); the base
   // class keeps owning what the rest of TPS reads from it.  nccl_comm: created once per job with
   // tpsb_comm_get_unique_id (rank 0) + MPI_Bcast of the 128 bytes + tpsb_comm_init_rank; NULL in a serial run.
   template <class... A>
   RHSoperatorB200(mfem::ParMesh *mesh, mfem::ParFiniteElementSpace *vfes, mfem::IntegrationRules *intRules,
                   RunConfiguration &config, const double &dt, const mfem::ParGridFunction *U,
-                  const mfem::ParGridFunction *distance, const mfem::ParGridFunction *joule_heating, void *nccl_comm,
-                  void *cuda_stream, A &&...base_args)
+                  const mfem::ParGridFunction *distance, const mfem::ParGridFunction *joule_heating,
+                  const tpsb_lte_tables *lte_tables, void *nccl_comm, void *cuda_stream, A &&...base_args)
       : RHSoperator(std::forward<A>(base_args)...), U_view_(U), distance_view_(distance), dt_(dt) {
     const int dim = mesh->Dimension(), NE = mesh->GetNE(), NEH = mesh->GetNFaceNeighborElements();
     fill_vertices(mesh);
@@ -286,6 +287,10 @@ class RHSoperatorB200 : public RHSoperator {
       fill_plasma(config);
       phys.plasma = &pm_;
     }
+    // LTE_FLUID, flow/lte/table_dim = 1: the host TableInputs M2ulPhyS::initMixtureAndTransportModels reads from the thermo
+    // and transport files (thermo_tables[0..2] = energy, R, c over T; trans_tables[0..2] = mu, kappa, sigma;
+    // src/M2ulPhyS.cpp:178-250) handed over as plain arrays, plus radiationInput.necTableInput when NET_EMISSION is on
+    if (config.GetWorkingFluid() == LTE_FLUID) phys.lte = lte_tables;
 
     fill_bcs(config, config.GetNumSpecies());
     fill_nr_data(config, mesh, vfes, intRules);

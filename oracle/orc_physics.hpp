@@ -35,6 +35,18 @@ struct OrcPhysParams {
   // mixingLengthTransportData src/dataStructures.hpp:548-554; reference back end only)
   int use_mixing_length;
   double max_mixing_length, mixing_length_Prt, mixing_length_bulk_mult;
+  const struct OrcLte *lte;  // fluid == 2 (LTE_FLUID): 1-D look-up tables (reference back end only)
+};
+// LteMixture / LteTransport with 1-D tables (flow/lte/table_dim = 1, src/M2ulPhyS.cpp:175-258): thermodynamic table
+// T -> (energy, R, c) and its inverse energy -> T, transport table T -> (mu, kappa, sigma), optional net emission
+// coefficient.  Same layout as tpsb_lte_tables.
+struct OrcLte {
+  int num_thermo;
+  const double *T, *energy, *R, *c;
+  int num_trans;
+  const double *T_trans, *mu, *kappa, *sigma;
+  int nec_table_n, nec_table_xlog, nec_table_flog;
+  const double *nec_table_x, *nec_table_f;
 };
 // Plasma models of a user-defined fluid: PerfectMixtureInput + constantTransportData + ChemistryInput
 // (src/dataStructures.hpp:537-546,623-633,690-712) flattened; same layout as tpsb_plasma_models.

@@ -12,6 +12,8 @@
 #include "equation_of_state.hpp"
 #include "fluxes.hpp"
 #include "gas_transport.hpp"
+#include "lte_mixture.hpp"
+#include "lte_transport_properties.hpp"
 #include "radiation.hpp"
 #include "mixing_length_transport.hpp"
 #include "riemann_solver.hpp"
@@ -127,25 +129,50 @@ static Fluxes *make_fluxes(const OrcPhysParams &p, GasMixture *mix, Equations eq
 
 namespace orc {
 
+// Single-species fluids: DryAir + DryAirTransport, or LteMixture + LteTransport over 1-D tables (fluid == 2).
 class DryAirRef : public Physics {
   int dim_, nvel_, neq_;
-  DryAir *mix_;
-  DryAirTransport *trans_;
+  GasMixture *mix_;
+  MolecularTransport *trans_;
   Fluxes *flux_;
   RiemannSolverTPS *rs_;
+  NetEmission *rad_ = nullptr;
   bool use_roe_ = false;
   Equations eqs_;
   WallCache walls_[256];
 
+  static TableInput table(int n, const double *x, const double *f) {
+    TableInput t;
+    t.Ndata = n, t.xdata = x, t.fdata = f, t.xLogScale = false, t.fLogScale = false, t.order = 1;
+    return t;
+  }
+
  public:
   DryAirRef(const OrcPhysParams &p, int dim, int nvel, int neq) : dim_(dim), nvel_(nvel), neq_(neq) {
-    DryAirInput in;
-    in.f = DRY_AIR;
-    in.eq_sys = static_cast<Equations>(p.eq_system);
-    in.specific_heat_ratio = p.gamma;
-    in.gas_constant = p.R;
-    mix_ = new DryAir(in, dim, nvel);                                                          // equation_of_state.cpp:150
-    trans_ = new DryAirTransport(mix_, p.visc_mult, p.bulk_visc_mult, p.C1, p.S0, p.Pr);       // transport_properties.cpp:208
+    if (p.fluid == 2) {  // M2ulPhyS::initMixtureAndTransportModels, table_dim == 1 (M2ulPhyS.cpp:175-258)
+      const OrcLte &l = *p.lte;
+      // energy, R and c over T; the e -> T table is the T -> e table with its columns swapped (M2ulPhyS.cpp:193-200)
+      mix_ = new LteMixture(LTE_FLUID, dim, nvel, 0.0, table(l.num_thermo, l.T, l.energy), table(l.num_thermo, l.T, l.R),
+                            table(l.num_thermo, l.T, l.c), table(l.num_thermo, l.energy, l.T));
+      trans_ = new LteTransport(mix_, table(l.num_trans, l.T_trans, l.mu), table(l.num_trans, l.T_trans, l.kappa),
+                                table(l.num_trans, l.T_trans, l.sigma));
+      if (l.nec_table_n > 0) {
+        RadiationInput ri;
+        ri.model = NET_EMISSION;
+        ri.necModel = TABULATED_NEC;
+        ri.necTableInput = table(l.nec_table_n, l.nec_table_x, l.nec_table_f);
+        ri.necTableInput.xLogScale = l.nec_table_xlog != 0, ri.necTableInput.fLogScale = l.nec_table_flog != 0;
+        rad_ = new NetEmission(ri);
+      }
+    } else {
+      DryAirInput in;
+      in.f = DRY_AIR;
+      in.eq_sys = static_cast<Equations>(p.eq_system);
+      in.specific_heat_ratio = p.gamma;
+      in.gas_constant = p.R;
+      mix_ = new DryAir(in, dim, nvel);                                                          // equation_of_state.cpp:150
+      trans_ = new DryAirTransport(mix_, p.visc_mult, p.bulk_visc_mult, p.C1, p.S0, p.Pr);       // transport_properties.cpp:208
+    }
     const bool axisym = (dim == 2 && nvel == 3);  // config.isAxisymmetric()
     flux_ = make_fluxes(p, mix_, static_cast<Equations>(p.eq_system), wrap_mixing_length(p, mix_, trans_), neq, dim, axisym);
     rs_ = new RiemannSolverTPS(neq, mix_, static_cast<Equations>(p.eq_system), flux_, p.use_roe != 0, axisym);  // riemann_solver.cpp:38
@@ -153,6 +180,7 @@ class DryAirRef : public Physics {
     eqs_ = static_cast<Equations>(p.eq_system);
   }
   ~DryAirRef() {
+    delete rad_;
     delete rs_;
     delete flux_;
     delete trans_;
@@ -204,6 +232,13 @@ class DryAirRef : public Physics {
       bc.primFluxIdxs[i] = i < 16 ? primFluxIdxs[i] : false;
     }
     flux_->ComputeBdrViscousFluxes(U, gradUp, xyz, delta, dist, bc, normalFlux);  // fluxes.cpp:344
+  }
+  // SourceTerm::updateTerms for one species without reactions (source_term.cpp:117-250): only the radiative energy sink
+  // (:205-207) reaches dU/dt; the plasma conductivity it also writes is an output field, not part of the residual
+  bool has_source() const override { return rad_ != nullptr; }
+  void source_term(double *Un, double *upn, const double *gradUpn, int n, double *srcTerm) override {
+    for (int eq = 0; eq < neq_; eq++) srcTerm[eq] = 0.0;
+    if (rad_) srcTerm[1 + nvel_] += rad_->computeEnergySink(upn[1 + nvel_]);
   }
   void prim(const double *U, double *Up) override { mix_->GetPrimitivesFromConservatives(U, Up); }
   void cons(const double *Up, double *U) override { mix_->GetConservativesFromPrimitives(Up, U); }
@@ -518,6 +553,7 @@ class MixtureRef : public Physics {
 
 Physics *make_physics(const OrcPhysParams &p, int dim, int nvel, int neq) {
   if (p.fluid == 1 && p.plasma) return new MixtureRef(p, dim, nvel, neq);
+  if (p.fluid == 2 && p.lte) return new DryAirRef(p, dim, nvel, neq);
   if (p.fluid != 0) return nullptr;
   return new DryAirRef(p, dim, nvel, neq);
 }

@@ -28,6 +28,7 @@ class RunConfiguration {
   constantTransportData constantTransport;
   ChemistryInput chemistryInput;
   RadiationInput radiationInput;
+  LteMixtureInput lteMixtureInput;
   mixingLengthTransportData mix_length_trans_input_;
   SutherlandData sutherland_;
   linearlyVaryingVisc linViscData;

@@ -17,7 +17,7 @@ class OrcPhysParams(C.Structure):
                 ("sgs_model", C.c_int), ("sgs_const", C.c_double), ("sgs_floor", C.c_double), ("sponge_enabled", C.c_int),
                 ("sponge_normal", C.c_double * 3), ("sponge_point", C.c_double * 3), ("sponge_ratio", C.c_double),
                 ("sponge_width", C.c_double), ("use_mixing_length", C.c_int), ("max_mixing_length", C.c_double),
-                ("mixing_length_Prt", C.c_double), ("mixing_length_bulk_mult", C.c_double)]
+                ("mixing_length_Prt", C.c_double), ("mixing_length_bulk_mult", C.c_double), ("lte", C.c_void_p)]
 
 
 class OrcBc(C.Structure):
@@ -30,6 +30,14 @@ def make_bc(attr, kind, type_, data=()):
     for i, v in enumerate(data):
         b.data[i] = float(v)
     return b
+
+
+def lte_params(tables, eq_system=1):
+    """LTE_FLUID over the 1-D tables of a tps_b200.LteTables (same layout as OrcLte); reference back end (kind="ref") only."""
+    p = OrcPhysParams(eq_system, 2, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, None, 0)
+    p.lte = C.addressof(tables)
+    p._tables = tables
+    return p
 
 
 def dry_air_params(eq_system=1, visc_mult=1.0, bulk_visc_mult=0.0, use_roe=False, sgs=None, sponge=None):

@@ -128,6 +128,30 @@ class PlasmaModels(C.Structure):
         return pm
 
 
+class LteTables(C.Structure):
+    """tpsb_lte_tables (same layout as the oracle's OrcLte): 1-D look-up tables of the LTE working fluid."""
+    _fields_ = [("num_thermo", C.c_int), ("T", C.c_void_p), ("energy", C.c_void_p), ("R", C.c_void_p), ("c", C.c_void_p),
+                ("num_trans", C.c_int), ("T_trans", C.c_void_p), ("mu", C.c_void_p), ("kappa", C.c_void_p), ("sigma", C.c_void_p),
+                ("nec_table_n", C.c_int), ("nec_table_xlog", C.c_int), ("nec_table_flog", C.c_int),
+                ("nec_table_x", C.c_void_p), ("nec_table_f", C.c_void_p)]
+
+    @classmethod
+    def make(cls, T, energy, R, c, T_trans, mu, kappa, sigma, nec=None):
+        """nec = (x, f, xlog, flog) of the net emission coefficient, or None.  The arrays are kept alive on the object."""
+        t = cls()
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (T, energy, R, c, T_trans, mu, kappa, sigma)]
+        t.num_thermo, t.num_trans = len(keep[0]), len(keep[4])
+        for name, a in zip(("T", "energy", "R", "c", "T_trans", "mu", "kappa", "sigma"), keep):
+            setattr(t, name, a.ctypes.data)
+        if nec is not None:
+            nx, nf = np.ascontiguousarray(nec[0], dtype=np.float64), np.ascontiguousarray(nec[1], dtype=np.float64)
+            keep += [nx, nf]
+            t.nec_table_n, t.nec_table_xlog, t.nec_table_flog = len(nx), int(nec[2]), int(nec[3])
+            t.nec_table_x, t.nec_table_f = nx.ctypes.data, nf.ctypes.data
+        t._keep = keep
+        return t
+
+
 class Physics(C.Structure):
     """tpsb_physics; defaults are the reference's dry-air constants."""
     _fields_ = [("eq_system", C.c_int), ("fluid", C.c_int), ("specific_heat_ratio", C.c_double),
@@ -137,7 +161,7 @@ class Physics(C.Structure):
                 ("sgs_model", C.c_int), ("sgs_const", C.c_double), ("sgs_floor", C.c_double), ("sponge_enabled", C.c_int),
                 ("sponge_normal", C.c_double * 3), ("sponge_point", C.c_double * 3), ("sponge_ratio", C.c_double),
                 ("sponge_width", C.c_double), ("use_mixing_length", C.c_int), ("max_mixing_length", C.c_double),
-                ("mixing_length_Prt", C.c_double), ("mixing_length_bulk_mult", C.c_double)]
+                ("mixing_length_Prt", C.c_double), ("mixing_length_bulk_mult", C.c_double), ("lte", C.POINTER(LteTables))]
 
     def with_mixing_length(self, max_mixing_length, pr_ratio=1.0, bulk_multiplier=0.0):
         """flow/useMixingLength = True with mixing-length/{max-mixing-length, Pr_ratio, bulk-multiplier}."""
@@ -156,6 +180,14 @@ class Physics(C.Structure):
             for d in range(3):
                 ph.sponge_normal[d], ph.sponge_point[d] = float(sponge[0][d]), float(sponge[1][d])
             ph.sponge_ratio, ph.sponge_width = float(sponge[2]), float(sponge[3])
+        return ph
+
+    @classmethod
+    def lte_fluid(cls, tables, eq_system=1):
+        """fluid = LTE_FLUID with 1-D look-up tables (LteTables.make), kept alive on the returned object."""
+        ph = cls(eq_system, 2, 1.4, 287.058, 1.0, 0.0, 1.458e-6, 110.4, 0.71, None, 0)
+        ph.lte = C.pointer(tables)
+        ph._tables = tables
         return ph
 
     @classmethod

@@ -13,6 +13,97 @@ namespace tpsb {
 constexpr int GEN_MAXEQ = 12;  // gpudata::MAXEQUATIONS of the reference's CUDA build (src/dataStructures.hpp:52)
 constexpr int GEN_MAXDIM = 3;
 
+// LteMixture / LteTransport over 1-D linear tables (flow/lte/table_dim = 1: lte_mixture.cpp, lte_transport_properties.cpp,
+// LinearTable table.cpp:52-116): one species, one temperature; energy, gas constant, speed of sound, viscosity and
+// conductivity are functions of T alone.  Tables live in one device pool: x[n] | a[n-1] | b[n-1] per table.
+constexpr int LTE_E = 0, LTE_R = 1, LTE_C = 2, LTE_T = 3, LTE_MU = 4, LTE_KAPPA = 5, LTE_NEC = 6, LTE_NTAB = 7;
+struct LteParams {
+  int n[LTE_NTAB];  // rows; n[LTE_NEC] == 0: no radiation
+  int xlog[LTE_NTAB], flog[LTE_NTAB];
+  const double *x[LTE_NTAB];
+};
+// TableInterpolator::findInterval + LinearTable::eval / eval_x (table.cpp:52-116)
+__host__ __device__ __forceinline__ int lte_interval(const LteParams &L, int t, double xEval) {
+  const int n = L.n[t];
+  const double *x = L.x[t];
+  int count = n, first = 0;
+  while (count > 0) {  // std::upper_bound
+    int it = first;
+    const int step = count / 2;
+    it += step;
+    if (xEval > x[it]) {
+      first = ++it;
+      count -= step + 1;
+    } else {
+      count = step;
+    }
+  }
+  first = first < n - 1 ? first : n - 1;
+  first = first > 1 ? first : 1;
+  return first - 1;
+}
+__host__ __device__ __forceinline__ double lte_eval(const LteParams &L, int t, double xEval) {
+  const int i = lte_interval(L, t, xEval), n = L.n[t];
+  const double *ta = L.x[t] + n, *tb = ta + (n - 1);
+  const double xt = L.xlog[t] ? log(xEval) : xEval;
+  double ft = ta[i] + tb[i] * xt;
+  if (L.flog[t]) ft = exp(ft);
+  return ft;
+}
+__host__ __device__ __forceinline__ double lte_eval_x(const LteParams &L, int t, double xEval) {
+  const int i = lte_interval(L, t, xEval), n = L.n[t];
+  const double *ta = L.x[t] + n, *tb = ta + (n - 1);
+  const double xt = L.xlog[t] ? log(xEval) : xEval;
+  const double xt_xt = L.xlog[t] ? 1. / xEval : 1.0;
+  double ft_x = tb[i] * xt_xt;
+  if (L.flog[t]) ft_x *= exp(ta[i] + tb[i] * xt);
+  return ft_x;
+}
+// LteMixture::ComputeTemperatureInternal (lte_mixture.cpp:161-223): Newton on e(T) = e(U) from the T(e) table's guess
+__host__ __device__ __forceinline__ double lte_temperature(const LteParams &L, int nvel, const double *state) {
+  const double rho = state[0];
+  double den_vel2 = 0;
+  for (int d = 0; d < nvel; d++) den_vel2 += state[d + 1] * state[d + 1];
+  den_vel2 /= rho;
+  const double energy = (state[1 + nvel] - 0.5 * den_vel2) / rho;
+  double T = lte_eval(L, LTE_T, energy);
+  double res = energy - lte_eval(L, LTE_E, T);
+  const double res0 = fabs(res);
+  const double atol = 1e-18, rtol = 1e-12, dT_atol = 1e-12, dT_rtol = 1e-8;
+  bool converged = ((fabs(res) < atol) || (fabs(res) / fabs(res0) < rtol));
+  int niter = 0;
+  while (!converged && (niter < 20)) {
+    const double dedT = lte_eval_x(L, LTE_E, T);
+    const double dT = res / dedT;
+    T += dT;
+    res = energy - lte_eval(L, LTE_E, T);
+    converged = ((fabs(res) < atol) || (fabs(res) / res0 < rtol) || (fabs(dT) < dT_atol) || (fabs(dT) / T < dT_rtol));
+    niter++;
+  }
+  return T;
+}
+// LteMixture::ComputeTemperatureFromDensityPressure (lte_mixture.cpp:241-305): Newton on p = rho R(T) T from T = p / (208 rho)
+__host__ __device__ __forceinline__ double lte_temperature_rho_p(const LteParams &L, double rho, double p) {
+  double T = p / (rho * 208.);
+  double R = lte_eval(L, LTE_R, T);
+  double res = p - rho * R * T;
+  const double res0 = fabs(res);
+  const double atol = 1e-18, rtol = 1e-12, dT_atol = 1e-12, dT_rtol = 1e-8;
+  bool converged = ((fabs(res) < atol) || (fabs(res) / fabs(res0) < rtol));
+  int niter = 0;
+  while (!converged && (niter < 20)) {
+    const double R_T = lte_eval_x(L, LTE_R, T);
+    const double dpdT = rho * R + rho * R_T * T;
+    const double dT = res / dpdT;
+    T += dT;
+    R = lte_eval(L, LTE_R, T);
+    res = p - rho * R * T;
+    converged = ((fabs(res) < atol) || (fabs(res) / res0 < rtol) || (fabs(dT) < dT_atol) || (fabs(dT) / T < dT_rtol));
+    niter++;
+  }
+  return T;
+}
+
 struct GenPhys {
   int dim, nvel, neq;
   int use_roe;           // flow/useRoe (2-D dry air): Eval_Roe unless a caller forces Lax-Friedrichs
@@ -23,10 +114,17 @@ struct GenPhys {
   // flow/useMixingLength for dry air (mixtures carry it in MixParams): MixingLengthTransport (mixing_length_transport.cpp)
   int ml_on;
   double ml_max, ml_prt, ml_bulk;
+  // LTE_FLUID with 1-D tables: fluid stays 0 (one species, the dry-air code structure) and every equation-of-state /
+  // transport evaluation below switches to the tables
+  const LteParams *lte;
 };
 
 // DryAir::ComputePressure (equation_of_state.hpp:610-617)
 __host__ __device__ __forceinline__ double dry_gen_pressure(const GenPhys &g, const double *s) {
+  if (g.lte) {  // LteMixture::ComputePressure (lte_mixture.cpp:123-135)
+    const double T = lte_temperature(*g.lte, g.nvel, s);
+    return s[0] * lte_eval(*g.lte, LTE_R, T) * T;
+  }
   double den_vel2 = 0;
   for (int d = 0; d < g.nvel; d++) den_vel2 += s[d + 1] * s[d + 1];
   den_vel2 /= s[0];
@@ -38,7 +136,8 @@ __host__ __device__ __forceinline__ void dry_gen_prim(const GenPhys &g, const do
   double den_vel2 = 0;
   for (int d = 0; d < g.nvel; d++) den_vel2 += s[d + 1] * s[d + 1];
   den_vel2 /= s[0];
-  const double T = g.dry.gm1 / g.dry.R * (s[1 + g.nvel] - 0.5 * den_vel2) / s[0];
+  const double T = g.lte ? lte_temperature(*g.lte, g.nvel, s)  // LteMixture::GetPrimitivesFromConservatives (:319-330)
+                         : g.dry.gm1 / g.dry.R * (s[1 + g.nvel] - 0.5 * den_vel2) / s[0];
   for (int eq = 0; eq < g.neq; eq++) up[eq] = s[eq];
   for (int d = 0; d < g.nvel; d++) up[1 + d] = s[1 + d] / s[0];
   up[1 + g.nvel] = T;
@@ -50,6 +149,8 @@ __host__ __device__ __forceinline__ double dry_gen_max_char_speed(const GenPhys 
   double den_vel2 = 0;
   for (int d = 0; d < g.nvel; d++) den_vel2 += s[d + 1] * s[d + 1];
   den_vel2 /= den;
+  if (g.lte)  // LteMixture::ComputeMaxCharSpeed / ComputeSpeedOfSound (lte_mixture.cpp:366-401)
+    return sqrt(den_vel2 / den) + lte_eval(*g.lte, LTE_C, lte_temperature(*g.lte, g.nvel, s));
   const double pres = g.dry.gm1 * (s[1 + g.nvel] - 0.5 * den_vel2);
   return sqrt(den_vel2 / den) + sqrt(g.dry.gamma * pres / den);
 }
@@ -67,6 +168,23 @@ __host__ __device__ __forceinline__ void dry_gen_conv_flux(const GenPhys &g, con
   for (int d = 0; d < g.dim; d++) f[1 + g.nvel + d * neq] = s[d + 1] * H;
 }
 
+// DryAirTransport::ComputeFluxMolecularTransport (transport_properties.cpp:223-234: Sutherland viscosity, bulk and Prandtl
+// conductivity) or LteTransport::ComputeFluxMolecularTransport (lte_transport_properties.cpp:86-108: tables, no bulk viscosity)
+__host__ __device__ __forceinline__ void dry_gen_transport(const GenPhys &g, const double *s, double &visc, double &bulk, double &k) {
+  if (g.lte) {
+    const double T = lte_temperature(*g.lte, g.nvel, s);
+    visc = lte_eval(*g.lte, LTE_MU, T);
+    k = lte_eval(*g.lte, LTE_KAPPA, T);
+    bulk = 0.0;
+    return;
+  }
+  const double pr = dry_gen_pressure(g, s);
+  const double temp = pr / g.dry.R / s[0];
+  visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
+  bulk = g.dry.bulk_visc_mult * visc;
+  k = g.dry.cp_div_pr * visc;
+}
+
 // Fluxes::ComputeViscousFluxes (fluxes.cpp:178-335) with DryAirTransport (transport_properties.cpp:223-234);
 // no SGS, no sponge.  gr[eq + d*neq] = d Up_eq / d x_d; radius = x[0] of the point (axisymmetric terms only).
 // Written with fixed 3x3 register tiles and guards instead of run-time-indexed local arrays (entries beyond
@@ -80,11 +198,8 @@ __host__ __device__ __forceinline__ void dry_gen_visc_flux(const GenPhys &g, con
   const int neq = g.neq, dim = g.dim;
   for (int i = 0; i < neq * dim; i++) f[i] = 0.;
   if (g.dry.eq_system == 0) return;
-  const double pr = dry_gen_pressure(g, s);
-  const double temp = pr / g.dry.R / s[0];
-  double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
-  double bulk = g.dry.bulk_visc_mult * visc;
-  double k = g.dry.cp_div_pr * visc;
+  double visc, bulk, k;
+  dry_gen_transport(g, s, visc, bulk, k);
   if (g.ml_on) mixlen_add(dim, g.nvel, neq, g.ml_max, g.ml_prt, g.ml_bulk, s, gr, radius, distance, visc, bulk, k);
   bulk -= 2. / 3. * visc;
   if (ax && (g.dry.sgs_model | g.dry.sponge)) dry_modify_transport(g.dry, s[0], gr + 1, neq, *ax, visc, bulk, k);
@@ -143,11 +258,8 @@ __host__ __device__ __forceinline__ void dry_gen_bdr_visc_flux(const GenPhys &g,
   const int neq = g.neq, dim = g.dim, nvel = g.nvel;
   for (int eq = 0; eq < neq; eq++) nf[eq] = 0.;
   if (g.dry.eq_system == 0) return;
-  const double pr = dry_gen_pressure(g, s);
-  const double temp = pr / g.dry.R / s[0];
-  double visc = (g.dry.C1 * g.dry.visc_mult * (temp * sqrt(temp)) / (temp + g.dry.S0));
-  double bulk = g.dry.bulk_visc_mult * visc;
-  double k = g.dry.cp_div_pr * visc;
+  double visc, bulk, k;
+  dry_gen_transport(g, s, visc, bulk, k);
   bulk -= 2. / 3. * visc;
   if (ax && (g.dry.sgs_model | g.dry.sponge)) dry_modify_transport(g.dry, s[0], gr + 1, neq, *ax, visc, bulk, k);  // fluxes.cpp:386-407
   double gu[3][3], st[3][3], nn[3];
@@ -220,6 +332,7 @@ __host__ __device__ __forceinline__ double gen_pressure(const GenPhys &g, const 
 }
 // GasMixture::ComputePressureFromPrimitives (equation_of_state.cpp:360-364, 988-1010)
 __host__ __device__ __forceinline__ double gen_pressure_from_prim(const GenPhys &g, const double *up) {
+  if (g.lte) return up[0] * lte_eval(*g.lte, LTE_R, up[1 + g.nvel]) * up[1 + g.nvel];  // lte_mixture.cpp:142-151
   return g.fluid ? mix_pressure_from_prim(*g.mix, up) : g.dry.R * up[0] * up[1 + g.nvel];
 }
 // TransportProperties::GetViscosities (transport_properties.hpp:264-269, 305-309): visc[0] shear, visc[1] bulk
@@ -228,6 +341,11 @@ __host__ __device__ __forceinline__ void gen_viscosities(const GenPhys &g, const
     mix_viscosities(*g.mix, U, up, visc);
   } else {
     const double temp = up[1 + g.nvel];
+    if (g.lte) {  // LteTransport::GetViscosities (lte_transport_properties.cpp:125-136)
+      visc[0] = lte_eval(*g.lte, LTE_MU, temp);
+      visc[1] = 0.;
+      return;
+    }
     visc[0] = (g.dry.C1 * g.dry.visc_mult * pow(temp, 1.5) / (temp + g.dry.S0));
     visc[1] = g.dry.bulk_visc_mult * visc[0];
   }
@@ -243,13 +361,16 @@ __host__ __device__ __forceinline__ void gen_cons(const GenPhys &g, const double
       v2 += up[1 + d] * up[1 + d];
       U[1 + d] *= up[0];
     }
-    U[1 + g.nvel] = g.dry.R * up[0] * up[1 + g.nvel] / g.dry.gm1 + 0.5 * up[0] * v2;
+    if (g.lte)  // LteMixture::GetConservativesFromPrimitives (lte_mixture.cpp:337-359)
+      U[1 + g.nvel] = up[0] * (lte_eval(*g.lte, LTE_E, up[1 + g.nvel]) + 0.5 * v2);
+    else
+      U[1 + g.nvel] = g.dry.R * up[0] * up[1 + g.nvel] / g.dry.gm1 + 0.5 * up[0] * v2;
   }
 }
 // GasMixture::computeStagnationState (equation_of_state.cpp:100-116; DryAir :367-377)
 __host__ __device__ __forceinline__ void gen_stagnation_state(const GenPhys &g, const double *in, double *out) {
   for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];
-  if (g.fluid) {
+  if (g.fluid || g.lte) {  // LteMixture keeps the base-class version
     double ke = 0.0;
     for (int d = 0; d < g.nvel; d++) ke += 0.5 * in[1 + d] * in[1 + d] / in[0];
     for (int d = 0; d < g.nvel; d++) out[1 + d] = 0.;
@@ -267,7 +388,8 @@ __host__ __device__ __forceinline__ void gen_stagnant_state_with_temp(const GenP
   } else {
     for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];
     for (int d = 0; d < g.nvel; d++) out[1 + d] = 0.;
-    out[1 + g.nvel] = g.dry.R / g.dry.gm1 * in[0] * T;
+    out[1 + g.nvel] = g.lte ? in[0] * lte_eval(*g.lte, LTE_E, T)  // lte_mixture.cpp:430-446
+                            : g.dry.R / g.dry.gm1 * in[0] * T;
   }
 }
 // GasMixture::modifyEnergyForPressure (DryAir :402-411, PerfectMixture :1698-1741); in and out may alias
@@ -279,8 +401,12 @@ __host__ __device__ __forceinline__ void gen_modify_energy_for_pressure(const Ge
     double ke = 0.;
     for (int d = 0; d < g.nvel; d++) ke += in[1 + d] * in[1 + d];
     ke *= 0.5 / in[0];
+    const double rho = in[0];
     for (int eq = 0; eq < g.neq; eq++) out[eq] = in[eq];
-    out[1 + g.nvel] = p / g.dry.gm1 + ke;
+    if (g.lte)  // LteMixture::modifyEnergyForPressure (lte_mixture.cpp:453-470)
+      out[1 + g.nvel] = rho * lte_eval(*g.lte, LTE_E, lte_temperature_rho_p(*g.lte, rho, p)) + ke;
+    else
+      out[1 + g.nvel] = p / g.dry.gm1 + ke;
   }
 }
 __host__ __device__ __forceinline__ int gen_num_active_species(const GenPhys &g) { return g.fluid ? g.mix->numActive : 0; }

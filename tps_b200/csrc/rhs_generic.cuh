@@ -897,6 +897,15 @@ __global__ void gen_point_eval_kernel(GenArgs a, int which, int n, const double 
   }
 }
 
+// SourceTerm::updateTerms for the LTE fluid (one species, no reactions): the net-emission radiative sink
+// -4 pi eps_N(T) on the total energy (source_term.cpp:205-207, radiation.hpp:57-70), T the nodal primitive of this evaluation
+__global__ void gen_lte_source_kernel(GenArgs a) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  const double Th = a.Up[n + static_cast<long long>(1 + a.nvel) * a.N];
+  a.y[n + static_cast<long long>(1 + a.nvel) * a.N] += -4.0 * 3.14159265358979323846 * lte_eval(*a.phys.lte, LTE_NEC, Th);
+}
+
 // InletBC::updateMean / OutletBC::updateMean (inletBC.cpp:482-564, outletBC.cpp:470-561), called by every Mult after
 // the gradients (rhs_operator.cpp:364): sum of the primitives interpolated to the patch's face quadrature points, their
 // number and (for the first evaluation) the patch area; the first evaluation also initialises the boundary states with

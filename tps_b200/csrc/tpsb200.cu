@@ -110,6 +110,7 @@ struct tpsb_ctx {
   std::vector<GenNrPatch> nr_patches;
   std::vector<int> nr_attr;
   double bc_dt = 0.0;
+  bool lte_radiation = false;  // LTE fluid with a net-emission-coefficient table
   double *d_xiN3 = nullptr;  // [dof][3] reference coordinates of the nodes (3-D dry-air paths; the generic path has its own)
   bool forcing_needs_grad = false;
   long long launches = 0;
@@ -668,6 +669,42 @@ std::string create_generic(tpsb_ctx *c, const tpsb_mesh_maps *maps, const tpsb_s
       if (gbt.bc[i].nr >= 0) c->nr_attr.push_back(bcs->bcs[i].attr);
   }
   if (ce == cudaSuccess && !mixv.empty()) ce = g_upload(c, &g.phys.mix, mixv);
+  if (ce == cudaSuccess && phys->fluid == TPSB_LTE_FLUID) {
+    // LinearTable's constructor (table.cpp:76-87) on the host: per table x[n] | a[n-1] | b[n-1], one device pool
+    const tpsb_lte_tables &lt = *phys->lte;
+    struct Src { int n; const double *x, *f; int xlog, flog; };
+    const Src src[LTE_NTAB] = {{lt.num_thermo, lt.T, lt.energy, 0, 0}, {lt.num_thermo, lt.T, lt.R, 0, 0},
+                               {lt.num_thermo, lt.T, lt.c, 0, 0},      {lt.num_thermo, lt.energy, lt.T, 0, 0},
+                               {lt.num_trans, lt.T_trans, lt.mu, 0, 0}, {lt.num_trans, lt.T_trans, lt.kappa, 0, 0},
+                               {lt.nec_table_n, lt.nec_table_x, lt.nec_table_f, lt.nec_table_xlog, lt.nec_table_flog}};
+    std::vector<double> pool;
+    size_t off[LTE_NTAB];
+    LteParams L;
+    memset(&L, 0, sizeof(L));
+    for (int t = 0; t < LTE_NTAB; t++) {
+      off[t] = pool.size();
+      const int n = src[t].n;
+      L.n[t] = n, L.xlog[t] = src[t].xlog ? 1 : 0, L.flog[t] = src[t].flog ? 1 : 0;
+      if (n < 2) continue;
+      pool.insert(pool.end(), src[t].x, src[t].x + n);
+      std::vector<double> a(n - 1), b(n - 1);
+      for (int k = 0; k < n - 1; k++) {
+        const double *x = src[t].x, *f = src[t].f;
+        a[k] = L.flog[t] ? std::log(f[k]) : f[k];
+        const double df = L.flog[t] ? (std::log(f[k + 1]) - std::log(f[k])) : (f[k + 1] - f[k]);
+        b[k] = L.xlog[t] ? df / (std::log(x[k + 1]) - std::log(x[k])) : df / (x[k + 1] - x[k]);
+        a[k] -= L.xlog[t] ? b[k] * std::log(x[k]) : b[k] * x[k];
+      }
+      pool.insert(pool.end(), a.begin(), a.end());
+      pool.insert(pool.end(), b.begin(), b.end());
+    }
+    const double *d_pool = nullptr;
+    ce = g_upload(c, &d_pool, pool);
+    for (int t = 0; t < LTE_NTAB; t++) L.x[t] = d_pool + off[t];
+    c->lte_radiation = lt.nec_table_n >= 2;
+    std::vector<LteParams> lv(1, L);
+    if (ce == cudaSuccess) ce = g_upload(c, &g.phys.lte, lv);
+  }
   const size_t nb = static_cast<size_t>(g.N) * sizeof(double);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_Up, nb * g.neq);
   if (ce == cudaSuccess) ce = cudaMalloc(&c->d_gradUp, nb * g.neq * dim);
@@ -897,6 +934,26 @@ int tpsb_create(const tpsb_mesh_maps *maps, const tpsb_space_desc *space, const 
     const int nact = pm->ambipolar ? pm->num_species - 2 : pm->num_species - 1;
     if (space->num_equation != space->nvel + 2 + nact + (pm->two_temperature ? 1 : 0) || space->num_equation > GEN_MAXEQ)
       return fail(ctx, TPSB_EINVAL, "num_equation does not match the mixture (nvel + 2 + active species [+ 1 electron energy])");
+  } else if (phys->fluid == TPSB_LTE_FLUID) {
+    // LteMixture / LteTransport with 1-D tables (flow/lte/table_dim = 1, src/M2ulPhyS.cpp:175-258); the 2-D (GSL) tables are
+    // a CPU-only feature of the reference (src/M2ulPhyS.cpp:168-170)
+    const tpsb_lte_tables *lt = phys->lte;
+    if (!lt) return fail(ctx, TPSB_EINVAL, "fluid = lte needs tpsb_physics.lte");
+    if (lt->num_thermo < 2 || lt->num_thermo > 1000 || !lt->T || !lt->energy || !lt->R || !lt->c)
+      return fail(ctx, TPSB_EINVAL, "the LTE thermodynamic table needs 2..1000 rows of T, energy, R, c (gpudata::MAXTABLE)");
+    if (lt->num_trans < 2 || lt->num_trans > 1000 || !lt->T_trans || !lt->mu || !lt->kappa)
+      return fail(ctx, TPSB_EINVAL, "the LTE transport table needs 2..1000 rows of T, mu, kappa");
+    if (lt->nec_table_n != 0 && (lt->nec_table_n < 2 || lt->nec_table_n > 1000 || !lt->nec_table_x || !lt->nec_table_f))
+      return fail(ctx, TPSB_EINVAL, "the net-emission-coefficient table needs 2..1000 points");
+    for (int k = 1; k < lt->num_thermo; k++)
+      if (!(lt->T[k] > lt->T[k - 1]) || !(lt->energy[k] > lt->energy[k - 1]))
+        return fail(ctx, TPSB_EINVAL, "LTE tables: T and energy(T) must increase strictly (the e -> T table is the inverse)");
+    if (space->num_equation != space->nvel + 2) return fail(ctx, TPSB_EINVAL, "the LTE fluid has num_equation = nvel + 2");
+    if (phys->use_mixing_length || phys->sgs_model != 0 || phys->sponge_enabled)
+      return fail(ctx, TPSB_ENOTIMPL, "mixing length / SGS / viscous sponge with the LTE fluid are not built");
+    for (int i = 0; bcs && bcs->bcs && i < bcs->num_bcs; i++)
+      if (bcs->bcs[i].kind == TPSB_BC_WALL && bcs->bcs[i].type == 4)
+        return fail(ctx, TPSB_ENOTIMPL, "the general wall (VISC_GNRL) with the LTE fluid is not built");
   } else {
     return fail(ctx, TPSB_ENOTIMPL, "working fluid %d not built", phys->fluid);
   }
@@ -1928,6 +1985,10 @@ static int run_mult_generic(tpsb_ctx *ctx, const double *d_x, double *d_y) {
     else GEN_LAUNCH_RESID(0, 0, 0);
 #undef GEN_LAUNCH_RESID
   }
+  if (g.phys.lte && c->lte_radiation) {  // SourceTerm of the LTE fluid: the radiative sink only (source_term.cpp:205-207)
+    ProfScope ps(c, K_RESID);
+    gen_lte_source_kernel<<<static_cast<unsigned>((g.N + 127) / 128), 128, 0, c->stream>>>(g);
+  }
   if (g.phys.fluid) {  // forcing terms are added after Me^-1 (rhs_operator.cpp:451-461)
     ProfScope ps(c, K_RESID);
     gen_source_kernel<<<static_cast<unsigned>((g.N + 127) / 128), 128, 0, c->stream>>>(g, c->sol_view ? c->sol_view : d_x);
@@ -2306,6 +2367,8 @@ int tpsb_add_forcing(tpsb_ctx *ctx, const tpsb_forcing_desc *d) {
   CU(cudaSetDevice(c->device));
   const int dim = c->generic ? c->gen.dim : 3, nvel = c->generic ? c->gen.nvel : 3, neq = c->neq;
   const bool mixture = c->generic && c->gen.phys.fluid != 0;
+  if (c->generic && c->gen.phys.lte && d->kind != TPSB_FORCING_HEAT_SOURCE && d->kind != TPSB_FORCING_JOULE_HEATING)
+    return fail(ctx, TPSB_ENOTIMPL, "forcing kind %d with the LTE fluid is not built (its dry-air formulas read gamma and R)", d->kind);
   ForcingDev f;
   memset(&f, 0, sizeof(f));
   f.kind = d->kind;
