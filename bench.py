@@ -201,6 +201,142 @@ def workload_config(args, grid, sample_n=None):
     return cfg
 
 
+# BASELINE configs C1 / C3 / C4 at the reference's sizes on the generic tensor-product path (algorithmic
+# bytes per DOF-eval 64 / 336 / 616).  Single GPU; same JSON contract as the headline line.
+GENERIC_WORKLOADS = {
+    "c1": ("C1 mms.euler_2d: 2-D Euler, 160 x 160 periodic quadrilaterals (25 600), p = 2, Gauss-Lobatto nodes and rule", 64.0),
+    "c3": ("C3 mms.ternary_2d: 2-D ternary argon plasma (Ar+, e, Ar; two temperatures), collision-integral transport and "
+           "ionisation chemistry, 64 x 64 quadrilaterals, p = 3, Gauss-Legendre", 336.0),
+    "c4": ("C4 plasma.axisym type: axisymmetric six-species two-temperature argon, constant transport, inlet / outlet / "
+           "inviscid + isothermal walls, 40 x 40 quadrilaterals, p = 3", 616.0),
+}
+
+
+def run_generic_workload(args):
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import tps_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the RHS path has no CPU fallback")
+    torch.cuda.set_device(0)
+    t0 = time.perf_counter()
+    PI = np.pi
+    wl = args.workload
+    orc = None
+    if wl == "c1":
+        n = args.n if args.n != 96 else 160
+        m = tps_b200.cartesian_quad_mesh(n, n, lo=(0, 0), hi=(3.02, 3.02))
+        op = tps_b200.RhsOperator(m, order=2, physics=tps_b200.Physics.dry_air(0), basis_type=1, int_rule_type=1)
+        from test_gpu_generic_parity import _state2d
+        from common import node_coords_from_mesh  # noqa: F401
+        import oracle_api
+        orc = oracle_api.Oracle(2, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                                phys=oracle_api.dry_air_params(0), basis_type=1, int_rule=1)
+        U = _state2d(orc.node_coords() * (2 * PI / 3.02))
+        cpu_kind = "port"
+    else:
+        import axisym_cases as ac
+        import oracle_api
+        import plasma_cases as pc
+        if wl == "c3":
+            n = args.n if args.n != 96 else 64
+            m = tps_b200.cartesian_quad_mesh(n, n, lo=(-PI, -PI), hi=(PI, PI))
+            pm = tps_b200.PlasmaModels.from_dict(pc.argon_minimal_dict())
+            op = tps_b200.RhsOperator(m, order=3, physics=tps_b200.Physics.plasma_mixture(pm, 1), nvel=2)
+            orc = oracle_api.Oracle(3, m["elem_xyz"], m["face_el1"], m["face_el2"], m["face_inf1"], m["face_inf2"],
+                                    phys=oracle_api.mixture_params(pm, 1), kind="ref", neq=op.neq, nvel=2)
+            up = pc.hot_primitives(orc.node_coords())
+        else:
+            n = args.n if args.n != 96 else 40
+            m = ac.box(n=(n, n), warp=0.05)
+            op, orc = ac.make_pair(m, 3, 1, 0, 0, 3, "c4", True, mixture=ac.argon6_dict())
+            up = ac.argon6_primitives(orc.node_coords(), 3)
+        U = np.ascontiguousarray(orc.pt("cons", up).T).reshape(-1)
+        cpu_kind = "reference"
+    setup_s = time.perf_counter() - t0
+    N, neq = op.N, op.neq
+    x = torch.from_numpy(U).cuda()
+    y = torch.empty_like(x)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    flush = torch.empty(160 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2: these states are tiny
+    for _ in range(warmup):
+        op.Mult(x, y)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = op.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        flush.fill_(1.0)
+        e0.record()
+        op.Mult(x, y)
+        e1.record()
+    torch.cuda.synchronize()
+    launches = op.launch_count() - l0
+    clocks = sampler.stop()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / steps
+    value = N / (ms * 1e-3)
+    op.set_profiling(True)
+    op.kernel_times()
+    for _ in range(3):
+        op.Mult(x, y)
+    kt = {k: v[0] / 3 for k, v in op.kernel_times().items() if v[1] > 0}
+    op.set_profiling(False)
+    # parity of this very evaluation against the oracle (the sizes are small enough)
+    yo = orc.mult(U)
+    yd = y.cpu().numpy()
+    err = max(float(np.linalg.norm(yd[k * N:(k + 1) * N] - yo[k * N:(k + 1) * N]) / max(np.linalg.norm(yo[k * N:(k + 1) * N]), 1e-300))
+              for k in range(neq))
+    # CPU beside it: the oracle on the same mesh (reference physics object code for the plasma cases), all host threads
+    tc = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - tc < 10.0 and reps < 50:
+        orc.mult(U)
+        reps += 1
+    cpu_s = (time.perf_counter() - tc) / reps
+    # end to end: host buffers through tpsb_rhs_mult_host
+    hx, hy = torch.from_numpy(U).pin_memory(), torch.empty(U.shape, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        op.mult_host(hx, hy)
+    te = time.perf_counter()
+    e2e_steps = 10
+    for _ in range(e2e_steps):
+        op.mult_host(hx, hy)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - te) / e2e_steps * 1e3
+    peak, peak_src = peaks()
+    desc, bytes_per_dof = GENERIC_WORKLOADS[wl]
+    dom = max(kt, key=kt.get) if kt else "elem_resid"
+    out = {"metric": "rhs_dof_evals_per_s", "value": value, "unit": "DOF-evals/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": desc, "elements": int(op.NE), "order": int(3 if wl != "c1" else 2), "num_equation": int(neq),
+                      "l2_policy": "160 MB buffer written between timed evaluations (the state fits in L2)"},
+           "roofline": {"bound": "hbm", "kernel": "gen_resid_kernel" if dom == "elem_resid" else "gen_grad_kernel", "timer_class": dom,
+                        "achieved": bytes_per_dof * value / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_per_dof * value / 1e9 / peak,
+                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_dof": bytes_per_dof,
+                        "kernel_ms_per_step": kt,
+                        "note": "whole-step figure on BASELINE.md section 3's bytes per DOF-eval; these configurations are bound by "
+                                "per-point physics and dependent latency at one CTA per element, not by HBM"},
+           "cpu_baseline": {"value": N / cpu_s, "unit": "DOF-evals/s", "cores": os.cpu_count(), "kind": cpu_kind,
+                            "sample": f"the same mesh and state, {reps} evaluations of {cpu_s:.3f} s (oracle with "
+                                      + ("the reference's physics object code" if cpu_kind == "reference" else "the restated dry-air physics") + ")"},
+           "clocks": clocks,
+           "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "DOF-evals/s", "h2d_bytes_per_step": int(U.nbytes), "d2h_bytes_per_step": int(U.nbytes),
+                   "steps": e2e_steps, "api": "tpsb_rhs_mult_host (pinned host x -> device, Mult, y -> pinned host)"},
+           "gpu_launches": int(launches), "finite": bool(np.isfinite(yd).all()), "setup_s": setup_s, "dofs_per_gpu": int(N),
+           "path": op.path(), "parity_vs_oracle_rel_l2": err}
+    if not (err < 1e-9):
+        raise SystemExit(f"--workload {wl}: device result differs from the oracle ({err:.3e})")
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,7 +353,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partitioner", default="metis", choices=["metis", "rcb"], help="element partition of --workload cyl3d at N > 1")
     ap.add_argument("--no-verify", action="store_true", help="skip the N-rank == 1-rank checksum comparison at N > 1")
-    ap.add_argument("--workload", default="tgv", choices=["tgv", "cyl3d"],
+    ap.add_argument("--workload", default="tgv", choices=["tgv", "cyl3d", "c1", "c3", "c4"],
                     help="tgv: BASELINE config C5 (the headline line); cyl3d: config C2 restated on a hex O-grid "
                          "(general trilinear path + boundary conditions), single GPU, development measurement")
     args = ap.parse_args()
@@ -229,6 +365,11 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload in ("c1", "c3", "c4"):
+        if world > 1:
+            raise SystemExit("--workload c1 / c3 / c4 are single-GPU lines (multi-rank parity of the generic path: tests/multirank_generic_worker.py)")
+        run_generic_workload(args)
         return
 
     # the JSON line must be the only thing on stdout: libraries (NCCL prints its version banner there) write to
