@@ -75,7 +75,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.lines, self.mark_at = device, None, [], 0
+
+    def mark(self):
+        """start of the timed region: nvidia-smi needs a few hundred ms to come up, so it is started before the warm-up and
+        only the samples taken after this mark are reported"""
+        self.mark_at = len(self.lines)
 
     def start(self):
         try:
@@ -102,7 +107,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = self.lines[self.mark_at:]
+        in_region = len(window) > 0
+        if not in_region:  # a timed region shorter than the sampling period: the warm-up samples (same load) stand in
+            window = self.lines[-4:]
+        for ln in window:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -115,7 +124,7 @@ class ClockSampler:
                 if f[3 + k] == "Active":
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": "timed region" if in_region else "warm-up (same load)"}
 
 
 def cpu_baseline(n, nthreads, evals=3, eq=1, target_s=12.0):
@@ -225,6 +234,8 @@ def run_generic_workload(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the RHS path has no CPU fallback")
     torch.cuda.set_device(0)
+    sampler = ClockSampler(0)
+    sampler.start()
     t0 = time.perf_counter()
     PI = np.pi
     wl = args.workload
@@ -268,8 +279,7 @@ def run_generic_workload(args):
     for _ in range(warmup):
         op.Mult(x, y)
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler.mark()
     l0 = op.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for e0, e1 in evs:
@@ -388,6 +398,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the RHS path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)  # started now: nvidia-smi takes a few hundred ms to deliver its first sample
+    if rank == 0:
+        sampler.start()
     if world not in PROC_GRID:
         raise SystemExit(f"unsupported world size {world}")
     grid = PROC_GRID[world]
@@ -503,11 +516,9 @@ def main():
         op.Mult(U, Y)
     barrier()
     l0 = op.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record()
     for _ in range(args.steps):
         op.Mult(U, Y)
