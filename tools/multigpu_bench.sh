@@ -4,8 +4,12 @@
 N=$1
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 run 29618 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
-run 29619 bench.py --gpus $N --steps 10 --warmup 3 --workload cyl3d --elems 48 > gpurun_out/r2_bench_cyl3d_n$N.json 2> gpurun_out/r2_bench_cyl3d_n$N.err
-for f in gpurun_out/r2_bench_n$N.json gpurun_out/r2_bench_cyl3d_n$N.json; do python - "$f" <<'PY'
+FILES=gpurun_out/r2_bench_n$N.json
+if [ "$2" != "tgv" ]; then
+  run 29619 bench.py --gpus $N --steps 10 --warmup 3 --workload cyl3d --elems 48 > gpurun_out/r2_bench_cyl3d_n$N.json 2> gpurun_out/r2_bench_cyl3d_n$N.err
+  FILES="$FILES gpurun_out/r2_bench_cyl3d_n$N.json"
+fi
+for f in $FILES; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

@@ -1703,13 +1703,17 @@ static void grad_trace(tpsb_ctx *c, const KernelArgs &a, int begin, int count, c
     launch_grad_trace<2, 16, 4>(c, a, begin, count, list);
   }
 }
+static int comm_grain();
 template <int WPB, int MINB>
 static void launch_face_mma(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (count <= 0) return;
   ProfScope ps(c, K_FACE);
   int grid = (count + WPB - 1) / WPB;
   const int cap = c->num_sms * MINB;
-  if (grid > cap) grid = cap;
+  if (grid > cap) {
+    const int g = comm_grain();  // partitioned runs: warps retire after g faces so the exchange kernels get SM slots
+    grid = (c->NEH > 0 && g > 0) ? std::max(cap, (count + WPB * g - 1) / (WPB * g)) : cap;
+  }
   const size_t smem = face_mma_smem_bytes(WPB);
   static bool attr_set[MAX_DEV] = {};  // per instantiation and device
   if (!attr_set[c->device]) {
@@ -1785,6 +1789,15 @@ static int run_gradients_fast(tpsb_ctx *ctx, const KernelArgs &a, bool prims_don
 
 static void resid(tpsb_ctx *c, const KernelArgs &a, int begin, int count);
 
+// Partitioned runs: a persistent grid that fills every SM keeps the NCCL send / receive kernels of the overlapped exchange
+// out until it drains -- stream priority does not preempt resident CTAs -- so the "overlapped" exchange ran after the
+// interior kernel (0.8 ms of idle stream per evaluation at 8 ranks).  With a halo the element and face kernels therefore use
+// CTAs that retire after `grain` elements (faces per warp), which frees SM slots every few tens of microseconds.
+// TPSB_COMM_GRAIN=0 restores the persistent grids.
+static int comm_grain() {
+  static const int g = getenv("TPSB_COMM_GRAIN") ? std::max(0, atoi(getenv("TPSB_COMM_GRAIN"))) : 8;
+  return g;
+}
 // ---- fused fast path (rhs_fused.cuh) ----
 static void elem_fused(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list, int mode) {
   if (count <= 0) return;
@@ -1797,7 +1810,9 @@ static void elem_fused(tpsb_ctx *c, const KernelArgs &a, int begin, int count, c
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[c->device], elem_fused_kernel<REGS>, 64, 0);               \
       if (per_sm[c->device] < 1) per_sm[c->device] = 1;                                                                \
     }                                                                                                                  \
-    elem_fused_kernel<REGS><<<std::min(count, c->num_sms * per_sm[c->device]), 64, 0, c->stream>>>(a, begin, count, list, mode); \
+    int grid = std::min(count, c->num_sms * per_sm[c->device]);                                                       \
+    if (c->NEH > 0 && comm_grain() > 0) grid = std::min(count, std::max(grid, (count + comm_grain() - 1) / comm_grain())); \
+    elem_fused_kernel<REGS><<<grid, 64, 0, c->stream>>>(a, begin, count, list, mode);                                  \
   } while (0)
   switch (c->tune[0]) {
     case 1: FUSED_LAUNCH(96); break;
