@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--n", "--elems", dest="n", type=int, default=96,
                     help="elements per direction per GPU (--elems: the spelling torchrun does not mistake for its own --n* flags)")
     ap.add_argument("--cpu-n", type=int, default=20, help="elements per direction of the CPU-baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--strong", type=int, default=0, metavar="G",
                     help="strong scaling: a fixed global G^3 box split over the ranks (SURVEY.md 8d: 128); "
                          "default 0 = weak scaling with --n elements per direction per GPU")
@@ -633,7 +633,8 @@ def main():
         hx = torch.empty(5 * N, dtype=torch.float64, pin_memory=True)
         hy = torch.empty(5 * N, dtype=torch.float64, pin_memory=True)
         hx.copy_(U)
-        op.mult_host(hx, hy)
+        for _ in range(3):  # warm-up: pinned pages touched, copy streams and the chunk schedule's events created
+            op.mult_host(hx, hy)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):

@@ -133,3 +133,29 @@ def test_refusals(lib_built):
     with pytest.raises(tps_b200.TpsbError, match="increase strictly"):
         tps_b200.RhsOperator(m, order=2, physics=tps_b200.Physics.lte_fluid(bad), nvel=2, face_attr=m["face_attr"],
                              bcs=[tps_b200.BcDesc.make(*b) for b in WALLS])
+
+
+def test_ideal_gas_tables_reproduce_the_dry_air_operator_on_the_device(lib_built):
+    """no oracle involved: the device's LTE path over tables that describe a calorically perfect gas against the device's own
+    dry-air path (Euler, so the only interpolation error is the tabulated sound speed: 1000 points over 250 K, 2e-8)"""
+    import torch
+    from test_cpu_nr_lte_oracle import ideal_gas_tables
+    m = ac.box(warp=0.05)
+    specs = ac.bcs("c4", 2)
+    kw = dict(order=3, nvel=2, face_attr=m["face_attr"], use_bc_in_grad=False, bcs=[tps_b200.BcDesc.make(*b) for b in specs])
+    lte = tps_b200.RhsOperator(m, physics=tps_b200.Physics.lte_fluid(ideal_gas_tables(), 0), **kw)
+    dry = tps_b200.RhsOperator(m, physics=tps_b200.Physics.dry_air(0), **kw)
+    assert lte.path() == "generic" and dry.path() == "generic"
+    from common import node_coords_from_mesh  # noqa: F401
+    N = dry.N
+    rng = np.random.default_rng(5)
+    rho = 1.2 + 0.05 * rng.uniform(-1, 1, N)
+    u, v = 20 + 5 * rng.uniform(-1, 1, N), 8 + 5 * rng.uniform(-1, 1, N)
+    p = 101300 + 800 * rng.uniform(-1, 1, N)
+    U = np.concatenate([rho, rho * u, rho * v, p / 0.4 + 0.5 * rho * (u * u + v * v)])
+    x = torch.from_numpy(U).cuda()
+    yl, yd = lte.Mult(x).cpu().numpy(), dry.Mult(x).cpu().numpy()
+    assert rel_l2(lte.fields()[0].cpu().numpy(), dry.fields()[0].cpu().numpy()) < 1e-13
+    for k in range(4):
+        assert rel_l2(yl[k * N:(k + 1) * N], yd[k * N:(k + 1) * N]) < 2e-8, k
+    assert abs(lte.max_char_speed() / dry.max_char_speed() - 1) < 3e-8

@@ -1704,6 +1704,7 @@ static void grad_trace(tpsb_ctx *c, const KernelArgs &a, int begin, int count, c
   }
 }
 static int comm_grain();
+static int face_grain();
 template <int WPB, int MINB>
 static void launch_face_mma(tpsb_ctx *c, const KernelArgs &a, int begin, int count) {
   if (count <= 0) return;
@@ -1711,8 +1712,8 @@ static void launch_face_mma(tpsb_ctx *c, const KernelArgs &a, int begin, int cou
   int grid = (count + WPB - 1) / WPB;
   const int cap = c->num_sms * MINB;
   if (grid > cap) {
-    const int g = comm_grain();  // partitioned runs: warps retire after g faces so the exchange kernels get SM slots
-    grid = (c->NEH > 0 && g > 0) ? std::max(cap, (count + WPB * g - 1) / (WPB * g)) : cap;
+    const int g = c->NEH > 0 ? comm_grain() : face_grain();  // partitioned runs: warps retire after g faces so the exchange kernels get SM slots
+    grid = g > 0 ? std::max(cap, (count + WPB * g - 1) / (WPB * g)) : cap;
   }
   const size_t smem = face_mma_smem_bytes(WPB);
   static bool attr_set[MAX_DEV] = {};  // per instantiation and device
@@ -1798,6 +1799,19 @@ static int comm_grain() {
   static const int g = getenv("TPSB_COMM_GRAIN") ? std::max(0, atoi(getenv("TPSB_COMM_GRAIN"))) : 8;
   return g;
 }
+// Single-rank runs: CTAs of the element kernel that retire after 32 elements are also 3-5 % faster than one persistent CTA
+// per resident slot (96^3: 5.38 against 5.65 ms; grains 4 / 8 / 16 / 32 / 64 / 128 / 256 measured: 5.63 / 5.52 / 5.48 / 5.38 /
+// 5.46 / 5.57 / 5.72 ms) -- the resident CTAs drift out of phase instead of hitting the DMMA, shared-memory and load phases
+// together, and the tail is one short CTA instead of the slowest of 1184 long ones.  0 = persistent.
+static int elem_grain() {
+  static const int g = getenv("TPSB_ELEM_GRAIN") ? std::max(0, atoi(getenv("TPSB_ELEM_GRAIN"))) : 32;
+  return g;
+}
+// the same for the face kernel (faces per warp): 0 / 4 / 8 / 16 / 32 / 64 -> 3.904 / 4.009 / 3.913 / 3.862 / 3.853 / 3.879 ms
+static int face_grain() {
+  static const int g = getenv("TPSB_FACE_GRAIN") ? std::max(0, atoi(getenv("TPSB_FACE_GRAIN"))) : 32;
+  return g;
+}
 // ---- fused fast path (rhs_fused.cuh) ----
 static void elem_fused(tpsb_ctx *c, const KernelArgs &a, int begin, int count, const int *list, int mode) {
   if (count <= 0) return;
@@ -1811,7 +1825,8 @@ static void elem_fused(tpsb_ctx *c, const KernelArgs &a, int begin, int count, c
       if (per_sm[c->device] < 1) per_sm[c->device] = 1;                                                                \
     }                                                                                                                  \
     int grid = std::min(count, c->num_sms * per_sm[c->device]);                                                       \
-    if (c->NEH > 0 && comm_grain() > 0) grid = std::min(count, std::max(grid, (count + comm_grain() - 1) / comm_grain())); \
+    const int grain = c->NEH > 0 ? comm_grain() : elem_grain();                                                       \
+    if (grain > 0) grid = std::min(count, std::max(grid, (count + grain - 1) / grain));                               \
     elem_fused_kernel<REGS><<<grid, 64, 0, c->stream>>>(a, begin, count, list, mode);                                  \
   } while (0)
   switch (c->tune[0]) {
