@@ -119,6 +119,27 @@ class RHSoperator {
     check(tpsb_get_hmin(ctx_, &h), "getMinElementSize");
     return h;
   }
+  // ForcingTerms registered by RHSoperator's constructor (src/rhs_operator.cpp:101-167): pressure gradient, sponge zones, heat
+  // sources, Joule heating -- in the order of the calls
+  void addForcing(const tpsb_forcing_desc &d) const { check(tpsb_add_forcing(ctx_, &d), "addForcing"); }
+  void clearForcings() const { check(tpsb_clear_forcings(ctx_), "clearForcings"); }
+  // BoundaryCondition::dt (a reference to M2ulPhyS::dt): the step the non-reflecting inlets / outlets advance their boundary
+  // states with at every Mult (src/inletBC.cpp:703, src/outletBC.cpp:707)
+  void setTimeStep(double dt) const { check(tpsb_set_time_step(ctx_, dt), "setTimeStep"); }
+  // InletBC / OutletBC members meanUp and boundaryU of the non-reflecting condition on a boundary attribute
+  int getBoundaryState(int attr, double *mean_up, double *boundary_u, int capacity) const {
+    int n = 0;
+    check(tpsb_get_bc_state(ctx_, attr, mean_up, boundary_u, capacity, &n), "getBoundaryState");
+    return n;
+  }
+  // Averaging::addSample (src/averaging.cpp:198-420) on device vectors; the caller keeps ns_mean / ns_vari
+  void addSample(const Vector &inst, int num_fields, Vector &mean, Vector *vari, int vari_start, int vari_components, int ns_mean,
+                 int ns_vari, int pressure_slot) const {
+    check(tpsb_averaging_add_sample(ctx_, inst.Read(), num_fields, mean.ReadWrite(), vari ? vari->ReadWrite() : nullptr, vari_start,
+                                    vari_components, ns_mean, ns_vari, pressure_slot),
+          "addSample");
+  }
+  int path() const { return tpsb_get_path(ctx_); }  // 0 general 3-D, 1 fast, 2 fused, 3 generic (include/tpsb200.h)
   tpsb_ctx *context() const { return ctx_; }
 };
 
